@@ -1,0 +1,165 @@
+/*
+ * srcgan_b200 - C ABI of the B200-native (sm_100a) kernels behind the SRCGAN G+D training
+ * hot path.  Plain pointers and sizes only: every buffer is DEVICE memory owned by the
+ * caller (PyTorch on the Python side), every call is asynchronous on `stream`
+ * (a cudaStream_t passed as void*), every call returns 0 on success or a non-zero
+ * SRCGAN_E_* code, with a thread-local message available from srcgan_last_error().
+ * The library never allocates user-visible memory and has no CPU fallback.
+ *
+ * What each entry point replaces in the reference (paths relative to /root/reference):
+ *   srcgan_conv_fprop / _dgrad / _wgrad   nn.Conv2d forward / autograd backward used by
+ *        ResidualDenseBlock_5 (src/model/model.py:193-211), RRDB (:214-233), RDDBNet /
+ *        RDDBNetB trunk, upconv, HRconv, conv_first/last (:347-440), Decoder (:236-289) and
+ *        NLayerDiscriminator's 4x4 convs (:612-635); torch.cat of the dense block
+ *        (:207-210), the in-place LeakyReLU (:202,:410), the x0.2 residuals (:211,:233) and
+ *        F.interpolate(nearest, x2) (:426-427) are folded into the operand addressing and
+ *        the epilogue.
+ *   srcgan_bn_*                           nn.BatchNorm2d train/eval forward + backward
+ *        (model.py:240-260, :622, :630) fused with the following LeakyReLU.
+ *   srcgan_upsample2x_adjoint             backward of F.interpolate(nearest, x2) (:426-427).
+ *   srcgan_loss_fwd_bwd                   nn.L1Loss / nn.MSELoss forward+backward
+ *        (src/losses.py:95-133, src/train.py:87 via GANLoss).
+ *   srcgan_metrics_* / srcgan_ssim        src/metrics.py:10-144, src/losses.py:20-93,136-147.
+ *   srcgan_rgb2lab / srcgan_lab2rgb       skimage.color calls at src/dataset.py:148-159,
+ *        src/utils.py:22-26.
+ */
+#ifndef SRCGAN_B200_H
+#define SRCGAN_B200_H
+
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define SRCGAN_OK 0
+#define SRCGAN_E_INVALID 1      /* bad argument / unsupported shape (no fallback exists) */
+#define SRCGAN_E_CUDA 2         /* CUDA runtime / driver error */
+#define SRCGAN_E_WORKSPACE 3    /* workspace too small */
+
+#define SRCGAN_DT_F32 0
+#define SRCGAN_DT_BF16 1
+
+/* packed-weight layouts produced by srcgan_pack_weights from fp32 OIHW */
+#define SRCGAN_WL_RSCK 0        /* [kh][kw][cin][cout]  - fprop, SIMT engine             */
+#define SRCGAN_WL_RSKC 1        /* [kh][kw][cout][cin]  - dgrad, SIMT engine             */
+#define SRCGAN_WL_TC   2        /* tcgen05 engine: [cin/64][kw][kh][cout][64] bf16 K-major */
+
+#define SRCGAN_ENGINE_AUTO 0
+#define SRCGAN_ENGINE_SIMT 1    /* fp32-accumulating FFMA implicit GEMM (fp32 parity mode) */
+#define SRCGAN_ENGINE_TC   2    /* TMA + tcgen05/TMEM implicit GEMM (bf16)                 */
+
+/*
+ * One convolution over channel-sliced NHWC tensors.  A tensor is (ptr, ld): element
+ * (n,y,x,c) lives at ptr[((n*H + y)*W + x)*ld + c], so a slice of a wider concat buffer
+ * is expressed by offsetting ptr and keeping ld = the buffer's channel count.
+ *
+ * The struct always describes the FORWARD geometry:  X[n,h,w,cin] (*) W -> Y[n,ho,wo,cout],
+ * ho = (h*(upsample?2:1) + 2*pad - kh)/stride + 1.
+ *   fprop : reads x (=X) and wgt, writes y (=Y).
+ *   dgrad : reads x (=dY, ho x wo x cout), writes y (=dX, h x w x cin); upsample must be 0.
+ *   wgrad : reads x (=X) and y (=dY); writes alpha * (the fp32 OIHW gradient) passed separately.
+ * Epilogue applied to each written element v (fprop and dgrad):
+ *   v = acc + bias[c];  if (act) v = v > 0 ? v : act_slope*v;
+ *   v = alpha*v + beta1*r1 + beta2*r2;
+ *   if (mask) v *= (mask > 0 ? 1 : mask_slope);
+ */
+typedef struct srcgan_conv_params {
+  int32_t n, h, w;
+  int32_t cin, cout;
+  int32_t kh, kw, stride, pad;
+  int32_t upsample;
+  int32_t ho, wo;
+  int32_t dtype;      /* SRCGAN_DT_* of x, y, wgt, r1, r2, mask */
+  int32_t engine;     /* SRCGAN_ENGINE_* */
+  const void* x;
+  int32_t x_ld;
+  const void* wgt;
+  const float* bias;
+  void* y;
+  int32_t y_ld;
+  int32_t act;
+  float act_slope;
+  float alpha;
+  const void* r1;
+  int32_t r1_ld;
+  float beta1;
+  const void* r2;
+  int32_t r2_ld;
+  float beta2;
+  const void* mask;
+  int32_t mask_ld;
+  float mask_slope;
+} srcgan_conv_params;
+
+const char* srcgan_version(void);
+const char* srcgan_last_error(void);
+/* number of kernels this library has launched in the calling process (for bench.py's gpu_launches) */
+int64_t srcgan_launch_count(void);
+
+int srcgan_pack_weights(const float* w_oihw, int cout, int cin, int kh, int kw, int layout, int dtype,
+                        void* out, void* stream);
+size_t srcgan_packed_weight_bytes(int cout, int cin, int kh, int kw, int layout, int dtype);
+
+int srcgan_conv_fprop(const srcgan_conv_params* p, void* stream);
+int srcgan_conv_dgrad(const srcgan_conv_params* p, void* stream);
+size_t srcgan_conv_wgrad_workspace_bytes(const srcgan_conv_params* p);
+/* dw: fp32 [cout][cin][kh][kw]; db: fp32 [cout] or NULL; accumulate != 0 adds into dw/db */
+int srcgan_conv_wgrad(const srcgan_conv_params* p, float* dw, float* db, int accumulate,
+                      void* workspace, size_t workspace_bytes, void* stream);
+
+/* layout glue at the module boundary: NCHW fp32 <-> channel-sliced NHWC (f32 | bf16) */
+int srcgan_nchw_to_nhwc(const float* src, int n, int c, int h, int w, void* dst, int dst_ld, int dtype, void* stream);
+int srcgan_nhwc_to_nchw(const void* src, int src_ld, int dtype, float* dst, int n, int c, int h, int w, void* stream);
+
+/* dst = a + b over channel-sliced NHWC rows (gradient merge at the 'fea + trunk' skip, model.py:421) */
+int srcgan_add(const void* a, int a_ld, const void* b, int b_ld, void* dst, int dst_ld, int64_t npix, int c, int dtype,
+               void* stream);
+
+/* dst[n,h,w,c] = (sum of the 2x2 block of src[n,2h,2w,c]) * (mask>0 ? 1 : mask_slope); mask may be NULL */
+int srcgan_upsample2x_adjoint(const void* src, int src_ld, void* dst, int dst_ld, const void* mask, int mask_ld,
+                              float mask_slope, int n, int h, int w, int c, int dtype, void* stream);
+
+/* BatchNorm2d over NHWC rows (npix = n*h*w).  Training: batch statistics -> save_mean/save_invstd
+ * (fp32 [c]) and running-stat update (momentum, unbiased variance).  Eval: running stats.
+ * y = lrelu(gamma*(x-mean)*invstd + beta, slope).  workspace: >= srcgan_bn_workspace_bytes. */
+size_t srcgan_bn_workspace_bytes(int64_t npix, int c);
+int srcgan_bn_forward(const void* x, int x_ld, void* y, int y_ld, int64_t npix, int c, int dtype,
+                      const float* gamma, const float* beta, float* running_mean, float* running_var,
+                      float* save_mean, float* save_invstd, int training, float momentum, float eps,
+                      float slope, void* workspace, size_t workspace_bytes, void* stream);
+/* dy_post: gradient w.r.t. y (after LeakyReLU); y: saved forward output (sign = LeakyReLU mask);
+ * x: saved conv output.  Writes dx (may alias dy_post), dgamma/dbeta (+= if accumulate). */
+int srcgan_bn_backward(const void* dy_post, int dy_ld, const void* y, int y_ld, const void* x, int x_ld,
+                       void* dx, int dx_ld, int64_t npix, int c, int dtype, const float* gamma,
+                       const float* save_mean, const float* save_invstd, float slope, int training,
+                       float* dgamma, float* dbeta, int accumulate,
+                       void* workspace, size_t workspace_bytes, void* stream);
+
+/* kind 0 = L1 (mean |a-b|), 1 = MSE (mean (a-b)^2); b == NULL means the scalar `b_scalar`
+ * (GANLoss's expanded label).  loss_out: one fp32 (overwritten).  grad_out (optional, fp32[n]):
+ * d loss / d a.  Two-stage deterministic reduction; workspace >= srcgan_loss_workspace_bytes(n). */
+size_t srcgan_loss_workspace_bytes(int64_t n);
+int srcgan_loss_fwd_bwd(int kind, const float* a, const float* b, float b_scalar, int64_t n,
+                        float* loss_out, float* grad_out, void* workspace, size_t workspace_bytes, void* stream);
+
+/* metrics on NCHW fp32 (src/metrics.py): out[0]=sum (a-b)^2 (MSE*count); AE: out[b] = mean angular error (deg) */
+int srcgan_metrics_sqerr(const float* a, const float* b, int64_t n, float* out_sum, void* workspace,
+                         size_t workspace_bytes, void* stream);
+int srcgan_metrics_ae(const float* pred, const float* truth, int n, int c, int h, int w, float* out_per_image,
+                      void* stream);
+/* SSIM, 11x11 sigma=1.5 'valid' window, data range L; out_per_image[b] = sum of ssim_map over (c,h',w') */
+size_t srcgan_ssim_workspace_bytes(int n, int c, int h, int w);
+int srcgan_ssim(const float* pred, const float* truth, int n, int c, int h, int w, float L, float* out_per_image,
+                void* workspace, size_t workspace_bytes, void* stream);
+int srcgan_minmax(const float* a, int64_t n, float* out_min_max, void* stream);
+
+/* colour: NCHW fp32; rgb in [0,1]; lab normalised as dataset.py:154-157 (L/100,(a,b+128)/255) when normalised!=0 */
+int srcgan_rgb2lab(const float* rgb, float* lab, int n, int h, int w, int normalised, void* stream);
+int srcgan_lab2rgb(const float* lab, float* rgb, int n, int h, int w, int normalised, void* stream);
+
+#ifdef __cplusplus
+}
+#endif
+#endif

@@ -1,0 +1,207 @@
+// extern "C" surface of libsrcgan_b200.so (see include/srcgan_b200.h).  No exceptions cross this
+// boundary; errors are returned as codes with a thread-local message.
+#include <atomic>
+#include <stdarg.h>
+#include <string.h>
+
+#include "common.cuh"
+
+namespace srcgan {
+
+static thread_local char g_err[512] = "";
+static std::atomic<int64_t> g_launches{0};
+
+void set_error(const char* fmt, ...) {
+  va_list ap;
+  va_start(ap, fmt);
+  vsnprintf(g_err, sizeof(g_err), fmt, ap);
+  va_end(ap);
+}
+void count_launch(int n) { g_launches.fetch_add(n, std::memory_order_relaxed); }
+int check_launch(const char* what) {
+  cudaError_t e = cudaGetLastError();
+  if (e != cudaSuccess) {
+    set_error("%s: kernel launch failed: %s", what, cudaGetErrorString(e));
+    return SRCGAN_E_CUDA;
+  }
+  return SRCGAN_OK;
+}
+
+// engines (conv_simt.cu / conv_tc.cu)
+int validate_conv(const srcgan_conv_params* p, bool need_w);
+int conv_fprop_simt(const srcgan_conv_params* p, cudaStream_t st);
+int conv_dgrad_simt(const srcgan_conv_params* p, cudaStream_t st);
+size_t conv_wgrad_simt_workspace(const srcgan_conv_params* p);
+int conv_wgrad_simt(const srcgan_conv_params* p, float* dw, float* db, int accumulate, void* ws, size_t ws_bytes,
+                    cudaStream_t st);
+int pack_weights_simt_host(const float* w, int cout, int cin, int kh, int kw, int layout, int dtype, void* out,
+                           cudaStream_t st);
+bool conv_tc_supported(const srcgan_conv_params* p);
+int conv_fprop_tc(const srcgan_conv_params* p, cudaStream_t st);
+int pack_weights_tc_host(const float* w, int cout, int cin, int kh, int kw, void* out, cudaStream_t st);
+size_t packed_weight_bytes_tc(int cout, int cin, int kh, int kw);
+bool conv_wgrad_tc_supported(const srcgan_conv_params* p);
+size_t conv_wgrad_tc_workspace(const srcgan_conv_params* p);
+int conv_wgrad_tc(const srcgan_conv_params* p, float* dw, float* db, int accumulate, void* ws, size_t ws_bytes,
+                  cudaStream_t st);
+// other kernels
+int nchw_to_nhwc(const float* src, int n, int c, int h, int w, void* dst, int ld, int dtype, cudaStream_t st);
+int nhwc_to_nchw(const void* src, int ld, int dtype, float* dst, int n, int c, int h, int w, cudaStream_t st);
+int upsample2x_adjoint(const void* src, int src_ld, void* dst, int dst_ld, const void* mask, int mask_ld,
+                       float mslope, int n, int h, int w, int c, int dtype, cudaStream_t st);
+int add_slices(const void* a, int a_ld, const void* b, int b_ld, void* d, int d_ld, int64_t npix, int c, int dtype,
+               cudaStream_t st);
+size_t bn_workspace_bytes(int64_t npix, int c);
+int bn_forward(const void* x, int x_ld, void* y, int y_ld, int64_t npix, int c, int dtype, const float* gamma,
+               const float* beta, float* rm, float* rv, float* save_mean, float* save_invstd, int training,
+               float momentum, float eps, float slope, void* ws, size_t ws_bytes, cudaStream_t st);
+int bn_backward(const void* dy, int dy_ld, const void* y, int y_ld, const void* x, int x_ld, void* dx, int dx_ld,
+                int64_t npix, int c, int dtype, const float* gamma, const float* mean, const float* invstd,
+                float slope, int training, float* dgamma, float* dbeta, int accumulate, void* ws, size_t ws_bytes,
+                cudaStream_t st);
+size_t loss_workspace_bytes(int64_t n);
+int loss_fwd_bwd(int kind, const float* a, const float* b, float b_scalar, int64_t n, float* loss_out,
+                 float* grad_out, void* ws, size_t ws_bytes, int mean, cudaStream_t st);
+size_t ssim_workspace_bytes(int n, int c, int h, int w);
+int ssim(const float* p, const float* t, int n, int c, int h, int w, float L, float* out, void* ws, size_t ws_bytes,
+         cudaStream_t st);
+int metrics_ae(const float* p, const float* t, int n, int c, int h, int w, float* out, cudaStream_t st);
+int minmax(const float* a, int64_t n, float* out, cudaStream_t st);
+int rgb2lab(const float* rgb, float* lab, int n, int h, int w, int normalised, cudaStream_t st);
+int lab2rgb(const float* lab, float* rgb, int n, int h, int w, int normalised, cudaStream_t st);
+
+}  // namespace srcgan
+
+using namespace srcgan;
+
+extern "C" {
+
+const char* srcgan_version(void) { return "srcgan_b200 0.1 (sm_100a)"; }
+const char* srcgan_last_error(void) { return g_err; }
+int64_t srcgan_launch_count(void) { return g_launches.load(std::memory_order_relaxed); }
+
+size_t srcgan_packed_weight_bytes(int cout, int cin, int kh, int kw, int layout, int dtype) {
+  if (layout == SRCGAN_WL_TC) return packed_weight_bytes_tc(cout, cin, kh, kw);
+  return (size_t)cout * cin * kh * kw * (dtype == SRCGAN_DT_F32 ? 4 : 2);
+}
+
+int srcgan_pack_weights(const float* w, int cout, int cin, int kh, int kw, int layout, int dtype, void* out,
+                        void* stream) {
+  SRCGAN_REQUIRE(w && out && cout > 0 && cin > 0 && kh > 0 && kw > 0, "pack_weights: bad arguments");
+  if (layout == SRCGAN_WL_TC) {
+    SRCGAN_REQUIRE(dtype == SRCGAN_DT_BF16, "pack_weights: the tcgen05 layout is bf16 only");
+    return pack_weights_tc_host(w, cout, cin, kh, kw, out, (cudaStream_t)stream);
+  }
+  SRCGAN_REQUIRE(layout == SRCGAN_WL_RSCK || layout == SRCGAN_WL_RSKC, "pack_weights: unknown layout %d", layout);
+  return pack_weights_simt_host(w, cout, cin, kh, kw, layout, dtype, out, (cudaStream_t)stream);
+}
+
+int srcgan_conv_fprop(const srcgan_conv_params* p, void* stream) {
+  int rc = validate_conv(p, true);
+  if (rc) return rc;
+  int engine = p->engine;
+  if (engine == SRCGAN_ENGINE_AUTO) engine = conv_tc_supported(p) ? SRCGAN_ENGINE_TC : SRCGAN_ENGINE_SIMT;
+  if (engine == SRCGAN_ENGINE_TC) {
+    SRCGAN_REQUIRE(conv_tc_supported(p), "conv_fprop: shape not supported by the tcgen05 engine");
+    return conv_fprop_tc(p, (cudaStream_t)stream);
+  }
+  return conv_fprop_simt(p, (cudaStream_t)stream);
+}
+
+int srcgan_conv_dgrad(const srcgan_conv_params* p, void* stream) {
+  int rc = validate_conv(p, true);
+  if (rc) return rc;
+  SRCGAN_REQUIRE(p->engine != SRCGAN_ENGINE_TC,
+                 "conv_dgrad: the tcgen05 engine takes dgrad as an fprop over transposed weights");
+  return conv_dgrad_simt(p, (cudaStream_t)stream);
+}
+
+size_t srcgan_conv_wgrad_workspace_bytes(const srcgan_conv_params* p) {
+  if (!p) return 0;
+  size_t a = conv_wgrad_simt_workspace(p);
+  size_t b = conv_wgrad_tc_supported(p) ? conv_wgrad_tc_workspace(p) : 0;
+  return a > b ? a : b;
+}
+
+int srcgan_conv_wgrad(const srcgan_conv_params* p, float* dw, float* db, int accumulate, void* workspace,
+                      size_t workspace_bytes, void* stream) {
+  int rc = validate_conv(p, false);
+  if (rc) return rc;
+  SRCGAN_REQUIRE(dw || db, "conv_wgrad: nothing to compute");
+  int engine = p->engine;
+  if (engine == SRCGAN_ENGINE_AUTO) engine = conv_wgrad_tc_supported(p) ? SRCGAN_ENGINE_TC : SRCGAN_ENGINE_SIMT;
+  if (engine == SRCGAN_ENGINE_TC) {
+    SRCGAN_REQUIRE(conv_wgrad_tc_supported(p), "conv_wgrad: shape not supported by the tcgen05 engine");
+    return conv_wgrad_tc(p, dw, db, accumulate, workspace, workspace_bytes, (cudaStream_t)stream);
+  }
+  return conv_wgrad_simt(p, dw, db, accumulate, workspace, workspace_bytes, (cudaStream_t)stream);
+}
+
+int srcgan_nchw_to_nhwc(const float* src, int n, int c, int h, int w, void* dst, int dst_ld, int dtype, void* stream) {
+  SRCGAN_REQUIRE(src && dst && n > 0 && c > 0 && h > 0 && w > 0 && dst_ld >= c, "nchw_to_nhwc: bad arguments");
+  return nchw_to_nhwc(src, n, c, h, w, dst, dst_ld, dtype, (cudaStream_t)stream);
+}
+int srcgan_nhwc_to_nchw(const void* src, int src_ld, int dtype, float* dst, int n, int c, int h, int w, void* stream) {
+  SRCGAN_REQUIRE(src && dst && n > 0 && c > 0 && h > 0 && w > 0 && src_ld >= c, "nhwc_to_nchw: bad arguments");
+  return nhwc_to_nchw(src, src_ld, dtype, dst, n, c, h, w, (cudaStream_t)stream);
+}
+int srcgan_upsample2x_adjoint(const void* src, int src_ld, void* dst, int dst_ld, const void* mask, int mask_ld,
+                              float mask_slope, int n, int h, int w, int c, int dtype, void* stream) {
+  SRCGAN_REQUIRE(src && dst && n > 0 && c > 0 && h > 0 && w > 0, "upsample2x_adjoint: bad arguments");
+  return upsample2x_adjoint(src, src_ld, dst, dst_ld, mask, mask_ld, mask_slope, n, h, w, c, dtype,
+                            (cudaStream_t)stream);
+}
+
+int srcgan_add(const void* a, int a_ld, const void* b, int b_ld, void* dst, int dst_ld, int64_t npix, int c, int dtype,
+               void* stream) {
+  SRCGAN_REQUIRE(a && b && dst && npix > 0 && c > 0, "add: bad arguments");
+  return add_slices(a, a_ld, b, b_ld, dst, dst_ld, npix, c, dtype, (cudaStream_t)stream);
+}
+
+size_t srcgan_bn_workspace_bytes(int64_t npix, int c) { return bn_workspace_bytes(npix, c); }
+int srcgan_bn_forward(const void* x, int x_ld, void* y, int y_ld, int64_t npix, int c, int dtype, const float* gamma,
+                      const float* beta, float* running_mean, float* running_var, float* save_mean,
+                      float* save_invstd, int training, float momentum, float eps, float slope, void* workspace,
+                      size_t workspace_bytes, void* stream) {
+  return bn_forward(x, x_ld, y, y_ld, npix, c, dtype, gamma, beta, running_mean, running_var, save_mean, save_invstd,
+                    training, momentum, eps, slope, workspace, workspace_bytes, (cudaStream_t)stream);
+}
+int srcgan_bn_backward(const void* dy_post, int dy_ld, const void* y, int y_ld, const void* x, int x_ld, void* dx,
+                       int dx_ld, int64_t npix, int c, int dtype, const float* gamma, const float* save_mean,
+                       const float* save_invstd, float slope, int training, float* dgamma, float* dbeta,
+                       int accumulate, void* workspace, size_t workspace_bytes, void* stream) {
+  return bn_backward(dy_post, dy_ld, y, y_ld, x, x_ld, dx, dx_ld, npix, c, dtype, gamma, save_mean, save_invstd,
+                     slope, training, dgamma, dbeta, accumulate, workspace, workspace_bytes, (cudaStream_t)stream);
+}
+
+size_t srcgan_loss_workspace_bytes(int64_t n) { return loss_workspace_bytes(n); }
+int srcgan_loss_fwd_bwd(int kind, const float* a, const float* b, float b_scalar, int64_t n, float* loss_out,
+                        float* grad_out, void* workspace, size_t workspace_bytes, void* stream) {
+  return loss_fwd_bwd(kind, a, b, b_scalar, n, loss_out, grad_out, workspace, workspace_bytes, 1,
+                      (cudaStream_t)stream);
+}
+int srcgan_metrics_sqerr(const float* a, const float* b, int64_t n, float* out_sum, void* workspace,
+                         size_t workspace_bytes, void* stream) {
+  SRCGAN_REQUIRE(b != nullptr, "metrics_sqerr: null pointer");
+  return loss_fwd_bwd(1, a, b, 0.f, n, out_sum, nullptr, workspace, workspace_bytes, 0, (cudaStream_t)stream);
+}
+int srcgan_metrics_ae(const float* pred, const float* truth, int n, int c, int h, int w, float* out_per_image,
+                      void* stream) {
+  return metrics_ae(pred, truth, n, c, h, w, out_per_image, (cudaStream_t)stream);
+}
+size_t srcgan_ssim_workspace_bytes(int n, int c, int h, int w) { return ssim_workspace_bytes(n, c, h, w); }
+int srcgan_ssim(const float* pred, const float* truth, int n, int c, int h, int w, float L, float* out_per_image,
+                void* workspace, size_t workspace_bytes, void* stream) {
+  return ssim(pred, truth, n, c, h, w, L, out_per_image, workspace, workspace_bytes, (cudaStream_t)stream);
+}
+int srcgan_minmax(const float* a, int64_t n, float* out_min_max, void* stream) {
+  return minmax(a, n, out_min_max, (cudaStream_t)stream);
+}
+int srcgan_rgb2lab(const float* rgb, float* lab, int n, int h, int w, int normalised, void* stream) {
+  return rgb2lab(rgb, lab, n, h, w, normalised, (cudaStream_t)stream);
+}
+int srcgan_lab2rgb(const float* lab, float* rgb, int n, int h, int w, int normalised, void* stream) {
+  return lab2rgb(lab, rgb, n, h, w, normalised, (cudaStream_t)stream);
+}
+
+}  // extern "C"

@@ -1,0 +1,222 @@
+// BatchNorm2d (+ fused LeakyReLU) over channel-sliced NHWC rows, forward and backward.
+// Reference: nn.BatchNorm2d(train) + nn.LeakyReLU in Decoder (src/model/model.py:240-289, slope 0.1)
+// and NLayerDiscriminator (src/model/model.py:620-632, slope 0.2); eps 1e-5, momentum 0.1, running
+// variance updated with the unbiased estimate.  HBM-bound: one read pass for the statistics, one
+// read+write pass for the normalisation.
+#include "common.cuh"
+
+namespace srcgan {
+
+constexpr int kBnMaxParts = 1024;
+
+static int bn_parts(int64_t npix) {
+  int64_t p = (npix + 511) / 512;
+  if (p < 1) p = 1;
+  if (p > kBnMaxParts) p = kBnMaxParts;
+  return (int)p;
+}
+
+size_t bn_workspace_bytes(int64_t npix, int c) {
+  return ((size_t)2 * bn_parts(npix) * c + 2 * (size_t)c) * sizeof(float) + 256;
+}
+
+// block (32,8); grid (ceil(c/32), parts)
+template <typename T>
+__global__ void bn_stats_partial(const T* __restrict__ x, int ld, int64_t npix, int c, float* __restrict__ psum,
+                                 float* __restrict__ psq) {
+  __shared__ float r0[8][33], r1[8][33];
+  int ch = blockIdx.x * 32 + threadIdx.x;
+  float s = 0.f, q = 0.f;
+  if (ch < c)
+    for (int64_t m = (int64_t)blockIdx.y * 8 + threadIdx.y; m < npix; m += (int64_t)gridDim.y * 8) {
+      float v = to_f32(x[m * ld + ch]);
+      s += v; q = fmaf(v, v, q);
+    }
+  r0[threadIdx.y][threadIdx.x] = s; r1[threadIdx.y][threadIdx.x] = q;
+  __syncthreads();
+  if (threadIdx.y == 0 && ch < c) {
+    float a = 0.f, b = 0.f;
+#pragma unroll
+    for (int k = 0; k < 8; ++k) { a += r0[k][threadIdx.x]; b += r1[k][threadIdx.x]; }
+    psum[(int64_t)blockIdx.y * c + ch] = a;
+    psq[(int64_t)blockIdx.y * c + ch] = b;
+  }
+}
+
+__global__ void bn_finalize(const float* __restrict__ psum, const float* __restrict__ psq, int parts, int c,
+                            int64_t npix, float eps, float momentum, float* __restrict__ running_mean,
+                            float* __restrict__ running_var, float* __restrict__ save_mean,
+                            float* __restrict__ save_invstd) {
+  int ch = blockIdx.x * blockDim.x + threadIdx.x;
+  if (ch >= c) return;
+  double s = 0.0, q = 0.0;
+  for (int k = 0; k < parts; ++k) { s += (double)psum[(int64_t)k * c + ch]; q += (double)psq[(int64_t)k * c + ch]; }
+  double mean = s / (double)npix;
+  double var = q / (double)npix - mean * mean;
+  if (var < 0.0) var = 0.0;
+  save_mean[ch] = (float)mean;
+  save_invstd[ch] = (float)(1.0 / sqrt(var + (double)eps));
+  if (running_mean) running_mean[ch] = (1.f - momentum) * running_mean[ch] + momentum * (float)mean;
+  if (running_var) {
+    double unb = npix > 1 ? var * (double)npix / (double)(npix - 1) : var;
+    running_var[ch] = (1.f - momentum) * running_var[ch] + momentum * (float)unb;
+  }
+}
+
+__global__ void bn_eval_stats(const float* __restrict__ running_mean, const float* __restrict__ running_var, int c,
+                              float eps, float* __restrict__ save_mean, float* __restrict__ save_invstd) {
+  int ch = blockIdx.x * blockDim.x + threadIdx.x;
+  if (ch >= c) return;
+  save_mean[ch] = running_mean[ch];
+  save_invstd[ch] = rsqrtf(running_var[ch] + eps);
+}
+
+template <typename T>
+__global__ void bn_apply(const T* __restrict__ x, int x_ld, T* __restrict__ y, int y_ld, int64_t npix, int c,
+                         const float* __restrict__ gamma, const float* __restrict__ beta,
+                         const float* __restrict__ mean, const float* __restrict__ invstd, float slope) {
+  int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= npix * c) return;
+  int ch = (int)(i % c);
+  int64_t m = i / c;
+  float sc = gamma[ch] * invstd[ch];
+  float v = fmaf(to_f32(x[m * x_ld + ch]) - mean[ch], sc, beta[ch]);
+  v = v > 0.f ? v : v * slope;
+  y[m * y_ld + ch] = from_f32<T>(v);
+}
+
+// partial sums of dz and dz*xhat, dz = dy_post * lrelu'(y)
+template <typename T>
+__global__ void bn_bwd_partial(const T* __restrict__ dy, int dy_ld, const T* __restrict__ y, int y_ld,
+                               const T* __restrict__ x, int x_ld, int64_t npix, int c,
+                               const float* __restrict__ mean, const float* __restrict__ invstd, float slope,
+                               float* __restrict__ p0, float* __restrict__ p1) {
+  __shared__ float r0[8][33], r1[8][33];
+  int ch = blockIdx.x * 32 + threadIdx.x;
+  float s = 0.f, q = 0.f;
+  if (ch < c) {
+    float mu = mean[ch], is = invstd[ch];
+    for (int64_t m = (int64_t)blockIdx.y * 8 + threadIdx.y; m < npix; m += (int64_t)gridDim.y * 8) {
+      float dz = to_f32(dy[m * dy_ld + ch]);
+      if (!(to_f32(y[m * y_ld + ch]) > 0.f)) dz *= slope;
+      float xh = (to_f32(x[m * x_ld + ch]) - mu) * is;
+      s += dz; q = fmaf(dz, xh, q);
+    }
+  }
+  r0[threadIdx.y][threadIdx.x] = s; r1[threadIdx.y][threadIdx.x] = q;
+  __syncthreads();
+  if (threadIdx.y == 0 && ch < c) {
+    float a = 0.f, b = 0.f;
+#pragma unroll
+    for (int k = 0; k < 8; ++k) { a += r0[k][threadIdx.x]; b += r1[k][threadIdx.x]; }
+    p0[(int64_t)blockIdx.y * c + ch] = a;
+    p1[(int64_t)blockIdx.y * c + ch] = b;
+  }
+}
+
+__global__ void bn_bwd_finalize(const float* __restrict__ p0, const float* __restrict__ p1, int parts, int c,
+                                float* __restrict__ tot, float* __restrict__ dgamma, float* __restrict__ dbeta,
+                                int accumulate) {
+  int ch = blockIdx.x * blockDim.x + threadIdx.x;
+  if (ch >= c) return;
+  double s = 0.0, q = 0.0;
+  for (int k = 0; k < parts; ++k) { s += (double)p0[(int64_t)k * c + ch]; q += (double)p1[(int64_t)k * c + ch]; }
+  tot[ch] = (float)s; tot[c + ch] = (float)q;
+  if (dbeta) dbeta[ch] = accumulate ? dbeta[ch] + (float)s : (float)s;
+  if (dgamma) dgamma[ch] = accumulate ? dgamma[ch] + (float)q : (float)q;
+}
+
+template <typename T>
+__global__ void bn_bwd_apply(const T* __restrict__ dy, int dy_ld, const T* __restrict__ y, int y_ld,
+                             const T* __restrict__ x, int x_ld, T* __restrict__ dx, int dx_ld, int64_t npix, int c,
+                             const float* __restrict__ gamma, const float* __restrict__ mean,
+                             const float* __restrict__ invstd, const float* __restrict__ tot, float slope,
+                             int training) {
+  int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= npix * c) return;
+  int ch = (int)(i % c);
+  int64_t m = i / c;
+  float dz = to_f32(dy[m * dy_ld + ch]);
+  if (!(to_f32(y[m * y_ld + ch]) > 0.f)) dz *= slope;
+  float is = invstd[ch];
+  float g = gamma[ch] * is;
+  float v;
+  if (training) {
+    float inv_n = 1.f / (float)npix;
+    float xh = (to_f32(x[m * x_ld + ch]) - mean[ch]) * is;
+    v = g * (dz - tot[ch] * inv_n - xh * tot[c + ch] * inv_n);
+  } else {
+    v = g * dz;
+  }
+  dx[m * dx_ld + ch] = from_f32<T>(v);
+}
+
+template <typename T>
+static int bn_forward_t(const T* x, int x_ld, T* y, int y_ld, int64_t npix, int c, const float* gamma,
+                        const float* beta, float* rm, float* rv, float* save_mean, float* save_invstd, int training,
+                        float momentum, float eps, float slope, float* ws, cudaStream_t st) {
+  if (training) {
+    int parts = bn_parts(npix);
+    float* psum = ws;
+    float* psq = ws + (size_t)parts * c;
+    dim3 grid(ceil_div(c, 32), parts), blk(32, 8);
+    bn_stats_partial<T><<<grid, blk, 0, st>>>(x, x_ld, npix, c, psum, psq);
+    bn_finalize<<<ceil_div(c, 128), 128, 0, st>>>(psum, psq, parts, c, npix, eps, momentum, rm, rv, save_mean,
+                                                  save_invstd);
+    count_launch(2);
+  } else {
+    bn_eval_stats<<<ceil_div(c, 128), 128, 0, st>>>(rm, rv, c, eps, save_mean, save_invstd);
+    count_launch();
+  }
+  bn_apply<T><<<ceil_div(npix * c, 256), 256, 0, st>>>(x, x_ld, y, y_ld, npix, c, gamma, beta, save_mean, save_invstd,
+                                                       slope);
+  count_launch();
+  return check_launch("bn_forward");
+}
+
+int bn_forward(const void* x, int x_ld, void* y, int y_ld, int64_t npix, int c, int dtype, const float* gamma,
+               const float* beta, float* rm, float* rv, float* save_mean, float* save_invstd, int training,
+               float momentum, float eps, float slope, void* ws, size_t ws_bytes, cudaStream_t st) {
+  SRCGAN_REQUIRE(x && y && gamma && beta && save_mean && save_invstd, "bn_forward: null pointer");
+  SRCGAN_REQUIRE(training || (rm && rv), "bn_forward: eval mode needs running stats");
+  SRCGAN_REQUIRE(ws && ws_bytes >= bn_workspace_bytes(npix, c), "bn_forward: workspace too small");
+  if (dtype == SRCGAN_DT_F32)
+    return bn_forward_t<float>((const float*)x, x_ld, (float*)y, y_ld, npix, c, gamma, beta, rm, rv, save_mean,
+                               save_invstd, training, momentum, eps, slope, (float*)ws, st);
+  return bn_forward_t<__nv_bfloat16>((const __nv_bfloat16*)x, x_ld, (__nv_bfloat16*)y, y_ld, npix, c, gamma, beta, rm,
+                                     rv, save_mean, save_invstd, training, momentum, eps, slope, (float*)ws, st);
+}
+
+template <typename T>
+static int bn_backward_t(const T* dy, int dy_ld, const T* y, int y_ld, const T* x, int x_ld, T* dx, int dx_ld,
+                         int64_t npix, int c, const float* gamma, const float* mean, const float* invstd, float slope,
+                         int training, float* dgamma, float* dbeta, int accumulate, float* ws, cudaStream_t st) {
+  int parts = bn_parts(npix);
+  float* p0 = ws;
+  float* p1 = ws + (size_t)parts * c;
+  float* tot = ws + (size_t)2 * parts * c;
+  dim3 grid(ceil_div(c, 32), parts), blk(32, 8);
+  bn_bwd_partial<T><<<grid, blk, 0, st>>>(dy, dy_ld, y, y_ld, x, x_ld, npix, c, mean, invstd, slope, p0, p1);
+  bn_bwd_finalize<<<ceil_div(c, 128), 128, 0, st>>>(p0, p1, parts, c, tot, dgamma, dbeta, accumulate);
+  bn_bwd_apply<T><<<ceil_div(npix * c, 256), 256, 0, st>>>(dy, dy_ld, y, y_ld, x, x_ld, dx, dx_ld, npix, c, gamma,
+                                                           mean, invstd, tot, slope, training);
+  count_launch(3);
+  return check_launch("bn_backward");
+}
+
+int bn_backward(const void* dy, int dy_ld, const void* y, int y_ld, const void* x, int x_ld, void* dx, int dx_ld,
+                int64_t npix, int c, int dtype, const float* gamma, const float* mean, const float* invstd,
+                float slope, int training, float* dgamma, float* dbeta, int accumulate, void* ws, size_t ws_bytes,
+                cudaStream_t st) {
+  SRCGAN_REQUIRE(dy && y && x && dx && gamma && mean && invstd, "bn_backward: null pointer");
+  SRCGAN_REQUIRE(ws && ws_bytes >= bn_workspace_bytes(npix, c), "bn_backward: workspace too small");
+  if (dtype == SRCGAN_DT_F32)
+    return bn_backward_t<float>((const float*)dy, dy_ld, (const float*)y, y_ld, (const float*)x, x_ld, (float*)dx,
+                                dx_ld, npix, c, gamma, mean, invstd, slope, training, dgamma, dbeta, accumulate,
+                                (float*)ws, st);
+  return bn_backward_t<__nv_bfloat16>((const __nv_bfloat16*)dy, dy_ld, (const __nv_bfloat16*)y, y_ld,
+                                      (const __nv_bfloat16*)x, x_ld, (__nv_bfloat16*)dx, dx_ld, npix, c, gamma, mean,
+                                      invstd, slope, training, dgamma, dbeta, accumulate, (float*)ws, st);
+}
+
+}  // namespace srcgan

@@ -1,0 +1,58 @@
+// Shared helpers for the srcgan_b200 kernels (sm_100a).
+#pragma once
+#include <cuda_bf16.h>
+#include <cuda_runtime.h>
+#include <stdint.h>
+#include <stdio.h>
+
+#include "../../include/srcgan_b200.h"
+
+namespace srcgan {
+
+void set_error(const char* fmt, ...);
+void count_launch(int n = 1);
+int check_launch(const char* what);
+
+#define SRCGAN_REQUIRE(cond, ...)              \
+  do {                                         \
+    if (!(cond)) {                             \
+      srcgan::set_error(__VA_ARGS__);          \
+      return SRCGAN_E_INVALID;                 \
+    }                                          \
+  } while (0)
+
+#define SRCGAN_CUDA(call)                                                                 \
+  do {                                                                                    \
+    cudaError_t _e = (call);                                                              \
+    if (_e != cudaSuccess) {                                                              \
+      srcgan::set_error("%s failed: %s (%s:%d)", #call, cudaGetErrorString(_e), __FILE__, \
+                        __LINE__);                                                        \
+      return SRCGAN_E_CUDA;                                                               \
+    }                                                                                     \
+  } while (0)
+
+__device__ __forceinline__ float to_f32(float v) { return v; }
+__device__ __forceinline__ float to_f32(__nv_bfloat16 v) { return __bfloat162float(v); }
+template <typename T>
+__device__ __forceinline__ T from_f32(float v);
+template <>
+__device__ __forceinline__ float from_f32<float>(float v) { return v; }
+template <>
+__device__ __forceinline__ __nv_bfloat16 from_f32<__nv_bfloat16>(float v) { return __float2bfloat16_rn(v); }
+
+__device__ __forceinline__ float warp_sum(float v) {
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
+  return v;
+}
+__device__ __forceinline__ double warp_sum(double v) {
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
+  return v;
+}
+
+constexpr int kNumSMs = 148;  // B200
+
+static inline int ceil_div(int64_t a, int64_t b) { return (int)((a + b - 1) / b); }
+
+}  // namespace srcgan

@@ -1,0 +1,162 @@
+// Bandwidth-bound glue kernels: layout conversion at the module boundary (NCHW fp32 <-> NHWC),
+// adjoint of nearest x2 upsampling (backward of F.interpolate at src/model/model.py:426-427).
+#include "common.cuh"
+
+namespace srcgan {
+
+// NCHW fp32 -> NHWC T.  One thread per (pixel, channel) with channel fastest in the write; the
+// read is strided by H*W per channel which is fine for the tiny C (1..3) this is used for, and a
+// 32x32 smem transpose is used for wide C.
+template <typename T>
+__global__ void nchw_to_nhwc_small(const float* __restrict__ src, int c, int64_t hw, int64_t npix,
+                                   T* __restrict__ dst, int ld) {
+  int64_t p = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (p >= npix) return;
+  int64_t n = p / hw, q = p - n * hw;
+  const float* s = src + n * c * hw + q;
+  T* d = dst + p * ld;
+  for (int k = 0; k < c; ++k) d[k] = from_f32<T>(__ldg(s + (int64_t)k * hw));
+}
+
+template <typename T>
+__global__ void nhwc_to_nchw_small(const T* __restrict__ src, int ld, int c, int64_t hw, int64_t npix,
+                                   float* __restrict__ dst) {
+  int64_t p = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (p >= npix) return;
+  int64_t n = p / hw, q = p - n * hw;
+  const T* s = src + p * ld;
+  float* d = dst + n * c * hw + q;
+  for (int k = 0; k < c; ++k) d[(int64_t)k * hw] = to_f32(s[k]);
+}
+
+// wide-C variants: tile of 32 pixels x 32 channels through shared memory, both sides coalesced
+template <typename T>
+__global__ void nchw_to_nhwc_tiled(const float* __restrict__ src, int c, int64_t hw, T* __restrict__ dst, int ld) {
+  __shared__ float tile[32][33];
+  const int64_t n = blockIdx.z;
+  const int64_t q0 = (int64_t)blockIdx.x * 32;
+  const int c0 = blockIdx.y * 32;
+  for (int j = threadIdx.y; j < 32; j += blockDim.y) {
+    int ch = c0 + j;
+    int64_t q = q0 + threadIdx.x;
+    tile[j][threadIdx.x] = (ch < c && q < hw) ? __ldg(src + (n * c + ch) * hw + q) : 0.f;
+  }
+  __syncthreads();
+  for (int j = threadIdx.y; j < 32; j += blockDim.y) {
+    int64_t q = q0 + j;
+    int ch = c0 + threadIdx.x;
+    if (q < hw && ch < c) dst[(n * hw + q) * ld + ch] = from_f32<T>(tile[threadIdx.x][j]);
+  }
+}
+template <typename T>
+__global__ void nhwc_to_nchw_tiled(const T* __restrict__ src, int ld, int c, int64_t hw, float* __restrict__ dst) {
+  __shared__ float tile[32][33];
+  const int64_t n = blockIdx.z;
+  const int64_t q0 = (int64_t)blockIdx.x * 32;
+  const int c0 = blockIdx.y * 32;
+  for (int j = threadIdx.y; j < 32; j += blockDim.y) {
+    int64_t q = q0 + j;
+    int ch = c0 + threadIdx.x;
+    tile[j][threadIdx.x] = (q < hw && ch < c) ? to_f32(src[(n * hw + q) * ld + ch]) : 0.f;
+  }
+  __syncthreads();
+  for (int j = threadIdx.y; j < 32; j += blockDim.y) {
+    int ch = c0 + j;
+    int64_t q = q0 + threadIdx.x;
+    if (ch < c && q < hw) dst[(n * c + ch) * hw + q] = tile[threadIdx.x][j];
+  }
+}
+
+template <typename T>
+__global__ void upsample2x_adjoint_k(const T* __restrict__ src, int src_ld, T* __restrict__ dst, int dst_ld,
+                                     const T* __restrict__ mask, int mask_ld, float mslope, int n, int h, int w,
+                                     int c) {
+  int64_t total = (int64_t)n * h * w * c;
+  int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= total) return;
+  int ch = (int)(i % c);
+  int64_t p = i / c;
+  int x = (int)(p % w);
+  int64_t t = p / w;
+  int y = (int)(t % h);
+  int64_t b = t / h;
+  const int W2 = 2 * w;
+  int64_t s00 = ((b * 2 * h + 2 * y) * W2 + 2 * x) * src_ld + ch;
+  float v = to_f32(src[s00]) + to_f32(src[s00 + src_ld]) + to_f32(src[s00 + (int64_t)W2 * src_ld]) +
+            to_f32(src[s00 + (int64_t)(W2 + 1) * src_ld]);
+  if (mask) v *= (to_f32(mask[p * mask_ld + ch]) > 0.f ? 1.f : mslope);
+  dst[p * dst_ld + ch] = from_f32<T>(v);
+}
+
+template <typename T>
+__global__ void add_k(const T* __restrict__ a, int a_ld, const T* __restrict__ b, int b_ld, T* __restrict__ d, int d_ld,
+                      int64_t npix, int c) {
+  int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= npix * c) return;
+  int ch = (int)(i % c);
+  int64_t m = i / c;
+  d[m * d_ld + ch] = from_f32<T>(to_f32(a[m * a_ld + ch]) + to_f32(b[m * b_ld + ch]));
+}
+
+int add_slices(const void* a, int a_ld, const void* b, int b_ld, void* d, int d_ld, int64_t npix, int c, int dtype,
+               cudaStream_t st) {
+  if (dtype == SRCGAN_DT_F32)
+    add_k<float><<<ceil_div(npix * c, 256), 256, 0, st>>>((const float*)a, a_ld, (const float*)b, b_ld, (float*)d, d_ld,
+                                                          npix, c);
+  else
+    add_k<__nv_bfloat16><<<ceil_div(npix * c, 256), 256, 0, st>>>((const __nv_bfloat16*)a, a_ld,
+                                                                  (const __nv_bfloat16*)b, b_ld, (__nv_bfloat16*)d,
+                                                                  d_ld, npix, c);
+  count_launch();
+  return check_launch("add");
+}
+
+template <typename T>
+static int nchw_to_nhwc_t(const float* src, int n, int c, int h, int w, T* dst, int ld, cudaStream_t st) {
+  int64_t hw = (int64_t)h * w, npix = hw * n;
+  if (c <= 8) {
+    nchw_to_nhwc_small<T><<<ceil_div(npix, 256), 256, 0, st>>>(src, c, hw, npix, dst, ld);
+  } else {
+    dim3 grid(ceil_div(hw, 32), ceil_div(c, 32), n), blk(32, 8);
+    nchw_to_nhwc_tiled<T><<<grid, blk, 0, st>>>(src, c, hw, dst, ld);
+  }
+  count_launch();
+  return check_launch("nchw_to_nhwc");
+}
+template <typename T>
+static int nhwc_to_nchw_t(const T* src, int ld, float* dst, int n, int c, int h, int w, cudaStream_t st) {
+  int64_t hw = (int64_t)h * w, npix = hw * n;
+  if (c <= 8) {
+    nhwc_to_nchw_small<T><<<ceil_div(npix, 256), 256, 0, st>>>(src, ld, c, hw, npix, dst);
+  } else {
+    dim3 grid(ceil_div(hw, 32), ceil_div(c, 32), n), blk(32, 8);
+    nhwc_to_nchw_tiled<T><<<grid, blk, 0, st>>>(src, ld, c, hw, dst);
+  }
+  count_launch();
+  return check_launch("nhwc_to_nchw");
+}
+
+int nchw_to_nhwc(const float* src, int n, int c, int h, int w, void* dst, int ld, int dtype, cudaStream_t st) {
+  if (dtype == SRCGAN_DT_F32) return nchw_to_nhwc_t<float>(src, n, c, h, w, (float*)dst, ld, st);
+  return nchw_to_nhwc_t<__nv_bfloat16>(src, n, c, h, w, (__nv_bfloat16*)dst, ld, st);
+}
+int nhwc_to_nchw(const void* src, int ld, int dtype, float* dst, int n, int c, int h, int w, cudaStream_t st) {
+  if (dtype == SRCGAN_DT_F32) return nhwc_to_nchw_t<float>((const float*)src, ld, dst, n, c, h, w, st);
+  return nhwc_to_nchw_t<__nv_bfloat16>((const __nv_bfloat16*)src, ld, dst, n, c, h, w, st);
+}
+
+int upsample2x_adjoint(const void* src, int src_ld, void* dst, int dst_ld, const void* mask, int mask_ld,
+                       float mslope, int n, int h, int w, int c, int dtype, cudaStream_t st) {
+  int64_t total = (int64_t)n * h * w * c;
+  if (dtype == SRCGAN_DT_F32)
+    upsample2x_adjoint_k<float><<<ceil_div(total, 256), 256, 0, st>>>((const float*)src, src_ld, (float*)dst, dst_ld,
+                                                                     (const float*)mask, mask_ld, mslope, n, h, w, c);
+  else
+    upsample2x_adjoint_k<__nv_bfloat16><<<ceil_div(total, 256), 256, 0, st>>>(
+        (const __nv_bfloat16*)src, src_ld, (__nv_bfloat16*)dst, dst_ld, (const __nv_bfloat16*)mask, mask_ld, mslope,
+        n, h, w, c);
+  count_launch();
+  return check_launch("upsample2x_adjoint");
+}
+
+}  // namespace srcgan

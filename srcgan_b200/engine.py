@@ -1,0 +1,40 @@
+"""Engine selection: which kernel family runs a given convolution.
+
+SIMT  - FFMA implicit GEMM, fp32 accumulate; the fp32 parity mode and the thin / strided layers.
+TC    - TMA + tcgen05/TMEM implicit GEMM (bf16); 3x3 stride-1 pad-1 convs with wide channels.
+"""
+from __future__ import annotations
+
+import os
+
+import torch
+
+from ._lib import ENGINE_SIMT, ENGINE_TC, WL_RSCK, WL_TC
+
+_force_simt = os.environ.get("SRCGAN_B200_ENGINE", "auto").lower() == "simt"
+
+
+def force_simt(flag: bool) -> None:
+    global _force_simt
+    _force_simt = bool(flag)
+
+
+def tc_fprop_supported(cin: int, cout: int, k: int, stride: int, upsample: bool, dtype, h: int, w: int) -> bool:
+    return False
+
+
+def tc_wgrad_supported(cin: int, cout: int, k: int, stride: int, upsample: bool, dtype, h: int, w: int) -> bool:
+    return False
+
+
+def select(cin, cout, k, stride, upsample, dtype, h, w):
+    """-> (engine, fprop weight layout); (h, w) are the OUTPUT spatial dims."""
+    if not _force_simt and dtype == torch.bfloat16 and tc_fprop_supported(cin, cout, k, stride, upsample, dtype, h, w):
+        return ENGINE_TC, WL_TC
+    return ENGINE_SIMT, WL_RSCK
+
+
+def select_wgrad(cin, cout, k, stride, upsample, dtype, h, w):
+    if not _force_simt and dtype == torch.bfloat16 and tc_wgrad_supported(cin, cout, k, stride, upsample, dtype, h, w):
+        return ENGINE_TC
+    return ENGINE_SIMT

@@ -1,0 +1,596 @@
+"""B200-native networks of the SRCGAN hot path: the RRDB generators and the patch discriminator.
+
+Each network is ONE ``torch.autograd.Function`` whose forward and backward sequence the C-ABI
+kernels of libsrcgan_b200.so over channel-sliced NHWC buffers:
+
+* the dense block's ``torch.cat`` (reference src/model/model.py:205-211) is a 192-channel concat
+  buffer that every conv writes its slice of; LeakyReLU, bias, the x0.2 residuals of the RDB
+  (:211) and of the RRDB (:233) are conv epilogues;
+* the backward of a dense block is run as the *mirrored* dense block over a gradient concat
+  buffer [dOut | dZ4 | dZ3 | dZ2 | dZ1] with transposed/flipped weights, so dgrad needs no
+  read-modify-write accumulation and uses the same forward conv kernel;
+* parameters are ordinary fp32 ``nn.Parameter``s with the reference's names and shapes
+  (state_dict compatible); packed engine-layout copies are derived caches keyed on the
+  parameter version.
+
+Precision: ``SRCGAN_B200_PRECISION=fp32`` (exact-fp32 parity mode, SIMT engine) or ``bf16``
+(default: bf16 activations / weights, fp32 accumulation).
+"""
+from __future__ import annotations
+
+import os
+from typing import Dict, List, Optional, Tuple
+
+import torch
+import torch.nn as nn
+
+from . import ops
+from .ops import ENGINE_SIMT, Slice, WL_RSCK, WL_RSKC
+
+LRELU = 0.2
+
+_precision = os.environ.get("SRCGAN_B200_PRECISION", "bf16").lower()
+
+
+def set_precision(p: str) -> None:
+    global _precision
+    if p not in ("fp32", "bf16"):
+        raise ValueError("precision must be 'fp32' or 'bf16'")
+    _precision = p
+
+
+def precision() -> str:
+    return _precision
+
+
+def act_dtype() -> torch.dtype:
+    return torch.float32 if _precision == "fp32" else torch.bfloat16
+
+
+def select_engine(cin: int, cout: int, k: int, stride: int, upsample: bool, dtype: torch.dtype, h: int, w: int):
+    """(engine, fprop weight layout) for one convolution."""
+    from . import engine as _engine  # late import: keeps this module importable on CPU-only boxes
+    return _engine.select(cin, cout, k, stride, upsample, dtype, h, w)
+
+
+# ------------------------------------------------------------------------------------------
+# packed-weight cache
+# ------------------------------------------------------------------------------------------
+
+class _Packs:
+    def __init__(self):
+        self.d: Dict[tuple, tuple] = {}
+
+    def get(self, key, params, build, layout: int, dtype: torch.dtype) -> torch.Tensor:
+        stamp = tuple((p._version, p.data_ptr()) for p in params)
+        k = (key, layout, dtype)
+        hit = self.d.get(k)
+        if hit is not None and hit[0] == stamp:
+            return hit[1]
+        with torch.no_grad():
+            packed = ops.pack_weights(build(), layout, dtype)
+        self.d[k] = (stamp, packed)
+        return packed
+
+
+def _wT(w: torch.Tensor) -> torch.Tensor:
+    """OIHW weight of the stride-1 convolution that computes dgrad: swap in/out, rotate taps 180."""
+    return w.detach().transpose(0, 1).flip(2, 3)
+
+
+class _GradSink:
+    """Collects parameter gradients produced by wgrad kernels (handles shared weights)."""
+
+    def __init__(self):
+        self.g: Dict[int, torch.Tensor] = {}
+
+    def slot(self, p: Optional[torch.Tensor], wanted: bool):
+        """-> (tensor or None, accumulate)"""
+        if p is None or not wanted:
+            return None, False
+        t = self.g.get(id(p))
+        if t is None:
+            t = torch.empty_like(p, dtype=torch.float32, memory_format=torch.contiguous_format)
+            self.g[id(p)] = t
+            return t, False
+        return t, True
+
+    def get(self, p):
+        return self.g.get(id(p))
+
+
+class _NetBase(nn.Module):
+    """Shared plumbing: packed weights, conv helpers."""
+
+    def __init__(self):
+        super().__init__()
+        object.__setattr__(self, "_packs", _Packs())
+
+    # nn.Module.__setattr__ would try to register the cache; keep it a plain attribute
+    def _pk(self) -> _Packs:
+        return self.__dict__["_packs"]
+
+    def _w_f(self, conv: nn.Conv2d, dtype, layout=WL_RSCK):
+        return self._pk().get(("f", id(conv)), (conv.weight,), lambda: conv.weight.detach(), layout, dtype)
+
+    def _w_t(self, conv: nn.Conv2d, dtype, layout=WL_RSCK):
+        return self._pk().get(("t", id(conv)), (conv.weight,), lambda: _wT(conv.weight).contiguous(), layout, dtype)
+
+    def _w_d(self, conv: nn.Conv2d, dtype):
+        return self._pk().get(("d", id(conv)), (conv.weight,), lambda: conv.weight.detach(), WL_RSKC, dtype)
+
+    def _fprop(self, conv: nn.Conv2d, x: Slice, y: Slice, *, upsample=False, **ep) -> None:
+        k, s, p = conv.kernel_size[0], conv.stride[0], conv.padding[0]
+        eng, layout = select_engine(x.c, y.c, k, s, upsample, x.dtype, y.h, y.w)
+        ops.conv_fprop(x, self._w_f(conv, x.dtype, layout), conv.bias, y, k, s, p, upsample=upsample, engine=eng, **ep)
+
+    def _dgrad(self, conv: nn.Conv2d, dy: Slice, dx: Slice, **ep) -> None:
+        """dx = conv^T(dy) with epilogue.  Stride-1 wide convs run as an fprop over transposed weights
+        (the path the tensor-core engine shares); strided / thin ones use the gather-form kernel."""
+        k, s, p = conv.kernel_size[0], conv.stride[0], conv.padding[0]
+        if s == 1 and dy.c > 4 and dx.c > 4:
+            eng, layout = select_engine(dy.c, dx.c, k, 1, False, dy.dtype, dx.h, dx.w)
+            ops.conv_fprop(dy, self._w_t(conv, dy.dtype, layout), None, dx, k, 1, k - 1 - p, engine=eng, **ep)
+        else:
+            ops.conv_dgrad(dy, self._w_d(conv, dy.dtype), dx, k, s, p, **ep)
+
+    def _wgrad(self, conv: nn.Conv2d, x: Slice, dy: Slice, sink: _GradSink, want_w: bool, want_b: bool, *,
+               upsample=False, alpha=1.0) -> None:
+        dw, acc_w = sink.slot(conv.weight, want_w)
+        db, acc_b = sink.slot(conv.bias, want_b)
+        if dw is None and db is None:
+            return
+        k, s, p = conv.kernel_size[0], conv.stride[0], conv.padding[0]
+        if dw is not None and db is not None and acc_w != acc_b:   # cannot happen (same usage count)
+            raise RuntimeError("inconsistent accumulate state")
+        from . import engine as _engine
+        eng = _engine.select_wgrad(x.c, dy.c, k, s, upsample, x.dtype, dy.h, dy.w)
+        ops.conv_wgrad(x, dy, dw, db, k, s, p, upsample=upsample, accumulate=acc_w or acc_b, alpha=alpha, engine=eng)
+
+
+# ------------------------------------------------------------------------------------------
+# parameter containers with the reference's module tree (state_dict compatibility)
+# ------------------------------------------------------------------------------------------
+
+class ResidualDenseBlock_5(nn.Module):
+    """Parameter container of reference model.py:193-202 (conv1..conv5); compute lives in the generator Function."""
+
+    def __init__(self, nf=64, gc=32, bias=True):
+        super().__init__()
+        self.conv1 = nn.Conv2d(nf, gc, 3, 1, 1, bias=bias)
+        self.conv2 = nn.Conv2d(nf + gc, gc, 3, 1, 1, bias=bias)
+        self.conv3 = nn.Conv2d(nf + 2 * gc, gc, 3, 1, 1, bias=bias)
+        self.conv4 = nn.Conv2d(nf + 3 * gc, gc, 3, 1, 1, bias=bias)
+        self.conv5 = nn.Conv2d(nf + 4 * gc, nf, 3, 1, 1, bias=bias)
+
+    def convs(self):
+        return [self.conv1, self.conv2, self.conv3, self.conv4, self.conv5]
+
+
+class RRDB(nn.Module):
+    """Parameter container of reference model.py:214-219 (RDB1..3)."""
+
+    def __init__(self, nf, gc=32):
+        super().__init__()
+        self.RDB1 = ResidualDenseBlock_5(nf, gc)
+        self.RDB2 = ResidualDenseBlock_5(nf, gc)
+        self.RDB3 = ResidualDenseBlock_5(nf, gc)
+
+
+def _kaiming_fanout_(module: nn.Module) -> None:
+    """Same initialisation pass as the reference constructors (model.py:411-416)."""
+    for m in module.modules():
+        if isinstance(m, nn.Conv2d):
+            nn.init.kaiming_normal_(m.weight, mode="fan_out", nonlinearity="relu")
+        elif isinstance(m, nn.BatchNorm2d):
+            nn.init.constant_(m.weight, 1)
+            nn.init.constant_(m.bias, 0)
+
+
+class Decoder(nn.Module):
+    """Parameter container of reference model.py:236-261 (conv1..6 without bias, bn1..6)."""
+    PLAN = ((64, 64, 1), (64, 128, 1), (128, 128, 2), (128, 256, 2), (256, 128, 1), (128, 64, 1))
+    SLOPE = 0.1
+
+    def __init__(self):
+        super().__init__()
+        for i, (cin, cout, s) in enumerate(self.PLAN, start=1):
+            setattr(self, f"conv{i}", nn.Conv2d(cin, cout, 3, stride=s, padding=1, bias=False))
+            setattr(self, f"bn{i}", nn.BatchNorm2d(cout))
+
+    def layers(self):
+        return [(getattr(self, f"conv{i}"), getattr(self, f"bn{i}")) for i in range(1, 7)]
+
+
+# ------------------------------------------------------------------------------------------
+# RRDB trunk: forward / backward over concat buffers
+# ------------------------------------------------------------------------------------------
+
+class _RRDBGenerator(_NetBase):
+    nf: int
+    gc: int
+    nb: int
+
+    def _rdbs(self) -> List[ResidualDenseBlock_5]:
+        out = []
+        for rr in self.RRDB_trunk:
+            out += [rr.RDB1, rr.RDB2, rr.RDB3]
+        return out
+
+    def _dense_wT(self, rdb: ResidualDenseBlock_5, k: int, s5: float, dtype, layout):
+        """Packed weights of mirrored-dense-block step k (k=4..1: produces dZ_k; k=0: produces dX)."""
+        nf, gc = self.nf, self.gc
+        convs = rdb.convs()
+        sl = slice(0, nf) if k == 0 else slice(nf + gc * (k - 1), nf + gc * k)
+
+        def build():
+            blocks = [_wT(convs[4].weight[:, sl]) * s5]
+            for j in range(4, k, -1):                       # conv4 .. conv(k+1)
+                blocks.append(_wT(convs[j - 1].weight[:, sl]))
+            return torch.cat(blocks, dim=1).contiguous()
+
+        params = tuple(c.weight for c in convs[k:])
+        return self._pk().get(("dense", id(rdb), k, s5), params, build, layout, dtype)
+
+    def _trunk_forward(self, x_in: Slice, st: dict) -> Slice:
+        """conv_first -> nb x RRDB -> trunk_conv (+fea).  Returns fea2; saves buffers in ``st``."""
+        nf, gc = self.nf, self.gc
+        ctot = nf + 4 * gc
+        n, h, w, dev, dt = x_in.n, x_in.h, x_in.w, x_in.buf.device, x_in.dtype
+        rdbs = self._rdbs()
+        bufs = [ops.new_buf(n, h, w, ctot, dt, dev) for _ in rdbs]
+        trunk_out = ops.new_buf(n, h, w, nf, dt, dev)
+        fea2 = ops.new_buf(n, h, w, nf, dt, dev)
+        self._fprop(self.conv_first, x_in, Slice(bufs[0], 0, nf))
+        for j, rdb in enumerate(rdbs):
+            C = bufs[j]
+            convs = rdb.convs()
+            for k in range(1, 5):
+                self._fprop(convs[k - 1], Slice(C, 0, nf + gc * (k - 1)), Slice(C, nf + gc * (k - 1), gc), act=LRELU)
+            dest = Slice(bufs[j + 1], 0, nf) if j + 1 < len(rdbs) else Slice(trunk_out)
+            if j % 3 != 2:      # x5*0.2 + x                                    (model.py:211)
+                self._fprop(convs[4], Slice(C), dest, alpha=0.2, r1=Slice(C, 0, nf), beta1=1.0)
+            else:               # RDB3: (x5*0.2 + x)*0.2 + rrdb_in              (model.py:211,233)
+                self._fprop(convs[4], Slice(C), dest, alpha=0.04, r1=Slice(C, 0, nf), beta1=0.2,
+                            r2=Slice(bufs[j - 2], 0, nf), beta2=1.0)
+        self._fprop(self.trunk_conv, Slice(trunk_out), Slice(fea2), r1=Slice(bufs[0], 0, nf), beta1=1.0)
+        st["x_in"], st["bufs"], st["trunk_out"], st["fea2"] = x_in, bufs, trunk_out, fea2
+        return Slice(fea2)
+
+    def _trunk_backward(self, st: dict, g_fea2: Slice, sink: _GradSink, want: dict, need_dx: bool) -> Optional[Slice]:
+        """Backward of _trunk_forward.  ``want[param_id]`` says which params need grads."""
+        nf, gc = self.nf, self.gc
+        ctot = nf + 4 * gc
+        bufs, trunk_out, x_in = st["bufs"], st["trunk_out"], st["x_in"]
+        n, h, w, dev, dt = x_in.n, x_in.h, x_in.w, x_in.buf.device, x_in.dtype
+        rdbs = self._rdbs()
+        W = lambda p: p is not None and want.get(id(p), False)
+        Dbuf = [ops.new_buf(n, h, w, ctot, dt, dev) for _ in range(4)]
+        last = len(rdbs) - 1
+        # trunk_conv
+        self._wgrad(self.trunk_conv, Slice(trunk_out), g_fea2, sink, W(self.trunk_conv.weight), W(self.trunk_conv.bias))
+        self._dgrad(self.trunk_conv, g_fea2, Slice(Dbuf[last % 4], 0, nf))
+        dfea_trunk = ops.new_buf(n, h, w, nf, dt, dev)
+        for j in range(last, -1, -1):
+            rdb, C, D = rdbs[j], bufs[j], Dbuf[j % 4]
+            convs = rdb.convs()
+            is_rdb3, is_rdb1 = (j % 3 == 2), (j % 3 == 0)
+            s5 = 0.04 if is_rdb3 else 0.2
+            for k in (4, 3, 2, 1):
+                cin_v = nf + gc * (4 - k)
+                eng, layout = select_engine(cin_v, gc, 3, 1, False, dt, h, w)
+                ops.conv_fprop(Slice(D, 0, cin_v), self._dense_wT(rdb, k, s5, dt, layout), None,
+                               Slice(D, nf + gc * (4 - k), gc), 3, 1, 1,
+                               mask=Slice(C, nf + gc * (k - 1), gc), mask_slope=LRELU, engine=eng)
+            dest = Slice(Dbuf[(j - 1) % 4], 0, nf) if j > 0 else Slice(dfea_trunk)
+            eng, layout = select_engine(ctot, nf, 3, 1, False, dt, h, w)
+            ops.conv_fprop(Slice(D), self._dense_wT(rdb, 0, s5, dt, layout), None, dest, 3, 1, 1,
+                           r1=Slice(D, 0, nf), beta1=(0.2 if is_rdb3 else 1.0),
+                           r2=(Slice(Dbuf[(j + 2) % 4], 0, nf) if is_rdb1 else None), beta2=1.0, engine=eng)
+            for k in range(1, 5):
+                c = convs[k - 1]
+                self._wgrad(c, Slice(C, 0, nf + gc * (k - 1)), Slice(D, nf + gc * (4 - k), gc), sink, W(c.weight), W(c.bias))
+            self._wgrad(convs[4], Slice(C), Slice(D, 0, nf), sink, W(convs[4].weight), W(convs[4].bias), alpha=s5)
+        # fea feeds both the trunk and the skip (model.py:421)
+        d_fea = ops.new_buf(n, h, w, nf, dt, dev)
+        ops.add(Slice(dfea_trunk), g_fea2, Slice(d_fea))
+        self._wgrad(self.conv_first, x_in, Slice(d_fea), sink, W(self.conv_first.weight), W(self.conv_first.bias))
+        if not need_dx:
+            return None
+        dx = ops.new_buf(n, h, w, x_in.c, dt, dev)
+        self._dgrad(self.conv_first, Slice(d_fea), Slice(dx))
+        return Slice(dx)
+
+
+def _flat_params(module: nn.Module) -> List[nn.Parameter]:
+    return [p for p in module.parameters()]
+
+
+def _want_map(ctx_flags, params) -> dict:
+    return {id(p): bool(f) for p, f in zip(params, ctx_flags)}
+
+
+class _NetFn(torch.autograd.Function):
+    """forward(net, x, *params) -> NCHW fp32; the module implements _forward_impl/_backward_impl."""
+
+    @staticmethod
+    def forward(ctx, net, x, *params):
+        if not x.is_cuda:
+            raise RuntimeError("srcgan_b200: input must be a CUDA tensor - there is no CPU fallback")
+        st: dict = {}
+        out = net._forward_impl(x, st)
+        ctx.net, ctx.st, ctx.params = net, st, params
+        return out
+
+    @staticmethod
+    def backward(ctx, grad_out):
+        net, st, params = ctx.net, ctx.st, ctx.params
+        flags = ctx.needs_input_grad
+        want = _want_map(flags[2:], params)
+        sink = _GradSink()
+        dx = net._backward_impl(st, grad_out, sink, want, flags[1])
+        ctx.st = None
+        grads = [sink.get(p) if want[id(p)] else None for p in params]
+        return (None, dx) + tuple(grads)
+
+
+# ------------------------------------------------------------------------------------------
+# RDDBNetB : the SR generator G_A (reference model.py:396-440)
+# ------------------------------------------------------------------------------------------
+
+class RDDBNetB(_RRDBGenerator):
+    def __init__(self, in_nc, out_nc, nf, nb=3, gc=32, mode="x2"):
+        super().__init__()
+        self.nf, self.gc, self.nb, self.mode = nf, gc, nb, mode
+        self.conv_first = nn.Conv2d(in_nc, nf, 3, 1, 1, bias=True)
+        self.RRDB_trunk = nn.Sequential(*[RRDB(nf, gc) for _ in range(nb)])
+        self.trunk_conv = nn.Conv2d(nf, nf, 3, 1, 1, bias=True)
+        self.upconv1 = nn.Conv2d(nf, nf, 3, 1, 1, bias=True)
+        self.upconv2 = nn.Conv2d(nf, nf, 3, 1, 1, bias=True)
+        self.HRconv = nn.Conv2d(nf, nf, 3, 1, 1, bias=True)
+        self.conv_last = nn.Conv2d(nf, out_nc, 3, 1, 1, bias=True)
+        _kaiming_fanout_(self)
+
+    def _stages(self) -> List[Tuple[nn.Conv2d, bool]]:
+        st: List[Tuple[nn.Conv2d, bool]] = []
+        if self.mode == "x4":
+            st += [(self.upconv1, True), (self.upconv2, True)]
+        elif self.mode == "x2":
+            st += [(self.upconv1, True), (self.upconv1, False)]      # model.py:429-430
+        st += [(self.HRconv, False)] * 8                              # model.py:431-439
+        return st
+
+    def forward(self, x):
+        return _NetFn.apply(self, x, *_flat_params(self))
+
+    def _forward_impl(self, x: torch.Tensor, st: dict) -> torch.Tensor:
+        dt, dev = act_dtype(), x.device
+        n, c, h, w = x.shape
+        x_in = Slice(ops.new_buf(n, h, w, c, dt, dev))
+        ops.nchw_to_nhwc(x, x_in)
+        cur = self._trunk_forward(x_in, st)
+        acts = [cur]
+        for conv, up in self._stages():
+            hh, ww = (cur.h * 2, cur.w * 2) if up else (cur.h, cur.w)
+            nxt = Slice(ops.new_buf(n, hh, ww, self.nf, dt, dev))
+            self._fprop(conv, cur, nxt, upsample=up, act=LRELU)
+            acts.append(nxt)
+            cur = nxt
+        out = Slice(ops.new_buf(n, cur.h, cur.w, self.conv_last.out_channels, dt, dev))
+        self._fprop(self.conv_last, cur, out)
+        st["acts"] = acts
+        return ops.nhwc_to_nchw(out)
+
+    def _backward_impl(self, st, grad_out, sink, want, need_dx):
+        dt = act_dtype()
+        acts = st["acts"]
+        dev = grad_out.device
+        W = lambda p: p is not None and want.get(id(p), False)
+        n = acts[0].n
+        last = acts[-1]
+        d_o = Slice(ops.new_buf(n, last.h, last.w, self.conv_last.out_channels, dt, dev))
+        ops.nchw_to_nhwc(grad_out, d_o)
+        self._wgrad(self.conv_last, last, d_o, sink, W(self.conv_last.weight), W(self.conv_last.bias))
+        stages = self._stages()
+        gz = Slice(ops.new_buf(n, last.h, last.w, self.nf, dt, dev))
+        self._dgrad(self.conv_last, d_o, gz, mask=(last if stages else None), mask_slope=LRELU)
+        for i in range(len(stages) - 1, -1, -1):
+            conv, up = stages[i]
+            src = acts[i]
+            self._wgrad(conv, src, gz, sink, W(conv.weight), W(conv.bias), upsample=up)
+            mask = src if i > 0 else None                    # acts[0] = fea2 is not an activation output
+            if up:
+                full = Slice(ops.new_buf(n, gz.h, gz.w, self.nf, dt, dev))
+                self._dgrad(conv, gz, full)
+                nxt = Slice(ops.new_buf(n, src.h, src.w, self.nf, dt, dev))
+                ops.upsample2x_adjoint(full, nxt, mask, LRELU)
+            else:
+                nxt = Slice(ops.new_buf(n, src.h, src.w, self.nf, dt, dev))
+                self._dgrad(conv, gz, nxt, mask=mask, mask_slope=LRELU)
+            gz = nxt
+            if "_debug" in st:
+                st["_debug"]["gz%d" % i] = gz.view().float().permute(0, 3, 1, 2).clone()
+        dx = self._trunk_backward(st, gz, sink, want, need_dx)
+        return ops.nhwc_to_nchw(dx) if dx is not None else None
+
+
+# ------------------------------------------------------------------------------------------
+# RDDBNetA : G_B.  The reference never defines this class; this is the
+# documented shim: RDDBNet's constructor (model.py:347-368) + Decoder (model.py:236-289), forward
+# = the commented-out one at model.py:370-378.  x4 only.
+# ------------------------------------------------------------------------------------------
+
+class RDDBNetA(_RRDBGenerator):
+    def __init__(self, in_nc, out_nc, nf, nb, gc=32, mode="x2"):
+        super().__init__()
+        self.nf, self.gc, self.nb, self.mode = nf, gc, nb, mode
+        self.conv_first = nn.Conv2d(in_nc, nf, 3, 1, 1, bias=True)
+        self.RRDB_trunk = nn.Sequential(*[RRDB(nf, gc) for _ in range(nb)])
+        self.trunk_conv = nn.Conv2d(nf, nf, 3, 1, 1, bias=True)
+        self.upconv = nn.Conv2d(nf, nf, 3, 1, 1, bias=True)      # ctor-compatible, unused by the shim
+        self.HRconv = nn.Conv2d(nf, nf, 3, 1, 1, bias=True)      # ctor-compatible, unused by the shim
+        self.conv_last = nn.Conv2d(nf, out_nc, 3, 1, 1, bias=True)
+        _kaiming_fanout_(self)
+        self.decode = Decoder()                                   # attached after the init pass, like the shim
+        if nf != 64:
+            raise ValueError("RDDBNetA shim: Decoder is hard-wired to nf=64 (reference model.py:239)")
+
+    def forward(self, x):
+        used = [p for name, p in self.named_parameters() if not name.startswith(("upconv.", "HRconv."))]
+        return _NetFn.apply(self, x, *used)
+
+    def _forward_impl(self, x, st):
+        dt, dev = act_dtype(), x.device
+        n, c, h, w = x.shape
+        x_in = Slice(ops.new_buf(n, h, w, c, dt, dev))
+        ops.nchw_to_nhwc(x, x_in)
+        cur = self._trunk_forward(x_in, st)
+        training = self.training
+        ys, zs, stats = [], [cur], []
+        for conv, bn in self.decode.layers():
+            s = conv.stride[0]
+            ho, wo = (cur.h + 2 - 3) // s + 1, (cur.w + 2 - 3) // s + 1
+            y = Slice(ops.new_buf(n, ho, wo, conv.out_channels, dt, dev))
+            self._fprop(conv, cur, y)
+            z = Slice(ops.new_buf(n, ho, wo, conv.out_channels, dt, dev))
+            use_batch = training or bn.running_mean is None
+            sm, si = ops.bn_forward(y, z, bn.weight, bn.bias, bn.running_mean, bn.running_var, use_batch,
+                                    Decoder.SLOPE, bn.momentum if bn.momentum is not None else 0.1, bn.eps)
+            if training and bn.num_batches_tracked is not None:
+                bn.num_batches_tracked += 1
+            ys.append(y); zs.append(z); stats.append((sm, si, use_batch))
+            cur = z
+        out = Slice(ops.new_buf(n, cur.h, cur.w, self.conv_last.out_channels, dt, dev))
+        self._fprop(self.conv_last, cur, out)
+        st["ys"], st["zs"], st["stats"] = ys, zs, stats
+        return ops.nhwc_to_nchw(out)
+
+    def _backward_impl(self, st, grad_out, sink, want, need_dx):
+        dt, dev = act_dtype(), grad_out.device
+        ys, zs, stats = st["ys"], st["zs"], st["stats"]
+        W = lambda p: p is not None and want.get(id(p), False)
+        n = zs[0].n
+        last = zs[-1]
+        d_o = Slice(ops.new_buf(n, last.h, last.w, self.conv_last.out_channels, dt, dev))
+        ops.nchw_to_nhwc(grad_out, d_o)
+        self._wgrad(self.conv_last, last, d_o, sink, W(self.conv_last.weight), W(self.conv_last.bias))
+        g = Slice(ops.new_buf(n, last.h, last.w, last.c, dt, dev))
+        self._dgrad(self.conv_last, d_o, g)
+        layers = self.decode.layers()
+        for i in range(len(layers) - 1, -1, -1):
+            conv, bn = layers[i]
+            y, z, (sm, si, use_batch) = ys[i], zs[i + 1], stats[i]
+            dg, acc_g = sink.slot(bn.weight, W(bn.weight))
+            db, acc_b = sink.slot(bn.bias, W(bn.bias))
+            ops.bn_backward(g, z, y, g, bn.weight, sm, si, Decoder.SLOPE, use_batch, dg, db, acc_g or acc_b)
+            src = zs[i]
+            self._wgrad(conv, src, g, sink, W(conv.weight), False)
+            nxt = Slice(ops.new_buf(n, src.h, src.w, src.c, dt, dev))
+            self._dgrad(conv, g, nxt)
+            g = nxt
+        dx = self._trunk_backward(st, g, sink, want, need_dx)
+        return ops.nhwc_to_nchw(dx) if dx is not None else None
+
+
+# ------------------------------------------------------------------------------------------
+# NLayerDiscriminator (reference model.py:595-639), BatchNorm2d norm layer
+# ------------------------------------------------------------------------------------------
+
+class NLayerDiscriminator(_NetBase):
+    def __init__(self, input_nc, ndf=64, n_layers=3, norm_layer=nn.BatchNorm2d):
+        super().__init__()
+        if norm_layer is not nn.BatchNorm2d:
+            raise NotImplementedError("srcgan_b200.NLayerDiscriminator: only nn.BatchNorm2d is implemented "
+                                      "(the only norm layer the reference's trainers use, train.py:169-180)")
+        seq: List[nn.Module] = [nn.Conv2d(input_nc, ndf, 4, 2, 1), nn.LeakyReLU(0.2, True)]
+        mult = 1
+        for i in range(1, n_layers):
+            prev, mult = mult, min(2 ** i, 8)
+            seq += [nn.Conv2d(ndf * prev, ndf * mult, 4, 2, 1, bias=False), nn.BatchNorm2d(ndf * mult),
+                    nn.LeakyReLU(0.2, True)]
+        prev, mult = mult, min(2 ** n_layers, 8)
+        seq += [nn.Conv2d(ndf * prev, ndf * mult, 4, 1, 1, bias=False), nn.BatchNorm2d(ndf * mult),
+                nn.LeakyReLU(0.2, True)]
+        seq += [nn.Conv2d(ndf * mult, 1, 4, 1, 1)]
+        self.model = nn.Sequential(*seq)     # same indices => same state_dict keys as the reference
+
+    def _plan(self):
+        """[(conv, bn or None, has_act)] in execution order."""
+        mods = list(self.model)
+        plan, i = [], 0
+        while i < len(mods):
+            conv = mods[i]; i += 1
+            bn = None
+            if i < len(mods) and isinstance(mods[i], nn.BatchNorm2d):
+                bn = mods[i]; i += 1
+            act = False
+            if i < len(mods) and isinstance(mods[i], nn.LeakyReLU):
+                act = True; i += 1
+            plan.append((conv, bn, act))
+        return plan
+
+    def forward(self, input):
+        return _NetFn.apply(self, input, *_flat_params(self))
+
+    def _forward_impl(self, x, st):
+        dt, dev = act_dtype(), x.device
+        n, c, h, w = x.shape
+        cur = Slice(ops.new_buf(n, h, w, c, dt, dev))
+        ops.nchw_to_nhwc(x, cur)
+        ins, ys, outs, stats = [], [], [], []
+        training = self.training
+        for conv, bn, act in self._plan():
+            k, s, p = conv.kernel_size[0], conv.stride[0], conv.padding[0]
+            ho, wo = (cur.h + 2 * p - k) // s + 1, (cur.w + 2 * p - k) // s + 1
+            if ho < 1 or wo < 1:
+                raise RuntimeError("NLayerDiscriminator: input %dx%d too small" % (h, w))
+            ins.append(cur)
+            y = Slice(ops.new_buf(n, ho, wo, conv.out_channels, dt, dev))
+            if bn is None:
+                self._fprop(conv, cur, y, act=(LRELU if act else None))
+                ys.append(None); stats.append(None)
+                cur = y
+            else:
+                self._fprop(conv, cur, y)
+                z = Slice(ops.new_buf(n, ho, wo, conv.out_channels, dt, dev))
+                use_batch = training or bn.running_mean is None
+                sm, si = ops.bn_forward(y, z, bn.weight, bn.bias, bn.running_mean, bn.running_var, use_batch,
+                                        LRELU if act else 1.0, bn.momentum if bn.momentum is not None else 0.1, bn.eps)
+                if training and bn.num_batches_tracked is not None:
+                    bn.num_batches_tracked += 1
+                ys.append(y); stats.append((sm, si, use_batch))
+                cur = z
+            outs.append(cur)
+        st["ins"], st["ys"], st["outs"], st["stats"] = ins, ys, outs, stats
+        return ops.nhwc_to_nchw(cur)
+
+    def _backward_impl(self, st, grad_out, sink, want, need_dx):
+        dt, dev = act_dtype(), grad_out.device
+        ins, ys, outs, stats = st["ins"], st["ys"], st["outs"], st["stats"]
+        W = lambda p: p is not None and want.get(id(p), False)
+        plan = self._plan()
+        n = ins[0].n
+        g = Slice(ops.new_buf(n, outs[-1].h, outs[-1].w, outs[-1].c, dt, dev))
+        ops.nchw_to_nhwc(grad_out, g)
+        # g is always the gradient w.r.t. the *conv output* of layer i when we reach its wgrad
+        for i in range(len(plan) - 1, -1, -1):
+            conv, bn, act = plan[i]
+            if bn is not None:
+                sm, si, use_batch = stats[i]
+                dg, acc_g = sink.slot(bn.weight, W(bn.weight))
+                db, acc_b = sink.slot(bn.bias, W(bn.bias))
+                ops.bn_backward(g, outs[i], ys[i], g, bn.weight, sm, si, LRELU if act else 1.0, use_batch, dg, db,
+                                acc_g or acc_b)
+            self._wgrad(conv, ins[i], g, sink, W(conv.weight), W(conv.bias))
+            if i == 0 and not need_dx:
+                return None
+            src = ins[i]
+            nxt = Slice(ops.new_buf(n, src.h, src.w, src.c, dt, dev))
+            # the previous layer's LeakyReLU (no BN) is folded into this dgrad's mask epilogue
+            prev_plain_act = i > 0 and plan[i - 1][1] is None and plan[i - 1][2]
+            if prev_plain_act:
+                self._dgrad(conv, g, nxt, mask=outs[i - 1], mask_slope=LRELU)
+            else:
+                self._dgrad(conv, g, nxt)
+            g = nxt
+        return ops.nhwc_to_nchw(g)

@@ -1,0 +1,335 @@
+"""Thin Python wrappers over the C ABI: torch tensors in, raw device pointers out.
+
+All tensors are torch-owned CUDA memory; calls are asynchronous on torch's current stream.
+Activations inside the networks are channel-sliced NHWC buffers (``Slice``)."""
+from __future__ import annotations
+
+import ctypes as C
+from typing import Optional
+
+import torch
+
+from . import _lib
+from ._lib import ConvParams, DT_BF16, DT_F32, ENGINE_AUTO, ENGINE_SIMT, ENGINE_TC, WL_RSCK, WL_RSKC, WL_TC  # noqa: F401
+
+
+def dt_code(dtype: torch.dtype) -> int:
+    if dtype == torch.float32:
+        return DT_F32
+    if dtype == torch.bfloat16:
+        return DT_BF16
+    raise TypeError("srcgan_b200: unsupported activation dtype %s" % dtype)
+
+
+def _stream() -> int:
+    return torch.cuda.current_stream().cuda_stream
+
+
+def _require_cuda(t: torch.Tensor, what: str) -> None:
+    if not t.is_cuda:
+        raise RuntimeError("srcgan_b200: %s must be a CUDA tensor - this library has no CPU path" % what)
+
+
+class Slice:
+    """Channels [c0, c0+c) of an NHWC buffer tensor of shape (N, H, W, Ctot)."""
+    __slots__ = ("buf", "c0", "c")
+
+    def __init__(self, buf: torch.Tensor, c0: int = 0, c: Optional[int] = None):
+        assert buf.dim() == 4 and buf.is_contiguous()
+        self.buf, self.c0 = buf, c0
+        self.c = buf.shape[3] - c0 if c is None else c
+        assert 0 <= c0 and c0 + self.c <= buf.shape[3]
+
+    @property
+    def ptr(self) -> int:
+        return self.buf.data_ptr() + self.c0 * self.buf.element_size()
+
+    @property
+    def ld(self) -> int:
+        return self.buf.shape[3]
+
+    @property
+    def n(self) -> int:
+        return self.buf.shape[0]
+
+    @property
+    def h(self) -> int:
+        return self.buf.shape[1]
+
+    @property
+    def w(self) -> int:
+        return self.buf.shape[2]
+
+    @property
+    def npix(self) -> int:
+        return self.buf.shape[0] * self.buf.shape[1] * self.buf.shape[2]
+
+    @property
+    def dtype(self) -> torch.dtype:
+        return self.buf.dtype
+
+    def view(self) -> torch.Tensor:
+        return self.buf[..., self.c0:self.c0 + self.c]
+
+
+def new_buf(n: int, h: int, w: int, c: int, dtype: torch.dtype, device) -> torch.Tensor:
+    return torch.empty((n, h, w, c), dtype=dtype, device=device)
+
+
+# ------------------------------------------------------------------------------------------
+# workspace (one growing byte buffer per device; safe because every use is stream-ordered)
+# ------------------------------------------------------------------------------------------
+_workspaces = {}
+
+
+def workspace(nbytes: int, device) -> torch.Tensor:
+    key = (torch.device(device).index, torch.cuda.current_stream().cuda_stream)
+    ws = _workspaces.get(key)
+    if ws is None or ws.numel() < nbytes:
+        ws = torch.empty(max(int(nbytes), 1 << 20), dtype=torch.uint8, device=device)
+        _workspaces[key] = ws
+    return ws
+
+
+# ------------------------------------------------------------------------------------------
+# weights
+# ------------------------------------------------------------------------------------------
+
+def pack_weights(w_oihw: torch.Tensor, layout: int, dtype: torch.dtype) -> torch.Tensor:
+    """fp32 OIHW -> packed engine layout (a flat tensor of ``dtype``)."""
+    _require_cuda(w_oihw, "weight")
+    w = w_oihw.detach()
+    if w.dtype != torch.float32 or not w.is_contiguous():
+        w = w.float().contiguous()
+    cout, cin, kh, kw = w.shape
+    lib = _lib.load()
+    nbytes = lib.srcgan_packed_weight_bytes(cout, cin, kh, kw, layout, dt_code(dtype))
+    out = torch.empty(nbytes // torch.empty((), dtype=dtype).element_size(), dtype=dtype, device=w.device)
+    _lib.check(lib.srcgan_pack_weights(w.data_ptr(), cout, cin, kh, kw, layout, dt_code(dtype), out.data_ptr(),
+                                       _stream()), "pack_weights")
+    return out
+
+
+# ------------------------------------------------------------------------------------------
+# convolution
+# ------------------------------------------------------------------------------------------
+
+def _conv_params(n, h, w, cin, cout, k, stride, pad, upsample, ho, wo, dtype, engine) -> ConvParams:
+    p = ConvParams()
+    p.n, p.h, p.w, p.cin, p.cout = n, h, w, cin, cout
+    p.kh = p.kw = k
+    p.stride, p.pad, p.upsample = stride, pad, int(bool(upsample))
+    p.ho, p.wo = ho, wo
+    p.dtype, p.engine = dt_code(dtype), engine
+    p.alpha = 1.0
+    return p
+
+
+def _epilogue(p: ConvParams, bias, act, alpha, r1, beta1, r2, beta2, mask, mask_slope) -> None:
+    p.bias = bias.data_ptr() if bias is not None else None
+    p.act = 0 if act is None else 1
+    p.act_slope = 0.0 if act is None else float(act)
+    p.alpha = float(alpha)
+    if r1 is not None:
+        p.r1, p.r1_ld, p.beta1 = r1.ptr, r1.ld, float(beta1)
+    if r2 is not None:
+        p.r2, p.r2_ld, p.beta2 = r2.ptr, r2.ld, float(beta2)
+    if mask is not None:
+        p.mask, p.mask_ld, p.mask_slope = mask.ptr, mask.ld, float(mask_slope)
+
+
+def conv_fprop(x: Slice, wgt: torch.Tensor, bias: Optional[torch.Tensor], y: Slice, k: int, stride: int = 1,
+               pad: int = 1, *, upsample: bool = False, act: Optional[float] = None, alpha: float = 1.0,
+               r1: Optional[Slice] = None, beta1: float = 0.0, r2: Optional[Slice] = None, beta2: float = 0.0,
+               mask: Optional[Slice] = None, mask_slope: float = 0.0, engine: int = ENGINE_SIMT) -> None:
+    """y = epilogue(conv(x, w)); see include/srcgan_b200.h for the epilogue definition."""
+    _require_cuda(x.buf, "conv input")
+    p = _conv_params(x.n, x.h, x.w, x.c, y.c, k, stride, pad, upsample, y.h, y.w, x.dtype, engine)
+    p.x, p.x_ld, p.wgt, p.y, p.y_ld = x.ptr, x.ld, wgt.data_ptr(), y.ptr, y.ld
+    _epilogue(p, bias, act, alpha, r1, beta1, r2, beta2, mask, mask_slope)
+    _lib.check(_lib.load().srcgan_conv_fprop(C.byref(p), _stream()), "conv_fprop")
+
+
+def conv_dgrad(dy: Slice, wgt_rskc: torch.Tensor, dx: Slice, k: int, stride: int, pad: int, *, alpha: float = 1.0,
+               r1: Optional[Slice] = None, beta1: float = 0.0, mask: Optional[Slice] = None,
+               mask_slope: float = 0.0) -> None:
+    """dx = epilogue(conv_transpose(dy, w)) - gather form, any stride (SIMT engine)."""
+    _require_cuda(dy.buf, "conv grad")
+    p = _conv_params(dx.n, dx.h, dx.w, dx.c, dy.c, k, stride, pad, False, dy.h, dy.w, dy.dtype, ENGINE_SIMT)
+    p.x, p.x_ld, p.wgt, p.y, p.y_ld = dy.ptr, dy.ld, wgt_rskc.data_ptr(), dx.ptr, dx.ld
+    _epilogue(p, None, None, alpha, r1, beta1, None, 0.0, mask, mask_slope)
+    _lib.check(_lib.load().srcgan_conv_dgrad(C.byref(p), _stream()), "conv_dgrad")
+
+
+def conv_wgrad(x: Slice, dy: Slice, dw: Optional[torch.Tensor], db: Optional[torch.Tensor], k: int, stride: int = 1,
+               pad: int = 1, *, upsample: bool = False, accumulate: bool = False, alpha: float = 1.0,
+               engine: int = ENGINE_SIMT) -> None:
+    """dw (fp32 OIHW) (+)= alpha * sum_pixels x (x) dy ; db (+)= alpha * sum_pixels dy."""
+    _require_cuda(x.buf, "conv input")
+    if dw is not None:
+        assert dw.dtype == torch.float32 and dw.is_contiguous() and tuple(dw.shape) == (dy.c, x.c, k, k), \
+            (tuple(dw.shape), (dy.c, x.c, k, k))
+    if db is not None:
+        assert db.dtype == torch.float32 and db.is_contiguous() and db.numel() == dy.c
+    p = _conv_params(x.n, x.h, x.w, x.c, dy.c, k, stride, pad, upsample, dy.h, dy.w, x.dtype, engine)
+    p.x, p.x_ld, p.y, p.y_ld = x.ptr, x.ld, dy.ptr, dy.ld
+    p.alpha = float(alpha)
+    lib = _lib.load()
+    nbytes = lib.srcgan_conv_wgrad_workspace_bytes(C.byref(p))
+    ws = workspace(nbytes, x.buf.device)
+    _lib.check(lib.srcgan_conv_wgrad(C.byref(p), dw.data_ptr() if dw is not None else None,
+                                     db.data_ptr() if db is not None else None, int(accumulate),
+                                     ws.data_ptr(), ws.numel(), _stream()), "conv_wgrad")
+
+
+# ------------------------------------------------------------------------------------------
+# glue
+# ------------------------------------------------------------------------------------------
+
+def nchw_to_nhwc(src: torch.Tensor, dst: Slice) -> None:
+    _require_cuda(src, "input")
+    s = src.detach()
+    if s.dtype != torch.float32 or not s.is_contiguous():
+        s = s.float().contiguous()
+    n, c, h, w = s.shape
+    assert (dst.n, dst.h, dst.w, dst.c) == (n, h, w, c)
+    _lib.check(_lib.load().srcgan_nchw_to_nhwc(s.data_ptr(), n, c, h, w, dst.ptr, dst.ld, dt_code(dst.dtype), _stream()),
+               "nchw_to_nhwc")
+
+
+def nhwc_to_nchw(src: Slice) -> torch.Tensor:
+    out = torch.empty((src.n, src.c, src.h, src.w), dtype=torch.float32, device=src.buf.device)
+    _lib.check(_lib.load().srcgan_nhwc_to_nchw(src.ptr, src.ld, dt_code(src.dtype), out.data_ptr(), src.n, src.c,
+                                               src.h, src.w, _stream()), "nhwc_to_nchw")
+    return out
+
+
+def add(a: Slice, b: Slice, dst: Slice) -> None:
+    _lib.check(_lib.load().srcgan_add(a.ptr, a.ld, b.ptr, b.ld, dst.ptr, dst.ld, dst.npix, dst.c, dt_code(dst.dtype),
+                                      _stream()), "add")
+
+
+def upsample2x_adjoint(src: Slice, dst: Slice, mask: Optional[Slice] = None, mask_slope: float = 0.0) -> None:
+    assert src.h == 2 * dst.h and src.w == 2 * dst.w and src.c == dst.c
+    _lib.check(_lib.load().srcgan_upsample2x_adjoint(
+        src.ptr, src.ld, dst.ptr, dst.ld, mask.ptr if mask is not None else None, mask.ld if mask is not None else 0,
+        float(mask_slope), dst.n, dst.h, dst.w, dst.c, dt_code(dst.dtype), _stream()), "upsample2x_adjoint")
+
+
+# ------------------------------------------------------------------------------------------
+# batch norm (+ LeakyReLU)
+# ------------------------------------------------------------------------------------------
+
+def bn_forward(x: Slice, y: Slice, gamma, beta, running_mean, running_var, training: bool, slope: float,
+               momentum: float = 0.1, eps: float = 1e-5):
+    c = x.c
+    save_mean = torch.empty(c, dtype=torch.float32, device=x.buf.device)
+    save_invstd = torch.empty(c, dtype=torch.float32, device=x.buf.device)
+    lib = _lib.load()
+    ws = workspace(lib.srcgan_bn_workspace_bytes(x.npix, c), x.buf.device)
+    _lib.check(lib.srcgan_bn_forward(
+        x.ptr, x.ld, y.ptr, y.ld, x.npix, c, dt_code(x.dtype), gamma.data_ptr(), beta.data_ptr(),
+        running_mean.data_ptr() if running_mean is not None else None,
+        running_var.data_ptr() if running_var is not None else None,
+        save_mean.data_ptr(), save_invstd.data_ptr(), int(training), float(momentum), float(eps), float(slope),
+        ws.data_ptr(), ws.numel(), _stream()), "bn_forward")
+    return save_mean, save_invstd
+
+
+def bn_backward(dy_post: Slice, y: Slice, x: Slice, dx: Slice, gamma, save_mean, save_invstd, slope: float,
+                training: bool, dgamma, dbeta, accumulate: bool = False) -> None:
+    lib = _lib.load()
+    c = x.c
+    ws = workspace(lib.srcgan_bn_workspace_bytes(x.npix, c), x.buf.device)
+    _lib.check(lib.srcgan_bn_backward(
+        dy_post.ptr, dy_post.ld, y.ptr, y.ld, x.ptr, x.ld, dx.ptr, dx.ld, x.npix, c, dt_code(x.dtype),
+        gamma.data_ptr(), save_mean.data_ptr(), save_invstd.data_ptr(), float(slope), int(training),
+        dgamma.data_ptr() if dgamma is not None else None, dbeta.data_ptr() if dbeta is not None else None,
+        int(accumulate), ws.data_ptr(), ws.numel(), _stream()), "bn_backward")
+
+
+# ------------------------------------------------------------------------------------------
+# losses / metrics / colour (NCHW fp32 tensors at the module boundary)
+# ------------------------------------------------------------------------------------------
+
+def _f32c(t: torch.Tensor, what: str) -> torch.Tensor:
+    _require_cuda(t, what)
+    t = t.detach()
+    if t.dtype != torch.float32 or not t.is_contiguous():
+        t = t.float().contiguous()
+    return t
+
+
+def loss_fwd_bwd(kind: int, a: torch.Tensor, b, want_grad: bool):
+    """Returns (loss 0-dim fp32 tensor, d loss / d a or None).  ``b``: tensor like ``a`` or a python float."""
+    a = _f32c(a, "loss input")
+    n = a.numel()
+    lib = _lib.load()
+    ws = workspace(lib.srcgan_loss_workspace_bytes(n), a.device)
+    out = torch.empty((), dtype=torch.float32, device=a.device)
+    grad = torch.empty_like(a) if want_grad else None
+    if isinstance(b, torch.Tensor):
+        b = _f32c(b, "loss target")
+        assert b.numel() == n, "loss: shape mismatch"
+        bp, bs = b.data_ptr(), 0.0
+    else:
+        bp, bs = None, float(b)
+    _lib.check(lib.srcgan_loss_fwd_bwd(kind, a.data_ptr(), bp, bs, n, out.data_ptr(),
+                                       grad.data_ptr() if grad is not None else None, ws.data_ptr(), ws.numel(),
+                                       _stream()), "loss_fwd_bwd")
+    return out, grad
+
+
+def sq_err_sum(a: torch.Tensor, b: torch.Tensor) -> torch.Tensor:
+    a, b = _f32c(a, "metric input"), _f32c(b, "metric input")
+    lib = _lib.load()
+    ws = workspace(lib.srcgan_loss_workspace_bytes(a.numel()), a.device)
+    out = torch.empty((), dtype=torch.float32, device=a.device)
+    _lib.check(lib.srcgan_metrics_sqerr(a.data_ptr(), b.data_ptr(), a.numel(), out.data_ptr(), ws.data_ptr(),
+                                        ws.numel(), _stream()), "metrics_sqerr")
+    return out
+
+
+def angular_error(p: torch.Tensor, t: torch.Tensor) -> torch.Tensor:
+    p, t = _f32c(p, "metric input"), _f32c(t, "metric input")
+    n, c, h, w = p.shape
+    out = torch.empty(n, dtype=torch.float32, device=p.device)
+    _lib.check(_lib.load().srcgan_metrics_ae(p.data_ptr(), t.data_ptr(), n, c, h, w, out.data_ptr(), _stream()), "ae")
+    return out
+
+
+def minmax(a: torch.Tensor) -> torch.Tensor:
+    a = _f32c(a, "metric input")
+    out = torch.empty(2, dtype=torch.float32, device=a.device)
+    _lib.check(_lib.load().srcgan_minmax(a.data_ptr(), a.numel(), out.data_ptr(), _stream()), "minmax")
+    return out
+
+
+def ssim_sums(p: torch.Tensor, t: torch.Tensor, L: float) -> torch.Tensor:
+    """Per-image sum of the SSIM map (11x11 'valid' gaussian window)."""
+    p, t = _f32c(p, "metric input"), _f32c(t, "metric input")
+    n, c, h, w = p.shape
+    lib = _lib.load()
+    ws = workspace(lib.srcgan_ssim_workspace_bytes(n, c, h, w), p.device)
+    out = torch.empty(n, dtype=torch.float32, device=p.device)
+    _lib.check(lib.srcgan_ssim(p.data_ptr(), t.data_ptr(), n, c, h, w, float(L), out.data_ptr(), ws.data_ptr(),
+                               ws.numel(), _stream()), "ssim")
+    return out
+
+
+def rgb2lab(rgb: torch.Tensor, normalised: bool = True) -> torch.Tensor:
+    rgb = _f32c(rgb, "rgb")
+    n, c, h, w = rgb.shape
+    assert c == 3
+    out = torch.empty_like(rgb)
+    _lib.check(_lib.load().srcgan_rgb2lab(rgb.data_ptr(), out.data_ptr(), n, h, w, int(normalised), _stream()), "rgb2lab")
+    return out
+
+
+def lab2rgb(lab: torch.Tensor, normalised: bool = True) -> torch.Tensor:
+    lab = _f32c(lab, "lab")
+    n, c, h, w = lab.shape
+    assert c == 3
+    out = torch.empty_like(lab)
+    _lib.check(_lib.load().srcgan_lab2rgb(lab.data_ptr(), out.data_ptr(), n, h, w, int(normalised), _stream()), "lab2rgb")
+    return out

@@ -1,0 +1,223 @@
+"""Kernel-level parity (through the C ABI) against torch fp32 references computed on the CPU."""
+import math
+
+import pytest
+import torch
+import torch.nn.functional as F
+
+pytestmark = pytest.mark.gpu
+
+DEV = "cuda:0"
+
+
+def rand(shape, seed, scale=1.0):
+    return (torch.rand(*shape, generator=torch.Generator().manual_seed(seed)) - 0.5) * 2 * scale
+
+
+def relerr(a, b):
+    return float((a.double() - b.double()).abs().max() / b.double().abs().max().clamp_min(1e-30))
+
+
+def to_nhwc(x, dtype, ctot=None, c0=0):
+    from srcgan_b200 import ops
+    n, c, h, w = x.shape
+    buf = torch.zeros((n, h, w, ctot or c), dtype=dtype, device=DEV)
+    buf[..., c0:c0 + c] = x.permute(0, 2, 3, 1).to(DEV, dtype)
+    return ops.Slice(buf, c0, c)
+
+
+def from_nhwc(s):
+    return s.view().float().permute(0, 3, 1, 2).cpu()
+
+
+CONV_CASES = [
+    # n, h, w, cin, cout, k, stride, pad, upsample
+    (2, 12, 10, 64, 32, 3, 1, 1, False),
+    (1, 9, 11, 96, 32, 3, 1, 1, False),
+    (1, 8, 8, 192, 64, 3, 1, 1, False),
+    (2, 7, 5, 3, 64, 3, 1, 1, False),
+    (2, 7, 5, 64, 3, 3, 1, 1, False),
+    (1, 6, 6, 64, 64, 3, 1, 1, True),
+    (2, 16, 16, 3, 64, 4, 2, 1, False),
+    (2, 16, 14, 64, 128, 4, 2, 1, False),
+    (1, 9, 9, 128, 256, 4, 1, 1, False),
+    (2, 8, 8, 256, 1, 4, 1, 1, False),
+    (1, 16, 16, 128, 128, 3, 2, 1, False),
+    (1, 15, 13, 128, 256, 3, 2, 1, False),
+]
+
+
+@pytest.mark.parametrize("dtype,tol", [(torch.float32, 2e-5), (torch.bfloat16, 2e-2)])
+@pytest.mark.parametrize("case", CONV_CASES)
+def test_conv_fprop_dgrad_wgrad(case, dtype, tol):
+    from srcgan_b200 import ops
+    n, h, w, cin, cout, k, s, p, up = case
+    x = rand((n, cin, h, w), 1)
+    wt = rand((cout, cin, k, k), 2, 0.1)
+    b = rand((cout,), 3)
+    if dtype == torch.bfloat16:
+        x, wt = x.bfloat16().float(), wt.bfloat16().float()
+    xin = F.interpolate(x, scale_factor=2, mode="nearest") if up else x
+    xin = xin.clone().requires_grad_(True)
+    wr = wt.clone().requires_grad_(True)
+    br = b.clone().requires_grad_(True)
+    y_ref = F.conv2d(xin, wr, br, stride=s, padding=p)
+    ho, wo = y_ref.shape[2:]
+    gy = rand(tuple(y_ref.shape), 4)
+    if dtype == torch.bfloat16:
+        gy = gy.bfloat16().float()
+    y_ref.backward(gy)
+
+    xs = to_nhwc(x, dtype, ctot=cin + 8, c0=8)           # exercise channel-slice addressing
+    ys = ops.Slice(torch.zeros((n, ho, wo, cout + 4), dtype=dtype, device=DEV), 4, cout)
+    wp = ops.pack_weights(wt.to(DEV), ops.WL_RSCK, dtype)
+    ops.conv_fprop(xs, wp, b.to(DEV), ys, k, s, p, upsample=up)
+    assert relerr(from_nhwc(ys), y_ref.detach()) < tol
+
+    gys = to_nhwc(gy, dtype)
+    dw = torch.empty((cout, cin, k, k), device=DEV)
+    db = torch.empty((cout,), device=DEV)
+    ops.conv_wgrad(xs, gys, dw, db, k, s, p, upsample=up)
+    assert relerr(dw.cpu(), wr.grad) < tol
+    assert relerr(db.cpu(), br.grad) < tol
+    ops.conv_wgrad(xs, gys, dw, db, k, s, p, upsample=up, accumulate=True, alpha=0.5)
+    assert relerr(dw.cpu(), 1.5 * wr.grad) < tol
+
+    if not up:
+        dxs = ops.Slice(torch.zeros((n, h, w, cin), dtype=dtype, device=DEV))
+        wd = ops.pack_weights(wt.to(DEV), ops.WL_RSKC, dtype)
+        ops.conv_dgrad(gys, wd, dxs, k, s, p)
+        assert relerr(from_nhwc(dxs), xin.grad) < tol
+        if s == 1:   # dgrad as an fprop over transposed+rotated weights
+            wtp = ops.pack_weights(wt.transpose(0, 1).flip(2, 3).contiguous().to(DEV), ops.WL_RSCK, dtype)
+            dxs2 = ops.Slice(torch.zeros((n, h, w, cin), dtype=dtype, device=DEV))
+            ops.conv_fprop(gys, wtp, None, dxs2, k, 1, k - 1 - p)
+            assert relerr(from_nhwc(dxs2), xin.grad) < tol
+
+
+def test_conv_epilogue():
+    from srcgan_b200 import ops
+    n, h, w, cin, cout = 1, 6, 7, 64, 32
+    x, wt, b = rand((n, cin, h, w), 1), rand((cout, cin, 3, 3), 2, 0.1), rand((cout,), 3)
+    r1, r2, mk = rand((n, cout, h, w), 5), rand((n, cout, h, w), 6), rand((n, cout, h, w), 7)
+    y = F.leaky_relu(F.conv2d(x, wt, b, padding=1), 0.2) * 0.3 + 0.7 * r1 - 1.5 * r2
+    y = y * torch.where(mk > 0, torch.ones_like(mk), torch.full_like(mk, 0.2))
+    ys = ops.Slice(torch.zeros((n, h, w, cout), device=DEV))
+    ops.conv_fprop(to_nhwc(x, torch.float32), ops.pack_weights(wt.to(DEV), ops.WL_RSCK, torch.float32), b.to(DEV), ys,
+                   3, 1, 1, act=0.2, alpha=0.3, r1=to_nhwc(r1, torch.float32), beta1=0.7,
+                   r2=to_nhwc(r2, torch.float32), beta2=-1.5, mask=to_nhwc(mk, torch.float32), mask_slope=0.2)
+    assert relerr(from_nhwc(ys), y) < 2e-5
+
+
+@pytest.mark.parametrize("c", [3, 64])
+def test_layout_roundtrip_and_adjoint(c):
+    from srcgan_b200 import ops
+    x = rand((2, c, 10, 12), 1)
+    s = ops.Slice(torch.zeros((2, 10, 12, c + 5), device=DEV), 5, c)
+    ops.nchw_to_nhwc(x.to(DEV), s)
+    assert torch.equal(from_nhwc(s), x)
+    assert torch.equal(ops.nhwc_to_nchw(s).cpu(), x)
+    # adjoint of nearest x2
+    g = rand((2, c, 20, 24), 2)
+    ref = F.avg_pool2d(g, 2) * 4
+    d = ops.Slice(torch.zeros((2, 10, 12, c), device=DEV))
+    ops.upsample2x_adjoint(to_nhwc(g, torch.float32), d)
+    assert relerr(from_nhwc(d), ref) < 1e-6
+
+
+@pytest.mark.parametrize("training", [True, False])
+def test_batchnorm_lrelu(training):
+    from srcgan_b200 import ops
+    n, c, h, w = 3, 128, 9, 7
+    x = rand((n, c, h, w), 1, 2.0) + 0.3
+    gamma, beta = rand((c,), 2) + 1.5, rand((c,), 3)
+    rm, rv = rand((c,), 4) * 0.1, rand((c,), 5).abs() + 0.5
+    xr = x.clone().requires_grad_(True)
+    gr, br = gamma.clone().requires_grad_(True), beta.clone().requires_grad_(True)
+    rm_ref, rv_ref = rm.clone(), rv.clone()
+    y_ref = F.leaky_relu(F.batch_norm(xr, rm_ref, rv_ref, gr, br, training, 0.1, 1e-5), 0.2)
+    gy = rand((n, c, h, w), 6)
+    y_ref.backward(gy)
+
+    xs = to_nhwc(x, torch.float32)
+    ys = ops.Slice(torch.zeros((n, h, w, c), device=DEV))
+    rm_d, rv_d = rm.to(DEV), rv.to(DEV)
+    g_d, b_d = gamma.to(DEV), beta.to(DEV)
+    sm, si = ops.bn_forward(xs, ys, g_d, b_d, rm_d, rv_d, training, 0.2)
+    assert relerr(from_nhwc(ys), y_ref.detach()) < 2e-5
+    assert relerr(rm_d.cpu(), rm_ref) < 1e-5 and relerr(rv_d.cpu(), rv_ref) < 1e-5
+    dys = to_nhwc(gy, torch.float32)
+    dg, dbt = torch.empty(c, device=DEV), torch.empty(c, device=DEV)
+    ops.bn_backward(dys, ys, xs, dys, g_d, sm, si, 0.2, training, dg, dbt)
+    assert relerr(from_nhwc(dys), xr.grad) < 1e-4
+    assert relerr(dg.cpu(), gr.grad) < 1e-4 and relerr(dbt.cpu(), br.grad) < 1e-4
+
+
+@pytest.mark.parametrize("shape", [(2, 3, 64, 64), (1, 1, 14, 14), (3, 3, 7, 5)])
+def test_fused_losses(shape):
+    from srcgan_b200 import losses
+    a, b = rand(shape, 1), rand(shape, 2)
+    for kind, ref in ((losses.L1, F.l1_loss), (losses.MSE, F.mse_loss)):
+        ar = a.clone().requires_grad_(True)
+        lr = ref(ar, b) * 3.0
+        lr.backward()
+        ad = a.to(DEV).requires_grad_(True)
+        ld = losses.fused_loss(kind, ad, b.to(DEV)) * 3.0
+        ld.backward()
+        assert math.isclose(float(ld), float(lr), rel_tol=1e-5)
+        assert relerr(ad.grad.cpu(), ar.grad) < 1e-5
+    # scalar target (GANLoss label)
+    ad = a.to(DEV).requires_grad_(True)
+    ld = losses.fused_loss(losses.MSE, ad, 1.0)
+    ld.backward()
+    ar = a.clone().requires_grad_(True)
+    lr = F.mse_loss(ar, torch.ones_like(ar))
+    lr.backward()
+    assert math.isclose(float(ld), float(lr), rel_tol=1e-5) and relerr(ad.grad.cpu(), ar.grad) < 1e-5
+    assert math.isclose(float(losses.PSNRLoss()(a.to(DEV), b.to(DEV))), float(10 * torch.log10(1 / F.mse_loss(a, b))),
+                        rel_tol=1e-5)
+
+
+def test_metrics_against_oracle_and_golden(golden_modules):
+    from oracle import srcgan_oracle as O
+    from srcgan_b200 import metrics
+    g = golden_modules["scalars"]
+    a = torch.rand(2, 3, 40, 36, generator=torch.Generator().manual_seed(105))
+    b = (a + 0.05 * torch.randn(a.shape, generator=torch.Generator().manual_seed(106))).clamp(0, 1)
+    ad, bd = a.to(DEV), b.to(DEV)
+    close = lambda x, y, t=2e-5: math.isclose(float(x), float(y), rel_tol=t, abs_tol=1e-7)
+    assert close(metrics.MSE()(ad, bd), g["MSEm"]) and close(metrics.PSNR()(ad, bd), g["PSNR"])
+    assert close(metrics.SSIM()(ad, bd), g["SSIM"]) and close(metrics.SSIM()(ad, ad), 1.0)
+    assert close(metrics.SSIM()(ad * 255, bd * 255), g["SSIM_255"])
+    assert close(metrics.SSIM()(ad * 2 - 1, bd * 2 - 1), g["SSIM_neg"])
+    assert torch.allclose(metrics.SSIM()(ad, bd, size_average=False).cpu(), g["SSIM_per_image"], rtol=2e-5)
+    assert torch.allclose(metrics.AE()(ad, bd).cpu(), g["AE"], rtol=1e-4)
+    assert math.isinf(float(metrics.PSNR()(ad, ad)))
+    # larger, ragged (non multiple of the 32-pixel tile) image against the oracle
+    a = torch.rand(1, 3, 150, 97, generator=torch.Generator().manual_seed(7))
+    b = (a + 0.1 * torch.randn(a.shape, generator=torch.Generator().manual_seed(8))).clamp(0, 1)
+    assert close(metrics.SSIM()(a.to(DEV), b.to(DEV)), O.ssim(a, b), 5e-5)
+    assert torch.allclose(metrics.AE()(a.to(DEV), b.to(DEV)).cpu(), O.angular_error(a, b), rtol=1e-4)
+    assert repr(metrics.SSIM()) == "SSIM" and repr(metrics.AE()) == "AE"
+
+
+def test_color_against_oracle():
+    import numpy as np
+    from oracle import srcgan_oracle as O
+    from srcgan_b200 import color
+    rgb = torch.rand(2, 3, 33, 17, generator=torch.Generator().manual_seed(3))
+    lab = color.rgb2lab(rgb.to(DEV), True).cpu()
+    ref = np.stack([O.lab_normalise(O.rgb2lab(im.permute(1, 2, 0).numpy())) for im in rgb]).transpose(0, 3, 1, 2)
+    assert np.abs(lab.numpy() - ref).max() < 2e-5
+    back = color.lab2rgb(lab.to(DEV), True).cpu()
+    assert float((back - rgb).abs().max()) < 2e-4
+    raw = color.rgb2lab(rgb.to(DEV), False).cpu()
+    ref_raw = np.stack([O.rgb2lab(im.permute(1, 2, 0).numpy()) for im in rgb]).transpose(0, 3, 1, 2)
+    assert np.abs(raw.numpy() - ref_raw).max() < 2e-3
+
+
+def test_cpu_tensors_are_rejected_loudly():
+    from srcgan_b200 import nn as snn
+    net = snn.NLayerDiscriminator(3, 64, 2)
+    with pytest.raises(RuntimeError, match="no CPU fallback"):
+        net(torch.rand(1, 3, 32, 32))
