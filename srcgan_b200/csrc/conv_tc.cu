@@ -1,11 +1,469 @@
-// placeholder until the tcgen05 engine lands
+// tcgen05 / TMEM / TMA implicit-GEMM convolution engine for sm_100a (bf16 in, fp32 accumulate).
+//
+//   Y[n,y,x,co] = epilogue( sum_{kh,kw,ci} X[n, y+kh-pad, x+kw-pad, ci] * W[co,ci,kh,kw] )     stride 1
+//
+// GEMM view: M = output pixels (one CTA tile = 16 rows x 8 columns = 128 pixels = UMMA M),
+//            N = output channels (BN = 32/64/128 per tile), K = taps x input channels.
+// Pipeline (warp-specialised, persistent CTAs, one per SM):
+//   warp 0  TMA producer : per (64-channel chunk, kw) ONE 4-D tensor-map box load of the haloed
+//                          activation slab  [16+KH-1 rows][8 px][64 ch]  (SWIZZLE_128B, OOB zero fill
+//                          = the convolution padding), plus one bulk copy of the KH pre-swizzled
+//                          weight tiles [BN][64].  The KH taps of a column reuse the SAME slab:
+//                          a row shift is +8 px = +1024 B = one swizzle atom, so the UMMA descriptor
+//                          start address just moves by kh*1024 (3 L2->SMEM loads per chunk, not 9).
+//   warp 1  MMA issuer   : tcgen05.mma.cta_group::1.kind::f16, M=128, N=BN, K=16 per instruction,
+//                          accumulators in TMEM (double buffered: epilogue of tile i overlaps the
+//                          MMAs of tile i+1), tcgen05.commit releases SMEM stages / publishes TMEM.
+//   warps 2-5 epilogue   : tcgen05.ld 32x32b -> bias, LeakyReLU, alpha, two residuals, LeakyReLU-mask
+//                          (see include/srcgan_b200.h) -> bf16 -> 16-byte stores into the channel
+//                          slice of the NHWC (concat) buffer.
+// Reference semantics replaced: nn.Conv2d 3x3 of the dense blocks / HRconv / trunk / Decoder
+// (src/model/model.py:193-211, :236-289, :396-440) and their dgrad (as an fprop over transposed weights).
+#include <cuda.h>
+
+#include <mutex>
+
 #include "common.cuh"
+
 namespace srcgan {
-bool conv_tc_supported(const srcgan_conv_params*) { return false; }
-int conv_fprop_tc(const srcgan_conv_params*, cudaStream_t) { set_error("tcgen05 engine not built"); return SRCGAN_E_INVALID; }
-int pack_weights_tc_host(const float*, int, int, int, int, void*, cudaStream_t) { set_error("tcgen05 engine not built"); return SRCGAN_E_INVALID; }
-size_t packed_weight_bytes_tc(int, int, int, int) { return 0; }
+namespace tc {
+
+constexpr int TILE_H = 16, TILE_W = 8, TILE_M = TILE_H * TILE_W;
+constexpr int KCH = 64;                 // channels per K chunk = one 128-byte swizzle row
+constexpr int NUM_THREADS = 192;        // warp0 TMA, warp1 MMA, warps 2..5 epilogue
+constexpr int SMEM_BUDGET = 227 * 1024;
+constexpr int SMEM_AUX = 2048;          // barriers + tmem ptr + bias
+
+struct TcArgs {
+  int n, h, w, cin, cout, pad;
+  int nchunks, n_blocks;                // K chunks of 64 channels; N blocks of BN channels
+  int tiles_x, tiles_y;
+  long long num_tiles;
+  const __nv_bfloat16* wgt;             // packed [n_block][chunk][kw][kh][BN][64] (pre-swizzled)
+  const float* bias;
+  __nv_bfloat16* y; int y_ld;
+  int act; float act_slope, alpha;
+  const __nv_bfloat16* r1; int r1_ld; float beta1;
+  const __nv_bfloat16* r2; int r2_ld; float beta2;
+  const __nv_bfloat16* mask; int mask_ld; float mask_slope;
+};
+
+__device__ __forceinline__ uint32_t smem_u32(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
+
+__device__ __forceinline__ void mbar_init(uint64_t* bar, uint32_t count) {
+  asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(smem_u32(bar)), "r"(count) : "memory");
+}
+__device__ __forceinline__ void mbar_expect_tx(uint64_t* bar, uint32_t bytes) {
+  asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(smem_u32(bar)), "r"(bytes) : "memory");
+}
+__device__ __forceinline__ void mbar_arrive(uint64_t* bar) {
+  asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(smem_u32(bar)) : "memory");
+}
+__device__ __forceinline__ bool mbar_try_wait(uint64_t* bar, uint32_t parity) {
+  uint32_t ok;
+  asm volatile(
+      "{\n\t.reg .pred p;\n\t"
+      "mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n\t"
+      "selp.u32 %0, 1, 0, p;\n\t}"
+      : "=r"(ok)
+      : "r"(smem_u32(bar)), "r"(parity)
+      : "memory");
+  return ok != 0;
+}
+// Bounded wait: a pipeline bug must fault (trap), never hang the GPU box.
+__device__ __forceinline__ void mbar_wait(uint64_t* bar, uint32_t parity) {
+  if (mbar_try_wait(bar, parity)) return;
+  const long long t0 = clock64();
+  while (!mbar_try_wait(bar, parity)) {
+    if (clock64() - t0 > 4000000000LL) __trap();
+  }
+}
+
+__device__ __forceinline__ void tma_load_4d(const CUtensorMap* map, uint64_t* bar, void* dst, int c0, int c1, int c2,
+                                            int c3) {
+  asm volatile(
+      "cp.async.bulk.tensor.4d.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4, %5, %6}], [%2];"
+      ::"r"(smem_u32(dst)), "l"(map), "r"(smem_u32(bar)), "r"(c0), "r"(c1), "r"(c2), "r"(c3)
+      : "memory");
+}
+__device__ __forceinline__ void bulk_load(const void* src, uint64_t* bar, void* dst, uint32_t bytes) {
+  asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];" ::"r"(
+                   smem_u32(dst)),
+               "l"(src), "r"(bytes), "r"(smem_u32(bar))
+               : "memory");
+}
+
+// K-major SWIZZLE_128B shared-memory matrix descriptor: rows of 128 B, 8-row atoms 1024 B apart.
+__device__ __forceinline__ uint64_t umma_desc(uint32_t saddr) {
+  uint64_t d = 0;
+  d |= (uint64_t)((saddr & 0x3FFFFu) >> 4);   // start address  [0,14)
+  d |= (uint64_t)1 << 16;                     // leading byte offset (unused for swizzled K-major)
+  d |= (uint64_t)(1024 >> 4) << 32;           // stride byte offset = 1024 B between 8-row groups
+  d |= (uint64_t)1 << 46;                     // descriptor version (Blackwell)
+  d |= (uint64_t)2 << 61;                     // SWIZZLE_128B
+  return d;
+}
+__host__ __device__ constexpr uint32_t umma_idesc(int M, int N) {
+  return (1u << 4)                            // D format  F32
+         | (1u << 7)                          // A format  BF16
+         | (1u << 10)                         // B format  BF16
+         | ((uint32_t)(N >> 3) << 17)         // N
+         | ((uint32_t)(M >> 4) << 24);        // M         (A, B K-major: bits 15,16 = 0)
+}
+__device__ __forceinline__ void umma_bf16(uint32_t tmem_d, uint64_t adesc, uint64_t bdesc, uint32_t idesc,
+                                          uint32_t accumulate) {
+  asm volatile(
+      "{\n\t.reg .pred p;\n\t"
+      "setp.ne.b32 p, %4, 0;\n\t"
+      "tcgen05.mma.cta_group::1.kind::f16 [%0], %1, %2, %3, p;\n\t}"
+      ::"r"(tmem_d), "l"(adesc), "l"(bdesc), "r"(idesc), "r"(accumulate)
+      : "memory");
+}
+__device__ __forceinline__ void umma_commit(uint64_t* bar) {
+  asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(smem_u32(bar))
+               : "memory");
+}
+__device__ __forceinline__ void tc_fence_before() { asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory"); }
+__device__ __forceinline__ void tc_fence_after() { asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory"); }
+
+__device__ __forceinline__ void tmem_ld32(uint32_t taddr, uint32_t (&v)[32]) {
+  asm volatile(
+      "tcgen05.ld.sync.aligned.32x32b.x32.b32 "
+      "{%0, %1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15, "
+      "%16, %17, %18, %19, %20, %21, %22, %23, %24, %25, %26, %27, %28, %29, %30, %31}, [%32];"
+      : "=r"(v[0]), "=r"(v[1]), "=r"(v[2]), "=r"(v[3]), "=r"(v[4]), "=r"(v[5]), "=r"(v[6]), "=r"(v[7]), "=r"(v[8]),
+        "=r"(v[9]), "=r"(v[10]), "=r"(v[11]), "=r"(v[12]), "=r"(v[13]), "=r"(v[14]), "=r"(v[15]), "=r"(v[16]),
+        "=r"(v[17]), "=r"(v[18]), "=r"(v[19]), "=r"(v[20]), "=r"(v[21]), "=r"(v[22]), "=r"(v[23]), "=r"(v[24]),
+        "=r"(v[25]), "=r"(v[26]), "=r"(v[27]), "=r"(v[28]), "=r"(v[29]), "=r"(v[30]), "=r"(v[31])
+      : "r"(taddr));
+  asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
+}
+
+__device__ __forceinline__ void unpack8(const uint4& q, float (&f)[8]) {
+  const __nv_bfloat162* h = reinterpret_cast<const __nv_bfloat162*>(&q);
+#pragma unroll
+  for (int i = 0; i < 4; ++i) { f[2 * i] = __low2float(h[i]); f[2 * i + 1] = __high2float(h[i]); }
+}
+
+template <int BN, int KH, int KW>
+struct Cfg {
+  static constexpr int A_BYTES = (TILE_H + KH - 1) * TILE_W * 128;
+  static constexpr int B_TAP_BYTES = BN * 128;
+  static constexpr int B_BYTES = KH * B_TAP_BYTES;
+  static constexpr int STAGE_BYTES = A_BYTES + B_BYTES;
+  static constexpr int STAGES_RAW = (SMEM_BUDGET - SMEM_AUX - 1024) / STAGE_BYTES;
+  static constexpr int STAGES = STAGES_RAW > 8 ? 8 : STAGES_RAW;
+  static constexpr int SMEM_BYTES = STAGES * STAGE_BYTES + SMEM_AUX + 1024;
+  static constexpr int TMEM_COLS = 2 * BN < 32 ? 32 : 2 * BN;     // 64 / 128 / 256: powers of two
+  static_assert(A_BYTES % 1024 == 0 && B_TAP_BYTES % 1024 == 0, "swizzle atoms must stay 1024-B aligned");
+  static_assert(STAGES >= 2, "not enough shared memory for a pipeline");
+};
+
+template <int BN, int KH, int KW>
+__global__ void __launch_bounds__(NUM_THREADS, 1)
+conv_igemm_tc(const __grid_constant__ CUtensorMap tmap_x, const TcArgs a) {
+  using C = Cfg<BN, KH, KW>;
+  extern __shared__ uint8_t smem_raw[];
+  uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~(uintptr_t)1023);
+  uint8_t* aux = smem + C::STAGES * C::STAGE_BYTES;
+  uint64_t* full_bar = reinterpret_cast<uint64_t*>(aux);            // [STAGES]
+  uint64_t* empty_bar = full_bar + C::STAGES;                        // [STAGES]
+  uint64_t* tfull_bar = empty_bar + C::STAGES;                       // [2]
+  uint64_t* tempty_bar = tfull_bar + 2;                              // [2]
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(tempty_bar + 2);
+  float* sbias = reinterpret_cast<float*>(aux + 512);                // [<=256]
+
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+
+  if (threadIdx.x == 0) {
+    for (int s = 0; s < C::STAGES; ++s) { mbar_init(&full_bar[s], 1); mbar_init(&empty_bar[s], 1); }
+    for (int s = 0; s < 2; ++s) { mbar_init(&tfull_bar[s], 1); mbar_init(&tempty_bar[s], 128); }
+    asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+  }
+  for (int i = threadIdx.x; i < a.cout; i += NUM_THREADS) sbias[i] = a.bias ? a.bias[i] : 0.f;
+  if (warp == 1) {
+    asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(tmem_slot)),
+                 "r"((uint32_t)C::TMEM_COLS)
+                 : "memory");
+    asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
+  }
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  const uint32_t tmem_base = *tmem_slot;
+
+  const int per_img = a.tiles_x * a.tiles_y;
+
+  if (warp == 0) {
+    // ------------------------------------------------------------------ TMA producer
+    if (lane == 0) {
+      int stage = 0;
+      uint32_t phase = 0;
+      for (long long t = blockIdx.x; t < a.num_tiles; t += gridDim.x) {
+        const int nb = (int)(t % a.n_blocks);
+        long long r = t / a.n_blocks;
+        const int bx = (int)(r % a.tiles_x); r /= a.tiles_x;
+        const int by = (int)(r % a.tiles_y);
+        const int img = (int)(r / a.tiles_y);
+        const int x0 = bx * TILE_W, y0 = by * TILE_H;
+        for (int c = 0; c < a.nchunks; ++c) {
+          for (int s = 0; s < KW; ++s) {
+            mbar_wait(&empty_bar[stage], phase ^ 1);
+            uint8_t* sa = smem + stage * C::STAGE_BYTES;
+            mbar_expect_tx(&full_bar[stage], C::STAGE_BYTES);
+            tma_load_4d(&tmap_x, &full_bar[stage], sa, c * KCH, x0 + s - a.pad, y0 - a.pad, img);
+            const __nv_bfloat16* wsrc =
+                a.wgt + ((((size_t)nb * a.nchunks + c) * KW + s) * KH) * (size_t)(BN * KCH);
+            bulk_load(wsrc, &full_bar[stage], sa + C::A_BYTES, C::B_BYTES);
+            if (++stage == C::STAGES) { stage = 0; phase ^= 1; }
+          }
+        }
+      }
+    }
+  } else if (warp == 1) {
+    // ------------------------------------------------------------------ MMA issuer
+    if (lane == 0) {
+      constexpr uint32_t idesc = umma_idesc(TILE_M, BN);
+      int stage = 0;
+      uint32_t phase = 0;
+      int acc = 0;
+      uint32_t acc_phase = 0;
+      for (long long t = blockIdx.x; t < a.num_tiles; t += gridDim.x) {
+        mbar_wait(&tempty_bar[acc], acc_phase ^ 1);
+        tc_fence_after();
+        const uint32_t tmem_d = tmem_base + (uint32_t)(acc * BN);
+        uint32_t accumulate = 0;
+        for (int c = 0; c < a.nchunks; ++c) {
+          const int rem = a.cin - c * KCH;
+          const int ksteps = (rem >= KCH ? KCH : rem) >> 4;
+          for (int s = 0; s < KW; ++s) {
+            mbar_wait(&full_bar[stage], phase);
+            tc_fence_after();
+            const uint32_t sa = smem_u32(smem + stage * C::STAGE_BYTES);
+            const uint32_t sb = sa + C::A_BYTES;
+#pragma unroll
+            for (int kh = 0; kh < KH; ++kh) {
+              for (int ks = 0; ks < ksteps; ++ks) {
+                umma_bf16(tmem_d, umma_desc(sa + kh * (TILE_W * 128) + ks * 32),
+                          umma_desc(sb + kh * C::B_TAP_BYTES + ks * 32), idesc, accumulate);
+                accumulate = 1;
+              }
+            }
+            umma_commit(&empty_bar[stage]);        // frees the SMEM stage when these MMAs retire
+            if (++stage == C::STAGES) { stage = 0; phase ^= 1; }
+          }
+        }
+        umma_commit(&tfull_bar[acc]);              // accumulator complete -> epilogue
+        if (++acc == 2) { acc = 0; acc_phase ^= 1; }
+      }
+    }
+  } else {
+    // ------------------------------------------------------------------ epilogue (warps 2..5)
+    const int q = warp & 3;                        // TMEM lane quadrant this warp may access
+    const int row = q * 32 + lane;                 // GEMM row = tile pixel
+    const int ty = row >> 3, tx = row & 7;
+    int acc = 0;
+    uint32_t acc_phase = 0;
+    for (long long t = blockIdx.x; t < a.num_tiles; t += gridDim.x) {
+      const int nb = (int)(t % a.n_blocks);
+      long long r = t / a.n_blocks;
+      const int bx = (int)(r % a.tiles_x); r /= a.tiles_x;
+      const int by = (int)(r % a.tiles_y);
+      const int img = (int)(r / a.tiles_y);
+      const int y = by * TILE_H + ty, x = bx * TILE_W + tx;
+      const bool valid = (y < a.h) && (x < a.w);
+      const long long pix = ((long long)img * a.h + y) * a.w + x;
+      mbar_wait(&tfull_bar[acc], acc_phase);
+      tc_fence_after();
+      const uint32_t taddr = tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)(acc * BN);
+#pragma unroll 1
+      for (int cb = 0; cb < BN; cb += 32) {
+        uint32_t v[32];
+        tmem_ld32(taddr + cb, v);
+        if (valid) {
+          const int c0 = nb * BN + cb;
+#pragma unroll
+          for (int g = 0; g < 4; ++g) {
+            float f[8];
+#pragma unroll
+            for (int i = 0; i < 8; ++i) {
+              float t0 = __uint_as_float(v[g * 8 + i]) + sbias[c0 + g * 8 + i];
+              if (a.act) t0 = t0 > 0.f ? t0 : t0 * a.act_slope;
+              f[i] = t0 * a.alpha;
+            }
+            const int cc = c0 + g * 8;
+            if (a.r1) {
+              float rr[8];
+              unpack8(__ldg(reinterpret_cast<const uint4*>(a.r1 + pix * a.r1_ld + cc)), rr);
+#pragma unroll
+              for (int i = 0; i < 8; ++i) f[i] = fmaf(a.beta1, rr[i], f[i]);
+            }
+            if (a.r2) {
+              float rr[8];
+              unpack8(__ldg(reinterpret_cast<const uint4*>(a.r2 + pix * a.r2_ld + cc)), rr);
+#pragma unroll
+              for (int i = 0; i < 8; ++i) f[i] = fmaf(a.beta2, rr[i], f[i]);
+            }
+            if (a.mask) {
+              float mm[8];
+              unpack8(__ldg(reinterpret_cast<const uint4*>(a.mask + pix * a.mask_ld + cc)), mm);
+#pragma unroll
+              for (int i = 0; i < 8; ++i) f[i] *= (mm[i] > 0.f ? 1.f : a.mask_slope);
+            }
+            uint4 o;
+            __nv_bfloat162* oh = reinterpret_cast<__nv_bfloat162*>(&o);
+#pragma unroll
+            for (int i = 0; i < 4; ++i) oh[i] = __floats2bfloat162_rn(f[2 * i], f[2 * i + 1]);
+            *reinterpret_cast<uint4*>(a.y + pix * a.y_ld + cc) = o;
+          }
+        }
+      }
+      tc_fence_before();
+      mbar_arrive(&tempty_bar[acc]);
+      if (++acc == 2) { acc = 0; acc_phase ^= 1; }
+    }
+  }
+
+  tc_fence_before();
+  __syncthreads();
+  if (warp == 1) {
+    asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "r"((uint32_t)C::TMEM_COLS)
+                 : "memory");
+  }
+}
+
+// fp32 OIHW -> bf16 [n_block][chunk][kw][kh][BN][64], each [BN][64] tile stored as its SWIZZLE_128B
+// shared-memory image (16-byte chunk j of row r lives at chunk j ^ (r & 7)); zero padded in K.
+__global__ void pack_weights_tc(const float* __restrict__ w, int cout, int cin, int kh, int kw, int bn, int nchunks,
+                                __nv_bfloat16* __restrict__ out) {
+  const long long total = (long long)(cout / bn) * nchunks * kw * kh * bn * KCH;
+  long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= total) return;
+  const int j = (int)(i % KCH);
+  long long t = i / KCH;
+  const int r = (int)(t % bn); t /= bn;
+  const int fh = (int)(t % kh); t /= kh;
+  const int fw = (int)(t % kw); t /= kw;
+  const int c = (int)(t % nchunks);
+  const int nb = (int)(t / nchunks);
+  const int co = nb * bn + r, ci = c * KCH + j;
+  float v = 0.f;
+  if (ci < cin) v = w[(((long long)co * cin + ci) * kh + fh) * kw + fw];
+  const long long tile = i - (long long)r * KCH - j;   // start of this [BN][64] tile
+  const int chunk16 = (j >> 3) ^ (r & 7);
+  out[tile + (long long)r * KCH + chunk16 * 8 + (j & 7)] = __float2bfloat16_rn(v);
+}
+
+typedef CUresult (*EncodeTiledFn)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*,
+                                  const cuuint64_t*, const cuuint32_t*, const cuuint32_t*, CUtensorMapInterleave,
+                                  CUtensorMapSwizzle, CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
+
+static EncodeTiledFn get_encode_fn() {
+  static EncodeTiledFn fn = nullptr;
+  static std::once_flag once;
+  std::call_once(once, [] {
+    void* p = nullptr;
+    cudaDriverEntryPointQueryResult q;
+    if (cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &p, cudaEnableDefault, &q) == cudaSuccess &&
+        q == cudaDriverEntryPointSuccess)
+      fn = reinterpret_cast<EncodeTiledFn>(p);
+  });
+  return fn;
+}
+
+static int bn_for(int cout) { return cout >= 128 ? 128 : cout; }
+
+template <int BN, int KH, int KW>
+static int launch(const CUtensorMap& tmap, const TcArgs& a, cudaStream_t st) {
+  using C = Cfg<BN, KH, KW>;
+  static bool attr_set = false;
+  if (!attr_set) {
+    SRCGAN_CUDA(cudaFuncSetAttribute(conv_igemm_tc<BN, KH, KW>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                     C::SMEM_BYTES));
+    attr_set = true;
+  }
+  long long grid = a.num_tiles < kNumSMs ? a.num_tiles : kNumSMs;
+  conv_igemm_tc<BN, KH, KW><<<(unsigned)grid, NUM_THREADS, C::SMEM_BYTES, st>>>(tmap, a);
+  count_launch();
+  return check_launch("conv_igemm_tc");
+}
+
+}  // namespace tc
+
+bool conv_tc_supported(const srcgan_conv_params* p) {
+  if (p->dtype != SRCGAN_DT_BF16 || p->stride != 1 || p->upsample) return false;
+  if (p->kh != p->kw || (p->kh != 3 && p->kh != 4)) return false;
+  if (p->cin < 64 || p->cin % 16 != 0) return false;
+  if (!(p->cout == 32 || p->cout == 64 || p->cout == 128 || p->cout == 256)) return false;
+  if (p->x_ld % 8 || p->y_ld % 8) return false;
+  if (((uintptr_t)p->x) % 16 || ((uintptr_t)p->y) % 16) return false;
+  if (p->r1 && (p->r1_ld % 8 || ((uintptr_t)p->r1) % 16)) return false;
+  if (p->r2 && (p->r2_ld % 8 || ((uintptr_t)p->r2) % 16)) return false;
+  if (p->mask && (p->mask_ld % 8 || ((uintptr_t)p->mask) % 16)) return false;
+  return true;
+}
+
+size_t packed_weight_bytes_tc(int cout, int cin, int kh, int kw) {
+  const int nchunks = (cin + tc::KCH - 1) / tc::KCH;
+  return (size_t)cout * nchunks * tc::KCH * kh * kw * sizeof(__nv_bfloat16);
+}
+
+int pack_weights_tc_host(const float* w, int cout, int cin, int kh, int kw, void* out, cudaStream_t st) {
+  SRCGAN_REQUIRE(cout == 32 || cout == 64 || cout == 128 || cout == 256, "pack_weights(tc): cout %d unsupported", cout);
+  const int bn = tc::bn_for(cout);
+  const int nchunks = (cin + tc::KCH - 1) / tc::KCH;
+  const long long total = (long long)cout * nchunks * tc::KCH * kh * kw;
+  tc::pack_weights_tc<<<ceil_div(total, 256), 256, 0, st>>>(w, cout, cin, kh, kw, bn, nchunks, (__nv_bfloat16*)out);
+  count_launch();
+  return check_launch("pack_weights_tc");
+}
+
+int conv_fprop_tc(const srcgan_conv_params* p, cudaStream_t st) {
+  tc::EncodeTiledFn encode = tc::get_encode_fn();
+  SRCGAN_REQUIRE(encode != nullptr, "conv_fprop_tc: cuTensorMapEncodeTiled is not available from the driver");
+  const int KH = p->kh;
+  CUtensorMap tmap;
+  cuuint64_t gdim[4] = {(cuuint64_t)p->cin, (cuuint64_t)p->w, (cuuint64_t)p->h, (cuuint64_t)p->n};
+  cuuint64_t gstr[3] = {(cuuint64_t)p->x_ld * 2, (cuuint64_t)p->x_ld * 2 * p->w, (cuuint64_t)p->x_ld * 2 * p->w * p->h};
+  cuuint32_t box[4] = {(cuuint32_t)tc::KCH, (cuuint32_t)tc::TILE_W, (cuuint32_t)(tc::TILE_H + KH - 1), 1};
+  cuuint32_t estr[4] = {1, 1, 1, 1};
+  CUresult cr = encode(&tmap, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 4, const_cast<void*>(p->x), gdim, gstr, box, estr,
+                       CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
+                       CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+  if (cr != CUDA_SUCCESS) {
+    set_error("conv_fprop_tc: cuTensorMapEncodeTiled failed with CUresult %d", (int)cr);
+    return SRCGAN_E_CUDA;
+  }
+  tc::TcArgs a;
+  a.n = p->n; a.h = p->ho; a.w = p->wo; a.cin = p->cin; a.cout = p->cout; a.pad = p->pad;
+  a.nchunks = (p->cin + tc::KCH - 1) / tc::KCH;
+  const int bn = tc::bn_for(p->cout);
+  a.n_blocks = p->cout / bn;
+  a.tiles_x = (p->wo + tc::TILE_W - 1) / tc::TILE_W;
+  a.tiles_y = (p->ho + tc::TILE_H - 1) / tc::TILE_H;
+  a.num_tiles = (long long)a.tiles_x * a.tiles_y * p->n * a.n_blocks;
+  a.wgt = (const __nv_bfloat16*)p->wgt; a.bias = p->bias;
+  a.y = (__nv_bfloat16*)p->y; a.y_ld = p->y_ld;
+  a.act = p->act; a.act_slope = p->act_slope; a.alpha = p->alpha;
+  a.r1 = (const __nv_bfloat16*)p->r1; a.r1_ld = p->r1_ld; a.beta1 = p->beta1;
+  a.r2 = (const __nv_bfloat16*)p->r2; a.r2_ld = p->r2_ld; a.beta2 = p->beta2;
+  a.mask = (const __nv_bfloat16*)p->mask; a.mask_ld = p->mask_ld; a.mask_slope = p->mask_slope;
+  if (KH == 3) {
+    if (bn == 32) return tc::launch<32, 3, 3>(tmap, a, st);
+    if (bn == 64) return tc::launch<64, 3, 3>(tmap, a, st);
+    return tc::launch<128, 3, 3>(tmap, a, st);
+  }
+  if (bn == 32) return tc::launch<32, 4, 4>(tmap, a, st);
+  if (bn == 64) return tc::launch<64, 4, 4>(tmap, a, st);
+  return tc::launch<128, 4, 4>(tmap, a, st);
+}
+
+// tcgen05 wgrad: not built yet (the SIMT engine serves wgrad)
 bool conv_wgrad_tc_supported(const srcgan_conv_params*) { return false; }
 size_t conv_wgrad_tc_workspace(const srcgan_conv_params*) { return 0; }
-int conv_wgrad_tc(const srcgan_conv_params*, float*, float*, int, void*, size_t, cudaStream_t) { set_error("tcgen05 engine not built"); return SRCGAN_E_INVALID; }
+int conv_wgrad_tc(const srcgan_conv_params*, float*, float*, int, void*, size_t, cudaStream_t) {
+  set_error("conv_wgrad: the tcgen05 wgrad kernel is not built yet");
+  return SRCGAN_E_INVALID;
 }
+
+}  // namespace srcgan

@@ -20,7 +20,9 @@ def force_simt(flag: bool) -> None:
 
 
 def tc_fprop_supported(cin: int, cout: int, k: int, stride: int, upsample: bool, dtype, h: int, w: int) -> bool:
-    return False
+    """Mirror of conv_tc_supported() in csrc/conv_tc.cu (the C side re-checks alignment and refuses loudly)."""
+    return (dtype == torch.bfloat16 and stride == 1 and not upsample and k in (3, 4) and cin >= 64
+            and cin % 16 == 0 and cout in (32, 64, 128, 256))
 
 
 def tc_wgrad_supported(cin: int, cout: int, k: int, stride: int, upsample: bool, dtype, h: int, w: int) -> bool:

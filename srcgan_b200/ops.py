@@ -111,6 +111,56 @@ def pack_weights(w_oihw: torch.Tensor, layout: int, dtype: torch.dtype) -> torch
 
 
 # ------------------------------------------------------------------------------------------
+# per-launch timing (used by bench.py for the roofline line; off by default)
+# ------------------------------------------------------------------------------------------
+
+class KernelTimer:
+    """CUDA-event timing of every convolution launch on the launching stream, keyed by kernel family."""
+
+    def __init__(self):
+        self.enabled = False
+        self.records = []      # (key, flops, start_event, end_event)
+
+    def reset(self):
+        self.records = []
+
+    def summary(self):
+        """-> {key: dict(launches, ms, flops)} ; call after torch.cuda.synchronize()"""
+        out = {}
+        for key, flops, a, b in self.records:
+            d = out.setdefault(key, {"launches": 0, "ms": 0.0, "flops": 0.0})
+            d["launches"] += 1
+            d["ms"] += a.elapsed_time(b)
+            d["flops"] += flops
+        return out
+
+
+timer = KernelTimer()
+
+
+class _Timed:
+    def __init__(self, kind: str, p: ConvParams):
+        self.on = timer.enabled
+        if self.on:
+            eng = {ENGINE_SIMT: "simt", ENGINE_TC: "tc", ENGINE_AUTO: "auto"}[p.engine]
+            self.key = "conv_%s_%s" % (kind, eng)
+            self.flops = 2.0 * p.n * p.ho * p.wo * p.cin * p.cout * p.kh * p.kw
+
+    def __enter__(self):
+        if self.on:
+            self.a = torch.cuda.Event(enable_timing=True)
+            self.b = torch.cuda.Event(enable_timing=True)
+            self.a.record()
+        return self
+
+    def __exit__(self, *exc):
+        if self.on:
+            self.b.record()
+            timer.records.append((self.key, self.flops, self.a, self.b))
+        return False
+
+
+# ------------------------------------------------------------------------------------------
 # convolution
 # ------------------------------------------------------------------------------------------
 
@@ -147,7 +197,8 @@ def conv_fprop(x: Slice, wgt: torch.Tensor, bias: Optional[torch.Tensor], y: Sli
     p = _conv_params(x.n, x.h, x.w, x.c, y.c, k, stride, pad, upsample, y.h, y.w, x.dtype, engine)
     p.x, p.x_ld, p.wgt, p.y, p.y_ld = x.ptr, x.ld, wgt.data_ptr(), y.ptr, y.ld
     _epilogue(p, bias, act, alpha, r1, beta1, r2, beta2, mask, mask_slope)
-    _lib.check(_lib.load().srcgan_conv_fprop(C.byref(p), _stream()), "conv_fprop")
+    with _Timed("fprop", p):
+        _lib.check(_lib.load().srcgan_conv_fprop(C.byref(p), _stream()), "conv_fprop")
 
 
 def conv_dgrad(dy: Slice, wgt_rskc: torch.Tensor, dx: Slice, k: int, stride: int, pad: int, *, alpha: float = 1.0,
@@ -158,7 +209,8 @@ def conv_dgrad(dy: Slice, wgt_rskc: torch.Tensor, dx: Slice, k: int, stride: int
     p = _conv_params(dx.n, dx.h, dx.w, dx.c, dy.c, k, stride, pad, False, dy.h, dy.w, dy.dtype, ENGINE_SIMT)
     p.x, p.x_ld, p.wgt, p.y, p.y_ld = dy.ptr, dy.ld, wgt_rskc.data_ptr(), dx.ptr, dx.ld
     _epilogue(p, None, None, alpha, r1, beta1, None, 0.0, mask, mask_slope)
-    _lib.check(_lib.load().srcgan_conv_dgrad(C.byref(p), _stream()), "conv_dgrad")
+    with _Timed("dgrad", p):
+        _lib.check(_lib.load().srcgan_conv_dgrad(C.byref(p), _stream()), "conv_dgrad")
 
 
 def conv_wgrad(x: Slice, dy: Slice, dw: Optional[torch.Tensor], db: Optional[torch.Tensor], k: int, stride: int = 1,
@@ -177,9 +229,10 @@ def conv_wgrad(x: Slice, dy: Slice, dw: Optional[torch.Tensor], db: Optional[tor
     lib = _lib.load()
     nbytes = lib.srcgan_conv_wgrad_workspace_bytes(C.byref(p))
     ws = workspace(nbytes, x.buf.device)
-    _lib.check(lib.srcgan_conv_wgrad(C.byref(p), dw.data_ptr() if dw is not None else None,
-                                     db.data_ptr() if db is not None else None, int(accumulate),
-                                     ws.data_ptr(), ws.numel(), _stream()), "conv_wgrad")
+    with _Timed("wgrad", p):
+        _lib.check(lib.srcgan_conv_wgrad(C.byref(p), dw.data_ptr() if dw is not None else None,
+                                         db.data_ptr() if db is not None else None, int(accumulate),
+                                         ws.data_ptr(), ws.numel(), _stream()), "conv_wgrad")
 
 
 # ------------------------------------------------------------------------------------------

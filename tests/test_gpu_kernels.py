@@ -221,3 +221,56 @@ def test_cpu_tensors_are_rejected_loudly():
     net = snn.NLayerDiscriminator(3, 64, 2)
     with pytest.raises(RuntimeError, match="no CPU fallback"):
         net(torch.rand(1, 3, 32, 32))
+
+
+TC_CASES = [
+    # n, h, w, cin, cout, k, pad
+    (2, 16, 8, 64, 64, 3, 1),        # exactly one tile per image
+    (1, 32, 24, 64, 32, 3, 1),
+    (2, 20, 13, 96, 32, 3, 1),       # ragged tiles + 32-channel K tail
+    (1, 16, 16, 128, 32, 3, 1),
+    (1, 17, 9, 160, 32, 3, 1),
+    (2, 24, 16, 192, 64, 3, 1),
+    (1, 16, 8, 64, 128, 3, 1),
+    (1, 16, 16, 256, 128, 3, 1),
+    (1, 18, 10, 128, 256, 4, 1),     # discriminator 4x4 s1 (output 17x9)
+    (1, 12, 12, 256, 128, 4, 2),     # its dgrad as an fprop (pad = k-1-p = 2)
+    (3, 64, 64, 192, 64, 3, 1),      # many tiles per CTA: exercises stage/phase wrap-around
+]
+
+
+@pytest.mark.parametrize("case", TC_CASES)
+def test_conv_tc_matches_reference(case):
+    """tcgen05 engine vs torch fp32 conv on bf16-rounded operands (fp32 accumulate both sides)."""
+    from srcgan_b200 import ops
+    n, h, w, cin, cout, k, p = case
+    x = rand((n, cin, h, w), 11).bfloat16().float()
+    wt = rand((cout, cin, k, k), 12, 0.1).bfloat16().float()
+    b = rand((cout,), 13)
+    y_ref = F.conv2d(x, wt, b, stride=1, padding=p)
+    ho, wo = y_ref.shape[2:]
+    xs = to_nhwc(x, torch.bfloat16, ctot=cin + 64, c0=0)
+    ys = ops.Slice(torch.zeros((n, ho, wo, cout + 64), dtype=torch.bfloat16, device=DEV), 64, cout)
+    wp = ops.pack_weights(wt.to(DEV), ops.WL_TC, torch.bfloat16)
+    ops.conv_fprop(xs, wp, b.to(DEV), ys, k, 1, p, engine=ops.ENGINE_TC)
+    torch.cuda.synchronize()
+    got = from_nhwc(ys)
+    assert relerr(got, y_ref) < 1e-2, relerr(got, y_ref)
+    # untouched neighbouring channels of the concat buffer
+    assert float(ys.buf[..., :64].abs().max()) == 0.0
+
+
+def test_conv_tc_epilogue_matches_simt():
+    from srcgan_b200 import ops
+    n, h, w, cin, cout = 2, 32, 16, 128, 64
+    x, wt, b = rand((n, cin, h, w), 1), rand((cout, cin, 3, 3), 2, 0.1), rand((cout,), 3)
+    r1, r2, mk = rand((n, cout, h, w), 5), rand((n, cout, h, w), 6), rand((n, cout, h, w), 7)
+    outs = []
+    for eng, layout in ((ops.ENGINE_SIMT, ops.WL_RSCK), (ops.ENGINE_TC, ops.WL_TC)):
+        ys = ops.Slice(torch.zeros((n, h, w, cout), dtype=torch.bfloat16, device=DEV))
+        ops.conv_fprop(to_nhwc(x, torch.bfloat16), ops.pack_weights(wt.to(DEV), layout, torch.bfloat16), b.to(DEV), ys,
+                       3, 1, 1, act=0.2, alpha=0.3, r1=to_nhwc(r1, torch.bfloat16), beta1=0.7,
+                       r2=to_nhwc(r2, torch.bfloat16), beta2=-1.5, mask=to_nhwc(mk, torch.bfloat16), mask_slope=0.2,
+                       engine=eng)
+        outs.append(from_nhwc(ys))
+    assert relerr(outs[1], outs[0]) < 1e-2
