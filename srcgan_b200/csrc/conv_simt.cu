@@ -460,6 +460,31 @@ int conv_wgrad_simt(const srcgan_conv_params* p, float* dw, float* db, int accum
   return launch_wgrad<__nv_bfloat16>(p, dw, db, accumulate, ws, ws_bytes, st);
 }
 
+int wgrad_reduce_launch(const float* part, int splits, int taps, int cin, int cout, float* dw, int accumulate,
+                        float alpha, cudaStream_t st) {
+  int64_t total = (int64_t)taps * cin * cout;
+  wgrad_reduce<<<ceil_div(total, 256), 256, 0, st>>>(part, splits, taps, cin, cout, dw, accumulate, alpha);
+  count_launch();
+  return check_launch("wgrad_reduce");
+}
+
+int bias_grad_launch(const void* dy, int dy_ld, int dtype, long long M, int cout, float* db, int accumulate,
+                     float alpha, void* ws, cudaStream_t st) {
+  float* bpart = reinterpret_cast<float*>(ws);
+  int ny = (int)((M + 2047) / 2048);
+  if (ny > 1024) ny = 1024;
+  if (ny < 1) ny = 1;
+  dim3 grid(ceil_div(cout, 32), ny), blk(32, 8);
+  if (dtype == SRCGAN_DT_F32)
+    colsum_partial<float><<<grid, blk, 0, st>>>(reinterpret_cast<const float*>(dy), dy_ld, M, cout, bpart);
+  else
+    colsum_partial<__nv_bfloat16><<<grid, blk, 0, st>>>(reinterpret_cast<const __nv_bfloat16*>(dy), dy_ld, M, cout,
+                                                        bpart);
+  colsum_final<<<ceil_div(cout, 128), 128, 0, st>>>(bpart, ny, cout, db, accumulate, alpha);
+  count_launch(2);
+  return check_launch("bias_grad");
+}
+
 int pack_weights_simt_host(const float* w, int cout, int cin, int kh, int kw, int layout, int dtype, void* out,
                            cudaStream_t st) {
   int64_t total = (int64_t)kh * kw * cin * cout;

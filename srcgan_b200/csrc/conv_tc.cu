@@ -458,12 +458,291 @@ int conv_fprop_tc(const srcgan_conv_params* p, cudaStream_t st) {
   return tc::launch<128, 4, 4>(tmap, a, st);
 }
 
-// tcgen05 wgrad: not built yet (the SIMT engine serves wgrad)
-bool conv_wgrad_tc_supported(const srcgan_conv_params*) { return false; }
-size_t conv_wgrad_tc_workspace(const srcgan_conv_params*) { return 0; }
-int conv_wgrad_tc(const srcgan_conv_params*, float*, float*, int, void*, size_t, cudaStream_t) {
-  set_error("conv_wgrad: the tcgen05 wgrad kernel is not built yet");
-  return SRCGAN_E_INVALID;
+// ---------------------------------------------------------------------------------------------
+// tcgen05 wgrad:  dW[co][ci][kh][kw] = sum_{n,y,x} X[n,y+kh-pad,x+kw-pad,ci] * dY[n,y,x,co]
+//
+// GEMM view per tap: D[ci][co] += X_tap^T[ci][pixels] * dY[pixels][co] :  M = 128 input channels (two
+// 64-channel swizzle atoms), N = BN output channels, K = pixels.  Both operands are "MN-major" for the
+// tensor core: NHWC keeps the channel (M resp. N) contiguous and the pixel (K) strided, which is
+// exactly the SWIZZLE_128B slab a TMA box load produces - no transposes anywhere.
+// One CTA owns (kw, 128-channel ci block, co block, pixel split): it streams its pixel tiles
+// (16x8 pixels = 8 MMA K-steps) through a TMA ring, accumulates the KH taps of its column into KH
+// TMEM accumulators (a tap's row shift is again +1024 B on the descriptor), and finally writes fp32
+// partials [split][tap][ci][co]; a fixed-order reduce kernel sums the splits into the OIHW gradient.
+// ---------------------------------------------------------------------------------------------
+namespace tcw {
+using namespace tc;
+
+struct WgArgs {
+  int n, ho, wo, cin, cout, pad, kw;
+  int cblocks, nblocks, splits;
+  int tiles_x, tiles_y;
+  long long num_tiles, tiles_per_split;
+  float* part;        // [splits][KH*KW][cin][cout]
+};
+
+// MN-major SWIZZLE_128B descriptor: 64-element (128 B) rows along M/N, 8 K-rows per 1024-B atom,
+// next 8 K-rows at SBO, next 64 M/N elements at LBO.
+__device__ __forceinline__ uint64_t umma_desc_mn(uint32_t saddr, uint32_t lbo_bytes) {
+  uint64_t d = 0;
+  d |= (uint64_t)((saddr & 0x3FFFFu) >> 4);
+  d |= (uint64_t)((lbo_bytes >> 4) & 0x3FFF) << 16;
+  d |= (uint64_t)(1024 >> 4) << 32;
+  d |= (uint64_t)1 << 46;
+  d |= (uint64_t)2 << 61;
+  return d;
+}
+__host__ __device__ constexpr uint32_t umma_idesc_mn(int M, int N) {
+  return umma_idesc(M, N) | (1u << 15) | (1u << 16);      // A and B MN-major
+}
+
+template <int BN, int KH>
+struct WCfg {
+  static constexpr int A_SLAB = (TILE_H + KH - 1) * TILE_W * 128;   // one 64-channel chunk of X (haloed rows)
+  static constexpr int A_BYTES = 2 * A_SLAB;
+  static constexpr int G_SLAB = TILE_M * 128;                        // 128 pixels x 64 channels of dY
+  static constexpr int G_BYTES = (BN / 64) * G_SLAB;
+  static constexpr int STAGE_BYTES = A_BYTES + G_BYTES;
+  static constexpr int STAGES_RAW = (SMEM_BUDGET - SMEM_AUX - 1024) / STAGE_BYTES;
+  static constexpr int STAGES = STAGES_RAW > 6 ? 6 : STAGES_RAW;
+  static constexpr int SMEM_BYTES = STAGES * STAGE_BYTES + SMEM_AUX + 1024;
+  static constexpr int TMEM_COLS = KH * BN <= 256 ? 256 : 512;
+  static_assert(KH * BN <= 512, "accumulators exceed TMEM");
+  static_assert(STAGES >= 2, "not enough shared memory for a pipeline");
+};
+
+template <int BN, int KH>
+__global__ void __launch_bounds__(NUM_THREADS, 1)
+conv_wgrad_tc_kernel(const __grid_constant__ CUtensorMap tmap_x, const __grid_constant__ CUtensorMap tmap_g,
+                     const WgArgs a) {
+  using C = WCfg<BN, KH>;
+  extern __shared__ uint8_t smem_raw[];
+  uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~(uintptr_t)1023);
+  uint8_t* aux = smem + C::STAGES * C::STAGE_BYTES;
+  uint64_t* full_bar = reinterpret_cast<uint64_t*>(aux);
+  uint64_t* empty_bar = full_bar + C::STAGES;
+  uint64_t* done_bar = empty_bar + C::STAGES;
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(done_bar + 1);
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+
+  if (threadIdx.x == 0) {
+    for (int s = 0; s < C::STAGES; ++s) { mbar_init(&full_bar[s], 1); mbar_init(&empty_bar[s], 1); }
+    mbar_init(done_bar, 1);
+    asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+  }
+  if (warp == 1) {
+    asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(tmem_slot)),
+                 "r"((uint32_t)C::TMEM_COLS)
+                 : "memory");
+    asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
+  }
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  const uint32_t tmem_base = *tmem_slot;
+
+  // CTA -> (kw, ci block, co block, split)
+  int b = blockIdx.x;
+  const int split = b % a.splits; b /= a.splits;
+  const int nb = b % a.nblocks; b /= a.nblocks;
+  const int cb = b % a.cblocks; b /= a.cblocks;
+  const int fw = b;
+  const long long t_beg = (long long)split * a.tiles_per_split;
+  long long t_end = t_beg + a.tiles_per_split;
+  if (t_end > a.num_tiles) t_end = a.num_tiles;
+
+  if (warp == 0) {
+    if (lane == 0) {
+      int stage = 0;
+      uint32_t phase = 0;
+      for (long long t = t_beg; t < t_end; ++t) {
+        long long r = t;
+        const int bx = (int)(r % a.tiles_x); r /= a.tiles_x;
+        const int by = (int)(r % a.tiles_y);
+        const int img = (int)(r / a.tiles_y);
+        const int x0 = bx * TILE_W, y0 = by * TILE_H;
+        mbar_wait(&empty_bar[stage], phase ^ 1);
+        uint8_t* sa = smem + stage * C::STAGE_BYTES;
+        mbar_expect_tx(&full_bar[stage], C::STAGE_BYTES);
+        tma_load_4d(&tmap_x, &full_bar[stage], sa, cb * 128, x0 + fw - a.pad, y0 - a.pad, img);
+        tma_load_4d(&tmap_x, &full_bar[stage], sa + C::A_SLAB, cb * 128 + 64, x0 + fw - a.pad, y0 - a.pad, img);
+#pragma unroll
+        for (int j = 0; j < BN / 64; ++j)
+          tma_load_4d(&tmap_g, &full_bar[stage], sa + C::A_BYTES + j * C::G_SLAB, nb * BN + j * 64, x0, y0, img);
+        if (++stage == C::STAGES) { stage = 0; phase ^= 1; }
+      }
+    }
+  } else if (warp == 1) {
+    if (lane == 0) {
+      constexpr uint32_t idesc = umma_idesc_mn(128, BN);
+      int stage = 0;
+      uint32_t phase = 0;
+      uint32_t accumulate = 0;
+      for (long long t = t_beg; t < t_end; ++t) {
+        mbar_wait(&full_bar[stage], phase);
+        tc_fence_after();
+        const uint32_t sa = smem_u32(smem + stage * C::STAGE_BYTES);
+        const uint32_t sg = sa + C::A_BYTES;
+#pragma unroll
+        for (int kh = 0; kh < KH; ++kh) {
+#pragma unroll
+          for (int ks = 0; ks < TILE_M / 16; ++ks) {
+            umma_bf16(tmem_base + (uint32_t)(kh * BN),
+                      umma_desc_mn(sa + kh * (TILE_W * 128) + ks * 2048, C::A_SLAB),
+                      umma_desc_mn(sg + ks * 2048, C::G_SLAB), idesc, accumulate | (uint32_t)(ks > 0));
+          }
+        }
+        accumulate = 1;
+        umma_commit(&empty_bar[stage]);
+        if (++stage == C::STAGES) { stage = 0; phase ^= 1; }
+      }
+      umma_commit(done_bar);
+    }
+  } else {
+    const int q = warp & 3;
+    const int row = q * 32 + lane;
+    const int ci = cb * 128 + row;
+    mbar_wait(done_bar, 0);
+    tc_fence_after();
+    const bool has_work = t_end > t_beg;
+    const int kw_total = a.kw;
+#pragma unroll 1
+    for (int kh = 0; kh < KH; ++kh) {
+      float* dst = a.part + (((long long)split * (KH * kw_total) + (kh * kw_total + fw)) * a.cin + ci) * a.cout;
+#pragma unroll 1
+      for (int cb32 = 0; cb32 < BN; cb32 += 32) {
+        uint32_t v[32];
+        tmem_ld32(tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)(kh * BN + cb32), v);
+        const int co0 = nb * BN + cb32;
+        if (ci < a.cin && co0 < a.cout) {
+#pragma unroll
+          for (int g = 0; g < 8; ++g) {
+            float4 o;
+            o.x = has_work ? __uint_as_float(v[4 * g + 0]) : 0.f;
+            o.y = has_work ? __uint_as_float(v[4 * g + 1]) : 0.f;
+            o.z = has_work ? __uint_as_float(v[4 * g + 2]) : 0.f;
+            o.w = has_work ? __uint_as_float(v[4 * g + 3]) : 0.f;
+            if (co0 + 4 * g < a.cout) *reinterpret_cast<float4*>(dst + co0 + 4 * g) = o;
+          }
+        }
+      }
+    }
+  }
+  tc_fence_before();
+  __syncthreads();
+  if (warp == 1) {
+    asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "r"((uint32_t)C::TMEM_COLS)
+                 : "memory");
+  }
+}
+
+static void plan(const srcgan_conv_params* p, int& bn, int& cblocks, int& nblocks, int& splits, long long& tiles,
+                 long long& tps) {
+  bn = p->cout > 64 ? 128 : 64;
+  cblocks = (p->cin + 127) / 128;
+  nblocks = (p->cout + bn - 1) / bn;
+  const int tx = (p->wo + TILE_W - 1) / TILE_W, ty = (p->ho + TILE_H - 1) / TILE_H;
+  tiles = (long long)tx * ty * p->n;
+  const int groups = p->kw * cblocks * nblocks;
+  long long s = (2 * kNumSMs + groups - 1) / groups;     // ~2 CTAs per SM worth of work, 1 resident
+  if (s > tiles) s = tiles;
+  if (s < 1) s = 1;
+  tps = (tiles + s - 1) / s;
+  splits = (int)((tiles + tps - 1) / tps);
+}
+
+template <int BN, int KH>
+static int launch(const CUtensorMap& tx, const CUtensorMap& tg, const WgArgs& a, cudaStream_t st) {
+  using C = WCfg<BN, KH>;
+  static bool attr_set = false;
+  if (!attr_set) {
+    SRCGAN_CUDA(cudaFuncSetAttribute(conv_wgrad_tc_kernel<BN, KH>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                     C::SMEM_BYTES));
+    attr_set = true;
+  }
+  const unsigned grid = (unsigned)(a.kw * a.cblocks * a.nblocks * a.splits);
+  conv_wgrad_tc_kernel<BN, KH><<<grid, NUM_THREADS, C::SMEM_BYTES, st>>>(tx, tg, a);
+  count_launch();
+  return check_launch("conv_wgrad_tc");
+}
+}  // namespace tcw
+
+// shared with the SIMT engine (conv_simt.cu)
+int wgrad_reduce_launch(const float* part, int splits, int taps, int cin, int cout, float* dw, int accumulate,
+                        float alpha, cudaStream_t st);
+int bias_grad_launch(const void* dy, int dy_ld, int dtype, long long M, int cout, float* db, int accumulate,
+                     float alpha, void* ws, cudaStream_t st);
+
+bool conv_wgrad_tc_supported(const srcgan_conv_params* p) {
+  if (p->dtype != SRCGAN_DT_BF16 || p->stride != 1 || p->upsample) return false;
+  if (p->kh != p->kw || (p->kh != 3 && p->kh != 4)) return false;
+  if (p->cin < 16 || p->cin % 8 || p->cout < 16 || p->cout % 8) return false;
+  if (p->x_ld % 8 || p->y_ld % 8) return false;
+  if (((uintptr_t)p->x) % 16 || ((uintptr_t)p->y) % 16) return false;
+  return true;
+}
+
+size_t conv_wgrad_tc_workspace(const srcgan_conv_params* p) {
+  int bn, cblocks, nblocks, splits;
+  long long tiles, tps;
+  tcw::plan(p, bn, cblocks, nblocks, splits, tiles, tps);
+  size_t wbytes = (size_t)splits * p->kh * p->kw * p->cin * p->cout * sizeof(float);
+  return ((wbytes + 255) / 256) * 256 + (size_t)1024 * p->cout * sizeof(float) + 256;
+}
+
+int conv_wgrad_tc(const srcgan_conv_params* p, float* dw, float* db, int accumulate, void* ws, size_t ws_bytes,
+                  cudaStream_t st) {
+  tc::EncodeTiledFn encode = tc::get_encode_fn();
+  SRCGAN_REQUIRE(encode != nullptr, "conv_wgrad_tc: cuTensorMapEncodeTiled is not available from the driver");
+  SRCGAN_REQUIRE(ws && ws_bytes >= conv_wgrad_tc_workspace(p), "conv_wgrad_tc: workspace too small");
+  int bn, cblocks, nblocks, splits;
+  long long tiles, tps;
+  tcw::plan(p, bn, cblocks, nblocks, splits, tiles, tps);
+  const size_t wbytes = (size_t)splits * p->kh * p->kw * p->cin * p->cout * sizeof(float);
+  if (dw) {
+    CUtensorMap tx, tg;
+    cuuint32_t estr[4] = {1, 1, 1, 1};
+    {
+      cuuint64_t gdim[4] = {(cuuint64_t)p->cin, (cuuint64_t)p->w, (cuuint64_t)p->h, (cuuint64_t)p->n};
+      cuuint64_t gstr[3] = {(cuuint64_t)p->x_ld * 2, (cuuint64_t)p->x_ld * 2 * p->w,
+                            (cuuint64_t)p->x_ld * 2 * p->w * p->h};
+      cuuint32_t box[4] = {64, (cuuint32_t)tc::TILE_W, (cuuint32_t)(tc::TILE_H + p->kh - 1), 1};
+      CUresult cr = encode(&tx, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 4, const_cast<void*>(p->x), gdim, gstr, box, estr,
+                           CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B,
+                           CU_TENSOR_MAP_L2_PROMOTION_L2_256B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+      if (cr != CUDA_SUCCESS) { set_error("conv_wgrad_tc: tensor map (x) failed: CUresult %d", (int)cr); return SRCGAN_E_CUDA; }
+    }
+    {
+      cuuint64_t gdim[4] = {(cuuint64_t)p->cout, (cuuint64_t)p->wo, (cuuint64_t)p->ho, (cuuint64_t)p->n};
+      cuuint64_t gstr[3] = {(cuuint64_t)p->y_ld * 2, (cuuint64_t)p->y_ld * 2 * p->wo,
+                            (cuuint64_t)p->y_ld * 2 * p->wo * p->ho};
+      cuuint32_t box[4] = {64, (cuuint32_t)tc::TILE_W, (cuuint32_t)tc::TILE_H, 1};
+      CUresult cr = encode(&tg, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 4, p->y, gdim, gstr, box, estr,
+                           CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B,
+                           CU_TENSOR_MAP_L2_PROMOTION_L2_256B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+      if (cr != CUDA_SUCCESS) { set_error("conv_wgrad_tc: tensor map (dy) failed: CUresult %d", (int)cr); return SRCGAN_E_CUDA; }
+    }
+    tcw::WgArgs a;
+    a.n = p->n; a.ho = p->ho; a.wo = p->wo; a.cin = p->cin; a.cout = p->cout; a.pad = p->pad; a.kw = p->kw;
+    a.cblocks = cblocks; a.nblocks = nblocks; a.splits = splits;
+    a.tiles_x = (p->wo + tc::TILE_W - 1) / tc::TILE_W;
+    a.tiles_y = (p->ho + tc::TILE_H - 1) / tc::TILE_H;
+    a.num_tiles = tiles; a.tiles_per_split = tps;
+    a.part = reinterpret_cast<float*>(ws);
+    int rc;
+    if (p->kh == 3) rc = bn == 64 ? tcw::launch<64, 3>(tx, tg, a, st) : tcw::launch<128, 3>(tx, tg, a, st);
+    else rc = bn == 64 ? tcw::launch<64, 4>(tx, tg, a, st) : tcw::launch<128, 4>(tx, tg, a, st);
+    if (rc) return rc;
+    rc = wgrad_reduce_launch(reinterpret_cast<const float*>(ws), splits, p->kh * p->kw, p->cin, p->cout, dw,
+                             accumulate, p->alpha, st);
+    if (rc) return rc;
+  }
+  if (db) {
+    void* bws = reinterpret_cast<char*>(ws) + ((wbytes + 255) / 256) * 256;
+    return bias_grad_launch(p->y, p->y_ld, p->dtype, (long long)p->n * p->ho * p->wo, p->cout, db, accumulate, p->alpha,
+                            bws, st);
+  }
+  return SRCGAN_OK;
 }
 
 }  // namespace srcgan

@@ -26,7 +26,9 @@ def tc_fprop_supported(cin: int, cout: int, k: int, stride: int, upsample: bool,
 
 
 def tc_wgrad_supported(cin: int, cout: int, k: int, stride: int, upsample: bool, dtype, h: int, w: int) -> bool:
-    return False
+    """Mirror of conv_wgrad_tc_supported() in csrc/conv_tc.cu."""
+    return (dtype == torch.bfloat16 and stride == 1 and not upsample and k in (3, 4) and cin >= 16
+            and cin % 8 == 0 and cout >= 16 and cout % 8 == 0)
 
 
 def select(cin, cout, k, stride, upsample, dtype, h, w):

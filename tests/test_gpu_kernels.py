@@ -274,3 +274,37 @@ def test_conv_tc_epilogue_matches_simt():
                        engine=eng)
         outs.append(from_nhwc(ys))
     assert relerr(outs[1], outs[0]) < 1e-2
+
+
+WGRAD_TC_CASES = [
+    # n, h, w, cin, cout, k, pad
+    (2, 16, 8, 64, 64, 3, 1),
+    (2, 20, 13, 96, 32, 3, 1),
+    (1, 32, 32, 160, 32, 3, 1),
+    (2, 24, 16, 192, 64, 3, 1),
+    (1, 16, 16, 64, 128, 3, 1),
+    (1, 16, 16, 256, 128, 3, 1),
+    (1, 18, 10, 128, 256, 4, 1),
+    (4, 64, 64, 64, 64, 3, 1),       # many pixel tiles per CTA
+]
+
+
+@pytest.mark.parametrize("case", WGRAD_TC_CASES)
+def test_conv_wgrad_tc_matches_reference(case):
+    from srcgan_b200 import ops
+    n, h, w, cin, cout, k, p = case
+    x = rand((n, cin, h, w), 21).bfloat16().float()
+    wt = torch.zeros(cout, cin, k, k, requires_grad=True)
+    y = F.conv2d(x, wt, None, stride=1, padding=p)
+    gy = rand(tuple(y.shape), 22).bfloat16().float()
+    y.backward(gy)
+    xs = to_nhwc(x, torch.bfloat16, ctot=cin + 64, c0=64)
+    gys = to_nhwc(gy, torch.bfloat16, ctot=cout + 32, c0=32) if cout % 64 else to_nhwc(gy, torch.bfloat16, ctot=cout + 64, c0=0)
+    dw = torch.empty((cout, cin, k, k), device=DEV)
+    db = torch.empty((cout,), device=DEV)
+    ops.conv_wgrad(xs, gys, dw, db, k, 1, p, engine=ops.ENGINE_TC)
+    torch.cuda.synchronize()
+    assert relerr(dw.cpu(), wt.grad) < 5e-3, relerr(dw.cpu(), wt.grad)
+    assert relerr(db.cpu(), gy.sum((0, 2, 3))) < 5e-3
+    ops.conv_wgrad(xs, gys, dw, db, k, 1, p, engine=ops.ENGINE_TC, accumulate=True, alpha=0.5)
+    assert relerr(dw.cpu(), 1.5 * wt.grad) < 5e-3
