@@ -117,6 +117,9 @@ int srcgan_nhwc_to_nchw(const void* src, int src_ld, int dtype, float* dst, int 
 int srcgan_add(const void* a, int a_ld, const void* b, int b_ld, void* dst, int dst_ld, int64_t npix, int c, int dtype,
                void* stream);
 
+/* dst[n,2h,2w,c] = nearest x2 of src[n,h,w,c]  (F.interpolate(scale_factor=2, 'nearest'), model.py:426-427) */
+int srcgan_upsample2x(const void* src, int src_ld, void* dst, int dst_ld, int n, int h, int w, int c, int dtype,
+                      void* stream);
 /* dst[n,h,w,c] = (sum of the 2x2 block of src[n,2h,2w,c]) * (mask>0 ? 1 : mask_slope); mask may be NULL */
 int srcgan_upsample2x_adjoint(const void* src, int src_ld, void* dst, int dst_ld, const void* mask, int mask_ld,
                               float mask_slope, int n, int h, int w, int c, int dtype, void* stream);

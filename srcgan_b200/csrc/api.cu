@@ -47,6 +47,8 @@ int conv_wgrad_tc(const srcgan_conv_params* p, float* dw, float* db, int accumul
 // other kernels
 int nchw_to_nhwc(const float* src, int n, int c, int h, int w, void* dst, int ld, int dtype, cudaStream_t st);
 int nhwc_to_nchw(const void* src, int ld, int dtype, float* dst, int n, int c, int h, int w, cudaStream_t st);
+int upsample2x(const void* src, int src_ld, void* dst, int dst_ld, int n, int h, int w, int c, int dtype,
+               cudaStream_t st);
 int upsample2x_adjoint(const void* src, int src_ld, void* dst, int dst_ld, const void* mask, int mask_ld,
                        float mslope, int n, int h, int w, int c, int dtype, cudaStream_t st);
 int add_slices(const void* a, int a_ld, const void* b, int b_ld, void* d, int d_ld, int64_t npix, int c, int dtype,
@@ -144,6 +146,11 @@ int srcgan_nchw_to_nhwc(const float* src, int n, int c, int h, int w, void* dst,
 int srcgan_nhwc_to_nchw(const void* src, int src_ld, int dtype, float* dst, int n, int c, int h, int w, void* stream) {
   SRCGAN_REQUIRE(src && dst && n > 0 && c > 0 && h > 0 && w > 0 && src_ld >= c, "nhwc_to_nchw: bad arguments");
   return nhwc_to_nchw(src, src_ld, dtype, dst, n, c, h, w, (cudaStream_t)stream);
+}
+int srcgan_upsample2x(const void* src, int src_ld, void* dst, int dst_ld, int n, int h, int w, int c, int dtype,
+                      void* stream) {
+  SRCGAN_REQUIRE(src && dst && n > 0 && c > 0 && h > 0 && w > 0, "upsample2x: bad arguments");
+  return upsample2x(src, src_ld, dst, dst_ld, n, h, w, c, dtype, (cudaStream_t)stream);
 }
 int srcgan_upsample2x_adjoint(const void* src, int src_ld, void* dst, int dst_ld, const void* mask, int mask_ld,
                               float mask_slope, int n, int h, int w, int c, int dtype, void* stream) {

@@ -88,6 +88,35 @@ __global__ void upsample2x_adjoint_k(const T* __restrict__ src, int src_ld, T* _
   dst[p * dst_ld + ch] = from_f32<T>(v);
 }
 
+// nearest x2 upsampling, 16-byte vectors: dst[n,2y+a,2x+b,:] = src[n,y,x,:]
+__global__ void upsample2x_vec(const uint4* __restrict__ src, int src_ld16, uint4* __restrict__ dst, int dst_ld16, int n,
+                               int h, int w, int c16) {
+  int64_t total = (int64_t)n * 2 * h * 2 * w * c16;
+  int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= total) return;
+  int v = (int)(i % c16);
+  int64_t p = i / c16;
+  int X = (int)(p % (2 * w));
+  int64_t t = p / (2 * w);
+  int Y = (int)(t % (2 * h));
+  int64_t b = t / (2 * h);
+  dst[p * dst_ld16 + v] = __ldg(src + ((b * h + (Y >> 1)) * w + (X >> 1)) * src_ld16 + v);
+}
+
+int upsample2x(const void* src, int src_ld, void* dst, int dst_ld, int n, int h, int w, int c, int dtype,
+               cudaStream_t st) {
+  const int es = dtype == SRCGAN_DT_F32 ? 4 : 2;
+  const int per16 = 16 / es;
+  SRCGAN_REQUIRE(c % per16 == 0 && src_ld % per16 == 0 && dst_ld % per16 == 0 && ((uintptr_t)src % 16 == 0) &&
+                     ((uintptr_t)dst % 16 == 0),
+                 "upsample2x: channels / strides must be multiples of 16 bytes");
+  int64_t total = (int64_t)n * 4 * h * w * (c / per16);
+  upsample2x_vec<<<ceil_div(total, 256), 256, 0, st>>>((const uint4*)src, src_ld / per16, (uint4*)dst, dst_ld / per16, n,
+                                                       h, w, c / per16);
+  count_launch();
+  return check_launch("upsample2x");
+}
+
 template <typename T>
 __global__ void add_k(const T* __restrict__ a, int a_ld, const T* __restrict__ b, int b_ld, T* __restrict__ d, int d_ld,
                       int64_t npix, int c) {

@@ -370,12 +370,21 @@ class RDDBNetB(_RRDBGenerator):
         ops.nchw_to_nhwc(x, x_in)
         cur = self._trunk_forward(x_in, st)
         acts = [cur]
-        for conv, up in self._stages():
+        ups = {}            # stage index -> materialised nearest-x2 input (bf16 mode: keeps the conv on tcgen05)
+        materialise = dt == torch.bfloat16
+        for i, (conv, up) in enumerate(self._stages()):
             hh, ww = (cur.h * 2, cur.w * 2) if up else (cur.h, cur.w)
             nxt = Slice(ops.new_buf(n, hh, ww, self.nf, dt, dev))
-            self._fprop(conv, cur, nxt, upsample=up, act=LRELU)
+            if up and materialise:
+                big = Slice(ops.new_buf(n, hh, ww, self.nf, dt, dev))
+                ops.upsample2x(cur, big)
+                ups[i] = big
+                self._fprop(conv, big, nxt, act=LRELU)
+            else:
+                self._fprop(conv, cur, nxt, upsample=up, act=LRELU)
             acts.append(nxt)
             cur = nxt
+        st["ups"] = ups
         out = Slice(ops.new_buf(n, cur.h, cur.w, self.conv_last.out_channels, dt, dev))
         self._fprop(self.conv_last, cur, out)
         st["acts"] = acts
@@ -397,7 +406,10 @@ class RDDBNetB(_RRDBGenerator):
         for i in range(len(stages) - 1, -1, -1):
             conv, up = stages[i]
             src = acts[i]
-            self._wgrad(conv, src, gz, sink, W(conv.weight), W(conv.bias), upsample=up)
+            if i in st["ups"]:
+                self._wgrad(conv, st["ups"][i], gz, sink, W(conv.weight), W(conv.bias))
+            else:
+                self._wgrad(conv, src, gz, sink, W(conv.weight), W(conv.bias), upsample=up)
             mask = src if i > 0 else None                    # acts[0] = fea2 is not an activation output
             if up:
                 full = Slice(ops.new_buf(n, gz.h, gz.w, self.nf, dt, dev))

@@ -262,6 +262,12 @@ def add(a: Slice, b: Slice, dst: Slice) -> None:
                                       _stream()), "add")
 
 
+def upsample2x(src: Slice, dst: Slice) -> None:
+    assert dst.h == 2 * src.h and dst.w == 2 * src.w and src.c == dst.c
+    _lib.check(_lib.load().srcgan_upsample2x(src.ptr, src.ld, dst.ptr, dst.ld, src.n, src.h, src.w, src.c,
+                                             dt_code(dst.dtype), _stream()), "upsample2x")
+
+
 def upsample2x_adjoint(src: Slice, dst: Slice, mask: Optional[Slice] = None, mask_slope: float = 0.0) -> None:
     assert src.h == 2 * dst.h and src.w == 2 * dst.w and src.c == dst.c
     _lib.check(_lib.load().srcgan_upsample2x_adjoint(

@@ -1,0 +1,164 @@
+"""CPU-side checks: the C-ABI library loads and exports every symbol include/srcgan_b200.h declares,
+the host logic (packed-weight caches, engine selection, drop-in modules, data-parallel helpers) works
+without a GPU, and the product path refuses CPU tensors instead of falling back."""
+import os
+import re
+import subprocess
+import sys
+
+import pytest
+import torch
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+
+
+def header_symbols():
+    src = open(os.path.join(ROOT, "include", "srcgan_b200.h")).read()
+    src = re.sub(r"/\*.*?\*/", "", src, flags=re.S)
+    return sorted(set(re.findall(r"\b(srcgan_[a-z0-9_]+)\s*\(", src)))
+
+
+def test_library_exports_every_declared_symbol():
+    from srcgan_b200 import _lib
+    lib = _lib.load()
+    declared = header_symbols()
+    assert len(declared) >= 25
+    for name in declared:
+        assert hasattr(lib, name), name
+    assert set(declared) == set(_lib.SIGNATURES), set(declared) ^ set(_lib.SIGNATURES)
+    assert b"sm_100a" in lib.srcgan_version()
+
+
+def test_conv_params_struct_matches_header():
+    import ctypes as C
+    from srcgan_b200._lib import ConvParams
+    src = open(os.path.join(ROOT, "include", "srcgan_b200.h")).read()
+    body = src[src.index("typedef struct srcgan_conv_params {"):src.index("} srcgan_conv_params;")]
+    fields = re.findall(r"(?:int32_t|float|const void\*|const float\*|void\*)\s+([a-z0-9_, ]+);", body)
+    names = [n.strip() for grp in fields for n in grp.split(",")]
+    assert names == [f[0] for f in ConvParams._fields_]
+    assert C.sizeof(ConvParams) % 8 == 0
+
+
+def test_argument_validation_without_gpu():
+    """Bad arguments are rejected with an error code + message before any CUDA call."""
+    import ctypes as C
+    from srcgan_b200 import _lib
+    lib = _lib.load()
+    p = _lib.ConvParams()
+    rc = lib.srcgan_conv_fprop(C.byref(p), None)
+    assert rc == 1 and b"conv" in lib.srcgan_last_error()
+    with pytest.raises(RuntimeError, match="non-positive"):
+        _lib.check(rc, "conv_fprop")
+    assert lib.srcgan_pack_weights(None, 1, 1, 3, 3, 0, 0, None, None) == 1
+
+
+def test_missing_library_fails_loudly(tmp_path, monkeypatch):
+    from srcgan_b200 import _lib
+    monkeypatch.setattr(_lib, "_lib", None)
+    monkeypatch.setattr(_lib, "LIB_PATH", str(tmp_path / "nope.so"))
+    with pytest.raises(RuntimeError, match="no CPU fallback"):
+        _lib.load()
+
+
+def test_networks_refuse_cpu_tensors():
+    from srcgan_b200 import losses, nn as snn
+    for net, shape in ((snn.NLayerDiscriminator(3, 64, 2), (1, 3, 32, 32)),
+                       (snn.RDDBNetB(3, 3, 64, nb=1, mode="x4"), (1, 3, 8, 8))):
+        with pytest.raises(RuntimeError, match="no CPU"):
+            net(torch.rand(*shape))
+    with pytest.raises(RuntimeError, match="no CPU"):
+        losses.L1Loss()(torch.rand(4), torch.rand(4))
+
+
+def test_state_dict_compatibility_with_oracle_layout():
+    from oracle import srcgan_oracle as O
+    from srcgan_b200 import nn as snn
+    g = snn.RDDBNetB(3, 3, 64, nb=3, mode="x4")
+    assert list(g.state_dict().keys()) == list(O.init_rddbnet_b(0).keys())
+    g.load_state_dict(O.init_rddbnet_b(3), strict=True)
+    a = snn.RDDBNetA(3, 3, 64, nb=3, mode="x4")
+    a.load_state_dict(O.init_rddbnet_a(3), strict=True)
+    d = snn.NLayerDiscriminator(3, 64, 2)
+    d.load_state_dict(O.init_discriminator(3), strict=True)
+    assert sum(p.numel() for p in g.parameters()) == 2309507
+    assert sum(p.numel() for p in a.parameters()) == 3195715
+    assert sum(p.numel() for p in d.parameters()) == 663361
+
+
+def test_dense_block_transposed_weights_are_the_adjoint():
+    """Host logic of the mirrored dense block: step-k virtual weights reproduce autograd's input
+    gradient of the reference dense block (checked with torch on the CPU)."""
+    import torch.nn.functional as F
+    from oracle import srcgan_oracle as O
+    from srcgan_b200.nn import _wT
+    torch.manual_seed(0)
+    nf, gc = 16, 8
+    ws = [torch.randn(gc if k < 5 else nf, nf + gc * (k - 1), 3, 3) * 0.1 for k in range(1, 6)]
+    x = torch.randn(1, nf, 6, 5, requires_grad=True)
+    feats = [x]
+    for k in range(4):
+        feats.append(F.leaky_relu(F.conv2d(torch.cat(feats, 1), ws[k], padding=1), 0.2))
+    out = F.conv2d(torch.cat(feats, 1), ws[4], padding=1) * 0.2 + x
+    g = torch.randn_like(out)
+    out.backward(g)
+    # mirrored pass
+    D = [g]                                     # [dOut, dZ4, dZ3, dZ2, dZ1]
+    for k in (4, 3, 2, 1):
+        sl = slice(nf + gc * (k - 1), nf + gc * k)
+        blocks = [_wT(ws[4][:, sl]) * 0.2] + [_wT(ws[j - 1][:, sl]) for j in range(4, k, -1)]
+        d = F.conv2d(torch.cat(D, 1), torch.cat(blocks, 1), padding=1)
+        mask = torch.where(feats[k] > 0, torch.ones_like(d), torch.full_like(d, 0.2))
+        D.append(d * mask)
+    blocks = [_wT(ws[4][:, :nf]) * 0.2] + [_wT(ws[j - 1][:, :nf]) for j in range(4, 0, -1)]
+    dx = F.conv2d(torch.cat(D, 1), torch.cat(blocks, 1), padding=1) + g
+    assert torch.allclose(dx, x.grad, rtol=1e-4, atol=1e-5)
+
+
+def test_engine_selection():
+    from srcgan_b200 import engine
+    from srcgan_b200._lib import ENGINE_SIMT, ENGINE_TC, WL_RSCK, WL_TC
+    bf, f32 = torch.bfloat16, torch.float32
+    assert engine.select(64, 32, 3, 1, False, bf, 64, 64) == (ENGINE_TC, WL_TC)
+    assert engine.select(64, 32, 3, 1, False, f32, 64, 64) == (ENGINE_SIMT, WL_RSCK)      # fp32 parity mode
+    assert engine.select(3, 64, 3, 1, False, bf, 64, 64) == (ENGINE_SIMT, WL_RSCK)        # thin image conv
+    assert engine.select(64, 3, 3, 1, False, bf, 64, 64)[0] == ENGINE_SIMT
+    assert engine.select_wgrad(192, 64, 3, 1, False, bf, 64, 64) == ENGINE_TC
+    assert engine.select_wgrad(3, 64, 3, 1, False, bf, 64, 64) == ENGINE_SIMT
+
+
+def test_dropin_modules_resolve_reference_imports():
+    """`from model import RDDBNetA, RDDBNetB, NLayerDiscriminator, ...` (train.py:11), `import losses`,
+    `import metrics` resolve to this package when srcgan_b200/dropin is first on the path."""
+    code = (
+        "import sys; sys.path.insert(0, %r);"
+        "from model import RDDBNetA, RDDBNetB, NLayerDiscriminator, SRDenseNetA, SRDenseNetB;"
+        "import losses, metrics;"
+        "assert RDDBNetB.__module__ == 'srcgan_b200.nn';"
+        "assert repr(losses.L1Loss()) == 'L1' and repr(metrics.SSIM()) == 'SSIM' and repr(metrics.AE()) == 'AE';"
+        "assert repr(losses.PSNRLoss()) == 'PSNR' and repr(losses.MSELoss()) == 'MSE';"
+        "print('ok')" % os.path.join(ROOT, "srcgan_b200", "dropin"))
+    out = subprocess.run([sys.executable, "-c", code], capture_output=True, text=True, cwd="/tmp")
+    assert out.returncode == 0 and "ok" in out.stdout, out.stderr[-2000:]
+
+
+@pytest.mark.skipif(not os.path.isdir("/root/reference/src"), reason="reference tree not on this box")
+def test_reference_train_script_constructs_on_the_dropin():
+    """The reference's UNMODIFIED train.py imports and builds SRCycleGAN on the drop-in modules
+    (visdom / skimage / dataset are stubbed: they are I/O, outside the hot path)."""
+    code = (
+        "import sys, types, torch;"
+        "sys.path.insert(0, '/root/reference/src'); sys.path.insert(0, %r);"
+        "sys.modules['visdom'] = types.SimpleNamespace(Visdom=lambda *a, **k: None);"
+        "sk = types.ModuleType('skimage'); sk.io = types.ModuleType('skimage.io'); sk.color = types.ModuleType('skimage.color');"
+        "sk.color.lab2rgb = sk.color.rgb2lab = sk.color.rgb2gray = None; sk.io.imsave = sk.io.imread = None;"
+        "sys.modules.update({'skimage': sk, 'skimage.io': sk.io, 'skimage.color': sk.color});"
+        "import train;"
+        "opt = train.params(); opt.device = torch.device('cpu'); opt.mode = 'x4';"
+        "m = train.SRCycleGAN(opt);"
+        "assert type(m.netG_A).__module__ == 'srcgan_b200.nn' and type(m.netD_A).__module__ == 'srcgan_b200.nn';"
+        "assert type(m.criterionCycle).__module__ == 'srcgan_b200.losses';"
+        "assert len(m.optimizer_G.param_groups[0]['params']) == 102 + 118;"
+        "print('ok')" % os.path.join(ROOT, "srcgan_b200", "dropin"))
+    out = subprocess.run([sys.executable, "-W", "ignore", "-c", code], capture_output=True, text=True, cwd="/tmp")
+    assert out.returncode == 0 and "ok" in out.stdout, out.stderr[-3000:]
