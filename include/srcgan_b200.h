@@ -44,7 +44,9 @@ extern "C" {
 /* packed-weight layouts produced by srcgan_pack_weights from fp32 OIHW */
 #define SRCGAN_WL_RSCK 0        /* [kh][kw][cin][cout]  - fprop, SIMT engine             */
 #define SRCGAN_WL_RSKC 1        /* [kh][kw][cout][cin]  - dgrad, SIMT engine             */
-#define SRCGAN_WL_TC   2        /* tcgen05 engine: [cin/64][kw][kh][cout][64] bf16 K-major */
+#define SRCGAN_WL_TC   2        /* tcgen05 engine, stride 1: [cout/BN][cin/64][kw][kh][BN][64] bf16, pre-swizzled */
+#define SRCGAN_WL_TC_S2 3       /* tcgen05 engine, stride-2 fprop (taps grouped by row parity)                  */
+#define SRCGAN_WL_TC_DGRAD_S2 4 /* tcgen05 engine, stride-2 dgrad (pad 1): four output-phase packs, transposed  */
 
 #define SRCGAN_ENGINE_AUTO 0
 #define SRCGAN_ENGINE_SIMT 1    /* fp32-accumulating FFMA implicit GEMM (fp32 parity mode) */
@@ -59,6 +61,8 @@ extern "C" {
  * ho = (h*(upsample?2:1) + 2*pad - kh)/stride + 1.
  *   fprop : reads x (=X) and wgt, writes y (=Y).
  *   dgrad : reads x (=dY, ho x wo x cout), writes y (=dX, h x w x cin); upsample must be 0.
+ *           (SIMT engine: any stride, RSKC weights.  tcgen05 engine: stride 2 only, TC_DGRAD_S2 weights;
+ *           a stride-1 dgrad on tcgen05 is an fprop over transposed+rotated weights.)
  *   wgrad : reads x (=X) and y (=dY); writes alpha * (the fp32 OIHW gradient) passed separately.
  * Epilogue applied to each written element v (fprop and dgrad):
  *   v = acc + bias[c];  if (act) v = v > 0 ? v : act_slope*v;

@@ -13,7 +13,7 @@ _HERE = os.path.dirname(os.path.abspath(__file__))
 LIB_PATH = os.path.join(_HERE, "lib", "libsrcgan_b200.so")
 
 DT_F32, DT_BF16 = 0, 1
-WL_RSCK, WL_RSKC, WL_TC = 0, 1, 2
+WL_RSCK, WL_RSKC, WL_TC, WL_TC_S2, WL_TC_DGRAD_S2 = 0, 1, 2, 3, 4
 ENGINE_AUTO, ENGINE_SIMT, ENGINE_TC = 0, 1, 2
 
 

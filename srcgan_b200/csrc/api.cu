@@ -38,8 +38,10 @@ int pack_weights_simt_host(const float* w, int cout, int cin, int kh, int kw, in
                            cudaStream_t st);
 bool conv_tc_supported(const srcgan_conv_params* p);
 int conv_fprop_tc(const srcgan_conv_params* p, cudaStream_t st);
-int pack_weights_tc_host(const float* w, int cout, int cin, int kh, int kw, void* out, cudaStream_t st);
-size_t packed_weight_bytes_tc(int cout, int cin, int kh, int kw);
+int pack_weights_tc_host(const float* w, int cout, int cin, int kh, int kw, int layout, void* out, cudaStream_t st);
+size_t packed_weight_bytes_tc(int cout, int cin, int kh, int kw, int layout);
+bool conv_dgrad_tc_supported(const srcgan_conv_params* p);
+int conv_dgrad_tc(const srcgan_conv_params* p, cudaStream_t st);
 bool conv_wgrad_tc_supported(const srcgan_conv_params* p);
 size_t conv_wgrad_tc_workspace(const srcgan_conv_params* p);
 int conv_wgrad_tc(const srcgan_conv_params* p, float* dw, float* db, int accumulate, void* ws, size_t ws_bytes,
@@ -83,16 +85,16 @@ const char* srcgan_last_error(void) { return g_err; }
 int64_t srcgan_launch_count(void) { return g_launches.load(std::memory_order_relaxed); }
 
 size_t srcgan_packed_weight_bytes(int cout, int cin, int kh, int kw, int layout, int dtype) {
-  if (layout == SRCGAN_WL_TC) return packed_weight_bytes_tc(cout, cin, kh, kw);
+  if (layout >= SRCGAN_WL_TC) return packed_weight_bytes_tc(cout, cin, kh, kw, layout);
   return (size_t)cout * cin * kh * kw * (dtype == SRCGAN_DT_F32 ? 4 : 2);
 }
 
 int srcgan_pack_weights(const float* w, int cout, int cin, int kh, int kw, int layout, int dtype, void* out,
                         void* stream) {
   SRCGAN_REQUIRE(w && out && cout > 0 && cin > 0 && kh > 0 && kw > 0, "pack_weights: bad arguments");
-  if (layout == SRCGAN_WL_TC) {
-    SRCGAN_REQUIRE(dtype == SRCGAN_DT_BF16, "pack_weights: the tcgen05 layout is bf16 only");
-    return pack_weights_tc_host(w, cout, cin, kh, kw, out, (cudaStream_t)stream);
+  if (layout >= SRCGAN_WL_TC) {
+    SRCGAN_REQUIRE(dtype == SRCGAN_DT_BF16, "pack_weights: the tcgen05 layouts are bf16 only");
+    return pack_weights_tc_host(w, cout, cin, kh, kw, layout, out, (cudaStream_t)stream);
   }
   SRCGAN_REQUIRE(layout == SRCGAN_WL_RSCK || layout == SRCGAN_WL_RSKC, "pack_weights: unknown layout %d", layout);
   return pack_weights_simt_host(w, cout, cin, kh, kw, layout, dtype, out, (cudaStream_t)stream);
@@ -113,8 +115,11 @@ int srcgan_conv_fprop(const srcgan_conv_params* p, void* stream) {
 int srcgan_conv_dgrad(const srcgan_conv_params* p, void* stream) {
   int rc = validate_conv(p, true);
   if (rc) return rc;
-  SRCGAN_REQUIRE(p->engine != SRCGAN_ENGINE_TC,
-                 "conv_dgrad: the tcgen05 engine takes dgrad as an fprop over transposed weights");
+  if (p->engine == SRCGAN_ENGINE_TC) {
+    SRCGAN_REQUIRE(conv_dgrad_tc_supported(p),
+                   "conv_dgrad: tcgen05 engine handles stride-2 dgrad only (stride 1 = fprop over transposed weights)");
+    return conv_dgrad_tc(p, (cudaStream_t)stream);
+  }
   return conv_dgrad_simt(p, (cudaStream_t)stream);
 }
 

@@ -1,6 +1,6 @@
 // tcgen05 / TMEM / TMA implicit-GEMM convolution engine for sm_100a (bf16 in, fp32 accumulate).
 //
-//   Y[n,y,x,co] = epilogue( sum_{kh,kw,ci} X[n, y+kh-pad, x+kw-pad, ci] * W[co,ci,kh,kw] )     stride 1
+//   Y[n,y,x,co] = epilogue( sum_{kh,kw,ci} X[n, s*y+kh-pad, s*x+kw-pad, ci] * W[co,ci,kh,kw] )   s = 1, 2
 //
 // GEMM view: M = output pixels (one CTA tile = 16 rows x 8 columns = 128 pixels = UMMA M),
 //            N = output channels (BN = 32/64/128 per tile), K = taps x input channels.
@@ -34,8 +34,23 @@ constexpr int NUM_THREADS = 192;        // warp0 TMA, warp1 MMA, warps 2..5 epil
 constexpr int SMEM_BUDGET = 227 * 1024;
 constexpr int SMEM_AUX = 2048;          // barriers + tmem ptr + bias
 
+// A "load" is one TMA box of the (possibly stride-sampled) input: [16+MAXT-1 rows][8 px][64 ch].
+// The taps that differ only by a row shift share it (tap j reads the slab shifted by j rows = j*1024 B).
+//   stride 1, KxK : K loads (one per kw), K taps each (kh)
+//   stride 2, KxK : the box samples every 2nd pixel (tensor-map elementStrides = 2); taps whose kh have
+//                   the same parity share a load: 3x3 -> 6 loads (2+1 taps), 4x4 -> 8 loads (2 taps)
+//   stride-2 dgrad: four output phases, each a stride-1 conv over dY with 1x1 / 1x2 / 2x1 / 2x2 taps
+constexpr int MAX_LOADS = 8, MAX_SLOTS = 16;
+struct Plan {
+  int nloads, total_slots, in_scale;     // slab origin = in_scale * (x0, y0) + (dx, dy)
+  int dx[MAX_LOADS], dy[MAX_LOADS], ntaps[MAX_LOADS], slot0[MAX_LOADS];
+};
+
 struct TcArgs {
-  int n, h, w, cin, cout, pad;
+  int n, cin, cout;
+  int gh, gw;                           // extent of the tile grid (output positions of this launch)
+  int oh, ow, os, oa, ob;               // output tensor dims; position (y,x) is written at (y*os+oa, x*os+ob)
+  Plan plan;
   int nchunks, n_blocks;                // K chunks of 64 channels; N blocks of BN channels
   int tiles_x, tiles_y;
   long long num_tiles;
@@ -145,11 +160,11 @@ __device__ __forceinline__ void unpack8(const uint4& q, float (&f)[8]) {
   for (int i = 0; i < 4; ++i) { f[2 * i] = __low2float(h[i]); f[2 * i + 1] = __high2float(h[i]); }
 }
 
-template <int BN, int KH, int KW>
+template <int BN, int MAXT>
 struct Cfg {
-  static constexpr int A_BYTES = (TILE_H + KH - 1) * TILE_W * 128;
+  static constexpr int A_BYTES = (TILE_H + MAXT - 1) * TILE_W * 128;
   static constexpr int B_TAP_BYTES = BN * 128;
-  static constexpr int B_BYTES = KH * B_TAP_BYTES;
+  static constexpr int B_BYTES = MAXT * B_TAP_BYTES;
   static constexpr int STAGE_BYTES = A_BYTES + B_BYTES;
   static constexpr int STAGES_RAW = (SMEM_BUDGET - SMEM_AUX - 1024) / STAGE_BYTES;
   static constexpr int STAGES = STAGES_RAW > 8 ? 8 : STAGES_RAW;
@@ -159,10 +174,10 @@ struct Cfg {
   static_assert(STAGES >= 2, "not enough shared memory for a pipeline");
 };
 
-template <int BN, int KH, int KW>
+template <int BN, int MAXT>
 __global__ void __launch_bounds__(NUM_THREADS, 1)
 conv_igemm_tc(const __grid_constant__ CUtensorMap tmap_x, const TcArgs a) {
-  using C = Cfg<BN, KH, KW>;
+  using C = Cfg<BN, MAXT>;
   extern __shared__ uint8_t smem_raw[];
   uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~(uintptr_t)1023);
   uint8_t* aux = smem + C::STAGES * C::STAGE_BYTES;
@@ -192,8 +207,6 @@ conv_igemm_tc(const __grid_constant__ CUtensorMap tmap_x, const TcArgs a) {
   tc_fence_after();
   const uint32_t tmem_base = *tmem_slot;
 
-  const int per_img = a.tiles_x * a.tiles_y;
-
   if (warp == 0) {
     // ------------------------------------------------------------------ TMA producer
     if (lane == 0) {
@@ -207,14 +220,16 @@ conv_igemm_tc(const __grid_constant__ CUtensorMap tmap_x, const TcArgs a) {
         const int img = (int)(r / a.tiles_y);
         const int x0 = bx * TILE_W, y0 = by * TILE_H;
         for (int c = 0; c < a.nchunks; ++c) {
-          for (int s = 0; s < KW; ++s) {
+          for (int l = 0; l < a.plan.nloads; ++l) {
             mbar_wait(&empty_bar[stage], phase ^ 1);
             uint8_t* sa = smem + stage * C::STAGE_BYTES;
-            mbar_expect_tx(&full_bar[stage], C::STAGE_BYTES);
-            tma_load_4d(&tmap_x, &full_bar[stage], sa, c * KCH, x0 + s - a.pad, y0 - a.pad, img);
+            const uint32_t bbytes = (uint32_t)(a.plan.ntaps[l] * C::B_TAP_BYTES);
+            mbar_expect_tx(&full_bar[stage], C::A_BYTES + bbytes);
+            tma_load_4d(&tmap_x, &full_bar[stage], sa, c * KCH, a.plan.in_scale * x0 + a.plan.dx[l],
+                        a.plan.in_scale * y0 + a.plan.dy[l], img);
             const __nv_bfloat16* wsrc =
-                a.wgt + ((((size_t)nb * a.nchunks + c) * KW + s) * KH) * (size_t)(BN * KCH);
-            bulk_load(wsrc, &full_bar[stage], sa + C::A_BYTES, C::B_BYTES);
+                a.wgt + (((size_t)nb * a.nchunks + c) * a.plan.total_slots + a.plan.slot0[l]) * (size_t)(BN * KCH);
+            bulk_load(wsrc, &full_bar[stage], sa + C::A_BYTES, bbytes);
             if (++stage == C::STAGES) { stage = 0; phase ^= 1; }
           }
         }
@@ -236,16 +251,16 @@ conv_igemm_tc(const __grid_constant__ CUtensorMap tmap_x, const TcArgs a) {
         for (int c = 0; c < a.nchunks; ++c) {
           const int rem = a.cin - c * KCH;
           const int ksteps = (rem >= KCH ? KCH : rem) >> 4;
-          for (int s = 0; s < KW; ++s) {
+          for (int l = 0; l < a.plan.nloads; ++l) {
             mbar_wait(&full_bar[stage], phase);
             tc_fence_after();
             const uint32_t sa = smem_u32(smem + stage * C::STAGE_BYTES);
             const uint32_t sb = sa + C::A_BYTES;
-#pragma unroll
-            for (int kh = 0; kh < KH; ++kh) {
+            const int nt = a.plan.ntaps[l];
+            for (int j = 0; j < nt; ++j) {
               for (int ks = 0; ks < ksteps; ++ks) {
-                umma_bf16(tmem_d, umma_desc(sa + kh * (TILE_W * 128) + ks * 32),
-                          umma_desc(sb + kh * C::B_TAP_BYTES + ks * 32), idesc, accumulate);
+                umma_bf16(tmem_d, umma_desc(sa + j * (TILE_W * 128) + ks * 32),
+                          umma_desc(sb + j * C::B_TAP_BYTES + ks * 32), idesc, accumulate);
                 accumulate = 1;
               }
             }
@@ -271,8 +286,8 @@ conv_igemm_tc(const __grid_constant__ CUtensorMap tmap_x, const TcArgs a) {
       const int by = (int)(r % a.tiles_y);
       const int img = (int)(r / a.tiles_y);
       const int y = by * TILE_H + ty, x = bx * TILE_W + tx;
-      const bool valid = (y < a.h) && (x < a.w);
-      const long long pix = ((long long)img * a.h + y) * a.w + x;
+      const bool valid = (y < a.gh) && (x < a.gw);
+      const long long pix = ((long long)img * a.oh + (y * a.os + a.oa)) * a.ow + (x * a.os + a.ob);
       mbar_wait(&tfull_bar[acc], acc_phase);
       tc_fence_after();
       const uint32_t taddr = tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)(acc * BN);
@@ -332,23 +347,27 @@ conv_igemm_tc(const __grid_constant__ CUtensorMap tmap_x, const TcArgs a) {
   }
 }
 
-// fp32 OIHW -> bf16 [n_block][chunk][kw][kh][BN][64], each [BN][64] tile stored as its SWIZZLE_128B
-// shared-memory image (16-byte chunk j of row r lives at chunk j ^ (r & 7)); zero padded in K.
-__global__ void pack_weights_tc(const float* __restrict__ w, int cout, int cin, int kh, int kw, int bn, int nchunks,
-                                __nv_bfloat16* __restrict__ out) {
-  const long long total = (long long)(cout / bn) * nchunks * kw * kh * bn * KCH;
+// fp32 OIHW -> bf16 [n_block][chunk][slot][BN][64]: each [BN][64] tile is stored as its SWIZZLE_128B
+// shared-memory image (16-byte chunk j of row r lives at chunk j ^ (r & 7)), zero padded in K.
+// Rows are the GEMM-N channels, columns the GEMM-K channels: (co, ci) for fprop, (ci, co) for dgrad.
+struct PackArgs {
+  int n_total, k_total, bn, nchunks, total_slots;
+  long long nstride, kstride;            // element strides of the N / K channel index in the OIHW tensor
+  int slot_off[MAX_SLOTS];               // kh*KW + kw of each slot
+};
+__global__ void pack_weights_tc(const float* __restrict__ w, const PackArgs a, __nv_bfloat16* __restrict__ out) {
+  const long long total = (long long)(a.n_total / a.bn) * a.nchunks * a.total_slots * a.bn * KCH;
   long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
   if (i >= total) return;
   const int j = (int)(i % KCH);
   long long t = i / KCH;
-  const int r = (int)(t % bn); t /= bn;
-  const int fh = (int)(t % kh); t /= kh;
-  const int fw = (int)(t % kw); t /= kw;
-  const int c = (int)(t % nchunks);
-  const int nb = (int)(t / nchunks);
-  const int co = nb * bn + r, ci = c * KCH + j;
+  const int r = (int)(t % a.bn); t /= a.bn;
+  const int slot = (int)(t % a.total_slots); t /= a.total_slots;
+  const int c = (int)(t % a.nchunks);
+  const int nb = (int)(t / a.nchunks);
+  const int nch = nb * a.bn + r, kch = c * KCH + j;
   float v = 0.f;
-  if (ci < cin) v = w[(((long long)co * cin + ci) * kh + fh) * kw + fw];
+  if (kch < a.k_total) v = w[nch * a.nstride + kch * a.kstride + a.slot_off[slot]];
   const long long tile = i - (long long)r * KCH - j;   // start of this [BN][64] tile
   const int chunk16 = (j >> 3) ^ (r & 7);
   out[tile + (long long)r * KCH + chunk16 * 8 + (j & 7)] = __float2bfloat16_rn(v);
@@ -371,30 +390,140 @@ static EncodeTiledFn get_encode_fn() {
   return fn;
 }
 
+// NHWC bf16 tensor (c channels at ptr, pixel pitch ld) -> tensor map whose box is the sampled slab
+// [rows][8 px][64 ch]; sample = 1 (dense) or 2 (every other pixel, for stride-2 convolutions).
+static int make_tmap(CUtensorMap* tm, const void* ptr, int c, int w, int h, int n, int ld, int rows, int sample,
+                     const char* what) {
+  EncodeTiledFn encode = get_encode_fn();
+  SRCGAN_REQUIRE(encode != nullptr, "%s: cuTensorMapEncodeTiled is not available from the driver", what);
+  cuuint64_t gdim[4] = {(cuuint64_t)c, (cuuint64_t)w, (cuuint64_t)h, (cuuint64_t)n};
+  cuuint64_t gstr[3] = {(cuuint64_t)ld * 2, (cuuint64_t)ld * 2 * w, (cuuint64_t)ld * 2 * w * h};
+  cuuint32_t box[4] = {(cuuint32_t)KCH, (cuuint32_t)(TILE_W * sample), (cuuint32_t)(rows * sample), 1};
+  cuuint32_t estr[4] = {1, (cuuint32_t)sample, (cuuint32_t)sample, 1};
+  CUresult cr = encode(tm, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 4, const_cast<void*>(ptr), gdim, gstr, box, estr,
+                       CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
+                       CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+  if (cr != CUDA_SUCCESS) {
+    set_error("%s: cuTensorMapEncodeTiled failed with CUresult %d", what, (int)cr);
+    return SRCGAN_E_CUDA;
+  }
+  return SRCGAN_OK;
+}
+
 static int bn_for(int cout) { return cout >= 128 ? 128 : cout; }
 
-template <int BN, int KH, int KW>
+struct HostPlan {
+  Plan plan;
+  int maxt;
+  int slot_kh[MAX_SLOTS], slot_kw[MAX_SLOTS];
+};
+
+// forward convolution KxK, stride s (1|2), padding p
+static HostPlan fprop_plan(int K, int s, int p) {
+  HostPlan hp = {};
+  Plan& pl = hp.plan;
+  pl.in_scale = s;
+  int slot = 0;
+  if (s == 1) {
+    hp.maxt = K;
+    for (int kw = 0; kw < K; ++kw) {
+      pl.dx[pl.nloads] = kw - p; pl.dy[pl.nloads] = -p; pl.ntaps[pl.nloads] = K; pl.slot0[pl.nloads] = slot;
+      for (int kh = 0; kh < K; ++kh) { hp.slot_kh[slot] = kh; hp.slot_kw[slot] = kw; ++slot; }
+      ++pl.nloads;
+    }
+  } else {
+    hp.maxt = 2;
+    for (int kw = 0; kw < K; ++kw)
+      for (int first = 0; first < 2 && first < K; ++first) {       // kh = first, first+2  (same row parity)
+        int l = pl.nloads++;
+        pl.dx[l] = kw - p; pl.dy[l] = first - p; pl.slot0[l] = slot; pl.ntaps[l] = 0;
+        for (int kh = first; kh < K; kh += 2) { hp.slot_kh[slot] = kh; hp.slot_kw[slot] = kw; ++slot; ++pl.ntaps[l]; }
+      }
+  }
+  pl.total_slots = slot;
+  return hp;
+}
+
+// output phase (a,b) of the stride-2 dgrad of a KxK pad-p convolution: a stride-1 conv over dY
+static HostPlan dgrad2_phase_plan(int K, int p, int a, int b) {
+  HostPlan hp = {};
+  Plan& pl = hp.plan;
+  pl.in_scale = 1;
+  hp.maxt = 2;
+  int khs[4], nkh = 0, kws[4], nkw = 0;
+  for (int kh = K - 1; kh >= 0; --kh)              // descending kh = ascending row offset (a+p-kh)/2
+    if (((a + p - kh) & 1) == 0) khs[nkh++] = kh;
+  for (int kw = K - 1; kw >= 0; --kw)
+    if (((b + p - kw) & 1) == 0) kws[nkw++] = kw;
+  int slot = 0;
+  for (int i = 0; i < nkw; ++i) {
+    int l = pl.nloads++;
+    pl.dx[l] = (b + p - kws[i]) / 2;               // exact: numerator is even (may be negative)
+    pl.dy[l] = nkh ? (a + p - khs[0]) / 2 : 0;
+    pl.ntaps[l] = nkh; pl.slot0[l] = slot;
+    for (int j = 0; j < nkh; ++j) { hp.slot_kh[slot] = khs[j]; hp.slot_kw[slot] = kws[i]; ++slot; }
+  }
+  pl.total_slots = slot;
+  return hp;
+}
+
+static size_t packed_elems(int n_total, int k_total, int slots) {
+  return (size_t)n_total * ((k_total + KCH - 1) / KCH) * KCH * slots;
+}
+
+static int pack_launch(const float* w, int n_total, int k_total, long long nstride, long long kstride, int KW,
+                       const HostPlan& hp, __nv_bfloat16* out, cudaStream_t st) {
+  PackArgs a;
+  a.n_total = n_total; a.k_total = k_total; a.bn = bn_for(n_total); a.nchunks = (k_total + KCH - 1) / KCH;
+  a.total_slots = hp.plan.total_slots; a.nstride = nstride; a.kstride = kstride;
+  for (int s = 0; s < MAX_SLOTS; ++s) a.slot_off[s] = s < a.total_slots ? hp.slot_kh[s] * KW + hp.slot_kw[s] : 0;
+  const long long total = (long long)packed_elems(n_total, k_total, a.total_slots);
+  if (total == 0) return SRCGAN_OK;
+  pack_weights_tc<<<ceil_div(total, 256), 256, 0, st>>>(w, a, out);
+  count_launch();
+  return check_launch("pack_weights_tc");
+}
+
+template <int BN, int MAXT>
 static int launch(const CUtensorMap& tmap, const TcArgs& a, cudaStream_t st) {
-  using C = Cfg<BN, KH, KW>;
+  using C = Cfg<BN, MAXT>;
   static bool attr_set = false;
   if (!attr_set) {
-    SRCGAN_CUDA(cudaFuncSetAttribute(conv_igemm_tc<BN, KH, KW>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+    SRCGAN_CUDA(cudaFuncSetAttribute(conv_igemm_tc<BN, MAXT>, cudaFuncAttributeMaxDynamicSharedMemorySize,
                                      C::SMEM_BYTES));
     attr_set = true;
   }
   long long grid = a.num_tiles < kNumSMs ? a.num_tiles : kNumSMs;
-  conv_igemm_tc<BN, KH, KW><<<(unsigned)grid, NUM_THREADS, C::SMEM_BYTES, st>>>(tmap, a);
+  conv_igemm_tc<BN, MAXT><<<(unsigned)grid, NUM_THREADS, C::SMEM_BYTES, st>>>(tmap, a);
   count_launch();
   return check_launch("conv_igemm_tc");
 }
 
+static int dispatch(int bn, int maxt, const CUtensorMap& tmap, const TcArgs& a, cudaStream_t st) {
+#define SRCGAN_TC_CASE(B, T) if (bn == B && maxt == T) return launch<B, T>(tmap, a, st)
+  SRCGAN_TC_CASE(32, 2); SRCGAN_TC_CASE(64, 2); SRCGAN_TC_CASE(128, 2);
+  SRCGAN_TC_CASE(32, 3); SRCGAN_TC_CASE(64, 3); SRCGAN_TC_CASE(128, 3);
+  SRCGAN_TC_CASE(32, 4); SRCGAN_TC_CASE(64, 4); SRCGAN_TC_CASE(128, 4);
+#undef SRCGAN_TC_CASE
+  set_error("conv tc: no kernel for BN=%d MAXT=%d", bn, maxt);
+  return SRCGAN_E_INVALID;
+}
+
+static void fill_epilogue(TcArgs& a, const srcgan_conv_params* p) {
+  a.wgt = (const __nv_bfloat16*)p->wgt; a.bias = p->bias;
+  a.y = (__nv_bfloat16*)p->y; a.y_ld = p->y_ld;
+  a.act = p->act; a.act_slope = p->act_slope; a.alpha = p->alpha;
+  a.r1 = (const __nv_bfloat16*)p->r1; a.r1_ld = p->r1_ld; a.beta1 = p->beta1;
+  a.r2 = (const __nv_bfloat16*)p->r2; a.r2_ld = p->r2_ld; a.beta2 = p->beta2;
+  a.mask = (const __nv_bfloat16*)p->mask; a.mask_ld = p->mask_ld; a.mask_slope = p->mask_slope;
+}
+
 }  // namespace tc
 
-bool conv_tc_supported(const srcgan_conv_params* p) {
-  if (p->dtype != SRCGAN_DT_BF16 || p->stride != 1 || p->upsample) return false;
+static bool tc_common_ok(const srcgan_conv_params* p) {
+  if (p->dtype != SRCGAN_DT_BF16 || p->upsample) return false;
   if (p->kh != p->kw || (p->kh != 3 && p->kh != 4)) return false;
-  if (p->cin < 64 || p->cin % 16 != 0) return false;
-  if (!(p->cout == 32 || p->cout == 64 || p->cout == 128 || p->cout == 256)) return false;
+  if (p->stride != 1 && p->stride != 2) return false;
   if (p->x_ld % 8 || p->y_ld % 8) return false;
   if (((uintptr_t)p->x) % 16 || ((uintptr_t)p->y) % 16) return false;
   if (p->r1 && (p->r1_ld % 8 || ((uintptr_t)p->r1) % 16)) return false;
@@ -402,60 +531,96 @@ bool conv_tc_supported(const srcgan_conv_params* p) {
   if (p->mask && (p->mask_ld % 8 || ((uintptr_t)p->mask) % 16)) return false;
   return true;
 }
+static bool tc_nch_ok(int c) { return c == 32 || c == 64 || c == 128 || c == 256; }
 
-size_t packed_weight_bytes_tc(int cout, int cin, int kh, int kw) {
-  const int nchunks = (cin + tc::KCH - 1) / tc::KCH;
-  return (size_t)cout * nchunks * tc::KCH * kh * kw * sizeof(__nv_bfloat16);
+bool conv_tc_supported(const srcgan_conv_params* p) {
+  return tc_common_ok(p) && p->cin >= 64 && p->cin % 16 == 0 && tc_nch_ok(p->cout);
+}
+// stride-2 dgrad on the tensor-core engine (stride-1 dgrad is an fprop over transposed weights)
+bool conv_dgrad_tc_supported(const srcgan_conv_params* p) {
+  return tc_common_ok(p) && p->stride == 2 && p->cout >= 64 && p->cout % 16 == 0 && tc_nch_ok(p->cin);
 }
 
-int pack_weights_tc_host(const float* w, int cout, int cin, int kh, int kw, void* out, cudaStream_t st) {
-  SRCGAN_REQUIRE(cout == 32 || cout == 64 || cout == 128 || cout == 256, "pack_weights(tc): cout %d unsupported", cout);
-  const int bn = tc::bn_for(cout);
-  const int nchunks = (cin + tc::KCH - 1) / tc::KCH;
-  const long long total = (long long)cout * nchunks * tc::KCH * kh * kw;
-  tc::pack_weights_tc<<<ceil_div(total, 256), 256, 0, st>>>(w, cout, cin, kh, kw, bn, nchunks, (__nv_bfloat16*)out);
-  count_launch();
-  return check_launch("pack_weights_tc");
+size_t packed_weight_bytes_tc(int cout, int cin, int kh, int kw, int layout) {
+  if (layout == SRCGAN_WL_TC) return tc::packed_elems(cout, cin, kh * kw) * sizeof(__nv_bfloat16);
+  if (layout == SRCGAN_WL_TC_S2) return tc::packed_elems(cout, cin, kh * kw) * sizeof(__nv_bfloat16);
+  return tc::packed_elems(cin, cout, kh * kw) * sizeof(__nv_bfloat16);     // SRCGAN_WL_TC_DGRAD_S2: 4 phases
+}
+
+int pack_weights_tc_host(const float* w, int cout, int cin, int kh, int kw, int layout, void* out, cudaStream_t st) {
+  SRCGAN_REQUIRE(kh == kw, "pack_weights(tc): square filters only");
+  const long long taps = (long long)kh * kw;
+  if (layout == SRCGAN_WL_TC || layout == SRCGAN_WL_TC_S2) {
+    SRCGAN_REQUIRE(tc_nch_ok(cout), "pack_weights(tc): cout %d unsupported", cout);
+    tc::HostPlan hp = tc::fprop_plan(kh, layout == SRCGAN_WL_TC ? 1 : 2, 0);   // slot order does not depend on pad
+    return tc::pack_launch(w, cout, cin, (long long)cin * taps, taps, kw, hp, (__nv_bfloat16*)out, st);
+  }
+  SRCGAN_REQUIRE(layout == SRCGAN_WL_TC_DGRAD_S2, "pack_weights(tc): unknown layout %d", layout);
+  SRCGAN_REQUIRE(tc_nch_ok(cin), "pack_weights(tc dgrad): cin %d unsupported", cin);
+  __nv_bfloat16* o = (__nv_bfloat16*)out;
+  for (int a = 0; a < 2; ++a)
+    for (int b = 0; b < 2; ++b) {
+      // phase tap sets depend on pad only through parity; the packer is told the pad via kh's parity class:
+      // caller convention: pad = 1 (the only padding the stride-2 layers of the reference use)
+      tc::HostPlan hp = tc::dgrad2_phase_plan(kh, 1, a, b);
+      int rc = tc::pack_launch(w, cin, cout, taps, (long long)cin * taps, kw, hp, o, st);
+      if (rc) return rc;
+      o += tc::packed_elems(cin, cout, hp.plan.total_slots);
+    }
+  return SRCGAN_OK;
 }
 
 int conv_fprop_tc(const srcgan_conv_params* p, cudaStream_t st) {
-  tc::EncodeTiledFn encode = tc::get_encode_fn();
-  SRCGAN_REQUIRE(encode != nullptr, "conv_fprop_tc: cuTensorMapEncodeTiled is not available from the driver");
-  const int KH = p->kh;
+  tc::HostPlan hp = tc::fprop_plan(p->kh, p->stride, p->pad);
   CUtensorMap tmap;
-  cuuint64_t gdim[4] = {(cuuint64_t)p->cin, (cuuint64_t)p->w, (cuuint64_t)p->h, (cuuint64_t)p->n};
-  cuuint64_t gstr[3] = {(cuuint64_t)p->x_ld * 2, (cuuint64_t)p->x_ld * 2 * p->w, (cuuint64_t)p->x_ld * 2 * p->w * p->h};
-  cuuint32_t box[4] = {(cuuint32_t)tc::KCH, (cuuint32_t)tc::TILE_W, (cuuint32_t)(tc::TILE_H + KH - 1), 1};
-  cuuint32_t estr[4] = {1, 1, 1, 1};
-  CUresult cr = encode(&tmap, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 4, const_cast<void*>(p->x), gdim, gstr, box, estr,
-                       CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
-                       CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
-  if (cr != CUDA_SUCCESS) {
-    set_error("conv_fprop_tc: cuTensorMapEncodeTiled failed with CUresult %d", (int)cr);
-    return SRCGAN_E_CUDA;
-  }
+  int rc = tc::make_tmap(&tmap, p->x, p->cin, p->w, p->h, p->n, p->x_ld, tc::TILE_H + hp.maxt - 1, p->stride,
+                         "conv_fprop_tc");
+  if (rc) return rc;
   tc::TcArgs a;
-  a.n = p->n; a.h = p->ho; a.w = p->wo; a.cin = p->cin; a.cout = p->cout; a.pad = p->pad;
+  a.n = p->n; a.cin = p->cin; a.cout = p->cout;
+  a.gh = p->ho; a.gw = p->wo; a.oh = p->ho; a.ow = p->wo; a.os = 1; a.oa = 0; a.ob = 0;
+  a.plan = hp.plan;
   a.nchunks = (p->cin + tc::KCH - 1) / tc::KCH;
   const int bn = tc::bn_for(p->cout);
   a.n_blocks = p->cout / bn;
-  a.tiles_x = (p->wo + tc::TILE_W - 1) / tc::TILE_W;
-  a.tiles_y = (p->ho + tc::TILE_H - 1) / tc::TILE_H;
+  a.tiles_x = (a.gw + tc::TILE_W - 1) / tc::TILE_W;
+  a.tiles_y = (a.gh + tc::TILE_H - 1) / tc::TILE_H;
   a.num_tiles = (long long)a.tiles_x * a.tiles_y * p->n * a.n_blocks;
-  a.wgt = (const __nv_bfloat16*)p->wgt; a.bias = p->bias;
-  a.y = (__nv_bfloat16*)p->y; a.y_ld = p->y_ld;
-  a.act = p->act; a.act_slope = p->act_slope; a.alpha = p->alpha;
-  a.r1 = (const __nv_bfloat16*)p->r1; a.r1_ld = p->r1_ld; a.beta1 = p->beta1;
-  a.r2 = (const __nv_bfloat16*)p->r2; a.r2_ld = p->r2_ld; a.beta2 = p->beta2;
-  a.mask = (const __nv_bfloat16*)p->mask; a.mask_ld = p->mask_ld; a.mask_slope = p->mask_slope;
-  if (KH == 3) {
-    if (bn == 32) return tc::launch<32, 3, 3>(tmap, a, st);
-    if (bn == 64) return tc::launch<64, 3, 3>(tmap, a, st);
-    return tc::launch<128, 3, 3>(tmap, a, st);
-  }
-  if (bn == 32) return tc::launch<32, 4, 4>(tmap, a, st);
-  if (bn == 64) return tc::launch<64, 4, 4>(tmap, a, st);
-  return tc::launch<128, 4, 4>(tmap, a, st);
+  tc::fill_epilogue(a, p);
+  return tc::dispatch(bn, hp.maxt, tmap, a, st);
+}
+
+// stride-2 dgrad: dX (h x w x cin) from dY (ho x wo x cout); x = dY, y = dX, wgt = SRCGAN_WL_TC_DGRAD_S2 pack
+int conv_dgrad_tc(const srcgan_conv_params* p, cudaStream_t st) {
+  SRCGAN_REQUIRE(p->pad == 1, "conv_dgrad_tc: stride-2 dgrad is built for pad 1 (got %d)", p->pad);
+  CUtensorMap tmap;
+  int rc = tc::make_tmap(&tmap, p->x, p->cout, p->wo, p->ho, p->n, p->x_ld, tc::TILE_H + 1, 1, "conv_dgrad_tc");
+  if (rc) return rc;
+  const int bn = tc::bn_for(p->cin);
+  const __nv_bfloat16* w = (const __nv_bfloat16*)p->wgt;
+  for (int pa = 0; pa < 2; ++pa)
+    for (int pb = 0; pb < 2; ++pb) {
+      tc::HostPlan hp = tc::dgrad2_phase_plan(p->kh, p->pad, pa, pb);
+      tc::TcArgs a;
+      a.n = p->n; a.cin = p->cout; a.cout = p->cin;          // GEMM K channels = dY channels, N = dX channels
+      a.gh = (p->h - pa + 1) / 2; a.gw = (p->w - pb + 1) / 2;
+      a.oh = p->h; a.ow = p->w; a.os = 2; a.oa = pa; a.ob = pb;
+      a.plan = hp.plan;
+      a.nchunks = (p->cout + tc::KCH - 1) / tc::KCH;
+      a.n_blocks = p->cin / bn;
+      a.tiles_x = (a.gw + tc::TILE_W - 1) / tc::TILE_W;
+      a.tiles_y = (a.gh + tc::TILE_H - 1) / tc::TILE_H;
+      a.num_tiles = (long long)a.tiles_x * a.tiles_y * p->n * a.n_blocks;
+      tc::fill_epilogue(a, p);
+      a.wgt = w;
+      a.bias = nullptr;
+      if (a.num_tiles > 0 && hp.plan.total_slots > 0) {
+        rc = tc::dispatch(bn, 2, tmap, a, st);
+        if (rc) return rc;
+      }
+      w += tc::packed_elems(p->cin, p->cout, hp.plan.total_slots);
+    }
+  return SRCGAN_OK;
 }
 
 // ---------------------------------------------------------------------------------------------
@@ -474,7 +639,10 @@ namespace tcw {
 using namespace tc;
 
 struct WgArgs {
-  int n, ho, wo, cin, cout, pad, kw;
+  int n, ho, wo, cin, cout;
+  Plan plan;                 // the forward convolution's load plan (X slabs; stride-sampled for s=2)
+  int tapidx[MAX_SLOTS];     // slot -> kh*KW + kw
+  int ktaps;                 // KH*KW
   int cblocks, nblocks, splits;
   int tiles_x, tiles_y;
   long long num_tiles, tiles_per_split;
@@ -496,7 +664,7 @@ __host__ __device__ constexpr uint32_t umma_idesc_mn(int M, int N) {
   return umma_idesc(M, N) | (1u << 15) | (1u << 16);      // A and B MN-major
 }
 
-template <int BN, int KH>
+template <int BN, int KH>      // KH = max taps per load (MAXT)
 struct WCfg {
   static constexpr int A_SLAB = (TILE_H + KH - 1) * TILE_W * 128;   // one 64-channel chunk of X (haloed rows)
   static constexpr int A_BYTES = 2 * A_SLAB;
@@ -541,12 +709,14 @@ conv_wgrad_tc_kernel(const __grid_constant__ CUtensorMap tmap_x, const __grid_co
   tc_fence_after();
   const uint32_t tmem_base = *tmem_slot;
 
-  // CTA -> (kw, ci block, co block, split)
+  // CTA -> (load, ci block, co block, split)
   int b = blockIdx.x;
   const int split = b % a.splits; b /= a.splits;
   const int nb = b % a.nblocks; b /= a.nblocks;
   const int cb = b % a.cblocks; b /= a.cblocks;
-  const int fw = b;
+  const int ld = b;
+  const int nt = a.plan.ntaps[ld];
+  const int ox = a.plan.dx[ld], oy = a.plan.dy[ld], sc = a.plan.in_scale;
   const long long t_beg = (long long)split * a.tiles_per_split;
   long long t_end = t_beg + a.tiles_per_split;
   if (t_end > a.num_tiles) t_end = a.num_tiles;
@@ -564,8 +734,8 @@ conv_wgrad_tc_kernel(const __grid_constant__ CUtensorMap tmap_x, const __grid_co
         mbar_wait(&empty_bar[stage], phase ^ 1);
         uint8_t* sa = smem + stage * C::STAGE_BYTES;
         mbar_expect_tx(&full_bar[stage], C::STAGE_BYTES);
-        tma_load_4d(&tmap_x, &full_bar[stage], sa, cb * 128, x0 + fw - a.pad, y0 - a.pad, img);
-        tma_load_4d(&tmap_x, &full_bar[stage], sa + C::A_SLAB, cb * 128 + 64, x0 + fw - a.pad, y0 - a.pad, img);
+        tma_load_4d(&tmap_x, &full_bar[stage], sa, cb * 128, sc * x0 + ox, sc * y0 + oy, img);
+        tma_load_4d(&tmap_x, &full_bar[stage], sa + C::A_SLAB, cb * 128 + 64, sc * x0 + ox, sc * y0 + oy, img);
 #pragma unroll
         for (int j = 0; j < BN / 64; ++j)
           tma_load_4d(&tmap_g, &full_bar[stage], sa + C::A_BYTES + j * C::G_SLAB, nb * BN + j * 64, x0, y0, img);
@@ -583,8 +753,7 @@ conv_wgrad_tc_kernel(const __grid_constant__ CUtensorMap tmap_x, const __grid_co
         tc_fence_after();
         const uint32_t sa = smem_u32(smem + stage * C::STAGE_BYTES);
         const uint32_t sg = sa + C::A_BYTES;
-#pragma unroll
-        for (int kh = 0; kh < KH; ++kh) {
+        for (int kh = 0; kh < nt; ++kh) {
 #pragma unroll
           for (int ks = 0; ks < TILE_M / 16; ++ks) {
             umma_bf16(tmem_base + (uint32_t)(kh * BN),
@@ -605,10 +774,10 @@ conv_wgrad_tc_kernel(const __grid_constant__ CUtensorMap tmap_x, const __grid_co
     mbar_wait(done_bar, 0);
     tc_fence_after();
     const bool has_work = t_end > t_beg;
-    const int kw_total = a.kw;
 #pragma unroll 1
-    for (int kh = 0; kh < KH; ++kh) {
-      float* dst = a.part + (((long long)split * (KH * kw_total) + (kh * kw_total + fw)) * a.cin + ci) * a.cout;
+    for (int kh = 0; kh < nt; ++kh) {
+      const int tap = a.tapidx[a.plan.slot0[ld] + kh];
+      float* dst = a.part + (((long long)split * a.ktaps + tap) * a.cin + ci) * a.cout;
 #pragma unroll 1
       for (int cb32 = 0; cb32 < BN; cb32 += 32) {
         uint32_t v[32];
@@ -643,7 +812,7 @@ static void plan(const srcgan_conv_params* p, int& bn, int& cblocks, int& nblock
   nblocks = (p->cout + bn - 1) / bn;
   const int tx = (p->wo + TILE_W - 1) / TILE_W, ty = (p->ho + TILE_H - 1) / TILE_H;
   tiles = (long long)tx * ty * p->n;
-  const int groups = p->kw * cblocks * nblocks;
+  const int groups = tc::fprop_plan(p->kh, p->stride, p->pad).plan.nloads * cblocks * nblocks;
   long long s = (2 * kNumSMs + groups - 1) / groups;     // ~2 CTAs per SM worth of work, 1 resident
   if (s > tiles) s = tiles;
   if (s < 1) s = 1;
@@ -660,7 +829,7 @@ static int launch(const CUtensorMap& tx, const CUtensorMap& tg, const WgArgs& a,
                                      C::SMEM_BYTES));
     attr_set = true;
   }
-  const unsigned grid = (unsigned)(a.kw * a.cblocks * a.nblocks * a.splits);
+  const unsigned grid = (unsigned)(a.plan.nloads * a.cblocks * a.nblocks * a.splits);
   conv_wgrad_tc_kernel<BN, KH><<<grid, NUM_THREADS, C::SMEM_BYTES, st>>>(tx, tg, a);
   count_launch();
   return check_launch("conv_wgrad_tc");
@@ -674,7 +843,7 @@ int bias_grad_launch(const void* dy, int dy_ld, int dtype, long long M, int cout
                      float alpha, void* ws, cudaStream_t st);
 
 bool conv_wgrad_tc_supported(const srcgan_conv_params* p) {
-  if (p->dtype != SRCGAN_DT_BF16 || p->stride != 1 || p->upsample) return false;
+  if (p->dtype != SRCGAN_DT_BF16 || (p->stride != 1 && p->stride != 2) || p->upsample) return false;
   if (p->kh != p->kw || (p->kh != 3 && p->kh != 4)) return false;
   if (p->cin < 16 || p->cin % 8 || p->cout < 16 || p->cout % 8) return false;
   if (p->x_ld % 8 || p->y_ld % 8) return false;
@@ -692,45 +861,32 @@ size_t conv_wgrad_tc_workspace(const srcgan_conv_params* p) {
 
 int conv_wgrad_tc(const srcgan_conv_params* p, float* dw, float* db, int accumulate, void* ws, size_t ws_bytes,
                   cudaStream_t st) {
-  tc::EncodeTiledFn encode = tc::get_encode_fn();
-  SRCGAN_REQUIRE(encode != nullptr, "conv_wgrad_tc: cuTensorMapEncodeTiled is not available from the driver");
   SRCGAN_REQUIRE(ws && ws_bytes >= conv_wgrad_tc_workspace(p), "conv_wgrad_tc: workspace too small");
   int bn, cblocks, nblocks, splits;
   long long tiles, tps;
   tcw::plan(p, bn, cblocks, nblocks, splits, tiles, tps);
   const size_t wbytes = (size_t)splits * p->kh * p->kw * p->cin * p->cout * sizeof(float);
   if (dw) {
+    tc::HostPlan hp = tc::fprop_plan(p->kh, p->stride, p->pad);
     CUtensorMap tx, tg;
-    cuuint32_t estr[4] = {1, 1, 1, 1};
-    {
-      cuuint64_t gdim[4] = {(cuuint64_t)p->cin, (cuuint64_t)p->w, (cuuint64_t)p->h, (cuuint64_t)p->n};
-      cuuint64_t gstr[3] = {(cuuint64_t)p->x_ld * 2, (cuuint64_t)p->x_ld * 2 * p->w,
-                            (cuuint64_t)p->x_ld * 2 * p->w * p->h};
-      cuuint32_t box[4] = {64, (cuuint32_t)tc::TILE_W, (cuuint32_t)(tc::TILE_H + p->kh - 1), 1};
-      CUresult cr = encode(&tx, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 4, const_cast<void*>(p->x), gdim, gstr, box, estr,
-                           CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B,
-                           CU_TENSOR_MAP_L2_PROMOTION_L2_256B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
-      if (cr != CUDA_SUCCESS) { set_error("conv_wgrad_tc: tensor map (x) failed: CUresult %d", (int)cr); return SRCGAN_E_CUDA; }
-    }
-    {
-      cuuint64_t gdim[4] = {(cuuint64_t)p->cout, (cuuint64_t)p->wo, (cuuint64_t)p->ho, (cuuint64_t)p->n};
-      cuuint64_t gstr[3] = {(cuuint64_t)p->y_ld * 2, (cuuint64_t)p->y_ld * 2 * p->wo,
-                            (cuuint64_t)p->y_ld * 2 * p->wo * p->ho};
-      cuuint32_t box[4] = {64, (cuuint32_t)tc::TILE_W, (cuuint32_t)tc::TILE_H, 1};
-      CUresult cr = encode(&tg, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 4, p->y, gdim, gstr, box, estr,
-                           CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B,
-                           CU_TENSOR_MAP_L2_PROMOTION_L2_256B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
-      if (cr != CUDA_SUCCESS) { set_error("conv_wgrad_tc: tensor map (dy) failed: CUresult %d", (int)cr); return SRCGAN_E_CUDA; }
-    }
+    int rc = tc::make_tmap(&tx, p->x, p->cin, p->w, p->h, p->n, p->x_ld, tc::TILE_H + hp.maxt - 1, p->stride,
+                           "conv_wgrad_tc(x)");
+    if (rc) return rc;
+    rc = tc::make_tmap(&tg, p->y, p->cout, p->wo, p->ho, p->n, p->y_ld, tc::TILE_H, 1, "conv_wgrad_tc(dy)");
+    if (rc) return rc;
     tcw::WgArgs a;
-    a.n = p->n; a.ho = p->ho; a.wo = p->wo; a.cin = p->cin; a.cout = p->cout; a.pad = p->pad; a.kw = p->kw;
+    a.n = p->n; a.ho = p->ho; a.wo = p->wo; a.cin = p->cin; a.cout = p->cout;
+    a.plan = hp.plan;
+    for (int s = 0; s < tc::MAX_SLOTS; ++s)
+      a.tapidx[s] = s < hp.plan.total_slots ? hp.slot_kh[s] * p->kw + hp.slot_kw[s] : 0;
+    a.ktaps = p->kh * p->kw;
     a.cblocks = cblocks; a.nblocks = nblocks; a.splits = splits;
     a.tiles_x = (p->wo + tc::TILE_W - 1) / tc::TILE_W;
     a.tiles_y = (p->ho + tc::TILE_H - 1) / tc::TILE_H;
     a.num_tiles = tiles; a.tiles_per_split = tps;
     a.part = reinterpret_cast<float*>(ws);
-    int rc;
-    if (p->kh == 3) rc = bn == 64 ? tcw::launch<64, 3>(tx, tg, a, st) : tcw::launch<128, 3>(tx, tg, a, st);
+    if (hp.maxt == 2) rc = bn == 64 ? tcw::launch<64, 2>(tx, tg, a, st) : tcw::launch<128, 2>(tx, tg, a, st);
+    else if (hp.maxt == 3) rc = bn == 64 ? tcw::launch<64, 3>(tx, tg, a, st) : tcw::launch<128, 3>(tx, tg, a, st);
     else rc = bn == 64 ? tcw::launch<64, 4>(tx, tg, a, st) : tcw::launch<128, 4>(tx, tg, a, st);
     if (rc) return rc;
     rc = wgrad_reduce_launch(reinterpret_cast<const float*>(ws), splits, p->kh * p->kw, p->cin, p->cout, dw,

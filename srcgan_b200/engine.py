@@ -9,7 +9,7 @@ import os
 
 import torch
 
-from ._lib import ENGINE_SIMT, ENGINE_TC, WL_RSCK, WL_TC
+from ._lib import ENGINE_SIMT, ENGINE_TC, WL_RSCK, WL_TC, WL_TC_S2
 
 _force_simt = os.environ.get("SRCGAN_B200_ENGINE", "auto").lower() == "simt"
 
@@ -21,20 +21,26 @@ def force_simt(flag: bool) -> None:
 
 def tc_fprop_supported(cin: int, cout: int, k: int, stride: int, upsample: bool, dtype, h: int, w: int) -> bool:
     """Mirror of conv_tc_supported() in csrc/conv_tc.cu (the C side re-checks alignment and refuses loudly)."""
-    return (dtype == torch.bfloat16 and stride == 1 and not upsample and k in (3, 4) and cin >= 64
+    return (dtype == torch.bfloat16 and stride in (1, 2) and not upsample and k in (3, 4) and cin >= 64
             and cin % 16 == 0 and cout in (32, 64, 128, 256))
+
+
+def tc_dgrad_s2_supported(cin: int, cout: int, k: int, stride: int, pad: int, dtype) -> bool:
+    """Mirror of conv_dgrad_tc_supported(): stride-2 dgrad as four output-phase convolutions."""
+    return (not _force_simt and dtype == torch.bfloat16 and stride == 2 and pad == 1 and k in (3, 4) and cout >= 64
+            and cout % 16 == 0 and cin in (32, 64, 128, 256))
 
 
 def tc_wgrad_supported(cin: int, cout: int, k: int, stride: int, upsample: bool, dtype, h: int, w: int) -> bool:
     """Mirror of conv_wgrad_tc_supported() in csrc/conv_tc.cu."""
-    return (dtype == torch.bfloat16 and stride == 1 and not upsample and k in (3, 4) and cin >= 16
+    return (dtype == torch.bfloat16 and stride in (1, 2) and not upsample and k in (3, 4) and cin >= 16
             and cin % 8 == 0 and cout >= 16 and cout % 8 == 0)
 
 
 def select(cin, cout, k, stride, upsample, dtype, h, w):
     """-> (engine, fprop weight layout); (h, w) are the OUTPUT spatial dims."""
     if not _force_simt and dtype == torch.bfloat16 and tc_fprop_supported(cin, cout, k, stride, upsample, dtype, h, w):
-        return ENGINE_TC, WL_TC
+        return ENGINE_TC, (WL_TC if stride == 1 else WL_TC_S2)
     return ENGINE_SIMT, WL_RSCK
 
 

@@ -25,7 +25,7 @@ import torch
 import torch.nn as nn
 
 from . import ops
-from .ops import ENGINE_SIMT, Slice, WL_RSCK, WL_RSKC
+from .ops import ENGINE_SIMT, ENGINE_TC, Slice, WL_RSCK, WL_RSKC, WL_TC_DGRAD_S2
 
 LRELU = 0.2
 
@@ -51,6 +51,11 @@ def select_engine(cin: int, cout: int, k: int, stride: int, upsample: bool, dtyp
     """(engine, fprop weight layout) for one convolution."""
     from . import engine as _engine  # late import: keeps this module importable on CPU-only boxes
     return _engine.select(cin, cout, k, stride, upsample, dtype, h, w)
+
+
+def _engine_mod():
+    from . import engine as _engine
+    return _engine
 
 
 # ------------------------------------------------------------------------------------------
@@ -119,6 +124,9 @@ class _NetBase(nn.Module):
     def _w_d(self, conv: nn.Conv2d, dtype):
         return self._pk().get(("d", id(conv)), (conv.weight,), lambda: conv.weight.detach(), WL_RSKC, dtype)
 
+    def _w_d2(self, conv: nn.Conv2d, dtype):
+        return self._pk().get(("d2", id(conv)), (conv.weight,), lambda: conv.weight.detach(), WL_TC_DGRAD_S2, dtype)
+
     def _fprop(self, conv: nn.Conv2d, x: Slice, y: Slice, *, upsample=False, **ep) -> None:
         k, s, p = conv.kernel_size[0], conv.stride[0], conv.padding[0]
         eng, layout = select_engine(x.c, y.c, k, s, upsample, x.dtype, y.h, y.w)
@@ -131,6 +139,8 @@ class _NetBase(nn.Module):
         if s == 1 and dy.c > 4 and dx.c > 4:
             eng, layout = select_engine(dy.c, dx.c, k, 1, False, dy.dtype, dx.h, dx.w)
             ops.conv_fprop(dy, self._w_t(conv, dy.dtype, layout), None, dx, k, 1, k - 1 - p, engine=eng, **ep)
+        elif _engine_mod().tc_dgrad_s2_supported(dx.c, dy.c, k, s, p, dy.dtype):
+            ops.conv_dgrad(dy, self._w_d2(conv, dy.dtype), dx, k, s, p, engine=ENGINE_TC, **ep)
         else:
             ops.conv_dgrad(dy, self._w_d(conv, dy.dtype), dx, k, s, p, **ep)
 

@@ -10,7 +10,8 @@ from typing import Optional
 import torch
 
 from . import _lib
-from ._lib import ConvParams, DT_BF16, DT_F32, ENGINE_AUTO, ENGINE_SIMT, ENGINE_TC, WL_RSCK, WL_RSKC, WL_TC  # noqa: F401
+from ._lib import (ConvParams, DT_BF16, DT_F32, ENGINE_AUTO, ENGINE_SIMT, ENGINE_TC, WL_RSCK, WL_RSKC, WL_TC,  # noqa: F401
+                   WL_TC_DGRAD_S2, WL_TC_S2)
 
 
 def dt_code(dtype: torch.dtype) -> int:
@@ -203,10 +204,11 @@ def conv_fprop(x: Slice, wgt: torch.Tensor, bias: Optional[torch.Tensor], y: Sli
 
 def conv_dgrad(dy: Slice, wgt_rskc: torch.Tensor, dx: Slice, k: int, stride: int, pad: int, *, alpha: float = 1.0,
                r1: Optional[Slice] = None, beta1: float = 0.0, mask: Optional[Slice] = None,
-               mask_slope: float = 0.0) -> None:
-    """dx = epilogue(conv_transpose(dy, w)) - gather form, any stride (SIMT engine)."""
+               mask_slope: float = 0.0, engine: int = ENGINE_SIMT) -> None:
+    """dx = epilogue(conv_transpose(dy, w)).  SIMT engine: gather form, any stride, RSKC weights.
+    tcgen05 engine: stride 2 (four output-phase convolutions), WL_TC_DGRAD_S2 weights."""
     _require_cuda(dy.buf, "conv grad")
-    p = _conv_params(dx.n, dx.h, dx.w, dx.c, dy.c, k, stride, pad, False, dy.h, dy.w, dy.dtype, ENGINE_SIMT)
+    p = _conv_params(dx.n, dx.h, dx.w, dx.c, dy.c, k, stride, pad, False, dy.h, dy.w, dy.dtype, engine)
     p.x, p.x_ld, p.wgt, p.y, p.y_ld = dy.ptr, dy.ld, wgt_rskc.data_ptr(), dx.ptr, dx.ld
     _epilogue(p, None, None, alpha, r1, beta1, None, 0.0, mask, mask_slope)
     with _Timed("dgrad", p):

@@ -308,3 +308,45 @@ def test_conv_wgrad_tc_matches_reference(case):
     assert relerr(db.cpu(), gy.sum((0, 2, 3))) < 5e-3
     ops.conv_wgrad(xs, gys, dw, db, k, 1, p, engine=ops.ENGINE_TC, accumulate=True, alpha=0.5)
     assert relerr(dw.cpu(), 1.5 * wt.grad) < 5e-3
+
+
+S2_CASES = [
+    # n, h, w, cin, cout, k
+    (2, 32, 16, 128, 128, 3),      # Decoder conv3
+    (1, 32, 32, 128, 256, 3),      # Decoder conv4
+    (2, 32, 32, 64, 128, 4),       # discriminator conv1
+    (1, 34, 18, 64, 64, 3),        # ragged tile grid
+    (1, 36, 20, 64, 64, 4),
+]
+
+
+@pytest.mark.parametrize("case", S2_CASES)
+def test_conv_tc_stride2_fprop_dgrad_wgrad(case):
+    """tcgen05 engine on stride-2 convolutions: element-strided TMA boxes (fprop, wgrad) and the four
+    output-phase convolutions (dgrad), against torch fp32 on bf16-rounded operands."""
+    from srcgan_b200 import ops
+    n, h, w, cin, cout, k = case
+    x = rand((n, cin, h, w), 31).bfloat16().float().requires_grad_(True)
+    wt = (rand((cout, cin, k, k), 32, 0.1)).bfloat16().float().requires_grad_(True)
+    b = rand((cout,), 33)
+    y_ref = F.conv2d(x, wt, b, stride=2, padding=1)
+    ho, wo = y_ref.shape[2:]
+    gy = rand(tuple(y_ref.shape), 34).bfloat16().float()
+    y_ref.backward(gy)
+    xs = to_nhwc(x.detach(), torch.bfloat16)
+    ys = ops.Slice(torch.zeros((n, ho, wo, cout), dtype=torch.bfloat16, device=DEV))
+    ops.conv_fprop(xs, ops.pack_weights(wt.detach().to(DEV), ops.WL_TC_S2, torch.bfloat16), b.to(DEV), ys, k, 2, 1,
+                   engine=ops.ENGINE_TC)
+    assert relerr(from_nhwc(ys), y_ref.detach()) < 1e-2
+    gys = to_nhwc(gy, torch.bfloat16)
+    mk = rand((n, cin, h, w), 35)
+    dxs = ops.Slice(torch.zeros((n, h, w, cin), dtype=torch.bfloat16, device=DEV))
+    ops.conv_dgrad(gys, ops.pack_weights(wt.detach().to(DEV), ops.WL_TC_DGRAD_S2, torch.bfloat16), dxs, k, 2, 1,
+                   mask=to_nhwc(mk, torch.bfloat16), mask_slope=0.2, engine=ops.ENGINE_TC)
+    ref_dx = x.grad * torch.where(mk.bfloat16().float() > 0, torch.ones_like(mk), torch.full_like(mk, 0.2))
+    assert relerr(from_nhwc(dxs), ref_dx) < 1e-2
+    dw = torch.empty((cout, cin, k, k), device=DEV)
+    db = torch.empty((cout,), device=DEV)
+    ops.conv_wgrad(xs, gys, dw, db, k, 2, 1, engine=ops.ENGINE_TC)
+    assert relerr(dw.cpu(), wt.grad) < 5e-3
+    assert relerr(db.cpu(), gy.sum((0, 2, 3))) < 5e-3
