@@ -320,6 +320,110 @@ __global__ void colsum_final(const float* __restrict__ part, int nparts, int c, 
   out[ch] = accumulate ? out[ch] + (float)s : (float)s;
 }
 
+// ---------------------------------------------------------------------------------------------
+// thin wgrad: one side of the convolution has <= 4 channels (image convs 3->64 / 64->3, patch logits
+// 256->1).  Bandwidth-bound: every element of the wide tensor is read exactly once, by the thread that
+// owns its channel; the thin tensor's haloed tile sits in shared memory as float4 per pixel and is
+// read as warp-uniform broadcasts.  dW[tap][c][k] = sum_q wide[q][c] * thin[ts*q + sign*(tap-pad)][k]
+//   case A (thin = dY, wide = X, stride 1):  sign = -1, ts = 1
+//   case B (thin = X, wide = dY, stride s):  sign = +1, ts = s
+// ---------------------------------------------------------------------------------------------
+struct ThinArgs {
+  const void* wide; int wide_ld; int cw;          // wide tensor (n, hw, ww, cw)
+  const void* thin; int thin_ld; int kt;          // thin tensor (n, ht, wt, kt<=4)
+  int n, hw, ww, ht, wt;
+  int ts, sign, pad;
+  int tiles_x, tiles_y;
+  long long num_tiles;
+};
+constexpr int THIN_TH = 8, THIN_TW = 32;
+
+template <typename T, int KH, int KW>
+__global__ void __launch_bounds__(256)
+thin_wgrad_kernel(const ThinArgs a, float* __restrict__ part) {
+  constexpr int TAPS = KH * KW;
+  constexpr int TTH = 2 * (THIN_TH - 1) + KH, TTW = 2 * (THIN_TW - 1) + KW;   // sized for ts = 2
+  __shared__ float4 st[TTH][TTW];
+  const int t = threadIdx.x, c = t & 63, g = t >> 6;
+  const int c0 = blockIdx.y * 64;
+  const T* __restrict__ W = reinterpret_cast<const T*>(a.wide);
+  const T* __restrict__ Th = reinterpret_cast<const T*>(a.thin);
+  const int tth = a.ts * (THIN_TH - 1) + KH, ttw = a.ts * (THIN_TW - 1) + KW;
+  const int omin_y = a.sign > 0 ? -a.pad : -(KH - 1 - a.pad);
+  const int omin_x = a.sign > 0 ? -a.pad : -(KW - 1 - a.pad);
+  float acc[TAPS][4];
+#pragma unroll
+  for (int i = 0; i < TAPS; ++i) { acc[i][0] = acc[i][1] = acc[i][2] = acc[i][3] = 0.f; }
+
+  for (long long tile = blockIdx.x; tile < a.num_tiles; tile += gridDim.x) {
+    long long r = tile;
+    const int bx = (int)(r % a.tiles_x); r /= a.tiles_x;
+    const int by = (int)(r % a.tiles_y);
+    const int img = (int)(r / a.tiles_y);
+    const int y0 = by * THIN_TH, x0 = bx * THIN_TW;
+    const int gy0 = a.ts * y0 + omin_y, gx0 = a.ts * x0 + omin_x;
+    __syncthreads();
+    for (int e = t; e < tth * ttw; e += 256) {
+      int ry = e / ttw, rx = e - ry * ttw;
+      int gy = gy0 + ry, gx = gx0 + rx;
+      float4 v = make_float4(0.f, 0.f, 0.f, 0.f);
+      if (gy >= 0 && gy < a.ht && gx >= 0 && gx < a.wt) {
+        const T* src = Th + (((long long)img * a.ht + gy) * a.wt + gx) * a.thin_ld;
+        v.x = to_f32(src[0]);
+        if (a.kt > 1) v.y = to_f32(src[1]);
+        if (a.kt > 2) v.z = to_f32(src[2]);
+        if (a.kt > 3) v.w = to_f32(src[3]);
+      }
+      st[ry][rx] = v;
+    }
+    __syncthreads();
+#pragma unroll 1
+    for (int rr = 0; rr < 2; ++rr) {
+      const int ly = 2 * g + rr, y = y0 + ly;
+      if (y >= a.hw) continue;
+      const T* wrow = W + (((long long)img * a.hw + y) * a.ww) * a.wide_ld + c0 + c;
+#pragma unroll 4
+      for (int lx = 0; lx < THIN_TW; ++lx) {
+        const int x = x0 + lx;
+        const float wv = x < a.ww ? to_f32(wrow[(long long)x * a.wide_ld]) : 0.f;
+#pragma unroll
+        for (int fr = 0; fr < KH; ++fr) {
+          const int ry = a.ts * ly + (a.sign > 0 ? fr : KH - 1 - fr);
+#pragma unroll
+          for (int fs = 0; fs < KW; ++fs) {
+            const int rx = a.ts * lx + (a.sign > 0 ? fs : KW - 1 - fs);
+            const float4 tv = st[ry][rx];
+            float* ac = acc[fr * KW + fs];
+            ac[0] = fmaf(wv, tv.x, ac[0]); ac[1] = fmaf(wv, tv.y, ac[1]);
+            ac[2] = fmaf(wv, tv.z, ac[2]); ac[3] = fmaf(wv, tv.w, ac[3]);
+          }
+        }
+      }
+    }
+  }
+  // partial [(block*4+g)][tap][cw][4]
+  float4* out = reinterpret_cast<float4*>(part) + ((long long)(blockIdx.x * 4 + g) * TAPS) * a.cw + c0 + c;
+#pragma unroll
+  for (int i = 0; i < TAPS; ++i) out[(long long)i * a.cw] = make_float4(acc[i][0], acc[i][1], acc[i][2], acc[i][3]);
+}
+
+// dw (OIHW) (+)= alpha * sum_parts part[p][tap][c][k];  thin_is_out: k indexes cout (case A) else cin (case B)
+__global__ void thin_wgrad_reduce(const float* __restrict__ part, int nparts, int taps, int cw, int kt, int thin_is_out,
+                                  float* __restrict__ dw, int accumulate, float alpha) {
+  long long total = (long long)taps * cw * kt;
+  long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= total) return;
+  int k = (int)(i % kt);
+  long long r = i / kt;
+  int c = (int)(r % cw);
+  int tap = (int)(r / cw);
+  float s = 0.f;
+  for (int p = 0; p < nparts; ++p) s += part[(((long long)p * taps + tap) * cw + c) * 4 + k];
+  s *= alpha;
+  long long o = thin_is_out ? ((long long)k * cw + c) * taps + tap : ((long long)c * kt + k) * taps + tap;
+  dw[o] = accumulate ? dw[o] + s : s;
+}
+
 // OIHW fp32 -> packed [tap][a][b] with (a,b) = (cin,cout) for RSCK or (cout,cin) for RSKC
 template <typename T>
 __global__ void pack_weights_simt(const float* __restrict__ w, int cout, int cin, int taps, int layout,
@@ -397,6 +501,9 @@ int conv_dgrad_simt(const srcgan_conv_params* p, cudaStream_t st) {
   return launch_igemm<__nv_bfloat16, true>(p, st);
 }
 
+int bias_grad_launch(const void* dy, int dy_ld, int dtype, long long M, int cout, float* db, int accumulate,
+                     float alpha, void* ws, cudaStream_t st);
+
 static void wgrad_plan(const srcgan_conv_params* p, int& bi, int& bo, int& splits, int& pix_per_split) {
   bi = p->cin <= 4 ? 4 : 64;
   bo = p->cout <= 4 ? 4 : 64;
@@ -410,12 +517,61 @@ static void wgrad_plan(const srcgan_conv_params* p, int& bi, int& bo, int& split
   splits = (int)((M + pix_per_split - 1) / pix_per_split);
 }
 
+static bool thin_wgrad_ok(const srcgan_conv_params* p) {
+  if (p->upsample || p->kh != p->kw || (p->kh != 3 && p->kh != 4)) return false;
+  if (p->cout <= 4 && p->cin % 64 == 0 && p->stride == 1) return true;                       // case A
+  if (p->cin <= 4 && p->cout % 64 == 0 && (p->stride == 1 || p->stride == 2)) return true;   // case B
+  return false;
+}
+static int thin_grid(const srcgan_conv_params* p, long long& tiles, int& tx, int& ty) {
+  const bool case_a = p->cout <= 4;
+  const int hw = case_a ? p->h : p->ho, ww = case_a ? p->w : p->wo;
+  tx = (ww + THIN_TW - 1) / THIN_TW; ty = (hw + THIN_TH - 1) / THIN_TH;
+  tiles = (long long)tx * ty * p->n;
+  return (int)(tiles < 2 * kNumSMs ? tiles : 2 * kNumSMs);
+}
+
 size_t conv_wgrad_simt_workspace(const srcgan_conv_params* p) {
+  size_t bbytes = (size_t)1024 * p->cout * sizeof(float);
+  if (thin_wgrad_ok(p)) {
+    long long tiles; int tx, ty;
+    int grid = thin_grid(p, tiles, tx, ty);
+    const int cw = p->cout <= 4 ? p->cin : p->cout;
+    size_t wbytes = (size_t)grid * 4 * p->kh * p->kw * cw * 4 * sizeof(float);
+    return ((wbytes + 255) / 256) * 256 + bbytes + 256;
+  }
   int bi, bo, splits, pps;
   wgrad_plan(p, bi, bo, splits, pps);
   size_t wbytes = (size_t)splits * p->kh * p->kw * p->cin * p->cout * sizeof(float);
-  size_t bbytes = (size_t)1024 * p->cout * sizeof(float);
-  return wbytes + bbytes + 256;
+  return ((wbytes + 255) / 256) * 256 + bbytes + 256;
+}
+
+template <typename T>
+static int launch_thin_wgrad(const srcgan_conv_params* p, float* dw, int accumulate, void* ws, cudaStream_t st) {
+  const bool case_a = p->cout <= 4;
+  ThinArgs a;
+  a.n = p->n;
+  if (case_a) {
+    a.wide = p->x; a.wide_ld = p->x_ld; a.cw = p->cin; a.hw = p->h; a.ww = p->w;
+    a.thin = p->y; a.thin_ld = p->y_ld; a.kt = p->cout; a.ht = p->ho; a.wt = p->wo;
+    a.ts = 1; a.sign = -1;
+  } else {
+    a.wide = p->y; a.wide_ld = p->y_ld; a.cw = p->cout; a.hw = p->ho; a.ww = p->wo;
+    a.thin = p->x; a.thin_ld = p->x_ld; a.kt = p->cin; a.ht = p->h; a.wt = p->w;
+    a.ts = p->stride; a.sign = 1;
+  }
+  a.pad = p->pad;
+  int grid = thin_grid(p, a.num_tiles, a.tiles_x, a.tiles_y);
+  float* part = reinterpret_cast<float*>(ws);
+  dim3 g(grid, a.cw / 64);
+  if (p->kh == 3) thin_wgrad_kernel<T, 3, 3><<<g, 256, 0, st>>>(a, part);
+  else thin_wgrad_kernel<T, 4, 4><<<g, 256, 0, st>>>(a, part);
+  const int taps = p->kh * p->kw;
+  long long total = (long long)taps * a.cw * a.kt;
+  thin_wgrad_reduce<<<ceil_div(total, 128), 128, 0, st>>>(part, grid * 4, taps, a.cw, a.kt, case_a ? 1 : 0, dw,
+                                                          accumulate, p->alpha);
+  count_launch(2);
+  return check_launch("thin_wgrad");
 }
 
 template <typename T>
@@ -429,6 +585,20 @@ static int launch_wgrad(const srcgan_conv_params* p, float* dw, float* db, int a
   SRCGAN_REQUIRE(ws && ws_bytes >= conv_wgrad_simt_workspace(p), "conv_wgrad: workspace too small");
   float* part = reinterpret_cast<float*>(ws);
   const int64_t M = (int64_t)p->n * p->ho * p->wo;
+  if (dw && thin_wgrad_ok(p)) {
+    int rc = launch_thin_wgrad<T>(p, dw, accumulate, ws, st);
+    if (rc) return rc;
+    long long tiles; int tx_, ty_;
+    int tg = thin_grid(p, tiles, tx_, ty_);
+    const int cw = p->cout <= 4 ? p->cin : p->cout;
+    size_t tb = (size_t)tg * 4 * taps * cw * 4 * sizeof(float);
+    if (db) {
+      int rc2 = bias_grad_launch(p->y, p->y_ld, p->dtype, M, p->cout, db, accumulate, p->alpha,
+                                 reinterpret_cast<char*>(ws) + ((tb + 255) / 256) * 256, st);
+      if (rc2) return rc2;
+    }
+    return SRCGAN_OK;
+  }
   if (dw) {
     dim3 grid(taps * ceil_div(p->cin, bi) * ceil_div(p->cout, bo), splits);
     if (bi == 64 && bo == 64) conv_wgrad_simt<T, 64, 64, 4, 4><<<grid, 256, 0, st>>>(a, part, pps);
