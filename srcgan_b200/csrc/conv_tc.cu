@@ -138,6 +138,18 @@ __device__ __forceinline__ void umma_commit(uint64_t* bar) {
   asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(smem_u32(bar))
                : "memory");
 }
+// One lane of a fully converged warp.  The producer / MMA warps keep their control flow warp-uniform and
+// predicate only the issuing instructions with this: addresses, descriptors and loop counters then live in
+// uniform registers (no per-MMA R2UR round trips; a lone divergent lane cost ~150 cycles per UTCHMMA).
+__device__ __forceinline__ bool elect_one() {
+  uint32_t pred;
+  asm volatile(
+      "{\n\t.reg .pred p;\n\t"
+      "elect.sync _|p, 0xffffffff;\n\t"
+      "selp.u32 %0, 1, 0, p;\n\t}"
+      : "=r"(pred));
+  return pred != 0;
+}
 __device__ __forceinline__ void tc_fence_before() { asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory"); }
 __device__ __forceinline__ void tc_fence_after() { asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory"); }
 
@@ -160,30 +172,41 @@ __device__ __forceinline__ void unpack8(const uint4& q, float (&f)[8]) {
   for (int i = 0; i < 4; ++i) { f[2 * i] = __low2float(h[i]); f[2 * i + 1] = __high2float(h[i]); }
 }
 
+// Shared-memory / TMEM budget of one CTA.  A CTA works on a SUPER-TILE of MT = 256/BN adjacent pixel
+// tiles that share every weight stage (weights are the larger half of the L2->SMEM traffic at BN <= 64,
+// and L2->SMEM bandwidth, not the tensor pipe, bounds this kernel): the weight ring is filled once per
+// (chunk, load) and reused by MT activation slabs from a separate, deeper ring.  TMEM holds two sets of
+// MT accumulators (2 x 256 columns): the epilogue drains one set while the MMAs fill the other.
 template <int BN, int MAXT>
 struct Cfg {
+  static constexpr int MT = 256 / BN;
   static constexpr int A_BYTES = (TILE_H + MAXT - 1) * TILE_W * 128;
   static constexpr int B_TAP_BYTES = BN * 128;
   static constexpr int B_BYTES = MAXT * B_TAP_BYTES;
-  static constexpr int STAGE_BYTES = A_BYTES + B_BYTES;
-  static constexpr int STAGES_RAW = (SMEM_BUDGET - SMEM_AUX - 1024) / STAGE_BYTES;
-  static constexpr int STAGES = STAGES_RAW > 8 ? 8 : STAGES_RAW;
-  static constexpr int SMEM_BYTES = STAGES * STAGE_BYTES + SMEM_AUX + 1024;
-  static constexpr int TMEM_COLS = 2 * BN < 32 ? 32 : 2 * BN;     // 64 / 128 / 256: powers of two
+  static constexpr int NB = (3 * B_BYTES <= 80 * 1024) ? 3 : 2;
+  static constexpr int NA_RAW = (SMEM_BUDGET - SMEM_AUX - 1024 - NB * B_BYTES) / A_BYTES;
+  static constexpr int NA = NA_RAW > 10 ? 10 : NA_RAW;
+  static constexpr int SMEM_BYTES = NA * A_BYTES + NB * B_BYTES + SMEM_AUX + 1024;
+  static constexpr int TMEM_COLS = 512;
   static_assert(A_BYTES % 1024 == 0 && B_TAP_BYTES % 1024 == 0, "swizzle atoms must stay 1024-B aligned");
-  static_assert(STAGES >= 2, "not enough shared memory for a pipeline");
+  static_assert(NA >= 3, "not enough shared memory for the activation ring");
 };
 
 template <int BN, int MAXT>
 __global__ void __launch_bounds__(NUM_THREADS, 1)
 conv_igemm_tc(const __grid_constant__ CUtensorMap tmap_x, const TcArgs a) {
   using C = Cfg<BN, MAXT>;
+  constexpr int MT = C::MT;
   extern __shared__ uint8_t smem_raw[];
   uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~(uintptr_t)1023);
-  uint8_t* aux = smem + C::STAGES * C::STAGE_BYTES;
-  uint64_t* full_bar = reinterpret_cast<uint64_t*>(aux);            // [STAGES]
-  uint64_t* empty_bar = full_bar + C::STAGES;                        // [STAGES]
-  uint64_t* tfull_bar = empty_bar + C::STAGES;                       // [2]
+  uint8_t* smem_a = smem;
+  uint8_t* smem_b = smem + C::NA * C::A_BYTES;
+  uint8_t* aux = smem_b + C::NB * C::B_BYTES;
+  uint64_t* a_full = reinterpret_cast<uint64_t*>(aux);              // [NA]
+  uint64_t* a_empty = a_full + C::NA;                                // [NA]
+  uint64_t* b_full = a_empty + C::NA;                                // [NB]
+  uint64_t* b_empty = b_full + C::NB;                                // [NB]
+  uint64_t* tfull_bar = b_empty + C::NB;                             // [2]
   uint64_t* tempty_bar = tfull_bar + 2;                              // [2]
   uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(tempty_bar + 2);
   float* sbias = reinterpret_cast<float*>(aux + 512);                // [<=256]
@@ -191,7 +214,8 @@ conv_igemm_tc(const __grid_constant__ CUtensorMap tmap_x, const TcArgs a) {
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
 
   if (threadIdx.x == 0) {
-    for (int s = 0; s < C::STAGES; ++s) { mbar_init(&full_bar[s], 1); mbar_init(&empty_bar[s], 1); }
+    for (int s = 0; s < C::NA; ++s) { mbar_init(&a_full[s], 1); mbar_init(&a_empty[s], 1); }
+    for (int s = 0; s < C::NB; ++s) { mbar_init(&b_full[s], 1); mbar_init(&b_empty[s], 1); }
     for (int s = 0; s < 2; ++s) { mbar_init(&tfull_bar[s], 1); mbar_init(&tempty_bar[s], 128); }
     asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
   }
@@ -207,69 +231,100 @@ conv_igemm_tc(const __grid_constant__ CUtensorMap tmap_x, const TcArgs a) {
   tc_fence_after();
   const uint32_t tmem_base = *tmem_slot;
 
+  // super-tile t -> (n block, x group of MT tiles, tile row, image); identical decode in all roles
+  const int groups_x = (a.tiles_x + MT - 1) / MT;
+#define SRCGAN_DECODE_SUPERTILE(t)                                     \
+  const int nb = (int)((t) % a.n_blocks);                              \
+  long long r_ = (t) / a.n_blocks;                                     \
+  const int bxg = (int)(r_ % groups_x); r_ /= groups_x;                \
+  const int by = (int)(r_ % a.tiles_y);                                \
+  const int img = (int)(r_ / a.tiles_y);                               \
+  const int mcount = (a.tiles_x - bxg * MT) < MT ? (a.tiles_x - bxg * MT) : MT;
+
   if (warp == 0) {
-    // ------------------------------------------------------------------ TMA producer
-    if (lane == 0) {
-      int stage = 0;
-      uint32_t phase = 0;
+    // ------------------------------------------------------------------ TMA producer (warp-uniform)
+    {
+      int as = 0, bs = 0;
+      uint32_t aph = 0, bph = 0;
       for (long long t = blockIdx.x; t < a.num_tiles; t += gridDim.x) {
-        const int nb = (int)(t % a.n_blocks);
-        long long r = t / a.n_blocks;
-        const int bx = (int)(r % a.tiles_x); r /= a.tiles_x;
-        const int by = (int)(r % a.tiles_y);
-        const int img = (int)(r / a.tiles_y);
-        const int x0 = bx * TILE_W, y0 = by * TILE_H;
+        SRCGAN_DECODE_SUPERTILE(t)
+        const int y0 = by * TILE_H;
         for (int c = 0; c < a.nchunks; ++c) {
           for (int l = 0; l < a.plan.nloads; ++l) {
-            mbar_wait(&empty_bar[stage], phase ^ 1);
-            uint8_t* sa = smem + stage * C::STAGE_BYTES;
+            mbar_wait(&b_empty[bs], bph ^ 1);
             const uint32_t bbytes = (uint32_t)(a.plan.ntaps[l] * C::B_TAP_BYTES);
-            mbar_expect_tx(&full_bar[stage], C::A_BYTES + bbytes);
-            tma_load_4d(&tmap_x, &full_bar[stage], sa, c * KCH, a.plan.in_scale * x0 + a.plan.dx[l],
-                        a.plan.in_scale * y0 + a.plan.dy[l], img);
             const __nv_bfloat16* wsrc =
                 a.wgt + (((size_t)nb * a.nchunks + c) * a.plan.total_slots + a.plan.slot0[l]) * (size_t)(BN * KCH);
-            bulk_load(wsrc, &full_bar[stage], sa + C::A_BYTES, bbytes);
-            if (++stage == C::STAGES) { stage = 0; phase ^= 1; }
+            if (elect_one()) {
+              mbar_expect_tx(&b_full[bs], bbytes);
+              bulk_load(wsrc, &b_full[bs], smem_b + bs * C::B_BYTES, bbytes);
+            }
+            __syncwarp();
+            if (++bs == C::NB) { bs = 0; bph ^= 1; }
+            for (int m = 0; m < mcount; ++m) {
+              const int x0 = (bxg * MT + m) * TILE_W;
+              mbar_wait(&a_empty[as], aph ^ 1);
+              if (elect_one()) {
+                mbar_expect_tx(&a_full[as], C::A_BYTES);
+                tma_load_4d(&tmap_x, &a_full[as], smem_a + as * C::A_BYTES, c * KCH,
+                            a.plan.in_scale * x0 + a.plan.dx[l], a.plan.in_scale * y0 + a.plan.dy[l], img);
+              }
+              __syncwarp();
+              if (++as == C::NA) { as = 0; aph ^= 1; }
+            }
           }
         }
       }
     }
   } else if (warp == 1) {
-    // ------------------------------------------------------------------ MMA issuer
-    if (lane == 0) {
+    // ------------------------------------------------------------------ MMA issuer (warp-uniform)
+    {
       constexpr uint32_t idesc = umma_idesc(TILE_M, BN);
-      int stage = 0;
-      uint32_t phase = 0;
-      int acc = 0;
-      uint32_t acc_phase = 0;
+      int as = 0, bs = 0;
+      uint32_t aph = 0, bph = 0;
+      int set = 0;
+      uint32_t set_phase = 0;
       for (long long t = blockIdx.x; t < a.num_tiles; t += gridDim.x) {
-        mbar_wait(&tempty_bar[acc], acc_phase ^ 1);
+        SRCGAN_DECODE_SUPERTILE(t)
+        (void)nb; (void)by; (void)img;
+        mbar_wait(&tempty_bar[set], set_phase ^ 1);
         tc_fence_after();
-        const uint32_t tmem_d = tmem_base + (uint32_t)(acc * BN);
-        uint32_t accumulate = 0;
+        uint32_t started = 0;                       // 0 while the first (chunk, load) initialises the accumulators
         for (int c = 0; c < a.nchunks; ++c) {
           const int rem = a.cin - c * KCH;
           const int ksteps = (rem >= KCH ? KCH : rem) >> 4;
           for (int l = 0; l < a.plan.nloads; ++l) {
-            mbar_wait(&full_bar[stage], phase);
-            tc_fence_after();
-            const uint32_t sa = smem_u32(smem + stage * C::STAGE_BYTES);
-            const uint32_t sb = sa + C::A_BYTES;
+            mbar_wait(&b_full[bs], bph);
+            const uint32_t sb = smem_u32(smem_b + bs * C::B_BYTES);
             const int nt = a.plan.ntaps[l];
-            for (int j = 0; j < nt; ++j) {
-              for (int ks = 0; ks < ksteps; ++ks) {
-                umma_bf16(tmem_d, umma_desc(sa + j * (TILE_W * 128) + ks * 32),
-                          umma_desc(sb + j * C::B_TAP_BYTES + ks * 32), idesc, accumulate);
-                accumulate = 1;
+            for (int m = 0; m < mcount; ++m) {
+              mbar_wait(&a_full[as], aph);
+              tc_fence_after();
+              const uint32_t sa = smem_u32(smem_a + as * C::A_BYTES);
+              const uint32_t tmem_d = tmem_base + (uint32_t)((set * MT + m) * BN);
+              if (elect_one()) {
+                uint32_t accumulate = started;
+                for (int j = 0; j < nt; ++j) {
+                  for (int ks = 0; ks < ksteps; ++ks) {
+                    umma_bf16(tmem_d, umma_desc(sa + j * (TILE_W * 128) + ks * 32),
+                              umma_desc(sb + j * C::B_TAP_BYTES + ks * 32), idesc, accumulate);
+                    accumulate = 1;
+                  }
+                }
+                umma_commit(&a_empty[as]);         // frees the activation slab when these MMAs retire
               }
+              __syncwarp();
+              if (++as == C::NA) { as = 0; aph ^= 1; }
             }
-            umma_commit(&empty_bar[stage]);        // frees the SMEM stage when these MMAs retire
-            if (++stage == C::STAGES) { stage = 0; phase ^= 1; }
+            if (elect_one()) umma_commit(&b_empty[bs]);   // frees the weight stage
+            __syncwarp();
+            if (++bs == C::NB) { bs = 0; bph ^= 1; }
+            started = 1;
           }
         }
-        umma_commit(&tfull_bar[acc]);              // accumulator complete -> epilogue
-        if (++acc == 2) { acc = 0; acc_phase ^= 1; }
+        if (elect_one()) umma_commit(&tfull_bar[set]);    // all MT accumulators complete -> epilogue
+        __syncwarp();
+        if (++set == 2) { set = 0; set_phase ^= 1; }
       }
     }
   } else {
@@ -277,67 +332,68 @@ conv_igemm_tc(const __grid_constant__ CUtensorMap tmap_x, const TcArgs a) {
     const int q = warp & 3;                        // TMEM lane quadrant this warp may access
     const int row = q * 32 + lane;                 // GEMM row = tile pixel
     const int ty = row >> 3, tx = row & 7;
-    int acc = 0;
-    uint32_t acc_phase = 0;
+    int set = 0;
+    uint32_t set_phase = 0;
     for (long long t = blockIdx.x; t < a.num_tiles; t += gridDim.x) {
-      const int nb = (int)(t % a.n_blocks);
-      long long r = t / a.n_blocks;
-      const int bx = (int)(r % a.tiles_x); r /= a.tiles_x;
-      const int by = (int)(r % a.tiles_y);
-      const int img = (int)(r / a.tiles_y);
-      const int y = by * TILE_H + ty, x = bx * TILE_W + tx;
-      const bool valid = (y < a.gh) && (x < a.gw);
-      const long long pix = ((long long)img * a.oh + (y * a.os + a.oa)) * a.ow + (x * a.os + a.ob);
-      mbar_wait(&tfull_bar[acc], acc_phase);
+      SRCGAN_DECODE_SUPERTILE(t)
+      const int y = by * TILE_H + ty;
+      mbar_wait(&tfull_bar[set], set_phase);
       tc_fence_after();
-      const uint32_t taddr = tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)(acc * BN);
 #pragma unroll 1
-      for (int cb = 0; cb < BN; cb += 32) {
-        uint32_t v[32];
-        tmem_ld32(taddr + cb, v);
-        if (valid) {
-          const int c0 = nb * BN + cb;
+      for (int m = 0; m < mcount; ++m) {
+        const int x = (bxg * MT + m) * TILE_W + tx;
+        const bool valid = (y < a.gh) && (x < a.gw);
+        const long long pix = ((long long)img * a.oh + (y * a.os + a.oa)) * a.ow + (x * a.os + a.ob);
+        const uint32_t taddr = tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)((set * MT + m) * BN);
+#pragma unroll 1
+        for (int cb = 0; cb < BN; cb += 32) {
+          uint32_t v[32];
+          tmem_ld32(taddr + cb, v);
+          if (valid) {
+            const int c0 = nb * BN + cb;
 #pragma unroll
-          for (int g = 0; g < 4; ++g) {
-            float f[8];
+            for (int g = 0; g < 4; ++g) {
+              float f[8];
 #pragma unroll
-            for (int i = 0; i < 8; ++i) {
-              float t0 = __uint_as_float(v[g * 8 + i]) + sbias[c0 + g * 8 + i];
-              if (a.act) t0 = t0 > 0.f ? t0 : t0 * a.act_slope;
-              f[i] = t0 * a.alpha;
+              for (int i = 0; i < 8; ++i) {
+                float t0 = __uint_as_float(v[g * 8 + i]) + sbias[c0 + g * 8 + i];
+                if (a.act) t0 = t0 > 0.f ? t0 : t0 * a.act_slope;
+                f[i] = t0 * a.alpha;
+              }
+              const int cc = c0 + g * 8;
+              if (a.r1) {
+                float rr[8];
+                unpack8(__ldg(reinterpret_cast<const uint4*>(a.r1 + pix * a.r1_ld + cc)), rr);
+#pragma unroll
+                for (int i = 0; i < 8; ++i) f[i] = fmaf(a.beta1, rr[i], f[i]);
+              }
+              if (a.r2) {
+                float rr[8];
+                unpack8(__ldg(reinterpret_cast<const uint4*>(a.r2 + pix * a.r2_ld + cc)), rr);
+#pragma unroll
+                for (int i = 0; i < 8; ++i) f[i] = fmaf(a.beta2, rr[i], f[i]);
+              }
+              if (a.mask) {
+                float mm[8];
+                unpack8(__ldg(reinterpret_cast<const uint4*>(a.mask + pix * a.mask_ld + cc)), mm);
+#pragma unroll
+                for (int i = 0; i < 8; ++i) f[i] *= (mm[i] > 0.f ? 1.f : a.mask_slope);
+              }
+              uint4 o;
+              __nv_bfloat162* oh = reinterpret_cast<__nv_bfloat162*>(&o);
+#pragma unroll
+              for (int i = 0; i < 4; ++i) oh[i] = __floats2bfloat162_rn(f[2 * i], f[2 * i + 1]);
+              *reinterpret_cast<uint4*>(a.y + pix * a.y_ld + cc) = o;
             }
-            const int cc = c0 + g * 8;
-            if (a.r1) {
-              float rr[8];
-              unpack8(__ldg(reinterpret_cast<const uint4*>(a.r1 + pix * a.r1_ld + cc)), rr);
-#pragma unroll
-              for (int i = 0; i < 8; ++i) f[i] = fmaf(a.beta1, rr[i], f[i]);
-            }
-            if (a.r2) {
-              float rr[8];
-              unpack8(__ldg(reinterpret_cast<const uint4*>(a.r2 + pix * a.r2_ld + cc)), rr);
-#pragma unroll
-              for (int i = 0; i < 8; ++i) f[i] = fmaf(a.beta2, rr[i], f[i]);
-            }
-            if (a.mask) {
-              float mm[8];
-              unpack8(__ldg(reinterpret_cast<const uint4*>(a.mask + pix * a.mask_ld + cc)), mm);
-#pragma unroll
-              for (int i = 0; i < 8; ++i) f[i] *= (mm[i] > 0.f ? 1.f : a.mask_slope);
-            }
-            uint4 o;
-            __nv_bfloat162* oh = reinterpret_cast<__nv_bfloat162*>(&o);
-#pragma unroll
-            for (int i = 0; i < 4; ++i) oh[i] = __floats2bfloat162_rn(f[2 * i], f[2 * i + 1]);
-            *reinterpret_cast<uint4*>(a.y + pix * a.y_ld + cc) = o;
           }
         }
       }
       tc_fence_before();
-      mbar_arrive(&tempty_bar[acc]);
-      if (++acc == 2) { acc = 0; acc_phase ^= 1; }
+      mbar_arrive(&tempty_bar[set]);
+      if (++set == 2) { set = 0; set_phase ^= 1; }
     }
   }
+#undef SRCGAN_DECODE_SUPERTILE
 
   tc_fence_before();
   __syncthreads();
@@ -411,6 +467,7 @@ static int make_tmap(CUtensorMap* tm, const void* ptr, int c, int w, int h, int 
 }
 
 static int bn_for(int cout) { return cout >= 128 ? 128 : cout; }
+static long long supertiles(int tiles_x, int bn) { const int mt = 256 / bn; return (tiles_x + mt - 1) / mt; }
 
 struct HostPlan {
   Plan plan;
@@ -585,7 +642,7 @@ int conv_fprop_tc(const srcgan_conv_params* p, cudaStream_t st) {
   a.n_blocks = p->cout / bn;
   a.tiles_x = (a.gw + tc::TILE_W - 1) / tc::TILE_W;
   a.tiles_y = (a.gh + tc::TILE_H - 1) / tc::TILE_H;
-  a.num_tiles = (long long)a.tiles_x * a.tiles_y * p->n * a.n_blocks;
+  a.num_tiles = tc::supertiles(a.tiles_x, bn) * a.tiles_y * p->n * a.n_blocks;
   tc::fill_epilogue(a, p);
   return tc::dispatch(bn, hp.maxt, tmap, a, st);
 }
@@ -610,7 +667,7 @@ int conv_dgrad_tc(const srcgan_conv_params* p, cudaStream_t st) {
       a.n_blocks = p->cin / bn;
       a.tiles_x = (a.gw + tc::TILE_W - 1) / tc::TILE_W;
       a.tiles_y = (a.gh + tc::TILE_H - 1) / tc::TILE_H;
-      a.num_tiles = (long long)a.tiles_x * a.tiles_y * p->n * a.n_blocks;
+      a.num_tiles = tc::supertiles(a.tiles_x, bn) * a.tiles_y * p->n * a.n_blocks;
       tc::fill_epilogue(a, p);
       a.wgt = w;
       a.bias = nullptr;
@@ -722,7 +779,7 @@ conv_wgrad_tc_kernel(const __grid_constant__ CUtensorMap tmap_x, const __grid_co
   if (t_end > a.num_tiles) t_end = a.num_tiles;
 
   if (warp == 0) {
-    if (lane == 0) {
+    {
       int stage = 0;
       uint32_t phase = 0;
       for (long long t = t_beg; t < t_end; ++t) {
@@ -733,17 +790,20 @@ conv_wgrad_tc_kernel(const __grid_constant__ CUtensorMap tmap_x, const __grid_co
         const int x0 = bx * TILE_W, y0 = by * TILE_H;
         mbar_wait(&empty_bar[stage], phase ^ 1);
         uint8_t* sa = smem + stage * C::STAGE_BYTES;
-        mbar_expect_tx(&full_bar[stage], C::STAGE_BYTES);
-        tma_load_4d(&tmap_x, &full_bar[stage], sa, cb * 128, sc * x0 + ox, sc * y0 + oy, img);
-        tma_load_4d(&tmap_x, &full_bar[stage], sa + C::A_SLAB, cb * 128 + 64, sc * x0 + ox, sc * y0 + oy, img);
+        if (elect_one()) {
+          mbar_expect_tx(&full_bar[stage], C::STAGE_BYTES);
+          tma_load_4d(&tmap_x, &full_bar[stage], sa, cb * 128, sc * x0 + ox, sc * y0 + oy, img);
+          tma_load_4d(&tmap_x, &full_bar[stage], sa + C::A_SLAB, cb * 128 + 64, sc * x0 + ox, sc * y0 + oy, img);
 #pragma unroll
-        for (int j = 0; j < BN / 64; ++j)
-          tma_load_4d(&tmap_g, &full_bar[stage], sa + C::A_BYTES + j * C::G_SLAB, nb * BN + j * 64, x0, y0, img);
+          for (int j = 0; j < BN / 64; ++j)
+            tma_load_4d(&tmap_g, &full_bar[stage], sa + C::A_BYTES + j * C::G_SLAB, nb * BN + j * 64, x0, y0, img);
+        }
+        __syncwarp();
         if (++stage == C::STAGES) { stage = 0; phase ^= 1; }
       }
     }
   } else if (warp == 1) {
-    if (lane == 0) {
+    {
       constexpr uint32_t idesc = umma_idesc_mn(128, BN);
       int stage = 0;
       uint32_t phase = 0;
@@ -753,19 +813,23 @@ conv_wgrad_tc_kernel(const __grid_constant__ CUtensorMap tmap_x, const __grid_co
         tc_fence_after();
         const uint32_t sa = smem_u32(smem + stage * C::STAGE_BYTES);
         const uint32_t sg = sa + C::A_BYTES;
-        for (int kh = 0; kh < nt; ++kh) {
+        if (elect_one()) {
+          for (int kh = 0; kh < nt; ++kh) {
 #pragma unroll
-          for (int ks = 0; ks < TILE_M / 16; ++ks) {
-            umma_bf16(tmem_base + (uint32_t)(kh * BN),
-                      umma_desc_mn(sa + kh * (TILE_W * 128) + ks * 2048, C::A_SLAB),
-                      umma_desc_mn(sg + ks * 2048, C::G_SLAB), idesc, accumulate | (uint32_t)(ks > 0));
+            for (int ks = 0; ks < TILE_M / 16; ++ks) {
+              umma_bf16(tmem_base + (uint32_t)(kh * BN),
+                        umma_desc_mn(sa + kh * (TILE_W * 128) + ks * 2048, C::A_SLAB),
+                        umma_desc_mn(sg + ks * 2048, C::G_SLAB), idesc, accumulate | (uint32_t)(ks > 0));
+            }
           }
+          umma_commit(&empty_bar[stage]);
         }
+        __syncwarp();
         accumulate = 1;
-        umma_commit(&empty_bar[stage]);
         if (++stage == C::STAGES) { stage = 0; phase ^= 1; }
       }
-      umma_commit(done_bar);
+      if (elect_one()) umma_commit(done_bar);
+      __syncwarp();
     }
   } else {
     const int q = warp & 3;
