@@ -22,6 +22,7 @@
 #include <cuda.h>
 
 #include <mutex>
+#include <stdlib.h>
 
 #include "common.cuh"
 
@@ -132,6 +133,25 @@ __device__ __forceinline__ void umma_bf16(uint32_t tmem_d, uint64_t adesc, uint6
       "setp.ne.b32 p, %4, 0;\n\t"
       "tcgen05.mma.cta_group::1.kind::f16 [%0], %1, %2, %3, p;\n\t}"
       ::"r"(tmem_d), "l"(adesc), "l"(bdesc), "r"(idesc), "r"(accumulate)
+      : "memory");
+}
+// Descriptor words kept separately: every descriptor of a stage differs from the stage's base only in
+// the low word (start address >> 4), so an MMA costs one uniform add per operand at issue.
+__device__ __forceinline__ uint32_t desc_lo(uint32_t saddr, uint32_t lbo_bytes = 16) {
+  return ((saddr & 0x3FFFFu) >> 4) | (((lbo_bytes >> 4) & 0x3FFFu) << 16);
+}
+__host__ __device__ constexpr uint32_t desc_hi(uint32_t sbo_bytes) {
+  return (sbo_bytes >> 4) | (1u << 14) | (2u << 29);      // SBO, descriptor version 1, SWIZZLE_128B
+}
+__device__ __forceinline__ void umma_bf16_w(uint32_t tmem_d, uint32_t a_lo, uint32_t a_hi, uint32_t b_lo, uint32_t b_hi,
+                                            uint32_t idesc, uint32_t accumulate) {
+  asm volatile(
+      "{\n\t.reg .pred p;\n\t.reg .b64 da, db;\n\t"
+      "setp.ne.b32 p, %6, 0;\n\t"
+      "mov.b64 da, {%1, %2};\n\t"
+      "mov.b64 db, {%3, %4};\n\t"
+      "tcgen05.mma.cta_group::1.kind::f16 [%0], da, db, %5, p;\n\t}"
+      ::"r"(tmem_d), "r"(a_lo), "r"(a_hi), "r"(b_lo), "r"(b_hi), "r"(idesc), "r"(accumulate)
       : "memory");
 }
 __device__ __forceinline__ void umma_commit(uint64_t* bar) {
@@ -303,12 +323,23 @@ conv_igemm_tc(const __grid_constant__ CUtensorMap tmap_x, const TcArgs a) {
               const uint32_t sa = smem_u32(smem_a + as * C::A_BYTES);
               const uint32_t tmem_d = tmem_base + (uint32_t)((set * MT + m) * BN);
               if (elect_one()) {
+                const uint32_t a_lo = desc_lo(sa), b_lo = desc_lo(sb);
+                constexpr uint32_t d_hi = desc_hi(1024);
                 uint32_t accumulate = started;
                 for (int j = 0; j < nt; ++j) {
-                  for (int ks = 0; ks < ksteps; ++ks) {
-                    umma_bf16(tmem_d, umma_desc(sa + j * (TILE_W * 128) + ks * 32),
-                              umma_desc(sb + j * C::B_TAP_BYTES + ks * 32), idesc, accumulate);
-                    accumulate = 1;
+                  if (ksteps == 4) {
+#pragma unroll
+                    for (int ks = 0; ks < 4; ++ks) {
+                      umma_bf16_w(tmem_d, a_lo + (uint32_t)(j * (TILE_W * 8) + ks * 2), d_hi,
+                                  b_lo + (uint32_t)(j * (C::B_TAP_BYTES >> 4) + ks * 2), d_hi, idesc, accumulate);
+                      accumulate = 1;
+                    }
+                  } else {
+                    for (int ks = 0; ks < ksteps; ++ks) {
+                      umma_bf16_w(tmem_d, a_lo + (uint32_t)(j * (TILE_W * 8) + ks * 2), d_hi,
+                                  b_lo + (uint32_t)(j * (C::B_TAP_BYTES >> 4) + ks * 2), d_hi, idesc, accumulate);
+                      accumulate = 1;
+                    }
                   }
                 }
                 umma_commit(&a_empty[as]);         // frees the activation slab when these MMAs retire
@@ -403,6 +434,250 @@ conv_igemm_tc(const __grid_constant__ CUtensorMap tmap_x, const TcArgs a) {
   }
 }
 
+// ---------------------------------------------------------------------------------------------
+// 3x3 stride-1 fprop (and dgrad-as-fprop) for BN = 32 / 64 - the dense-block, HRconv, trunk and Decoder
+// shapes that carry >90 % of the step's FLOPs.  Measured on B200 (scripts/exp/exp_halo.cu): the UMMA
+// SWIZZLE_128B pattern is a pure function of the shared-memory ADDRESS, so a K-major A descriptor may
+// start at any 128-byte row, not only at a 1024-byte atom.  One haloed slab [18 rows][10 px][64 ch]
+// (23 KB, one TMA box) therefore feeds all nine taps of a tile: tap (kh,kw) = start + (kh*10+kw)*128 B,
+// SBO = 1280 B.  That is 2.4x less L2->SMEM traffic than three kw-shifted slabs - and L2->SMEM feed is
+// what bounds these kernels.  The chunk's nine weight tiles form ONE stage shared by the 256/BN pixel
+// tiles of a super-tile.
+// ---------------------------------------------------------------------------------------------
+constexpr int HALO_W = TILE_W + 2, HALO_H = TILE_H + 2;
+template <int BN>
+struct HCfg {
+  static constexpr int MT = 256 / BN;
+  static constexpr int A_BOX_BYTES = HALO_H * HALO_W * 128;                  // 23040
+  static constexpr int A_STRIDE = (A_BOX_BYTES + 1023) / 1024 * 1024;        // 23552
+  static constexpr int B_TAP_BYTES = BN * 128;
+  static constexpr int B_BYTES = 9 * B_TAP_BYTES;
+  static constexpr int NB = 2;
+  static constexpr int NA_RAW = (SMEM_BUDGET - SMEM_AUX - 1024 - NB * B_BYTES) / A_STRIDE;
+  static constexpr int NA = NA_RAW > 8 ? 8 : NA_RAW;
+  static constexpr int SMEM_BYTES = NA * A_STRIDE + NB * B_BYTES + SMEM_AUX + 1024;
+  static constexpr int TMEM_COLS = 512;
+  static_assert(NA >= 3, "not enough shared memory for the activation ring");
+};
+
+__device__ __forceinline__ uint64_t umma_desc_sbo(uint32_t saddr, uint32_t sbo_bytes) {
+  uint64_t d = 0;
+  d |= (uint64_t)((saddr & 0x3FFFFu) >> 4);
+  d |= (uint64_t)1 << 16;
+  d |= (uint64_t)(sbo_bytes >> 4) << 32;
+  d |= (uint64_t)1 << 46;
+  d |= (uint64_t)2 << 61;
+  return d;
+}
+
+template <int BN>
+__global__ void __launch_bounds__(NUM_THREADS, 1)
+conv3x3_halo_tc(const __grid_constant__ CUtensorMap tmap_x, const TcArgs a) {
+  using C = HCfg<BN>;
+  constexpr int MT = C::MT;
+  extern __shared__ uint8_t smem_raw[];
+  uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~(uintptr_t)1023);
+  uint8_t* smem_a = smem;
+  uint8_t* smem_b = smem + C::NA * C::A_STRIDE;
+  uint8_t* aux = smem_b + C::NB * C::B_BYTES;
+  uint64_t* a_full = reinterpret_cast<uint64_t*>(aux);
+  uint64_t* a_empty = a_full + C::NA;
+  uint64_t* b_full = a_empty + C::NA;
+  uint64_t* b_empty = b_full + C::NB;
+  uint64_t* tfull_bar = b_empty + C::NB;
+  uint64_t* tempty_bar = tfull_bar + 2;
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(tempty_bar + 2);
+  float* sbias = reinterpret_cast<float*>(aux + 512);
+
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  if (threadIdx.x == 0) {
+    for (int s = 0; s < C::NA; ++s) { mbar_init(&a_full[s], 1); mbar_init(&a_empty[s], 1); }
+    for (int s = 0; s < C::NB; ++s) { mbar_init(&b_full[s], 1); mbar_init(&b_empty[s], 1); }
+    for (int s = 0; s < 2; ++s) { mbar_init(&tfull_bar[s], 1); mbar_init(&tempty_bar[s], 128); }
+    asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+  }
+  for (int i = threadIdx.x; i < a.cout; i += NUM_THREADS) sbias[i] = a.bias ? a.bias[i] : 0.f;
+  if (warp == 1) {
+    asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(tmem_slot)),
+                 "r"((uint32_t)C::TMEM_COLS)
+                 : "memory");
+    asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
+  }
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  const uint32_t tmem_base = *tmem_slot;
+  const int groups_x = (a.tiles_x + MT - 1) / MT;
+  const int pad = -a.plan.dy[0];
+#define SRCGAN_DECODE_SUPERTILE(t)                                     \
+  const int nb = (int)((t) % a.n_blocks);                              \
+  long long r_ = (t) / a.n_blocks;                                     \
+  const int bxg = (int)(r_ % groups_x); r_ /= groups_x;                \
+  const int by = (int)(r_ % a.tiles_y);                                \
+  const int img = (int)(r_ / a.tiles_y);                               \
+  const int mcount = (a.tiles_x - bxg * MT) < MT ? (a.tiles_x - bxg * MT) : MT;
+
+  if (warp == 0) {
+    int as = 0, bs = 0;
+    uint32_t aph = 0, bph = 0;
+    for (long long t = blockIdx.x; t < a.num_tiles; t += gridDim.x) {
+      SRCGAN_DECODE_SUPERTILE(t)
+      const int y0 = by * TILE_H;
+      for (int c = 0; c < a.nchunks; ++c) {
+        mbar_wait(&b_empty[bs], bph ^ 1);
+        const __nv_bfloat16* wsrc = a.wgt + (((size_t)nb * a.nchunks + c) * 9) * (size_t)(BN * KCH);
+        if (elect_one()) {
+          mbar_expect_tx(&b_full[bs], C::B_BYTES);
+          bulk_load(wsrc, &b_full[bs], smem_b + bs * C::B_BYTES, C::B_BYTES);
+        }
+        __syncwarp();
+        if (++bs == C::NB) { bs = 0; bph ^= 1; }
+        for (int m = 0; m < mcount; ++m) {
+          const int x0 = (bxg * MT + m) * TILE_W;
+          mbar_wait(&a_empty[as], aph ^ 1);
+          if (elect_one()) {
+            mbar_expect_tx(&a_full[as], C::A_BOX_BYTES);
+            tma_load_4d(&tmap_x, &a_full[as], smem_a + as * C::A_STRIDE, c * KCH, x0 - pad, y0 - pad, img);
+          }
+          __syncwarp();
+          if (++as == C::NA) { as = 0; aph ^= 1; }
+        }
+      }
+    }
+  } else if (warp == 1) {
+    constexpr uint32_t idesc = umma_idesc(TILE_M, BN);
+    int as = 0, bs = 0;
+    uint32_t aph = 0, bph = 0;
+    int set = 0;
+    uint32_t set_phase = 0;
+    for (long long t = blockIdx.x; t < a.num_tiles; t += gridDim.x) {
+      SRCGAN_DECODE_SUPERTILE(t)
+      (void)nb; (void)by; (void)img;
+      mbar_wait(&tempty_bar[set], set_phase ^ 1);
+      tc_fence_after();
+      for (int c = 0; c < a.nchunks; ++c) {
+        const int rem = a.cin - c * KCH;
+        const int ksteps = (rem >= KCH ? KCH : rem) >> 4;
+        mbar_wait(&b_full[bs], bph);
+        const uint32_t sb = smem_u32(smem_b + bs * C::B_BYTES);
+        for (int m = 0; m < mcount; ++m) {
+          mbar_wait(&a_full[as], aph);
+          tc_fence_after();
+          const uint32_t sa = smem_u32(smem_a + as * C::A_STRIDE);
+          const uint32_t tmem_d = tmem_base + (uint32_t)((set * MT + m) * BN);
+          if (elect_one()) {
+            const uint32_t a_lo = desc_lo(sa), b_lo = desc_lo(sb);
+            constexpr uint32_t a_hi = desc_hi(HALO_W * 128), b_hi = desc_hi(1024);
+            uint32_t accumulate = c > 0 ? 1u : 0u;
+            if (ksteps == 4) {
+#pragma unroll
+              for (int fw = 0; fw < 3; ++fw)
+#pragma unroll
+                for (int fh = 0; fh < 3; ++fh)
+#pragma unroll
+                  for (int ks = 0; ks < 4; ++ks) {
+                    umma_bf16_w(tmem_d, a_lo + (uint32_t)((fh * HALO_W + fw) * 8 + ks * 2), a_hi,
+                                b_lo + (uint32_t)(((fw * 3 + fh) * C::B_TAP_BYTES >> 4) + ks * 2), b_hi, idesc, accumulate);
+                    accumulate = 1;
+                  }
+            } else {
+#pragma unroll 1
+              for (int tap = 0; tap < 9; ++tap) {
+                const int fw = tap / 3, fh = tap - fw * 3;
+                for (int ks = 0; ks < ksteps; ++ks) {
+                  umma_bf16_w(tmem_d, a_lo + (uint32_t)((fh * HALO_W + fw) * 8 + ks * 2), a_hi,
+                              b_lo + (uint32_t)((tap * C::B_TAP_BYTES >> 4) + ks * 2), b_hi, idesc, accumulate);
+                  accumulate = 1;
+                }
+              }
+            }
+            umma_commit(&a_empty[as]);
+          }
+          __syncwarp();
+          if (++as == C::NA) { as = 0; aph ^= 1; }
+        }
+        if (elect_one()) umma_commit(&b_empty[bs]);
+        __syncwarp();
+        if (++bs == C::NB) { bs = 0; bph ^= 1; }
+      }
+      if (elect_one()) umma_commit(&tfull_bar[set]);
+      __syncwarp();
+      if (++set == 2) { set = 0; set_phase ^= 1; }
+    }
+  } else {
+    const int q = warp & 3;
+    const int row = q * 32 + lane;
+    const int ty = row >> 3, tx = row & 7;
+    int set = 0;
+    uint32_t set_phase = 0;
+    for (long long t = blockIdx.x; t < a.num_tiles; t += gridDim.x) {
+      SRCGAN_DECODE_SUPERTILE(t)
+      const int y = by * TILE_H + ty;
+      mbar_wait(&tfull_bar[set], set_phase);
+      tc_fence_after();
+#pragma unroll 1
+      for (int m = 0; m < mcount; ++m) {
+        const int x = (bxg * MT + m) * TILE_W + tx;
+        const bool valid = (y < a.gh) && (x < a.gw);
+        const long long pix = ((long long)img * a.oh + y) * a.ow + x;
+        const uint32_t taddr = tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)((set * MT + m) * BN);
+#pragma unroll 1
+        for (int cb = 0; cb < BN; cb += 32) {
+          uint32_t v[32];
+          tmem_ld32(taddr + cb, v);
+          if (valid) {
+            const int c0 = nb * BN + cb;
+#pragma unroll
+            for (int g = 0; g < 4; ++g) {
+              float f[8];
+#pragma unroll
+              for (int i = 0; i < 8; ++i) {
+                float t0 = __uint_as_float(v[g * 8 + i]) + sbias[c0 + g * 8 + i];
+                if (a.act) t0 = t0 > 0.f ? t0 : t0 * a.act_slope;
+                f[i] = t0 * a.alpha;
+              }
+              const int cc = c0 + g * 8;
+              if (a.r1) {
+                float rr[8];
+                unpack8(__ldg(reinterpret_cast<const uint4*>(a.r1 + pix * a.r1_ld + cc)), rr);
+#pragma unroll
+                for (int i = 0; i < 8; ++i) f[i] = fmaf(a.beta1, rr[i], f[i]);
+              }
+              if (a.r2) {
+                float rr[8];
+                unpack8(__ldg(reinterpret_cast<const uint4*>(a.r2 + pix * a.r2_ld + cc)), rr);
+#pragma unroll
+                for (int i = 0; i < 8; ++i) f[i] = fmaf(a.beta2, rr[i], f[i]);
+              }
+              if (a.mask) {
+                float mm[8];
+                unpack8(__ldg(reinterpret_cast<const uint4*>(a.mask + pix * a.mask_ld + cc)), mm);
+#pragma unroll
+                for (int i = 0; i < 8; ++i) f[i] *= (mm[i] > 0.f ? 1.f : a.mask_slope);
+              }
+              uint4 o;
+              __nv_bfloat162* oh = reinterpret_cast<__nv_bfloat162*>(&o);
+#pragma unroll
+              for (int i = 0; i < 4; ++i) oh[i] = __floats2bfloat162_rn(f[2 * i], f[2 * i + 1]);
+              *reinterpret_cast<uint4*>(a.y + pix * a.y_ld + cc) = o;
+            }
+          }
+        }
+      }
+      tc_fence_before();
+      mbar_arrive(&tempty_bar[set]);
+      if (++set == 2) { set = 0; set_phase ^= 1; }
+    }
+  }
+#undef SRCGAN_DECODE_SUPERTILE
+  tc_fence_before();
+  __syncthreads();
+  if (warp == 1) {
+    asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "r"((uint32_t)C::TMEM_COLS)
+                 : "memory");
+  }
+}
+
 // fp32 OIHW -> bf16 [n_block][chunk][slot][BN][64]: each [BN][64] tile is stored as its SWIZZLE_128B
 // shared-memory image (16-byte chunk j of row r lives at chunk j ^ (r & 7)), zero padded in K.
 // Rows are the GEMM-N channels, columns the GEMM-K channels: (co, ci) for fprop, (ci, co) for dgrad.
@@ -449,12 +724,12 @@ static EncodeTiledFn get_encode_fn() {
 // NHWC bf16 tensor (c channels at ptr, pixel pitch ld) -> tensor map whose box is the sampled slab
 // [rows][8 px][64 ch]; sample = 1 (dense) or 2 (every other pixel, for stride-2 convolutions).
 static int make_tmap(CUtensorMap* tm, const void* ptr, int c, int w, int h, int n, int ld, int rows, int sample,
-                     const char* what) {
+                     const char* what, int box_w = TILE_W) {
   EncodeTiledFn encode = get_encode_fn();
   SRCGAN_REQUIRE(encode != nullptr, "%s: cuTensorMapEncodeTiled is not available from the driver", what);
   cuuint64_t gdim[4] = {(cuuint64_t)c, (cuuint64_t)w, (cuuint64_t)h, (cuuint64_t)n};
   cuuint64_t gstr[3] = {(cuuint64_t)ld * 2, (cuuint64_t)ld * 2 * w, (cuuint64_t)ld * 2 * w * h};
-  cuuint32_t box[4] = {(cuuint32_t)KCH, (cuuint32_t)(TILE_W * sample), (cuuint32_t)(rows * sample), 1};
+  cuuint32_t box[4] = {(cuuint32_t)KCH, (cuuint32_t)(box_w * sample), (cuuint32_t)(rows * sample), 1};
   cuuint32_t estr[4] = {1, (cuuint32_t)sample, (cuuint32_t)sample, 1};
   CUresult cr = encode(tm, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 4, const_cast<void*>(ptr), gdim, gstr, box, estr,
                        CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
@@ -556,6 +831,20 @@ static int launch(const CUtensorMap& tmap, const TcArgs& a, cudaStream_t st) {
   return check_launch("conv_igemm_tc");
 }
 
+template <int BN>
+static int launch_halo(const CUtensorMap& tmap, const TcArgs& a, cudaStream_t st) {
+  using C = HCfg<BN>;
+  static bool attr_set = false;
+  if (!attr_set) {
+    SRCGAN_CUDA(cudaFuncSetAttribute(conv3x3_halo_tc<BN>, cudaFuncAttributeMaxDynamicSharedMemorySize, C::SMEM_BYTES));
+    attr_set = true;
+  }
+  long long grid = a.num_tiles < kNumSMs ? a.num_tiles : kNumSMs;
+  conv3x3_halo_tc<BN><<<(unsigned)grid, NUM_THREADS, C::SMEM_BYTES, st>>>(tmap, a);
+  count_launch();
+  return check_launch("conv3x3_halo_tc");
+}
+
 static int dispatch(int bn, int maxt, const CUtensorMap& tmap, const TcArgs& a, cudaStream_t st) {
 #define SRCGAN_TC_CASE(B, T) if (bn == B && maxt == T) return launch<B, T>(tmap, a, st)
   SRCGAN_TC_CASE(32, 2); SRCGAN_TC_CASE(64, 2); SRCGAN_TC_CASE(128, 2);
@@ -629,9 +918,12 @@ int pack_weights_tc_host(const float* w, int cout, int cin, int kh, int kw, int 
 
 int conv_fprop_tc(const srcgan_conv_params* p, cudaStream_t st) {
   tc::HostPlan hp = tc::fprop_plan(p->kh, p->stride, p->pad);
+  const bool halo = p->kh == 3 && p->stride == 1 && (p->cout == 32 || p->cout == 64) && !getenv("SRCGAN_B200_NO_HALO");
   CUtensorMap tmap;
-  int rc = tc::make_tmap(&tmap, p->x, p->cin, p->w, p->h, p->n, p->x_ld, tc::TILE_H + hp.maxt - 1, p->stride,
-                         "conv_fprop_tc");
+  int rc = halo ? tc::make_tmap(&tmap, p->x, p->cin, p->w, p->h, p->n, p->x_ld, tc::HALO_H, 1, "conv_fprop_tc",
+                                tc::HALO_W)
+                : tc::make_tmap(&tmap, p->x, p->cin, p->w, p->h, p->n, p->x_ld, tc::TILE_H + hp.maxt - 1, p->stride,
+                                "conv_fprop_tc");
   if (rc) return rc;
   tc::TcArgs a;
   a.n = p->n; a.cin = p->cin; a.cout = p->cout;
@@ -644,6 +936,7 @@ int conv_fprop_tc(const srcgan_conv_params* p, cudaStream_t st) {
   a.tiles_y = (a.gh + tc::TILE_H - 1) / tc::TILE_H;
   a.num_tiles = tc::supertiles(a.tiles_x, bn) * a.tiles_y * p->n * a.n_blocks;
   tc::fill_epilogue(a, p);
+  if (halo) return bn == 32 ? tc::launch_halo<32>(tmap, a, st) : tc::launch_halo<64>(tmap, a, st);
   return tc::dispatch(bn, hp.maxt, tmap, a, st);
 }
 
@@ -814,12 +1107,13 @@ conv_wgrad_tc_kernel(const __grid_constant__ CUtensorMap tmap_x, const __grid_co
         const uint32_t sa = smem_u32(smem + stage * C::STAGE_BYTES);
         const uint32_t sg = sa + C::A_BYTES;
         if (elect_one()) {
+          const uint32_t a_lo = desc_lo(sa, C::A_SLAB), g_lo = desc_lo(sg, C::G_SLAB);
+          constexpr uint32_t d_hi = desc_hi(1024);
           for (int kh = 0; kh < nt; ++kh) {
 #pragma unroll
             for (int ks = 0; ks < TILE_M / 16; ++ks) {
-              umma_bf16(tmem_base + (uint32_t)(kh * BN),
-                        umma_desc_mn(sa + kh * (TILE_W * 128) + ks * 2048, C::A_SLAB),
-                        umma_desc_mn(sg + ks * 2048, C::G_SLAB), idesc, accumulate | (uint32_t)(ks > 0));
+              umma_bf16_w(tmem_base + (uint32_t)(kh * BN), a_lo + (uint32_t)(kh * (TILE_W * 8) + ks * 128), d_hi,
+                          g_lo + (uint32_t)(ks * 128), d_hi, idesc, accumulate | (uint32_t)(ks > 0));
             }
           }
           umma_commit(&empty_bar[stage]);
