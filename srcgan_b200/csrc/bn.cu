@@ -85,6 +85,67 @@ __global__ void bn_apply(const T* __restrict__ x, int x_ld, T* __restrict__ y, i
   y[m * y_ld + ch] = from_f32<T>(v);
 }
 
+// bf16 fast paths: 16-byte vectors, 8 channels per thread (c % 8 == 0, lds % 8 == 0, 16-byte aligned)
+__device__ __forceinline__ void unpack8b(const uint4& q, float (&f)[8]) {
+  const __nv_bfloat162* h = reinterpret_cast<const __nv_bfloat162*>(&q);
+#pragma unroll
+  for (int i = 0; i < 4; ++i) { f[2 * i] = __low2float(h[i]); f[2 * i + 1] = __high2float(h[i]); }
+}
+__device__ __forceinline__ uint4 pack8b(const float (&f)[8]) {
+  uint4 o;
+  __nv_bfloat162* h = reinterpret_cast<__nv_bfloat162*>(&o);
+#pragma unroll
+  for (int i = 0; i < 4; ++i) h[i] = __floats2bfloat162_rn(f[2 * i], f[2 * i + 1]);
+  return o;
+}
+
+__global__ void bn_apply_vec(const __nv_bfloat16* __restrict__ x, int x_ld, __nv_bfloat16* __restrict__ y, int y_ld,
+                             int64_t npix, int c, const float* __restrict__ gamma, const float* __restrict__ beta,
+                             const float* __restrict__ mean, const float* __restrict__ invstd, float slope) {
+  const int oct = c >> 3;
+  int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= npix * oct) return;
+  const int ch = (int)(i % oct) * 8;
+  const int64_t m = i / oct;
+  float f[8];
+  unpack8b(__ldg(reinterpret_cast<const uint4*>(x + m * x_ld + ch)), f);
+#pragma unroll
+  for (int k = 0; k < 8; ++k) {
+    float v = fmaf(f[k] - mean[ch + k], gamma[ch + k] * invstd[ch + k], beta[ch + k]);
+    f[k] = v > 0.f ? v : v * slope;
+  }
+  *reinterpret_cast<uint4*>(y + m * y_ld + ch) = pack8b(f);
+}
+
+__global__ void bn_bwd_apply_vec(const __nv_bfloat16* __restrict__ dy, int dy_ld, const __nv_bfloat16* __restrict__ y,
+                                 int y_ld, const __nv_bfloat16* __restrict__ x, int x_ld, __nv_bfloat16* __restrict__ dx,
+                                 int dx_ld, int64_t npix, int c, const float* __restrict__ gamma,
+                                 const float* __restrict__ mean, const float* __restrict__ invstd,
+                                 const float* __restrict__ tot, float slope, int training) {
+  const int oct = c >> 3;
+  int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= npix * oct) return;
+  const int ch = (int)(i % oct) * 8;
+  const int64_t m = i / oct;
+  float d[8], yy[8], xx[8];
+  unpack8b(__ldg(reinterpret_cast<const uint4*>(dy + m * dy_ld + ch)), d);
+  unpack8b(__ldg(reinterpret_cast<const uint4*>(y + m * y_ld + ch)), yy);
+  unpack8b(__ldg(reinterpret_cast<const uint4*>(x + m * x_ld + ch)), xx);
+  const float inv_n = 1.f / (float)npix;
+#pragma unroll
+  for (int k = 0; k < 8; ++k) {
+    float dz = yy[k] > 0.f ? d[k] : d[k] * slope;
+    const float is = invstd[ch + k], g = gamma[ch + k] * is;
+    if (training) {
+      const float xh = (xx[k] - mean[ch + k]) * is;
+      d[k] = g * (dz - tot[ch + k] * inv_n - xh * tot[c + ch + k] * inv_n);
+    } else {
+      d[k] = g * dz;
+    }
+  }
+  *reinterpret_cast<uint4*>(dx + m * dx_ld + ch) = pack8b(d);
+}
+
 // partial sums of dz and dz*xhat, dz = dy_post * lrelu'(y)
 template <typename T>
 __global__ void bn_bwd_partial(const T* __restrict__ dy, int dy_ld, const T* __restrict__ y, int y_ld,
@@ -168,8 +229,14 @@ static int bn_forward_t(const T* x, int x_ld, T* y, int y_ld, int64_t npix, int 
     bn_eval_stats<<<ceil_div(c, 128), 128, 0, st>>>(rm, rv, c, eps, save_mean, save_invstd);
     count_launch();
   }
-  bn_apply<T><<<ceil_div(npix * c, 256), 256, 0, st>>>(x, x_ld, y, y_ld, npix, c, gamma, beta, save_mean, save_invstd,
-                                                       slope);
+  if (sizeof(T) == 2 && c % 8 == 0 && x_ld % 8 == 0 && y_ld % 8 == 0 && ((uintptr_t)x) % 16 == 0 &&
+      ((uintptr_t)y) % 16 == 0)
+    bn_apply_vec<<<ceil_div(npix * (c / 8), 256), 256, 0, st>>>(
+        reinterpret_cast<const __nv_bfloat16*>(x), x_ld, reinterpret_cast<__nv_bfloat16*>(y), y_ld, npix, c, gamma,
+        beta, save_mean, save_invstd, slope);
+  else
+    bn_apply<T><<<ceil_div(npix * c, 256), 256, 0, st>>>(x, x_ld, y, y_ld, npix, c, gamma, beta, save_mean,
+                                                         save_invstd, slope);
   count_launch();
   return check_launch("bn_forward");
 }
@@ -198,8 +265,15 @@ static int bn_backward_t(const T* dy, int dy_ld, const T* y, int y_ld, const T* 
   dim3 grid(ceil_div(c, 32), parts), blk(32, 8);
   bn_bwd_partial<T><<<grid, blk, 0, st>>>(dy, dy_ld, y, y_ld, x, x_ld, npix, c, mean, invstd, slope, p0, p1);
   bn_bwd_finalize<<<ceil_div(c, 128), 128, 0, st>>>(p0, p1, parts, c, tot, dgamma, dbeta, accumulate);
-  bn_bwd_apply<T><<<ceil_div(npix * c, 256), 256, 0, st>>>(dy, dy_ld, y, y_ld, x, x_ld, dx, dx_ld, npix, c, gamma,
-                                                           mean, invstd, tot, slope, training);
+  if (sizeof(T) == 2 && c % 8 == 0 && dy_ld % 8 == 0 && y_ld % 8 == 0 && x_ld % 8 == 0 && dx_ld % 8 == 0 &&
+      ((uintptr_t)dy) % 16 == 0 && ((uintptr_t)y) % 16 == 0 && ((uintptr_t)x) % 16 == 0 && ((uintptr_t)dx) % 16 == 0)
+    bn_bwd_apply_vec<<<ceil_div(npix * (c / 8), 256), 256, 0, st>>>(
+        reinterpret_cast<const __nv_bfloat16*>(dy), dy_ld, reinterpret_cast<const __nv_bfloat16*>(y), y_ld,
+        reinterpret_cast<const __nv_bfloat16*>(x), x_ld, reinterpret_cast<__nv_bfloat16*>(dx), dx_ld, npix, c, gamma,
+        mean, invstd, tot, slope, training);
+  else
+    bn_bwd_apply<T><<<ceil_div(npix * c, 256), 256, 0, st>>>(dy, dy_ld, y, y_ld, x, x_ld, dx, dx_ld, npix, c, gamma,
+                                                             mean, invstd, tot, slope, training);
   count_launch(3);
   return check_launch("bn_backward");
 }

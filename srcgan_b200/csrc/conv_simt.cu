@@ -310,6 +310,34 @@ __global__ void colsum_partial(const T* __restrict__ g, int ld, int64_t M, int c
     part[(int64_t)blockIdx.y * c + ch] = t;
   }
 }
+// bf16, 16-byte loads: thread = (row lane, channel octet); block-level tree reduce over the row lanes
+__global__ void __launch_bounds__(256)
+colsum_partial_vec(const __nv_bfloat16* __restrict__ g, int ld, int64_t M, int c, float* __restrict__ part) {
+  __shared__ float red[256][9];
+  const int octets = c >> 3;
+  const int rows_per_iter = 256 / octets;
+  const int oc = threadIdx.x % octets, rl = threadIdx.x / octets;
+  float acc[8] = {0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f};
+  if (rl < rows_per_iter) {
+    for (int64_t m = (int64_t)blockIdx.x * rows_per_iter + rl; m < M; m += (int64_t)gridDim.x * rows_per_iter) {
+      uint4 q = __ldg(reinterpret_cast<const uint4*>(g + m * ld + oc * 8));
+      const __nv_bfloat162* h = reinterpret_cast<const __nv_bfloat162*>(&q);
+#pragma unroll
+      for (int i = 0; i < 4; ++i) { acc[2 * i] += __low2float(h[i]); acc[2 * i + 1] += __high2float(h[i]); }
+    }
+  }
+#pragma unroll
+  for (int i = 0; i < 8; ++i) red[threadIdx.x][i] = acc[i];
+  __syncthreads();
+  // thread t < c sums channel t over the row lanes
+  if (threadIdx.x < c) {
+    const int o = threadIdx.x >> 3, i = threadIdx.x & 7;
+    float s = 0.f;
+    for (int r = 0; r < rows_per_iter; ++r) s += red[r * octets + o][i];
+    part[(int64_t)blockIdx.x * c + threadIdx.x] = s;
+  }
+}
+
 __global__ void colsum_final(const float* __restrict__ part, int nparts, int c, float* __restrict__ out,
                              int accumulate, float alpha) {
   int ch = blockIdx.x * blockDim.x + threadIdx.x;
@@ -318,6 +346,191 @@ __global__ void colsum_final(const float* __restrict__ part, int nparts, int c, 
   for (int k = 0; k < nparts; ++k) s += (double)part[(int64_t)k * c + ch];
   s *= (double)alpha;
   out[ch] = accumulate ? out[ch] + (float)s : (float)s;
+}
+
+// ---------------------------------------------------------------------------------------------
+// thin fprop / dgrad (bandwidth-bound): one side of the GEMM has <= 4 channels.
+//   thin_out_conv : <= 4 output channels (64->3 image conv, 256->1 patch logits, dgrad of 3->64):
+//                   one thread per output pixel, 4-wide vector loads of the wide source, weights
+//                   [K][4] in shared memory read as warp-uniform float4 broadcasts
+//   thin_in_conv  : <= 4 GEMM-K channels (3->64 image conv, dgrad of 64->3 / 256->1): one thread per
+//                   (output pixel, 8 output channels), weights [K][N] in shared memory, 16/32-byte stores
+// Pixel mapping (fprop vs gather-form dgrad, stride, upsample) is the same as in conv_igemm_simt.
+// ---------------------------------------------------------------------------------------------
+template <bool DGRAD>
+__device__ __forceinline__ int64_t thin_src_pixel(const ConvDev& a, int n, int oy, int ox, int fr, int fs, int SH,
+                                                  int SW, int HV, int WV) {
+  int sy, sx;
+  if (!DGRAD) {
+    int iy = oy * a.stride - a.pad + fr, ix = ox * a.stride - a.pad + fs;
+    if (iy < 0 || iy >= HV || ix < 0 || ix >= WV) return -1;
+    sy = a.up ? (iy >> 1) : iy; sx = a.up ? (ix >> 1) : ix;
+  } else {
+    int ty_ = oy + a.pad - fr, tx_ = ox + a.pad - fs;
+    if (ty_ < 0 || tx_ < 0) return -1;
+    if (a.stride > 1) {
+      if ((ty_ % a.stride) | (tx_ % a.stride)) return -1;
+      ty_ /= a.stride; tx_ /= a.stride;
+    }
+    if (ty_ >= SH || tx_ >= SW) return -1;
+    sy = ty_; sx = tx_;
+  }
+  return (((int64_t)n * SH + sy) * SW + sx) * a.x_ld;
+}
+
+template <typename T, bool DGRAD>
+__global__ void __launch_bounds__(256)
+thin_out_conv(const ConvDev a) {
+  extern __shared__ float4 wsm[];                 // [taps*kch] float4 (N padded to 4)
+  const int OH = DGRAD ? a.h : a.ho, OW = DGRAD ? a.w : a.wo;
+  const int64_t M = (int64_t)a.n * OH * OW;
+  const int kch = DGRAD ? a.cout : a.cin, nch = DGRAD ? a.cin : a.cout;
+  const int taps = a.kh * a.kw, K = taps * kch;
+  const T* __restrict__ Wt = reinterpret_cast<const T*>(a.wgt);
+  for (int k = threadIdx.x; k < K; k += 256) {
+    float4 v = make_float4(0.f, 0.f, 0.f, 0.f);
+    v.x = to_f32(Wt[(int64_t)k * nch]);
+    if (nch > 1) v.y = to_f32(Wt[(int64_t)k * nch + 1]);
+    if (nch > 2) v.z = to_f32(Wt[(int64_t)k * nch + 2]);
+    if (nch > 3) v.w = to_f32(Wt[(int64_t)k * nch + 3]);
+    wsm[k] = v;
+  }
+  __syncthreads();
+  const int64_t m = (int64_t)blockIdx.x * 256 + threadIdx.x;
+  if (m >= M) return;
+  const int ox = (int)(m % OW);
+  const int64_t t = m / OW;
+  const int oy = (int)(t % OH), n = (int)(t / OH);
+  const int SH = DGRAD ? a.ho : a.h, SW = DGRAD ? a.wo : a.w;
+  const int HV = a.up ? 2 * a.h : a.h, WV = a.up ? 2 * a.w : a.w;
+  const T* __restrict__ X = reinterpret_cast<const T*>(a.x);
+  float acc[4] = {0.f, 0.f, 0.f, 0.f};
+  for (int fr = 0; fr < a.kh; ++fr)
+    for (int fs = 0; fs < a.kw; ++fs) {
+      const int64_t off = thin_src_pixel<DGRAD>(a, n, oy, ox, fr, fs, SH, SW, HV, WV);
+      if (off < 0) continue;
+      const float4* wrow = wsm + (fr * a.kw + fs) * kch;
+      const T* src = X + off;
+#pragma unroll 4
+      for (int c = 0; c < kch; c += 4) {
+        float v[4];
+        load4<T>(src + c, v);
+#pragma unroll
+        for (int q = 0; q < 4; ++q) {
+          const float4 w4 = wrow[c + q];
+          acc[0] = fmaf(v[q], w4.x, acc[0]); acc[1] = fmaf(v[q], w4.y, acc[1]);
+          acc[2] = fmaf(v[q], w4.z, acc[2]); acc[3] = fmaf(v[q], w4.w, acc[3]);
+        }
+      }
+    }
+  T* __restrict__ Y = reinterpret_cast<T*>(a.y);
+  const T* R1 = reinterpret_cast<const T*>(a.r1);
+  const T* R2 = reinterpret_cast<const T*>(a.r2);
+  const T* MK = reinterpret_cast<const T*>(a.mask);
+  for (int c = 0; c < nch; ++c) {
+    float v = acc[c];
+    if (a.bias) v += a.bias[c];
+    if (a.act) v = v > 0.f ? v : v * a.act_slope;
+    v *= a.alpha;
+    if (R1) v = fmaf(a.beta1, to_f32(R1[m * a.r1_ld + c]), v);
+    if (R2) v = fmaf(a.beta2, to_f32(R2[m * a.r2_ld + c]), v);
+    if (MK) v *= (to_f32(MK[m * a.mask_ld + c]) > 0.f ? 1.f : a.mask_slope);
+    Y[m * a.y_ld + c] = from_f32<T>(v);
+  }
+}
+
+template <typename T>
+__device__ __forceinline__ void load8(const T* p, float (&v)[8]);
+template <>
+__device__ __forceinline__ void load8<float>(const float* p, float (&v)[8]) {
+  float4 a = __ldg(reinterpret_cast<const float4*>(p)), b = __ldg(reinterpret_cast<const float4*>(p) + 1);
+  v[0] = a.x; v[1] = a.y; v[2] = a.z; v[3] = a.w; v[4] = b.x; v[5] = b.y; v[6] = b.z; v[7] = b.w;
+}
+template <>
+__device__ __forceinline__ void load8<__nv_bfloat16>(const __nv_bfloat16* p, float (&v)[8]) {
+  uint4 q = __ldg(reinterpret_cast<const uint4*>(p));
+  const __nv_bfloat162* h = reinterpret_cast<const __nv_bfloat162*>(&q);
+#pragma unroll
+  for (int i = 0; i < 4; ++i) { v[2 * i] = __low2float(h[i]); v[2 * i + 1] = __high2float(h[i]); }
+}
+template <typename T>
+__device__ __forceinline__ void store8(T* p, const float (&v)[8]);
+template <>
+__device__ __forceinline__ void store8<float>(float* p, const float (&v)[8]) {
+  reinterpret_cast<float4*>(p)[0] = make_float4(v[0], v[1], v[2], v[3]);
+  reinterpret_cast<float4*>(p)[1] = make_float4(v[4], v[5], v[6], v[7]);
+}
+template <>
+__device__ __forceinline__ void store8<__nv_bfloat16>(__nv_bfloat16* p, const float (&v)[8]) {
+  uint4 o;
+  __nv_bfloat162* h = reinterpret_cast<__nv_bfloat162*>(&o);
+#pragma unroll
+  for (int i = 0; i < 4; ++i) h[i] = __floats2bfloat162_rn(v[2 * i], v[2 * i + 1]);
+  *reinterpret_cast<uint4*>(p) = o;
+}
+
+template <typename T, bool DGRAD>
+__global__ void __launch_bounds__(256)
+thin_in_conv(const ConvDev a) {
+  extern __shared__ float wsf[];                  // [taps*kch][nch] fp32
+  const int OH = DGRAD ? a.h : a.ho, OW = DGRAD ? a.w : a.wo;
+  const int64_t M = (int64_t)a.n * OH * OW;
+  const int kch = DGRAD ? a.cout : a.cin, nch = DGRAD ? a.cin : a.cout;
+  const int taps = a.kh * a.kw, K = taps * kch;
+  const T* __restrict__ Wt = reinterpret_cast<const T*>(a.wgt);
+  for (int i = threadIdx.x; i < K * nch; i += 256) wsf[i] = to_f32(Wt[i]);
+  __syncthreads();
+  const int octs = nch >> 3;
+  const int64_t gid = (int64_t)blockIdx.x * 256 + threadIdx.x;
+  if (gid >= M * octs) return;
+  const int c0 = (int)(gid % octs) * 8;
+  const int64_t m = gid / octs;
+  const int ox = (int)(m % OW);
+  const int64_t t = m / OW;
+  const int oy = (int)(t % OH), n = (int)(t / OH);
+  const int SH = DGRAD ? a.ho : a.h, SW = DGRAD ? a.wo : a.w;
+  const int HV = a.up ? 2 * a.h : a.h, WV = a.up ? 2 * a.w : a.w;
+  const T* __restrict__ X = reinterpret_cast<const T*>(a.x);
+  float acc[8] = {0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f};
+  for (int fr = 0; fr < a.kh; ++fr)
+    for (int fs = 0; fs < a.kw; ++fs) {
+      const int64_t off = thin_src_pixel<DGRAD>(a, n, oy, ox, fr, fs, SH, SW, HV, WV);
+      if (off < 0) continue;
+      for (int k = 0; k < kch; ++k) {
+        const float xv = to_f32(X[off + k]);
+        const float* wr = wsf + ((fr * a.kw + fs) * kch + k) * nch + c0;
+        const float4 w0 = *reinterpret_cast<const float4*>(wr), w1 = *reinterpret_cast<const float4*>(wr + 4);
+        acc[0] = fmaf(xv, w0.x, acc[0]); acc[1] = fmaf(xv, w0.y, acc[1]); acc[2] = fmaf(xv, w0.z, acc[2]);
+        acc[3] = fmaf(xv, w0.w, acc[3]); acc[4] = fmaf(xv, w1.x, acc[4]); acc[5] = fmaf(xv, w1.y, acc[5]);
+        acc[6] = fmaf(xv, w1.z, acc[6]); acc[7] = fmaf(xv, w1.w, acc[7]);
+      }
+    }
+#pragma unroll
+  for (int i = 0; i < 8; ++i) {
+    float v = acc[i];
+    if (a.bias) v += a.bias[c0 + i];
+    if (a.act) v = v > 0.f ? v : v * a.act_slope;
+    acc[i] = v * a.alpha;
+  }
+  if (a.r1) {
+    float r[8];
+    load8<T>(reinterpret_cast<const T*>(a.r1) + m * a.r1_ld + c0, r);
+#pragma unroll
+    for (int i = 0; i < 8; ++i) acc[i] = fmaf(a.beta1, r[i], acc[i]);
+  }
+  if (a.r2) {
+    float r[8];
+    load8<T>(reinterpret_cast<const T*>(a.r2) + m * a.r2_ld + c0, r);
+#pragma unroll
+    for (int i = 0; i < 8; ++i) acc[i] = fmaf(a.beta2, r[i], acc[i]);
+  }
+  if (a.mask) {
+    float r[8];
+    load8<T>(reinterpret_cast<const T*>(a.mask) + m * a.mask_ld + c0, r);
+#pragma unroll
+    for (int i = 0; i < 8; ++i) acc[i] *= (r[i] > 0.f ? 1.f : a.mask_slope);
+  }
+  store8<T>(reinterpret_cast<T*>(a.y) + m * a.y_ld + c0, acc);
 }
 
 // ---------------------------------------------------------------------------------------------
@@ -401,10 +614,26 @@ thin_wgrad_kernel(const ThinArgs a, float* __restrict__ part) {
       }
     }
   }
-  // partial [(block*4+g)][tap][cw][4]
-  float4* out = reinterpret_cast<float4*>(part) + ((long long)(blockIdx.x * 4 + g) * TAPS) * a.cw + c0 + c;
+  // reduce the four row-pair subgroups through shared memory (reusing the thin tile), then one partial per block:
+  // part[block][tap][cw][4]
+  __syncthreads();
+  float4* red = &st[0][0];                       // TTH*TTW float4 >= 3*64 entries
+  float4* out = reinterpret_cast<float4*>(part) + ((long long)blockIdx.x * TAPS) * a.cw + c0 + c;
 #pragma unroll
-  for (int i = 0; i < TAPS; ++i) out[(long long)i * a.cw] = make_float4(acc[i][0], acc[i][1], acc[i][2], acc[i][3]);
+  for (int i = 0; i < TAPS; ++i) {
+    if (g > 0) red[(g - 1) * 64 + c] = make_float4(acc[i][0], acc[i][1], acc[i][2], acc[i][3]);
+    __syncthreads();
+    if (g == 0) {
+      float4 s = make_float4(acc[i][0], acc[i][1], acc[i][2], acc[i][3]);
+#pragma unroll
+      for (int k = 0; k < 3; ++k) {
+        float4 v = red[k * 64 + c];
+        s.x += v.x; s.y += v.y; s.z += v.z; s.w += v.w;
+      }
+      out[(long long)i * a.cw] = s;
+    }
+    __syncthreads();
+  }
 }
 
 // dw (OIHW) (+)= alpha * sum_parts part[p][tap][c][k];  thin_is_out: k indexes cout (case A) else cin (case B)
@@ -477,7 +706,27 @@ static int launch_igemm(const srcgan_conv_params* p, cudaStream_t st) {
   ConvDev a = to_dev(p, DGRAD);
   const int64_t M = (int64_t)p->n * (DGRAD ? p->h * p->w : p->ho * p->wo);
   const int nch = DGRAD ? p->cin : p->cout;
-  if (nch <= 4) {
+  const int kch = DGRAD ? p->cout : p->cin;
+  const int es = (int)sizeof(T);
+  auto al = [&](const void* ptr, int ld) { return ptr == nullptr || (((uintptr_t)ptr) % (8 * es) == 0 && ld % 8 == 0); };
+  if (nch <= 4 && kch % 4 == 0 && a.vec_a && (size_t)p->kh * p->kw * kch * 16 <= 160 * 1024) {
+    const size_t smem = (size_t)p->kh * p->kw * kch * sizeof(float4);
+    static bool attr_done = false;
+    if (!attr_done) {
+      cudaFuncSetAttribute(thin_out_conv<T, DGRAD>, cudaFuncAttributeMaxDynamicSharedMemorySize, 160 * 1024);
+      attr_done = true;
+    }
+    thin_out_conv<T, DGRAD><<<ceil_div(M, 256), 256, smem, st>>>(a);
+  } else if (kch <= 4 && nch % 8 == 0 && al(p->y, p->y_ld) && al(p->r1, p->r1_ld) && al(p->r2, p->r2_ld) &&
+             al(p->mask, p->mask_ld) && (size_t)p->kh * p->kw * kch * nch * 4 <= 160 * 1024) {
+    const size_t smem = (size_t)p->kh * p->kw * kch * nch * sizeof(float);
+    static bool attr_done2 = false;
+    if (!attr_done2) {
+      cudaFuncSetAttribute(thin_in_conv<T, DGRAD>, cudaFuncAttributeMaxDynamicSharedMemorySize, 160 * 1024);
+      attr_done2 = true;
+    }
+    thin_in_conv<T, DGRAD><<<ceil_div(M * (nch / 8), 256), 256, smem, st>>>(a);
+  } else if (nch <= 4) {
     dim3 grid(ceil_div(M, 256), 1);
     conv_igemm_simt<T, 256, 4, 1, 4, DGRAD><<<grid, 256, 0, st>>>(a);
   } else if (nch <= 32) {
@@ -568,7 +817,7 @@ static int launch_thin_wgrad(const srcgan_conv_params* p, float* dw, int accumul
   else thin_wgrad_kernel<T, 4, 4><<<g, 256, 0, st>>>(a, part);
   const int taps = p->kh * p->kw;
   long long total = (long long)taps * a.cw * a.kt;
-  thin_wgrad_reduce<<<ceil_div(total, 128), 128, 0, st>>>(part, grid * 4, taps, a.cw, a.kt, case_a ? 1 : 0, dw,
+  thin_wgrad_reduce<<<ceil_div(total, 128), 128, 0, st>>>(part, grid, taps, a.cw, a.kt, case_a ? 1 : 0, dw,
                                                           accumulate, p->alpha);
   count_launch(2);
   return check_launch("thin_wgrad");
@@ -612,14 +861,9 @@ static int launch_wgrad(const srcgan_conv_params* p, float* dw, float* db, int a
     count_launch();
   }
   if (db) {
-    float* bpart = reinterpret_cast<float*>(reinterpret_cast<char*>(ws) + ((wbytes + 255) / 256) * 256);
-    int ny = (int)((M + 2047) / 2048);
-    if (ny > 1024) ny = 1024;
-    if (ny < 1) ny = 1;
-    dim3 grid(ceil_div(p->cout, 32), ny), blk(32, 8);
-    colsum_partial<T><<<grid, blk, 0, st>>>(reinterpret_cast<const T*>(p->y), p->y_ld, M, p->cout, bpart);
-    colsum_final<<<ceil_div(p->cout, 128), 128, 0, st>>>(bpart, ny, p->cout, db, accumulate, p->alpha);
-    count_launch(2);
+    int rc = bias_grad_launch(p->y, p->y_ld, p->dtype, M, p->cout, db, accumulate, p->alpha,
+                              reinterpret_cast<char*>(ws) + ((wbytes + 255) / 256) * 256, st);
+    if (rc) return rc;
   }
   return check_launch("conv_wgrad_simt");
 }
@@ -641,6 +885,17 @@ int wgrad_reduce_launch(const float* part, int splits, int taps, int cin, int co
 int bias_grad_launch(const void* dy, int dy_ld, int dtype, long long M, int cout, float* db, int accumulate,
                      float alpha, void* ws, cudaStream_t st) {
   float* bpart = reinterpret_cast<float*>(ws);
+  if (dtype == SRCGAN_DT_BF16 && cout % 8 == 0 && cout <= 256 && 256 % (cout / 8) == 0 && dy_ld % 8 == 0 &&
+      ((uintptr_t)dy) % 16 == 0) {
+    const int rows_per_iter = 256 / (cout / 8);
+    long long nb = (M + (long long)rows_per_iter * 8 - 1) / ((long long)rows_per_iter * 8);
+    if (nb > 2 * kNumSMs) nb = 2 * kNumSMs;
+    if (nb < 1) nb = 1;
+    colsum_partial_vec<<<(unsigned)nb, 256, 0, st>>>(reinterpret_cast<const __nv_bfloat16*>(dy), dy_ld, M, cout, bpart);
+    colsum_final<<<ceil_div(cout, 128), 128, 0, st>>>(bpart, (int)nb, cout, db, accumulate, alpha);
+    count_launch(2);
+    return check_launch("bias_grad");
+  }
   int ny = (int)((M + 2047) / 2048);
   if (ny > 1024) ny = 1024;
   if (ny < 1) ny = 1;

@@ -1194,6 +1194,216 @@ static int launch(const CUtensorMap& tx, const CUtensorMap& tg, const WgArgs& a,
 }
 }  // namespace tcw
 
+// ---------------------------------------------------------------------------------------------
+// 3x3 stride-1 wgrad over haloed slabs.  As in the fprop kernel, ONE haloed X slab [18][10][64] per
+// 64-channel chunk serves all nine taps (MN-major A descriptor: start = slab + (kh*10+kw)*128 B,
+// 8-pixel K groups SBO = 1280 B apart), so a CTA owns every tap its TMEM can hold:
+//   cout = 32      : N = 32 (first half of the 64-wide dY rows), 9 accumulators x 32 columns
+//   cout % 64 == 0 : N = 64, taps split into two groups (5 + 4 accumulators)
+//   cin <= 64      : "tap pairing" - the M = 128 rows of one MMA are two taps x 64 channels (the second
+//                    swizzle atom is simply another tap of the same slab: LBO = tap offset difference),
+//                    so no half-empty M blocks: 5 accumulators, one group
+// CTA = (tap group, 128-channel ci block, 64-channel co block, pixel split); fp32 partials
+// [split][tap][ci][co] are summed in fixed order by wgrad_reduce.
+// ---------------------------------------------------------------------------------------------
+namespace tcw3 {
+using namespace tc;
+
+struct Wg3Args {
+  int n, ho, wo, cin, cout, pad;
+  int cblocks, nblocks, splits, ngroups, slots, slots_per_group, pair;
+  int tiles_x, tiles_y;
+  long long num_tiles, tiles_per_split;
+  float* part;
+};
+
+template <int BN>
+struct W3Cfg {
+  static constexpr int X_BOX = HALO_H * HALO_W * 128;                 // 23040
+  static constexpr int X_SLAB = (X_BOX + 1023) / 1024 * 1024;         // 23552
+  static constexpr int G_BYTES = TILE_M * 128;                         // 128 px x 64 ch
+  static constexpr int STAGE_BYTES = 2 * X_SLAB + G_BYTES;
+  static constexpr int STAGES = (SMEM_BUDGET - SMEM_AUX - 1024) / STAGE_BYTES;
+  static constexpr int SMEM_BYTES = STAGES * STAGE_BYTES + SMEM_AUX + 1024;
+  static constexpr int MAX_SLOTS = 512 / BN;
+  static_assert(STAGES >= 2, "not enough shared memory for a pipeline");
+};
+
+template <int BN>
+__global__ void __launch_bounds__(NUM_THREADS, 1)
+conv3x3_wgrad_halo_tc(const __grid_constant__ CUtensorMap tmap_x, const __grid_constant__ CUtensorMap tmap_g,
+                      const Wg3Args a) {
+  using C = W3Cfg<BN>;
+  extern __shared__ uint8_t smem_raw[];
+  uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~(uintptr_t)1023);
+  uint8_t* aux = smem + C::STAGES * C::STAGE_BYTES;
+  uint64_t* full_bar = reinterpret_cast<uint64_t*>(aux);
+  uint64_t* empty_bar = full_bar + C::STAGES;
+  uint64_t* done_bar = empty_bar + C::STAGES;
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(done_bar + 1);
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+
+  if (threadIdx.x == 0) {
+    for (int s = 0; s < C::STAGES; ++s) { mbar_init(&full_bar[s], 1); mbar_init(&empty_bar[s], 1); }
+    mbar_init(done_bar, 1);
+    asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+  }
+  if (warp == 1) {
+    asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(tmem_slot)),
+                 "r"(512u)
+                 : "memory");
+    asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
+  }
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  const uint32_t tmem_base = *tmem_slot;
+
+  int b = blockIdx.x;
+  const int split = b % a.splits; b /= a.splits;
+  const int nb = b % a.nblocks; b /= a.nblocks;
+  const int cb = b % a.cblocks; b /= a.cblocks;
+  const int grp = b;
+  const int slot_beg = grp * a.slots_per_group;
+  const int slot_end = (slot_beg + a.slots_per_group) < a.slots ? (slot_beg + a.slots_per_group) : a.slots;
+  const long long t_beg = (long long)split * a.tiles_per_split;
+  long long t_end = t_beg + a.tiles_per_split;
+  if (t_end > a.num_tiles) t_end = a.num_tiles;
+  const uint32_t stage_tx = (uint32_t)((a.pair ? 1 : 2) * C::X_BOX + C::G_BYTES);
+
+  if (warp == 0) {
+    int stage = 0;
+    uint32_t phase = 0;
+    for (long long t = t_beg; t < t_end; ++t) {
+      long long r = t;
+      const int bx = (int)(r % a.tiles_x); r /= a.tiles_x;
+      const int by = (int)(r % a.tiles_y);
+      const int img = (int)(r / a.tiles_y);
+      const int x0 = bx * TILE_W, y0 = by * TILE_H;
+      mbar_wait(&empty_bar[stage], phase ^ 1);
+      uint8_t* sx = smem + stage * C::STAGE_BYTES;
+      if (elect_one()) {
+        mbar_expect_tx(&full_bar[stage], stage_tx);
+        tma_load_4d(&tmap_x, &full_bar[stage], sx, cb * 128, x0 - a.pad, y0 - a.pad, img);
+        if (!a.pair) tma_load_4d(&tmap_x, &full_bar[stage], sx + C::X_SLAB, cb * 128 + 64, x0 - a.pad, y0 - a.pad, img);
+        tma_load_4d(&tmap_g, &full_bar[stage], sx + 2 * C::X_SLAB, nb * 64, x0, y0, img);
+      }
+      __syncwarp();
+      if (++stage == C::STAGES) { stage = 0; phase ^= 1; }
+    }
+  } else if (warp == 1) {
+    constexpr uint32_t idesc = tcw::umma_idesc_mn(128, BN);
+    constexpr uint32_t a_hi = desc_hi(HALO_W * 128), g_hi = desc_hi(1024);
+    int stage = 0;
+    uint32_t phase = 0;
+    uint32_t accumulate = 0;
+    for (long long t = t_beg; t < t_end; ++t) {
+      mbar_wait(&full_bar[stage], phase);
+      tc_fence_after();
+      const uint32_t sx = smem_u32(smem + stage * C::STAGE_BYTES);
+      const uint32_t sg = sx + 2 * C::X_SLAB;
+      if (elect_one()) {
+        const uint32_t g_lo = desc_lo(sg, C::G_BYTES);
+        for (int slot = slot_beg; slot < slot_end; ++slot) {
+          uint32_t a_lo;
+          if (a.pair) {
+            const int t0 = 2 * slot, t1 = (2 * slot + 1) < 9 ? (2 * slot + 1) : t0;
+            const int o0 = (t0 / 3) * HALO_W + (t0 % 3), o1 = (t1 / 3) * HALO_W + (t1 % 3);
+            const uint32_t lbo = (uint32_t)(o1 > o0 ? (o1 - o0) * 128 : 128);
+            a_lo = desc_lo(sx + o0 * 128, lbo);
+          } else {
+            const int o0 = (slot / 3) * HALO_W + (slot % 3);
+            a_lo = desc_lo(sx + o0 * 128, C::X_SLAB);
+          }
+          const uint32_t tmem_d = tmem_base + (uint32_t)((slot - slot_beg) * BN);
+#pragma unroll
+          for (int ks = 0; ks < TILE_M / 16; ++ks)
+            umma_bf16_w(tmem_d, a_lo + (uint32_t)(ks * (2 * HALO_W * 8)), a_hi, g_lo + (uint32_t)(ks * 128), g_hi, idesc,
+                        accumulate | (uint32_t)(ks > 0));
+        }
+        umma_commit(&empty_bar[stage]);
+      }
+      __syncwarp();
+      accumulate = 1;
+      if (++stage == C::STAGES) { stage = 0; phase ^= 1; }
+    }
+    if (elect_one()) umma_commit(done_bar);
+    __syncwarp();
+  } else {
+    const int q = warp & 3;
+    const int row = q * 32 + lane;
+    mbar_wait(done_bar, 0);
+    tc_fence_after();
+    const bool has_work = t_end > t_beg;
+#pragma unroll 1
+    for (int slot = slot_beg; slot < slot_end; ++slot) {
+      int tap, ci;
+      if (a.pair) { tap = 2 * slot + (row >> 6); ci = row & 63; }
+      else { tap = slot; ci = cb * 128 + row; }
+      const bool row_ok = tap < 9 && ci < a.cin;
+      float* dst = a.part + (((long long)split * 9 + (tap < 9 ? tap : 0)) * a.cin + (row_ok ? ci : 0)) * a.cout;
+#pragma unroll 1
+      for (int cb32 = 0; cb32 < BN; cb32 += 32) {
+        uint32_t v[32];
+        tmem_ld32(tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)((slot - slot_beg) * BN + cb32), v);
+        const int co0 = nb * 64 + cb32;
+        if (row_ok && co0 < a.cout) {
+#pragma unroll
+          for (int g = 0; g < 8; ++g) {
+            float4 o;
+            o.x = has_work ? __uint_as_float(v[4 * g + 0]) : 0.f;
+            o.y = has_work ? __uint_as_float(v[4 * g + 1]) : 0.f;
+            o.z = has_work ? __uint_as_float(v[4 * g + 2]) : 0.f;
+            o.w = has_work ? __uint_as_float(v[4 * g + 3]) : 0.f;
+            if (co0 + 4 * g < a.cout) *reinterpret_cast<float4*>(dst + co0 + 4 * g) = o;
+          }
+        }
+      }
+    }
+  }
+  tc_fence_before();
+  __syncthreads();
+  if (warp == 1) {
+    asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "r"(512u) : "memory");
+  }
+}
+
+static void plan3(const srcgan_conv_params* p, Wg3Args& a) {
+  const int bn = p->cout % 64 == 0 ? 64 : 32;
+  a.pair = p->cin <= 64 ? 1 : 0;
+  a.cblocks = a.pair ? 1 : (p->cin + 127) / 128;
+  a.nblocks = (p->cout + 63) / 64;
+  a.slots = a.pair ? 5 : 9;
+  const int max_slots = 512 / bn;
+  a.ngroups = (a.slots + max_slots - 1) / max_slots;
+  a.slots_per_group = (a.slots + a.ngroups - 1) / a.ngroups;
+  a.tiles_x = (p->wo + TILE_W - 1) / TILE_W;
+  a.tiles_y = (p->ho + TILE_H - 1) / TILE_H;
+  a.num_tiles = (long long)a.tiles_x * a.tiles_y * p->n;
+  const int groups = a.ngroups * a.cblocks * a.nblocks;
+  long long s = (2 * kNumSMs + groups - 1) / groups;
+  if (s > a.num_tiles) s = a.num_tiles;
+  if (s < 1) s = 1;
+  a.tiles_per_split = (a.num_tiles + s - 1) / s;
+  a.splits = (int)((a.num_tiles + a.tiles_per_split - 1) / a.tiles_per_split);
+}
+
+template <int BN>
+static int launch3(const CUtensorMap& tx, const CUtensorMap& tg, const Wg3Args& a, cudaStream_t st) {
+  using C = W3Cfg<BN>;
+  static bool attr_set = false;
+  if (!attr_set) {
+    SRCGAN_CUDA(cudaFuncSetAttribute(conv3x3_wgrad_halo_tc<BN>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                     C::SMEM_BYTES));
+    attr_set = true;
+  }
+  const unsigned grid = (unsigned)(a.ngroups * a.cblocks * a.nblocks * a.splits);
+  conv3x3_wgrad_halo_tc<BN><<<grid, NUM_THREADS, C::SMEM_BYTES, st>>>(tx, tg, a);
+  count_launch();
+  return check_launch("conv3x3_wgrad_halo_tc");
+}
+}  // namespace tcw3
+
 // shared with the SIMT engine (conv_simt.cu)
 int wgrad_reduce_launch(const float* part, int splits, int taps, int cin, int cout, float* dw, int accumulate,
                         float alpha, cudaStream_t st);
@@ -1209,10 +1419,20 @@ bool conv_wgrad_tc_supported(const srcgan_conv_params* p) {
   return true;
 }
 
+static bool wgrad_halo_ok(const srcgan_conv_params* p) {
+  return p->kh == 3 && p->kw == 3 && p->stride == 1 && (p->cout == 32 || p->cout % 64 == 0) && p->cin % 16 == 0 &&
+         !getenv("SRCGAN_B200_NO_HALO");
+}
+
 size_t conv_wgrad_tc_workspace(const srcgan_conv_params* p) {
   int bn, cblocks, nblocks, splits;
   long long tiles, tps;
   tcw::plan(p, bn, cblocks, nblocks, splits, tiles, tps);
+  if (wgrad_halo_ok(p)) {
+    tcw3::Wg3Args a3;
+    tcw3::plan3(p, a3);
+    if (a3.splits > splits) splits = a3.splits;
+  }
   size_t wbytes = (size_t)splits * p->kh * p->kw * p->cin * p->cout * sizeof(float);
   return ((wbytes + 255) / 256) * 256 + (size_t)1024 * p->cout * sizeof(float) + 256;
 }
@@ -1223,8 +1443,24 @@ int conv_wgrad_tc(const srcgan_conv_params* p, float* dw, float* db, int accumul
   int bn, cblocks, nblocks, splits;
   long long tiles, tps;
   tcw::plan(p, bn, cblocks, nblocks, splits, tiles, tps);
-  const size_t wbytes = (size_t)splits * p->kh * p->kw * p->cin * p->cout * sizeof(float);
-  if (dw) {
+  size_t wbytes = (size_t)splits * p->kh * p->kw * p->cin * p->cout * sizeof(float);
+  if (dw && wgrad_halo_ok(p)) {
+    tcw3::Wg3Args a3;
+    tcw3::plan3(p, a3);
+    a3.n = p->n; a3.ho = p->ho; a3.wo = p->wo; a3.cin = p->cin; a3.cout = p->cout; a3.pad = p->pad;
+    a3.part = reinterpret_cast<float*>(ws);
+    wbytes = (size_t)a3.splits * 9 * p->cin * p->cout * sizeof(float);
+    CUtensorMap tx, tg;
+    int rc = tc::make_tmap(&tx, p->x, p->cin, p->w, p->h, p->n, p->x_ld, tc::HALO_H, 1, "conv_wgrad_tc(x)", tc::HALO_W);
+    if (rc) return rc;
+    rc = tc::make_tmap(&tg, p->y, p->cout, p->wo, p->ho, p->n, p->y_ld, tc::TILE_H, 1, "conv_wgrad_tc(dy)");
+    if (rc) return rc;
+    rc = p->cout % 64 == 0 ? tcw3::launch3<64>(tx, tg, a3, st) : tcw3::launch3<32>(tx, tg, a3, st);
+    if (rc) return rc;
+    rc = wgrad_reduce_launch(reinterpret_cast<const float*>(ws), a3.splits, 9, p->cin, p->cout, dw, accumulate,
+                             p->alpha, st);
+    if (rc) return rc;
+  } else if (dw) {
     tc::HostPlan hp = tc::fprop_plan(p->kh, p->stride, p->pad);
     CUtensorMap tx, tg;
     int rc = tc::make_tmap(&tx, p->x, p->cin, p->w, p->h, p->n, p->x_ld, tc::TILE_H + hp.maxt - 1, p->stride,
