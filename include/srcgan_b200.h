@@ -121,6 +121,12 @@ int srcgan_nhwc_to_nchw(const void* src, int src_ld, int dtype, float* dst, int 
 int srcgan_add(const void* a, int a_ld, const void* b, int b_ld, void* dst, int dst_ld, int64_t npix, int c, int dtype,
                void* stream);
 
+/* out[ch] (+)= alpha * sum over the npix rows of x[row, ch]  (bias gradients of a whole dense block in one pass:
+ * the gradient concat buffer [dOut | dZ4 | dZ3 | dZ2 | dZ1] holds the output gradients of all five convs) */
+size_t srcgan_colsum_workspace_bytes(int64_t npix, int c);
+int srcgan_colsum(const void* x, int x_ld, int dtype, int64_t npix, int c, float* out, float alpha, int accumulate,
+                  void* workspace, size_t workspace_bytes, void* stream);
+
 /* dst[n,2h,2w,c] = nearest x2 of src[n,h,w,c]  (F.interpolate(scale_factor=2, 'nearest'), model.py:426-427) */
 int srcgan_upsample2x(const void* src, int src_ld, void* dst, int dst_ld, int n, int h, int w, int c, int dtype,
                       void* stream);

@@ -55,6 +55,8 @@ int upsample2x_adjoint(const void* src, int src_ld, void* dst, int dst_ld, const
                        float mslope, int n, int h, int w, int c, int dtype, cudaStream_t st);
 int add_slices(const void* a, int a_ld, const void* b, int b_ld, void* d, int d_ld, int64_t npix, int c, int dtype,
                cudaStream_t st);
+int bias_grad_launch(const void* dy, int dy_ld, int dtype, long long M, int cout, float* db, int accumulate,
+                     float alpha, void* ws, cudaStream_t st);
 size_t bn_workspace_bytes(int64_t npix, int c);
 int bn_forward(const void* x, int x_ld, void* y, int y_ld, int64_t npix, int c, int dtype, const float* gamma,
                const float* beta, float* rm, float* rv, float* save_mean, float* save_invstd, int training,
@@ -168,6 +170,14 @@ int srcgan_add(const void* a, int a_ld, const void* b, int b_ld, void* dst, int 
                void* stream) {
   SRCGAN_REQUIRE(a && b && dst && npix > 0 && c > 0, "add: bad arguments");
   return add_slices(a, a_ld, b, b_ld, dst, dst_ld, npix, c, dtype, (cudaStream_t)stream);
+}
+
+size_t srcgan_colsum_workspace_bytes(int64_t, int c) { return (size_t)1024 * c * sizeof(float) + 256; }
+int srcgan_colsum(const void* x, int x_ld, int dtype, int64_t npix, int c, float* out, float alpha, int accumulate,
+                  void* workspace, size_t workspace_bytes, void* stream) {
+  SRCGAN_REQUIRE(x && out && npix > 0 && c > 0, "colsum: bad arguments");
+  SRCGAN_REQUIRE(workspace && workspace_bytes >= srcgan_colsum_workspace_bytes(npix, c), "colsum: workspace too small");
+  return bias_grad_launch(x, x_ld, dtype, npix, c, out, accumulate, alpha, workspace, (cudaStream_t)stream);
 }
 
 size_t srcgan_bn_workspace_bytes(int64_t npix, int c) { return bn_workspace_bytes(npix, c); }

@@ -7,7 +7,7 @@
 
 namespace srcgan {
 
-constexpr int kBnMaxParts = 1024;
+constexpr int kBnMaxParts = 256;
 
 static int bn_parts(int64_t npix) {
   int64_t p = (npix + 511) / 512;

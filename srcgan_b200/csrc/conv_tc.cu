@@ -1381,7 +1381,7 @@ static void plan3(const srcgan_conv_params* p, Wg3Args& a) {
   a.tiles_y = (p->ho + TILE_H - 1) / TILE_H;
   a.num_tiles = (long long)a.tiles_x * a.tiles_y * p->n;
   const int groups = a.ngroups * a.cblocks * a.nblocks;
-  long long s = (2 * kNumSMs + groups - 1) / groups;
+  long long s = (kNumSMs + groups - 1) / groups;          // one wave of CTAs: fewer fp32 partials to reduce
   if (s > a.num_tiles) s = a.num_tiles;
   if (s < 1) s = 1;
   a.tiles_per_split = (a.num_tiles + s - 1) / s;

@@ -103,6 +103,11 @@ class _GradSink:
     def get(self, p):
         return self.g.get(id(p))
 
+    def put(self, p, t: torch.Tensor) -> None:
+        """Adopt an externally computed gradient (adds if the parameter already has one)."""
+        cur = self.g.get(id(p))
+        self.g[id(p)] = t if cur is None else cur.add_(t)
+
 
 class _NetBase(nn.Module):
     """Shared plumbing: packed weights, conv helpers."""
@@ -299,8 +304,17 @@ class _RRDBGenerator(_NetBase):
                            r2=(Slice(Dbuf[(j + 2) % 4], 0, nf) if is_rdb1 else None), beta2=1.0, engine=eng)
             for k in range(1, 5):
                 c = convs[k - 1]
-                self._wgrad(c, Slice(C, 0, nf + gc * (k - 1)), Slice(D, nf + gc * (4 - k), gc), sink, W(c.weight), W(c.bias))
-            self._wgrad(convs[4], Slice(C), Slice(D, 0, nf), sink, W(convs[4].weight), W(convs[4].bias), alpha=s5)
+                self._wgrad(c, Slice(C, 0, nf + gc * (k - 1)), Slice(D, nf + gc * (4 - k), gc), sink, W(c.weight), False)
+            self._wgrad(convs[4], Slice(C), Slice(D, 0, nf), sink, W(convs[4].weight), False, alpha=s5)
+            # all five bias gradients = column sums of the gradient concat buffer, one pass
+            if any(W(c.bias) for c in convs):
+                flat = torch.empty(ctot, dtype=torch.float32, device=dev)
+                ops.colsum(Slice(D), flat)
+                if W(convs[4].bias):
+                    sink.put(convs[4].bias, flat[0:nf].mul_(s5))
+                for k in range(1, 5):
+                    if W(convs[k - 1].bias):
+                        sink.put(convs[k - 1].bias, flat[nf + gc * (4 - k): nf + gc * (5 - k)])
         # fea feeds both the trunk and the skip (model.py:421)
         d_fea = ops.new_buf(n, h, w, nf, dt, dev)
         ops.add(Slice(dfea_trunk), g_fea2, Slice(d_fea))

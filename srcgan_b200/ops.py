@@ -264,6 +264,15 @@ def add(a: Slice, b: Slice, dst: Slice) -> None:
                                       _stream()), "add")
 
 
+def colsum(x: Slice, out: torch.Tensor, alpha: float = 1.0, accumulate: bool = False) -> None:
+    """out[c] (+)= alpha * sum over all pixels of x[..., c]   (fp32 out, one entry per channel of the slice)"""
+    assert out.dtype == torch.float32 and out.is_contiguous() and out.numel() == x.c
+    lib = _lib.load()
+    ws = workspace(lib.srcgan_colsum_workspace_bytes(x.npix, x.c), x.buf.device)
+    _lib.check(lib.srcgan_colsum(x.ptr, x.ld, dt_code(x.dtype), x.npix, x.c, out.data_ptr(), float(alpha),
+                                 int(accumulate), ws.data_ptr(), ws.numel(), _stream()), "colsum")
+
+
 def upsample2x(src: Slice, dst: Slice) -> None:
     assert dst.h == 2 * src.h and dst.w == 2 * src.w and src.c == dst.c
     _lib.check(_lib.load().srcgan_upsample2x(src.ptr, src.ld, dst.ptr, dst.ld, src.n, src.h, src.w, src.c,
