@@ -218,6 +218,8 @@ def run_ours(args):
     sampler.stop_flag = True
 
     if rank != 0:
+        if world > 1:
+            dist.barrier()
         return
     value = B * world * args.steps / (ms * 1e-3)
     # dominant kernel family by device time
@@ -251,6 +253,8 @@ def run_ours(args):
                                 "sample": "1 step at batch 1 of the same full-size step, fp32, oracle port of the "
                                           "reference (pure PyTorch) on the host cores, %.1f s" % dt}
     print(json.dumps(line), flush=True)
+    if world > 1:
+        dist.barrier()
 
 
 def main():
@@ -259,6 +263,12 @@ def main():
         run_reference(args)
     else:
         run_ours(args)
+        try:
+            import torch.distributed as dist
+            if dist.is_available() and dist.is_initialized():
+                dist.destroy_process_group()
+        except Exception:
+            pass
 
 
 if __name__ == "__main__":

@@ -457,6 +457,7 @@ struct HCfg {
   static constexpr int NA = NA_RAW > 8 ? 8 : NA_RAW;
   static constexpr int SMEM_BYTES = NA * A_STRIDE + NB * B_BYTES + SMEM_AUX + 1024;
   static constexpr int TMEM_COLS = 512;
+  static constexpr int ILV = NA >= 4 ? 2 : 1;      // pixel tiles whose MMA chains are interleaved
   static_assert(NA >= 3, "not enough shared memory for the activation ring");
 };
 
@@ -560,24 +561,37 @@ conv3x3_halo_tc(const __grid_constant__ CUtensorMap tmap_x, const TcArgs a) {
         const int ksteps = (rem >= KCH ? KCH : rem) >> 4;
         mbar_wait(&b_full[bs], bph);
         const uint32_t sb = smem_u32(smem_b + bs * C::B_BYTES);
-        for (int m = 0; m < mcount; ++m) {
+        // Consecutive MMAs into the SAME accumulator form a dependent chain that the tensor pipe does not
+        // overlap (short N=32/64 MMAs then pay the full issue-to-retire latency each).  Two pixel tiles are
+        // therefore processed together, their MMAs interleaved: two independent accumulation chains.
+        for (int m = 0; m < mcount; m += C::ILV) {
+          const int cnt = (mcount - m) < C::ILV ? (mcount - m) : C::ILV;
+          const int as0 = as;
           mbar_wait(&a_full[as], aph);
+          if (++as == C::NA) { as = 0; aph ^= 1; }
+          const int as1 = as;
+          if (cnt == 2) {
+            mbar_wait(&a_full[as], aph);
+            if (++as == C::NA) { as = 0; aph ^= 1; }
+          }
           tc_fence_after();
-          const uint32_t sa = smem_u32(smem_a + as * C::A_STRIDE);
-          const uint32_t tmem_d = tmem_base + (uint32_t)((set * MT + m) * BN);
+          const uint32_t sa0 = smem_u32(smem_a + as0 * C::A_STRIDE), sa1 = smem_u32(smem_a + as1 * C::A_STRIDE);
+          const uint32_t tmem_d0 = tmem_base + (uint32_t)((set * MT + m) * BN), tmem_d1 = tmem_d0 + BN;
           if (elect_one()) {
-            const uint32_t a_lo = desc_lo(sa), b_lo = desc_lo(sb);
+            const uint32_t a_lo0 = desc_lo(sa0), a_lo1 = desc_lo(sa1), b_lo = desc_lo(sb);
             constexpr uint32_t a_hi = desc_hi(HALO_W * 128), b_hi = desc_hi(1024);
             uint32_t accumulate = c > 0 ? 1u : 0u;
-            if (ksteps == 4) {
+            if (ksteps == 4 && cnt == 2) {
 #pragma unroll
               for (int fw = 0; fw < 3; ++fw)
 #pragma unroll
                 for (int fh = 0; fh < 3; ++fh)
 #pragma unroll
                   for (int ks = 0; ks < 4; ++ks) {
-                    umma_bf16_w(tmem_d, a_lo + (uint32_t)((fh * HALO_W + fw) * 8 + ks * 2), a_hi,
-                                b_lo + (uint32_t)(((fw * 3 + fh) * C::B_TAP_BYTES >> 4) + ks * 2), b_hi, idesc, accumulate);
+                    const uint32_t ao = (uint32_t)((fh * HALO_W + fw) * 8 + ks * 2);
+                    const uint32_t bo = (uint32_t)(((fw * 3 + fh) * C::B_TAP_BYTES >> 4) + ks * 2);
+                    umma_bf16_w(tmem_d0, a_lo0 + ao, a_hi, b_lo + bo, b_hi, idesc, accumulate);
+                    umma_bf16_w(tmem_d1, a_lo1 + ao, a_hi, b_lo + bo, b_hi, idesc, accumulate);
                     accumulate = 1;
                   }
             } else {
@@ -585,16 +599,18 @@ conv3x3_halo_tc(const __grid_constant__ CUtensorMap tmap_x, const TcArgs a) {
               for (int tap = 0; tap < 9; ++tap) {
                 const int fw = tap / 3, fh = tap - fw * 3;
                 for (int ks = 0; ks < ksteps; ++ks) {
-                  umma_bf16_w(tmem_d, a_lo + (uint32_t)((fh * HALO_W + fw) * 8 + ks * 2), a_hi,
-                              b_lo + (uint32_t)((tap * C::B_TAP_BYTES >> 4) + ks * 2), b_hi, idesc, accumulate);
+                  const uint32_t ao = (uint32_t)((fh * HALO_W + fw) * 8 + ks * 2);
+                  const uint32_t bo = (uint32_t)((tap * C::B_TAP_BYTES >> 4) + ks * 2);
+                  umma_bf16_w(tmem_d0, a_lo0 + ao, a_hi, b_lo + bo, b_hi, idesc, accumulate);
+                  if (cnt == 2) umma_bf16_w(tmem_d1, a_lo1 + ao, a_hi, b_lo + bo, b_hi, idesc, accumulate);
                   accumulate = 1;
                 }
               }
             }
-            umma_commit(&a_empty[as]);
+            umma_commit(&a_empty[as0]);
+            if (cnt == 2) umma_commit(&a_empty[as1]);
           }
           __syncwarp();
-          if (++as == C::NA) { as = 0; aph ^= 1; }
         }
         if (elect_one()) umma_commit(&b_empty[bs]);
         __syncwarp();
