@@ -230,7 +230,11 @@ def run_ours(args):
         achieved = d["flops"] / (d["ms"] * 1e-3) / 1e12
         conv_ms = sum(v["ms"] for v in ksum.values())
         roof = {"bound": "tensor", "kernel": name, "achieved": achieved, "peak": peaks["tflops"], "unit": "TFLOP/s",
-                "frac": achieved / peaks["tflops"], "traffic": None, "peak_source": peaks["source"],
+                "frac": achieved / peaks["tflops"], "traffic": None,
+                "traffic_note": "launches of this kernel span many layer shapes; per-shape DRAM bytes from ncu --set "
+                                "full are in profiles/r1_ncu_halo_kernels.txt (64->64 @16x256x256: 291 MB measured "
+                                "vs 268 MB algorithmic)",
+                "peak_source": peaks["source"],
                 "launches_per_step": d["launches"] / args.steps, "avg_launch_ms": d["ms"] / d["launches"],
                 "share_of_step": d["ms"] / ms, "conv_share_of_step": conv_ms / ms,
                 "families": {k: {"ms_per_step": v["ms"] / args.steps, "tflops": v["flops"] / (v["ms"] * 1e-3) / 1e12,

@@ -145,6 +145,11 @@ class _Timed:
         if self.on:
             eng = {ENGINE_SIMT: "simt", ENGINE_TC: "tc", ENGINE_AUTO: "auto"}[p.engine]
             self.key = "conv_%s_%s" % (kind, eng)
+            if p.engine == ENGINE_TC and p.kh == 3 and p.stride == 1:      # name the kernel that actually runs
+                if kind == "fprop" and p.cout in (32, 64):
+                    self.key = "conv3x3_halo_tc<%d>" % p.cout
+                elif kind == "wgrad" and (p.cout == 32 or p.cout % 64 == 0):
+                    self.key = "conv3x3_wgrad_halo_tc<%d>" % (64 if p.cout % 64 == 0 else 32)
             self.flops = 2.0 * p.n * p.ho * p.wo * p.cin * p.cout * p.kh * p.kw
 
     def __enter__(self):
