@@ -127,6 +127,14 @@ size_t srcgan_colsum_workspace_bytes(int64_t npix, int c);
 int srcgan_colsum(const void* x, int x_ld, int dtype, int64_t npix, int c, float* out, float alpha, int accumulate,
                   void* workspace, size_t workspace_bytes, void* stream);
 
+/* Non-overlapping transposed convolution (ConvTranspose2d k2 s2, src/model/rddb.py:28-38,94-97) = 1x1 conv to
+ * 4*c channels ordered (a,b,co) + this permutation: dst[n,2y+a,2x+b,co] = src[n,y,x,(a*2+b)*c+co].
+ * space_to_depth is its adjoint with an optional LeakyReLU mask (mask indexed like dst). */
+int srcgan_depth_to_space(const void* src, int src_ld, void* dst, int dst_ld, int n, int h, int w, int c, int dtype,
+                          void* stream);
+int srcgan_space_to_depth(const void* src, int src_ld, void* dst, int dst_ld, const void* mask, int mask_ld,
+                          float mask_slope, int n, int h, int w, int c, int dtype, void* stream);
+
 /* dst[n,2h,2w,c] = nearest x2 of src[n,h,w,c]  (F.interpolate(scale_factor=2, 'nearest'), model.py:426-427) */
 int srcgan_upsample2x(const void* src, int src_ld, void* dst, int dst_ld, int n, int h, int w, int c, int dtype,
                       void* stream);

@@ -101,6 +101,27 @@ def modules_fixture() -> dict:
     return fx
 
 
+def cascade_fixture() -> dict:
+    """Generators of the cascaded trainers that share the dense-block kernels: package RDDBNet
+    (src/model/rddb.py) for up = 2, 4 and SRDN (src/model/srdn.py), as built by trainCas.py:30."""
+    pkg, _M, _losses, _metrics = ref_harness.import_reference()
+    fx = {}
+    for up in (2, 4):
+        net = pkg.RDDBNet(1, 1, up)
+        net.load_state_dict(O.init_rddbnet_pkg(31, 1, 1, up), strict=True)
+        x = rand((2, 1, 16, 12), 301).requires_grad_(True)
+        y = net(x)
+        (y * probe_like(y, 17)).sum().backward()
+        fx[f"RDDBNet_x{up}"] = {"out": y.detach().clone(), "grad_norms": grad_norms(net), "dx": x.grad.clone()}
+    net = pkg.SRDN(1, 1, 2)
+    net.load_state_dict(O.init_srdn(32), strict=True)
+    x = rand((2, 1, 16, 12), 302).requires_grad_(True)
+    y = net(x)
+    (y * probe_like(y, 18)).sum().backward()
+    fx["SRDN"] = {"out": y.detach().clone(), "grad_norms": grad_norms(net), "dx": x.grad.clone()}
+    return fx
+
+
 def step_fixture() -> dict:
     train = ref_harness.import_train()
     opt = train.params()
@@ -137,6 +158,7 @@ def main() -> None:
     torch.set_num_threads(os.cpu_count() or 1)
     torch.save(modules_fixture(), os.path.join(OUT, "modules_tiny.pt"))
     torch.save(step_fixture(), os.path.join(OUT, "step_tiny.pt"))
+    torch.save(cascade_fixture(), os.path.join(OUT, "cascade_tiny.pt"))
     for f in sorted(os.listdir(OUT)):
         print(f, os.path.getsize(os.path.join(OUT, f)))
 

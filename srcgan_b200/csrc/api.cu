@@ -49,6 +49,8 @@ int conv_wgrad_tc(const srcgan_conv_params* p, float* dw, float* db, int accumul
 // other kernels
 int nchw_to_nhwc(const float* src, int n, int c, int h, int w, void* dst, int ld, int dtype, cudaStream_t st);
 int nhwc_to_nchw(const void* src, int ld, int dtype, float* dst, int n, int c, int h, int w, cudaStream_t st);
+int depth_to_space(const void* src, int src_ld, void* dst, int dst_ld, const void* mask, int mask_ld, float mslope,
+                   int n, int h, int w, int c, int dtype, int adjoint, cudaStream_t st);
 int upsample2x(const void* src, int src_ld, void* dst, int dst_ld, int n, int h, int w, int c, int dtype,
                cudaStream_t st);
 int upsample2x_adjoint(const void* src, int src_ld, void* dst, int dst_ld, const void* mask, int mask_ld,
@@ -158,6 +160,16 @@ int srcgan_upsample2x(const void* src, int src_ld, void* dst, int dst_ld, int n,
                       void* stream) {
   SRCGAN_REQUIRE(src && dst && n > 0 && c > 0 && h > 0 && w > 0, "upsample2x: bad arguments");
   return upsample2x(src, src_ld, dst, dst_ld, n, h, w, c, dtype, (cudaStream_t)stream);
+}
+int srcgan_depth_to_space(const void* src, int src_ld, void* dst, int dst_ld, int n, int h, int w, int c, int dtype,
+                          void* stream) {
+  SRCGAN_REQUIRE(src && dst && n > 0 && c > 0 && h > 0 && w > 0, "depth_to_space: bad arguments");
+  return depth_to_space(src, src_ld, dst, dst_ld, nullptr, 0, 0.f, n, h, w, c, dtype, 0, (cudaStream_t)stream);
+}
+int srcgan_space_to_depth(const void* src, int src_ld, void* dst, int dst_ld, const void* mask, int mask_ld,
+                          float mask_slope, int n, int h, int w, int c, int dtype, void* stream) {
+  SRCGAN_REQUIRE(src && dst && n > 0 && c > 0 && h > 0 && w > 0, "space_to_depth: bad arguments");
+  return depth_to_space(src, src_ld, dst, dst_ld, mask, mask_ld, mask_slope, n, h, w, c, dtype, 1, (cudaStream_t)stream);
 }
 int srcgan_upsample2x_adjoint(const void* src, int src_ld, void* dst, int dst_ld, const void* mask, int mask_ld,
                               float mask_slope, int n, int h, int w, int c, int dtype, void* stream) {

@@ -117,6 +117,47 @@ int upsample2x(const void* src, int src_ld, void* dst, int dst_ld, int n, int h,
   return check_launch("upsample2x");
 }
 
+// depth-to-space for the k2 s2 transposed convolution (rddb.py:94-97) computed as a 1x1 conv to 4*c channels:
+//   forward : dst[n,2y+a,2x+b,co] = src[n,y,x,(a*2+b)*c+co]
+//   adjoint : dst[n,y,x,(a*2+b)*c+co] = src[n,2y+a,2x+b,co] * (mask[n,y,x,(a*2+b)*c+co] > 0 ? 1 : slope)
+template <typename T, bool ADJ>
+__global__ void d2s_k(const T* __restrict__ src, int src_ld, T* __restrict__ dst, int dst_ld, const T* __restrict__ mask,
+                      int mask_ld, float mslope, int n, int h, int w, int c) {
+  int64_t total = (int64_t)n * h * w * 4 * c;
+  int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= total) return;
+  int wc = (int)(i % (4 * c));
+  int64_t p = i / (4 * c);
+  int x = (int)(p % w);
+  int64_t t = p / w;
+  int y = (int)(t % h);
+  int64_t b = t / h;
+  int ab = wc / c, co = wc - ab * c;
+  int64_t big = ((b * 2 * h + 2 * y + (ab >> 1)) * (2 * w) + 2 * x + (ab & 1));
+  if (!ADJ) {
+    dst[big * dst_ld + co] = src[p * src_ld + wc];
+  } else {
+    float v = to_f32(src[big * src_ld + co]);
+    if (mask) v *= (to_f32(mask[p * mask_ld + wc]) > 0.f ? 1.f : mslope);
+    dst[p * dst_ld + wc] = from_f32<T>(v);
+  }
+}
+
+int depth_to_space(const void* src, int src_ld, void* dst, int dst_ld, const void* mask, int mask_ld, float mslope,
+                   int n, int h, int w, int c, int dtype, int adjoint, cudaStream_t st) {
+  int64_t total = (int64_t)n * h * w * 4 * c;
+  unsigned grid = (unsigned)ceil_div(total, 256);
+  if (dtype == SRCGAN_DT_F32) {
+    if (adjoint) d2s_k<float, true><<<grid, 256, 0, st>>>((const float*)src, src_ld, (float*)dst, dst_ld, (const float*)mask, mask_ld, mslope, n, h, w, c);
+    else d2s_k<float, false><<<grid, 256, 0, st>>>((const float*)src, src_ld, (float*)dst, dst_ld, nullptr, 0, 0.f, n, h, w, c);
+  } else {
+    if (adjoint) d2s_k<__nv_bfloat16, true><<<grid, 256, 0, st>>>((const __nv_bfloat16*)src, src_ld, (__nv_bfloat16*)dst, dst_ld, (const __nv_bfloat16*)mask, mask_ld, mslope, n, h, w, c);
+    else d2s_k<__nv_bfloat16, false><<<grid, 256, 0, st>>>((const __nv_bfloat16*)src, src_ld, (__nv_bfloat16*)dst, dst_ld, nullptr, 0, 0.f, n, h, w, c);
+  }
+  count_launch();
+  return check_launch("depth_to_space");
+}
+
 template <typename T>
 __global__ void add_k(const T* __restrict__ a, int a_ld, const T* __restrict__ b, int b_ld, T* __restrict__ d, int d_ld,
                       int64_t npix, int c) {

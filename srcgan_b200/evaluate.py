@@ -1,0 +1,44 @@
+"""Eval sweep on the device: generator inference + the four metrics of src/metrics.py with ONE
+device->host read per tile instead of four ``.item()`` syncs (reference loop: src/testCas.py:65-103,
+src/visCas.py:114-141; file I/O and the CSV are the caller's business).
+
+The reference builds an autograd graph for every eval forward (no ``torch.no_grad``); here
+inference runs under ``no_grad`` so no activation is retained."""
+from __future__ import annotations
+
+from typing import Callable, Dict, Iterable, List, Tuple
+
+import torch
+
+from . import metrics as M
+
+_EVALUATORS = (M.MSE(), M.PSNR(), M.AE(), M.SSIM())
+
+
+def metrics_on_device(pred: torch.Tensor, truth: torch.Tensor) -> torch.Tensor:
+    """(4,) fp32 device tensor [MSE, PSNR, AE (mean over the batch), SSIM] - no host sync except the
+    data-range probe SSIM needs (same heuristic as metrics.py:102-111)."""
+    vals = []
+    for ev in _EVALUATORS:
+        v = ev(pred, truth)
+        vals.append(v.mean() if v.dim() else v)
+    return torch.stack([v.float() for v in vals])
+
+
+@torch.no_grad()
+def evaluate(generator: Callable[[torch.Tensor], torch.Tensor],
+             pairs: Iterable[Tuple[torch.Tensor, torch.Tensor]]) -> Tuple[List[Dict[str, float]], Dict[str, float]]:
+    """``pairs`` yields (net_input, ground_truth) device tensors (NCHW fp32).  Returns the per-item metric
+    dicts and their mean, keyed by the evaluators' ``repr`` ("MSE", "PSNR", "AE", "SSIM") like the
+    reference's CSV columns (testCas.py:95)."""
+    names = [repr(e) for e in _EVALUATORS]
+    rows = []
+    for x, y in pairs:
+        out = generator(x)
+        rows.append(metrics_on_device(out, y))
+    if not rows:
+        return [], {n: float("nan") for n in names}
+    table = torch.stack(rows).cpu()                      # one D2H for the whole sweep
+    per_item = [dict(zip(names, map(float, r))) for r in table]
+    mean = dict(zip(names, map(float, table.mean(0))))
+    return per_item, mean

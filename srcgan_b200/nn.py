@@ -247,46 +247,29 @@ class _RRDBGenerator(_NetBase):
         params = tuple(c.weight for c in convs[k:])
         return self._pk().get(("dense", id(rdb), k, s5), params, build, layout, dtype)
 
-    def _trunk_forward(self, x_in: Slice, st: dict) -> Slice:
-        """conv_first -> nb x RRDB -> trunk_conv (+fea).  Returns fea2; saves buffers in ``st``."""
+    # ---- a chain of dense blocks (groups of three form an RRDB) over concat buffers --------------------
+    def _chain_forward(self, rdbs: List[ResidualDenseBlock_5], bufs: List[torch.Tensor], out: Slice) -> None:
+        """bufs[0][..., :nf] already holds the chain input; the chain output is written to ``out``."""
         nf, gc = self.nf, self.gc
-        ctot = nf + 4 * gc
-        n, h, w, dev, dt = x_in.n, x_in.h, x_in.w, x_in.buf.device, x_in.dtype
-        rdbs = self._rdbs()
-        bufs = [ops.new_buf(n, h, w, ctot, dt, dev) for _ in rdbs]
-        trunk_out = ops.new_buf(n, h, w, nf, dt, dev)
-        fea2 = ops.new_buf(n, h, w, nf, dt, dev)
-        self._fprop(self.conv_first, x_in, Slice(bufs[0], 0, nf))
         for j, rdb in enumerate(rdbs):
             C = bufs[j]
             convs = rdb.convs()
             for k in range(1, 5):
                 self._fprop(convs[k - 1], Slice(C, 0, nf + gc * (k - 1)), Slice(C, nf + gc * (k - 1), gc), act=LRELU)
-            dest = Slice(bufs[j + 1], 0, nf) if j + 1 < len(rdbs) else Slice(trunk_out)
+            dest = Slice(bufs[j + 1], 0, nf) if j + 1 < len(rdbs) else out
             if j % 3 != 2:      # x5*0.2 + x                                    (model.py:211)
                 self._fprop(convs[4], Slice(C), dest, alpha=0.2, r1=Slice(C, 0, nf), beta1=1.0)
             else:               # RDB3: (x5*0.2 + x)*0.2 + rrdb_in              (model.py:211,233)
                 self._fprop(convs[4], Slice(C), dest, alpha=0.04, r1=Slice(C, 0, nf), beta1=0.2,
                             r2=Slice(bufs[j - 2], 0, nf), beta2=1.0)
-        self._fprop(self.trunk_conv, Slice(trunk_out), Slice(fea2), r1=Slice(bufs[0], 0, nf), beta1=1.0)
-        st["x_in"], st["bufs"], st["trunk_out"], st["fea2"] = x_in, bufs, trunk_out, fea2
-        return Slice(fea2)
 
-    def _trunk_backward(self, st: dict, g_fea2: Slice, sink: _GradSink, want: dict, need_dx: bool) -> Optional[Slice]:
-        """Backward of _trunk_forward.  ``want[param_id]`` says which params need grads."""
+    def _chain_backward(self, rdbs, bufs, Dbuf: List[torch.Tensor], dest: Slice, sink: "_GradSink", W) -> None:
+        """Dbuf[(len-1) % 4][..., :nf] already holds the gradient w.r.t. the chain output; the gradient
+        w.r.t. the chain input (through the chain) is written to ``dest``.  Mirrored dense blocks."""
         nf, gc = self.nf, self.gc
         ctot = nf + 4 * gc
-        bufs, trunk_out, x_in = st["bufs"], st["trunk_out"], st["x_in"]
-        n, h, w, dev, dt = x_in.n, x_in.h, x_in.w, x_in.buf.device, x_in.dtype
-        rdbs = self._rdbs()
-        W = lambda p: p is not None and want.get(id(p), False)
-        Dbuf = [ops.new_buf(n, h, w, ctot, dt, dev) for _ in range(4)]
-        last = len(rdbs) - 1
-        # trunk_conv
-        self._wgrad(self.trunk_conv, Slice(trunk_out), g_fea2, sink, W(self.trunk_conv.weight), W(self.trunk_conv.bias))
-        self._dgrad(self.trunk_conv, g_fea2, Slice(Dbuf[last % 4], 0, nf))
-        dfea_trunk = ops.new_buf(n, h, w, nf, dt, dev)
-        for j in range(last, -1, -1):
+        h, w, dt, dev = bufs[0].shape[1], bufs[0].shape[2], bufs[0].dtype, bufs[0].device
+        for j in range(len(rdbs) - 1, -1, -1):
             rdb, C, D = rdbs[j], bufs[j], Dbuf[j % 4]
             convs = rdb.convs()
             is_rdb3, is_rdb1 = (j % 3 == 2), (j % 3 == 0)
@@ -297,9 +280,9 @@ class _RRDBGenerator(_NetBase):
                 ops.conv_fprop(Slice(D, 0, cin_v), self._dense_wT(rdb, k, s5, dt, layout), None,
                                Slice(D, nf + gc * (4 - k), gc), 3, 1, 1,
                                mask=Slice(C, nf + gc * (k - 1), gc), mask_slope=LRELU, engine=eng)
-            dest = Slice(Dbuf[(j - 1) % 4], 0, nf) if j > 0 else Slice(dfea_trunk)
+            dst = Slice(Dbuf[(j - 1) % 4], 0, nf) if j > 0 else dest
             eng, layout = select_engine(ctot, nf, 3, 1, False, dt, h, w)
-            ops.conv_fprop(Slice(D), self._dense_wT(rdb, 0, s5, dt, layout), None, dest, 3, 1, 1,
+            ops.conv_fprop(Slice(D), self._dense_wT(rdb, 0, s5, dt, layout), None, dst, 3, 1, 1,
                            r1=Slice(D, 0, nf), beta1=(0.2 if is_rdb3 else 1.0),
                            r2=(Slice(Dbuf[(j + 2) % 4], 0, nf) if is_rdb1 else None), beta2=1.0, engine=eng)
             for k in range(1, 5):
@@ -315,6 +298,36 @@ class _RRDBGenerator(_NetBase):
                 for k in range(1, 5):
                     if W(convs[k - 1].bias):
                         sink.put(convs[k - 1].bias, flat[nf + gc * (4 - k): nf + gc * (5 - k)])
+
+    def _trunk_forward(self, x_in: Slice, st: dict) -> Slice:
+        """conv_first -> nb x RRDB -> trunk_conv (+fea).  Returns fea2; saves buffers in ``st``."""
+        nf, gc = self.nf, self.gc
+        ctot = nf + 4 * gc
+        n, h, w, dev, dt = x_in.n, x_in.h, x_in.w, x_in.buf.device, x_in.dtype
+        rdbs = self._rdbs()
+        bufs = [ops.new_buf(n, h, w, ctot, dt, dev) for _ in rdbs]
+        trunk_out = ops.new_buf(n, h, w, nf, dt, dev)
+        fea2 = ops.new_buf(n, h, w, nf, dt, dev)
+        self._fprop(self.conv_first, x_in, Slice(bufs[0], 0, nf))
+        self._chain_forward(rdbs, bufs, Slice(trunk_out))
+        self._fprop(self.trunk_conv, Slice(trunk_out), Slice(fea2), r1=Slice(bufs[0], 0, nf), beta1=1.0)
+        st["x_in"], st["bufs"], st["trunk_out"], st["fea2"] = x_in, bufs, trunk_out, fea2
+        return Slice(fea2)
+
+    def _trunk_backward(self, st: dict, g_fea2: Slice, sink: _GradSink, want: dict, need_dx: bool) -> Optional[Slice]:
+        """Backward of _trunk_forward.  ``want[param_id]`` says which params need grads."""
+        nf, gc = self.nf, self.gc
+        ctot = nf + 4 * gc
+        bufs, trunk_out, x_in = st["bufs"], st["trunk_out"], st["x_in"]
+        n, h, w, dev, dt = x_in.n, x_in.h, x_in.w, x_in.buf.device, x_in.dtype
+        rdbs = self._rdbs()
+        W = lambda p: p is not None and want.get(id(p), False)
+        Dbuf = [ops.new_buf(n, h, w, ctot, dt, dev) for _ in range(4)]
+        last = len(rdbs) - 1
+        self._wgrad(self.trunk_conv, Slice(trunk_out), g_fea2, sink, W(self.trunk_conv.weight), W(self.trunk_conv.bias))
+        self._dgrad(self.trunk_conv, g_fea2, Slice(Dbuf[last % 4], 0, nf))
+        dfea_trunk = ops.new_buf(n, h, w, nf, dt, dev)
+        self._chain_backward(rdbs, bufs, Dbuf, Slice(dfea_trunk), sink, W)
         # fea feeds both the trunk and the skip (model.py:421)
         d_fea = ops.new_buf(n, h, w, nf, dt, dev)
         ops.add(Slice(dfea_trunk), g_fea2, Slice(d_fea))
@@ -526,6 +539,173 @@ class RDDBNetA(_RRDBGenerator):
             g = nxt
         dx = self._trunk_backward(st, g, sink, want, need_dx)
         return ops.nhwc_to_nchw(dx) if dx is not None else None
+
+
+# ------------------------------------------------------------------------------------------
+# Cascaded-trainer generators that reuse the dense-block kernels (reference src/model/rddb.py:85-114,
+# src/model/srdn.py:53-78); constructed by ``eval(opt.SRModel)(1, 1, opt.up)`` (src/trainCas.py:30)
+# ------------------------------------------------------------------------------------------
+
+class RDDBNet(_RRDBGenerator):
+    """pkg RDDBNet: conv_first -> nb RRDB -> trunk_conv (+fea) -> log2(up) x [ConvTranspose2d(k2,s2,no bias)
+    -> LeakyReLU(0.2)] -> conv_last (no bias).  The non-overlapping deconvolution is a 1x1 convolution to
+    4*nf channels (LeakyReLU fused) followed by a depth-to-space permutation."""
+
+    def __init__(self, in_ch, ou_ch, upscale_factor, nf=64, nb=3, gc=32):
+        super().__init__()
+        import math
+        self.nf, self.gc, self.nb, self.upscale_factor = nf, gc, nb, upscale_factor
+        self.conv_first = nn.Conv2d(in_ch, nf, 3, 1, 1, bias=True)
+        self.RRDB_trunk = nn.Sequential(*[RRDB(nf, gc) for _ in range(nb)])
+        self.trunk_conv = nn.Conv2d(nf, nf, 3, 1, 1, bias=True)
+        ups: List[nn.Module] = []
+        for _ in range(int(math.log2(upscale_factor))):
+            ups += [nn.ConvTranspose2d(nf, nf, kernel_size=2, stride=2, padding=0, bias=False, output_padding=0),
+                    nn.LeakyReLU(negative_slope=0.2, inplace=True)]
+        self.upscale_layers = nn.Sequential(*ups)
+        self.conv_last = nn.Conv2d(nf, ou_ch, 3, 1, 1, bias=False)
+        _kaiming_fanout_(self)                     # touches nn.Conv2d only, as in the reference (rddb.py:100-105)
+
+    def _deconvs(self) -> List[nn.ConvTranspose2d]:
+        return [m for m in self.upscale_layers if isinstance(m, nn.ConvTranspose2d)]
+
+    def _w_deconv(self, dc: nn.ConvTranspose2d, kind: str, dtype, layout):
+        """ConvTranspose2d weight (cin, cout, 2, 2) as the OIHW weight of a 1x1 conv to (a,b,cout) channels
+        ('f'), or of its transpose ('t': (a,b,cout) -> cin)."""
+        def build():
+            w = dc.weight.detach()                                      # [ci, co, a, b]
+            w1 = w.permute(2, 3, 1, 0).reshape(4 * w.shape[1], w.shape[0], 1, 1)   # [(a,b,co), ci, 1, 1]
+            return (w1 if kind == "f" else w1.transpose(0, 1)).contiguous()
+        return self._pk().get(("deconv", kind, id(dc)), (dc.weight,), build, layout, dtype)
+
+    def forward(self, x):
+        return _NetFn.apply(self, x, *_flat_params(self))
+
+    def _forward_impl(self, x, st):
+        dt, dev = act_dtype(), x.device
+        n, c, h, w = x.shape
+        x_in = Slice(ops.new_buf(n, h, w, c, dt, dev))
+        ops.nchw_to_nhwc(x, x_in)
+        cur = self._trunk_forward(x_in, st)
+        nf = self.nf
+        ups = []
+        for dc in self._deconvs():
+            wide = Slice(ops.new_buf(n, cur.h, cur.w, 4 * nf, dt, dev))
+            eng, layout = select_engine(nf, 4 * nf, 1, 1, False, dt, cur.h, cur.w)
+            ops.conv_fprop(cur, self._w_deconv(dc, "f", dt, layout), None, wide, 1, 1, 0, act=LRELU, engine=eng)
+            big = Slice(ops.new_buf(n, 2 * cur.h, 2 * cur.w, nf, dt, dev))
+            ops.depth_to_space(wide, big)
+            ups.append((cur, wide))
+            cur = big
+        out = Slice(ops.new_buf(n, cur.h, cur.w, self.conv_last.out_channels, dt, dev))
+        self._fprop(self.conv_last, cur, out)
+        st["ups"], st["last_in"] = ups, cur
+        return ops.nhwc_to_nchw(out)
+
+    def _backward_impl(self, st, grad_out, sink, want, need_dx):
+        dt, dev = act_dtype(), grad_out.device
+        W = lambda p: p is not None and want.get(id(p), False)
+        last = st["last_in"]
+        n, nf = last.n, self.nf
+        d_o = Slice(ops.new_buf(n, last.h, last.w, self.conv_last.out_channels, dt, dev))
+        ops.nchw_to_nhwc(grad_out, d_o)
+        self._wgrad(self.conv_last, last, d_o, sink, W(self.conv_last.weight), False)
+        g = Slice(ops.new_buf(n, last.h, last.w, nf, dt, dev))
+        self._dgrad(self.conv_last, d_o, g)
+        deconvs = self._deconvs()
+        for i in range(len(deconvs) - 1, -1, -1):
+            dc = deconvs[i]
+            src, wide = st["ups"][i]
+            gw = Slice(ops.new_buf(n, src.h, src.w, 4 * nf, dt, dev))
+            ops.space_to_depth(g, gw, mask=wide, mask_slope=LRELU)        # dZ of the 1x1 conv, LeakyReLU mask fused
+            if W(dc.weight):
+                dw1 = torch.empty((4 * nf, nf, 1, 1), dtype=torch.float32, device=dev)
+                eng = _engine_mod().select_wgrad(nf, 4 * nf, 1, 1, False, dt, src.h, src.w)
+                ops.conv_wgrad(src, gw, dw1, None, 1, 1, 0, engine=eng)
+                sink.put(dc.weight, dw1.reshape(2, 2, nf, nf).permute(3, 2, 0, 1).contiguous())
+            nxt = Slice(ops.new_buf(n, src.h, src.w, nf, dt, dev))
+            eng, layout = select_engine(4 * nf, nf, 1, 1, False, dt, src.h, src.w)
+            ops.conv_fprop(gw, self._w_deconv(dc, "t", dt, layout), None, nxt, 1, 1, 0, engine=eng)
+            g = nxt
+        dx = self._trunk_backward(st, g, sink, want, need_dx)
+        return ops.nhwc_to_nchw(dx) if dx is not None else None
+
+
+class SRDN(_RRDBGenerator):
+    """SRDN: conv_first -> encoder (nb RRDB) -> +fea -> decoder (nb RRDB) -> +fea -> conv_last (no bias).
+    No upsampling; ``trunk_conv`` exists (state_dict compatible) but is unused, as in srdn.py:60,69-76."""
+
+    def __init__(self, in_ch, ou_ch, upscale_factor, nf=64, nb=3, gc=32):
+        super().__init__()
+        self.nf, self.gc, self.nb, self.upscale_factor = nf, gc, nb, upscale_factor
+        self.conv_first = nn.Conv2d(in_ch, nf, 3, 1, 1, bias=True)
+        self.RRDB_encoder = nn.Sequential(*[RRDB(nf, gc) for _ in range(nb)])
+        self.trunk_conv = nn.Conv2d(nf, nf, 3, 1, 1, bias=True)
+        self.RRDB_decoder = nn.Sequential(*[RRDB(nf, gc) for _ in range(nb)])
+        self.conv_last = nn.Conv2d(nf, ou_ch, 3, 1, 1, bias=False)
+        _kaiming_fanout_(self)
+
+    @staticmethod
+    def _rdbs_of(seq) -> List[ResidualDenseBlock_5]:
+        out = []
+        for rr in seq:
+            out += [rr.RDB1, rr.RDB2, rr.RDB3]
+        return out
+
+    def forward(self, x):
+        used = [p for name, p in self.named_parameters() if not name.startswith("trunk_conv.")]
+        return _NetFn.apply(self, x, *used)
+
+    def _forward_impl(self, x, st):
+        dt, dev = act_dtype(), x.device
+        n, c, h, w = x.shape
+        nf, ctot = self.nf, self.nf + 4 * self.gc
+        x_in = Slice(ops.new_buf(n, h, w, c, dt, dev))
+        ops.nchw_to_nhwc(x, x_in)
+        enc, dec = self._rdbs_of(self.RRDB_encoder), self._rdbs_of(self.RRDB_decoder)
+        be = [ops.new_buf(n, h, w, ctot, dt, dev) for _ in enc]
+        bd = [ops.new_buf(n, h, w, ctot, dt, dev) for _ in dec]
+        tmp = Slice(ops.new_buf(n, h, w, nf, dt, dev))
+        fea2 = Slice(ops.new_buf(n, h, w, nf, dt, dev))
+        self._fprop(self.conv_first, x_in, Slice(be[0], 0, nf))
+        self._chain_forward(enc, be, tmp)
+        ops.add(Slice(be[0], 0, nf), tmp, Slice(bd[0], 0, nf))          # fea = fea + encoder(fea)
+        self._chain_forward(dec, bd, tmp)
+        ops.add(Slice(bd[0], 0, nf), tmp, fea2)                          # fea = fea + decoder(fea)
+        out = Slice(ops.new_buf(n, h, w, self.conv_last.out_channels, dt, dev))
+        self._fprop(self.conv_last, fea2, out)
+        st["x_in"], st["be"], st["bd"], st["fea2"] = x_in, be, bd, fea2
+        return ops.nhwc_to_nchw(out)
+
+    def _backward_impl(self, st, grad_out, sink, want, need_dx):
+        dt, dev = act_dtype(), grad_out.device
+        W = lambda p: p is not None and want.get(id(p), False)
+        x_in, be, bd, fea2 = st["x_in"], st["be"], st["bd"], st["fea2"]
+        n, h, w, nf, ctot = x_in.n, x_in.h, x_in.w, self.nf, self.nf + 4 * self.gc
+        enc, dec = self._rdbs_of(self.RRDB_encoder), self._rdbs_of(self.RRDB_decoder)
+        d_o = Slice(ops.new_buf(n, h, w, self.conv_last.out_channels, dt, dev))
+        ops.nchw_to_nhwc(grad_out, d_o)
+        self._wgrad(self.conv_last, fea2, d_o, sink, W(self.conv_last.weight), False)
+        Dbuf = [ops.new_buf(n, h, w, ctot, dt, dev) for _ in range(4)]
+        g2 = Slice(ops.new_buf(n, h, w, nf, dt, dev))                   # d fea2 (kept: the chain recycles its slots)
+        self._dgrad(self.conv_last, d_o, g2)
+        Slice(Dbuf[(len(dec) - 1) % 4], 0, nf).view().copy_(g2.view())   # = d decoder-out
+        through = Slice(ops.new_buf(n, h, w, nf, dt, dev))
+        g1 = Slice(ops.new_buf(n, h, w, nf, dt, dev))
+        self._chain_backward(dec, bd, Dbuf, through, sink, W)
+        ops.add(through, g2, g1)                                          # d fea1 = skip + through the decoder
+        Ebuf = [ops.new_buf(n, h, w, ctot, dt, dev) for _ in range(4)]
+        ge = Slice(Ebuf[(len(enc) - 1) % 4], 0, nf)
+        ge.view().copy_(g1.view())                                       # d encoder-out = d fea1
+        self._chain_backward(enc, be, Ebuf, through, sink, W)
+        d_fea = Slice(ops.new_buf(n, h, w, nf, dt, dev))
+        ops.add(through, g1, d_fea)
+        self._wgrad(self.conv_first, x_in, d_fea, sink, W(self.conv_first.weight), W(self.conv_first.bias))
+        if not need_dx:
+            return None
+        dx = Slice(ops.new_buf(n, h, w, x_in.c, dt, dev))
+        self._dgrad(self.conv_first, d_fea, dx)
+        return ops.nhwc_to_nchw(dx)
 
 
 # ------------------------------------------------------------------------------------------

@@ -278,6 +278,19 @@ def colsum(x: Slice, out: torch.Tensor, alpha: float = 1.0, accumulate: bool = F
                                  int(accumulate), ws.data_ptr(), ws.numel(), _stream()), "colsum")
 
 
+def depth_to_space(src: Slice, dst: Slice) -> None:
+    assert dst.h == 2 * src.h and dst.w == 2 * src.w and src.c == 4 * dst.c
+    _lib.check(_lib.load().srcgan_depth_to_space(src.ptr, src.ld, dst.ptr, dst.ld, src.n, src.h, src.w, dst.c,
+                                                 dt_code(dst.dtype), _stream()), "depth_to_space")
+
+
+def space_to_depth(src: Slice, dst: Slice, mask: Optional[Slice] = None, mask_slope: float = 0.0) -> None:
+    assert src.h == 2 * dst.h and src.w == 2 * dst.w and dst.c == 4 * src.c
+    _lib.check(_lib.load().srcgan_space_to_depth(
+        src.ptr, src.ld, dst.ptr, dst.ld, mask.ptr if mask is not None else None, mask.ld if mask is not None else 0,
+        float(mask_slope), dst.n, dst.h, dst.w, src.c, dt_code(dst.dtype), _stream()), "space_to_depth")
+
+
 def upsample2x(src: Slice, dst: Slice) -> None:
     assert dst.h == 2 * src.h and dst.w == 2 * src.w and src.c == dst.c
     _lib.check(_lib.load().srcgan_upsample2x(src.ptr, src.ld, dst.ptr, dst.ld, src.n, src.h, src.w, src.c,

@@ -38,3 +38,9 @@ def golden_modules():
 def golden_step():
     import torch
     return torch.load(os.path.join(GOLDEN, "step_tiny.pt"), weights_only=False)
+
+
+@pytest.fixture(scope="session")
+def golden_cascade():
+    import torch
+    return torch.load(os.path.join(GOLDEN, "cascade_tiny.pt"), weights_only=False)

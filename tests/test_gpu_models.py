@@ -77,11 +77,11 @@ def run_both(net, oracle_fn, sd, x, probe_seed):
             Ref(oracle_fn, sd, x, pr, torch.float32), Ref(oracle_fn, sd, x, pr, torch.float64))
 
 
-def grad_tol(cpu32, truth):
-    return min(GRAD_CAP, max(GRAD_FLOOR, 3 * l2err(cpu32, truth)))
+def grad_tol(cpu32, truth, floor=GRAD_FLOOR):
+    return min(GRAD_CAP, max(floor, 3 * l2err(cpu32, truth)))
 
 
-def check_grads(named, r32, r64, strict=False):
+def check_grads(named, r32, r64, strict=False, floor=GRAD_FLOOR):
     """every parameter gradient vs the fp64 oracle; ``strict``: plain 1e-3 (no kink allowance)"""
     from oracle import srcgan_oracle as O
     errs = []
@@ -93,7 +93,7 @@ def check_grads(named, r32, r64, strict=False):
             continue
         assert named[k].grad is not None, k
         e = l2err(named[k].grad, v.grad)
-        tol = TOL if strict else grad_tol(r32.sd[k].grad, v.grad)
+        tol = TOL if strict else grad_tol(r32.sd[k].grad, v.grad, floor)
         assert e < tol, (k, e, tol)
         errs.append(e)
     errs.sort()
@@ -250,3 +250,51 @@ def test_bf16_mode_psnr_matches_fp32():
     psnr = lambda a, b: float(10 * torch.log10(1.0 / ((a - b) ** 2).mean()))
     assert abs(psnr(y, target) - psnr(y_ref, target)) < 0.05
     assert relerr(y, y_ref) < 0.1
+
+
+def test_eval_sweep_512_tiles():
+    """BASELINE config 5 shape: 512x512 tiles through the generator + MSE/PSNR/AE/SSIM on the device,
+    against the CPU oracle on the same weights (bf16 inference: PSNR within 0.05 dB of fp32)."""
+    from oracle import srcgan_oracle as O
+    from srcgan_b200 import evaluate, nn as snn
+    sd = O.init_rddbnet_b(41)
+    net = snn.RDDBNetB(3, 3, 64, nb=3, mode="x4")
+    net.load_state_dict(sd)
+    net.to(DEV).eval()
+    hr = [rand((1, 3, 512, 512), 500 + i) for i in range(2)]
+    lr = [torch.nn.functional.interpolate(h, scale_factor=0.25, mode="nearest") for h in hr]
+    snn.set_precision("bf16")
+    rows, mean = evaluate.evaluate(net, [(l.to(DEV), h.to(DEV)) for l, h in zip(lr, hr)])
+    assert len(rows) == 2 and set(mean) == {"MSE", "PSNR", "AE", "SSIM"}
+    for l, h, row in zip(lr, hr, rows):
+        out = O.rddbnet_b(sd, l, "x4")
+        assert abs(row["PSNR"] - float(O.psnr(out, h))) < 0.05
+        assert math.isclose(row["MSE"], float(O.mse_loss(out, h)), rel_tol=2e-2)
+        assert math.isclose(row["SSIM"], float(O.ssim(out, h)), rel_tol=5e-2, abs_tol=5e-3)
+        assert math.isclose(row["AE"], float(O.angular_error(out, h).mean()), rel_tol=2e-2)
+
+
+@pytest.mark.parametrize("which", ["RDDBNet_x2", "RDDBNet_x4", "SRDN"])
+def test_cascade_generators_parity(golden_cascade, which):
+    """package RDDBNet (k2 s2 transposed-conv upsampling) and SRDN on the CUDA path, fp32 mode."""
+    from oracle import srcgan_oracle as O
+    from srcgan_b200 import nn as snn
+    fx = golden_cascade[which]
+    if which == "SRDN":
+        sd, net, fn, x, seed = O.init_srdn(32), snn.SRDN(1, 1, 2), (lambda s, t: O.srdn(s, t)), rand((2, 1, 16, 12), 302), 18
+    else:
+        up = int(which[-1])
+        sd, net, x, seed = O.init_rddbnet_pkg(31, 1, 1, up), snn.RDDBNet(1, 1, up), rand((2, 1, 16, 12), 301), 17
+        fn = lambda s, t: O.rddbnet_pkg(s, t, up)
+    y, named, dx, r32, r64 = run_both(net, fn, sd, x, seed)
+    assert relerr(y, r64.y) < 1e-4 and relerr(y, fx["out"]) < 1e-4
+    # SRDN stacks 18 dense blocks (72 LeakyReLU layers): one flipped kink in the last blocks measures
+    # 2e-3..7e-3 on the neighbouring layers (scripts/diag_srdn.py) -> judged at the cap
+    floor = GRAD_CAP if which == "SRDN" else GRAD_FLOOR
+    check_grads(named, r32, r64, floor=floor)
+    assert l2err(dx, r64.dx) < grad_tol(r32.dx, r64.dx, floor)
+    # bf16 mode runs and stays close
+    snn.set_precision("bf16")
+    with torch.no_grad():
+        yb = net(x.to(DEV))
+    assert relerr(yb, r64.y) < 0.1

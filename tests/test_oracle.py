@@ -168,3 +168,24 @@ def test_oracle_equals_live_reference():
     a, b = rand((1, 3, 30, 30), 204), rand((1, 3, 30, 30), 205)
     assert math.isclose(float(O.ssim(a, b)), float(metrics.SSIM()(a, b)), rel_tol=1e-5)
     assert math.isclose(float(O.l1_loss(a, b)), float(losses.L1Loss()(a, b)), rel_tol=1e-6)
+
+
+@pytest.mark.parametrize("which", ["RDDBNet_x2", "RDDBNet_x4", "SRDN"])
+def test_cascade_generators_golden(golden_cascade, which):
+    """package RDDBNet (rddb.py) / SRDN (srdn.py): oracle vs outputs of the real reference."""
+    fx = golden_cascade[which]
+    if which == "SRDN":
+        sd = O.as_leaf_params(O.init_srdn(32))
+        x = rand((2, 1, 16, 12), 302).requires_grad_(True)
+        y = O.srdn(sd, x)
+        seed = 18
+    else:
+        up = int(which[-1])
+        sd = O.as_leaf_params(O.init_rddbnet_pkg(31, 1, 1, up))
+        x = rand((2, 1, 16, 12), 301).requires_grad_(True)
+        y = O.rddbnet_pkg(sd, x, up)
+        seed = 17
+    assert y.shape == fx["out"].shape and relerr(y.detach(), fx["out"]) < TOL
+    (y * probe_like(y, seed)).sum().backward()
+    check_grad_norms(sd, fx["grad_norms"])
+    assert relerr(x.grad, fx["dx"]) < 1e-4
