@@ -239,7 +239,7 @@ conv_igemm_tc(const __grid_constant__ CUtensorMap tmap_x, const TcArgs a) {
     for (int s = 0; s < 2; ++s) { mbar_init(&tfull_bar[s], 1); mbar_init(&tempty_bar[s], 128); }
     asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
   }
-  for (int i = threadIdx.x; i < a.cout; i += NUM_THREADS) sbias[i] = a.bias ? a.bias[i] : 0.f;
+  for (int i = threadIdx.x; i < 256; i += NUM_THREADS) sbias[i] = (a.bias && i < a.cout) ? a.bias[i] : 0.f;
   if (warp == 1) {
     asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(tmem_slot)),
                  "r"((uint32_t)C::TMEM_COLS)
@@ -312,7 +312,7 @@ conv_igemm_tc(const __grid_constant__ CUtensorMap tmap_x, const TcArgs a) {
         uint32_t started = 0;                       // 0 while the first (chunk, load) initialises the accumulators
         for (int c = 0; c < a.nchunks; ++c) {
           const int rem = a.cin - c * KCH;
-          const int ksteps = (rem >= KCH ? KCH : rem) >> 4;
+          const int ksteps = ((rem >= KCH ? KCH : rem) + 15) >> 4;   // OOB channels are TMA zero-filled
           for (int l = 0; l < a.plan.nloads; ++l) {
             mbar_wait(&b_full[bs], bph);
             const uint32_t sb = smem_u32(smem_b + bs * C::B_BYTES);
@@ -447,7 +447,7 @@ conv_igemm_tc(const __grid_constant__ CUtensorMap tmap_x, const TcArgs a) {
 constexpr int HALO_W = TILE_W + 2, HALO_H = TILE_H + 2;
 template <int BN>
 struct HCfg {
-  static constexpr int MT = 256 / BN;
+  static constexpr int MT = 256 / BN > 8 ? 8 : 256 / BN;
   static constexpr int A_BOX_BYTES = HALO_H * HALO_W * 128;                  // 23040
   static constexpr int A_STRIDE = (A_BOX_BYTES + 1023) / 1024 * 1024;        // 23552
   static constexpr int B_TAP_BYTES = BN * 128;
@@ -497,7 +497,7 @@ conv3x3_halo_tc(const __grid_constant__ CUtensorMap tmap_x, const TcArgs a) {
     for (int s = 0; s < 2; ++s) { mbar_init(&tfull_bar[s], 1); mbar_init(&tempty_bar[s], 128); }
     asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
   }
-  for (int i = threadIdx.x; i < a.cout; i += NUM_THREADS) sbias[i] = a.bias ? a.bias[i] : 0.f;
+  for (int i = threadIdx.x; i < 256; i += NUM_THREADS) sbias[i] = (a.bias && i < a.cout) ? a.bias[i] : 0.f;
   if (warp == 1) {
     asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(tmem_slot)),
                  "r"((uint32_t)C::TMEM_COLS)
@@ -558,7 +558,7 @@ conv3x3_halo_tc(const __grid_constant__ CUtensorMap tmap_x, const TcArgs a) {
       tc_fence_after();
       for (int c = 0; c < a.nchunks; ++c) {
         const int rem = a.cin - c * KCH;
-        const int ksteps = (rem >= KCH ? KCH : rem) >> 4;
+        const int ksteps = ((rem >= KCH ? KCH : rem) + 15) >> 4;   // OOB channels are TMA zero-filled
         mbar_wait(&b_full[bs], bph);
         const uint32_t sb = smem_u32(smem_b + bs * C::B_BYTES);
         // Consecutive MMAs into the SAME accumulator form a dependent chain that the tensor pipe does not
@@ -637,6 +637,19 @@ conv3x3_halo_tc(const __grid_constant__ CUtensorMap tmap_x, const TcArgs a) {
         const bool valid = (y < a.gh) && (x < a.gw);
         const long long pix = ((long long)img * a.oh + y) * a.ow + x;
         const uint32_t taddr = tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)((set * MT + m) * BN);
+        if (BN == 16) {
+          // thin outputs (cout <= 16, e.g. the 3-channel image): scalar bf16 stores, bias / activation / alpha only
+          uint32_t v[32];
+          tmem_ld32(taddr, v);                     // 16 valid columns (+16 of the neighbouring accumulator, ignored)
+          if (valid) {
+            for (int c = 0; c < a.cout; ++c) {
+              float t0 = __uint_as_float(v[c]) + sbias[c];
+              if (a.act) t0 = t0 > 0.f ? t0 : t0 * a.act_slope;
+              a.y[pix * a.y_ld + c] = __float2bfloat16_rn(t0 * a.alpha);
+            }
+          }
+          continue;
+        }
 #pragma unroll 1
         for (int cb = 0; cb < BN; cb += 32) {
           uint32_t v[32];
@@ -703,7 +716,7 @@ struct PackArgs {
   int slot_off[MAX_SLOTS];               // kh*KW + kw of each slot
 };
 __global__ void pack_weights_tc(const float* __restrict__ w, const PackArgs a, __nv_bfloat16* __restrict__ out) {
-  const long long total = (long long)(a.n_total / a.bn) * a.nchunks * a.total_slots * a.bn * KCH;
+  const long long total = (long long)((a.n_total + a.bn - 1) / a.bn) * a.nchunks * a.total_slots * a.bn * KCH;
   long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
   if (i >= total) return;
   const int j = (int)(i % KCH);
@@ -714,7 +727,7 @@ __global__ void pack_weights_tc(const float* __restrict__ w, const PackArgs a, _
   const int nb = (int)(t / a.nchunks);
   const int nch = nb * a.bn + r, kch = c * KCH + j;
   float v = 0.f;
-  if (kch < a.k_total) v = w[nch * a.nstride + kch * a.kstride + a.slot_off[slot]];
+  if (kch < a.k_total && nch < a.n_total) v = w[nch * a.nstride + kch * a.kstride + a.slot_off[slot]];
   const long long tile = i - (long long)r * KCH - j;   // start of this [BN][64] tile
   const int chunk16 = (j >> 3) ^ (r & 7);
   out[tile + (long long)r * KCH + chunk16 * 8 + (j & 7)] = __float2bfloat16_rn(v);
@@ -757,8 +770,12 @@ static int make_tmap(CUtensorMap* tm, const void* ptr, int c, int w, int h, int 
   return SRCGAN_OK;
 }
 
-static int bn_for(int cout) { return cout >= 128 ? 128 : cout; }
-static long long supertiles(int tiles_x, int bn) { const int mt = 256 / bn; return (tiles_x + mt - 1) / mt; }
+static int bn_for(int cout) { return cout >= 128 ? 128 : (cout <= 16 ? 16 : cout); }   // thin outputs pad to N=16
+static long long supertiles(int tiles_x, int bn) {
+  int mt = 256 / bn;
+  if (mt > 8) mt = 8;
+  return (tiles_x + mt - 1) / mt;
+}
 
 struct HostPlan {
   Plan plan;
@@ -816,6 +833,7 @@ static HostPlan dgrad2_phase_plan(int K, int p, int a, int b) {
 }
 
 static size_t packed_elems(int n_total, int k_total, int slots) {
+  { const int bn = bn_for(n_total); n_total = (n_total + bn - 1) / bn * bn; }
   return (size_t)n_total * ((k_total + KCH - 1) / KCH) * KCH * slots;
 }
 
@@ -896,7 +914,10 @@ static bool tc_common_ok(const srcgan_conv_params* p) {
 static bool tc_nch_ok(int c) { return c == 32 || c == 64 || c == 128 || c == 256; }
 
 bool conv_tc_supported(const srcgan_conv_params* p) {
-  return tc_common_ok(p) && p->cin >= 64 && p->cin % 16 == 0 && tc_nch_ok(p->cout);
+  if (!tc_common_ok(p)) return false;
+  // thin outputs (<= 16 channels, e.g. the 64->3 image conv): 3x3 stride-1 halo kernel only, plain epilogue
+  if (p->cout <= 16) return p->kh == 3 && p->stride == 1 && !p->r1 && !p->r2 && !p->mask;
+  return tc_nch_ok(p->cout);      // any cin: channels beyond cin are zero-filled by TMA (K padded to 16)
 }
 // stride-2 dgrad on the tensor-core engine (stride-1 dgrad is an fprop over transposed weights)
 bool conv_dgrad_tc_supported(const srcgan_conv_params* p) {
@@ -913,7 +934,8 @@ int pack_weights_tc_host(const float* w, int cout, int cin, int kh, int kw, int 
   SRCGAN_REQUIRE(kh == kw, "pack_weights(tc): square filters only");
   const long long taps = (long long)kh * kw;
   if (layout == SRCGAN_WL_TC || layout == SRCGAN_WL_TC_S2) {
-    SRCGAN_REQUIRE(tc_nch_ok(cout), "pack_weights(tc): cout %d unsupported", cout);
+    SRCGAN_REQUIRE(tc_nch_ok(cout) || (cout <= 16 && layout == SRCGAN_WL_TC), "pack_weights(tc): cout %d unsupported",
+                   cout);
     tc::HostPlan hp = tc::fprop_plan(kh, layout == SRCGAN_WL_TC ? 1 : 2, 0);   // slot order does not depend on pad
     return tc::pack_launch(w, cout, cin, (long long)cin * taps, taps, kw, hp, (__nv_bfloat16*)out, st);
   }
@@ -934,7 +956,8 @@ int pack_weights_tc_host(const float* w, int cout, int cin, int kh, int kw, int 
 
 int conv_fprop_tc(const srcgan_conv_params* p, cudaStream_t st) {
   tc::HostPlan hp = tc::fprop_plan(p->kh, p->stride, p->pad);
-  const bool halo = p->kh == 3 && p->stride == 1 && (p->cout == 32 || p->cout == 64) && !getenv("SRCGAN_B200_NO_HALO");
+  const bool halo = p->kh == 3 && p->stride == 1 && (p->cout <= 16 || p->cout == 32 || p->cout == 64) &&
+                    !getenv("SRCGAN_B200_NO_HALO");
   CUtensorMap tmap;
   int rc = halo ? tc::make_tmap(&tmap, p->x, p->cin, p->w, p->h, p->n, p->x_ld, tc::HALO_H, 1, "conv_fprop_tc",
                                 tc::HALO_W)
@@ -947,12 +970,15 @@ int conv_fprop_tc(const srcgan_conv_params* p, cudaStream_t st) {
   a.plan = hp.plan;
   a.nchunks = (p->cin + tc::KCH - 1) / tc::KCH;
   const int bn = tc::bn_for(p->cout);
-  a.n_blocks = p->cout / bn;
+  a.n_blocks = (p->cout + bn - 1) / bn;
   a.tiles_x = (a.gw + tc::TILE_W - 1) / tc::TILE_W;
   a.tiles_y = (a.gh + tc::TILE_H - 1) / tc::TILE_H;
   a.num_tiles = tc::supertiles(a.tiles_x, bn) * a.tiles_y * p->n * a.n_blocks;
   tc::fill_epilogue(a, p);
-  if (halo) return bn == 32 ? tc::launch_halo<32>(tmap, a, st) : tc::launch_halo<64>(tmap, a, st);
+  if (halo) {
+    if (bn == 16) return tc::launch_halo<16>(tmap, a, st);
+    return bn == 32 ? tc::launch_halo<32>(tmap, a, st) : tc::launch_halo<64>(tmap, a, st);
+  }
   return tc::dispatch(bn, hp.maxt, tmap, a, st);
 }
 
@@ -1364,14 +1390,18 @@ conv3x3_wgrad_halo_tc(const __grid_constant__ CUtensorMap tmap_x, const __grid_c
         tmem_ld32(tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)((slot - slot_beg) * BN + cb32), v);
         const int co0 = nb * 64 + cb32;
         if (row_ok && co0 < a.cout) {
+          if (a.cout & 3) {                        // thin dY (e.g. 3 channels): scalar stores
+            for (int i = 0; i < 32 && co0 + i < a.cout; ++i) dst[co0 + i] = has_work ? __uint_as_float(v[i]) : 0.f;
+          } else {
 #pragma unroll
-          for (int g = 0; g < 8; ++g) {
-            float4 o;
-            o.x = has_work ? __uint_as_float(v[4 * g + 0]) : 0.f;
-            o.y = has_work ? __uint_as_float(v[4 * g + 1]) : 0.f;
-            o.z = has_work ? __uint_as_float(v[4 * g + 2]) : 0.f;
-            o.w = has_work ? __uint_as_float(v[4 * g + 3]) : 0.f;
-            if (co0 + 4 * g < a.cout) *reinterpret_cast<float4*>(dst + co0 + 4 * g) = o;
+            for (int g = 0; g < 8; ++g) {
+              float4 o;
+              o.x = has_work ? __uint_as_float(v[4 * g + 0]) : 0.f;
+              o.y = has_work ? __uint_as_float(v[4 * g + 1]) : 0.f;
+              o.z = has_work ? __uint_as_float(v[4 * g + 2]) : 0.f;
+              o.w = has_work ? __uint_as_float(v[4 * g + 3]) : 0.f;
+              if (co0 + 4 * g < a.cout) *reinterpret_cast<float4*>(dst + co0 + 4 * g) = o;
+            }
           }
         }
       }
@@ -1429,14 +1459,14 @@ int bias_grad_launch(const void* dy, int dy_ld, int dtype, long long M, int cout
 bool conv_wgrad_tc_supported(const srcgan_conv_params* p) {
   if (p->dtype != SRCGAN_DT_BF16 || (p->stride != 1 && p->stride != 2) || p->upsample) return false;
   if (p->kh != p->kw || (p->kh != 3 && p->kh != 4)) return false;
-  if (p->cin < 16 || p->cin % 8 || p->cout < 16 || p->cout % 8) return false;
+  if (!(p->kh == 3 && p->stride == 1) && (p->cin < 16 || p->cin % 8 || p->cout < 16 || p->cout % 8)) return false;
   if (p->x_ld % 8 || p->y_ld % 8) return false;
   if (((uintptr_t)p->x) % 16 || ((uintptr_t)p->y) % 16) return false;
   return true;
 }
 
 static bool wgrad_halo_ok(const srcgan_conv_params* p) {
-  return p->kh == 3 && p->kw == 3 && p->stride == 1 && (p->cout == 32 || p->cout % 64 == 0) && p->cin % 16 == 0 &&
+  return p->kh == 3 && p->kw == 3 && p->stride == 1 && (p->cout <= 32 || p->cout % 64 == 0) &&
          !getenv("SRCGAN_B200_NO_HALO");
 }
 

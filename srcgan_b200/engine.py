@@ -21,8 +21,11 @@ def force_simt(flag: bool) -> None:
 
 def tc_fprop_supported(cin: int, cout: int, k: int, stride: int, upsample: bool, dtype, h: int, w: int) -> bool:
     """Mirror of conv_tc_supported() in csrc/conv_tc.cu (the C side re-checks alignment and refuses loudly)."""
-    return (dtype == torch.bfloat16 and stride in (1, 2) and not upsample and k in (3, 4) and cin >= 64
-            and cin % 16 == 0 and cout in (32, 64, 128, 256))
+    if dtype != torch.bfloat16 or upsample or k not in (3, 4) or stride not in (1, 2):
+        return False
+    if cout <= 16:                     # thin outputs (64->3 image conv): 3x3 stride-1 halo kernel, plain epilogue
+        return k == 3 and stride == 1
+    return cout in (32, 64, 128, 256)  # any cin: TMA zero-fills the K padding (thin buffers have ld = 8)
 
 
 def tc_dgrad_s2_supported(cin: int, cout: int, k: int, stride: int, pad: int, dtype) -> bool:
@@ -33,8 +36,11 @@ def tc_dgrad_s2_supported(cin: int, cout: int, k: int, stride: int, pad: int, dt
 
 def tc_wgrad_supported(cin: int, cout: int, k: int, stride: int, upsample: bool, dtype, h: int, w: int) -> bool:
     """Mirror of conv_wgrad_tc_supported() in csrc/conv_tc.cu."""
-    return (dtype == torch.bfloat16 and stride in (1, 2) and not upsample and k in (3, 4) and cin >= 16
-            and cin % 8 == 0 and cout >= 16 and cout % 8 == 0)
+    if dtype != torch.bfloat16 or upsample or k not in (3, 4) or stride not in (1, 2):
+        return False
+    if k == 3 and stride == 1:         # halo wgrad kernel: thin sides allowed (buffers have ld = 8)
+        return cout <= 32 or cout % 64 == 0
+    return cin >= 16 and cin % 8 == 0 and cout >= 16 and cout % 8 == 0
 
 
 def select(cin, cout, k, stride, upsample, dtype, h, w):

@@ -53,6 +53,14 @@ def select_engine(cin: int, cout: int, k: int, stride: int, upsample: bool, dtyp
     return _engine.select(cin, cout, k, stride, upsample, dtype, h, w)
 
 
+def _io_buf(n: int, h: int, w: int, c: int, dt, dev) -> Slice:
+    """NHWC buffer for a thin (image / logit) tensor.  In bf16 mode the pixel pitch is padded to 8 channels
+    (16 bytes) so that TMA tensor maps can address it; only the first ``c`` channels are ever touched."""
+    if dt == torch.bfloat16 and c < 8:
+        return Slice(ops.new_buf(n, h, w, 8, dt, dev), 0, c)
+    return Slice(ops.new_buf(n, h, w, c, dt, dev))
+
+
 def _engine_mod():
     from . import engine as _engine
     return _engine
@@ -141,7 +149,9 @@ class _NetBase(nn.Module):
         """dx = conv^T(dy) with epilogue.  Stride-1 wide convs run as an fprop over transposed weights
         (the path the tensor-core engine shares); strided / thin ones use the gather-form kernel."""
         k, s, p = conv.kernel_size[0], conv.stride[0], conv.padding[0]
-        if s == 1 and dy.c > 4 and dx.c > 4:
+        thin_tc = s == 1 and _engine_mod().select(dy.c, dx.c, k, 1, False, dy.dtype, dx.h, dx.w)[0] == ENGINE_TC \
+            and not (dx.c <= 16 and (ep.get("mask") is not None or ep.get("r1") is not None))
+        if s == 1 and ((dy.c > 4 and dx.c > 4) or thin_tc):
             eng, layout = select_engine(dy.c, dx.c, k, 1, False, dy.dtype, dx.h, dx.w)
             ops.conv_fprop(dy, self._w_t(conv, dy.dtype, layout), None, dx, k, 1, k - 1 - p, engine=eng, **ep)
         elif _engine_mod().tc_dgrad_s2_supported(dx.c, dy.c, k, s, p, dy.dtype):
@@ -334,9 +344,9 @@ class _RRDBGenerator(_NetBase):
         self._wgrad(self.conv_first, x_in, Slice(d_fea), sink, W(self.conv_first.weight), W(self.conv_first.bias))
         if not need_dx:
             return None
-        dx = ops.new_buf(n, h, w, x_in.c, dt, dev)
-        self._dgrad(self.conv_first, Slice(d_fea), Slice(dx))
-        return Slice(dx)
+        dx = _io_buf(n, h, w, x_in.c, dt, dev)
+        self._dgrad(self.conv_first, Slice(d_fea), dx)
+        return dx
 
 
 def _flat_params(module: nn.Module) -> List[nn.Parameter]:
@@ -403,7 +413,7 @@ class RDDBNetB(_RRDBGenerator):
     def _forward_impl(self, x: torch.Tensor, st: dict) -> torch.Tensor:
         dt, dev = act_dtype(), x.device
         n, c, h, w = x.shape
-        x_in = Slice(ops.new_buf(n, h, w, c, dt, dev))
+        x_in = _io_buf(n, h, w, c, dt, dev)
         ops.nchw_to_nhwc(x, x_in)
         cur = self._trunk_forward(x_in, st)
         acts = [cur]
@@ -422,7 +432,7 @@ class RDDBNetB(_RRDBGenerator):
             acts.append(nxt)
             cur = nxt
         st["ups"] = ups
-        out = Slice(ops.new_buf(n, cur.h, cur.w, self.conv_last.out_channels, dt, dev))
+        out = _io_buf(n, cur.h, cur.w, self.conv_last.out_channels, dt, dev)
         self._fprop(self.conv_last, cur, out)
         st["acts"] = acts
         return ops.nhwc_to_nchw(out)
@@ -434,7 +444,7 @@ class RDDBNetB(_RRDBGenerator):
         W = lambda p: p is not None and want.get(id(p), False)
         n = acts[0].n
         last = acts[-1]
-        d_o = Slice(ops.new_buf(n, last.h, last.w, self.conv_last.out_channels, dt, dev))
+        d_o = _io_buf(n, last.h, last.w, self.conv_last.out_channels, dt, dev)
         ops.nchw_to_nhwc(grad_out, d_o)
         self._wgrad(self.conv_last, last, d_o, sink, W(self.conv_last.weight), W(self.conv_last.bias))
         stages = self._stages()
@@ -491,7 +501,7 @@ class RDDBNetA(_RRDBGenerator):
     def _forward_impl(self, x, st):
         dt, dev = act_dtype(), x.device
         n, c, h, w = x.shape
-        x_in = Slice(ops.new_buf(n, h, w, c, dt, dev))
+        x_in = _io_buf(n, h, w, c, dt, dev)
         ops.nchw_to_nhwc(x, x_in)
         cur = self._trunk_forward(x_in, st)
         training = self.training
@@ -509,7 +519,7 @@ class RDDBNetA(_RRDBGenerator):
                 bn.num_batches_tracked += 1
             ys.append(y); zs.append(z); stats.append((sm, si, use_batch))
             cur = z
-        out = Slice(ops.new_buf(n, cur.h, cur.w, self.conv_last.out_channels, dt, dev))
+        out = _io_buf(n, cur.h, cur.w, self.conv_last.out_channels, dt, dev)
         self._fprop(self.conv_last, cur, out)
         st["ys"], st["zs"], st["stats"] = ys, zs, stats
         return ops.nhwc_to_nchw(out)
@@ -520,7 +530,7 @@ class RDDBNetA(_RRDBGenerator):
         W = lambda p: p is not None and want.get(id(p), False)
         n = zs[0].n
         last = zs[-1]
-        d_o = Slice(ops.new_buf(n, last.h, last.w, self.conv_last.out_channels, dt, dev))
+        d_o = _io_buf(n, last.h, last.w, self.conv_last.out_channels, dt, dev)
         ops.nchw_to_nhwc(grad_out, d_o)
         self._wgrad(self.conv_last, last, d_o, sink, W(self.conv_last.weight), W(self.conv_last.bias))
         g = Slice(ops.new_buf(n, last.h, last.w, last.c, dt, dev))
@@ -584,7 +594,7 @@ class RDDBNet(_RRDBGenerator):
     def _forward_impl(self, x, st):
         dt, dev = act_dtype(), x.device
         n, c, h, w = x.shape
-        x_in = Slice(ops.new_buf(n, h, w, c, dt, dev))
+        x_in = _io_buf(n, h, w, c, dt, dev)
         ops.nchw_to_nhwc(x, x_in)
         cur = self._trunk_forward(x_in, st)
         nf = self.nf
@@ -597,7 +607,7 @@ class RDDBNet(_RRDBGenerator):
             ops.depth_to_space(wide, big)
             ups.append((cur, wide))
             cur = big
-        out = Slice(ops.new_buf(n, cur.h, cur.w, self.conv_last.out_channels, dt, dev))
+        out = _io_buf(n, cur.h, cur.w, self.conv_last.out_channels, dt, dev)
         self._fprop(self.conv_last, cur, out)
         st["ups"], st["last_in"] = ups, cur
         return ops.nhwc_to_nchw(out)
@@ -607,7 +617,7 @@ class RDDBNet(_RRDBGenerator):
         W = lambda p: p is not None and want.get(id(p), False)
         last = st["last_in"]
         n, nf = last.n, self.nf
-        d_o = Slice(ops.new_buf(n, last.h, last.w, self.conv_last.out_channels, dt, dev))
+        d_o = _io_buf(n, last.h, last.w, self.conv_last.out_channels, dt, dev)
         ops.nchw_to_nhwc(grad_out, d_o)
         self._wgrad(self.conv_last, last, d_o, sink, W(self.conv_last.weight), False)
         g = Slice(ops.new_buf(n, last.h, last.w, nf, dt, dev))
@@ -660,7 +670,7 @@ class SRDN(_RRDBGenerator):
         dt, dev = act_dtype(), x.device
         n, c, h, w = x.shape
         nf, ctot = self.nf, self.nf + 4 * self.gc
-        x_in = Slice(ops.new_buf(n, h, w, c, dt, dev))
+        x_in = _io_buf(n, h, w, c, dt, dev)
         ops.nchw_to_nhwc(x, x_in)
         enc, dec = self._rdbs_of(self.RRDB_encoder), self._rdbs_of(self.RRDB_decoder)
         be = [ops.new_buf(n, h, w, ctot, dt, dev) for _ in enc]
@@ -672,7 +682,7 @@ class SRDN(_RRDBGenerator):
         ops.add(Slice(be[0], 0, nf), tmp, Slice(bd[0], 0, nf))          # fea = fea + encoder(fea)
         self._chain_forward(dec, bd, tmp)
         ops.add(Slice(bd[0], 0, nf), tmp, fea2)                          # fea = fea + decoder(fea)
-        out = Slice(ops.new_buf(n, h, w, self.conv_last.out_channels, dt, dev))
+        out = _io_buf(n, h, w, self.conv_last.out_channels, dt, dev)
         self._fprop(self.conv_last, fea2, out)
         st["x_in"], st["be"], st["bd"], st["fea2"] = x_in, be, bd, fea2
         return ops.nhwc_to_nchw(out)
@@ -683,7 +693,7 @@ class SRDN(_RRDBGenerator):
         x_in, be, bd, fea2 = st["x_in"], st["be"], st["bd"], st["fea2"]
         n, h, w, nf, ctot = x_in.n, x_in.h, x_in.w, self.nf, self.nf + 4 * self.gc
         enc, dec = self._rdbs_of(self.RRDB_encoder), self._rdbs_of(self.RRDB_decoder)
-        d_o = Slice(ops.new_buf(n, h, w, self.conv_last.out_channels, dt, dev))
+        d_o = _io_buf(n, h, w, self.conv_last.out_channels, dt, dev)
         ops.nchw_to_nhwc(grad_out, d_o)
         self._wgrad(self.conv_last, fea2, d_o, sink, W(self.conv_last.weight), False)
         Dbuf = [ops.new_buf(n, h, w, ctot, dt, dev) for _ in range(4)]
@@ -703,7 +713,7 @@ class SRDN(_RRDBGenerator):
         self._wgrad(self.conv_first, x_in, d_fea, sink, W(self.conv_first.weight), W(self.conv_first.bias))
         if not need_dx:
             return None
-        dx = Slice(ops.new_buf(n, h, w, x_in.c, dt, dev))
+        dx = _io_buf(n, h, w, x_in.c, dt, dev)
         self._dgrad(self.conv_first, d_fea, dx)
         return ops.nhwc_to_nchw(dx)
 
@@ -751,7 +761,7 @@ class NLayerDiscriminator(_NetBase):
     def _forward_impl(self, x, st):
         dt, dev = act_dtype(), x.device
         n, c, h, w = x.shape
-        cur = Slice(ops.new_buf(n, h, w, c, dt, dev))
+        cur = _io_buf(n, h, w, c, dt, dev)
         ops.nchw_to_nhwc(x, cur)
         ins, ys, outs, stats = [], [], [], []
         training = self.training
@@ -761,7 +771,7 @@ class NLayerDiscriminator(_NetBase):
             if ho < 1 or wo < 1:
                 raise RuntimeError("NLayerDiscriminator: input %dx%d too small" % (h, w))
             ins.append(cur)
-            y = Slice(ops.new_buf(n, ho, wo, conv.out_channels, dt, dev))
+            y = _io_buf(n, ho, wo, conv.out_channels, dt, dev)
             if bn is None:
                 self._fprop(conv, cur, y, act=(LRELU if act else None))
                 ys.append(None); stats.append(None)
@@ -786,7 +796,7 @@ class NLayerDiscriminator(_NetBase):
         W = lambda p: p is not None and want.get(id(p), False)
         plan = self._plan()
         n = ins[0].n
-        g = Slice(ops.new_buf(n, outs[-1].h, outs[-1].w, outs[-1].c, dt, dev))
+        g = _io_buf(n, outs[-1].h, outs[-1].w, outs[-1].c, dt, dev)
         ops.nchw_to_nhwc(grad_out, g)
         # g is always the gradient w.r.t. the *conv output* of layer i when we reach its wgrad
         for i in range(len(plan) - 1, -1, -1):
@@ -801,7 +811,7 @@ class NLayerDiscriminator(_NetBase):
             if i == 0 and not need_dx:
                 return None
             src = ins[i]
-            nxt = Slice(ops.new_buf(n, src.h, src.w, src.c, dt, dev))
+            nxt = _io_buf(n, src.h, src.w, src.c, dt, dev)
             # the previous layer's LeakyReLU (no BN) is folded into this dgrad's mask epilogue
             prev_plain_act = i > 0 and plan[i - 1][1] is None and plan[i - 1][2]
             if prev_plain_act:

@@ -121,10 +121,13 @@ def test_engine_selection():
     bf, f32 = torch.bfloat16, torch.float32
     assert engine.select(64, 32, 3, 1, False, bf, 64, 64) == (ENGINE_TC, WL_TC)
     assert engine.select(64, 32, 3, 1, False, f32, 64, 64) == (ENGINE_SIMT, WL_RSCK)      # fp32 parity mode
-    assert engine.select(3, 64, 3, 1, False, bf, 64, 64) == (ENGINE_SIMT, WL_RSCK)        # thin image conv
-    assert engine.select(64, 3, 3, 1, False, bf, 64, 64)[0] == ENGINE_SIMT
+    assert engine.select(3, 64, 3, 1, False, bf, 64, 64) == (ENGINE_TC, WL_TC)            # thin image convs: K / N padded
+    assert engine.select(64, 3, 3, 1, False, bf, 64, 64)[0] == ENGINE_TC
+    assert engine.select(256, 1, 4, 1, False, bf, 62, 62)[0] == ENGINE_SIMT               # 4x4 patch-logit conv
+    assert engine.select(3, 64, 3, 1, False, f32, 64, 64)[0] == ENGINE_SIMT
     assert engine.select_wgrad(192, 64, 3, 1, False, bf, 64, 64) == ENGINE_TC
-    assert engine.select_wgrad(3, 64, 3, 1, False, bf, 64, 64) == ENGINE_SIMT
+    assert engine.select_wgrad(3, 64, 3, 1, False, bf, 64, 64) == ENGINE_TC
+    assert engine.select_wgrad(3, 64, 4, 2, False, bf, 64, 64) == ENGINE_SIMT
 
 
 def test_dropin_modules_resolve_reference_imports():
