@@ -146,6 +146,55 @@ __global__ void bn_bwd_apply_vec(const __nv_bfloat16* __restrict__ dy, int dy_ld
   *reinterpret_cast<uint4*>(dx + m * dx_ld + ch) = pack8b(d);
 }
 
+// bf16, 16-byte loads: thread = (row lane, channel octet); two sums per channel, block tree-reduce
+template <bool BWD>
+__global__ void __launch_bounds__(256)
+bn_partial_vec(const __nv_bfloat16* __restrict__ x, int x_ld, const __nv_bfloat16* __restrict__ dy, int dy_ld,
+               const __nv_bfloat16* __restrict__ y, int y_ld, int64_t npix, int c, const float* __restrict__ mean,
+               const float* __restrict__ invstd, float slope, float* __restrict__ p0, float* __restrict__ p1) {
+  __shared__ float r0[256][9], r1[256][9];
+  const int octets = c >> 3;
+  const int rows_per_iter = 256 / octets;
+  const int oc = threadIdx.x % octets, rl = threadIdx.x / octets;
+  float s[8], q[8];
+#pragma unroll
+  for (int i = 0; i < 8; ++i) { s[i] = 0.f; q[i] = 0.f; }
+  if (rl < rows_per_iter) {
+    float mu[8], is[8];
+    if (BWD) {
+#pragma unroll
+      for (int i = 0; i < 8; ++i) { mu[i] = mean[oc * 8 + i]; is[i] = invstd[oc * 8 + i]; }
+    }
+    for (int64_t m = (int64_t)blockIdx.x * rows_per_iter + rl; m < npix; m += (int64_t)gridDim.x * rows_per_iter) {
+      float xv[8];
+      unpack8b(__ldg(reinterpret_cast<const uint4*>(x + m * x_ld + oc * 8)), xv);
+      if (!BWD) {
+#pragma unroll
+        for (int i = 0; i < 8; ++i) { s[i] += xv[i]; q[i] = fmaf(xv[i], xv[i], q[i]); }
+      } else {
+        float dv[8], yv[8];
+        unpack8b(__ldg(reinterpret_cast<const uint4*>(dy + m * dy_ld + oc * 8)), dv);
+        unpack8b(__ldg(reinterpret_cast<const uint4*>(y + m * y_ld + oc * 8)), yv);
+#pragma unroll
+        for (int i = 0; i < 8; ++i) {
+          const float dz = yv[i] > 0.f ? dv[i] : dv[i] * slope;
+          s[i] += dz; q[i] = fmaf(dz, (xv[i] - mu[i]) * is[i], q[i]);
+        }
+      }
+    }
+  }
+#pragma unroll
+  for (int i = 0; i < 8; ++i) { r0[threadIdx.x][i] = s[i]; r1[threadIdx.x][i] = q[i]; }
+  __syncthreads();
+  if (threadIdx.x < c) {
+    const int o = threadIdx.x >> 3, i = threadIdx.x & 7;
+    float a = 0.f, bsum = 0.f;
+    for (int r = 0; r < rows_per_iter; ++r) { a += r0[r * octets + o][i]; bsum += r1[r * octets + o][i]; }
+    p0[(int64_t)blockIdx.x * c + threadIdx.x] = a;
+    p1[(int64_t)blockIdx.x * c + threadIdx.x] = bsum;
+  }
+}
+
 // partial sums of dz and dz*xhat, dz = dy_post * lrelu'(y)
 template <typename T>
 __global__ void bn_bwd_partial(const T* __restrict__ dy, int dy_ld, const T* __restrict__ y, int y_ld,
@@ -221,7 +270,11 @@ static int bn_forward_t(const T* x, int x_ld, T* y, int y_ld, int64_t npix, int 
     float* psum = ws;
     float* psq = ws + (size_t)parts * c;
     dim3 grid(ceil_div(c, 32), parts), blk(32, 8);
-    bn_stats_partial<T><<<grid, blk, 0, st>>>(x, x_ld, npix, c, psum, psq);
+    if (sizeof(T) == 2 && c % 8 == 0 && c <= 256 && x_ld % 8 == 0 && ((uintptr_t)x) % 16 == 0)
+      bn_partial_vec<false><<<parts, 256, 0, st>>>(reinterpret_cast<const __nv_bfloat16*>(x), x_ld, nullptr, 0, nullptr, 0,
+                                                   npix, c, nullptr, nullptr, 0.f, psum, psq);
+    else
+      bn_stats_partial<T><<<grid, blk, 0, st>>>(x, x_ld, npix, c, psum, psq);
     bn_finalize<<<ceil_div(c, 128), 128, 0, st>>>(psum, psq, parts, c, npix, eps, momentum, rm, rv, save_mean,
                                                   save_invstd);
     count_launch(2);
@@ -263,7 +316,14 @@ static int bn_backward_t(const T* dy, int dy_ld, const T* y, int y_ld, const T* 
   float* p1 = ws + (size_t)parts * c;
   float* tot = ws + (size_t)2 * parts * c;
   dim3 grid(ceil_div(c, 32), parts), blk(32, 8);
-  bn_bwd_partial<T><<<grid, blk, 0, st>>>(dy, dy_ld, y, y_ld, x, x_ld, npix, c, mean, invstd, slope, p0, p1);
+  if (sizeof(T) == 2 && c % 8 == 0 && c <= 256 && x_ld % 8 == 0 && dy_ld % 8 == 0 && y_ld % 8 == 0 &&
+      ((uintptr_t)x) % 16 == 0 && ((uintptr_t)dy) % 16 == 0 && ((uintptr_t)y) % 16 == 0)
+    bn_partial_vec<true><<<parts, 256, 0, st>>>(reinterpret_cast<const __nv_bfloat16*>(x), x_ld,
+                                                reinterpret_cast<const __nv_bfloat16*>(dy), dy_ld,
+                                                reinterpret_cast<const __nv_bfloat16*>(y), y_ld, npix, c, mean, invstd,
+                                                slope, p0, p1);
+  else
+    bn_bwd_partial<T><<<grid, blk, 0, st>>>(dy, dy_ld, y, y_ld, x, x_ld, npix, c, mean, invstd, slope, p0, p1);
   bn_bwd_finalize<<<ceil_div(c, 128), 128, 0, st>>>(p0, p1, parts, c, tot, dgamma, dbeta, accumulate);
   if (sizeof(T) == 2 && c % 8 == 0 && dy_ld % 8 == 0 && y_ld % 8 == 0 && x_ld % 8 == 0 && dx_ld % 8 == 0 &&
       ((uintptr_t)dy) % 16 == 0 && ((uintptr_t)y) % 16 == 0 && ((uintptr_t)x) % 16 == 0 && ((uintptr_t)dx) % 16 == 0)

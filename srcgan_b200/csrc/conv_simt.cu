@@ -885,7 +885,7 @@ int wgrad_reduce_launch(const float* part, int splits, int taps, int cin, int co
 int bias_grad_launch(const void* dy, int dy_ld, int dtype, long long M, int cout, float* db, int accumulate,
                      float alpha, void* ws, cudaStream_t st) {
   float* bpart = reinterpret_cast<float*>(ws);
-  if (dtype == SRCGAN_DT_BF16 && cout % 8 == 0 && cout <= 256 && 256 % (cout / 8) == 0 && dy_ld % 8 == 0 &&
+  if (dtype == SRCGAN_DT_BF16 && cout % 8 == 0 && cout <= 256 && dy_ld % 8 == 0 &&
       ((uintptr_t)dy) % 16 == 0) {
     const int rows_per_iter = 256 / (cout / 8);
     long long nb = (M + (long long)rows_per_iter * 8 - 1) / ((long long)rows_per_iter * 8);

@@ -168,8 +168,32 @@ __global__ void add_k(const T* __restrict__ a, int a_ld, const T* __restrict__ b
   d[m * d_ld + ch] = from_f32<T>(to_f32(a[m * a_ld + ch]) + to_f32(b[m * b_ld + ch]));
 }
 
+__global__ void add_vec_bf16(const __nv_bfloat16* __restrict__ a, int a_ld, const __nv_bfloat16* __restrict__ b, int b_ld,
+                             __nv_bfloat16* __restrict__ d, int d_ld, int64_t npix, int oct) {
+  int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= npix * oct) return;
+  const int ch = (int)(i % oct) * 8;
+  const int64_t m = i / oct;
+  uint4 qa = __ldg(reinterpret_cast<const uint4*>(a + m * a_ld + ch)), qb = __ldg(reinterpret_cast<const uint4*>(b + m * b_ld + ch));
+  const __nv_bfloat162* ha = reinterpret_cast<const __nv_bfloat162*>(&qa);
+  const __nv_bfloat162* hb = reinterpret_cast<const __nv_bfloat162*>(&qb);
+  uint4 o;
+  __nv_bfloat162* ho = reinterpret_cast<__nv_bfloat162*>(&o);
+#pragma unroll
+  for (int k = 0; k < 4; ++k)
+    ho[k] = __floats2bfloat162_rn(__low2float(ha[k]) + __low2float(hb[k]), __high2float(ha[k]) + __high2float(hb[k]));
+  *reinterpret_cast<uint4*>(d + m * d_ld + ch) = o;
+}
+
 int add_slices(const void* a, int a_ld, const void* b, int b_ld, void* d, int d_ld, int64_t npix, int c, int dtype,
                cudaStream_t st) {
+  if (dtype == SRCGAN_DT_BF16 && c % 8 == 0 && a_ld % 8 == 0 && b_ld % 8 == 0 && d_ld % 8 == 0 &&
+      ((uintptr_t)a) % 16 == 0 && ((uintptr_t)b) % 16 == 0 && ((uintptr_t)d) % 16 == 0) {
+    add_vec_bf16<<<ceil_div(npix * (c / 8), 256), 256, 0, st>>>((const __nv_bfloat16*)a, a_ld, (const __nv_bfloat16*)b, b_ld,
+                                                                (__nv_bfloat16*)d, d_ld, npix, c / 8);
+    count_launch();
+    return check_launch("add");
+  }
   if (dtype == SRCGAN_DT_F32)
     add_k<float><<<ceil_div(npix * c, 256), 256, 0, st>>>((const float*)a, a_ld, (const float*)b, b_ld, (float*)d, d_ld,
                                                           npix, c);

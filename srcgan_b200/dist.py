@@ -52,14 +52,15 @@ def allreduce_mean_(tensors: List[torch.Tensor]) -> None:
     n = world()
     if n == 1 or not tensors:
         return
-    flat = torch.cat([t.reshape(-1) for t in tensors])
+    flat = torch.cat([t.reshape(-1) for t in tensors])          # one bucket: one NCCL call over NVLink
     dist.all_reduce(flat, op=dist.ReduceOp.SUM)
     flat.mul_(1.0 / n)
-    off = 0
+    views, off = [], 0
     for t in tensors:
         k = t.numel()
-        t.copy_(flat[off:off + k].view_as(t))
+        views.append(flat[off:off + k].view_as(t))
         off += k
+    torch._foreach_copy_(tensors, views)                         # one fused scatter back into the .grad tensors
 
 
 def _step_pre_hook(optimizer, args, kwargs):
