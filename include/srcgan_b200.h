@@ -135,6 +135,11 @@ int srcgan_depth_to_space(const void* src, int src_ld, void* dst, int dst_ld, in
 int srcgan_space_to_depth(const void* src, int src_ld, void* dst, int dst_ld, const void* mask, int mask_ld,
                           float mask_slope, int n, int h, int w, int c, int dtype, void* stream);
 
+/* nn.PixelShuffle(r) (src/model/espcn.py:35,50) in NHWC: dst[n,h*r+a,w*r+b,c] = src[n,h,w,c*r*r+a*r+b];
+ * (n,h,w) are the LOW-resolution dims, c the number of output channels; adjoint != 0 runs the inverse. */
+int srcgan_pixel_shuffle(const void* src, int src_ld, void* dst, int dst_ld, int n, int h, int w, int c, int r,
+                         int dtype, int adjoint, void* stream);
+
 /* dst[n,2h,2w,c] = nearest x2 of src[n,h,w,c]  (F.interpolate(scale_factor=2, 'nearest'), model.py:426-427) */
 int srcgan_upsample2x(const void* src, int src_ld, void* dst, int dst_ld, int n, int h, int w, int c, int dtype,
                       void* stream);

@@ -119,6 +119,16 @@ def cascade_fixture() -> dict:
     y = net(x)
     (y * probe_like(y, 18)).sum().backward()
     fx["SRDN"] = {"out": y.detach().clone(), "grad_norms": grad_norms(net), "dx": x.grad.clone()}
+    # plain conv stacks: ESPCN (5x5 + PixelShuffle) and SRCNN (9x9 / 1x1 / 5x5, trailing ReLU)
+    for name, net, sd in (("ESPCN_x2", pkg.ESPCN(1, 1, 2), O.init_espcn(33, 1, 1, 2)),
+                          ("ESPCN_x4_rgb", pkg.ESPCN(3, 3, 4), O.init_espcn(34, 3, 3, 4)),
+                          ("SRCNN", pkg.SRCNN(1, 3, 2), O.init_srcnn(35, 1, 3))):
+        net.load_state_dict(sd, strict=True)
+        cin = sd["conv1.weight"].shape[1]
+        x = rand((2, cin, 14, 10), 303).requires_grad_(True)
+        y = net(x)
+        (y * probe_like(y, 19)).sum().backward()
+        fx[name] = {"out": y.detach().clone(), "grad_norms": grad_norms(net), "dx": x.grad.clone()}
     return fx
 
 

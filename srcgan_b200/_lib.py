@@ -61,6 +61,7 @@ SIGNATURES = {
     "srcgan_colsum": (_I, [_P, _I, _I, _L, _I, _P, _F, _I, _P, _Z, _P]),
     "srcgan_depth_to_space": (_I, [_P, _I, _P, _I, _I, _I, _I, _I, _I, _P]),
     "srcgan_space_to_depth": (_I, [_P, _I, _P, _I, _P, _I, _F, _I, _I, _I, _I, _I, _P]),
+    "srcgan_pixel_shuffle": (_I, [_P, _I, _P, _I, _I, _I, _I, _I, _I, _I, _I, _P]),
     "srcgan_upsample2x": (_I, [_P, _I, _P, _I, _I, _I, _I, _I, _I, _P]),
     "srcgan_upsample2x_adjoint": (_I, [_P, _I, _P, _I, _P, _I, _F, _I, _I, _I, _I, _I, _P]),
     "srcgan_bn_workspace_bytes": (_Z, [_L, _I]),

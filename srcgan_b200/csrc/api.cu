@@ -51,6 +51,8 @@ int nchw_to_nhwc(const float* src, int n, int c, int h, int w, void* dst, int ld
 int nhwc_to_nchw(const void* src, int ld, int dtype, float* dst, int n, int c, int h, int w, cudaStream_t st);
 int depth_to_space(const void* src, int src_ld, void* dst, int dst_ld, const void* mask, int mask_ld, float mslope,
                    int n, int h, int w, int c, int dtype, int adjoint, cudaStream_t st);
+int pixel_shuffle(const void* src, int src_ld, void* dst, int dst_ld, int n, int h, int w, int c, int r, int dtype,
+                  int adjoint, cudaStream_t st);
 int upsample2x(const void* src, int src_ld, void* dst, int dst_ld, int n, int h, int w, int c, int dtype,
                cudaStream_t st);
 int upsample2x_adjoint(const void* src, int src_ld, void* dst, int dst_ld, const void* mask, int mask_ld,
@@ -170,6 +172,11 @@ int srcgan_space_to_depth(const void* src, int src_ld, void* dst, int dst_ld, co
                           float mask_slope, int n, int h, int w, int c, int dtype, void* stream) {
   SRCGAN_REQUIRE(src && dst && n > 0 && c > 0 && h > 0 && w > 0, "space_to_depth: bad arguments");
   return depth_to_space(src, src_ld, dst, dst_ld, mask, mask_ld, mask_slope, n, h, w, c, dtype, 1, (cudaStream_t)stream);
+}
+int srcgan_pixel_shuffle(const void* src, int src_ld, void* dst, int dst_ld, int n, int h, int w, int c, int r,
+                         int dtype, int adjoint, void* stream) {
+  SRCGAN_REQUIRE(src && dst && n > 0 && c > 0 && h > 0 && w > 0 && r > 0, "pixel_shuffle: bad arguments");
+  return pixel_shuffle(src, src_ld, dst, dst_ld, n, h, w, c, r, dtype, adjoint, (cudaStream_t)stream);
 }
 int srcgan_upsample2x_adjoint(const void* src, int src_ld, void* dst, int dst_ld, const void* mask, int mask_ld,
                               float mask_slope, int n, int h, int w, int c, int dtype, void* stream) {

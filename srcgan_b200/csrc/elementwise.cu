@@ -143,6 +143,41 @@ __global__ void d2s_k(const T* __restrict__ src, int src_ld, T* __restrict__ dst
   }
 }
 
+// nn.PixelShuffle(r) in NHWC (src/model/espcn.py:35,50): dst[n,h*r+a,w*r+b,c] = src[n,h,w,c*r*r+a*r+b]; ADJ = inverse
+template <typename T, bool ADJ>
+__global__ void pixel_shuffle_k(const T* __restrict__ src, int src_ld, T* __restrict__ dst, int dst_ld, int n, int h,
+                                int w, int c, int r) {
+  const int rr = r * r;
+  int64_t total = (int64_t)n * h * w * c * rr;
+  int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= total) return;
+  int wc = (int)(i % (c * rr));
+  int64_t p = i / (c * rr);
+  int x = (int)(p % w);
+  int64_t t = p / w;
+  int y = (int)(t % h);
+  int64_t b = t / h;
+  int ch = wc / rr, ab = wc - ch * rr, a_ = ab / r, b_ = ab - a_ * r;
+  int64_t big = ((b * h * r + (int64_t)y * r + a_) * ((int64_t)w * r) + (int64_t)x * r + b_);
+  if (!ADJ) dst[big * dst_ld + ch] = src[p * src_ld + wc];
+  else dst[p * dst_ld + wc] = src[big * src_ld + ch];
+}
+
+int pixel_shuffle(const void* src, int src_ld, void* dst, int dst_ld, int n, int h, int w, int c, int r, int dtype,
+                  int adjoint, cudaStream_t st) {
+  int64_t total = (int64_t)n * h * w * c * r * r;
+  unsigned grid = (unsigned)ceil_div(total, 256);
+  if (dtype == SRCGAN_DT_F32) {
+    if (adjoint) pixel_shuffle_k<float, true><<<grid, 256, 0, st>>>((const float*)src, src_ld, (float*)dst, dst_ld, n, h, w, c, r);
+    else pixel_shuffle_k<float, false><<<grid, 256, 0, st>>>((const float*)src, src_ld, (float*)dst, dst_ld, n, h, w, c, r);
+  } else {
+    if (adjoint) pixel_shuffle_k<__nv_bfloat16, true><<<grid, 256, 0, st>>>((const __nv_bfloat16*)src, src_ld, (__nv_bfloat16*)dst, dst_ld, n, h, w, c, r);
+    else pixel_shuffle_k<__nv_bfloat16, false><<<grid, 256, 0, st>>>((const __nv_bfloat16*)src, src_ld, (__nv_bfloat16*)dst, dst_ld, n, h, w, c, r);
+  }
+  count_launch();
+  return check_launch("pixel_shuffle");
+}
+
 int depth_to_space(const void* src, int src_ld, void* dst, int dst_ld, const void* mask, int mask_ld, float mslope,
                    int n, int h, int w, int c, int dtype, int adjoint, cudaStream_t st) {
   int64_t total = (int64_t)n * h * w * 4 * c;

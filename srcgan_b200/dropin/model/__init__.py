@@ -9,7 +9,7 @@ _root = os.path.dirname(os.path.dirname(os.path.dirname(os.path.dirname(os.path.
 if _root not in sys.path:
     sys.path.insert(0, _root)
 
-from srcgan_b200.nn import NLayerDiscriminator, RDDBNet, RDDBNetA, RDDBNetB, SRDN  # noqa: E402,F401
+from srcgan_b200.nn import ESPCN, NLayerDiscriminator, RDDBNet, RDDBNetA, RDDBNetB, SRCNN, SRDN  # noqa: E402,F401
 
 
 def _missing(name):
@@ -22,7 +22,7 @@ def _missing(name):
 
 SRDenseNetA = _missing("SRDenseNetA")
 SRDenseNetB = _missing("SRDenseNetB")
-for _n in ("ESPCN", "SRCNN", "EDSR", "ResDeconv"):
+for _n in ("EDSR", "ResDeconv"):
     globals()[_n] = _missing(_n)
 __all__ = ["RDDBNetA", "RDDBNetB", "NLayerDiscriminator", "SRDenseNetA", "SRDenseNetB",
            "ESPCN", "SRCNN", "EDSR", "RDDBNet", "SRDN", "ResDeconv"]

@@ -719,6 +719,103 @@ class SRDN(_RRDBGenerator):
 
 
 # ------------------------------------------------------------------------------------------
+# Plain conv stacks of the cascaded trainers (reference src/model/espcn.py, src/model/srcnn.py)
+# ------------------------------------------------------------------------------------------
+
+class _SeqConvNet(_NetBase):
+    """conv (+ReLU) / PixelShuffle sequences.  ``_layers()`` -> [("conv", module, relu: bool) | ("shuffle", r)]."""
+
+    def forward(self, x):
+        return _NetFn.apply(self, x, *_flat_params(self))
+
+    def _forward_impl(self, x, st):
+        dt, dev = act_dtype(), x.device
+        n, c, h, w = x.shape
+        cur = _io_buf(n, h, w, c, dt, dev)
+        ops.nchw_to_nhwc(x, cur)
+        acts = [cur]
+        for layer in self._layers():
+            if layer[0] == "conv":
+                conv, relu = layer[1], layer[2]
+                nxt = _io_buf(n, cur.h, cur.w, conv.out_channels, dt, dev)
+                self._fprop(conv, cur, nxt, act=(0.0 if relu else None))
+            else:
+                r = layer[1]
+                nxt = _io_buf(n, cur.h * r, cur.w * r, cur.c // (r * r), dt, dev)
+                ops.pixel_shuffle(cur, nxt, r)
+            acts.append(nxt)
+            cur = nxt
+        st["acts"] = acts
+        return ops.nhwc_to_nchw(cur)
+
+    def _backward_impl(self, st, grad_out, sink, want, need_dx):
+        dt, dev = act_dtype(), grad_out.device
+        W = lambda p: p is not None and want.get(id(p), False)
+        acts, layers = st["acts"], self._layers()
+        n = acts[0].n
+        g = _io_buf(n, acts[-1].h, acts[-1].w, acts[-1].c, dt, dev)
+        ops.nchw_to_nhwc(grad_out, g)
+        if layers[-1][0] == "conv" and layers[-1][2]:              # trailing ReLU (SRCNN): mask the incoming gradient
+            g.view().mul_((acts[-1].view() > 0).to(g.dtype))
+        for i in range(len(layers) - 1, -1, -1):
+            layer, src = layers[i], acts[i]
+            if i == 0 and not need_dx and layer[0] != "conv":
+                return None
+            prev_relu = i > 0 and layers[i - 1][0] == "conv" and layers[i - 1][2]
+            if layer[0] == "conv":
+                conv = layer[1]
+                self._wgrad(conv, src, g, sink, W(conv.weight), W(conv.bias))
+                if i == 0 and not need_dx:
+                    return None
+                nxt = _io_buf(n, src.h, src.w, src.c, dt, dev)
+                if prev_relu:
+                    self._dgrad(conv, g, nxt, mask=src, mask_slope=0.0)
+                else:
+                    self._dgrad(conv, g, nxt)
+            else:
+                nxt = _io_buf(n, src.h, src.w, src.c, dt, dev)
+                ops.pixel_shuffle(g, nxt, layer[1], adjoint=True)
+                if prev_relu:
+                    nxt.view().mul_((src.view() > 0).to(nxt.dtype))
+            g = nxt
+        return ops.nhwc_to_nchw(g)
+
+
+class ESPCN(_SeqConvNet):
+    """ESPCN(in_ch, ou_ch, upscale_factor, base_kernel): 5x5, 3x3, 3x3 (ReLU) -> 3x3 -> PixelShuffle -> 3x3."""
+
+    def __init__(self, in_ch=3, ou_ch=3, upscale_factor=2, base_kernel=64):
+        super().__init__()
+        k = [int(x * base_kernel) for x in [1, 1, 1 / 2]]
+        self.up = upscale_factor
+        self.conv1 = nn.Conv2d(in_ch, k[0], kernel_size=5, stride=1, padding=2)
+        self.conv2 = nn.Conv2d(k[0], k[1], kernel_size=3, stride=1, padding=1)
+        self.conv3 = nn.Conv2d(k[1], k[2], kernel_size=3, stride=1, padding=1)
+        self.conv4 = nn.Conv2d(k[2], base_kernel * upscale_factor ** 2, kernel_size=3, stride=1, padding=1)
+        self.conv5 = nn.Conv2d(base_kernel, ou_ch, kernel_size=3, stride=1, padding=1)
+        _kaiming_fanout_(self)
+
+    def _layers(self):
+        return [("conv", self.conv1, True), ("conv", self.conv2, True), ("conv", self.conv3, True),
+                ("conv", self.conv4, False), ("shuffle", self.up), ("conv", self.conv5, False)]
+
+
+class SRCNN(_SeqConvNet):
+    """SRCNN(in_ch, ou_ch, upscale_factor, base_kernel): 9x9, 1x1, 5x5, each followed by ReLU (no upsampling)."""
+
+    def __init__(self, in_ch=3, ou_ch=3, upscale_factor=2, base_kernel=64):
+        super().__init__()
+        k = [int(x * base_kernel) for x in [1, 1 / 2]]
+        self.up = upscale_factor
+        self.conv1 = nn.Conv2d(in_ch, k[0], kernel_size=9, stride=1, padding=4)
+        self.conv2 = nn.Conv2d(k[0], k[1], kernel_size=1, stride=1, padding=0)
+        self.conv3 = nn.Conv2d(k[1], ou_ch, kernel_size=5, stride=1, padding=2)
+
+    def _layers(self):
+        return [("conv", self.conv1, True), ("conv", self.conv2, True), ("conv", self.conv3, True)]
+
+
+# ------------------------------------------------------------------------------------------
 # NLayerDiscriminator (reference model.py:595-639), BatchNorm2d norm layer
 # ------------------------------------------------------------------------------------------
 

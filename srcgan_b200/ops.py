@@ -291,6 +291,14 @@ def space_to_depth(src: Slice, dst: Slice, mask: Optional[Slice] = None, mask_sl
         float(mask_slope), dst.n, dst.h, dst.w, src.c, dt_code(dst.dtype), _stream()), "space_to_depth")
 
 
+def pixel_shuffle(src: Slice, dst: Slice, r: int, adjoint: bool = False) -> None:
+    """forward: src (n,h,w,c*r*r) -> dst (n,h*r,w*r,c); adjoint: src (n,h*r,w*r,c) -> dst (n,h,w,c*r*r)"""
+    lo, hi = (dst, src) if adjoint else (src, dst)
+    assert hi.h == lo.h * r and hi.w == lo.w * r and lo.c == hi.c * r * r
+    _lib.check(_lib.load().srcgan_pixel_shuffle(src.ptr, src.ld, dst.ptr, dst.ld, lo.n, lo.h, lo.w, hi.c, r,
+                                                dt_code(dst.dtype), int(adjoint), _stream()), "pixel_shuffle")
+
+
 def upsample2x(src: Slice, dst: Slice) -> None:
     assert dst.h == 2 * src.h and dst.w == 2 * src.w and src.c == dst.c
     _lib.check(_lib.load().srcgan_upsample2x(src.ptr, src.ld, dst.ptr, dst.ld, src.n, src.h, src.w, src.c,

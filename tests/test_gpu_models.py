@@ -298,3 +298,23 @@ def test_cascade_generators_parity(golden_cascade, which):
     with torch.no_grad():
         yb = net(x.to(DEV))
     assert relerr(yb, r64.y) < 0.1
+
+
+@pytest.mark.parametrize("which", ["ESPCN_x2", "ESPCN_x4_rgb", "SRCNN"])
+def test_plain_conv_stacks_parity(golden_cascade, which):
+    """ESPCN (5x5 conv, PixelShuffle) and SRCNN (9x9 / 1x1 / 5x5, trailing ReLU) on the CUDA path."""
+    from oracle import srcgan_oracle as O
+    from srcgan_b200 import nn as snn
+    from tests.test_oracle import cascade_case
+    fx = golden_cascade[which]
+    sd, fn, x, seed = cascade_case(which)
+    net = {"ESPCN_x2": lambda: snn.ESPCN(1, 1, 2), "ESPCN_x4_rgb": lambda: snn.ESPCN(3, 3, 4),
+           "SRCNN": lambda: snn.SRCNN(1, 3, 2)}[which]()
+    y, named, dx, r32, r64 = run_both(net, fn, sd, x, seed)
+    assert relerr(y, r64.y) < 1e-4 and relerr(y, fx["out"]) < 1e-4
+    check_grads(named, r32, r64)
+    assert l2err(dx, r64.dx) < grad_tol(r32.dx, r64.dx)
+    snn.set_precision("bf16")
+    with torch.no_grad():
+        yb = net(x.to(DEV))
+    assert relerr(yb, r64.y) < 0.1

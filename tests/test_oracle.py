@@ -170,6 +170,36 @@ def test_oracle_equals_live_reference():
     assert math.isclose(float(O.l1_loss(a, b)), float(losses.L1Loss()(a, b)), rel_tol=1e-6)
 
 
+def cascade_case(which):
+    """-> (state_dict, oracle_fn(sd, x), input, probe seed, constructor args) for one cascaded-trainer generator"""
+    if which == "SRDN":
+        return O.init_srdn(32), (lambda s, t: O.srdn(s, t)), rand((2, 1, 16, 12), 302), 18
+    if which.startswith("RDDBNet"):
+        up = int(which[-1])
+        return O.init_rddbnet_pkg(31, 1, 1, up), (lambda s, t: O.rddbnet_pkg(s, t, up)), rand((2, 1, 16, 12), 301), 17
+    if which == "ESPCN_x2":
+        return O.init_espcn(33, 1, 1, 2), (lambda s, t: O.espcn(s, t, 2)), rand((2, 1, 14, 10), 303), 19
+    if which == "ESPCN_x4_rgb":
+        return O.init_espcn(34, 3, 3, 4), (lambda s, t: O.espcn(s, t, 4)), rand((2, 3, 14, 10), 303), 19
+    if which == "SRCNN":
+        return O.init_srcnn(35, 1, 3), (lambda s, t: O.srcnn(s, t)), rand((2, 1, 14, 10), 303), 19
+    raise KeyError(which)
+
+
+@pytest.mark.parametrize("which", ["ESPCN_x2", "ESPCN_x4_rgb", "SRCNN"])
+def test_plain_conv_stacks_golden(golden_cascade, which):
+    """ESPCN (espcn.py) / SRCNN (srcnn.py): oracle vs outputs of the real reference."""
+    fx = golden_cascade[which]
+    sd0, fn, x, seed = cascade_case(which)
+    sd = O.as_leaf_params(sd0)
+    x = x.requires_grad_(True)
+    y = fn(sd, x)
+    assert y.shape == fx["out"].shape and relerr(y.detach(), fx["out"]) < TOL
+    (y * probe_like(y, seed)).sum().backward()
+    check_grad_norms(sd, fx["grad_norms"])
+    assert relerr(x.grad, fx["dx"]) < 1e-4
+
+
 @pytest.mark.parametrize("which", ["RDDBNet_x2", "RDDBNet_x4", "SRDN"])
 def test_cascade_generators_golden(golden_cascade, which):
     """package RDDBNet (rddb.py) / SRDN (srdn.py): oracle vs outputs of the real reference."""
