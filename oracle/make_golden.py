@@ -163,12 +163,41 @@ def step_fixture() -> dict:
     return out
 
 
+def cas_step_fixture() -> dict:
+    """Two iterations of the REAL ``trainCas*.CasSRC.optimize_parameters``: plain variant with ESPCN x2 + SRCNN
+    colouriser, ConstLAB variant (full-resolution SR input, LAB targets) with SRCNN + SRCNN as in runConstLAB.sh:
+    losses, PSNRs, transfer outputs."""
+    out = {}
+    for variant in ("", "ConstLAB"):
+        mod = ref_harness.import_traincas(variant)
+        opt = mod.params()
+        opt.device = torch.device("cpu")
+        opt.up, opt.SRModel, opt.CModel = 2, ("SRCNN" if "Const" in variant else "ESPCN"), "SRCNN"
+        model = mod.CasSRC(opt)
+        lab = "LAB" in variant
+        model.netG_A2C.load_state_dict(O.init_srcnn(51, 1, 1) if "Const" in variant else O.init_espcn(51, 1, 1, 2),
+                                       strict=True)
+        model.netG_C2B.load_state_dict(O.init_srcnn(52, 1, 2 if lab else 3), strict=True)
+        model.init_log()
+        steps = []
+        for it in range(2):
+            real_B = rand((2, 3, 32, 32), 600 + it)
+            real_A = rand((2, 1, 32, 32), 700 + it)
+            model.optimize_parameters(real_A, real_B)
+            steps.append({"loss_SR": float(model.loss_SR), "loss_C": float(model.loss_C),
+                          "psnr_SR": float(model.psnr_SR), "psnr_C": float(model.psnr_C),
+                          "fake_AB": model.fake_AB.detach().clone()})
+        out[variant or "plain"] = steps
+    return out
+
+
 def main() -> None:
     os.makedirs(OUT, exist_ok=True)
     torch.set_num_threads(os.cpu_count() or 1)
     torch.save(modules_fixture(), os.path.join(OUT, "modules_tiny.pt"))
     torch.save(step_fixture(), os.path.join(OUT, "step_tiny.pt"))
     torch.save(cascade_fixture(), os.path.join(OUT, "cascade_tiny.pt"))
+    torch.save(cas_step_fixture(), os.path.join(OUT, "cas_step_tiny.pt"))
     for f in sorted(os.listdir(OUT)):
         print(f, os.path.getsize(os.path.join(OUT, f)))
 

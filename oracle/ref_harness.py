@@ -90,3 +90,10 @@ def import_train():
             setattr(model_pkg, name, getattr(model_model, name))
     import importlib
     return importlib.import_module("train")
+
+
+def import_traincas(variant: str = ""):
+    """Imports the reference's ``trainCas{,Const,LAB,ConstLAB}`` module (CasSRC, params)."""
+    import_reference()
+    import importlib
+    return importlib.import_module("trainCas" + variant)

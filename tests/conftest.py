@@ -44,3 +44,9 @@ def golden_step():
 def golden_cascade():
     import torch
     return torch.load(os.path.join(GOLDEN, "cascade_tiny.pt"), weights_only=False)
+
+
+@pytest.fixture(scope="session")
+def golden_cas_step():
+    import torch
+    return torch.load(os.path.join(GOLDEN, "cas_step_tiny.pt"), weights_only=False)

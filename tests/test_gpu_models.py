@@ -318,3 +318,26 @@ def test_plain_conv_stacks_parity(golden_cascade, which):
     with torch.no_grad():
         yb = net(x.to(DEV))
     assert relerr(yb, r64.y) < 0.1
+
+
+@pytest.mark.parametrize("variant", ["", "ConstLAB"])
+def test_cascade_step_against_golden(golden_cas_step, variant):
+    """trainer_cas.CasSRC (mirror of trainCas*.py) on the CUDA path vs the real reference's iterations."""
+    from oracle import srcgan_oracle as O
+    from srcgan_b200 import trainer_cas
+    opt = trainer_cas.params()
+    opt.device = torch.device(DEV)
+    opt.up, opt.variant = 2, variant
+    opt.SRModel, opt.CModel = ("SRCNN" if "Const" in variant else "ESPCN"), "SRCNN"
+    m = trainer_cas.CasSRC(opt)
+    m.netG_A2C.load_state_dict(O.init_srcnn(51, 1, 1) if "Const" in variant else O.init_espcn(51, 1, 1, 2), strict=True)
+    m.netG_C2B.load_state_dict(O.init_srcnn(52, 1, 2 if "LAB" in variant else 3), strict=True)
+    for it, rec in enumerate(golden_cas_step[variant or "plain"]):
+        m.init_log()
+        m.optimize_parameters(rand((2, 1, 32, 32), 700 + it).to(DEV), rand((2, 3, 32, 32), 600 + it).to(DEV))
+        got = m.log_values()
+        for k, g in (("loss_SR", "loss_sr"), ("loss_C", "loss_c"), ("psnr_SR", "psnr_sr"), ("psnr_C", "psnr_c")):
+            assert math.isclose(got[g], rec[k], rel_tol=TOL, abs_tol=1e-5), (variant, it, k, got[g], rec[k])
+        assert relerr(m.fake_AB, rec["fake_AB"]) < TOL
+    with pytest.raises(NotImplementedError):
+        trainer_cas.build_model("ResDeconv", 1, 3)

@@ -219,3 +219,21 @@ def test_cascade_generators_golden(golden_cascade, which):
     (y * probe_like(y, seed)).sum().backward()
     check_grad_norms(sd, fx["grad_norms"])
     assert relerr(x.grad, fx["dx"]) < 1e-4
+
+
+def cas_oracle(variant):
+    lab, const = "LAB" in variant, "Const" in variant
+    sr_state = O.init_srcnn(51, 1, 1) if const else O.init_espcn(51, 1, 1, 2)
+    sr_fn = (lambda s, t: O.srcnn(s, t)) if const else (lambda s, t: O.espcn(s, t, 2))
+    return O.CascadeStepOracle(sr_state, O.init_srcnn(52, 1, 2 if lab else 3), sr_fn, lambda s, t: O.srcnn(s, t), 2, variant)
+
+
+@pytest.mark.parametrize("variant", ["", "ConstLAB"])
+def test_cascade_step_golden(golden_cas_step, variant):
+    """Two CasSRC iterations of the oracle reproduce the real trainCas*.py (losses, PSNRs, transfer output)."""
+    step = cas_oracle(variant)
+    for it, rec in enumerate(golden_cas_step[variant or "plain"]):
+        got = step.optimize_parameters(rand((2, 1, 32, 32), 700 + it), rand((2, 3, 32, 32), 600 + it))
+        for k in ("loss_SR", "loss_C", "psnr_SR", "psnr_C"):
+            assert math.isclose(got[k], rec[k], rel_tol=1e-4, abs_tol=1e-6), (variant, it, k, got[k], rec[k])
+        assert relerr(step.fake_AB, rec["fake_AB"]) < 1e-4
