@@ -118,6 +118,9 @@ int srcgan_nchw_to_nhwc(const float* src, int n, int c, int h, int w, void* dst,
 int srcgan_nhwc_to_nchw(const void* src, int src_ld, int dtype, float* dst, int n, int c, int h, int w, void* stream);
 
 /* dst = a + b over channel-sliced NHWC rows (gradient merge at the 'fea + trunk' skip, model.py:421) */
+/* dz = dy * (y > 0 ? 1 : slope): backward of an in-place (Leaky)ReLU whose output y was kept */
+int srcgan_act_backward(const void* dy, int dy_ld, const void* y, int y_ld, void* dz, int dz_ld, int64_t npix, int c,
+                        float slope, int dtype, void* stream);
 int srcgan_add(const void* a, int a_ld, const void* b, int b_ld, void* dst, int dst_ld, int64_t npix, int c, int dtype,
                void* stream);
 
@@ -162,6 +165,20 @@ int srcgan_bn_backward(const void* dy_post, int dy_ld, const void* y, int y_ld, 
                        const float* save_mean, const float* save_invstd, float slope, int training,
                        float* dgamma, float* dbeta, int accumulate,
                        void* workspace, size_t workspace_bytes, void* stream);
+
+/* GroupNorm(groups, c) over NHWC rows: statistics per (sample, group) over hw pixels x c/groups channels
+ * (nn.GroupNorm(32, C), src/model/resdeconv.py:67,75 and src/model/edsr.py:45); save_mean / save_rstd: fp32 [n*groups].
+ * forward fuses what follows the norm in the reference blocks: y = lrelu_slope(gn(x) + residual) (residual may be NULL,
+ * act = 0 disables the activation; BasicBlock.forward resdeconv.py:80-98, ResnetBlock.forward edsr.py:48-54). */
+size_t srcgan_gn_workspace_bytes(int n, int c);
+int srcgan_gn_forward(const void* x, int x_ld, void* y, int y_ld, int n, int64_t hw, int c, int groups, int dtype,
+                      const float* gamma, const float* beta, float* save_mean, float* save_rstd, float eps,
+                      const void* residual, int res_ld, int act, float slope, void* workspace, size_t workspace_bytes,
+                      void* stream);
+int srcgan_gn_backward(const void* dy, int dy_ld, const void* x, int x_ld, void* dx, int dx_ld, int n, int64_t hw, int c,
+                       int groups, int dtype, const float* gamma, const float* save_mean, const float* save_rstd,
+                       float* dgamma, float* dbeta, int accumulate, void* workspace, size_t workspace_bytes,
+                       void* stream);
 
 /* kind 0 = L1 (mean |a-b|), 1 = MSE (mean (a-b)^2); b == NULL means the scalar `b_scalar`
  * (GANLoss's expanded label).  loss_out: one fp32 (overwritten).  grad_out (optional, fp32[n]):

@@ -5,6 +5,7 @@ Fixtures hold only outputs (inputs and weights are regenerated from seeds throug
 ``oracle/srcgan_oracle.py``'s deterministic init + ``load_state_dict(strict=True)``):
   modules_tiny.pt   per-module outputs, per-parameter gradient norms, BN buffers,
                     loss / metric known answers
+  zoo_tiny.pt       ResDeconv / EDSR / SRDenseNetA,B outputs, gradient norms, input gradients
   step_tiny.pt      two consecutive ``train.SRCycleGAN.optimize_parameters`` calls
                     (x4, net '1', B=2, 16x16 -> 64x64): the 9 losses per step, parameter
                     norms after the Adam updates, BN buffers
@@ -132,6 +133,44 @@ def cascade_fixture() -> dict:
     return fx
 
 
+def zoo_cases():
+    """name -> (reference ctor(pkg, M), state_dict, oracle fn, input, probe seed); shared with the tests."""
+    return {
+        "ResDeconv": (lambda pkg, M: pkg.ResDeconv(1, 3), O.init_resdeconv(41, 3), lambda s, t: O.resdeconv(s, t),
+                      rand((2, 1, 32, 32), 401), 21),
+        "EDSR_x2": (lambda pkg, M: pkg.EDSR(1, 1, 2, num_residuals=3), O.init_edsr(42, 1, 1, 2, num_residuals=3),
+                    lambda s, t: O.edsr(s, t, 2, 3), rand((2, 1, 16, 12), 402), 22),
+        "EDSR_x4_rgb": (lambda pkg, M: pkg.EDSR(3, 3, 4, num_residuals=2), O.init_edsr(43, 3, 3, 4, num_residuals=2),
+                        lambda s, t: O.edsr(s, t, 4, 2), rand((2, 3, 8, 8), 403), 23),
+        "SRDenseNetA_x2": (lambda pkg, M: M.SRDenseNetA(1, 3, mode="x2", num_blocks=2, num_layers=2),
+                           O.init_srdensenet(44, "A", 1, 3), lambda s, t: O.srdensenet(s, t, "A", "x2"),
+                           rand((2, 1, 16, 12), 404), 24),
+        "SRDenseNetA_x4": (lambda pkg, M: M.SRDenseNetA(1, 3, mode="x4", num_blocks=2, num_layers=2),
+                           O.init_srdensenet(45, "A", 1, 3), lambda s, t: O.srdensenet(s, t, "A", "x4"),
+                           rand((2, 1, 8, 8), 405), 25),
+        "SRDenseNetB_x2": (lambda pkg, M: M.SRDenseNetB(3, 1, mode="x2", num_blocks=2, num_layers=2),
+                           O.init_srdensenet(46, "B", 3, 1), lambda s, t: O.srdensenet(s, t, "B", "x2"),
+                           rand((2, 3, 32, 24), 406), 26),
+        "SRDenseNetB_x4": (lambda pkg, M: M.SRDenseNetB(3, 1, mode="x4", num_blocks=2, num_layers=2),
+                           O.init_srdensenet(47, "B", 3, 1), lambda s, t: O.srdensenet(s, t, "B", "x4"),
+                           rand((2, 3, 32, 32), 407), 27),
+    }
+
+
+def zoo_fixture() -> dict:
+    """ResDeconv (resdeconv.py), EDSR (edsr.py), SRDenseNetA/B (model.py:659-778) run by the REAL reference."""
+    pkg, M, _losses, _metrics = ref_harness.import_reference()
+    fx = {}
+    for name, (ctor, sd, _fn, x, seed) in zoo_cases().items():
+        net = ctor(pkg, M)
+        net.load_state_dict(sd, strict=True)
+        x = x.clone().requires_grad_(True)
+        y = net(x)
+        (y * probe_like(y, seed)).sum().backward()
+        fx[name] = {"out": y.detach().clone(), "grad_norms": grad_norms(net), "dx": x.grad.clone()}
+    return fx
+
+
 def step_fixture() -> dict:
     train = ref_harness.import_train()
     opt = train.params()
@@ -198,6 +237,7 @@ def main() -> None:
     torch.save(step_fixture(), os.path.join(OUT, "step_tiny.pt"))
     torch.save(cascade_fixture(), os.path.join(OUT, "cascade_tiny.pt"))
     torch.save(cas_step_fixture(), os.path.join(OUT, "cas_step_tiny.pt"))
+    torch.save(zoo_fixture(), os.path.join(OUT, "zoo_tiny.pt"))
     for f in sorted(os.listdir(OUT)):
         print(f, os.path.getsize(os.path.join(OUT, f)))
 

@@ -56,6 +56,7 @@ SIGNATURES = {
     "srcgan_conv_wgrad": (_I, [C.POINTER(ConvParams), _P, _P, _I, _P, _Z, _P]),
     "srcgan_nchw_to_nhwc": (_I, [_P, _I, _I, _I, _I, _P, _I, _I, _P]),
     "srcgan_nhwc_to_nchw": (_I, [_P, _I, _I, _P, _I, _I, _I, _I, _P]),
+    "srcgan_act_backward": (_I, [_P, _I, _P, _I, _P, _I, _L, _I, _F, _I, _P]),
     "srcgan_add": (_I, [_P, _I, _P, _I, _P, _I, _L, _I, _I, _P]),
     "srcgan_colsum_workspace_bytes": (_Z, [_L, _I]),
     "srcgan_colsum": (_I, [_P, _I, _I, _L, _I, _P, _F, _I, _P, _Z, _P]),
@@ -67,6 +68,9 @@ SIGNATURES = {
     "srcgan_bn_workspace_bytes": (_Z, [_L, _I]),
     "srcgan_bn_forward": (_I, [_P, _I, _P, _I, _L, _I, _I, _P, _P, _P, _P, _P, _P, _I, _F, _F, _F, _P, _Z, _P]),
     "srcgan_bn_backward": (_I, [_P, _I, _P, _I, _P, _I, _P, _I, _L, _I, _I, _P, _P, _P, _F, _I, _P, _P, _I, _P, _Z, _P]),
+    "srcgan_gn_workspace_bytes": (_Z, [_I, _I]),
+    "srcgan_gn_forward": (_I, [_P, _I, _P, _I, _I, _L, _I, _I, _I, _P, _P, _P, _P, _F, _P, _I, _I, _F, _P, _Z, _P]),
+    "srcgan_gn_backward": (_I, [_P, _I, _P, _I, _P, _I, _I, _L, _I, _I, _I, _P, _P, _P, _P, _P, _I, _P, _Z, _P]),
     "srcgan_loss_workspace_bytes": (_Z, [_L]),
     "srcgan_loss_fwd_bwd": (_I, [_I, _P, _P, _F, _L, _P, _P, _P, _Z, _P]),
     "srcgan_metrics_sqerr": (_I, [_P, _P, _L, _P, _P, _Z, _P]),

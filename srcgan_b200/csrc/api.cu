@@ -69,6 +69,15 @@ int bn_backward(const void* dy, int dy_ld, const void* y, int y_ld, const void* 
                 int64_t npix, int c, int dtype, const float* gamma, const float* mean, const float* invstd,
                 float slope, int training, float* dgamma, float* dbeta, int accumulate, void* ws, size_t ws_bytes,
                 cudaStream_t st);
+size_t gn_workspace_bytes(int n, int c);
+int gn_forward(const void* x, int x_ld, void* y, int y_ld, int n, int64_t hw, int c, int groups, int dtype,
+               const float* gamma, const float* beta, float* mean, float* rstd, float eps, const void* res, int res_ld,
+               int act, float slope, void* ws, size_t ws_bytes, cudaStream_t st);
+int act_backward(const void* dy, int dy_ld, const void* y, int y_ld, void* dz, int dz_ld, int64_t npix, int c,
+                 float slope, int dtype, cudaStream_t st);
+int gn_backward(const void* dy, int dy_ld, const void* x, int x_ld, void* dx, int dx_ld, int n, int64_t hw, int c,
+                int groups, int dtype, const float* gamma, const float* mean, const float* rstd, float* dgamma,
+                float* dbeta, int accumulate, void* ws, size_t ws_bytes, cudaStream_t st);
 size_t loss_workspace_bytes(int64_t n);
 int loss_fwd_bwd(int kind, const float* a, const float* b, float b_scalar, int64_t n, float* loss_out,
                  float* grad_out, void* ws, size_t ws_bytes, int mean, cudaStream_t st);
@@ -191,6 +200,12 @@ int srcgan_add(const void* a, int a_ld, const void* b, int b_ld, void* dst, int 
   return add_slices(a, a_ld, b, b_ld, dst, dst_ld, npix, c, dtype, (cudaStream_t)stream);
 }
 
+int srcgan_act_backward(const void* dy, int dy_ld, const void* y, int y_ld, void* dz, int dz_ld, int64_t npix, int c,
+                        float slope, int dtype, void* stream) {
+  SRCGAN_REQUIRE(dy && y && dz && npix > 0 && c > 0, "act_backward: bad arguments");
+  return act_backward(dy, dy_ld, y, y_ld, dz, dz_ld, npix, c, slope, dtype, (cudaStream_t)stream);
+}
+
 size_t srcgan_colsum_workspace_bytes(int64_t, int c) { return (size_t)1024 * c * sizeof(float) + 256; }
 int srcgan_colsum(const void* x, int x_ld, int dtype, int64_t npix, int c, float* out, float alpha, int accumulate,
                   void* workspace, size_t workspace_bytes, void* stream) {
@@ -213,6 +228,22 @@ int srcgan_bn_backward(const void* dy_post, int dy_ld, const void* y, int y_ld, 
                        int accumulate, void* workspace, size_t workspace_bytes, void* stream) {
   return bn_backward(dy_post, dy_ld, y, y_ld, x, x_ld, dx, dx_ld, npix, c, dtype, gamma, save_mean, save_invstd,
                      slope, training, dgamma, dbeta, accumulate, workspace, workspace_bytes, (cudaStream_t)stream);
+}
+
+size_t srcgan_gn_workspace_bytes(int n, int c) { return gn_workspace_bytes(n, c); }
+int srcgan_gn_forward(const void* x, int x_ld, void* y, int y_ld, int n, int64_t hw, int c, int groups, int dtype,
+                      const float* gamma, const float* beta, float* save_mean, float* save_rstd, float eps,
+                      const void* residual, int res_ld, int act, float slope, void* workspace, size_t workspace_bytes,
+                      void* stream) {
+  return gn_forward(x, x_ld, y, y_ld, n, hw, c, groups, dtype, gamma, beta, save_mean, save_rstd, eps, residual, res_ld,
+                    act, slope, workspace, workspace_bytes, (cudaStream_t)stream);
+}
+int srcgan_gn_backward(const void* dy, int dy_ld, const void* x, int x_ld, void* dx, int dx_ld, int n, int64_t hw, int c,
+                       int groups, int dtype, const float* gamma, const float* save_mean, const float* save_rstd,
+                       float* dgamma, float* dbeta, int accumulate, void* workspace, size_t workspace_bytes,
+                       void* stream) {
+  return gn_backward(dy, dy_ld, x, x_ld, dx, dx_ld, n, hw, c, groups, dtype, gamma, save_mean, save_rstd, dgamma, dbeta,
+                     accumulate, workspace, workspace_bytes, (cudaStream_t)stream);
 }
 
 size_t srcgan_loss_workspace_bytes(int64_t n) { return loss_workspace_bytes(n); }

@@ -241,6 +241,54 @@ int add_slices(const void* a, int a_ld, const void* b, int b_ld, void* d, int d_
 }
 
 template <typename T>
+__global__ void act_bwd_k(const T* __restrict__ dy, int dy_ld, const T* __restrict__ y, int y_ld, T* __restrict__ d, int d_ld,
+                          int64_t npix, int c, float slope) {
+  int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= npix * c) return;
+  int ch = (int)(i % c);
+  int64_t m = i / c;
+  const float g = to_f32(dy[m * dy_ld + ch]);
+  d[m * d_ld + ch] = from_f32<T>(to_f32(y[m * y_ld + ch]) > 0.f ? g : g * slope);
+}
+
+__global__ void act_bwd_vec_bf16(const __nv_bfloat16* __restrict__ dy, int dy_ld, const __nv_bfloat16* __restrict__ y,
+                                 int y_ld, __nv_bfloat16* __restrict__ d, int d_ld, int64_t npix, int oct, float slope) {
+  int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= npix * oct) return;
+  const int ch = (int)(i % oct) * 8;
+  const int64_t m = i / oct;
+  uint4 qa = __ldg(reinterpret_cast<const uint4*>(dy + m * dy_ld + ch)), qb = __ldg(reinterpret_cast<const uint4*>(y + m * y_ld + ch));
+  const __nv_bfloat162* ha = reinterpret_cast<const __nv_bfloat162*>(&qa);
+  const __nv_bfloat162* hb = reinterpret_cast<const __nv_bfloat162*>(&qb);
+  uint4 o;
+  __nv_bfloat162* ho = reinterpret_cast<__nv_bfloat162*>(&o);
+#pragma unroll
+  for (int k = 0; k < 4; ++k) {
+    const float g0 = __low2float(ha[k]), g1 = __high2float(ha[k]);
+    ho[k] = __floats2bfloat162_rn(__low2float(hb[k]) > 0.f ? g0 : g0 * slope, __high2float(hb[k]) > 0.f ? g1 : g1 * slope);
+  }
+  *reinterpret_cast<uint4*>(d + m * d_ld + ch) = o;
+}
+
+int act_backward(const void* dy, int dy_ld, const void* y, int y_ld, void* d, int d_ld, int64_t npix, int c, float slope,
+                 int dtype, cudaStream_t st) {
+  if (dtype == SRCGAN_DT_BF16 && c % 8 == 0 && dy_ld % 8 == 0 && y_ld % 8 == 0 && d_ld % 8 == 0 &&
+      ((uintptr_t)dy) % 16 == 0 && ((uintptr_t)y) % 16 == 0 && ((uintptr_t)d) % 16 == 0) {
+    act_bwd_vec_bf16<<<ceil_div(npix * (c / 8), 256), 256, 0, st>>>((const __nv_bfloat16*)dy, dy_ld, (const __nv_bfloat16*)y,
+                                                                    y_ld, (__nv_bfloat16*)d, d_ld, npix, c / 8, slope);
+  } else if (dtype == SRCGAN_DT_F32) {
+    act_bwd_k<float><<<ceil_div(npix * c, 256), 256, 0, st>>>((const float*)dy, dy_ld, (const float*)y, y_ld, (float*)d,
+                                                              d_ld, npix, c, slope);
+  } else {
+    act_bwd_k<__nv_bfloat16><<<ceil_div(npix * c, 256), 256, 0, st>>>((const __nv_bfloat16*)dy, dy_ld,
+                                                                      (const __nv_bfloat16*)y, y_ld, (__nv_bfloat16*)d,
+                                                                      d_ld, npix, c, slope);
+  }
+  count_launch();
+  return check_launch("act_backward");
+}
+
+template <typename T>
 static int nchw_to_nhwc_t(const float* src, int n, int c, int h, int w, T* dst, int ld, cudaStream_t st) {
   int64_t hw = (int64_t)h * w, npix = hw * n;
   if (c <= 8) {

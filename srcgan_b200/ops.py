@@ -269,6 +269,11 @@ def add(a: Slice, b: Slice, dst: Slice) -> None:
                                       _stream()), "add")
 
 
+def act_backward(dy: Slice, y: Slice, dz: Slice, slope: float) -> None:
+    _lib.check(_lib.load().srcgan_act_backward(dy.ptr, dy.ld, y.ptr, y.ld, dz.ptr, dz.ld, dz.npix, dz.c, float(slope),
+                                               dt_code(dz.dtype), _stream()), "act_backward")
+
+
 def colsum(x: Slice, out: torch.Tensor, alpha: float = 1.0, accumulate: bool = False) -> None:
     """out[c] (+)= alpha * sum over all pixels of x[..., c]   (fp32 out, one entry per channel of the slice)"""
     assert out.dtype == torch.float32 and out.is_contiguous() and out.numel() == x.c
@@ -342,6 +347,33 @@ def bn_backward(dy_post: Slice, y: Slice, x: Slice, dx: Slice, gamma, save_mean,
         gamma.data_ptr(), save_mean.data_ptr(), save_invstd.data_ptr(), float(slope), int(training),
         dgamma.data_ptr() if dgamma is not None else None, dbeta.data_ptr() if dbeta is not None else None,
         int(accumulate), ws.data_ptr(), ws.numel(), _stream()), "bn_backward")
+
+
+def gn_forward(x: Slice, y: Slice, gamma, beta, groups: int, eps: float = 1e-5, residual: Optional[Slice] = None,
+               act: Optional[float] = None):
+    n, hw, c = x.n, x.h * x.w, x.c
+    mean = torch.empty(n * groups, dtype=torch.float32, device=x.buf.device)
+    rstd = torch.empty(n * groups, dtype=torch.float32, device=x.buf.device)
+    lib = _lib.load()
+    ws = workspace(lib.srcgan_gn_workspace_bytes(n, c), x.buf.device)
+    _lib.check(lib.srcgan_gn_forward(x.ptr, x.ld, y.ptr, y.ld, n, hw, c, groups, dt_code(x.dtype), gamma.data_ptr(),
+                                     beta.data_ptr(), mean.data_ptr(), rstd.data_ptr(), float(eps),
+                                     residual.ptr if residual is not None else None,
+                                     residual.ld if residual is not None else 0, int(act is not None),
+                                     float(act or 0.0), ws.data_ptr(), ws.numel(), _stream()), "gn_forward")
+    return mean, rstd
+
+
+def gn_backward(dy: Slice, x: Slice, dx: Slice, gamma, mean, rstd, groups: int, dgamma, dbeta,
+                accumulate: bool = False) -> None:
+    n, hw, c = x.n, x.h * x.w, x.c
+    lib = _lib.load()
+    ws = workspace(lib.srcgan_gn_workspace_bytes(n, c), x.buf.device)
+    _lib.check(lib.srcgan_gn_backward(dy.ptr, dy.ld, x.ptr, x.ld, dx.ptr, dx.ld, n, hw, c, groups, dt_code(x.dtype),
+                                      gamma.data_ptr(), mean.data_ptr(), rstd.data_ptr(),
+                                      dgamma.data_ptr() if dgamma is not None else None,
+                                      dbeta.data_ptr() if dbeta is not None else None, int(accumulate), ws.data_ptr(),
+                                      ws.numel(), _stream()), "gn_backward")
 
 
 # ------------------------------------------------------------------------------------------

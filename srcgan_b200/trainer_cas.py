@@ -18,8 +18,10 @@ import torch.nn.functional as F
 
 from . import losses
 from . import nn as snn
+from . import zoo
 
-MODELS = {"RDDBNet": snn.RDDBNet, "SRDN": snn.SRDN, "ESPCN": snn.ESPCN, "SRCNN": snn.SRCNN}
+MODELS = {"RDDBNet": snn.RDDBNet, "SRDN": snn.SRDN, "ESPCN": snn.ESPCN, "SRCNN": snn.SRCNN,
+          "EDSR": zoo.EDSR, "ResDeconv": zoo.ResDeconv}
 
 
 def build_model(name: str, *args):
@@ -41,7 +43,7 @@ class params(object):
         self.matrix = 0
         self.lr_policy = "cosine"
         self.SRModel = "ESPCN"
-        self.CModel = "SRCNN"          # the reference defaults to ResDeconv, which is not built here
+        self.CModel = "ResDeconv"
         self.up = 2
         self.variant = ""              # "", "Const", "LAB", "ConstLAB"
 

@@ -50,3 +50,9 @@ def golden_cascade():
 def golden_cas_step():
     import torch
     return torch.load(os.path.join(GOLDEN, "cas_step_tiny.pt"), weights_only=False)
+
+
+@pytest.fixture(scope="session")
+def golden_zoo():
+    import torch
+    return torch.load(os.path.join(GOLDEN, "zoo_tiny.pt"), weights_only=False)

@@ -390,3 +390,36 @@ def test_conv_tc_thin_sides(case):
     wtp = ops.pack_weights(wt.detach().transpose(0, 1).flip(2, 3).contiguous().to(DEV), ops.WL_TC, torch.bfloat16)
     ops.conv_fprop(gys, wtp, None, dxs, 3, 1, 1, engine=ops.ENGINE_TC)
     assert relerr(from_nhwc(dxs), xr.grad) < 1e-2
+
+
+@pytest.mark.parametrize("dtype,tol", [(torch.float32, 2e-5), (torch.bfloat16, 3e-2)])
+@pytest.mark.parametrize("shape", [(2, 64, 9, 7), (3, 128, 16, 16), (1, 512, 4, 4)])
+def test_groupnorm_fwd_bwd(shape, dtype, tol):
+    """srcgan_gn_forward / backward (GroupNorm(32, C) with the fused residual + LeakyReLU tail) vs torch on CPU."""
+    from srcgan_b200 import ops
+    n, c, h, w = shape
+    x = rand(shape, 1, 2.0) + 0.3
+    res = rand(shape, 2)
+    gy = rand(shape, 3)
+    gamma = (1.0 + 0.2 * rand((c,), 4)).requires_grad_(True)
+    beta = (0.2 * rand((c,), 5)).requires_grad_(True)
+    if dtype == torch.bfloat16:
+        x, res, gy = x.bfloat16().float(), res.bfloat16().float(), gy.bfloat16().float()
+    xr = x.clone().requires_grad_(True)
+    rr = res.clone().requires_grad_(True)
+    y_ref = F.leaky_relu(F.group_norm(xr, 32, gamma, beta, 1e-5) + rr, 0.2)
+    y_ref.backward(gy)
+    xs, rs, gs = to_nhwc(x, dtype), to_nhwc(res, dtype), to_nhwc(gy, dtype)
+    ys = ops.Slice(torch.empty_like(xs.buf))
+    g_dev, b_dev = gamma.detach().to(DEV), beta.detach().to(DEV)
+    mean, rstd = ops.gn_forward(xs, ys, g_dev, b_dev, 32, 1e-5, residual=rs, act=0.2)
+    assert relerr(from_nhwc(ys), y_ref.detach()) < tol
+    gz = ops.Slice(torch.empty_like(xs.buf))
+    ops.act_backward(gs, ys, gz, 0.2)
+    assert relerr(from_nhwc(gz), rr.grad) < tol
+    dx = ops.Slice(torch.empty_like(xs.buf))
+    dgamma = torch.empty(c, dtype=torch.float32, device=DEV)
+    dbeta = torch.empty(c, dtype=torch.float32, device=DEV)
+    ops.gn_backward(gz, xs, dx, g_dev, mean, rstd, 32, dgamma, dbeta)
+    assert relerr(from_nhwc(dx), xr.grad) < 2 * tol
+    assert relerr(dgamma.cpu(), gamma.grad) < tol and relerr(dbeta.cpu(), beta.grad) < tol

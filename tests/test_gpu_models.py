@@ -320,6 +320,41 @@ def test_plain_conv_stacks_parity(golden_cascade, which):
     assert relerr(yb, r64.y) < 0.1
 
 
+def zoo_net(which):
+    from srcgan_b200 import zoo
+    return {"ResDeconv": lambda: zoo.ResDeconv(1, 3), "EDSR_x2": lambda: zoo.EDSR(1, 1, 2, num_residuals=3),
+            "EDSR_x4_rgb": lambda: zoo.EDSR(3, 3, 4, num_residuals=2),
+            "SRDenseNetA_x2": lambda: zoo.SRDenseNetA(1, 3, mode="x2", num_blocks=2, num_layers=2),
+            "SRDenseNetA_x4": lambda: zoo.SRDenseNetA(1, 3, mode="x4", num_blocks=2, num_layers=2),
+            "SRDenseNetB_x2": lambda: zoo.SRDenseNetB(3, 1, mode="x2", num_blocks=2, num_layers=2),
+            "SRDenseNetB_x4": lambda: zoo.SRDenseNetB(3, 1, mode="x4", num_blocks=2, num_layers=2)}[which]()
+
+
+@pytest.mark.parametrize("which", ["ResDeconv", "EDSR_x2", "EDSR_x4_rgb", "SRDenseNetA_x2", "SRDenseNetA_x4",
+                                   "SRDenseNetB_x2", "SRDenseNetB_x4"])
+def test_zoo_generators_parity(golden_zoo, which):
+    """ResDeconv (GroupNorm ResNet-18 + k2 s2 deconvs), EDSR (shared-GN residual blocks), SRDenseNetA/B (shared
+    k3 s2 transposed / strided resampler) on the CUDA path: fp32 mode vs oracle + the real reference's outputs."""
+    from srcgan_b200 import nn as snn
+    from tests.test_oracle import zoo_case
+    fx = golden_zoo[which]
+    sd, fn, x, seed = zoo_case(which)
+    net = zoo_net(which)
+    y, named, dx, r32, r64 = run_both(net, fn, sd, x, seed)
+    assert relerr(y, r64.y) < 1e-4 and relerr(y, fx["out"]) < 1e-4
+    check_grads(named, r32, r64)
+    assert l2err(dx, r64.dx) < grad_tol(r32.dx, r64.dx)
+    snn.set_precision("bf16")
+    with torch.no_grad():
+        yb = net(x.to(DEV))
+    assert relerr(yb, r64.y) < 0.1
+    # bf16 training step runs through the tensor-core paths (wide layers) without refusing a shape
+    net.zero_grad()
+    xb = x.to(DEV).requires_grad_(True)
+    net(xb).sum().backward()
+    assert all(p.grad is not None and torch.isfinite(p.grad).all() for p in net.parameters())
+
+
 @pytest.mark.parametrize("variant", ["", "ConstLAB"])
 def test_cascade_step_against_golden(golden_cas_step, variant):
     """trainer_cas.CasSRC (mirror of trainCas*.py) on the CUDA path vs the real reference's iterations."""
@@ -340,4 +375,4 @@ def test_cascade_step_against_golden(golden_cas_step, variant):
             assert math.isclose(got[g], rec[k], rel_tol=TOL, abs_tol=1e-5), (variant, it, k, got[g], rec[k])
         assert relerr(m.fake_AB, rec["fake_AB"]) < TOL
     with pytest.raises(NotImplementedError):
-        trainer_cas.build_model("ResDeconv", 1, 3)
+        trainer_cas.build_model("NoSuchNet", 1, 3)

@@ -221,6 +221,30 @@ def test_cascade_generators_golden(golden_cascade, which):
     assert relerr(x.grad, fx["dx"]) < 1e-4
 
 
+ZOO = ["ResDeconv", "EDSR_x2", "EDSR_x4_rgb", "SRDenseNetA_x2", "SRDenseNetA_x4", "SRDenseNetB_x2", "SRDenseNetB_x4"]
+
+
+def zoo_case(which):
+    """-> (state_dict, oracle fn, input, probe seed): same table the fixture generator uses"""
+    from oracle.make_golden import zoo_cases
+    _ctor, sd, fn, x, seed = zoo_cases()[which]
+    return sd, fn, x, seed
+
+
+@pytest.mark.parametrize("which", ZOO)
+def test_zoo_generators_golden(golden_zoo, which):
+    """ResDeconv / EDSR / SRDenseNetA,B: oracle vs outputs and gradients of the real reference."""
+    fx = golden_zoo[which]
+    sd0, fn, x, seed = zoo_case(which)
+    sd = O.as_leaf_params(sd0)
+    x = x.clone().requires_grad_(True)
+    y = fn(sd, x)
+    assert y.shape == fx["out"].shape and relerr(y.detach(), fx["out"]) < TOL
+    (y * probe_like(y, seed)).sum().backward()
+    check_grad_norms(sd, fx["grad_norms"])
+    assert relerr(x.grad, fx["dx"]) < 1e-4
+
+
 def cas_oracle(variant):
     lab, const = "LAB" in variant, "Const" in variant
     sr_state = O.init_srcnn(51, 1, 1) if const else O.init_espcn(51, 1, 1, 2)
