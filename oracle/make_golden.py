@@ -6,6 +6,7 @@ Fixtures hold only outputs (inputs and weights are regenerated from seeds throug
   modules_tiny.pt   per-module outputs, per-parameter gradient norms, BN buffers,
                     loss / metric known answers
   zoo_tiny.pt       ResDeconv / EDSR / SRDenseNetA,B outputs, gradient norms, input gradients
+  step_gray_tiny.pt the same two iterations for opt.net = '2' (gray LR, RDDB pair) and 'SRdens' (SRDenseNet pair)
   step_tiny.pt      two consecutive ``train.SRCycleGAN.optimize_parameters`` calls
                     (x4, net '1', B=2, 16x16 -> 64x64): the 9 losses per step, parameter
                     norms after the Adam updates, BN buffers
@@ -171,15 +172,15 @@ def zoo_fixture() -> dict:
     return fx
 
 
-def step_fixture() -> dict:
+def step_fixture(net: str = "1") -> dict:
     train = ref_harness.import_train()
     opt = train.params()
     opt.device = torch.device("cpu")
     opt.mode = "x4"
-    opt.net = "1"
+    opt.net = net
     torch.manual_seed(0)
     model = train.SRCycleGAN(opt)
-    st = O.default_states(0)
+    st = O.default_states(0, net)
     model.netG_A.load_state_dict(st["G_A"], strict=True)
     model.netG_B.load_state_dict(st["G_B"], strict=True)
     model.netD_A.load_state_dict(st["D_A"], strict=True)
@@ -187,7 +188,7 @@ def step_fixture() -> dict:
     random.seed(5)
     steps = []
     for it in range(2):
-        real_A, real_B = O.synthetic_batch(2, lr=16, scale=4, seed=1234 + it)
+        real_A, real_B = (O.synthetic_batch if net == "1" else O.synthetic_gray_batch)(2, lr=16, scale=4, seed=1234 + it)
         model.optimize_parameters(real_A, real_B)
         rec = {"losses": {n: float(getattr(model, "loss_" + n)) for n in O.CycleGANStepOracle.LOSS_NAMES}}
         if it == 0:
@@ -235,6 +236,7 @@ def main() -> None:
     torch.set_num_threads(os.cpu_count() or 1)
     torch.save(modules_fixture(), os.path.join(OUT, "modules_tiny.pt"))
     torch.save(step_fixture(), os.path.join(OUT, "step_tiny.pt"))
+    torch.save({net: step_fixture(net) for net in ("2", "SRdens")}, os.path.join(OUT, "step_gray_tiny.pt"))
     torch.save(cascade_fixture(), os.path.join(OUT, "cascade_tiny.pt"))
     torch.save(cas_step_fixture(), os.path.join(OUT, "cas_step_tiny.pt"))
     torch.save(zoo_fixture(), os.path.join(OUT, "zoo_tiny.pt"))

@@ -42,3 +42,23 @@ def evaluate(generator: Callable[[torch.Tensor], torch.Tensor],
     per_item = [dict(zip(names, map(float, r))) for r in table]
     mean = dict(zip(names, map(float, table.mean(0))))
     return per_item, mean
+
+
+@torch.no_grad()
+def evaluate_cascade(net_a2c, net_c2b, pairs: Iterable[Tuple[torch.Tensor, torch.Tensor]], up: int,
+                     const: bool = False):
+    """The testCas.py:65-85 loop for a checkpoint pair: for each (realA gray, realB RGB) tile, the luma of realB
+    is resized by 1/up (nearest, the ``interpolate`` default; the Const variants go down and back up bilinearly,
+    testCasConst.py:75-76) and sent through SR -> colouriser; ``fake_BB`` is scored against realB.  Returns ``evaluate``'s result."""
+    import torch.nn.functional as F
+
+    def gen(real_b):
+        luma = 0.2125 * real_b[:, :1] + 0.7154 * real_b[:, 1:2] + 0.0721 * real_b[:, 2:3]
+        if const:
+            lr = F.interpolate(F.interpolate(luma, scale_factor=1.0 / up, mode="bilinear"), scale_factor=up,
+                               mode="bilinear")
+        else:
+            lr = F.interpolate(luma, scale_factor=1.0 / up)
+        return net_c2b(net_a2c(lr))
+
+    return evaluate(gen, ((b, b) for _a, b in pairs))

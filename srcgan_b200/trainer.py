@@ -5,8 +5,8 @@ runs unchanged on the drop-in modules (``srcgan_b200/dropin`` on PYTHONPATH); th
 because the reference tree is not available on the GPU box and because it routes the adversarial
 loss through the fused loss kernel as well.
 
-Only ``opt.net == '1'`` (RGB <-> RGB) and ``'2'`` (gray <-> RGB) with the RDDB generators are built;
-``'SRdens'`` raises.
+``opt.net == '1'`` (RGB <-> RGB, the benchmarked hot path) and ``'2'`` (gray <-> RGB) use the RDDB generators;
+``'SRdens'`` the SRDenseNetA/B pair of train.py:166-170.
 """
 from __future__ import annotations
 
@@ -19,6 +19,7 @@ import torch.nn.functional as F
 
 from . import losses
 from .nn import NLayerDiscriminator, RDDBNetA, RDDBNetB
+from .zoo import SRDenseNetA, SRDenseNetB
 
 
 class ImagePool:
@@ -96,11 +97,13 @@ class SRCycleGAN(object):
     def __init__(self, opt):
         self.opt = opt
         dev = opt.device
-        if opt.net == "SRdens":
-            raise NotImplementedError("srcgan_b200: the SRDenseNet generator pair is not built")
         gray = opt.net != "1"
-        self.netG_A = RDDBNetB(1 if gray else 3, 3, 64, nb=3, mode=opt.mode).to(dev)
-        self.netG_B = RDDBNetA(3, 1 if gray else 3, 64, nb=3, mode=opt.mode).to(dev)
+        if opt.net == "SRdens":
+            self.netG_A = SRDenseNetA(1, 3, mode=opt.mode, num_blocks=2, num_layers=2).to(dev)
+            self.netG_B = SRDenseNetB(3, 1, mode=opt.mode, num_blocks=2, num_layers=2).to(dev)
+        else:
+            self.netG_A = RDDBNetB(1 if gray else 3, 3, 64, nb=3, mode=opt.mode).to(dev)
+            self.netG_B = RDDBNetA(3, 1 if gray else 3, 64, nb=3, mode=opt.mode).to(dev)
         self.netD_A = NLayerDiscriminator(3, 64, 2).to(dev)
         self.netD_B = NLayerDiscriminator(1 if gray else 3, 64, 2).to(dev)
         self.fake_A_pool = ImagePool(opt.pool_size)

@@ -56,3 +56,9 @@ def golden_cas_step():
 def golden_zoo():
     import torch
     return torch.load(os.path.join(GOLDEN, "zoo_tiny.pt"), weights_only=False)
+
+
+@pytest.fixture(scope="session")
+def golden_step_gray():
+    import torch
+    return torch.load(os.path.join(GOLDEN, "step_gray_tiny.pt"), weights_only=False)

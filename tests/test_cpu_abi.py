@@ -165,3 +165,89 @@ def test_reference_train_script_constructs_on_the_dropin():
         "print('ok')" % os.path.join(ROOT, "srcgan_b200", "dropin"))
     out = subprocess.run([sys.executable, "-W", "ignore", "-c", code], capture_output=True, text=True, cwd="/tmp")
     assert out.returncode == 0 and "ok" in out.stdout, out.stderr[-3000:]
+
+
+def test_checkpoint_names_follow_the_reference_scripts():
+    from srcgan_b200 import checkpoint as C
+    assert C.cas_checkpoint_name("RDDBNet", "A2C", 4, 7) == "RDDBNet_A2C_x4_0007.pth"            # trainCas.py:222
+    assert C.cas_checkpoint_name("ResDeconv", "C2B", 2, 50, lab=True) == "ResDeconv@G2LAB_C2B_x2_0050.pth"
+    n = C.parse_cas_checkpoint_name("./checkpoints/ResDeconv@G2LAB_C2B_x2_0050.pth")
+    assert n == C.CasName("ResDeconv", True, "C2B", 2, 50)
+    # the reference's own parse (testCas.py:40-41,52) agrees
+    parts = "RDDBNet_A2C_x4_0007.pth".split(".pth")[0].split("_")
+    assert (parts[0], int(parts[2][1])) == ("RDDBNet", C.parse_cas_checkpoint_name("RDDBNet_A2C_x4_0007.pth").up)
+    assert C.cyclegan_checkpoint_names("x4", 3) == ("netG_A2B_SRtask_x4_0003.pth", "netG_B2A_SRtask_x4_0003.pth")
+    with pytest.raises(ValueError):
+        C.parse_cas_checkpoint_name("netG_A2B_SRtask_x4_0003.pth")
+
+
+def _zoo_pairs():
+    from oracle import srcgan_oracle as O
+    from srcgan_b200 import nn as snn, zoo
+    return {
+        "ResDeconv": (lambda: zoo.ResDeconv(1, 3), O.init_resdeconv(1, 3), 14982912),
+        "EDSR": (lambda: zoo.EDSR(1, 1, 2, num_residuals=3), O.init_edsr(2, 1, 1, 2, num_residuals=3), None),
+        "SRDenseNetA": (lambda: zoo.SRDenseNetA(1, 3, mode="x4", num_blocks=2, num_layers=2),
+                        O.init_srdensenet(3, "A", 1, 3), None),
+        "SRDenseNetB": (lambda: zoo.SRDenseNetB(3, 1, mode="x4", num_blocks=2, num_layers=2),
+                        O.init_srdensenet(4, "B", 3, 1), None),
+        "RDDBNet": (lambda: snn.RDDBNet(1, 1, 4), O.init_rddbnet_pkg(5, 1, 1, 4), 2229184),
+        "SRDN": (lambda: snn.SRDN(1, 1, 2), O.init_srdn(6), None),
+        "ESPCN": (lambda: snn.ESPCN(1, 1, 2), O.init_espcn(7, 1, 1, 2), None),
+        "SRCNN": (lambda: snn.SRCNN(1, 3, 2), O.init_srcnn(8, 1, 3), None),
+    }
+
+
+@pytest.mark.parametrize("name", ["ResDeconv", "EDSR", "SRDenseNetA", "SRDenseNetB", "RDDBNet", "SRDN", "ESPCN", "SRCNN"])
+def test_checkpoint_round_trip(tmp_path, name):
+    """.pth files written here hold reference-keyed CPU tensors and load back strictly; where the reference tree
+    is present, the REAL reference module loads the same file with strict=True (interchange both ways)."""
+    import torch
+    from srcgan_b200 import checkpoint as C
+    ctor, sd, nparams = _zoo_pairs()[name]
+    net = ctor()
+    assert list(net.state_dict().keys()) == list(sd.keys())
+    net.load_state_dict(sd, strict=True)
+    if nparams is not None:
+        assert sum(p.numel() for p in net.parameters()) == nparams
+    path = str(tmp_path / "checkpoints" / C.cas_checkpoint_name(name, "A2C", 2, 1))
+    C.save_state(net, path)
+    back = torch.load(path)
+    assert all(torch.equal(back[k], sd[k]) for k in sd) and list(back) == list(sd)
+    other = ctor()
+    C.load_state(other, path)
+    assert all(torch.equal(a, b) for a, b in zip(other.state_dict().values(), sd.values()))
+    if os.path.isdir("/root/reference/src"):
+        from oracle import ref_harness
+        pkg, M, _l, _m = ref_harness.import_reference()
+        ref = {"ResDeconv": lambda: pkg.ResDeconv(1, 3), "EDSR": lambda: pkg.EDSR(1, 1, 2, num_residuals=3),
+               "SRDenseNetA": lambda: M.SRDenseNetA(1, 3, mode="x4", num_blocks=2, num_layers=2),
+               "SRDenseNetB": lambda: M.SRDenseNetB(3, 1, mode="x4", num_blocks=2, num_layers=2),
+               "RDDBNet": lambda: pkg.RDDBNet(1, 1, 4), "SRDN": lambda: pkg.SRDN(1, 1, 2),
+               "ESPCN": lambda: pkg.ESPCN(1, 1, 2), "SRCNN": lambda: pkg.SRCNN(1, 3, 2)}[name]()
+        ref.load_state_dict(torch.load(path), strict=True)
+        assert list(ref.state_dict().keys()) == list(net.state_dict().keys())
+
+
+@pytest.mark.skipif(not os.path.isdir("/root/reference/src"), reason="reference tree not on this box")
+def test_reference_traincas_script_constructs_on_the_dropin():
+    """The reference's UNMODIFIED trainCas.py (`from model import *`, eval(opt.SRModel), default CModel ResDeconv)
+    builds CasSRC on the drop-in package for every generator name of src/model/__init__.py."""
+    code = (
+        "import sys, types, torch;"
+        "sys.path.insert(0, '/root/reference/src'); sys.path.insert(0, %r);"
+        "sys.modules['visdom'] = types.SimpleNamespace(Visdom=lambda *a, **k: None);"
+        "sk = types.ModuleType('skimage'); sk.io = types.ModuleType('skimage.io'); sk.color = types.ModuleType('skimage.color');"
+        "sk.color.lab2rgb = sk.color.rgb2lab = sk.color.rgb2gray = None; sk.io.imsave = sk.io.imread = None;"
+        "sys.modules.update({'skimage': sk, 'skimage.io': sk.io, 'skimage.color': sk.color});"
+        "import trainCas;"
+        "opt = trainCas.params(); opt.device = torch.device('cpu'); opt.up = 2;"
+        "seen = set();\n"
+        "for sr in ('ESPCN', 'SRCNN', 'EDSR', 'RDDBNet', 'SRDN'):\n"
+        "    opt.SRModel, opt.CModel = sr, 'ResDeconv'\n"
+        "    m = trainCas.CasSRC(opt)\n"
+        "    seen.add(type(m.netG_A2C).__module__); seen.add(type(m.netG_C2B).__module__)\n"
+        "assert seen == {'srcgan_b200.nn', 'srcgan_b200.zoo'}, seen\n"
+        "print('ok')" % os.path.join(ROOT, "srcgan_b200", "dropin"))
+    out = subprocess.run([sys.executable, "-W", "ignore", "-c", code], capture_output=True, text=True, cwd="/tmp")
+    assert out.returncode == 0 and "ok" in out.stdout, out.stderr[-3000:]

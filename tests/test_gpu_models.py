@@ -175,12 +175,12 @@ def test_state_dict_keys_and_loading():
     assert list(snn.NLayerDiscriminator(3, 64, 2).state_dict().keys()) == list(O.init_discriminator(0).keys())
 
 
-def make_trainer(states, mode="x4"):
+def make_trainer(states, mode="x4", net="1"):
     from srcgan_b200 import trainer
     opt = trainer.params()
     opt.device = torch.device(DEV)
     opt.mode = mode
-    opt.net = "1"
+    opt.net = net
     m = trainer.SRCycleGAN(opt)
     for name in ("G_A", "G_B", "D_A", "D_B"):
         getattr(m, "net" + name).load_state_dict(states[name], strict=True)
@@ -233,6 +233,29 @@ def test_full_step_against_golden_and_oracle(golden_step):
         assert bad_gpu <= 2 * bad_cpu + 1e-3 * total, (name, bad_gpu, bad_cpu, total)
 
 
+@pytest.mark.parametrize("net", ["2", "SRdens"])
+def test_full_step_gray_against_golden(golden_step_gray, net):
+    """opt.net = '2' (gray LR through the RDDB pair) and 'SRdens' (SRDenseNetA/B pair, train.py:166-170): two
+    optimize_parameters calls vs the real reference's."""
+    from oracle import srcgan_oracle as O
+    fx = golden_step_gray[net]
+    random.seed(5)
+    m = make_trainer(O.default_states(0, net), net=net)
+    for it, rec in enumerate(fx["steps"]):
+        real_A, real_B = O.synthetic_gray_batch(2, lr=16, scale=4, seed=1234 + it)
+        m.optimize_parameters(real_A.to(DEV), real_B.to(DEV))
+        got = m.current_losses()
+        for n, v in rec["losses"].items():
+            assert math.isclose(got[n], v, rel_tol=TOL, abs_tol=1e-5), (net, it, n, got[n], v)
+        if "fake_B" in rec:
+            assert relerr(m.fake_B.detach(), rec["fake_B"]) < TOL
+            assert relerr(m.fake_A.detach(), rec["fake_A"]) < TOL
+    for name, norms in fx["param_norms"].items():
+        lr = 1e-4 if name.startswith("G") else 1e-5
+        for k, p in getattr(m, "net" + name).named_parameters():
+            assert math.isclose(float(p.detach().double().norm()), norms[k], rel_tol=TOL, abs_tol=8 * lr), (name, k)
+
+
 def test_bf16_mode_psnr_matches_fp32():
     """north_star: bf16 mode must match the SR image's PSNR within 0.05 dB."""
     from oracle import srcgan_oracle as O
@@ -272,6 +295,38 @@ def test_eval_sweep_512_tiles():
         assert math.isclose(row["MSE"], float(O.mse_loss(out, h)), rel_tol=2e-2)
         assert math.isclose(row["SSIM"], float(O.ssim(out, h)), rel_tol=5e-2, abs_tol=5e-3)
         assert math.isclose(row["AE"], float(O.angular_error(out, h).mean()), rel_tol=2e-2)
+
+
+@pytest.mark.parametrize("const", [False, True])
+def test_cascade_eval_from_checkpoint_files(tmp_path, const):
+    """testCas.py / testCasConst.py flow: networks rebuilt from checkpoint file NAMES, weights from the files,
+    luma -> 1/up -> SR -> colouriser, four metrics per tile; against the CPU oracle on the same weights."""
+    import torch.nn.functional as F
+    from oracle import srcgan_oracle as O
+    from srcgan_b200 import checkpoint as C, evaluate, nn as snn
+    sr_name = "SRCNN" if const else "ESPCN"
+    sd_a = O.init_srcnn(61, 1, 1) if const else O.init_espcn(61, 1, 1, 2)
+    sd_b = O.init_resdeconv(62, 3)
+    pa = str(tmp_path / C.cas_checkpoint_name(sr_name, "A2C", 2, 3))
+    pb = str(tmp_path / C.cas_checkpoint_name("ResDeconv", "C2B", 2, 3))
+    torch.save(sd_a, pa)                      # as the reference's trainCas.py:224-225 would have written them
+    torch.save(sd_b, pb)
+    net_a, net_b, na, nb = C.load_cascade_pair(pa, pb, DEV)
+    assert (na.model, na.up, nb.model, nb.lab) == (sr_name, 2, "ResDeconv", False) and not net_a.training
+    tiles = [(rand((1, 1, 64, 64), 800 + i), rand((1, 3, 64, 64), 810 + i)) for i in range(2)]
+    rows, mean = evaluate.evaluate_cascade(net_a, net_b, [(a.to(DEV), b.to(DEV)) for a, b in tiles], 2, const=const)
+    for (_a, b), row in zip(tiles, rows):
+        luma = 0.2125 * b[:, :1] + 0.7154 * b[:, 1:2] + 0.0721 * b[:, 2:3]
+        if const:
+            lr = F.interpolate(F.interpolate(luma, scale_factor=0.5, mode="bilinear"), scale_factor=2, mode="bilinear")
+            sr = O.srcnn(sd_a, lr)
+        else:
+            sr = O.espcn(sd_a, F.interpolate(luma, scale_factor=0.5), 2)
+        out = O.resdeconv(sd_b, sr)
+        assert math.isclose(row["MSE"], float(O.mse_loss(out, b)), rel_tol=TOL)
+        assert abs(row["PSNR"] - float(O.psnr(out, b))) < 1e-2
+        assert math.isclose(row["SSIM"], float(O.ssim(out, b)), rel_tol=5e-3, abs_tol=1e-4)
+        assert math.isclose(row["AE"], float(O.angular_error(out, b).mean()), rel_tol=TOL)
 
 
 @pytest.mark.parametrize("which", ["RDDBNet_x2", "RDDBNet_x4", "SRDN"])

@@ -122,6 +122,26 @@ def test_step_golden(golden_step):
             assert torch.allclose(sd[k].to(v.dtype), v, rtol=1e-4, atol=1e-6), (name, k)
 
 
+@pytest.mark.parametrize("net", ["2", "SRdens"])
+def test_step_golden_gray(golden_step_gray, net):
+    """opt.net = '2' (gray LR, RDDB pair) and 'SRdens' (SRDenseNetA/B pair): two oracle steps vs the real train.py."""
+    fx = golden_step_gray[net]
+    random.seed(5)
+    step = O.CycleGANStepOracle(O.default_states(0, net), O.StepOptions(net=net))
+    for it, rec in enumerate(fx["steps"]):
+        real_A, real_B = O.synthetic_gray_batch(2, lr=16, scale=4, seed=1234 + it)
+        got = step.optimize_parameters(real_A, real_B)
+        for n, v in rec["losses"].items():
+            assert math.isclose(got[n], v, rel_tol=2e-4, abs_tol=1e-6), (net, it, n, got[n], v)
+        if "fake_B" in rec:
+            assert relerr(step.fake_B.detach(), rec["fake_B"]) < 1e-4
+            assert relerr(step.fake_A.detach(), rec["fake_A"]) < 1e-4
+    for name, norms in fx["param_norms"].items():
+        sd = getattr(step, name)
+        for k, n in norms.items():
+            assert math.isclose(float(sd[k].detach().double().norm()), n, rel_tol=1e-5), (name, k)
+
+
 def test_state_dict_keys_match_reference_layout():
     ga = O.init_rddbnet_b(0)
     assert len(ga) == 102 and sum(v.numel() for v in ga.values()) == 2309507
