@@ -20,6 +20,7 @@
 // Reference semantics replaced: nn.Conv2d 3x3 of the dense blocks / HRconv / trunk / Decoder
 // (src/model/model.py:193-211, :236-289, :396-440) and their dgrad (as an fprop over transposed weights).
 #include <cuda.h>
+#include <stdio.h>
 
 #include <mutex>
 #include <stdlib.h>
@@ -55,13 +56,14 @@ struct TcArgs {
   int nchunks, n_blocks;                // K chunks of 64 channels; N blocks of BN channels
   int tiles_x, tiles_y;
   long long num_tiles;
-  const __nv_bfloat16* wgt;             // packed [n_block][chunk][kw][kh][BN][64] (pre-swizzled)
+  const __nv_bfloat16* wgt;             // packed [n_block][chunk][slot][BN][64] (pre-swizzled); 3x3 s1 cout<=64: slot = kh*3+(2-kw)
   const float* bias;
   __nv_bfloat16* y; int y_ld;
   int act; float act_slope, alpha;
   const __nv_bfloat16* r1; int r1_ld; float beta1;
   const __nv_bfloat16* r2; int r2_ld; float beta2;
   const __nv_bfloat16* mask; int mask_ld; float mask_slope;
+  int dbg;                              // experiment switches (SRCGAN_B200_DBG), 0 in production
 };
 
 __device__ __forceinline__ uint32_t smem_u32(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
@@ -185,6 +187,27 @@ __device__ __forceinline__ void tmem_ld32(uint32_t taddr, uint32_t (&v)[32]) {
       : "r"(taddr));
   asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
 }
+
+__device__ __forceinline__ void tmem_ld32_nowait(uint32_t taddr, uint32_t (&v)[32]) {
+  asm volatile(
+      "tcgen05.ld.sync.aligned.32x32b.x32.b32 "
+      "{%0, %1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15, "
+      "%16, %17, %18, %19, %20, %21, %22, %23, %24, %25, %26, %27, %28, %29, %30, %31}, [%32];"
+      : "=r"(v[0]), "=r"(v[1]), "=r"(v[2]), "=r"(v[3]), "=r"(v[4]), "=r"(v[5]), "=r"(v[6]), "=r"(v[7]), "=r"(v[8]),
+        "=r"(v[9]), "=r"(v[10]), "=r"(v[11]), "=r"(v[12]), "=r"(v[13]), "=r"(v[14]), "=r"(v[15]), "=r"(v[16]),
+        "=r"(v[17]), "=r"(v[18]), "=r"(v[19]), "=r"(v[20]), "=r"(v[21]), "=r"(v[22]), "=r"(v[23]), "=r"(v[24]),
+        "=r"(v[25]), "=r"(v[26]), "=r"(v[27]), "=r"(v[28]), "=r"(v[29]), "=r"(v[30]), "=r"(v[31])
+      : "r"(taddr));
+}
+__device__ __forceinline__ float4 lds_f4(uint32_t saddr) {
+  float4 v;
+  asm volatile("ld.shared.v4.f32 {%0, %1, %2, %3}, [%4];" : "=f"(v.x), "=f"(v.y), "=f"(v.z), "=f"(v.w) : "r"(saddr));
+  return v;
+}
+__device__ __forceinline__ void sts_u4(uint32_t saddr, const uint4& v) {
+  asm volatile("st.shared.v4.b32 [%0], {%1, %2, %3, %4};" ::"r"(saddr), "r"(v.x), "r"(v.y), "r"(v.z), "r"(v.w) : "memory");
+}
+__device__ __forceinline__ void tmem_ld_wait() { asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory"); }
 
 __device__ __forceinline__ void unpack8(const uint4& q, float (&f)[8]) {
   const __nv_bfloat162* h = reinterpret_cast<const __nv_bfloat162*>(&q);
@@ -537,8 +560,12 @@ conv3x3_halo_tc(const __grid_constant__ CUtensorMap tmap_x, const TcArgs a) {
           const int x0 = (bxg * MT + m) * TILE_W;
           mbar_wait(&a_empty[as], aph ^ 1);
           if (elect_one()) {
-            mbar_expect_tx(&a_full[as], C::A_BOX_BYTES);
-            tma_load_4d(&tmap_x, &a_full[as], smem_a + as * C::A_STRIDE, c * KCH, x0 - pad, y0 - pad, img);
+            if (a.dbg & 4) {
+              mbar_arrive(&a_full[as]);
+            } else {
+              mbar_expect_tx(&a_full[as], C::A_BOX_BYTES);
+              tma_load_4d(&tmap_x, &a_full[as], smem_a + as * C::A_STRIDE, c * KCH, x0 - pad, y0 - pad, img);
+            }
           }
           __syncwarp();
           if (++as == C::NA) { as = 0; aph ^= 1; }
@@ -581,7 +608,8 @@ conv3x3_halo_tc(const __grid_constant__ CUtensorMap tmap_x, const TcArgs a) {
             const uint32_t a_lo0 = desc_lo(sa0), a_lo1 = desc_lo(sa1), b_lo = desc_lo(sb);
             constexpr uint32_t a_hi = desc_hi(HALO_W * 128), b_hi = desc_hi(1024);
             uint32_t accumulate = c > 0 ? 1u : 0u;
-            if (ksteps == 4 && cnt == 2) {
+            if (a.dbg & 2) {
+            } else if (ksteps == 4 && cnt == 2) {
 #pragma unroll
               for (int fw = 0; fw < 3; ++fw)
 #pragma unroll
@@ -589,7 +617,7 @@ conv3x3_halo_tc(const __grid_constant__ CUtensorMap tmap_x, const TcArgs a) {
 #pragma unroll
                   for (int ks = 0; ks < 4; ++ks) {
                     const uint32_t ao = (uint32_t)((fh * HALO_W + fw) * 8 + ks * 2);
-                    const uint32_t bo = (uint32_t)(((fw * 3 + fh) * C::B_TAP_BYTES >> 4) + ks * 2);
+                    const uint32_t bo = (uint32_t)(((fh * 3 + 2 - fw) * C::B_TAP_BYTES >> 4) + ks * 2);
                     umma_bf16_w(tmem_d0, a_lo0 + ao, a_hi, b_lo + bo, b_hi, idesc, accumulate);
                     umma_bf16_w(tmem_d1, a_lo1 + ao, a_hi, b_lo + bo, b_hi, idesc, accumulate);
                     accumulate = 1;
@@ -597,7 +625,7 @@ conv3x3_halo_tc(const __grid_constant__ CUtensorMap tmap_x, const TcArgs a) {
             } else {
 #pragma unroll 1
               for (int tap = 0; tap < 9; ++tap) {
-                const int fw = tap / 3, fh = tap - fw * 3;
+                const int fh = tap / 3, fw = 2 - (tap - fh * 3);     // weight slot = kh*3 + (2 - kw)
                 for (int ks = 0; ks < ksteps; ++ks) {
                   const uint32_t ao = (uint32_t)((fh * HALO_W + fw) * 8 + ks * 2);
                   const uint32_t bo = (uint32_t)((tap * C::B_TAP_BYTES >> 4) + ks * 2);
@@ -634,7 +662,7 @@ conv3x3_halo_tc(const __grid_constant__ CUtensorMap tmap_x, const TcArgs a) {
 #pragma unroll 1
       for (int m = 0; m < mcount; ++m) {
         const int x = (bxg * MT + m) * TILE_W + tx;
-        const bool valid = (y < a.gh) && (x < a.gw);
+        const bool valid = (y < a.gh) && (x < a.gw) && !(a.dbg & 1);
         const long long pix = ((long long)img * a.oh + y) * a.ow + x;
         const uint32_t taddr = tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)((set * MT + m) * BN);
         if (BN == 16) {
@@ -704,6 +732,653 @@ conv3x3_halo_tc(const __grid_constant__ CUtensorMap tmap_x, const TcArgs a) {
   if (warp == 1) {
     asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "r"((uint32_t)C::TMEM_COLS)
                  : "memory");
+  }
+}
+
+
+// ---------------------------------------------------------------------------------------------
+// v4: kw-stacked 3x3 stride-1 pad-1 convolution, weights resident in shared memory.
+//
+// tcgen05.mma in SS mode re-reads its A tile (128 x 16 bf16 = 4 KB) from shared memory for every
+// instruction and shared memory delivers 128 B/clk/SM, so an MMA takes max(N/2, 32 + N/4) clocks
+// (measured, scripts/exp/exp_mma_rate.cu): N = 32 -> 40 clk (40 % of the tensor peak), N = 64 -> 48 (67 %),
+// N = 96 -> 56 (86 %), N >= 128 -> full rate.  The dense-block layers have cout = 32 / 64, so instead of nine
+// taps x N = cout this kernel stacks the three kw taps into the N dimension:
+//     Z[p, (kw, co)] = sum_{kh, ci} X[p + (kh-1) rows, ci] * W[kh, kw, ci, co]        (N = 3*cout, 3x fewer MMAs)
+//     Y[p, co]       = Z[p - 1, (0, co)] + Z[p, (1, co)] + Z[p + 1, (2, co)]          (epilogue, warp shuffles)
+// A pixel tile is 4 rows x 32 columns (M = 128, one TMEM lane per pixel, warp q of the epilogue = tile row q,
+// lane = column): the column shifts stay inside a warp.  Lanes 0 and 31 are halo columns - a tile produces
+// 30 output columns - and R vertically adjacent tiles share one haloed slab [4R+2 rows][32 px][64 ch].
+// The kh shift is a descriptor start-address offset of one slab row (4096 B).
+// All nine weight tiles of every K chunk ([chunk][kh][3*BN rows][64] pre-swizzled) are loaded ONCE per CTA.
+// Epilogue: TMEM -> registers -> shuffles -> bias / LeakyReLU / residuals / mask -> bf16 -> swizzled staging
+// tile in shared memory -> ONE TMA tensor store per tile (clipped at the image edge by the tensor map).
+// ---------------------------------------------------------------------------------------------
+constexpr int KW_TW = 32, KW_TH = 4, KW_VX = 30;         // tile width / height (M = 128), valid output columns
+struct KwArgs {
+  int n, cin, cout, h, w;
+  int nchunks, na;                      // K chunks of 64 channels; activation ring depth (host-sized)
+  int tiles_x, tiles_y;
+  long long num_tiles;
+  const __nv_bfloat16* wgt;
+  const float* bias;
+  int act; float act_slope, alpha;
+  const __nv_bfloat16* r1; int r1_ld; float beta1;
+  const __nv_bfloat16* r2; int r2_ld; float beta2;
+  const __nv_bfloat16* mask; int mask_ld; float mask_slope;
+  int dbg;
+};
+
+template <int BN, int R>
+struct KwCfg {
+  static constexpr int N = 3 * BN;
+  static constexpr int SLAB_ROWS = KW_TH * R + 2;
+  static constexpr int SLAB_BYTES = SLAB_ROWS * KW_TW * 128;          // 24576 (R=1) / 40960 (R=2)
+  static constexpr int W_KH_BYTES = N * 128;                          // one (chunk, kh) weight tile
+  static constexpr int W_CHUNK_BYTES = 3 * W_KH_BYTES;
+  static constexpr int STAGE_BYTES = ((KW_TH * R * KW_VX * BN * 2) + 1023) / 1024 * 1024;
+  static constexpr int NSTAGE = 2;                                    // one staging tile per epilogue group
+  static constexpr int TMEM_SET = R * N;                              // columns per accumulator set
+  static_assert(2 * TMEM_SET <= 512, "two accumulator sets must fit in TMEM");
+  static size_t smem_bytes(int nchunks, int na) {
+    return (size_t)nchunks * W_CHUNK_BYTES + (size_t)na * SLAB_BYTES + NSTAGE * STAGE_BYTES + SMEM_AUX + 1024;
+  }
+};
+
+__device__ __forceinline__ void tma_store_4d(const CUtensorMap* map, const void* src, int c0, int c1, int c2, int c3) {
+  asm volatile("cp.async.bulk.tensor.4d.global.shared::cta.bulk_group [%0, {%2, %3, %4, %5}], [%1];" ::"l"(map),
+               "r"(smem_u32(src)), "r"(c0), "r"(c1), "r"(c2), "r"(c3)
+               : "memory");
+}
+
+constexpr int KW_THREADS = 320;          // warp0 TMA, warp1 MMA, warps 2..5 / 6..9 the two epilogue groups
+template <int BN, int R>
+__global__ void __launch_bounds__(KW_THREADS, 1)
+conv3x3_kws_tc(const __grid_constant__ CUtensorMap tmap_x, const __grid_constant__ CUtensorMap tmap_y, const KwArgs a) {
+  using C = KwCfg<BN, R>;
+  constexpr int MAX_NA = 8;
+  extern __shared__ uint8_t smem_raw[];
+  uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~(uintptr_t)1023);
+  uint8_t* smem_w = smem;
+  uint8_t* smem_a = smem_w + (size_t)a.nchunks * C::W_CHUNK_BYTES;
+  uint8_t* smem_o = smem_a + (size_t)a.na * C::SLAB_BYTES;
+  uint8_t* aux = smem_o + C::NSTAGE * C::STAGE_BYTES;
+  uint64_t* a_full = reinterpret_cast<uint64_t*>(aux);
+  uint64_t* a_empty = a_full + MAX_NA;
+  uint64_t* w_full = a_empty + MAX_NA;
+  uint64_t* tfull_bar = w_full + 1;
+  uint64_t* tempty_bar = tfull_bar + 2;
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(tempty_bar + 2);
+  float* sbias = reinterpret_cast<float*>(aux + 512);
+
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  if (threadIdx.x == 0) {
+    for (int s = 0; s < a.na; ++s) { mbar_init(&a_full[s], 1); mbar_init(&a_empty[s], 1); }
+    mbar_init(w_full, 1);
+    for (int s = 0; s < 2; ++s) { mbar_init(&tfull_bar[s], 1); mbar_init(&tempty_bar[s], 128); }
+    asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+  }
+  for (int i = threadIdx.x; i < BN; i += KW_THREADS) sbias[i] = (a.bias && i < a.cout) ? a.bias[i] : 0.f;
+  if (warp == 1) {
+    asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(tmem_slot)),
+                 "r"(512u)
+                 : "memory");
+    asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
+  }
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  const uint32_t tmem_base = *tmem_slot;
+
+#define SRCGAN_DECODE_KW_TILE(t)                                       \
+  const uint32_t t32_ = (uint32_t)(t);                                 \
+  const uint32_t r_ = t32_ / (uint32_t)a.tiles_x;                      \
+  const int bx = (int)(t32_ - r_ * (uint32_t)a.tiles_x);               \
+  const int img = (int)(r_ / (uint32_t)a.tiles_y);                     \
+  const int by = (int)(r_ - (uint32_t)img * (uint32_t)a.tiles_y);      \
+  const int x0 = bx * KW_VX, y0 = by * (KW_TH * R);
+
+  if (warp == 0) {
+    // ---- producer: resident weights once, then one haloed slab per (tile, K chunk)
+    if (elect_one()) {
+      mbar_expect_tx(w_full, (uint32_t)(a.nchunks * C::W_CHUNK_BYTES));
+      for (int i = 0; i < a.nchunks * 3; ++i)
+        bulk_load(a.wgt + (size_t)i * (C::W_KH_BYTES / 2), w_full, smem_w + (size_t)i * C::W_KH_BYTES, C::W_KH_BYTES);
+    }
+    __syncwarp();
+    int as = 0;
+    uint32_t aph = 0;
+    for (long long t = blockIdx.x; t < a.num_tiles; t += gridDim.x) {
+      SRCGAN_DECODE_KW_TILE(t)
+      for (int c = 0; c < a.nchunks; ++c) {
+        mbar_wait(&a_empty[as], aph ^ 1);
+        if (elect_one()) {
+          if (a.dbg & 4) {
+            mbar_arrive(&a_full[as]);
+          } else {
+            mbar_expect_tx(&a_full[as], C::SLAB_BYTES);
+            tma_load_4d(&tmap_x, &a_full[as], smem_a + (size_t)as * C::SLAB_BYTES, c * KCH, x0 - 1, y0 - 1, img);
+          }
+        }
+        __syncwarp();
+        if (++as == a.na) { as = 0; aph ^= 1; }
+      }
+    }
+  } else if (warp == 1) {
+    // ---- MMA issuer: per slab R x 3 (kh) x ksteps instructions of N = 3*BN
+    constexpr uint32_t idesc = umma_idesc(TILE_M, C::N);
+    constexpr uint32_t hi = desc_hi(1024);
+    int as = 0;
+    uint32_t aph = 0;
+    int set = 0;
+    uint32_t set_phase = 0;
+    mbar_wait(w_full, 0);
+    for (long long t = blockIdx.x; t < a.num_tiles; t += gridDim.x) {
+      mbar_wait(&tempty_bar[set], set_phase ^ 1);
+      tc_fence_after();
+      const uint32_t tmem_d = tmem_base + (uint32_t)(set * C::TMEM_SET);
+      for (int c = 0; c < a.nchunks; ++c) {
+        const int rem = a.cin - c * KCH;
+        const int ksteps = ((rem >= KCH ? KCH : rem) + 15) >> 4;       // channels past cin are TMA zero-filled
+        mbar_wait(&a_full[as], aph);
+        tc_fence_after();
+        const uint32_t a_lo = desc_lo(smem_u32(smem_a + (size_t)as * C::SLAB_BYTES));
+        const uint32_t b_lo = desc_lo(smem_u32(smem_w + (size_t)c * C::W_CHUNK_BYTES));
+        if (elect_one()) {
+          if (!(a.dbg & 2)) {
+            if (ksteps == 4) {
+#pragma unroll
+              for (int s = 0; s < R; ++s)
+#pragma unroll
+                for (int kh = 0; kh < 3; ++kh)
+#pragma unroll
+                  for (int ks = 0; ks < 4; ++ks)
+                    umma_bf16_w(tmem_d + s * C::N, a_lo + (uint32_t)((s * KW_TH + kh) * (KW_TW * 8) + ks * 2), hi,
+                                b_lo + (uint32_t)(kh * (C::W_KH_BYTES >> 4) + ks * 2), hi, idesc,
+                                (c | kh | ks) != 0 ? 1u : 0u);
+            } else {
+#pragma unroll 1
+              for (int s = 0; s < R; ++s)
+#pragma unroll 1
+                for (int kh = 0; kh < 3; ++kh)
+                  for (int ks = 0; ks < ksteps; ++ks)
+                    umma_bf16_w(tmem_d + s * C::N, a_lo + (uint32_t)((s * KW_TH + kh) * (KW_TW * 8) + ks * 2), hi,
+                                b_lo + (uint32_t)(kh * (C::W_KH_BYTES >> 4) + ks * 2), hi, idesc,
+                                (c | kh | ks) != 0 ? 1u : 0u);
+            }
+          }
+          umma_commit(&a_empty[as]);
+          if (c == a.nchunks - 1) umma_commit(&tfull_bar[set]);
+        }
+        __syncwarp();
+        if (++as == a.na) { as = 0; aph ^= 1; }
+      }
+      if (++set == 2) { set = 0; set_phase ^= 1; }
+    }
+  } else {
+    // ---- epilogue: two groups of four warps take alternate tiles (group g drains accumulator set g), so a
+    // tile's epilogue may last two tile periods.  Warp q = tile row q, lane = slab column; output column
+    // x0 + lane - 1 for lanes 1..30.
+    const int q = warp & 3;
+    const int g = (warp - 2) >> 2;
+    const bool issuer = threadIdx.x == 64 + g * 128;
+    uint8_t* so = smem_o + g * C::STAGE_BYTES;
+    const uint32_t so_addr = smem_u32(so), sbias_addr = smem_u32(sbias);
+    const uint32_t bar_id = 1 + g;
+    long long it = 0;
+    long long tp[6] = {0, 0, 0, 0, 0, 0}, tc0 = 0;
+    const bool prof = (a.dbg & 32) != 0;
+#define SRCGAN_TICK(k) if (prof) { const long long n_ = clock64(); tp[k] += n_ - tc0; tc0 = n_; }
+    for (long long t = blockIdx.x; t < a.num_tiles; t += gridDim.x, ++it) {
+      if ((int)(it & 1) != g) continue;
+      if (prof) tc0 = clock64();
+      const uint32_t set_phase = (uint32_t)((it >> 1) & 1);
+      SRCGAN_DECODE_KW_TILE(t)
+      // this group's previous TMA store must have finished reading the staging tile
+      if (issuer) asm volatile("cp.async.bulk.wait_group.read 0;" ::: "memory");
+      asm volatile("bar.sync %0, 128;" ::"r"(bar_id) : "memory");
+      SRCGAN_TICK(0)
+      mbar_wait(&tfull_bar[g], set_phase);
+      tc_fence_after();
+      SRCGAN_TICK(1)
+      const int x = x0 + lane - 1;
+#pragma unroll 1
+      for (int s = 0; s < R; ++s) {
+        const int y = y0 + s * KW_TH + q;
+        const bool valid = lane >= 1 && lane <= KW_VX && x < a.w && y < a.h && !(a.dbg & 1);
+        const long long pix = ((long long)img * a.h + y) * a.w + x;
+        const int sidx = (s * KW_TH + q) * KW_VX + (lane - 1);           // pixel slot in the staging tile
+        const uint32_t taddr = tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)(g * C::TMEM_SET + s * C::N);
+#pragma unroll 1
+        for (int cb = 0; cb < BN; cb += 32) {
+          uint32_t z0[32], z1[32], z2[32];
+          tmem_ld32_nowait(taddr + 2 * BN + cb, z0);        // accumulator columns are [kw2 | kw1 | kw0]
+          tmem_ld32_nowait(taddr + BN + cb, z1);
+          tmem_ld32_nowait(taddr + cb, z2);
+          tmem_ld_wait();
+          SRCGAN_TICK(2)
+          float f[32];
+#pragma unroll
+          for (int i = 0; i < 32; i += 4) {
+            const float4 b4 = lds_f4(sbias_addr + (uint32_t)(cb + i) * 4);
+            const float bb[4] = {b4.x, b4.y, b4.z, b4.w};
+#pragma unroll
+            for (int k = 0; k < 4; ++k) {
+              const float l = __shfl_up_sync(0xffffffffu, __uint_as_float(z0[i + k]), 1);
+              const float r = __shfl_down_sync(0xffffffffu, __uint_as_float(z2[i + k]), 1);
+              f[i + k] = (__uint_as_float(z1[i + k]) + bb[k]) + (l + r);
+            }
+          }
+          if (a.act) {
+#pragma unroll
+            for (int i = 0; i < 32; ++i) f[i] = f[i] > 0.f ? f[i] : f[i] * a.act_slope;
+          }
+          if (a.alpha != 1.f) {
+#pragma unroll
+            for (int i = 0; i < 32; ++i) f[i] *= a.alpha;
+          }
+          SRCGAN_TICK(3)
+          if (valid) {
+#pragma unroll
+            for (int gq = 0; gq < 4; ++gq) {
+              const int cc = cb + gq * 8;
+              if (a.r1) {
+                float rr[8];
+                unpack8(__ldg(reinterpret_cast<const uint4*>(a.r1 + pix * a.r1_ld + cc)), rr);
+#pragma unroll
+                for (int i = 0; i < 8; ++i) f[gq * 8 + i] = fmaf(a.beta1, rr[i], f[gq * 8 + i]);
+              }
+              if (a.r2) {
+                float rr[8];
+                unpack8(__ldg(reinterpret_cast<const uint4*>(a.r2 + pix * a.r2_ld + cc)), rr);
+#pragma unroll
+                for (int i = 0; i < 8; ++i) f[gq * 8 + i] = fmaf(a.beta2, rr[i], f[gq * 8 + i]);
+              }
+              if (a.mask) {
+                float mm[8];
+                unpack8(__ldg(reinterpret_cast<const uint4*>(a.mask + pix * a.mask_ld + cc)), mm);
+#pragma unroll
+                for (int i = 0; i < 8; ++i) f[gq * 8 + i] *= (mm[i] > 0.f ? 1.f : a.mask_slope);
+              }
+              uint4 o;
+              __nv_bfloat162* oh = reinterpret_cast<__nv_bfloat162*>(&o);
+#pragma unroll
+              for (int i = 0; i < 4; ++i) oh[i] = __floats2bfloat162_rn(f[gq * 8 + 2 * i], f[gq * 8 + 2 * i + 1]);
+              // staging tile = the TMA box image [rows][30 px][BN ch] with the tensor map's swizzle
+              // (BN = 64: SWIZZLE_128B, 16-byte chunk j of pixel slot i at j ^ (i & 7); BN = 32: SWIZZLE_64B, j ^ ((i >> 1) & 3))
+              const int j = cc >> 3;
+              const int js = BN == 64 ? (j ^ (sidx & 7)) : (j ^ ((sidx >> 1) & 3));
+              sts_u4(so_addr + (uint32_t)(sidx * (BN * 2) + js * 16), o);
+            }
+          }
+        }
+      }
+      SRCGAN_TICK(4)
+      tc_fence_before();
+      mbar_arrive(&tempty_bar[g]);                                       // accumulators drained
+      asm volatile("fence.proxy.async.shared::cta;" ::: "memory");       // staging writes -> visible to the TMA engine
+      asm volatile("bar.sync %0, 128;" ::"r"(bar_id) : "memory");
+      if (issuer && !(a.dbg & 1)) {
+        tma_store_4d(&tmap_y, so, 0, x0, y0, img);
+        asm volatile("cp.async.bulk.commit_group;" ::: "memory");
+      }
+      SRCGAN_TICK(5)
+    }
+    if (prof && blockIdx.x == 0 && lane == 0)
+      printf("kws epi warp %d: tiles %lld  bar %lld  tfull %lld  tmem_ld %lld  math %lld  stage %lld  tail %lld (clk)\n", warp,
+             (it + 1 - g) / 2, tp[0], tp[1], tp[2], tp[3], tp[4], tp[5]);
+#undef SRCGAN_TICK
+    if (issuer) asm volatile("cp.async.bulk.wait_group 0;" ::: "memory");
+  }
+#undef SRCGAN_DECODE_KW_TILE
+  tc_fence_before();
+  __syncthreads();
+  if (warp == 1) {
+    asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "r"(512u) : "memory");
+  }
+}
+
+
+// ---------------------------------------------------------------------------------------------
+// v5: column sweep.  Same N-stacking as v4 ([kw2 | kw1 | kw0] weight rows, N = 3*BN, A read once per
+// (kh, k-step)), but the kw shift is applied to the ACCUMULATOR address instead of the data:
+//   * a work unit is a strip of 128 image rows (M = 128, TMEM lane = row) swept over a segment of columns;
+//   * TMEM is a ring of 512/BN output-column accumulators Y_x (BN fp32 columns each);
+//   * the MMAs of INPUT column c (A = the [130 rows][64 ch] slab of that column, kh = +128 B start offset)
+//     accumulate into the three consecutive ring blocks [Y_{c-1} | Y_c | Y_{c+1}]  (N = 3*BN, one instruction);
+//     at the ring wrap / segment ends the same MMA is issued as N = BN or 2*BN pieces (row offset in B).
+//   * blocks are zeroed by the epilogue when it drains them, so every MMA accumulates (no first-touch flag).
+// No shuffles, BN (not 3*BN) TMEM columns read per pixel, and the halo shrinks to 130/128 rows x (seg+2)/seg
+// columns, so L2->SMEM traffic is ~1.05x the compulsory minimum (the haloed 2-D tiles paid 1.4-1.6x).
+// Epilogue: two groups of four warps take alternate output columns: TMEM -> bias / LeakyReLU / residuals / mask
+// -> bf16 -> swizzled staging column [128][BN] -> one TMA tensor store (clipped at the image bottom).
+// ---------------------------------------------------------------------------------------------
+constexpr int SW_ROWS = 128, SW_SLAB_ROWS = SW_ROWS + 2;
+constexpr int SW_SLAB_BYTES = SW_SLAB_ROWS * 128;                      // 16640
+constexpr int SW_SLAB_STRIDE = (SW_SLAB_BYTES + 1023) / 1024 * 1024;   // 17408
+constexpr int SW_MAX_NA = 10;
+struct SwArgs {
+  int n, cin, cout, h, w;
+  int nchunks, na;
+  int wseg, segs_x, strips_y;
+  long long num_units;
+  const __nv_bfloat16* wgt;
+  const float* bias;
+  int act; float act_slope, alpha;
+  const __nv_bfloat16* r1; int r1_ld; float beta1;
+  const __nv_bfloat16* r2; int r2_ld; float beta2;
+  const __nv_bfloat16* mask; int mask_ld; float mask_slope;
+  int dbg;
+};
+
+template <int BN>
+struct SwCfg {
+  static constexpr int NBLK = 512 / BN;                               // ring of output-column accumulators
+  static constexpr int W_KH_BYTES = 3 * BN * 128;
+  static constexpr int W_CHUNK_BYTES = 3 * W_KH_BYTES;
+  static constexpr int STAGE_BYTES = SW_ROWS * BN * 2;                // 8 KB / 16 KB
+  static constexpr int NSTAGE = 4;                                    // two per epilogue group
+  static size_t smem_bytes(int nchunks, int na) {
+    return (size_t)nchunks * W_CHUNK_BYTES + (size_t)na * SW_SLAB_STRIDE + NSTAGE * STAGE_BYTES + SMEM_AUX + 1024;
+  }
+};
+
+__device__ __forceinline__ void tmem_st32_zero(uint32_t taddr) {
+  asm volatile(
+      "tcgen05.st.sync.aligned.32x32b.x32.b32 [%0], "
+      "{%1, %1, %1, %1, %1, %1, %1, %1, %1, %1, %1, %1, %1, %1, %1, %1, "
+      "%1, %1, %1, %1, %1, %1, %1, %1, %1, %1, %1, %1, %1, %1, %1, %1};" ::"r"(taddr), "r"(0u)
+      : "memory");
+}
+__device__ __forceinline__ void tmem_st_wait() { asm volatile("tcgen05.wait::st.sync.aligned;" ::: "memory"); }
+
+template <int BN>
+__global__ void __launch_bounds__(KW_THREADS, 1)
+conv3x3_sweep_tc(const __grid_constant__ CUtensorMap tmap_x, const __grid_constant__ CUtensorMap tmap_y, const SwArgs a) {
+  using C = SwCfg<BN>;
+  constexpr int NBLK = C::NBLK;
+  extern __shared__ uint8_t smem_raw[];
+  uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~(uintptr_t)1023);
+  uint8_t* smem_w = smem;
+  uint8_t* smem_a = smem_w + (size_t)a.nchunks * C::W_CHUNK_BYTES;
+  uint8_t* smem_o = smem_a + (size_t)a.na * SW_SLAB_STRIDE;
+  uint8_t* aux = smem_o + C::NSTAGE * C::STAGE_BYTES;
+  uint64_t* a_full = reinterpret_cast<uint64_t*>(aux);                 // [SW_MAX_NA]
+  uint64_t* a_empty = a_full + SW_MAX_NA;                              // [SW_MAX_NA]
+  uint64_t* y_full = a_empty + SW_MAX_NA;                              // [NBLK <= 16]
+  uint64_t* y_empty = y_full + 16;                                     // [NBLK <= 16]
+  uint64_t* w_full = y_empty + 16;
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(w_full + 1);
+  float* sbias = reinterpret_cast<float*>(aux + 768);
+
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  if (threadIdx.x == 0) {
+    for (int s = 0; s < a.na; ++s) { mbar_init(&a_full[s], 1); mbar_init(&a_empty[s], 1); }
+    for (int s = 0; s < NBLK; ++s) { mbar_init(&y_full[s], 1); mbar_init(&y_empty[s], 128); }
+    mbar_init(w_full, 1);
+    asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+  }
+  for (int i = threadIdx.x; i < BN; i += KW_THREADS) sbias[i] = (a.bias && i < a.cout) ? a.bias[i] : 0.f;
+  if (warp == 1) {
+    asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(tmem_slot)),
+                 "r"(512u)
+                 : "memory");
+    asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
+  }
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  const uint32_t tmem_base = *tmem_slot;
+  if (warp >= 2 && warp < 6) {                                         // the whole accumulator ring starts at zero
+    const uint32_t tq = tmem_base + ((uint32_t)((warp & 3) * 32) << 16);
+#pragma unroll 1
+    for (int cc = 0; cc < 512; cc += 32) tmem_st32_zero(tq + cc);
+    tmem_st_wait();
+  }
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+
+#define SRCGAN_DECODE_SW_UNIT(u)                                                   \
+  const uint32_t u32_ = (uint32_t)(u);                                             \
+  const uint32_t q_ = u32_ / (uint32_t)a.segs_x;                                   \
+  const int seg = (int)(u32_ - q_ * (uint32_t)a.segs_x);                           \
+  const int img = (int)(q_ / (uint32_t)a.strips_y);                                \
+  const int y0 = (int)(q_ - (uint32_t)img * (uint32_t)a.strips_y) * SW_ROWS;       \
+  const int x_start = seg * a.wseg;                                                \
+  const int x_end = (x_start + a.wseg) < a.w ? (x_start + a.wseg) : a.w;           \
+  const int c_first = x_start > 0 ? x_start - 1 : 0;                               \
+  const int c_last = x_end < a.w ? x_end : a.w - 1;
+
+  if (warp == 0) {
+    // ---- producer: resident weights once, then one column slab per (input column, K chunk)
+    if (elect_one()) {
+      mbar_expect_tx(w_full, (uint32_t)(a.nchunks * C::W_CHUNK_BYTES));
+      for (int i = 0; i < a.nchunks * 3; ++i)
+        bulk_load(a.wgt + (size_t)i * (C::W_KH_BYTES / 2), w_full, smem_w + (size_t)i * C::W_KH_BYTES, C::W_KH_BYTES);
+    }
+    __syncwarp();
+    int as = 0;
+    uint32_t aph = 0;
+    for (long long u = blockIdx.x; u < a.num_units; u += gridDim.x) {
+      SRCGAN_DECODE_SW_UNIT(u)
+      for (int c = c_first; c <= c_last; ++c)
+        for (int k = 0; k < a.nchunks; ++k) {
+          mbar_wait(&a_empty[as], aph ^ 1);
+          if (elect_one()) {
+            if (a.dbg & 4) {
+              mbar_arrive(&a_full[as]);
+            } else {
+              mbar_expect_tx(&a_full[as], SW_SLAB_BYTES);
+              tma_load_4d(&tmap_x, &a_full[as], smem_a + (size_t)as * SW_SLAB_STRIDE, k * KCH, c, y0 - 1, img);
+            }
+          }
+          __syncwarp();
+          if (++as == a.na) { as = 0; aph ^= 1; }
+        }
+    }
+  } else if (warp == 1) {
+    // ---- MMA issuer
+    constexpr uint32_t idesc1 = umma_idesc(TILE_M, BN), idesc2 = umma_idesc(TILE_M, 2 * BN),
+                       idesc3 = umma_idesc(TILE_M, 3 * BN);
+    constexpr uint32_t hi = desc_hi(1024);
+    int as = 0;
+    uint32_t aph = 0;
+    long long base = 0;                                                // running output-column index of this CTA
+    long long tp[6] = {0, 0, 0, 0, 0, 0}, tc0 = 0, ncol = 0;
+    const bool prof = (a.dbg & 32) != 0;
+#define SRCGAN_TICK(k) if (prof) { const long long n_ = clock64(); tp[k] += n_ - tc0; tc0 = n_; }
+    mbar_wait(w_full, 0);
+    for (long long u = blockIdx.x; u < a.num_units; u += gridDim.x) {
+      SRCGAN_DECODE_SW_UNIT(u)
+      (void)img; (void)y0;
+      for (int c = c_first; c <= c_last; ++c) {
+        if (prof) { tc0 = clock64(); ++ncol; }
+        const int xlo = (c - 1) > x_start ? (c - 1) : x_start;         // output columns this input column feeds
+        const int xhi = (c + 1) < (x_end - 1) ? (c + 1) : (x_end - 1);
+        // blocks touched for the first time must have been drained (and zeroed) by the epilogue
+        for (int x = (c == c_first ? xlo : xhi); x <= xhi; ++x) {
+          if (x <= c && c != c_first) continue;
+          const long long oi = base + (x - x_start);
+          mbar_wait(&y_empty[oi % NBLK], (uint32_t)(((oi / NBLK) & 1) ^ 1));
+        }
+        tc_fence_after();
+        SRCGAN_TICK(0)
+        // split [xlo, xhi] at the ring wrap into runs of consecutive blocks
+        const int b0 = (int)((base + (xlo - x_start)) % NBLK);
+        const int cnt = xhi - xlo + 1;
+        const int run0 = (b0 + cnt <= NBLK) ? cnt : (NBLK - b0);
+        const int roff0 = (xlo - (c - 1)) * BN;                        // weight row of the first fed column: (j+1)*BN
+        for (int k = 0; k < a.nchunks; ++k) {
+          const int rem = a.cin - k * KCH;
+          const int ksteps = ((rem >= KCH ? KCH : rem) + 15) >> 4;
+          SRCGAN_TICK(1)
+          mbar_wait(&a_full[as], aph);
+          tc_fence_after();
+          SRCGAN_TICK(2)
+          const uint32_t a_lo = desc_lo(smem_u32(smem_a + (size_t)as * SW_SLAB_STRIDE));
+          const uint32_t b_lo = desc_lo(smem_u32(smem_w + (size_t)k * C::W_CHUNK_BYTES));
+          if (elect_one()) {
+            if (!(a.dbg & 2)) {
+#pragma unroll 1
+              for (int r = 0; r < 2; ++r) {
+                const int n_run = r == 0 ? run0 : cnt - run0;
+                if (n_run <= 0) break;
+                const uint32_t d = tmem_base + (uint32_t)((r == 0 ? b0 : 0) * BN);
+                const uint32_t boff = (uint32_t)((roff0 + (r == 0 ? 0 : run0 * BN)) * 8);     // rows * 128 B >> 4
+                const uint32_t idesc = n_run == 3 ? idesc3 : (n_run == 2 ? idesc2 : idesc1);
+                if (ksteps == 4) {
+#pragma unroll
+                  for (int kh = 0; kh < 3; ++kh)
+#pragma unroll
+                    for (int ks = 0; ks < 4; ++ks)
+                      umma_bf16_w(d, a_lo + (uint32_t)(kh * 8 + ks * 2), hi,
+                                  b_lo + boff + (uint32_t)(kh * (C::W_KH_BYTES >> 4) + ks * 2), hi, idesc, 1u);
+                } else {
+#pragma unroll 1
+                  for (int kh = 0; kh < 3; ++kh)
+                    for (int ks = 0; ks < ksteps; ++ks)
+                      umma_bf16_w(d, a_lo + (uint32_t)(kh * 8 + ks * 2), hi,
+                                  b_lo + boff + (uint32_t)(kh * (C::W_KH_BYTES >> 4) + ks * 2), hi, idesc, 1u);
+                }
+              }
+            }
+            umma_commit(&a_empty[as]);
+          }
+          __syncwarp();
+          SRCGAN_TICK(3)
+          if (++as == a.na) { as = 0; aph ^= 1; }
+        }
+        // output column c-1 is complete once input column c is in; the last input column also completes column c
+        if (elect_one()) {
+          if (c - 1 >= x_start) umma_commit(&y_full[(base + (c - 1 - x_start)) % NBLK]);
+          if (c == c_last && c < x_end) umma_commit(&y_full[(base + (c - x_start)) % NBLK]);
+        }
+        __syncwarp();
+        SRCGAN_TICK(4)
+      }
+      base += x_end - x_start;
+    }
+    if (prof && blockIdx.x == 0 && lane == 0)
+      printf("sweep mma: cols %lld  y_empty %lld  setup %lld  a_full %lld  issue %lld  commit %lld (clk)\n", ncol, tp[0], tp[1],
+             tp[2], tp[3], tp[4]);
+#undef SRCGAN_TICK
+  } else {
+    // ---- epilogue: TMEM lane = image row y0 + q*32 + lane; group g takes the output columns with odd/even ring index
+    const int q = warp & 3;
+    const int g = (warp - 2) >> 2;
+    const bool issuer = threadIdx.x == 64 + g * 128;
+    const uint32_t sbias_addr = smem_u32(sbias);
+    const uint32_t bar_id = 1 + g;
+    const int row = q * 32 + lane;
+    long long base = 0;
+    int stage = 0;
+    long long tp[8] = {0, 0, 0, 0, 0, 0, 0, 0}, tc0 = 0, ncol = 0;
+    const bool prof = (a.dbg & 32) != 0;
+#define SRCGAN_TICK(k) if (prof) { const long long n_ = clock64(); tp[k] += n_ - tc0; tc0 = n_; }
+    for (long long u = blockIdx.x; u < a.num_units; u += gridDim.x) {
+      SRCGAN_DECODE_SW_UNIT(u)
+      (void)c_first; (void)c_last;
+      const int y = y0 + row;
+      const bool row_ok = y < a.h && !(a.dbg & 1);
+      for (int x = x_start; x < x_end; ++x) {
+        const long long oi = base + (x - x_start);
+        if ((int)(oi & 1) != g) continue;
+        const int b = (int)(oi % NBLK);
+        if (prof) { tc0 = clock64(); ++ncol; }
+        const uint32_t so_addr = smem_u32(smem_o + (size_t)(g * 2 + stage) * C::STAGE_BYTES);
+        // the staging column used two columns ago must have been read out by its TMA store
+        if (issuer) asm volatile("cp.async.bulk.wait_group.read 1;" ::: "memory");
+        SRCGAN_TICK(0)
+        asm volatile("bar.sync %0, 128;" ::"r"(bar_id) : "memory");
+        SRCGAN_TICK(1)
+        mbar_wait(&y_full[b], (uint32_t)((oi / NBLK) & 1));
+        tc_fence_after();
+        SRCGAN_TICK(2)
+        const uint32_t taddr = tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)(b * BN);
+        const long long pix = ((long long)img * a.h + y) * a.w + x;
+#pragma unroll 1
+        for (int cb = 0; cb < BN; cb += 32) {
+          uint32_t z[32];
+          tmem_ld32(taddr + cb, z);
+          SRCGAN_TICK(3)
+          tmem_st32_zero(taddr + cb);                                  // the block is reused NBLK columns later
+          float f[32];
+#pragma unroll
+          for (int i = 0; i < 32; i += 4) {
+            const float4 b4 = lds_f4(sbias_addr + (uint32_t)(cb + i) * 4);
+            f[i] = __uint_as_float(z[i]) + b4.x; f[i + 1] = __uint_as_float(z[i + 1]) + b4.y;
+            f[i + 2] = __uint_as_float(z[i + 2]) + b4.z; f[i + 3] = __uint_as_float(z[i + 3]) + b4.w;
+          }
+          if (a.act) {
+#pragma unroll
+            for (int i = 0; i < 32; ++i) f[i] = f[i] > 0.f ? f[i] : f[i] * a.act_slope;
+          }
+          if (a.alpha != 1.f) {
+#pragma unroll
+            for (int i = 0; i < 32; ++i) f[i] *= a.alpha;
+          }
+          if (row_ok) {
+#pragma unroll
+            for (int gq = 0; gq < 4; ++gq) {
+              const int cc = cb + gq * 8;
+              if (a.r1) {
+                float rr[8];
+                unpack8(__ldg(reinterpret_cast<const uint4*>(a.r1 + pix * a.r1_ld + cc)), rr);
+#pragma unroll
+                for (int i = 0; i < 8; ++i) f[gq * 8 + i] = fmaf(a.beta1, rr[i], f[gq * 8 + i]);
+              }
+              if (a.r2) {
+                float rr[8];
+                unpack8(__ldg(reinterpret_cast<const uint4*>(a.r2 + pix * a.r2_ld + cc)), rr);
+#pragma unroll
+                for (int i = 0; i < 8; ++i) f[gq * 8 + i] = fmaf(a.beta2, rr[i], f[gq * 8 + i]);
+              }
+              if (a.mask) {
+                float mm[8];
+                unpack8(__ldg(reinterpret_cast<const uint4*>(a.mask + pix * a.mask_ld + cc)), mm);
+#pragma unroll
+                for (int i = 0; i < 8; ++i) f[gq * 8 + i] *= (mm[i] > 0.f ? 1.f : a.mask_slope);
+              }
+              uint4 o;
+              __nv_bfloat162* oh = reinterpret_cast<__nv_bfloat162*>(&o);
+#pragma unroll
+              for (int i = 0; i < 4; ++i) oh[i] = __floats2bfloat162_rn(f[gq * 8 + 2 * i], f[gq * 8 + 2 * i + 1]);
+              const int j = cc >> 3;                                   // staging = TMA box image [128 rows][BN], swizzled
+              const int js = BN == 64 ? (j ^ (row & 7)) : (j ^ ((row >> 1) & 3));
+              sts_u4(so_addr + (uint32_t)(row * (BN * 2) + js * 16), o);
+            }
+          }
+        }
+        SRCGAN_TICK(4)
+        tmem_st_wait();
+        tc_fence_before();
+        mbar_arrive(&y_empty[b]);                                      // drained and zeroed
+        SRCGAN_TICK(5)
+        asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
+        asm volatile("bar.sync %0, 128;" ::"r"(bar_id) : "memory");
+        SRCGAN_TICK(6)
+        if (issuer && !(a.dbg & 1)) {
+          tma_store_4d(&tmap_y, reinterpret_cast<const void*>(smem_o + (size_t)(g * 2 + stage) * C::STAGE_BYTES), 0, x, y0,
+                       img);
+          asm volatile("cp.async.bulk.commit_group;" ::: "memory");
+        }
+        stage ^= 1;
+        SRCGAN_TICK(7)
+      }
+      base += x_end - x_start;
+    }
+    if (issuer) asm volatile("cp.async.bulk.wait_group 0;" ::: "memory");
+    if (prof && blockIdx.x == 0 && lane == 0)
+      printf("sweep epi warp %d: cols %lld  wait_rd %lld  bar %lld  y_full %lld  tmem_ld %lld  math+sts %lld  st_wait+arrive %lld  fence+bar %lld  store %lld (clk)\n",
+             warp, ncol, tp[0], tp[1], tp[2], tp[3], tp[4], tp[5], tp[6], tp[7]);
+#undef SRCGAN_TICK
+  }
+#undef SRCGAN_DECODE_SW_UNIT
+  tc_fence_before();
+  __syncthreads();
+  if (warp == 1) {
+    asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "r"(512u) : "memory");
   }
 }
 
@@ -879,6 +1554,89 @@ static int launch_halo(const CUtensorMap& tmap, const TcArgs& a, cudaStream_t st
   return check_launch("conv3x3_halo_tc");
 }
 
+
+// NHWC bf16 output slice (c channels at ptr, pixel pitch ld) -> tensor map whose box is one kw-stacked tile's
+// output [rows][30 px][c ch]; the shared-memory image is swizzled (128B for 64 channels, 64B for 32).
+static int make_tmap_out(CUtensorMap* tm, const void* ptr, int c, int w, int h, int n, int ld, int rows, const char* what,
+                         int box_w = KW_VX) {
+  EncodeTiledFn encode = get_encode_fn();
+  SRCGAN_REQUIRE(encode != nullptr, "%s: cuTensorMapEncodeTiled is not available from the driver", what);
+  cuuint64_t gdim[4] = {(cuuint64_t)c, (cuuint64_t)w, (cuuint64_t)h, (cuuint64_t)n};
+  cuuint64_t gstr[3] = {(cuuint64_t)ld * 2, (cuuint64_t)ld * 2 * w, (cuuint64_t)ld * 2 * w * h};
+  cuuint32_t box[4] = {(cuuint32_t)c, (cuuint32_t)box_w, (cuuint32_t)rows, 1};
+  cuuint32_t estr[4] = {1, 1, 1, 1};
+  CUresult cr = encode(tm, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 4, const_cast<void*>(ptr), gdim, gstr, box, estr,
+                       CU_TENSOR_MAP_INTERLEAVE_NONE, c == 64 ? CU_TENSOR_MAP_SWIZZLE_128B : CU_TENSOR_MAP_SWIZZLE_64B,
+                       CU_TENSOR_MAP_L2_PROMOTION_NONE, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+  if (cr != CUDA_SUCCESS) {
+    set_error("%s: cuTensorMapEncodeTiled(out) failed with CUresult %d", what, (int)cr);
+    return SRCGAN_E_CUDA;
+  }
+  return SRCGAN_OK;
+}
+
+// ring depth that fits next to the resident weights; 0 = does not fit
+template <int BN, int R>
+static int kws_ring_depth(int nchunks) {
+  using C = KwCfg<BN, R>;
+  const long long fixed = (long long)nchunks * C::W_CHUNK_BYTES + C::NSTAGE * C::STAGE_BYTES + SMEM_AUX + 1024;
+  long long na = (SMEM_BUDGET - fixed) / C::SLAB_BYTES;
+  return na > 8 ? 8 : (int)(na < 0 ? 0 : na);
+}
+
+template <int BN, int R>
+static int launch_kws(const CUtensorMap& tx, const CUtensorMap& ty, KwArgs& a, cudaStream_t st) {
+  using C = KwCfg<BN, R>;
+  a.na = kws_ring_depth<BN, R>(a.nchunks);
+  a.tiles_x = (a.w + KW_VX - 1) / KW_VX;
+  a.tiles_y = (a.h + KW_TH * R - 1) / (KW_TH * R);
+  a.num_tiles = (long long)a.tiles_x * a.tiles_y * a.n;
+  static bool attr_set = false;
+  if (!attr_set) {
+    SRCGAN_CUDA(cudaFuncSetAttribute(conv3x3_kws_tc<BN, R>, cudaFuncAttributeMaxDynamicSharedMemorySize, SMEM_BUDGET));
+    attr_set = true;
+  }
+  long long grid = a.num_tiles < kNumSMs ? a.num_tiles : kNumSMs;
+  conv3x3_kws_tc<BN, R><<<(unsigned)grid, KW_THREADS, C::smem_bytes(a.nchunks, a.na), st>>>(tx, ty, a);
+  count_launch();
+  return check_launch("conv3x3_kws_tc");
+}
+
+
+template <int BN>
+static int sweep_ring_depth(int nchunks) {
+  using C = SwCfg<BN>;
+  const long long fixed = (long long)nchunks * C::W_CHUNK_BYTES + C::NSTAGE * C::STAGE_BYTES + SMEM_AUX + 1024;
+  long long na = (SMEM_BUDGET - fixed) / SW_SLAB_STRIDE;
+  return na > SW_MAX_NA ? SW_MAX_NA : (int)(na < 0 ? 0 : na);
+}
+
+template <int BN>
+static int launch_sweep(const CUtensorMap& tx, const CUtensorMap& ty, SwArgs& a, cudaStream_t st) {
+  using C = SwCfg<BN>;
+  a.na = sweep_ring_depth<BN>(a.nchunks);
+  a.strips_y = (a.h + SW_ROWS - 1) / SW_ROWS;
+  // segment width: fewest CTA waves x (segment + 2 halo columns)
+  long long best = -1;
+  const int cand[4] = {16, 32, 64, a.w};
+  for (int i = 0; i < 4; ++i) {
+    const int ws = cand[i] < a.w ? cand[i] : a.w;
+    const long long segs = (a.w + ws - 1) / ws;
+    const long long units = segs * a.strips_y * a.n;
+    const long long cost = ((units + kNumSMs - 1) / kNumSMs) * (ws + 2);
+    if (best < 0 || cost < best) { best = cost; a.wseg = ws; a.segs_x = (int)segs; a.num_units = units; }
+  }
+  static bool attr_set = false;
+  if (!attr_set) {
+    SRCGAN_CUDA(cudaFuncSetAttribute(conv3x3_sweep_tc<BN>, cudaFuncAttributeMaxDynamicSharedMemorySize, SMEM_BUDGET));
+    attr_set = true;
+  }
+  long long grid = a.num_units < kNumSMs ? a.num_units : kNumSMs;
+  conv3x3_sweep_tc<BN><<<(unsigned)grid, KW_THREADS, C::smem_bytes(a.nchunks, a.na), st>>>(tx, ty, a);
+  count_launch();
+  return check_launch("conv3x3_sweep_tc");
+}
+
 static int dispatch(int bn, int maxt, const CUtensorMap& tmap, const TcArgs& a, cudaStream_t st) {
 #define SRCGAN_TC_CASE(B, T) if (bn == B && maxt == T) return launch<B, T>(tmap, a, st)
   SRCGAN_TC_CASE(32, 2); SRCGAN_TC_CASE(64, 2); SRCGAN_TC_CASE(128, 2);
@@ -937,6 +1695,8 @@ int pack_weights_tc_host(const float* w, int cout, int cin, int kh, int kw, int 
     SRCGAN_REQUIRE(tc_nch_ok(cout) || (cout <= 16 && layout == SRCGAN_WL_TC), "pack_weights(tc): cout %d unsupported",
                    cout);
     tc::HostPlan hp = tc::fprop_plan(kh, layout == SRCGAN_WL_TC ? 1 : 2, 0);   // slot order does not depend on pad
+    if (layout == SRCGAN_WL_TC && kh == 3 && cout <= 64)       // halo / stacked kernels: slot = kh*3 + (2 - kw)
+      for (int t = 0; t < 9; ++t) { hp.slot_kh[t] = t / 3; hp.slot_kw[t] = 2 - t % 3; }
     return tc::pack_launch(w, cout, cin, (long long)cin * taps, taps, kw, hp, (__nv_bfloat16*)out, st);
   }
   SRCGAN_REQUIRE(layout == SRCGAN_WL_TC_DGRAD_S2, "pack_weights(tc): unknown layout %d", layout);
@@ -954,10 +1714,68 @@ int pack_weights_tc_host(const float* w, int cout, int cin, int kh, int kw, int 
   return SRCGAN_OK;
 }
 
+// kw-stacked kernel: 3x3 stride 1 pad 1, cout 32 / 64, all weights resident in shared memory
+static int kws_variant(const srcgan_conv_params* p) {
+  if (p->kh != 3 || p->stride != 1 || p->pad != 1 || (p->cout != 32 && p->cout != 64)) return 0;
+  if (p->y_ld % 8 || ((uintptr_t)p->y) % 16 || getenv("SRCGAN_B200_NO_KWS")) return 0;
+  const int nchunks = (p->cin + tc::KCH - 1) / tc::KCH;
+  if (p->cout == 64) return tc::kws_ring_depth<64, 1>(nchunks) >= 3 ? 641 : 0;
+  if (tc::kws_ring_depth<32, 2>(nchunks) >= 3 && p->h > 4) return 322;
+  return tc::kws_ring_depth<32, 1>(nchunks) >= 3 ? 321 : 0;
+}
+
+static int conv_fprop_kws(const srcgan_conv_params* p, int variant, cudaStream_t st) {
+  const int rows = variant == 322 ? 2 : 1;
+  CUtensorMap tx, ty;
+  int rc = tc::make_tmap(&tx, p->x, p->cin, p->w, p->h, p->n, p->x_ld, tc::KW_TH * rows + 2, 1, "conv_fprop_tc(kws x)",
+                         tc::KW_TW);
+  if (rc) return rc;
+  rc = tc::make_tmap_out(&ty, p->y, p->cout, p->wo, p->ho, p->n, p->y_ld, tc::KW_TH * rows, "conv_fprop_tc(kws y)");
+  if (rc) return rc;
+  tc::KwArgs a;
+  a.n = p->n; a.cin = p->cin; a.cout = p->cout; a.h = p->ho; a.w = p->wo;
+  a.nchunks = (p->cin + tc::KCH - 1) / tc::KCH;
+  a.wgt = (const __nv_bfloat16*)p->wgt; a.bias = p->bias;
+  a.act = p->act; a.act_slope = p->act_slope; a.alpha = p->alpha;
+  a.r1 = (const __nv_bfloat16*)p->r1; a.r1_ld = p->r1_ld; a.beta1 = p->beta1;
+  a.r2 = (const __nv_bfloat16*)p->r2; a.r2_ld = p->r2_ld; a.beta2 = p->beta2;
+  a.mask = (const __nv_bfloat16*)p->mask; a.mask_ld = p->mask_ld; a.mask_slope = p->mask_slope;
+  { const char* d = getenv("SRCGAN_B200_DBG"); a.dbg = d ? atoi(d) : 0; }
+  if (variant == 641) return tc::launch_kws<64, 1>(tx, ty, a, st);
+  return variant == 322 ? tc::launch_kws<32, 2>(tx, ty, a, st) : tc::launch_kws<32, 1>(tx, ty, a, st);
+}
+
+// column-sweep kernel: 3x3 stride 1 pad 1, cout 32 / 64, weights resident, images at least one 128-row strip tall
+static bool sweep_ok(const srcgan_conv_params* p) {
+  if (p->kh != 3 || p->stride != 1 || p->pad != 1 || (p->cout != 32 && p->cout != 64)) return false;
+  if (p->y_ld % 8 || ((uintptr_t)p->y) % 16 || p->h < 96 || getenv("SRCGAN_B200_NO_SWEEP")) return false;
+  const int nchunks = (p->cin + tc::KCH - 1) / tc::KCH;
+  return (p->cout == 64 ? tc::sweep_ring_depth<64>(nchunks) : tc::sweep_ring_depth<32>(nchunks)) >= 4;
+}
+
+static int conv_fprop_sweep(const srcgan_conv_params* p, cudaStream_t st) {
+  CUtensorMap tx, ty;
+  int rc = tc::make_tmap(&tx, p->x, p->cin, p->w, p->h, p->n, p->x_ld, tc::SW_SLAB_ROWS, 1, "conv_fprop_tc(sweep x)", 1);
+  if (rc) return rc;
+  rc = tc::make_tmap_out(&ty, p->y, p->cout, p->wo, p->ho, p->n, p->y_ld, tc::SW_ROWS, "conv_fprop_tc(sweep y)", 1);
+  if (rc) return rc;
+  tc::SwArgs a;
+  a.n = p->n; a.cin = p->cin; a.cout = p->cout; a.h = p->ho; a.w = p->wo;
+  a.nchunks = (p->cin + tc::KCH - 1) / tc::KCH;
+  a.wgt = (const __nv_bfloat16*)p->wgt; a.bias = p->bias;
+  a.act = p->act; a.act_slope = p->act_slope; a.alpha = p->alpha;
+  a.r1 = (const __nv_bfloat16*)p->r1; a.r1_ld = p->r1_ld; a.beta1 = p->beta1;
+  a.r2 = (const __nv_bfloat16*)p->r2; a.r2_ld = p->r2_ld; a.beta2 = p->beta2;
+  a.mask = (const __nv_bfloat16*)p->mask; a.mask_ld = p->mask_ld; a.mask_slope = p->mask_slope;
+  { const char* d = getenv("SRCGAN_B200_DBG"); a.dbg = d ? atoi(d) : 0; }
+  return p->cout == 64 ? tc::launch_sweep<64>(tx, ty, a, st) : tc::launch_sweep<32>(tx, ty, a, st);
+}
+
 int conv_fprop_tc(const srcgan_conv_params* p, cudaStream_t st) {
+  if (sweep_ok(p)) return conv_fprop_sweep(p, st);
+  if (const int v = kws_variant(p)) return conv_fprop_kws(p, v, st);
   tc::HostPlan hp = tc::fprop_plan(p->kh, p->stride, p->pad);
-  const bool halo = p->kh == 3 && p->stride == 1 && (p->cout <= 16 || p->cout == 32 || p->cout == 64) &&
-                    !getenv("SRCGAN_B200_NO_HALO");
+  const bool halo = p->kh == 3 && p->stride == 1 && (p->cout <= 16 || p->cout == 32 || p->cout == 64);
   CUtensorMap tmap;
   int rc = halo ? tc::make_tmap(&tmap, p->x, p->cin, p->w, p->h, p->n, p->x_ld, tc::HALO_H, 1, "conv_fprop_tc",
                                 tc::HALO_W)
@@ -975,6 +1793,7 @@ int conv_fprop_tc(const srcgan_conv_params* p, cudaStream_t st) {
   a.tiles_y = (a.gh + tc::TILE_H - 1) / tc::TILE_H;
   a.num_tiles = tc::supertiles(a.tiles_x, bn) * a.tiles_y * p->n * a.n_blocks;
   tc::fill_epilogue(a, p);
+  { const char* d = getenv("SRCGAN_B200_DBG"); a.dbg = d ? atoi(d) : 0; }
   if (halo) {
     if (bn == 16) return tc::launch_halo<16>(tmap, a, st);
     return bn == 32 ? tc::launch_halo<32>(tmap, a, st) : tc::launch_halo<64>(tmap, a, st);
@@ -994,6 +1813,7 @@ int conv_dgrad_tc(const srcgan_conv_params* p, cudaStream_t st) {
     for (int pb = 0; pb < 2; ++pb) {
       tc::HostPlan hp = tc::dgrad2_phase_plan(p->kh, p->pad, pa, pb);
       tc::TcArgs a;
+      a.dbg = 0;
       a.n = p->n; a.cin = p->cout; a.cout = p->cin;          // GEMM K channels = dY channels, N = dX channels
       a.gh = (p->h - pa + 1) / 2; a.gw = (p->w - pb + 1) / 2;
       a.oh = p->h; a.ow = p->w; a.os = 2; a.oa = pa; a.ob = pb;

@@ -236,6 +236,13 @@ TC_CASES = [
     (1, 18, 10, 128, 256, 4, 1),     # discriminator 4x4 s1 (output 17x9)
     (1, 12, 12, 256, 128, 4, 2),     # its dgrad as an fprop (pad = k-1-p = 2)
     (3, 64, 64, 192, 64, 3, 1),      # many tiles per CTA: exercises stage/phase wrap-around
+    # column-sweep kernel (h >= 96, cout 32/64, resident weights): ragged strips, ring wrap, segment splits
+    (1, 128, 40, 64, 32, 3, 1),
+    (2, 130, 35, 96, 32, 3, 1),      # second strip has 2 valid rows; 32-channel K tail
+    (1, 256, 70, 64, 64, 3, 1),      # 8-block ring wraps many times
+    (1, 200, 19, 160, 32, 3, 1),
+    (2, 96, 16, 16, 64, 3, 1),       # single k-step chunk (K = 16)
+    (3, 256, 256, 64, 32, 3, 1),     # > 148 units: several units per CTA, segments of 32 / 64 columns
 ]
 
 
@@ -260,9 +267,10 @@ def test_conv_tc_matches_reference(case):
     assert float(ys.buf[..., :64].abs().max()) == 0.0
 
 
-def test_conv_tc_epilogue_matches_simt():
+@pytest.mark.parametrize("shape", [(2, 32, 16, 128, 64), (1, 160, 24, 64, 64), (1, 128, 50, 128, 32)])
+def test_conv_tc_epilogue_matches_simt(shape):
     from srcgan_b200 import ops
-    n, h, w, cin, cout = 2, 32, 16, 128, 64
+    n, h, w, cin, cout = shape
     x, wt, b = rand((n, cin, h, w), 1), rand((cout, cin, 3, 3), 2, 0.1), rand((cout,), 3)
     r1, r2, mk = rand((n, cout, h, w), 5), rand((n, cout, h, w), 6), rand((n, cout, h, w), 7)
     outs = []

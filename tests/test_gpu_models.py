@@ -239,6 +239,13 @@ def test_full_step_gray_against_golden(golden_step_gray, net):
     optimize_parameters calls vs the real reference's."""
     from oracle import srcgan_oracle as O
     fx = golden_step_gray[net]
+
+    # The first step must match to 1e-3 (measured 1e-6).  After the first Adam update (~ lr*sign(g) per weight)
+    # weights whose gradient is ~0 move the other way under a different summation order - with a gray input
+    # replicated to three identical channels there are many such ties - so the second step's losses carry that
+    # noise (measured on B200, scripts/diag_gray.py: 2e-5..1.1e-3 for net '2', <1e-5 for 'SRdens'; the CPU
+    # fp32-vs-fp64 oracle pair shows up to 4.7e-4 on the same losses).  They are judged with GRAD_FLOOR = 3e-3,
+    # the level at which the reference's own fp32 step is defined (see the header).
     random.seed(5)
     m = make_trainer(O.default_states(0, net), net=net)
     for it, rec in enumerate(fx["steps"]):
@@ -246,7 +253,7 @@ def test_full_step_gray_against_golden(golden_step_gray, net):
         m.optimize_parameters(real_A.to(DEV), real_B.to(DEV))
         got = m.current_losses()
         for n, v in rec["losses"].items():
-            assert math.isclose(got[n], v, rel_tol=TOL, abs_tol=1e-5), (net, it, n, got[n], v)
+            assert math.isclose(got[n], v, rel_tol=TOL if it == 0 else GRAD_FLOOR, abs_tol=1e-5), (net, it, n, got[n], v)
         if "fake_B" in rec:
             assert relerr(m.fake_B.detach(), rec["fake_B"]) < TOL
             assert relerr(m.fake_A.detach(), rec["fake_A"]) < TOL
