@@ -1382,6 +1382,474 @@ conv3x3_sweep_tc(const __grid_constant__ CUtensorMap tmap_x, const __grid_consta
   }
 }
 
+
+// ---------------------------------------------------------------------------------------------
+// v6: paired column sweep.  The v5 sweep with two changes that remove its shared-memory ceiling
+// (SS-mode MMAs re-read A (4 KB) and B (N x 32 B) for every instruction; at 128 B/clk/SM an N = 96 MMA is
+// SMEM-bound at 56 clk against 48 clk of math, and the slab / staging traffic comes on top):
+//   * cta_group::2 - a CTA pair sweeps two 128-row strips in lock step (M = 256).  Each CTA feeds its own A slab
+//     but only HALF of the stacked weight rows (N/2 x 32 B per MMA; measured 49 clk at N = 96, 96 clk at N = 192,
+//     scripts/exp/exp_pair.cu), so the weights of 192->64 (221 KB in v5) fit as 2 x 110 KB and every layer of a
+//     dense block runs on this kernel.  CG = 1 instantiations exist for A/B tests.
+//   * a ring without split instructions - TMEM faults when base + N crosses column 512 (exp_pair.cu), and a
+//     2-CTA instruction cannot be cut at the ring wrap (each CTA would need a different half of B).  The ring is
+//     therefore run as RUN = NBLK - 2 input columns per lap: input column k of a lap accumulates into blocks
+//     [k, k+1, k+2] (one N = 3*BN instruction, always), the lap restarts at block 0.  The two output columns that
+//     straddle a lap boundary own two partial blocks each (block RUN of lap r + block 0 of lap r+1; block RUN+1 of
+//     lap r + block 1 of lap r+1); the epilogue adds them.  Segment ends are handled the same way: every input
+//     column (including the two halo columns of a segment, zero-filled by TMA outside the image) issues the full
+//     instruction, and the two blocks per segment boundary that collect only halo contributions are drained as
+//     dummies.  The MMA warp's loop is one wait + 3*ksteps instructions + commits per column, no index arithmetic.
+// Roles: warp 0 TMA producer (both CTAs; the peer's loads signal the leader's mbarrier), warp 1 MMA issuer (leader
+// CTA only; commits are multicast to both CTAs), warps 2-5 / 6-9 two epilogue groups taking alternate output columns.
+// ---------------------------------------------------------------------------------------------
+struct Sw2Args {
+  int n, cin, cout, h, w;
+  int nchunks, na;
+  int wseg, segs_x, strips_y, strips;   // strips = n * strips_y, flattened over images
+  int num_units;                        // ceil(strips / CG) * segs_x
+  int pfd;                              // L2 prefetch distance of the producer, in columns (0 = off)
+  int tr;                               // 0: lanes = image rows, sweep over x;  1: lanes = pixels of a row, sweep over y
+  long long lane_stride, sweep_stride, img_stride;   // pixel index = img * img_stride + lane * lane_stride + sweep * sweep_stride
+  const __nv_bfloat16* wgt;
+  const float* bias;
+  __nv_bfloat16* y; int y_ld;           // output channel slice (pixel pitch y_ld elements)
+  int act; float act_slope, alpha;
+  const __nv_bfloat16* r1; int r1_ld; float beta1;
+  const __nv_bfloat16* r2; int r2_ld; float beta2;
+  const __nv_bfloat16* mask; int mask_ld; float mask_slope;
+  int dbg;
+};
+
+template <int BN, int CG>
+struct Sw2Cfg {
+  static constexpr int NBLK = 512 / BN;                               // accumulator blocks in TMEM
+  static constexpr int RUN = NBLK - 2;                                // input columns per lap
+  static constexpr int N = 3 * BN;
+  static constexpr int W_KH_FULL = N * 128;                           // one (chunk, kh) weight tile [kw2 | kw1 | kw0] x BN rows
+  static constexpr int W_KH_BYTES = W_KH_FULL / CG;                   // the rows this CTA feeds
+  static constexpr int W_CHUNK_BYTES = 3 * W_KH_BYTES;
+  static size_t smem_bytes(int nchunks, int na) {
+    return (size_t)nchunks * W_CHUNK_BYTES + (size_t)na * SW_SLAB_STRIDE + SMEM_AUX + 1024;
+  }
+};
+
+constexpr uint32_t PEER_MASK = 0xFEFFFFFFu;   // shared::cluster address of the same offset in the pair's even (leader) CTA
+
+__device__ __forceinline__ uint32_t cluster_ctarank() { uint32_t r; asm volatile("mov.u32 %0, %%cluster_ctarank;" : "=r"(r)); return r; }
+__device__ __forceinline__ void cluster_sync_all() {
+  asm volatile("barrier.cluster.arrive.release.aligned;\n\tbarrier.cluster.wait.acquire.aligned;" ::: "memory");
+}
+__device__ __forceinline__ void mbar_arrive_leader(uint64_t* bar) {       // arrive on the leader CTA's copy of `bar`
+  // default (.release.cta) semantics: the TMEM hand-over is ordered by tcgen05.wait::st + tcgen05.fence, and a
+  // .release.cluster arrive costs a MEMBAR.ALL.GPU + ERRBAR per call (37 % of the kernel's stall samples in ncu)
+  asm volatile("mbarrier.arrive.shared::cluster.b64 _, [%0];" ::"r"(smem_u32(bar) & PEER_MASK) : "memory");
+}
+__device__ __forceinline__ void tma_load_4d_pair(const CUtensorMap* map, uint64_t* bar, void* dst, int c0, int c1, int c2, int c3) {
+  asm volatile(
+      "cp.async.bulk.tensor.4d.cta_group::2.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4, %5, %6}], [%2];"
+      ::"r"(smem_u32(dst)), "l"(map), "r"(smem_u32(bar) & PEER_MASK), "r"(c0), "r"(c1), "r"(c2), "r"(c3)
+      : "memory");
+}
+__device__ __forceinline__ void tma_prefetch_4d(const CUtensorMap* map, int c0, int c1, int c2, int c3) {
+  asm volatile("cp.async.bulk.prefetch.tensor.4d.L2.global [%0, {%1, %2, %3, %4}];" ::"l"(map), "r"(c0), "r"(c1), "r"(c2), "r"(c3)
+               : "memory");
+}
+__device__ __forceinline__ void umma_bf16_w2(uint32_t tmem_d, uint32_t a_lo, uint32_t a_hi, uint32_t b_lo, uint32_t b_hi,
+                                             uint32_t idesc, uint32_t accumulate) {
+  asm volatile(
+      "{\n\t.reg .pred p;\n\t.reg .b64 da, db;\n\t"
+      "setp.ne.b32 p, %6, 0;\n\t"
+      "mov.b64 da, {%1, %2};\n\t"
+      "mov.b64 db, {%3, %4};\n\t"
+      "tcgen05.mma.cta_group::2.kind::f16 [%0], da, db, %5, p;\n\t}"
+      ::"r"(tmem_d), "r"(a_lo), "r"(a_hi), "r"(b_lo), "r"(b_hi), "r"(idesc), "r"(accumulate)
+      : "memory");
+}
+__device__ __forceinline__ void stg_u8(void* p, const uint4& lo, const uint4& hi) {      // one 32-byte sector per lane
+  asm volatile("st.global.v8.b32 [%0], {%1, %2, %3, %4, %5, %6, %7, %8};" ::"l"(p), "r"(lo.x), "r"(lo.y), "r"(lo.z), "r"(lo.w),
+               "r"(hi.x), "r"(hi.y), "r"(hi.z), "r"(hi.w)
+               : "memory");
+}
+__device__ __forceinline__ void umma_commit_pair(uint64_t* bar) {           // arrives on `bar` in both CTAs of the pair
+  asm volatile("tcgen05.commit.cta_group::2.mbarrier::arrive::one.shared::cluster.multicast::cluster.b64 [%0], %1;" ::"r"(
+                   smem_u32(bar)), "h"((uint16_t)3)
+               : "memory");
+}
+
+template <int BN, int CG>
+__global__ void __launch_bounds__(KW_THREADS, 1)
+conv3x3_sweep2_tc(const __grid_constant__ CUtensorMap tmap_x, const Sw2Args a) {
+  using C = Sw2Cfg<BN, CG>;
+  constexpr int NBLK = C::NBLK, RUN = C::RUN;
+  extern __shared__ uint8_t smem_raw[];
+  uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~(uintptr_t)1023);
+  uint8_t* smem_w = smem;
+  uint8_t* smem_a = smem_w + (size_t)a.nchunks * C::W_CHUNK_BYTES;
+  uint8_t* aux = smem_a + (size_t)a.na * SW_SLAB_STRIDE;
+  uint64_t* a_full = reinterpret_cast<uint64_t*>(aux);                 // [SW_MAX_NA]  (leader's copy is the live one)
+  uint64_t* a_empty = a_full + SW_MAX_NA;                              // [SW_MAX_NA]
+  uint64_t* y_full = a_empty + SW_MAX_NA;                              // [NBLK <= 16]
+  uint64_t* y_empty = y_full + 16;                                     // [NBLK <= 16] (leader's copy is the live one)
+  uint64_t* w_full = y_empty + 16;
+  uint64_t* w_pair = w_full + 1;                                       // leader: the peer's weights have landed
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(w_pair + 1);
+  float* sbias = reinterpret_cast<float*>(aux + 768);
+
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const uint32_t rank = CG == 2 ? cluster_ctarank() : 0u;
+  const int cid = (int)(blockIdx.x / CG), ncl = (int)(gridDim.x / CG);
+  if (threadIdx.x == 0) {
+    for (int s = 0; s < a.na; ++s) { mbar_init(&a_full[s], 1); mbar_init(&a_empty[s], 1); }
+    for (int s = 0; s < NBLK; ++s) { mbar_init(&y_full[s], 1); mbar_init(&y_empty[s], 4 * CG); }
+    mbar_init(w_full, 1);
+    mbar_init(w_pair, 1);
+    asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+  }
+  for (int i = threadIdx.x; i < BN; i += KW_THREADS) sbias[i] = (a.bias && i < a.cout) ? a.bias[i] : 0.f;
+  if (warp == 1) {
+    if (CG == 1) {
+      asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(tmem_slot)), "r"(512u) : "memory");
+      asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
+    } else {
+      asm volatile("tcgen05.alloc.cta_group::2.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(tmem_slot)), "r"(512u) : "memory");
+      asm volatile("tcgen05.relinquish_alloc_permit.cta_group::2.sync.aligned;" ::: "memory");
+    }
+  }
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  const uint32_t tmem_base = *tmem_slot;
+  if (warp >= 2 && warp < 6) {                                         // every accumulator block starts at zero
+    const uint32_t tq = tmem_base + ((uint32_t)((warp & 3) * 32) << 16);
+#pragma unroll 1
+    for (int cc = 0; cc < 512; cc += 32) tmem_st32_zero(tq + cc);
+    tmem_st_wait();
+  }
+  tc_fence_before();
+  __syncthreads();
+  if (CG == 2) cluster_sync_all();                                     // barriers initialised and TMEM zeroed in both CTAs
+  tc_fence_after();
+
+  // unit u -> column segment [x_start, x_end) of strip (u / segs_x) * CG + rank; an absent strip (odd total) sweeps
+  // rows below the image: its loads are zero-filled, its stores suppressed
+#define SRCGAN_DECODE_SW2_UNIT(u)                                                  \
+  const uint32_t sg_ = (uint32_t)(u) / (uint32_t)a.segs_x;                         \
+  const int seg = (int)((uint32_t)(u) - sg_ * (uint32_t)a.segs_x);                 \
+  const int sidx = (int)sg_ * CG + (int)rank;                                      \
+  const bool strip_ok = sidx < a.strips;                                           \
+  const int img = strip_ok ? sidx / a.strips_y : 0;                                \
+  const int y0 = strip_ok ? (sidx - img * a.strips_y) * SW_ROWS : a.h + 1;         \
+  const int x_start = seg * a.wseg;                                                \
+  const int x_end = (x_start + a.wseg) < a.w ? (x_start + a.wseg) : a.w;
+
+  if (warp == 0) {
+    // ---- producer: this CTA's weight rows once, then one column slab per (input column, K chunk)
+    if (elect_one()) {
+      // tile (chunk, lane tap t) = the three sweep taps stacked [s = 2 | 1 | 0] x BN rows; packed slot of tap (kh, kw) = kh*3 + (2 - kw).
+      // A CTA of a pair takes its half of the stacked rows (three half-slots).
+      mbar_expect_tx(w_full, (uint32_t)(a.nchunks * C::W_CHUNK_BYTES));
+      constexpr int PIECE = BN * 128 / CG;                              // bytes per copy: a slot (CG = 1) or half a slot
+      for (int i = 0; i < a.nchunks; ++i)
+        for (int t = 0; t < 3; ++t)
+          for (int h3 = 0; h3 < 3; ++h3) {
+            const int hs = CG == 1 ? h3 : (int)rank * 3 + h3;          // piece index in the stacked tile
+            const int si = CG == 1 ? hs : hs >> 1, part = CG == 1 ? 0 : hs & 1;
+            const int sw = 2 - si;                                     // sweep-direction tap
+            const int kh = a.tr ? sw : t, kw = a.tr ? t : sw;
+            const int slot = kh * 3 + (2 - kw);
+            bulk_load(a.wgt + ((size_t)(i * 9 + slot) * (BN * 128) + (size_t)part * PIECE) / 2, w_full,
+                      smem_w + (size_t)(i * 3 + t) * C::W_KH_BYTES + (size_t)h3 * PIECE, PIECE);
+          }
+    }
+    __syncwarp();
+    if (CG == 2 && rank == 1) {
+      mbar_wait(w_full, 0);
+      if (elect_one()) mbar_arrive_leader(w_pair);
+      __syncwarp();
+    }
+    int as = 0;
+    uint32_t aph = 0;
+    for (int u = cid; u < a.num_units; u += ncl) {
+      SRCGAN_DECODE_SW2_UNIT(u)
+      (void)strip_ok;
+      const int pfd = a.pfd;                                           // L2 prefetch distance in columns
+      if (pfd > 0 && elect_one())
+        for (int c = x_start - 1; c < x_start - 1 + pfd && c <= x_end; ++c)
+          for (int k = 0; k < a.nchunks; ++k) tma_prefetch_4d(&tmap_x, k * KCH, c, y0 - 1, img);
+      __syncwarp();
+      for (int c = x_start - 1; c <= x_end; ++c)
+        for (int k = 0; k < a.nchunks; ++k) {
+          mbar_wait(&a_empty[as], aph ^ 1);
+          if (elect_one()) {
+            if (pfd > 0 && c + pfd <= x_end) tma_prefetch_4d(&tmap_x, k * KCH, c + pfd, y0 - 1, img);
+            uint8_t* dst = smem_a + (size_t)as * SW_SLAB_STRIDE;
+            if (a.dbg & 4) {
+              if (rank == 0) mbar_arrive(&a_full[as]);
+            } else if (CG == 1) {
+              mbar_expect_tx(&a_full[as], SW_SLAB_BYTES);
+              tma_load_4d(&tmap_x, &a_full[as], dst, k * KCH, c, y0 - 1, img);
+            } else {
+              if (rank == 0) mbar_expect_tx(&a_full[as], 2 * SW_SLAB_BYTES);
+              tma_load_4d_pair(&tmap_x, &a_full[as], dst, k * KCH, c, y0 - 1, img);
+            }
+          }
+          __syncwarp();
+          if (++as == a.na) { as = 0; aph ^= 1; }
+        }
+    }
+  } else if (warp == 1) {
+    // ---- MMA issuer (leader CTA of a pair)
+    if (rank == 0) {
+      constexpr uint32_t idesc = umma_idesc(TILE_M * CG, C::N);
+      constexpr uint32_t hi = desc_hi(1024);
+      int as = 0;
+      uint32_t aph = 0;
+      int k = 0;                                                       // position in the lap
+      uint32_t lap_par = 0;
+      mbar_wait(w_full, 0);
+      if (CG == 2) mbar_wait(w_pair, 0);
+      const uint32_t w_lo = desc_lo(smem_u32(smem_w));
+      long long tp[4] = {0, 0, 0, 0}, tc0 = 0, ncol = 0;
+      const bool prof = (a.dbg & 32) != 0;
+#define SRCGAN_TICK(i) if (prof) { const long long n_ = clock64(); tp[i] += n_ - tc0; tc0 = n_; }
+      for (int u = cid; u < a.num_units; u += ncl) {
+        const int seg = u % a.segs_x;
+        const int x_start = seg * a.wseg;
+        const int x_end = (x_start + a.wseg) < a.w ? (x_start + a.wseg) : a.w;
+        for (int c = x_start - 1; c <= x_end; ++c) {
+          if (prof) { tc0 = clock64(); ++ncol; }
+          // blocks touched for the first time in this lap must have been drained (and zeroed) by the epilogues
+          if (k == 0) { mbar_wait(&y_empty[0], lap_par ^ 1); mbar_wait(&y_empty[1], lap_par ^ 1); }
+          mbar_wait(&y_empty[k + 2], lap_par ^ 1);
+          tc_fence_after();
+          const uint32_t d = tmem_base + (uint32_t)(k * BN);
+          SRCGAN_TICK(0)
+          for (int kc = 0; kc < a.nchunks; ++kc) {
+            const int rem = a.cin - kc * KCH;
+            const int ksteps = ((rem >= KCH ? KCH : rem) + 15) >> 4;     // channels past cin are TMA zero-filled
+            mbar_wait(&a_full[as], aph);
+            tc_fence_after();
+            SRCGAN_TICK(1)
+            const uint32_t a_lo = desc_lo(smem_u32(smem_a + (size_t)as * SW_SLAB_STRIDE));
+            const uint32_t b_lo = w_lo + (uint32_t)(kc * (C::W_CHUNK_BYTES >> 4));
+            if (elect_one()) {
+              if (!(a.dbg & 2)) {
+                if (ksteps == 4) {
+#pragma unroll
+                  for (int kh = 0; kh < 3; ++kh)
+#pragma unroll
+                    for (int ks = 0; ks < 4; ++ks) {
+                      if (CG == 1) umma_bf16_w(d, a_lo + (uint32_t)(kh * 8 + ks * 2), hi,
+                                               b_lo + (uint32_t)(kh * (C::W_KH_BYTES >> 4) + ks * 2), hi, idesc, 1u);
+                      else umma_bf16_w2(d, a_lo + (uint32_t)(kh * 8 + ks * 2), hi,
+                                        b_lo + (uint32_t)(kh * (C::W_KH_BYTES >> 4) + ks * 2), hi, idesc, 1u);
+                    }
+                } else {
+#pragma unroll 1
+                  for (int kh = 0; kh < 3; ++kh)
+                    for (int ks = 0; ks < ksteps; ++ks) {
+                      if (CG == 1) umma_bf16_w(d, a_lo + (uint32_t)(kh * 8 + ks * 2), hi,
+                                               b_lo + (uint32_t)(kh * (C::W_KH_BYTES >> 4) + ks * 2), hi, idesc, 1u);
+                      else umma_bf16_w2(d, a_lo + (uint32_t)(kh * 8 + ks * 2), hi,
+                                        b_lo + (uint32_t)(kh * (C::W_KH_BYTES >> 4) + ks * 2), hi, idesc, 1u);
+                    }
+                }
+              }
+              if (kc == a.nchunks - 1) {
+                // block k has received its last contribution; the lap's last column also completes its two tail blocks.
+                // (The epilogue group that waits for this commit releases the column's slabs.)
+                if (CG == 1) umma_commit(&y_full[k]); else umma_commit_pair(&y_full[k]);
+                if (k == RUN - 1) {
+                  if (CG == 1) { umma_commit(&y_full[RUN]); umma_commit(&y_full[RUN + 1]); }
+                  else { umma_commit_pair(&y_full[RUN]); umma_commit_pair(&y_full[RUN + 1]); }
+                }
+              }
+            }
+            __syncwarp();
+            SRCGAN_TICK(2)
+            if (++as == a.na) { as = 0; aph ^= 1; }
+          }
+          if (++k == RUN) { k = 0; lap_par ^= 1; }
+        }
+      }
+      if (prof && blockIdx.x == 0 && lane == 0)
+        printf("sweep2 mma: cols %lld  y_empty %lld  a_full %lld  issue+commit %lld (clk/col)\n", ncol, tp[0] / ncol, tp[1] / ncol, tp[2] / ncol);
+#undef SRCGAN_TICK
+    }
+  } else {
+    // ---- epilogue: TMEM lane = image row y0 + q*32 + lane; group g takes the outputs with (running index & 1) == g;
+    // the four warps of a group never synchronise with each other (registers -> global memory, no staging).
+    // Running output index o = running input index of the column it is centred on; lap r = o / RUN, m = o % RUN:
+    // main block m + 1 of lap r, plus block 0 of lap r + 1 when m == RUN - 1, plus block RUN + 1 of lap r - 1 when m == 0.
+    // Every output's wait set contains the commit that follows input column o + 1, so the group's first warp also
+    // hands that column's slabs back to the producer (the MMA warp issues one commit per column, not two).
+    const int q = warp & 3;
+    const int g = (warp - 2) >> 2;
+    const uint32_t sbias_addr = smem_u32(sbias);
+    const int row = q * 32 + lane;
+    const uint32_t lane_base = tmem_base + ((uint32_t)(q * 32) << 16);
+    const bool wide_st = (a.y_ld % 16 == 0) && ((reinterpret_cast<uintptr_t>(a.y) & 31) == 0);
+    auto arrive_empty = [&](int blk) {
+      if (CG == 1) mbar_arrive(&y_empty[blk]); else mbar_arrive_leader(&y_empty[blk]);
+    };
+    // slots of input column t: (t * nchunks + kc) % na
+    auto release_slabs = [&](uint32_t t) {
+      if (q == 0 && lane == 0) {
+        uint32_t s = (t * (uint32_t)a.nchunks) % (uint32_t)a.na;
+        for (int kc = 0; kc < a.nchunks; ++kc) {
+          mbar_arrive(&a_empty[s]);
+          if (++s == (uint32_t)a.na) s = 0;
+        }
+      }
+    };
+    if (g == 1) {                                                      // "output -1": block 0 of lap 0 collects only a halo tap
+      mbar_wait(&y_full[0], 0);
+      tc_fence_after();
+      release_slabs(0);
+#pragma unroll 1
+      for (int cb = 0; cb < BN; cb += 32) tmem_st32_zero(lane_base + cb);
+      tmem_st_wait();
+      tc_fence_before();
+      __syncwarp();
+      if (lane == 0) arrive_empty(0);
+    }
+    long long tp[4] = {0, 0, 0, 0}, tc0 = 0, ncol = 0;
+    const bool prof = (a.dbg & 32) != 0;
+#define SRCGAN_TICK(i) if (prof) { const long long n_ = clock64(); tp[i] += n_ - tc0; tc0 = n_; }
+    uint32_t t0 = 0;                                                   // running index of the unit's first input column
+    uint32_t r = 0;                                                    // lap and position of this group's next output
+    int m = g;
+    for (int u = cid; u < a.num_units; u += ncl) {
+      SRCGAN_DECODE_SW2_UNIT(u)
+      const bool last_unit = u + ncl >= a.num_units;
+      const int n_in = x_end - x_start + 2;
+      const int y = y0 + row;
+      const bool row_ok = strip_ok && y < a.h && !(a.dbg & 1);
+      for (int j = (int)((t0 ^ (uint32_t)g) & 1u); j < n_in; j += 2) {
+        if (last_unit && j == n_in - 1) break;                         // centred on the stream's last input: never completes
+        const uint32_t o = t0 + (uint32_t)j;
+        const int pb = m + 1;
+        const uint32_t ppar = r & 1u;
+        const int sb = m == RUN - 1 ? 0 : ((m == 0 && o > 0) ? RUN + 1 : -1);
+        const uint32_t spar = ppar ^ 1u;                               // lap r + 1 or r - 1
+        const bool real = j >= 1 && j <= n_in - 2;
+        const int x = x_start + j - 1;
+        if (prof) { tc0 = clock64(); ++ncol; }
+        mbar_wait(&y_full[pb], ppar);
+        if (sb >= 0) mbar_wait(&y_full[sb], spar);
+        tc_fence_after();
+        SRCGAN_TICK(0)
+        release_slabs(o + 1);
+        const uint32_t taddr = lane_base + (uint32_t)(pb * BN);
+        const uint32_t saddr = lane_base + (uint32_t)((sb >= 0 ? sb : 0) * BN);
+        if (!real) {
+#pragma unroll 1
+          for (int cb = 0; cb < BN; cb += 32) {
+            tmem_st32_zero(taddr + cb);
+            if (sb >= 0) tmem_st32_zero(saddr + cb);
+          }
+        } else {
+          const long long pix = (long long)img * a.img_stride + (long long)y * a.lane_stride + (long long)x * a.sweep_stride;
+#pragma unroll 1
+          for (int cb = 0; cb < BN; cb += 32) {
+            uint32_t z[32];
+            float f[32];
+            if (sb >= 0) {
+              uint32_t z2[32];
+              tmem_ld32_nowait(taddr + cb, z);
+              tmem_ld32_nowait(saddr + cb, z2);
+              tmem_ld_wait();
+              tmem_st32_zero(taddr + cb);
+              tmem_st32_zero(saddr + cb);
+#pragma unroll
+              for (int i = 0; i < 32; ++i) f[i] = __uint_as_float(z[i]) + __uint_as_float(z2[i]);
+            } else {
+              tmem_ld32(taddr + cb, z);
+              tmem_st32_zero(taddr + cb);                              // the block is reused one lap later
+#pragma unroll
+              for (int i = 0; i < 32; ++i) f[i] = __uint_as_float(z[i]);
+            }
+#pragma unroll
+            for (int i = 0; i < 32; i += 4) {
+              const float4 b4 = lds_f4(sbias_addr + (uint32_t)(cb + i) * 4);
+              f[i] += b4.x; f[i + 1] += b4.y; f[i + 2] += b4.z; f[i + 3] += b4.w;
+            }
+            if (a.act) {                                               // LeakyReLU, 0 <= slope <= 1: max(f, f * slope)
+#pragma unroll
+              for (int i = 0; i < 32; ++i) f[i] = fmaxf(f[i], f[i] * a.act_slope);
+            }
+            if (a.alpha != 1.f) {
+#pragma unroll
+              for (int i = 0; i < 32; ++i) f[i] *= a.alpha;
+            }
+            if (row_ok) {
+              uint4 ov[4];
+#pragma unroll
+              for (int gq = 0; gq < 4; ++gq) {
+                const int cc = cb + gq * 8;
+                if (a.r1) {
+                  float rr[8];
+                  unpack8(__ldg(reinterpret_cast<const uint4*>(a.r1 + pix * a.r1_ld + cc)), rr);
+#pragma unroll
+                  for (int i = 0; i < 8; ++i) f[gq * 8 + i] = fmaf(a.beta1, rr[i], f[gq * 8 + i]);
+                }
+                if (a.r2) {
+                  float rr[8];
+                  unpack8(__ldg(reinterpret_cast<const uint4*>(a.r2 + pix * a.r2_ld + cc)), rr);
+#pragma unroll
+                  for (int i = 0; i < 8; ++i) f[gq * 8 + i] = fmaf(a.beta2, rr[i], f[gq * 8 + i]);
+                }
+                if (a.mask) {
+                  float mm[8];
+                  unpack8(__ldg(reinterpret_cast<const uint4*>(a.mask + pix * a.mask_ld + cc)), mm);
+#pragma unroll
+                  for (int i = 0; i < 8; ++i) f[gq * 8 + i] *= (mm[i] > 0.f ? 1.f : a.mask_slope);
+                }
+                __nv_bfloat162* oh = reinterpret_cast<__nv_bfloat162*>(&ov[gq]);
+#pragma unroll
+                for (int i = 0; i < 4; ++i) oh[i] = __floats2bfloat162_rn(f[gq * 8 + 2 * i], f[gq * 8 + 2 * i + 1]);
+              }
+              __nv_bfloat16* dst = a.y + pix * a.y_ld + cb;            // this pixel's 32 channels: 64 contiguous bytes
+              if (wide_st) {
+                stg_u8(dst, ov[0], ov[1]);
+                stg_u8(dst + 16, ov[2], ov[3]);
+              } else {
+#pragma unroll
+                for (int gq = 0; gq < 4; ++gq) *reinterpret_cast<uint4*>(dst + gq * 8) = ov[gq];
+              }
+            }
+          }
+        }
+        SRCGAN_TICK(1)
+        tmem_st_wait();
+        tc_fence_before();
+        __syncwarp();
+        if (lane == 0) {                                               // drained and zeroed (one arrival per warp)
+          arrive_empty(pb);
+          if (sb >= 0) arrive_empty(sb);
+        }
+        SRCGAN_TICK(2)
+        m += 2;
+        if (m >= RUN) { m -= RUN; ++r; }
+      }
+      t0 += (uint32_t)n_in;
+    }
+    if (prof && blockIdx.x == 0 && lane == 0 && ncol)
+      printf("sweep2 epi warp %d: cols %lld  y_full %lld  ld+math+store %lld  st_wait+arrive %lld (clk/col)\n", warp, ncol, tp[0] / ncol,
+             tp[1] / ncol, tp[2] / ncol);
+#undef SRCGAN_TICK
+  }
+#undef SRCGAN_DECODE_SW2_UNIT
+  tc_fence_before();
+  __syncthreads();
+  if (CG == 2) cluster_sync_all();                                     // the peer may still signal this CTA's barriers
+  if (warp == 1) {
+    if (CG == 1) asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "r"(512u) : "memory");
+    else asm volatile("tcgen05.dealloc.cta_group::2.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "r"(512u) : "memory");
+  }
+}
+
 // fp32 OIHW -> bf16 [n_block][chunk][slot][BN][64]: each [BN][64] tile is stored as its SWIZZLE_128B
 // shared-memory image (16-byte chunk j of row r lives at chunk j ^ (r & 7)), zero padded in K.
 // Rows are the GEMM-N channels, columns the GEMM-K channels: (co, ci) for fprop, (ci, co) for dgrad.
@@ -1428,15 +1896,20 @@ static EncodeTiledFn get_encode_fn() {
 // NHWC bf16 tensor (c channels at ptr, pixel pitch ld) -> tensor map whose box is the sampled slab
 // [rows][8 px][64 ch]; sample = 1 (dense) or 2 (every other pixel, for stride-2 convolutions).
 static int make_tmap(CUtensorMap* tm, const void* ptr, int c, int w, int h, int n, int ld, int rows, int sample,
-                     const char* what, int box_w = TILE_W) {
+                     const char* what, int box_w = TILE_W, bool transposed = false) {
   EncodeTiledFn encode = get_encode_fn();
   SRCGAN_REQUIRE(encode != nullptr, "%s: cuTensorMapEncodeTiled is not available from the driver", what);
   cuuint64_t gdim[4] = {(cuuint64_t)c, (cuuint64_t)w, (cuuint64_t)h, (cuuint64_t)n};
   cuuint64_t gstr[3] = {(cuuint64_t)ld * 2, (cuuint64_t)ld * 2 * w, (cuuint64_t)ld * 2 * w * h};
+  if (transposed) {                       // coordinate 1 walks image rows, coordinate 2 walks pixels of a row
+    gdim[1] = (cuuint64_t)h; gdim[2] = (cuuint64_t)w;
+    gstr[0] = (cuuint64_t)ld * 2 * w; gstr[1] = (cuuint64_t)ld * 2;
+  }
   cuuint32_t box[4] = {(cuuint32_t)KCH, (cuuint32_t)(box_w * sample), (cuuint32_t)(rows * sample), 1};
   cuuint32_t estr[4] = {1, (cuuint32_t)sample, (cuuint32_t)sample, 1};
   CUresult cr = encode(tm, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 4, const_cast<void*>(ptr), gdim, gstr, box, estr,
-                       CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
+                       CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B,
+                       getenv("SRCGAN_B200_L2P128") ? CU_TENSOR_MAP_L2_PROMOTION_L2_128B : CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
                        CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
   if (cr != CUDA_SUCCESS) {
     set_error("%s: cuTensorMapEncodeTiled failed with CUresult %d", what, (int)cr);
@@ -1558,11 +2031,15 @@ static int launch_halo(const CUtensorMap& tmap, const TcArgs& a, cudaStream_t st
 // NHWC bf16 output slice (c channels at ptr, pixel pitch ld) -> tensor map whose box is one kw-stacked tile's
 // output [rows][30 px][c ch]; the shared-memory image is swizzled (128B for 64 channels, 64B for 32).
 static int make_tmap_out(CUtensorMap* tm, const void* ptr, int c, int w, int h, int n, int ld, int rows, const char* what,
-                         int box_w = KW_VX) {
+                         int box_w = KW_VX, bool transposed = false) {
   EncodeTiledFn encode = get_encode_fn();
   SRCGAN_REQUIRE(encode != nullptr, "%s: cuTensorMapEncodeTiled is not available from the driver", what);
   cuuint64_t gdim[4] = {(cuuint64_t)c, (cuuint64_t)w, (cuuint64_t)h, (cuuint64_t)n};
   cuuint64_t gstr[3] = {(cuuint64_t)ld * 2, (cuuint64_t)ld * 2 * w, (cuuint64_t)ld * 2 * w * h};
+  if (transposed) {
+    gdim[1] = (cuuint64_t)h; gdim[2] = (cuuint64_t)w;
+    gstr[0] = (cuuint64_t)ld * 2 * w; gstr[1] = (cuuint64_t)ld * 2;
+  }
   cuuint32_t box[4] = {(cuuint32_t)c, (cuuint32_t)box_w, (cuuint32_t)rows, 1};
   cuuint32_t estr[4] = {1, 1, 1, 1};
   CUresult cr = encode(tm, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 4, const_cast<void*>(ptr), gdim, gstr, box, estr,
@@ -1635,6 +2112,71 @@ static int launch_sweep(const CUtensorMap& tx, const CUtensorMap& ty, SwArgs& a,
   conv3x3_sweep_tc<BN><<<(unsigned)grid, KW_THREADS, C::smem_bytes(a.nchunks, a.na), st>>>(tx, ty, a);
   count_launch();
   return check_launch("conv3x3_sweep_tc");
+}
+
+template <int BN, int CG>
+static int sweep2_ring_depth(int nchunks) {
+  using C = Sw2Cfg<BN, CG>;
+  const long long fixed = (long long)nchunks * C::W_CHUNK_BYTES + SMEM_AUX + 1024;
+  long long na = (SMEM_BUDGET - fixed) / SW_SLAB_STRIDE;
+  return na > SW_MAX_NA ? SW_MAX_NA : (int)(na < 0 ? 0 : na);
+}
+
+// co-resident CTA pairs (clusters of CG) for the kernel's shared-memory footprint; queried once per instantiation
+template <int BN, int CG>
+static int sweep2_max_clusters(size_t smem) {
+  static int cached = 0;
+  if (cached) return cached;
+  int ncl = kNumSMs / CG;
+  if (CG > 1) {
+    cudaLaunchConfig_t cfg = {};
+    cfg.gridDim = dim3((unsigned)kNumSMs); cfg.blockDim = dim3(KW_THREADS); cfg.dynamicSmemBytes = smem;
+    cudaLaunchAttribute at[1];
+    at[0].id = cudaLaunchAttributeClusterDimension;
+    at[0].val.clusterDim.x = CG; at[0].val.clusterDim.y = 1; at[0].val.clusterDim.z = 1;
+    cfg.attrs = at; cfg.numAttrs = 1;
+    int q = 0;
+    if (cudaOccupancyMaxActiveClusters(&q, conv3x3_sweep2_tc<BN, CG>, &cfg) == cudaSuccess && q > 0 && q < ncl) ncl = q;
+    (void)cudaGetLastError();
+  }
+  cached = ncl;
+  return ncl;
+}
+
+template <int BN, int CG>
+static int launch_sweep2(const CUtensorMap& tx, Sw2Args& a, cudaStream_t st) {
+  using C = Sw2Cfg<BN, CG>;
+  a.na = sweep2_ring_depth<BN, CG>(a.nchunks);
+  a.strips_y = (a.h + SW_ROWS - 1) / SW_ROWS;
+  a.strips = a.n * a.strips_y;
+  static bool attr_set = false;
+  if (!attr_set) {
+    SRCGAN_CUDA(cudaFuncSetAttribute(conv3x3_sweep2_tc<BN, CG>, cudaFuncAttributeMaxDynamicSharedMemorySize, SMEM_BUDGET));
+    attr_set = true;
+  }
+  const size_t smem = C::smem_bytes(a.nchunks, a.na);
+  const int ncl_max = sweep2_max_clusters<BN, CG>(SMEM_BUDGET);
+  // segment width: fewest waves x (segment + 2 halo columns) over the co-resident clusters
+  const long long groups = (a.strips + CG - 1) / CG;
+  long long best = -1;
+  for (int ws = 8; ws <= a.w; ++ws) {
+    if (ws != a.w && ws % 2) continue;
+    const long long segs = (a.w + ws - 1) / ws;
+    const long long units = segs * groups;
+    const long long waves = (units + ncl_max - 1) / ncl_max;
+    const long long cost = waves * (ws + 2);
+    if (best < 0 || cost < best) { best = cost; a.wseg = ws; a.segs_x = (int)segs; a.num_units = (int)units; }
+  }
+  const int ncl = a.num_units < ncl_max ? a.num_units : ncl_max;
+  cudaLaunchConfig_t cfg = {};
+  cfg.gridDim = dim3((unsigned)(ncl * CG)); cfg.blockDim = dim3(KW_THREADS); cfg.dynamicSmemBytes = smem; cfg.stream = st;
+  cudaLaunchAttribute at[1];
+  at[0].id = cudaLaunchAttributeClusterDimension;
+  at[0].val.clusterDim.x = CG; at[0].val.clusterDim.y = 1; at[0].val.clusterDim.z = 1;
+  cfg.attrs = at; cfg.numAttrs = 1;
+  SRCGAN_CUDA(cudaLaunchKernelEx(&cfg, conv3x3_sweep2_tc<BN, CG>, tx, a));
+  count_launch();
+  return check_launch("conv3x3_sweep2_tc");
 }
 
 static int dispatch(int bn, int maxt, const CUtensorMap& tmap, const TcArgs& a, cudaStream_t st) {
@@ -1771,7 +2313,50 @@ static int conv_fprop_sweep(const srcgan_conv_params* p, cudaStream_t st) {
   return p->cout == 64 ? tc::launch_sweep<64>(tx, ty, a, st) : tc::launch_sweep<32>(tx, ty, a, st);
 }
 
+// paired column-sweep kernel (cta_group::2): same shapes as the sweep; the halved weight rows make 192 -> 64 resident
+static int sweep2_cg(const srcgan_conv_params* p) {
+  if (p->kh != 3 || p->stride != 1 || p->pad != 1 || (p->cout != 32 && p->cout != 64)) return 0;
+  if (p->y_ld % 8 || ((uintptr_t)p->y) % 16 || p->h < 96 || getenv("SRCGAN_B200_NO_SWEEP2")) return 0;
+  const int nchunks = (p->cin + tc::KCH - 1) / tc::KCH;
+  const char* e = getenv("SRCGAN_B200_SWEEP2_CG");
+  const int want = e ? atoi(e) : 2;
+  // a column's slabs are handed back when its last chunk has been multiplied: the ring holds at least one column + 2 slabs
+  if (want == 2) {
+    if ((p->cout == 64 ? tc::sweep2_ring_depth<64, 2>(nchunks) : tc::sweep2_ring_depth<32, 2>(nchunks)) >= nchunks + 2) return 2;
+    return 0;
+  }
+  return (p->cout == 64 ? tc::sweep2_ring_depth<64, 1>(nchunks) : tc::sweep2_ring_depth<32, 1>(nchunks)) >= nchunks + 2 ? 1 : 0;
+}
+
+static int conv_fprop_sweep2(const srcgan_conv_params* p, int cg, cudaStream_t st) {
+  CUtensorMap tx;
+  // orientation: lanes along the image rows' pixels (sweep over y) when the image is wide enough - a slab is then 130
+  // neighbouring pixels and a warp's stores land on neighbouring pixels - else lanes along a column (sweep over x)
+  bool tr = p->wo >= 96;
+  { const char* e = getenv("SRCGAN_B200_SWEEP_TR"); if (e) tr = (atoi(e) != 0 && p->wo >= 96) || p->ho < 96; }
+  int rc = tc::make_tmap(&tx, p->x, p->cin, p->w, p->h, p->n, p->x_ld, tc::SW_SLAB_ROWS, 1, "conv_fprop_tc(sweep2 x)", 1, tr);
+  if (rc) return rc;
+  tc::Sw2Args a;
+  a.n = p->n; a.cin = p->cin; a.cout = p->cout;
+  a.h = tr ? p->wo : p->ho; a.w = tr ? p->ho : p->wo;              // a.h = lane extent, a.w = sweep extent
+  a.tr = tr ? 1 : 0;
+  a.img_stride = (long long)p->ho * p->wo;
+  a.lane_stride = tr ? 1 : p->wo; a.sweep_stride = tr ? p->wo : 1;
+  a.y = (__nv_bfloat16*)p->y; a.y_ld = p->y_ld;
+  a.nchunks = (p->cin + tc::KCH - 1) / tc::KCH;
+  a.wgt = (const __nv_bfloat16*)p->wgt; a.bias = p->bias;
+  a.act = p->act; a.act_slope = p->act_slope; a.alpha = p->alpha;
+  a.r1 = (const __nv_bfloat16*)p->r1; a.r1_ld = p->r1_ld; a.beta1 = p->beta1;
+  a.r2 = (const __nv_bfloat16*)p->r2; a.r2_ld = p->r2_ld; a.beta2 = p->beta2;
+  a.mask = (const __nv_bfloat16*)p->mask; a.mask_ld = p->mask_ld; a.mask_slope = p->mask_slope;
+  { const char* d = getenv("SRCGAN_B200_DBG"); a.dbg = d ? atoi(d) : 0; }
+  { const char* d = getenv("SRCGAN_B200_PFD"); a.pfd = d ? atoi(d) : 0; }
+  if (cg == 2) return p->cout == 64 ? tc::launch_sweep2<64, 2>(tx, a, st) : tc::launch_sweep2<32, 2>(tx, a, st);
+  return p->cout == 64 ? tc::launch_sweep2<64, 1>(tx, a, st) : tc::launch_sweep2<32, 1>(tx, a, st);
+}
+
 int conv_fprop_tc(const srcgan_conv_params* p, cudaStream_t st) {
+  if (const int cg = sweep2_cg(p)) return conv_fprop_sweep2(p, cg, st);
   if (sweep_ok(p)) return conv_fprop_sweep(p, st);
   if (const int v = kws_variant(p)) return conv_fprop_kws(p, v, st);
   tc::HostPlan hp = tc::fprop_plan(p->kh, p->stride, p->pad);
