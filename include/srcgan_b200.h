@@ -101,6 +101,9 @@ const char* srcgan_version(void);
 const char* srcgan_last_error(void);
 /* number of kernels this library has launched in the calling process (for bench.py's gpu_launches) */
 int64_t srcgan_launch_count(void);
+/* name (a static string) of the kernel the calling thread's most recent call launched last, e.g.
+   "conv3x3_sweep2_tc<32,2>" - bench.py keys its per-kernel timing on it */
+const char* srcgan_last_kernel(void);
 
 int srcgan_pack_weights(const float* w_oihw, int cout, int cin, int kh, int kw, int layout, int dtype,
                         void* out, void* stream);

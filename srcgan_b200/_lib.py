@@ -48,6 +48,7 @@ SIGNATURES = {
     "srcgan_version": (C.c_char_p, []),
     "srcgan_last_error": (C.c_char_p, []),
     "srcgan_launch_count": (_L, []),
+    "srcgan_last_kernel": (C.c_char_p, []),
     "srcgan_pack_weights": (_I, [_P, _I, _I, _I, _I, _I, _I, _P, _P]),
     "srcgan_packed_weight_bytes": (_Z, [_I, _I, _I, _I, _I, _I]),
     "srcgan_conv_fprop": (_I, [C.POINTER(ConvParams), _P]),
@@ -115,3 +116,8 @@ def check(rc: int, what: str = "") -> None:
 
 def launch_count() -> int:
     return int(load().srcgan_launch_count())
+
+
+def last_kernel() -> str:
+    """Name of the kernel this thread's most recent library call launched last."""
+    return load().srcgan_last_kernel().decode()

@@ -10,6 +10,7 @@ namespace srcgan {
 
 static thread_local char g_err[512] = "";
 static std::atomic<int64_t> g_launches{0};
+static thread_local const char* g_last_kernel = "";
 
 void set_error(const char* fmt, ...) {
   va_list ap;
@@ -19,6 +20,7 @@ void set_error(const char* fmt, ...) {
 }
 void count_launch(int n) { g_launches.fetch_add(n, std::memory_order_relaxed); }
 int check_launch(const char* what) {
+  g_last_kernel = what;
   cudaError_t e = cudaGetLastError();
   if (e != cudaSuccess) {
     set_error("%s: kernel launch failed: %s", what, cudaGetErrorString(e));
@@ -98,6 +100,7 @@ extern "C" {
 const char* srcgan_version(void) { return "srcgan_b200 0.1 (sm_100a)"; }
 const char* srcgan_last_error(void) { return g_err; }
 int64_t srcgan_launch_count(void) { return g_launches.load(std::memory_order_relaxed); }
+const char* srcgan_last_kernel(void) { return g_last_kernel; }
 
 size_t srcgan_packed_weight_bytes(int cout, int cin, int kh, int kw, int layout, int dtype) {
   if (layout >= SRCGAN_WL_TC) return packed_weight_bytes_tc(cout, cin, kh, kw, layout);

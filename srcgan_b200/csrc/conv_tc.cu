@@ -88,6 +88,17 @@ __device__ __forceinline__ bool mbar_try_wait(uint64_t* bar, uint32_t parity) {
       : "memory");
   return ok != 0;
 }
+__device__ __forceinline__ bool mbar_test_wait(uint64_t* bar, uint32_t parity) {       // non-blocking peek
+  uint32_t ok;
+  asm volatile(
+      "{\n\t.reg .pred p;\n\t"
+      "mbarrier.test_wait.parity.shared::cta.b64 p, [%1], %2;\n\t"
+      "selp.u32 %0, 1, 0, p;\n\t}"
+      : "=r"(ok)
+      : "r"(smem_u32(bar)), "r"(parity)
+      : "memory");
+  return ok != 0;
+}
 // Bounded wait: a pipeline bug must fault (trap), never hang the GPU box.
 __device__ __forceinline__ void mbar_wait(uint64_t* bar, uint32_t parity) {
   if (mbar_try_wait(bar, parity)) return;
@@ -1039,49 +1050,10 @@ conv3x3_kws_tc(const __grid_constant__ CUtensorMap tmap_x, const __grid_constant
 }
 
 
-// ---------------------------------------------------------------------------------------------
-// v5: column sweep.  Same N-stacking as v4 ([kw2 | kw1 | kw0] weight rows, N = 3*BN, A read once per
-// (kh, k-step)), but the kw shift is applied to the ACCUMULATOR address instead of the data:
-//   * a work unit is a strip of 128 image rows (M = 128, TMEM lane = row) swept over a segment of columns;
-//   * TMEM is a ring of 512/BN output-column accumulators Y_x (BN fp32 columns each);
-//   * the MMAs of INPUT column c (A = the [130 rows][64 ch] slab of that column, kh = +128 B start offset)
-//     accumulate into the three consecutive ring blocks [Y_{c-1} | Y_c | Y_{c+1}]  (N = 3*BN, one instruction);
-//     at the ring wrap / segment ends the same MMA is issued as N = BN or 2*BN pieces (row offset in B).
-//   * blocks are zeroed by the epilogue when it drains them, so every MMA accumulates (no first-touch flag).
-// No shuffles, BN (not 3*BN) TMEM columns read per pixel, and the halo shrinks to 130/128 rows x (seg+2)/seg
-// columns, so L2->SMEM traffic is ~1.05x the compulsory minimum (the haloed 2-D tiles paid 1.4-1.6x).
-// Epilogue: two groups of four warps take alternate output columns: TMEM -> bias / LeakyReLU / residuals / mask
-// -> bf16 -> swizzled staging column [128][BN] -> one TMA tensor store (clipped at the image bottom).
-// ---------------------------------------------------------------------------------------------
-constexpr int SW_ROWS = 128, SW_SLAB_ROWS = SW_ROWS + 2;
+constexpr int SW_ROWS = 128, SW_SLAB_ROWS = SW_ROWS + 2;               // a strip: 128 lanes + one halo row either side
 constexpr int SW_SLAB_BYTES = SW_SLAB_ROWS * 128;                      // 16640
 constexpr int SW_SLAB_STRIDE = (SW_SLAB_BYTES + 1023) / 1024 * 1024;   // 17408
 constexpr int SW_MAX_NA = 10;
-struct SwArgs {
-  int n, cin, cout, h, w;
-  int nchunks, na;
-  int wseg, segs_x, strips_y;
-  long long num_units;
-  const __nv_bfloat16* wgt;
-  const float* bias;
-  int act; float act_slope, alpha;
-  const __nv_bfloat16* r1; int r1_ld; float beta1;
-  const __nv_bfloat16* r2; int r2_ld; float beta2;
-  const __nv_bfloat16* mask; int mask_ld; float mask_slope;
-  int dbg;
-};
-
-template <int BN>
-struct SwCfg {
-  static constexpr int NBLK = 512 / BN;                               // ring of output-column accumulators
-  static constexpr int W_KH_BYTES = 3 * BN * 128;
-  static constexpr int W_CHUNK_BYTES = 3 * W_KH_BYTES;
-  static constexpr int STAGE_BYTES = SW_ROWS * BN * 2;                // 8 KB / 16 KB
-  static constexpr int NSTAGE = 4;                                    // two per epilogue group
-  static size_t smem_bytes(int nchunks, int na) {
-    return (size_t)nchunks * W_CHUNK_BYTES + (size_t)na * SW_SLAB_STRIDE + NSTAGE * STAGE_BYTES + SMEM_AUX + 1024;
-  }
-};
 
 __device__ __forceinline__ void tmem_st32_zero(uint32_t taddr) {
   asm volatile(
@@ -1092,304 +1064,20 @@ __device__ __forceinline__ void tmem_st32_zero(uint32_t taddr) {
 }
 __device__ __forceinline__ void tmem_st_wait() { asm volatile("tcgen05.wait::st.sync.aligned;" ::: "memory"); }
 
-template <int BN>
-__global__ void __launch_bounds__(KW_THREADS, 1)
-conv3x3_sweep_tc(const __grid_constant__ CUtensorMap tmap_x, const __grid_constant__ CUtensorMap tmap_y, const SwArgs a) {
-  using C = SwCfg<BN>;
-  constexpr int NBLK = C::NBLK;
-  extern __shared__ uint8_t smem_raw[];
-  uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~(uintptr_t)1023);
-  uint8_t* smem_w = smem;
-  uint8_t* smem_a = smem_w + (size_t)a.nchunks * C::W_CHUNK_BYTES;
-  uint8_t* smem_o = smem_a + (size_t)a.na * SW_SLAB_STRIDE;
-  uint8_t* aux = smem_o + C::NSTAGE * C::STAGE_BYTES;
-  uint64_t* a_full = reinterpret_cast<uint64_t*>(aux);                 // [SW_MAX_NA]
-  uint64_t* a_empty = a_full + SW_MAX_NA;                              // [SW_MAX_NA]
-  uint64_t* y_full = a_empty + SW_MAX_NA;                              // [NBLK <= 16]
-  uint64_t* y_empty = y_full + 16;                                     // [NBLK <= 16]
-  uint64_t* w_full = y_empty + 16;
-  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(w_full + 1);
-  float* sbias = reinterpret_cast<float*>(aux + 768);
-
-  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-  if (threadIdx.x == 0) {
-    for (int s = 0; s < a.na; ++s) { mbar_init(&a_full[s], 1); mbar_init(&a_empty[s], 1); }
-    for (int s = 0; s < NBLK; ++s) { mbar_init(&y_full[s], 1); mbar_init(&y_empty[s], 128); }
-    mbar_init(w_full, 1);
-    asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
-  }
-  for (int i = threadIdx.x; i < BN; i += KW_THREADS) sbias[i] = (a.bias && i < a.cout) ? a.bias[i] : 0.f;
-  if (warp == 1) {
-    asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(tmem_slot)),
-                 "r"(512u)
-                 : "memory");
-    asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
-  }
-  tc_fence_before();
-  __syncthreads();
-  tc_fence_after();
-  const uint32_t tmem_base = *tmem_slot;
-  if (warp >= 2 && warp < 6) {                                         // the whole accumulator ring starts at zero
-    const uint32_t tq = tmem_base + ((uint32_t)((warp & 3) * 32) << 16);
-#pragma unroll 1
-    for (int cc = 0; cc < 512; cc += 32) tmem_st32_zero(tq + cc);
-    tmem_st_wait();
-  }
-  tc_fence_before();
-  __syncthreads();
-  tc_fence_after();
-
-#define SRCGAN_DECODE_SW_UNIT(u)                                                   \
-  const uint32_t u32_ = (uint32_t)(u);                                             \
-  const uint32_t q_ = u32_ / (uint32_t)a.segs_x;                                   \
-  const int seg = (int)(u32_ - q_ * (uint32_t)a.segs_x);                           \
-  const int img = (int)(q_ / (uint32_t)a.strips_y);                                \
-  const int y0 = (int)(q_ - (uint32_t)img * (uint32_t)a.strips_y) * SW_ROWS;       \
-  const int x_start = seg * a.wseg;                                                \
-  const int x_end = (x_start + a.wseg) < a.w ? (x_start + a.wseg) : a.w;           \
-  const int c_first = x_start > 0 ? x_start - 1 : 0;                               \
-  const int c_last = x_end < a.w ? x_end : a.w - 1;
-
-  if (warp == 0) {
-    // ---- producer: resident weights once, then one column slab per (input column, K chunk)
-    if (elect_one()) {
-      mbar_expect_tx(w_full, (uint32_t)(a.nchunks * C::W_CHUNK_BYTES));
-      for (int i = 0; i < a.nchunks * 3; ++i)
-        bulk_load(a.wgt + (size_t)i * (C::W_KH_BYTES / 2), w_full, smem_w + (size_t)i * C::W_KH_BYTES, C::W_KH_BYTES);
-    }
-    __syncwarp();
-    int as = 0;
-    uint32_t aph = 0;
-    for (long long u = blockIdx.x; u < a.num_units; u += gridDim.x) {
-      SRCGAN_DECODE_SW_UNIT(u)
-      for (int c = c_first; c <= c_last; ++c)
-        for (int k = 0; k < a.nchunks; ++k) {
-          mbar_wait(&a_empty[as], aph ^ 1);
-          if (elect_one()) {
-            if (a.dbg & 4) {
-              mbar_arrive(&a_full[as]);
-            } else {
-              mbar_expect_tx(&a_full[as], SW_SLAB_BYTES);
-              tma_load_4d(&tmap_x, &a_full[as], smem_a + (size_t)as * SW_SLAB_STRIDE, k * KCH, c, y0 - 1, img);
-            }
-          }
-          __syncwarp();
-          if (++as == a.na) { as = 0; aph ^= 1; }
-        }
-    }
-  } else if (warp == 1) {
-    // ---- MMA issuer
-    constexpr uint32_t idesc1 = umma_idesc(TILE_M, BN), idesc2 = umma_idesc(TILE_M, 2 * BN),
-                       idesc3 = umma_idesc(TILE_M, 3 * BN);
-    constexpr uint32_t hi = desc_hi(1024);
-    int as = 0;
-    uint32_t aph = 0;
-    long long base = 0;                                                // running output-column index of this CTA
-    long long tp[6] = {0, 0, 0, 0, 0, 0}, tc0 = 0, ncol = 0;
-    const bool prof = (a.dbg & 32) != 0;
-#define SRCGAN_TICK(k) if (prof) { const long long n_ = clock64(); tp[k] += n_ - tc0; tc0 = n_; }
-    mbar_wait(w_full, 0);
-    for (long long u = blockIdx.x; u < a.num_units; u += gridDim.x) {
-      SRCGAN_DECODE_SW_UNIT(u)
-      (void)img; (void)y0;
-      for (int c = c_first; c <= c_last; ++c) {
-        if (prof) { tc0 = clock64(); ++ncol; }
-        const int xlo = (c - 1) > x_start ? (c - 1) : x_start;         // output columns this input column feeds
-        const int xhi = (c + 1) < (x_end - 1) ? (c + 1) : (x_end - 1);
-        // blocks touched for the first time must have been drained (and zeroed) by the epilogue
-        for (int x = (c == c_first ? xlo : xhi); x <= xhi; ++x) {
-          if (x <= c && c != c_first) continue;
-          const long long oi = base + (x - x_start);
-          mbar_wait(&y_empty[oi % NBLK], (uint32_t)(((oi / NBLK) & 1) ^ 1));
-        }
-        tc_fence_after();
-        SRCGAN_TICK(0)
-        // split [xlo, xhi] at the ring wrap into runs of consecutive blocks
-        const int b0 = (int)((base + (xlo - x_start)) % NBLK);
-        const int cnt = xhi - xlo + 1;
-        const int run0 = (b0 + cnt <= NBLK) ? cnt : (NBLK - b0);
-        const int roff0 = (xlo - (c - 1)) * BN;                        // weight row of the first fed column: (j+1)*BN
-        for (int k = 0; k < a.nchunks; ++k) {
-          const int rem = a.cin - k * KCH;
-          const int ksteps = ((rem >= KCH ? KCH : rem) + 15) >> 4;
-          SRCGAN_TICK(1)
-          mbar_wait(&a_full[as], aph);
-          tc_fence_after();
-          SRCGAN_TICK(2)
-          const uint32_t a_lo = desc_lo(smem_u32(smem_a + (size_t)as * SW_SLAB_STRIDE));
-          const uint32_t b_lo = desc_lo(smem_u32(smem_w + (size_t)k * C::W_CHUNK_BYTES));
-          if (elect_one()) {
-            if (!(a.dbg & 2)) {
-#pragma unroll 1
-              for (int r = 0; r < 2; ++r) {
-                const int n_run = r == 0 ? run0 : cnt - run0;
-                if (n_run <= 0) break;
-                const uint32_t d = tmem_base + (uint32_t)((r == 0 ? b0 : 0) * BN);
-                const uint32_t boff = (uint32_t)((roff0 + (r == 0 ? 0 : run0 * BN)) * 8);     // rows * 128 B >> 4
-                const uint32_t idesc = n_run == 3 ? idesc3 : (n_run == 2 ? idesc2 : idesc1);
-                if (ksteps == 4) {
-#pragma unroll
-                  for (int kh = 0; kh < 3; ++kh)
-#pragma unroll
-                    for (int ks = 0; ks < 4; ++ks)
-                      umma_bf16_w(d, a_lo + (uint32_t)(kh * 8 + ks * 2), hi,
-                                  b_lo + boff + (uint32_t)(kh * (C::W_KH_BYTES >> 4) + ks * 2), hi, idesc, 1u);
-                } else {
-#pragma unroll 1
-                  for (int kh = 0; kh < 3; ++kh)
-                    for (int ks = 0; ks < ksteps; ++ks)
-                      umma_bf16_w(d, a_lo + (uint32_t)(kh * 8 + ks * 2), hi,
-                                  b_lo + boff + (uint32_t)(kh * (C::W_KH_BYTES >> 4) + ks * 2), hi, idesc, 1u);
-                }
-              }
-            }
-            umma_commit(&a_empty[as]);
-          }
-          __syncwarp();
-          SRCGAN_TICK(3)
-          if (++as == a.na) { as = 0; aph ^= 1; }
-        }
-        // output column c-1 is complete once input column c is in; the last input column also completes column c
-        if (elect_one()) {
-          if (c - 1 >= x_start) umma_commit(&y_full[(base + (c - 1 - x_start)) % NBLK]);
-          if (c == c_last && c < x_end) umma_commit(&y_full[(base + (c - x_start)) % NBLK]);
-        }
-        __syncwarp();
-        SRCGAN_TICK(4)
-      }
-      base += x_end - x_start;
-    }
-    if (prof && blockIdx.x == 0 && lane == 0)
-      printf("sweep mma: cols %lld  y_empty %lld  setup %lld  a_full %lld  issue %lld  commit %lld (clk)\n", ncol, tp[0], tp[1],
-             tp[2], tp[3], tp[4]);
-#undef SRCGAN_TICK
-  } else {
-    // ---- epilogue: TMEM lane = image row y0 + q*32 + lane; group g takes the output columns with odd/even ring index
-    const int q = warp & 3;
-    const int g = (warp - 2) >> 2;
-    const bool issuer = threadIdx.x == 64 + g * 128;
-    const uint32_t sbias_addr = smem_u32(sbias);
-    const uint32_t bar_id = 1 + g;
-    const int row = q * 32 + lane;
-    long long base = 0;
-    int stage = 0;
-    long long tp[8] = {0, 0, 0, 0, 0, 0, 0, 0}, tc0 = 0, ncol = 0;
-    const bool prof = (a.dbg & 32) != 0;
-#define SRCGAN_TICK(k) if (prof) { const long long n_ = clock64(); tp[k] += n_ - tc0; tc0 = n_; }
-    for (long long u = blockIdx.x; u < a.num_units; u += gridDim.x) {
-      SRCGAN_DECODE_SW_UNIT(u)
-      (void)c_first; (void)c_last;
-      const int y = y0 + row;
-      const bool row_ok = y < a.h && !(a.dbg & 1);
-      for (int x = x_start; x < x_end; ++x) {
-        const long long oi = base + (x - x_start);
-        if ((int)(oi & 1) != g) continue;
-        const int b = (int)(oi % NBLK);
-        if (prof) { tc0 = clock64(); ++ncol; }
-        const uint32_t so_addr = smem_u32(smem_o + (size_t)(g * 2 + stage) * C::STAGE_BYTES);
-        // the staging column used two columns ago must have been read out by its TMA store
-        if (issuer) asm volatile("cp.async.bulk.wait_group.read 1;" ::: "memory");
-        SRCGAN_TICK(0)
-        asm volatile("bar.sync %0, 128;" ::"r"(bar_id) : "memory");
-        SRCGAN_TICK(1)
-        mbar_wait(&y_full[b], (uint32_t)((oi / NBLK) & 1));
-        tc_fence_after();
-        SRCGAN_TICK(2)
-        const uint32_t taddr = tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)(b * BN);
-        const long long pix = ((long long)img * a.h + y) * a.w + x;
-#pragma unroll 1
-        for (int cb = 0; cb < BN; cb += 32) {
-          uint32_t z[32];
-          tmem_ld32(taddr + cb, z);
-          SRCGAN_TICK(3)
-          tmem_st32_zero(taddr + cb);                                  // the block is reused NBLK columns later
-          float f[32];
-#pragma unroll
-          for (int i = 0; i < 32; i += 4) {
-            const float4 b4 = lds_f4(sbias_addr + (uint32_t)(cb + i) * 4);
-            f[i] = __uint_as_float(z[i]) + b4.x; f[i + 1] = __uint_as_float(z[i + 1]) + b4.y;
-            f[i + 2] = __uint_as_float(z[i + 2]) + b4.z; f[i + 3] = __uint_as_float(z[i + 3]) + b4.w;
-          }
-          if (a.act) {
-#pragma unroll
-            for (int i = 0; i < 32; ++i) f[i] = f[i] > 0.f ? f[i] : f[i] * a.act_slope;
-          }
-          if (a.alpha != 1.f) {
-#pragma unroll
-            for (int i = 0; i < 32; ++i) f[i] *= a.alpha;
-          }
-          if (row_ok) {
-#pragma unroll
-            for (int gq = 0; gq < 4; ++gq) {
-              const int cc = cb + gq * 8;
-              if (a.r1) {
-                float rr[8];
-                unpack8(__ldg(reinterpret_cast<const uint4*>(a.r1 + pix * a.r1_ld + cc)), rr);
-#pragma unroll
-                for (int i = 0; i < 8; ++i) f[gq * 8 + i] = fmaf(a.beta1, rr[i], f[gq * 8 + i]);
-              }
-              if (a.r2) {
-                float rr[8];
-                unpack8(__ldg(reinterpret_cast<const uint4*>(a.r2 + pix * a.r2_ld + cc)), rr);
-#pragma unroll
-                for (int i = 0; i < 8; ++i) f[gq * 8 + i] = fmaf(a.beta2, rr[i], f[gq * 8 + i]);
-              }
-              if (a.mask) {
-                float mm[8];
-                unpack8(__ldg(reinterpret_cast<const uint4*>(a.mask + pix * a.mask_ld + cc)), mm);
-#pragma unroll
-                for (int i = 0; i < 8; ++i) f[gq * 8 + i] *= (mm[i] > 0.f ? 1.f : a.mask_slope);
-              }
-              uint4 o;
-              __nv_bfloat162* oh = reinterpret_cast<__nv_bfloat162*>(&o);
-#pragma unroll
-              for (int i = 0; i < 4; ++i) oh[i] = __floats2bfloat162_rn(f[gq * 8 + 2 * i], f[gq * 8 + 2 * i + 1]);
-              const int j = cc >> 3;                                   // staging = TMA box image [128 rows][BN], swizzled
-              const int js = BN == 64 ? (j ^ (row & 7)) : (j ^ ((row >> 1) & 3));
-              sts_u4(so_addr + (uint32_t)(row * (BN * 2) + js * 16), o);
-            }
-          }
-        }
-        SRCGAN_TICK(4)
-        tmem_st_wait();
-        tc_fence_before();
-        mbar_arrive(&y_empty[b]);                                      // drained and zeroed
-        SRCGAN_TICK(5)
-        asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
-        asm volatile("bar.sync %0, 128;" ::"r"(bar_id) : "memory");
-        SRCGAN_TICK(6)
-        if (issuer && !(a.dbg & 1)) {
-          tma_store_4d(&tmap_y, reinterpret_cast<const void*>(smem_o + (size_t)(g * 2 + stage) * C::STAGE_BYTES), 0, x, y0,
-                       img);
-          asm volatile("cp.async.bulk.commit_group;" ::: "memory");
-        }
-        stage ^= 1;
-        SRCGAN_TICK(7)
-      }
-      base += x_end - x_start;
-    }
-    if (issuer) asm volatile("cp.async.bulk.wait_group 0;" ::: "memory");
-    if (prof && blockIdx.x == 0 && lane == 0)
-      printf("sweep epi warp %d: cols %lld  wait_rd %lld  bar %lld  y_full %lld  tmem_ld %lld  math+sts %lld  st_wait+arrive %lld  fence+bar %lld  store %lld (clk)\n",
-             warp, ncol, tp[0], tp[1], tp[2], tp[3], tp[4], tp[5], tp[6], tp[7]);
-#undef SRCGAN_TICK
-  }
-#undef SRCGAN_DECODE_SW_UNIT
-  tc_fence_before();
-  __syncthreads();
-  if (warp == 1) {
-    asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "r"(512u) : "memory");
-  }
-}
-
-
 // ---------------------------------------------------------------------------------------------
-// v6: paired column sweep.  The v5 sweep with two changes that remove its shared-memory ceiling
-// (SS-mode MMAs re-read A (4 KB) and B (N x 32 B) for every instruction; at 128 B/clk/SM an N = 96 MMA is
-// SMEM-bound at 56 clk against 48 clk of math, and the slab / staging traffic comes on top):
+// v5: paired sweep.  Same N-stacking as v4 (three taps of one direction stacked into N = 3*BN, A read once per
+// (tap of the other direction, k-step)), but the stacked taps' shift is applied to the ACCUMULATOR address, not the data:
+//   * a work unit is a strip of 128 lanes (image rows, or the pixels of an image row: see `tr`) swept over a segment
+//     of the other image dimension ("columns" below); TMEM is a ring of 512/BN accumulator blocks, one per output column;
+//   * the MMAs of INPUT column c (A = its [130 lanes][64 ch] slab, lane tap = +128 B start offset) accumulate into the
+//     three consecutive blocks [Y_{c-1} | Y_c | Y_{c+1}] with one N = 3*BN instruction;
+//   * blocks are zeroed by the epilogue when it drains them, so every MMA accumulates (no first-touch flag);
+//   * no shuffles, BN TMEM columns read per pixel, halo = 130/128 lanes x (seg+2)/seg columns.
+// SS-mode MMAs re-read A (4 KB) and B (N x 32 B) for every instruction; at 128 B/clk/SM an N = 96 MMA is SMEM-bound at
+// 56 clk against 48 clk of math (scripts/exp/exp_mma_rate.cu).  Two design points follow:
 //   * cta_group::2 - a CTA pair sweeps two 128-row strips in lock step (M = 256).  Each CTA feeds its own A slab
 //     but only HALF of the stacked weight rows (N/2 x 32 B per MMA; measured 49 clk at N = 96, 96 clk at N = 192,
-//     scripts/exp/exp_pair.cu), so the weights of 192->64 (221 KB in v5) fit as 2 x 110 KB and every layer of a
+//     scripts/exp/exp_pair.cu), so the weights of 192->64 (221 KB stacked) fit as 2 x 110 KB and every layer of a
 //     dense block runs on this kernel.  CG = 1 instantiations exist for A/B tests.
 //   * a ring without split instructions - TMEM faults when base + N crosses column 512 (exp_pair.cu), and a
 //     2-CTA instruction cannot be cut at the ring wrap (each CTA would need a different half of B).  The ring is
@@ -1607,11 +1295,15 @@ conv3x3_sweep2_tc(const __grid_constant__ CUtensorMap tmap_x, const Sw2Args a) {
       uint32_t aph = 0;
       int k = 0;                                                       // position in the lap
       uint32_t lap_par = 0;
+      bool ye_ready = false, af_ready = false;
       mbar_wait(w_full, 0);
       if (CG == 2) mbar_wait(w_pair, 0);
       const uint32_t w_lo = desc_lo(smem_u32(smem_w));
       long long tp[4] = {0, 0, 0, 0}, tc0 = 0, ncol = 0;
       const bool prof = (a.dbg & 32) != 0;
+      const long long t_begin = clock64();
+      unsigned long long g_begin;
+      asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(g_begin));
 #define SRCGAN_TICK(i) if (prof) { const long long n_ = clock64(); tp[i] += n_ - tc0; tc0 = n_; }
       for (int u = cid; u < a.num_units; u += ncl) {
         const int seg = u % a.segs_x;
@@ -1620,15 +1312,16 @@ conv3x3_sweep2_tc(const __grid_constant__ CUtensorMap tmap_x, const Sw2Args a) {
         for (int c = x_start - 1; c <= x_end; ++c) {
           if (prof) { tc0 = clock64(); ++ncol; }
           // blocks touched for the first time in this lap must have been drained (and zeroed) by the epilogues
+          // (the states of this column's barriers were peeked while the previous column's MMAs were being issued)
           if (k == 0) { mbar_wait(&y_empty[0], lap_par ^ 1); mbar_wait(&y_empty[1], lap_par ^ 1); }
-          mbar_wait(&y_empty[k + 2], lap_par ^ 1);
+          if (!ye_ready) mbar_wait(&y_empty[k + 2], lap_par ^ 1);
           tc_fence_after();
           const uint32_t d = tmem_base + (uint32_t)(k * BN);
           SRCGAN_TICK(0)
           for (int kc = 0; kc < a.nchunks; ++kc) {
             const int rem = a.cin - kc * KCH;
             const int ksteps = ((rem >= KCH ? KCH : rem) + 15) >> 4;     // channels past cin are TMA zero-filled
-            mbar_wait(&a_full[as], aph);
+            if (!af_ready) mbar_wait(&a_full[as], aph);
             tc_fence_after();
             SRCGAN_TICK(1)
             const uint32_t a_lo = desc_lo(smem_u32(smem_a + (size_t)as * SW_SLAB_STRIDE));
@@ -1667,14 +1360,25 @@ conv3x3_sweep2_tc(const __grid_constant__ CUtensorMap tmap_x, const Sw2Args a) {
               }
             }
             __syncwarp();
-            SRCGAN_TICK(2)
             if (++as == a.na) { as = 0; aph ^= 1; }
+            // peek the next slab's barrier (and, after the last chunk, the next column's block) while the tensor pipe works
+            af_ready = mbar_test_wait(&a_full[as], aph);
+            if (kc == a.nchunks - 1) {
+              const int kn = k + 1 == RUN ? 0 : k + 1;
+              ye_ready = mbar_test_wait(&y_empty[kn + 2], (k + 1 == RUN ? lap_par ^ 1 : lap_par) ^ 1);
+            }
+            SRCGAN_TICK(2)
           }
           if (++k == RUN) { k = 0; lap_par ^= 1; }
         }
       }
-      if (prof && blockIdx.x == 0 && lane == 0)
-        printf("sweep2 mma: cols %lld  y_empty %lld  a_full %lld  issue+commit %lld (clk/col)\n", ncol, tp[0] / ncol, tp[1] / ncol, tp[2] / ncol);
+      if (prof && (blockIdx.x % 16 == 0 || blockIdx.x == gridDim.x - 2) && lane == 0) {
+        unsigned long long g_end;
+        asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(g_end));
+        printf("sweep2 mma (cta %d of %d, units %d, wseg %d): cols %lld  y_empty %lld  a_full %lld  issue+commit %lld (clk/col)  loop total %lld clk = %llu ns, began at %llu us\n",
+               (int)blockIdx.x, (int)gridDim.x, a.num_units, a.wseg, ncol, tp[0] / ncol, tp[1] / ncol, tp[2] / ncol, clock64() - t_begin, g_end - g_begin,
+               (g_begin / 1000ull) % 1000000ull);
+      }
 #undef SRCGAN_TICK
     }
   } else {
@@ -1896,7 +1600,7 @@ static EncodeTiledFn get_encode_fn() {
 // NHWC bf16 tensor (c channels at ptr, pixel pitch ld) -> tensor map whose box is the sampled slab
 // [rows][8 px][64 ch]; sample = 1 (dense) or 2 (every other pixel, for stride-2 convolutions).
 static int make_tmap(CUtensorMap* tm, const void* ptr, int c, int w, int h, int n, int ld, int rows, int sample,
-                     const char* what, int box_w = TILE_W, bool transposed = false) {
+                     const char* what, int box_w = TILE_W, bool transposed = false, bool promote256 = true) {
   EncodeTiledFn encode = get_encode_fn();
   SRCGAN_REQUIRE(encode != nullptr, "%s: cuTensorMapEncodeTiled is not available from the driver", what);
   cuuint64_t gdim[4] = {(cuuint64_t)c, (cuuint64_t)w, (cuuint64_t)h, (cuuint64_t)n};
@@ -1909,7 +1613,7 @@ static int make_tmap(CUtensorMap* tm, const void* ptr, int c, int w, int h, int 
   cuuint32_t estr[4] = {1, (cuuint32_t)sample, (cuuint32_t)sample, 1};
   CUresult cr = encode(tm, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 4, const_cast<void*>(ptr), gdim, gstr, box, estr,
                        CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B,
-                       getenv("SRCGAN_B200_L2P128") ? CU_TENSOR_MAP_L2_PROMOTION_L2_128B : CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
+                       promote256 ? CU_TENSOR_MAP_L2_PROMOTION_L2_256B : CU_TENSOR_MAP_L2_PROMOTION_L2_128B,
                        CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
   if (cr != CUDA_SUCCESS) {
     set_error("%s: cuTensorMapEncodeTiled failed with CUresult %d", what, (int)cr);
@@ -2010,7 +1714,7 @@ static int launch(const CUtensorMap& tmap, const TcArgs& a, cudaStream_t st) {
   long long grid = a.num_tiles < kNumSMs ? a.num_tiles : kNumSMs;
   conv_igemm_tc<BN, MAXT><<<(unsigned)grid, NUM_THREADS, C::SMEM_BYTES, st>>>(tmap, a);
   count_launch();
-  return check_launch("conv_igemm_tc");
+  return check_launch(BN == 128 ? "conv_igemm_tc<128>" : (BN == 64 ? "conv_igemm_tc<64>" : "conv_igemm_tc<32>"));
 }
 
 template <int BN>
@@ -2024,7 +1728,7 @@ static int launch_halo(const CUtensorMap& tmap, const TcArgs& a, cudaStream_t st
   long long grid = a.num_tiles < kNumSMs ? a.num_tiles : kNumSMs;
   conv3x3_halo_tc<BN><<<(unsigned)grid, NUM_THREADS, C::SMEM_BYTES, st>>>(tmap, a);
   count_launch();
-  return check_launch("conv3x3_halo_tc");
+  return check_launch(BN == 64 ? "conv3x3_halo_tc<64>" : (BN == 32 ? "conv3x3_halo_tc<32>" : "conv3x3_halo_tc<16>"));
 }
 
 
@@ -2076,43 +1780,9 @@ static int launch_kws(const CUtensorMap& tx, const CUtensorMap& ty, KwArgs& a, c
   long long grid = a.num_tiles < kNumSMs ? a.num_tiles : kNumSMs;
   conv3x3_kws_tc<BN, R><<<(unsigned)grid, KW_THREADS, C::smem_bytes(a.nchunks, a.na), st>>>(tx, ty, a);
   count_launch();
-  return check_launch("conv3x3_kws_tc");
+  return check_launch(BN == 64 ? "conv3x3_kws_tc<64>" : "conv3x3_kws_tc<32>");
 }
 
-
-template <int BN>
-static int sweep_ring_depth(int nchunks) {
-  using C = SwCfg<BN>;
-  const long long fixed = (long long)nchunks * C::W_CHUNK_BYTES + C::NSTAGE * C::STAGE_BYTES + SMEM_AUX + 1024;
-  long long na = (SMEM_BUDGET - fixed) / SW_SLAB_STRIDE;
-  return na > SW_MAX_NA ? SW_MAX_NA : (int)(na < 0 ? 0 : na);
-}
-
-template <int BN>
-static int launch_sweep(const CUtensorMap& tx, const CUtensorMap& ty, SwArgs& a, cudaStream_t st) {
-  using C = SwCfg<BN>;
-  a.na = sweep_ring_depth<BN>(a.nchunks);
-  a.strips_y = (a.h + SW_ROWS - 1) / SW_ROWS;
-  // segment width: fewest CTA waves x (segment + 2 halo columns)
-  long long best = -1;
-  const int cand[4] = {16, 32, 64, a.w};
-  for (int i = 0; i < 4; ++i) {
-    const int ws = cand[i] < a.w ? cand[i] : a.w;
-    const long long segs = (a.w + ws - 1) / ws;
-    const long long units = segs * a.strips_y * a.n;
-    const long long cost = ((units + kNumSMs - 1) / kNumSMs) * (ws + 2);
-    if (best < 0 || cost < best) { best = cost; a.wseg = ws; a.segs_x = (int)segs; a.num_units = units; }
-  }
-  static bool attr_set = false;
-  if (!attr_set) {
-    SRCGAN_CUDA(cudaFuncSetAttribute(conv3x3_sweep_tc<BN>, cudaFuncAttributeMaxDynamicSharedMemorySize, SMEM_BUDGET));
-    attr_set = true;
-  }
-  long long grid = a.num_units < kNumSMs ? a.num_units : kNumSMs;
-  conv3x3_sweep_tc<BN><<<(unsigned)grid, KW_THREADS, C::smem_bytes(a.nchunks, a.na), st>>>(tx, ty, a);
-  count_launch();
-  return check_launch("conv3x3_sweep_tc");
-}
 
 template <int BN, int CG>
 static int sweep2_ring_depth(int nchunks) {
@@ -2136,7 +1806,9 @@ static int sweep2_max_clusters(size_t smem) {
     at[0].val.clusterDim.x = CG; at[0].val.clusterDim.y = 1; at[0].val.clusterDim.z = 1;
     cfg.attrs = at; cfg.numAttrs = 1;
     int q = 0;
-    if (cudaOccupancyMaxActiveClusters(&q, conv3x3_sweep2_tc<BN, CG>, &cfg) == cudaSuccess && q > 0 && q < ncl) ncl = q;
+    const cudaError_t qe = cudaOccupancyMaxActiveClusters(&q, conv3x3_sweep2_tc<BN, CG>, &cfg);
+    if (getenv("SRCGAN_B200_DBG")) fprintf(stderr, "sweep2<%d,%d>: cudaOccupancyMaxActiveClusters -> %s, %d clusters\n", BN, CG, cudaGetErrorString(qe), q);
+    if (qe == cudaSuccess && q > 0 && q < ncl) ncl = q;
     (void)cudaGetLastError();
   }
   cached = ncl;
@@ -2176,7 +1848,8 @@ static int launch_sweep2(const CUtensorMap& tx, Sw2Args& a, cudaStream_t st) {
   cfg.attrs = at; cfg.numAttrs = 1;
   SRCGAN_CUDA(cudaLaunchKernelEx(&cfg, conv3x3_sweep2_tc<BN, CG>, tx, a));
   count_launch();
-  return check_launch("conv3x3_sweep2_tc");
+  return check_launch(BN == 64 ? (CG == 2 ? "conv3x3_sweep2_tc<64,2>" : "conv3x3_sweep2_tc<64,1>")
+                               : (CG == 2 ? "conv3x3_sweep2_tc<32,2>" : "conv3x3_sweep2_tc<32,1>"));
 }
 
 static int dispatch(int bn, int maxt, const CUtensorMap& tmap, const TcArgs& a, cudaStream_t st) {
@@ -2287,32 +1960,6 @@ static int conv_fprop_kws(const srcgan_conv_params* p, int variant, cudaStream_t
   return variant == 322 ? tc::launch_kws<32, 2>(tx, ty, a, st) : tc::launch_kws<32, 1>(tx, ty, a, st);
 }
 
-// column-sweep kernel: 3x3 stride 1 pad 1, cout 32 / 64, weights resident, images at least one 128-row strip tall
-static bool sweep_ok(const srcgan_conv_params* p) {
-  if (p->kh != 3 || p->stride != 1 || p->pad != 1 || (p->cout != 32 && p->cout != 64)) return false;
-  if (p->y_ld % 8 || ((uintptr_t)p->y) % 16 || p->h < 96 || getenv("SRCGAN_B200_NO_SWEEP")) return false;
-  const int nchunks = (p->cin + tc::KCH - 1) / tc::KCH;
-  return (p->cout == 64 ? tc::sweep_ring_depth<64>(nchunks) : tc::sweep_ring_depth<32>(nchunks)) >= 4;
-}
-
-static int conv_fprop_sweep(const srcgan_conv_params* p, cudaStream_t st) {
-  CUtensorMap tx, ty;
-  int rc = tc::make_tmap(&tx, p->x, p->cin, p->w, p->h, p->n, p->x_ld, tc::SW_SLAB_ROWS, 1, "conv_fprop_tc(sweep x)", 1);
-  if (rc) return rc;
-  rc = tc::make_tmap_out(&ty, p->y, p->cout, p->wo, p->ho, p->n, p->y_ld, tc::SW_ROWS, "conv_fprop_tc(sweep y)", 1);
-  if (rc) return rc;
-  tc::SwArgs a;
-  a.n = p->n; a.cin = p->cin; a.cout = p->cout; a.h = p->ho; a.w = p->wo;
-  a.nchunks = (p->cin + tc::KCH - 1) / tc::KCH;
-  a.wgt = (const __nv_bfloat16*)p->wgt; a.bias = p->bias;
-  a.act = p->act; a.act_slope = p->act_slope; a.alpha = p->alpha;
-  a.r1 = (const __nv_bfloat16*)p->r1; a.r1_ld = p->r1_ld; a.beta1 = p->beta1;
-  a.r2 = (const __nv_bfloat16*)p->r2; a.r2_ld = p->r2_ld; a.beta2 = p->beta2;
-  a.mask = (const __nv_bfloat16*)p->mask; a.mask_ld = p->mask_ld; a.mask_slope = p->mask_slope;
-  { const char* d = getenv("SRCGAN_B200_DBG"); a.dbg = d ? atoi(d) : 0; }
-  return p->cout == 64 ? tc::launch_sweep<64>(tx, ty, a, st) : tc::launch_sweep<32>(tx, ty, a, st);
-}
-
 // paired column-sweep kernel (cta_group::2): same shapes as the sweep; the halved weight rows make 192 -> 64 resident
 static int sweep2_cg(const srcgan_conv_params* p) {
   if (p->kh != 3 || p->stride != 1 || p->pad != 1 || (p->cout != 32 && p->cout != 64)) return 0;
@@ -2334,7 +1981,8 @@ static int conv_fprop_sweep2(const srcgan_conv_params* p, int cg, cudaStream_t s
   // neighbouring pixels and a warp's stores land on neighbouring pixels - else lanes along a column (sweep over x)
   bool tr = p->wo >= 96;
   { const char* e = getenv("SRCGAN_B200_SWEEP_TR"); if (e) tr = (atoi(e) != 0 && p->wo >= 96) || p->ho < 96; }
-  int rc = tc::make_tmap(&tx, p->x, p->cin, p->w, p->h, p->n, p->x_ld, tc::SW_SLAB_ROWS, 1, "conv_fprop_tc(sweep2 x)", 1, tr);
+  int rc = tc::make_tmap(&tx, p->x, p->cin, p->w, p->h, p->n, p->x_ld, tc::SW_SLAB_ROWS, 1, "conv_fprop_tc(sweep2 x)", 1, tr,
+                         /*promote256=*/p->cin % 128 == 0 && p->x_ld == p->cin);
   if (rc) return rc;
   tc::Sw2Args a;
   a.n = p->n; a.cin = p->cin; a.cout = p->cout;
@@ -2357,7 +2005,6 @@ static int conv_fprop_sweep2(const srcgan_conv_params* p, int cg, cudaStream_t s
 
 int conv_fprop_tc(const srcgan_conv_params* p, cudaStream_t st) {
   if (const int cg = sweep2_cg(p)) return conv_fprop_sweep2(p, cg, st);
-  if (sweep_ok(p)) return conv_fprop_sweep(p, st);
   if (const int v = kws_variant(p)) return conv_fprop_kws(p, v, st);
   tc::HostPlan hp = tc::fprop_plan(p->kh, p->stride, p->pad);
   const bool halo = p->kh == 3 && p->stride == 1 && (p->cout <= 16 || p->cout == 32 || p->cout == 64);
@@ -2637,7 +2284,7 @@ static int launch(const CUtensorMap& tx, const CUtensorMap& tg, const WgArgs& a,
   const unsigned grid = (unsigned)(a.plan.nloads * a.cblocks * a.nblocks * a.splits);
   conv_wgrad_tc_kernel<BN, KH><<<grid, NUM_THREADS, C::SMEM_BYTES, st>>>(tx, tg, a);
   count_launch();
-  return check_launch("conv_wgrad_tc");
+  return check_launch(BN == 128 ? "conv_wgrad_tc<128>" : "conv_wgrad_tc<64>");
 }
 }  // namespace tcw
 
@@ -2851,7 +2498,7 @@ static int launch3(const CUtensorMap& tx, const CUtensorMap& tg, const Wg3Args& 
   const unsigned grid = (unsigned)(a.ngroups * a.cblocks * a.nblocks * a.splits);
   conv3x3_wgrad_halo_tc<BN><<<grid, NUM_THREADS, C::SMEM_BYTES, st>>>(tx, tg, a);
   count_launch();
-  return check_launch("conv3x3_wgrad_halo_tc");
+  return check_launch(BN == 64 ? "conv3x3_wgrad_halo_tc<64>" : "conv3x3_wgrad_halo_tc<32>");
 }
 }  // namespace tcw3
 

@@ -144,12 +144,11 @@ class _Timed:
         self.on = timer.enabled
         if self.on:
             eng = {ENGINE_SIMT: "simt", ENGINE_TC: "tc", ENGINE_AUTO: "auto"}[p.engine]
-            self.key = "conv_%s_%s" % (kind, eng)
-            if p.engine == ENGINE_TC and p.kh == 3 and p.stride == 1:      # name the kernel that actually runs
-                if kind == "fprop" and p.cout in (32, 64):
-                    self.key = "conv3x3_halo_tc<%d>" % p.cout
-                elif kind == "wgrad" and (p.cout == 32 or p.cout % 64 == 0):
-                    self.key = "conv3x3_wgrad_halo_tc<%d>" % (64 if p.cout % 64 == 0 else 32)
+            self.key = "conv_%s_%s" % (kind, eng)          # replaced in __exit__ by the kernel the library launched
+            self.tc = p.engine == ENGINE_TC and kind != "wgrad"
+            if p.engine == ENGINE_TC and kind == "wgrad" and p.kh == 3 and p.stride == 1 and (p.cout == 32 or p.cout % 64 == 0):
+                # wgrad = the tcgen05 kernel + a split reduce; name the former (csrc/conv_tc.cu: wgrad_halo_ok)
+                self.key = "conv3x3_wgrad_halo_tc<%d>" % (64 if p.cout % 64 == 0 else 32)
             self.flops = 2.0 * p.n * p.ho * p.wo * p.cin * p.cout * p.kh * p.kw
 
     def __enter__(self):
@@ -162,6 +161,10 @@ class _Timed:
     def __exit__(self, *exc):
         if self.on:
             self.b.record()
+            if self.tc and exc[0] is None:
+                name = _lib.last_kernel()
+                if name.startswith("conv"):
+                    self.key = name
             timer.records.append((self.key, self.flops, self.a, self.b))
         return False
 
