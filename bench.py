@@ -201,11 +201,14 @@ def run_ours(args):
     sampler = ClockSampler(local_rank)
     if rank == 0:
         sampler.start()
+    launches0 = _lib.launch_count()
+    ms = timed(step_resident, args.steps)                              # the reported value: no per-launch instrumentation
+    launches = _lib.launch_count() - launches0
+    # per-kernel timing for the roofline record: the same steps again with CUDA events around every convolution launch
+    # (the event records cost ~8 % of a step, so this pass is separate and its wall time is only the share denominator)
     ops.timer.enabled = True
     ops.timer.reset()
-    launches0 = _lib.launch_count()
-    ms = timed(step_resident, args.steps)
-    launches = _lib.launch_count() - launches0
+    ms_instr = timed(step_resident, args.steps)
     ops.timer.enabled = False
     ksum = ops.timer.summary()
     ops.timer.reset()
@@ -236,7 +239,8 @@ def run_ours(args):
                                 "vs 268 MB algorithmic)",
                 "peak_source": peaks["source"],
                 "launches_per_step": d["launches"] / args.steps, "avg_launch_ms": d["ms"] / d["launches"],
-                "share_of_step": d["ms"] / ms, "conv_share_of_step": conv_ms / ms,
+                "share_of_step": d["ms"] / ms_instr, "conv_share_of_step": conv_ms / ms_instr,
+                "instrumented_ms_per_step": ms_instr / args.steps,
                 "families": {k: {"ms_per_step": v["ms"] / args.steps, "tflops": v["flops"] / (v["ms"] * 1e-3) / 1e12,
                                  "launches_per_step": v["launches"] / args.steps} for k, v in sorted(ksum.items())}}
     line = {

@@ -2502,6 +2502,219 @@ static int launch3(const CUtensorMap& tx, const CUtensorMap& tg, const Wg3Args& 
 }
 }  // namespace tcw3
 
+
+// ---------------------------------------------------------------------------------------------
+// tcgen05 wgrad, kw-stacked (3x3 stride 1 pad 1, cout 32 / 64 - the dense-block and 64->64 layers):
+//   dW[kh][kw][ci][co] = sum_q X[q.y + kh - 1][q.x][ci] * dY[q.y][q.x - (kw - 1)][co]
+// The horizontal tap moves from X to dY, where it can be stacked into N: the MN-major B operand is an OVERLAPPING view
+// of the dY slab [rows][18 px][32 ch] - N atom j (32 channels = one 64-byte SWIZZLE_64B row) starts one pixel after atom
+// j-1 (LBO = 64 B < atom size; verified on hardware, scripts/exp/exp_wstack.cu) - so one instruction computes
+//   D_kh[ci][(j, co)] += X^T[ci][16 px] * [dY[px-1] | dY[px] | dY[px+1]][co]           (N = 96, kw = 2 - j)
+// and a 128-pixel tile costs 3 x 8 MMAs of N = 96 (56 clk each, SMEM-bound) instead of 9 x 8 of N = 32 (40 clk each).
+// A = X^T straight from the NHWC slab (MN-major, M = 128 input channels = two 64-channel atoms, vertical tap = slab
+// row offset).  Channel blocks of <= 64 channels stack two vertical taps into M instead (second atom = the same
+// slab two... one row further down), so M = 128 is always used.  cout = 64 runs as two independent 32-channel halves.
+// One CTA per (channel block, cout half, pixel split); fp32 partials [split][tap][ci][co] + the fixed-order reduce.
+// ---------------------------------------------------------------------------------------------
+namespace tcw4 {
+using namespace tc;
+
+constexpr int WS_TH = 8, WS_TW = 16;                                  // pixel tile: 8 rows x 16 px = 8 k-steps of one row each
+constexpr int WS_X_ROWS = WS_TH + 2;
+constexpr int WS_X_ATOM = WS_X_ROWS * WS_TW * 128;                    // 20480: [10 rows][16 px][64 ch]
+constexpr int WS_G_W = WS_TW + 2;
+constexpr int WS_G_BYTES = WS_TH * WS_G_W * 64;                       // 9216:  [8 rows][18 px][32 ch]
+constexpr int WS_STAGE = 2 * WS_X_ATOM + WS_G_BYTES;                  // 50176
+constexpr int WS_STAGES = (SMEM_BUDGET - SMEM_AUX - 1024) / WS_STAGE; // 4
+constexpr int WS_SMEM = WS_STAGES * WS_STAGE + SMEM_AUX + 1024;
+static_assert(WS_STAGES >= 3, "wgrad pipeline too shallow");
+
+struct Wg4Args {
+  int n, ho, wo, cin, cout;
+  int cblocks, nblocks, splits;
+  int tiles_x, tiles_y;
+  long long num_tiles, tiles_per_split;
+  float* part;
+};
+
+__host__ __device__ constexpr uint32_t desc_hi_sw64(uint32_t sbo_bytes) {
+  return (sbo_bytes >> 4) | (1u << 14) | (4u << 29);                  // SBO, descriptor version 1, SWIZZLE_64B
+}
+
+__global__ void __launch_bounds__(NUM_THREADS, 1)
+conv3x3_wgrad_stack_tc(const __grid_constant__ CUtensorMap tmap_x, const __grid_constant__ CUtensorMap tmap_g, const Wg4Args a) {
+  extern __shared__ uint8_t smem_raw[];
+  uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~(uintptr_t)1023);
+  uint8_t* aux = smem + WS_STAGES * WS_STAGE;
+  uint64_t* full_bar = reinterpret_cast<uint64_t*>(aux);
+  uint64_t* empty_bar = full_bar + WS_STAGES;
+  uint64_t* done_bar = empty_bar + WS_STAGES;
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(done_bar + 1);
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+
+  if (threadIdx.x == 0) {
+    for (int s = 0; s < WS_STAGES; ++s) { mbar_init(&full_bar[s], 1); mbar_init(&empty_bar[s], 1); }
+    mbar_init(done_bar, 1);
+    asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+  }
+  if (warp == 1) {
+    asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(tmem_slot)), "r"(512u)
+                 : "memory");
+    asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
+  }
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  const uint32_t tmem_base = *tmem_slot;
+
+  int b = blockIdx.x;
+  const int split = b % a.splits; b /= a.splits;
+  const int nb = b % a.nblocks; b /= a.nblocks;
+  const int cb = b;
+  const int c_rem = a.cin - cb * 128;
+  const bool paired = c_rem <= 64;                                   // one 64-channel atom: M = (tap kh | tap kh + 1)
+  const int ngroups = paired ? 2 : 3;                                // accumulators of 96 columns
+  const long long t_beg = (long long)split * a.tiles_per_split;
+  long long t_end = t_beg + a.tiles_per_split;
+  if (t_end > a.num_tiles) t_end = a.num_tiles;
+  const uint32_t stage_tx = (uint32_t)((paired ? 1 : 2) * WS_X_ATOM + WS_G_BYTES);
+
+  if (warp == 0) {
+    int stage = 0;
+    uint32_t phase = 0;
+    for (long long t = t_beg; t < t_end; ++t) {
+      long long r = t;
+      const int bx = (int)(r % a.tiles_x); r /= a.tiles_x;
+      const int by = (int)(r % a.tiles_y);
+      const int img = (int)(r / a.tiles_y);
+      const int x0 = bx * WS_TW, y0 = by * WS_TH;
+      mbar_wait(&empty_bar[stage], phase ^ 1);
+      uint8_t* sx = smem + stage * WS_STAGE;
+      if (elect_one()) {
+        mbar_expect_tx(&full_bar[stage], stage_tx);
+        tma_load_4d(&tmap_x, &full_bar[stage], sx, cb * 128, x0, y0 - 1, img);
+        if (!paired) tma_load_4d(&tmap_x, &full_bar[stage], sx + WS_X_ATOM, cb * 128 + 64, x0, y0 - 1, img);
+        tma_load_4d(&tmap_g, &full_bar[stage], sx + 2 * WS_X_ATOM, nb * 32, x0 - 1, y0, img);
+      }
+      __syncwarp();
+      if (++stage == WS_STAGES) { stage = 0; phase ^= 1; }
+    }
+  } else if (warp == 1) {
+    constexpr uint32_t idesc = tcw::umma_idesc_mn(128, 96);
+    constexpr uint32_t a_hi = desc_hi(1024), g_hi = desc_hi_sw64(512);  // 8 pixels of a row: 8 x 128 B resp. 8 x 64 B
+    constexpr uint32_t ROW_A = WS_TW * 128, ROW_G = WS_G_W * 64;        // slab row pitches: 2048 B, 1152 B
+    int stage = 0;
+    uint32_t phase = 0;
+    uint32_t accumulate = 0;
+    for (long long t = t_beg; t < t_end; ++t) {
+      mbar_wait(&full_bar[stage], phase);
+      tc_fence_after();
+      const uint32_t sx = smem_u32(smem + stage * WS_STAGE);
+      const uint32_t sg = sx + 2 * WS_X_ATOM;
+      if (elect_one()) {
+        // A: LBO = distance of the second 64-row half of M (the other channel atom, or the next vertical tap's row)
+        const uint32_t a_lo = desc_lo(sx, paired ? ROW_A : (uint32_t)WS_X_ATOM);
+        const uint32_t g_lo = desc_lo(sg, 64);                          // N atoms one pixel (64 B) apart
+        for (int g = 0; g < ngroups; ++g) {
+          const int kh0 = paired ? 2 * g : g;                           // vertical tap of the first half of M
+          const uint32_t tmem_d = tmem_base + (uint32_t)(g * 96);
+#pragma unroll
+          for (int r = 0; r < WS_TH; ++r)
+            umma_bf16_w(tmem_d, a_lo + (uint32_t)(((r + kh0) * ROW_A) >> 4), a_hi, g_lo + (uint32_t)((r * ROW_G) >> 4), g_hi, idesc,
+                        accumulate | (uint32_t)(r > 0));
+        }
+        umma_commit(&empty_bar[stage]);
+      }
+      __syncwarp();
+      accumulate = 1;
+      if (++stage == WS_STAGES) { stage = 0; phase ^= 1; }
+    }
+    if (elect_one()) umma_commit(done_bar);
+    __syncwarp();
+  } else {
+    const int q = warp & 3;
+    const int row = q * 32 + lane;
+    mbar_wait(done_bar, 0);
+    tc_fence_after();
+    const bool has_work = t_end > t_beg;
+#pragma unroll 1
+    for (int g = 0; g < ngroups; ++g) {
+      int kh, ci;
+      if (paired) { kh = 2 * g + (row >> 6); ci = cb * 128 + (row & 63); }
+      else { kh = g; ci = cb * 128 + row; }
+      const bool row_ok = kh < 3 && ci < a.cin;
+#pragma unroll 1
+      for (int j = 0; j < 3; ++j) {
+        uint32_t v[32];
+        tmem_ld32(tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)(g * 96 + j * 32), v);
+        if (row_ok) {
+          const int tap = kh * 3 + (2 - j);
+          float* dst = a.part + (((long long)split * 9 + tap) * a.cin + ci) * a.cout + nb * 32;
+#pragma unroll
+          for (int i = 0; i < 8; ++i) {
+            float4 o;
+            o.x = has_work ? __uint_as_float(v[4 * i + 0]) : 0.f;
+            o.y = has_work ? __uint_as_float(v[4 * i + 1]) : 0.f;
+            o.z = has_work ? __uint_as_float(v[4 * i + 2]) : 0.f;
+            o.w = has_work ? __uint_as_float(v[4 * i + 3]) : 0.f;
+            *reinterpret_cast<float4*>(dst + 4 * i) = o;
+          }
+        }
+      }
+    }
+  }
+  tc_fence_before();
+  __syncthreads();
+  if (warp == 1) {
+    asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "r"(512u) : "memory");
+  }
+}
+
+static void plan4(const srcgan_conv_params* p, Wg4Args& a) {
+  a.cblocks = (p->cin + 127) / 128;
+  a.nblocks = p->cout / 32;
+  a.tiles_x = (p->wo + WS_TW - 1) / WS_TW;
+  a.tiles_y = (p->ho + WS_TH - 1) / WS_TH;
+  a.num_tiles = (long long)a.tiles_x * a.tiles_y * p->n;
+  const int groups = a.cblocks * a.nblocks;
+  long long s = (kNumSMs + groups - 1) / groups;          // one wave of CTAs: fewer fp32 partials to reduce
+  if (s > a.num_tiles) s = a.num_tiles;
+  if (s < 1) s = 1;
+  a.tiles_per_split = (a.num_tiles + s - 1) / s;
+  a.splits = (int)((a.num_tiles + a.tiles_per_split - 1) / a.tiles_per_split);
+}
+
+// NHWC bf16 tensor -> tensor map with an explicit box [boxc ch][boxw px][rows] and swizzle
+static int make_tmap_box(CUtensorMap* tm, const void* ptr, int c, int w, int h, int n, int ld, int boxc, int boxw, int rows,
+                         CUtensorMapSwizzle sw, const char* what) {
+  EncodeTiledFn encode = get_encode_fn();
+  SRCGAN_REQUIRE(encode != nullptr, "%s: cuTensorMapEncodeTiled is not available from the driver", what);
+  cuuint64_t gdim[4] = {(cuuint64_t)c, (cuuint64_t)w, (cuuint64_t)h, (cuuint64_t)n};
+  cuuint64_t gstr[3] = {(cuuint64_t)ld * 2, (cuuint64_t)ld * 2 * w, (cuuint64_t)ld * 2 * w * h};
+  cuuint32_t box[4] = {(cuuint32_t)boxc, (cuuint32_t)boxw, (cuuint32_t)rows, 1};
+  cuuint32_t estr[4] = {1, 1, 1, 1};
+  CUresult cr = encode(tm, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 4, const_cast<void*>(ptr), gdim, gstr, box, estr,
+                       CU_TENSOR_MAP_INTERLEAVE_NONE, sw, CU_TENSOR_MAP_L2_PROMOTION_L2_128B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+  if (cr != CUDA_SUCCESS) {
+    set_error("%s: cuTensorMapEncodeTiled failed with CUresult %d", what, (int)cr);
+    return SRCGAN_E_CUDA;
+  }
+  return SRCGAN_OK;
+}
+
+static int launch4(const CUtensorMap& tx, const CUtensorMap& tg, const Wg4Args& a, cudaStream_t st) {
+  static bool attr_set = false;
+  if (!attr_set) {
+    SRCGAN_CUDA(cudaFuncSetAttribute(conv3x3_wgrad_stack_tc, cudaFuncAttributeMaxDynamicSharedMemorySize, WS_SMEM));
+    attr_set = true;
+  }
+  const unsigned grid = (unsigned)(a.cblocks * a.nblocks * a.splits);
+  conv3x3_wgrad_stack_tc<<<grid, NUM_THREADS, WS_SMEM, st>>>(tx, tg, a);
+  count_launch();
+  return check_launch("conv3x3_wgrad_stack_tc");
+}
+}  // namespace tcw4
+
 // shared with the SIMT engine (conv_simt.cu)
 int wgrad_reduce_launch(const float* part, int splits, int taps, int cin, int cout, float* dw, int accumulate,
                         float alpha, cudaStream_t st);
@@ -2515,6 +2728,11 @@ bool conv_wgrad_tc_supported(const srcgan_conv_params* p) {
   if (p->x_ld % 8 || p->y_ld % 8) return false;
   if (((uintptr_t)p->x) % 16 || ((uintptr_t)p->y) % 16) return false;
   return true;
+}
+
+static bool wgrad_stack_ok(const srcgan_conv_params* p) {
+  return p->kh == 3 && p->kw == 3 && p->stride == 1 && p->pad == 1 && (p->cout == 32 || p->cout == 64) && p->cin >= 16 &&
+         p->cin % 8 == 0 && !getenv("SRCGAN_B200_NO_WSTACK");
 }
 
 static bool wgrad_halo_ok(const srcgan_conv_params* p) {
@@ -2531,6 +2749,11 @@ size_t conv_wgrad_tc_workspace(const srcgan_conv_params* p) {
     tcw3::plan3(p, a3);
     if (a3.splits > splits) splits = a3.splits;
   }
+  if (wgrad_stack_ok(p)) {
+    tcw4::Wg4Args a4;
+    tcw4::plan4(p, a4);
+    if (a4.splits > splits) splits = a4.splits;
+  }
   size_t wbytes = (size_t)splits * p->kh * p->kw * p->cin * p->cout * sizeof(float);
   return ((wbytes + 255) / 256) * 256 + (size_t)1024 * p->cout * sizeof(float) + 256;
 }
@@ -2542,7 +2765,25 @@ int conv_wgrad_tc(const srcgan_conv_params* p, float* dw, float* db, int accumul
   long long tiles, tps;
   tcw::plan(p, bn, cblocks, nblocks, splits, tiles, tps);
   size_t wbytes = (size_t)splits * p->kh * p->kw * p->cin * p->cout * sizeof(float);
-  if (dw && wgrad_halo_ok(p)) {
+  if (dw && wgrad_stack_ok(p)) {
+    tcw4::Wg4Args a4;
+    tcw4::plan4(p, a4);
+    a4.n = p->n; a4.ho = p->ho; a4.wo = p->wo; a4.cin = p->cin; a4.cout = p->cout;
+    a4.part = reinterpret_cast<float*>(ws);
+    wbytes = (size_t)a4.splits * 9 * p->cin * p->cout * sizeof(float);
+    CUtensorMap tx, tg;
+    int rc = tcw4::make_tmap_box(&tx, p->x, p->cin, p->w, p->h, p->n, p->x_ld, 64, tcw4::WS_TW, tcw4::WS_X_ROWS,
+                                 CU_TENSOR_MAP_SWIZZLE_128B, "conv_wgrad_tc(stack x)");
+    if (rc) return rc;
+    rc = tcw4::make_tmap_box(&tg, p->y, p->cout, p->wo, p->ho, p->n, p->y_ld, 32, tcw4::WS_G_W, tcw4::WS_TH,
+                             CU_TENSOR_MAP_SWIZZLE_64B, "conv_wgrad_tc(stack dy)");
+    if (rc) return rc;
+    rc = tcw4::launch4(tx, tg, a4, st);
+    if (rc) return rc;
+    rc = wgrad_reduce_launch(reinterpret_cast<const float*>(ws), a4.splits, 9, p->cin, p->cout, dw, accumulate,
+                             p->alpha, st);
+    if (rc) return rc;
+  } else if (dw && wgrad_halo_ok(p)) {
     tcw3::Wg3Args a3;
     tcw3::plan3(p, a3);
     a3.n = p->n; a3.ho = p->ho; a3.wo = p->wo; a3.cin = p->cin; a3.cout = p->cout; a3.pad = p->pad;

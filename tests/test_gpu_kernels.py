@@ -294,6 +294,12 @@ WGRAD_TC_CASES = [
     (1, 16, 16, 256, 128, 3, 1),
     (1, 18, 10, 128, 256, 4, 1),
     (4, 64, 64, 64, 64, 3, 1),       # many pixel tiles per CTA
+    # kw-stacked kernel: channel blocks of 128 (two atoms) and <= 64 (two vertical taps per M), ragged tiles, cout halves
+    (1, 40, 50, 128, 32, 3, 1),
+    (2, 24, 40, 160, 64, 3, 1),
+    (3, 33, 17, 192, 32, 3, 1),
+    (2, 64, 64, 32, 64, 3, 1),
+    (1, 9, 70, 64, 32, 3, 1),
 ]
 
 
