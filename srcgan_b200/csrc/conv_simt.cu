@@ -352,14 +352,25 @@ colsum_partial_vec(const __nv_bfloat16* __restrict__ g, int ld, int64_t M, int c
   }
 }
 
-__global__ void colsum_final(const float* __restrict__ part, int nparts, int c, float* __restrict__ out,
-                             int accumulate, float alpha) {
-  int ch = blockIdx.x * blockDim.x + threadIdx.x;
-  if (ch >= c) return;
+// block = 32 channels x 8 row lanes; each lane sums every 8th partial row, the lanes are then added in a fixed order
+// (deterministic; a single thread per channel walking up to 1024 rows took 50 us per launch)
+__global__ void __launch_bounds__(256)
+colsum_final(const float* __restrict__ part, int nparts, int c, float* __restrict__ out, int accumulate, float alpha) {
+  __shared__ double red[8][33];
+  const int cl = threadIdx.x & 31, rl = threadIdx.x >> 5;
+  const int ch = blockIdx.x * 32 + cl;
   double s = 0.0;
-  for (int k = 0; k < nparts; ++k) s += (double)part[(int64_t)k * c + ch];
-  s *= (double)alpha;
-  out[ch] = accumulate ? out[ch] + (float)s : (float)s;
+  if (ch < c)
+    for (int k = rl; k < nparts; k += 8) s += (double)part[(int64_t)k * c + ch];
+  red[rl][cl] = s;
+  __syncthreads();
+  if (rl == 0 && ch < c) {
+    double t = 0.0;
+#pragma unroll
+    for (int r = 0; r < 8; ++r) t += red[r][cl];
+    t *= (double)alpha;
+    out[ch] = accumulate ? out[ch] + (float)t : (float)t;
+  }
 }
 
 // ---------------------------------------------------------------------------------------------
@@ -896,6 +907,13 @@ int wgrad_reduce_launch(const float* part, int splits, int taps, int cin, int co
   return check_launch("wgrad_reduce");
 }
 
+// fixed-order sum of `nparts` partial rows [nparts][c] -> out[c] (* alpha, optionally accumulated)
+int colsum_final_launch(const float* part, int nparts, int c, float* out, int accumulate, float alpha, cudaStream_t st) {
+  colsum_final<<<ceil_div(c, 32), 256, 0, st>>>(part, nparts, c, out, accumulate, alpha);
+  count_launch();
+  return check_launch("colsum_final");
+}
+
 int bias_grad_launch(const void* dy, int dy_ld, int dtype, long long M, int cout, float* db, int accumulate,
                      float alpha, void* ws, cudaStream_t st) {
   float* bpart = reinterpret_cast<float*>(ws);
@@ -906,7 +924,7 @@ int bias_grad_launch(const void* dy, int dy_ld, int dtype, long long M, int cout
     if (nb > 1024) nb = 1024;                 // the workspace holds 1024 partial rows (conv_wgrad_*_workspace)
     if (nb < 1) nb = 1;
     colsum_partial_vec<<<(unsigned)nb, 256, 0, st>>>(reinterpret_cast<const __nv_bfloat16*>(dy), dy_ld, M, cout, bpart);
-    colsum_final<<<ceil_div(cout, 128), 128, 0, st>>>(bpart, (int)nb, cout, db, accumulate, alpha);
+    colsum_final<<<ceil_div(cout, 32), 256, 0, st>>>(bpart, (int)nb, cout, db, accumulate, alpha);
     count_launch(2);
     return check_launch("bias_grad");
   }
@@ -919,7 +937,7 @@ int bias_grad_launch(const void* dy, int dy_ld, int dtype, long long M, int cout
   else
     colsum_partial<__nv_bfloat16><<<grid, blk, 0, st>>>(reinterpret_cast<const __nv_bfloat16*>(dy), dy_ld, M, cout,
                                                         bpart);
-  colsum_final<<<ceil_div(cout, 128), 128, 0, st>>>(bpart, ny, cout, db, accumulate, alpha);
+  colsum_final<<<ceil_div(cout, 32), 256, 0, st>>>(bpart, ny, cout, db, accumulate, alpha);
   count_launch(2);
   return check_launch("bias_grad");
 }

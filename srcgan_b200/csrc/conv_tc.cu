@@ -2535,6 +2535,7 @@ struct Wg4Args {
   int tiles_x, tiles_y;
   long long num_tiles, tiles_per_split;
   float* part;
+  float* dbpart;                        // [splits][cout] column sums of dY (bias gradient partials), or nullptr
 };
 
 __host__ __device__ constexpr uint32_t desc_hi_sw64(uint32_t sbo_bytes) {
@@ -2552,8 +2553,15 @@ conv3x3_wgrad_stack_tc(const __grid_constant__ CUtensorMap tmap_x, const __grid_
   uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(done_bar + 1);
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
 
+  int b = blockIdx.x;
+  const int split = b % a.splits; b /= a.splits;
+  const int nb = b % a.nblocks; b /= a.nblocks;
+  const int cb = b;
+  // the CTAs of channel block 0 also sum dY over the pixels (bias gradient): their four epilogue warps read every dY
+  // slab out of shared memory while the MMAs run, so a stage is released by the MMA commit AND those four warps
+  const bool do_db = a.dbpart != nullptr && cb == 0;
   if (threadIdx.x == 0) {
-    for (int s = 0; s < WS_STAGES; ++s) { mbar_init(&full_bar[s], 1); mbar_init(&empty_bar[s], 1); }
+    for (int s = 0; s < WS_STAGES; ++s) { mbar_init(&full_bar[s], 1); mbar_init(&empty_bar[s], do_db ? 5 : 1); }
     mbar_init(done_bar, 1);
     asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
   }
@@ -2567,10 +2575,6 @@ conv3x3_wgrad_stack_tc(const __grid_constant__ CUtensorMap tmap_x, const __grid_
   tc_fence_after();
   const uint32_t tmem_base = *tmem_slot;
 
-  int b = blockIdx.x;
-  const int split = b % a.splits; b /= a.splits;
-  const int nb = b % a.nblocks; b /= a.nblocks;
-  const int cb = b;
   const int c_rem = a.cin - cb * 128;
   const bool paired = c_rem <= 64;                                   // one 64-channel atom: M = (tap kh | tap kh + 1)
   const int ngroups = paired ? 2 : 3;                                // accumulators of 96 columns
@@ -2634,9 +2638,53 @@ conv3x3_wgrad_stack_tc(const __grid_constant__ CUtensorMap tmap_x, const __grid_
   } else {
     const int q = warp & 3;
     const int row = q * 32 + lane;
+    const bool has_work = t_end > t_beg;
+    if (do_db) {
+      // thread = (8-channel group c4, pixel lane): four 16-byte reads per tile from the SWIZZLE_64B slab
+      // [8 rows][18 px][32 ch] (interior pixels only; pixels outside the image were zero-filled by TMA)
+      const int t = (warp - 2) * 32 + lane, c4 = t & 3, pl = t >> 2;
+      float acc[8] = {0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f};
+      int stage = 0;
+      uint32_t phase = 0;
+      for (long long tt = t_beg; tt < t_end; ++tt) {
+        mbar_wait(&full_bar[stage], phase);
+        const uint32_t sg = smem_u32(smem + stage * WS_STAGE) + 2 * WS_X_ATOM;
+#pragma unroll
+        for (int i = 0; i < 4; ++i) {
+          const int px = pl + 32 * i;
+          const int idx = (px >> 4) * WS_G_W + (px & 15) + 1;
+          uint4 qv;
+          asm volatile("ld.shared.v4.b32 {%0, %1, %2, %3}, [%4];" : "=r"(qv.x), "=r"(qv.y), "=r"(qv.z), "=r"(qv.w)
+                       : "r"(sg + (uint32_t)(idx * 64 + ((c4 ^ ((idx >> 1) & 3)) << 4))));
+          float f8[8];
+          unpack8(qv, f8);
+#pragma unroll
+          for (int j = 0; j < 8; ++j) acc[j] += f8[j];
+        }
+        __syncwarp();
+        if (lane == 0) mbar_arrive(&empty_bar[stage]);
+        if (++stage == WS_STAGES) { stage = 0; phase ^= 1; }
+      }
+      // lanes with equal (lane & 3) hold the same channel group: fold lane bits 2..4, then the four warps through smem
+#pragma unroll
+      for (int j = 0; j < 8; ++j) {
+        acc[j] += __shfl_xor_sync(0xffffffffu, acc[j], 4);
+        acc[j] += __shfl_xor_sync(0xffffffffu, acc[j], 8);
+        acc[j] += __shfl_xor_sync(0xffffffffu, acc[j], 16);
+      }
+      float* red = reinterpret_cast<float*>(aux + 512);                 // [4 warps][32 channels]
+      if (lane < 4) {
+#pragma unroll
+        for (int j = 0; j < 8; ++j) red[q * 32 + lane * 8 + j] = acc[j];
+      }
+      asm volatile("bar.sync 1, 128;" ::: "memory");
+      if (t < 32) {
+        const float sum = (red[t] + red[32 + t]) + (red[64 + t] + red[96 + t]);
+        a.dbpart[(long long)split * a.cout + nb * 32 + t] = has_work ? sum : 0.f;
+      }
+    }
     mbar_wait(done_bar, 0);
     tc_fence_after();
-    const bool has_work = t_end > t_beg;
 #pragma unroll 1
     for (int g = 0; g < ngroups; ++g) {
       int kh, ci;
@@ -2720,6 +2768,7 @@ int wgrad_reduce_launch(const float* part, int splits, int taps, int cin, int co
                         float alpha, cudaStream_t st);
 int bias_grad_launch(const void* dy, int dy_ld, int dtype, long long M, int cout, float* db, int accumulate,
                      float alpha, void* ws, cudaStream_t st);
+int colsum_final_launch(const float* part, int nparts, int c, float* out, int accumulate, float alpha, cudaStream_t st);
 
 bool conv_wgrad_tc_supported(const srcgan_conv_params* p) {
   if (p->dtype != SRCGAN_DT_BF16 || (p->stride != 1 && p->stride != 2) || p->upsample) return false;
@@ -2771,6 +2820,7 @@ int conv_wgrad_tc(const srcgan_conv_params* p, float* dw, float* db, int accumul
     a4.n = p->n; a4.ho = p->ho; a4.wo = p->wo; a4.cin = p->cin; a4.cout = p->cout;
     a4.part = reinterpret_cast<float*>(ws);
     wbytes = (size_t)a4.splits * 9 * p->cin * p->cout * sizeof(float);
+    a4.dbpart = db ? reinterpret_cast<float*>(reinterpret_cast<char*>(ws) + ((wbytes + 255) / 256) * 256) : nullptr;
     CUtensorMap tx, tg;
     int rc = tcw4::make_tmap_box(&tx, p->x, p->cin, p->w, p->h, p->n, p->x_ld, 64, tcw4::WS_TW, tcw4::WS_X_ROWS,
                                  CU_TENSOR_MAP_SWIZZLE_128B, "conv_wgrad_tc(stack x)");
@@ -2783,6 +2833,8 @@ int conv_wgrad_tc(const srcgan_conv_params* p, float* dw, float* db, int accumul
     rc = wgrad_reduce_launch(reinterpret_cast<const float*>(ws), a4.splits, 9, p->cin, p->cout, dw, accumulate,
                              p->alpha, st);
     if (rc) return rc;
+    if (db) return colsum_final_launch(a4.dbpart, a4.splits, p->cout, db, accumulate, p->alpha, st);   // summed in-kernel
+    return SRCGAN_OK;
   } else if (dw && wgrad_halo_ok(p)) {
     tcw3::Wg3Args a3;
     tcw3::plan3(p, a3);

@@ -295,12 +295,18 @@ class _RRDBGenerator(_NetBase):
             ops.conv_fprop(Slice(D), self._dense_wT(rdb, 0, s5, dt, layout), None, dst, 3, 1, 1,
                            r1=Slice(D, 0, nf), beta1=(0.2 if is_rdb3 else 1.0),
                            r2=(Slice(Dbuf[(j + 2) % 4], 0, nf) if is_rdb1 else None), beta2=1.0, engine=eng)
+            # bias gradients: the kw-stacked tcgen05 wgrad kernel sums dY out of the slabs it has in shared memory anyway
+            # (csrc/conv_tc.cu, tcw4); other engines take one fused column-sum pass over the gradient concat buffer
+            from . import engine as _engine
+            fused_db = all(_engine.select_wgrad(nf + gc * (k - 1), gc if k < 5 else nf, 3, 1, False, dt, h, w) == ops.ENGINE_TC
+                           for k in range(1, 6)) and all(W(c.weight) == W(c.bias) for c in convs)
             for k in range(1, 5):
                 c = convs[k - 1]
-                self._wgrad(c, Slice(C, 0, nf + gc * (k - 1)), Slice(D, nf + gc * (4 - k), gc), sink, W(c.weight), False)
-            self._wgrad(convs[4], Slice(C), Slice(D, 0, nf), sink, W(convs[4].weight), False, alpha=s5)
+                self._wgrad(c, Slice(C, 0, nf + gc * (k - 1)), Slice(D, nf + gc * (4 - k), gc), sink, W(c.weight),
+                            fused_db and W(c.bias))
+            self._wgrad(convs[4], Slice(C), Slice(D, 0, nf), sink, W(convs[4].weight), fused_db and W(convs[4].bias), alpha=s5)
             # all five bias gradients = column sums of the gradient concat buffer, one pass
-            if any(W(c.bias) for c in convs):
+            if not fused_db and any(W(c.bias) for c in convs):
                 flat = torch.empty(ctot, dtype=torch.float32, device=dev)
                 ops.colsum(Slice(D), flat)
                 if W(convs[4].bias):
