@@ -234,9 +234,9 @@ def run_ours(args):
         conv_ms = sum(v["ms"] for v in ksum.values())
         roof = {"bound": "tensor", "kernel": name, "achieved": achieved, "peak": peaks["tflops"], "unit": "TFLOP/s",
                 "frac": achieved / peaks["tflops"], "traffic": None,
-                "traffic_note": "launches of this kernel span many layer shapes; per-shape DRAM bytes from ncu --set "
-                                "full are in profiles/r1_ncu_halo_kernels.txt (64->64 @16x256x256: 291 MB measured "
-                                "vs 268 MB algorithmic)",
+                "traffic_note": "launches of this kernel family span several layer shapes; per-shape DRAM bytes from ncu --set "
+                                "full are in profiles/r1_ncu_sweep2.txt and profiles/r1_ncu_wgrad_stack.txt (64->32 @64x256x256: "
+                                "563+248 MB measured vs 805 MB algorithmic; 192->64 @32x256x256: 897+247 MB vs 1074 MB)",
                 "peak_source": peaks["source"],
                 "launches_per_step": d["launches"] / args.steps, "avg_launch_ms": d["ms"] / d["launches"],
                 "share_of_step": d["ms"] / ms_instr, "conv_share_of_step": conv_ms / ms_instr,

@@ -1097,6 +1097,7 @@ struct Sw2Args {
   int wseg, segs_x, strips_y, strips;   // strips = n * strips_y, flattened over images
   int num_units;                        // ceil(strips / CG) * segs_x
   int pfd;                              // L2 prefetch distance of the producer, in columns (0 = off)
+  unsigned int* sched;                  // {next unit, finished clusters} of the dynamic unit queue, or nullptr (static round-robin)
   int tr;                               // 0: lanes = image rows, sweep over x;  1: lanes = pixels of a row, sweep over y
   long long lane_stride, sweep_stride, img_stride;   // pixel index = img * img_stride + lane * lane_stride + sweep * sweep_stride
   const __nv_bfloat16* wgt;
@@ -1165,6 +1166,38 @@ __device__ __forceinline__ void umma_commit_pair(uint64_t* bar) {           // a
                : "memory");
 }
 
+// Dynamic unit queue of a CTA pair.  The pairs of one launch take 127-216 us for equal shares of the work (the HBM-bound
+// layers see very different TMA latencies per SM), so units are claimed from a global counter instead of dealt round-robin.
+// The leader's producer warp claims one unit ahead and publishes it to both CTAs' `unit_list` (one single-use mbarrier per
+// list slot); every role of both CTAs walks the list.  A pair stops claiming after SW_MAXU - 1 units (host guarantees that
+// ncl * (SW_MAXU - 1) >= num_units, else the launch is static).
+constexpr int SW_MAXU = 32;
+__device__ __forceinline__ void mbar_wait_cluster(uint64_t* bar, uint32_t parity) {   // observes a peer CTA's release
+  uint32_t ok = 0;
+  const long long t0 = clock64();
+  while (!ok) {
+    asm volatile(
+        "{\n\t.reg .pred p;\n\t"
+        "mbarrier.try_wait.parity.acquire.cluster.shared::cta.b64 p, [%1], %2;\n\t"
+        "selp.u32 %0, 1, 0, p;\n\t}"
+        : "=r"(ok)
+        : "r"(smem_u32(bar)), "r"(parity)
+        : "memory");
+    if (!ok && clock64() - t0 > 4000000000LL) __trap();
+  }
+}
+__device__ __forceinline__ void publish_unit(int* list, uint64_t* bars, int i, int u, bool pair) {
+  list[i] = u;
+  mbar_arrive(&bars[i]);
+  if (pair) {
+    uint32_t rl, rb;
+    asm volatile("mapa.shared::cluster.u32 %0, %1, %2;" : "=r"(rl) : "r"(smem_u32(&list[i])), "r"(1u));
+    asm volatile("mapa.shared::cluster.u32 %0, %1, %2;" : "=r"(rb) : "r"(smem_u32(&bars[i])), "r"(1u));
+    asm volatile("st.shared::cluster.u32 [%0], %1;" ::"r"(rl), "r"(u) : "memory");
+    asm volatile("mbarrier.arrive.release.cluster.shared::cluster.b64 _, [%0];" ::"r"(rb) : "memory");
+  }
+}
+
 template <int BN, int CG>
 __global__ void __launch_bounds__(KW_THREADS, 1)
 conv3x3_sweep2_tc(const __grid_constant__ CUtensorMap tmap_x, const Sw2Args a) {
@@ -1183,6 +1216,8 @@ conv3x3_sweep2_tc(const __grid_constant__ CUtensorMap tmap_x, const Sw2Args a) {
   uint64_t* w_pair = w_full + 1;                                       // leader: the peer's weights have landed
   uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(w_pair + 1);
   float* sbias = reinterpret_cast<float*>(aux + 768);
+  uint64_t* u_full = reinterpret_cast<uint64_t*>(aux + 1024);          // [SW_MAXU] single-use: unit_list[i] is valid
+  int* unit_list = reinterpret_cast<int*>(aux + 1024 + SW_MAXU * 8);   // [SW_MAXU]
 
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const uint32_t rank = CG == 2 ? cluster_ctarank() : 0u;
@@ -1192,6 +1227,7 @@ conv3x3_sweep2_tc(const __grid_constant__ CUtensorMap tmap_x, const Sw2Args a) {
     for (int s = 0; s < NBLK; ++s) { mbar_init(&y_full[s], 1); mbar_init(&y_empty[s], 4 * CG); }
     mbar_init(w_full, 1);
     mbar_init(w_pair, 1);
+    for (int s = 0; s < SW_MAXU; ++s) mbar_init(&u_full[s], 1);
     asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
   }
   for (int i = threadIdx.x; i < BN; i += KW_THREADS) sbias[i] = (a.bias && i < a.cout) ? a.bias[i] : 0.f;
@@ -1218,6 +1254,21 @@ conv3x3_sweep2_tc(const __grid_constant__ CUtensorMap tmap_x, const Sw2Args a) {
   __syncthreads();
   if (CG == 2) cluster_sync_all();                                     // barriers initialised and TMEM zeroed in both CTAs
   tc_fence_after();
+
+  // i-th unit of this CTA pair (-1: none left)
+  auto get_unit = [&](int i) -> int {
+    if (a.sched == nullptr) { const int u = cid + i * ncl; return u < a.num_units ? u : -1; }
+    if (CG == 2 && rank == 1) mbar_wait_cluster(&u_full[i], 0); else mbar_wait(&u_full[i], 0);
+    return reinterpret_cast<volatile int*>(unit_list)[i];
+  };
+  auto claim_unit = [&](int i) {                                       // leader's producer warp, one lane
+    int u = -1;
+    if (i < SW_MAXU - 1) {
+      u = (int)atomicAdd(a.sched, 1u);
+      if (u >= a.num_units) u = -1;
+    }
+    publish_unit(unit_list, u_full, i, u, CG == 2);
+  };
 
   // unit u -> column segment [x_start, x_end) of strip (u / segs_x) * CG + rank; an absent strip (odd total) sweeps
   // rows below the image: its loads are zero-filled, its stores suppressed
@@ -1258,7 +1309,14 @@ conv3x3_sweep2_tc(const __grid_constant__ CUtensorMap tmap_x, const Sw2Args a) {
     }
     int as = 0;
     uint32_t aph = 0;
-    for (int u = cid; u < a.num_units; u += ncl) {
+    const bool fetcher = a.sched != nullptr && rank == 0;
+    if (fetcher && elect_one()) claim_unit(0);
+    __syncwarp();
+    for (int ui = 0;; ++ui) {
+      const int u = get_unit(ui);
+      if (u < 0) break;
+      if (fetcher && elect_one()) claim_unit(ui + 1);                  // one unit ahead: the claim's round trip is off the path
+      __syncwarp();
       SRCGAN_DECODE_SW2_UNIT(u)
       (void)strip_ok;
       const int pfd = a.pfd;                                           // L2 prefetch distance in columns
@@ -1286,6 +1344,15 @@ conv3x3_sweep2_tc(const __grid_constant__ CUtensorMap tmap_x, const Sw2Args a) {
           if (++as == a.na) { as = 0; aph ^= 1; }
         }
     }
+    if (fetcher && elect_one()) {                                      // the last pair to finish re-arms the queue
+      __threadfence();
+      if (atomicAdd(a.sched + 1, 1u) == (unsigned)ncl - 1) {
+        a.sched[0] = 0;
+        a.sched[1] = 0;
+        __threadfence();
+      }
+    }
+    __syncwarp();
   } else if (warp == 1) {
     // ---- MMA issuer (leader CTA of a pair)
     if (rank == 0) {
@@ -1305,7 +1372,9 @@ conv3x3_sweep2_tc(const __grid_constant__ CUtensorMap tmap_x, const Sw2Args a) {
       unsigned long long g_begin;
       asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(g_begin));
 #define SRCGAN_TICK(i) if (prof) { const long long n_ = clock64(); tp[i] += n_ - tc0; tc0 = n_; }
-      for (int u = cid; u < a.num_units; u += ncl) {
+      for (int ui = 0;; ++ui) {
+        const int u = get_unit(ui);
+        if (u < 0) break;
         const int seg = u % a.segs_x;
         const int x_start = seg * a.wseg;
         const int x_end = (x_start + a.wseg) < a.w ? (x_start + a.wseg) : a.w;
@@ -1424,9 +1493,11 @@ conv3x3_sweep2_tc(const __grid_constant__ CUtensorMap tmap_x, const Sw2Args a) {
     uint32_t t0 = 0;                                                   // running index of the unit's first input column
     uint32_t r = 0;                                                    // lap and position of this group's next output
     int m = g;
-    for (int u = cid; u < a.num_units; u += ncl) {
+    for (int ui = 0;; ++ui) {
+      const int u = get_unit(ui);
+      if (u < 0) break;
       SRCGAN_DECODE_SW2_UNIT(u)
-      const bool last_unit = u + ncl >= a.num_units;
+      const bool last_unit = get_unit(ui + 1) < 0;
       const int n_in = x_end - x_start + 2;
       const int y = y0 + row;
       const bool row_ok = strip_ok && y < a.h && !(a.dbg & 1);
@@ -1815,6 +1886,25 @@ static int sweep2_max_clusters(size_t smem) {
   return ncl;
 }
 
+// {next, done} counter pairs of the dynamic unit queue: a small per-device buffer owned by the library (allocated on first
+// use, zero-initialised, re-armed by each launch's last CTA pair); launches take the slots round-robin
+static unsigned int* sweep2_sched_slot() {
+  constexpr int SLOTS = 64, MAXDEV = 16;
+  static std::mutex mu;
+  static unsigned int* base[MAXDEV] = {};
+  static unsigned next[MAXDEV] = {};
+  int dev = 0;
+  if (cudaGetDevice(&dev) != cudaSuccess || dev < 0 || dev >= MAXDEV) return nullptr;
+  std::lock_guard<std::mutex> lock(mu);
+  if (!base[dev]) {
+    unsigned int* p = nullptr;
+    if (cudaMalloc(&p, SLOTS * 2 * sizeof(unsigned int)) != cudaSuccess) { (void)cudaGetLastError(); return nullptr; }
+    if (cudaMemset(p, 0, SLOTS * 2 * sizeof(unsigned int)) != cudaSuccess) { (void)cudaGetLastError(); return nullptr; }
+    base[dev] = p;
+  }
+  return base[dev] + 2 * (next[dev]++ % SLOTS);
+}
+
 template <int BN, int CG>
 static int launch_sweep2(const CUtensorMap& tx, Sw2Args& a, cudaStream_t st) {
   using C = Sw2Cfg<BN, CG>;
@@ -1840,6 +1930,9 @@ static int launch_sweep2(const CUtensorMap& tx, Sw2Args& a, cudaStream_t st) {
     if (best < 0 || cost < best) { best = cost; a.wseg = ws; a.segs_x = (int)segs; a.num_units = (int)units; }
   }
   const int ncl = a.num_units < ncl_max ? a.num_units : ncl_max;
+  a.sched = nullptr;
+  if (a.num_units > ncl && (long long)ncl * (SW_MAXU - 1) >= a.num_units && !getenv("SRCGAN_B200_SWEEP_STATIC"))
+    a.sched = sweep2_sched_slot();
   cudaLaunchConfig_t cfg = {};
   cfg.gridDim = dim3((unsigned)(ncl * CG)); cfg.blockDim = dim3(KW_THREADS); cfg.dynamicSmemBytes = smem; cfg.stream = st;
   cudaLaunchAttribute at[1];
