@@ -1089,7 +1089,7 @@ __device__ __forceinline__ void tmem_st_wait() { asm volatile("tcgen05.wait::st.
 //     instruction, and the two blocks per segment boundary that collect only halo contributions are drained as
 //     dummies.  The MMA warp's loop is one wait + 3*ksteps instructions + commits per column, no index arithmetic.
 // Roles: warp 0 TMA producer (both CTAs; the peer's loads signal the leader's mbarrier), warp 1 MMA issuer (leader
-// CTA only; commits are multicast to both CTAs), warps 2-5 / 6-9 two epilogue groups taking alternate output columns.
+// CTA only; commits are multicast to both CTAs), then SW2_GROUPS epilogue groups of four warps taking output columns in turn.
 // ---------------------------------------------------------------------------------------------
 struct Sw2Args {
   int n, cin, cout, h, w;
@@ -1198,8 +1198,13 @@ __device__ __forceinline__ void publish_unit(int* list, uint64_t* bars, int i, i
   }
 }
 
+// warp 0 producer, warp 1 MMA issuer, then SW2_GROUPS epilogue groups of four warps.  A group has SW2_GROUPS column periods
+// to drain one column; with two groups the 64-channel epilogue (TMEM loads compete with N = 192 MMAs) took 2 600-2 900 clk
+// per column against 2 x 1 152 clk of MMAs and the issuer waited 500 clk per column for free accumulator blocks.
+constexpr int SW2_GROUPS = 3;
+constexpr int SW2_THREADS = 64 + 128 * SW2_GROUPS;
 template <int BN, int CG>
-__global__ void __launch_bounds__(KW_THREADS, 1)
+__global__ void __launch_bounds__(SW2_THREADS, 1)
 conv3x3_sweep2_tc(const __grid_constant__ CUtensorMap tmap_x, const Sw2Args a) {
   using C = Sw2Cfg<BN, CG>;
   constexpr int NBLK = C::NBLK, RUN = C::RUN;
@@ -1230,7 +1235,7 @@ conv3x3_sweep2_tc(const __grid_constant__ CUtensorMap tmap_x, const Sw2Args a) {
     for (int s = 0; s < SW_MAXU; ++s) mbar_init(&u_full[s], 1);
     asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
   }
-  for (int i = threadIdx.x; i < BN; i += KW_THREADS) sbias[i] = (a.bias && i < a.cout) ? a.bias[i] : 0.f;
+  for (int i = threadIdx.x; i < BN; i += SW2_THREADS) sbias[i] = (a.bias && i < a.cout) ? a.bias[i] : 0.f;
   if (warp == 1) {
     if (CG == 1) {
       asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(tmem_slot)), "r"(512u) : "memory");
@@ -1451,7 +1456,7 @@ conv3x3_sweep2_tc(const __grid_constant__ CUtensorMap tmap_x, const Sw2Args a) {
 #undef SRCGAN_TICK
     }
   } else {
-    // ---- epilogue: TMEM lane = image row y0 + q*32 + lane; group g takes the outputs with (running index & 1) == g;
+    // ---- epilogue: TMEM lane = image row y0 + q*32 + lane; group g takes the outputs with running index % SW2_GROUPS == g;
     // the four warps of a group never synchronise with each other (registers -> global memory, no staging).
     // Running output index o = running input index of the column it is centred on; lap r = o / RUN, m = o % RUN:
     // main block m + 1 of lap r, plus block 0 of lap r + 1 when m == RUN - 1, plus block RUN + 1 of lap r - 1 when m == 0.
@@ -1476,7 +1481,7 @@ conv3x3_sweep2_tc(const __grid_constant__ CUtensorMap tmap_x, const Sw2Args a) {
         }
       }
     };
-    if (g == 1) {                                                      // "output -1": block 0 of lap 0 collects only a halo tap
+    if (g == SW2_GROUPS - 1) {                                         // "output -1": block 0 of lap 0 collects only a halo tap
       mbar_wait(&y_full[0], 0);
       tc_fence_after();
       release_slabs(0);
@@ -1501,7 +1506,7 @@ conv3x3_sweep2_tc(const __grid_constant__ CUtensorMap tmap_x, const Sw2Args a) {
       const int n_in = x_end - x_start + 2;
       const int y = y0 + row;
       const bool row_ok = strip_ok && y < a.h && !(a.dbg & 1);
-      for (int j = (int)((t0 ^ (uint32_t)g) & 1u); j < n_in; j += 2) {
+      for (int j = (g + SW2_GROUPS - (int)(t0 % (uint32_t)SW2_GROUPS)) % SW2_GROUPS; j < n_in; j += SW2_GROUPS) {
         if (last_unit && j == n_in - 1) break;                         // centred on the stream's last input: never completes
         const uint32_t o = t0 + (uint32_t)j;
         const int pb = m + 1;
@@ -1605,7 +1610,7 @@ conv3x3_sweep2_tc(const __grid_constant__ CUtensorMap tmap_x, const Sw2Args a) {
           if (sb >= 0) arrive_empty(sb);
         }
         SRCGAN_TICK(2)
-        m += 2;
+        m += SW2_GROUPS;
         if (m >= RUN) { m -= RUN; ++r; }
       }
       t0 += (uint32_t)n_in;
@@ -1871,7 +1876,7 @@ static int sweep2_max_clusters(size_t smem) {
   int ncl = kNumSMs / CG;
   if (CG > 1) {
     cudaLaunchConfig_t cfg = {};
-    cfg.gridDim = dim3((unsigned)kNumSMs); cfg.blockDim = dim3(KW_THREADS); cfg.dynamicSmemBytes = smem;
+    cfg.gridDim = dim3((unsigned)kNumSMs); cfg.blockDim = dim3(SW2_THREADS); cfg.dynamicSmemBytes = smem;
     cudaLaunchAttribute at[1];
     at[0].id = cudaLaunchAttributeClusterDimension;
     at[0].val.clusterDim.x = CG; at[0].val.clusterDim.y = 1; at[0].val.clusterDim.z = 1;
@@ -1934,7 +1939,7 @@ static int launch_sweep2(const CUtensorMap& tx, Sw2Args& a, cudaStream_t st) {
   if (a.num_units > ncl && (long long)ncl * (SW_MAXU - 1) >= a.num_units && !getenv("SRCGAN_B200_SWEEP_STATIC"))
     a.sched = sweep2_sched_slot();
   cudaLaunchConfig_t cfg = {};
-  cfg.gridDim = dim3((unsigned)(ncl * CG)); cfg.blockDim = dim3(KW_THREADS); cfg.dynamicSmemBytes = smem; cfg.stream = st;
+  cfg.gridDim = dim3((unsigned)(ncl * CG)); cfg.blockDim = dim3(SW2_THREADS); cfg.dynamicSmemBytes = smem; cfg.stream = st;
   cudaLaunchAttribute at[1];
   at[0].id = cudaLaunchAttributeClusterDimension;
   at[0].val.clusterDim.x = CG; at[0].val.clusterDim.y = 1; at[0].val.clusterDim.z = 1;
