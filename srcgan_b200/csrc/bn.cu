@@ -99,51 +99,102 @@ __device__ __forceinline__ uint4 pack8b(const float (&f)[8]) {
   return o;
 }
 
-__global__ void bn_apply_vec(const __nv_bfloat16* __restrict__ x, int x_ld, __nv_bfloat16* __restrict__ y, int y_ld,
-                             int64_t npix, int c, const float* __restrict__ gamma, const float* __restrict__ beta,
-                             const float* __restrict__ mean, const float* __restrict__ invstd, float slope) {
+// The apply passes are pure streaming (HBM-bound).  thread = (pixel lane, channel octet): the per-channel constants are
+// loaded once into registers and the thread then walks pixels with four 16-byte loads in flight (the first version was
+// one pixel-octet per thread and re-read 32 per-channel scalars for every 16 bytes of data: 2-5x off the roofline).
+__global__ void __launch_bounds__(256)
+bn_apply_vec(const __nv_bfloat16* __restrict__ x, int x_ld, __nv_bfloat16* __restrict__ y, int y_ld,
+             int64_t npix, int c, const float* __restrict__ gamma, const float* __restrict__ beta,
+             const float* __restrict__ mean, const float* __restrict__ invstd, float slope) {
   const int oct = c >> 3;
-  int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
-  if (i >= npix * oct) return;
-  const int ch = (int)(i % oct) * 8;
-  const int64_t m = i / oct;
-  float f[8];
-  unpack8b(__ldg(reinterpret_cast<const uint4*>(x + m * x_ld + ch)), f);
+  const int rows_per_iter = 256 / oct;
+  const int oc = threadIdx.x % oct, rl = threadIdx.x / oct;
+  if (rl >= rows_per_iter) return;
+  const int ch = oc * 8;
+  float mu[8], gi[8], be[8];
 #pragma unroll
-  for (int k = 0; k < 8; ++k) {
-    float v = fmaf(f[k] - mean[ch + k], gamma[ch + k] * invstd[ch + k], beta[ch + k]);
-    f[k] = v > 0.f ? v : v * slope;
-  }
-  *reinterpret_cast<uint4*>(y + m * y_ld + ch) = pack8b(f);
-}
-
-__global__ void bn_bwd_apply_vec(const __nv_bfloat16* __restrict__ dy, int dy_ld, const __nv_bfloat16* __restrict__ y,
-                                 int y_ld, const __nv_bfloat16* __restrict__ x, int x_ld, __nv_bfloat16* __restrict__ dx,
-                                 int dx_ld, int64_t npix, int c, const float* __restrict__ gamma,
-                                 const float* __restrict__ mean, const float* __restrict__ invstd,
-                                 const float* __restrict__ tot, float slope, int training) {
-  const int oct = c >> 3;
-  int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
-  if (i >= npix * oct) return;
-  const int ch = (int)(i % oct) * 8;
-  const int64_t m = i / oct;
-  float d[8], yy[8], xx[8];
-  unpack8b(__ldg(reinterpret_cast<const uint4*>(dy + m * dy_ld + ch)), d);
-  unpack8b(__ldg(reinterpret_cast<const uint4*>(y + m * y_ld + ch)), yy);
-  unpack8b(__ldg(reinterpret_cast<const uint4*>(x + m * x_ld + ch)), xx);
-  const float inv_n = 1.f / (float)npix;
+  for (int k = 0; k < 8; ++k) { mu[k] = mean[ch + k]; gi[k] = gamma[ch + k] * invstd[ch + k]; be[k] = beta[ch + k]; }
+  const int64_t step = (int64_t)gridDim.x * rows_per_iter;
+  int64_t m = (int64_t)blockIdx.x * rows_per_iter + rl;
+  for (; m + 3 * step < npix; m += 4 * step) {
+    uint4 q[4];
 #pragma unroll
-  for (int k = 0; k < 8; ++k) {
-    float dz = yy[k] > 0.f ? d[k] : d[k] * slope;
-    const float is = invstd[ch + k], g = gamma[ch + k] * is;
-    if (training) {
-      const float xh = (xx[k] - mean[ch + k]) * is;
-      d[k] = g * (dz - tot[ch + k] * inv_n - xh * tot[c + ch + k] * inv_n);
-    } else {
-      d[k] = g * dz;
+    for (int u = 0; u < 4; ++u) q[u] = __ldg(reinterpret_cast<const uint4*>(x + (m + u * step) * x_ld + ch));
+#pragma unroll
+    for (int u = 0; u < 4; ++u) {
+      float f[8];
+      unpack8b(q[u], f);
+#pragma unroll
+      for (int k = 0; k < 8; ++k) {
+        const float v = fmaf(f[k] - mu[k], gi[k], be[k]);
+        f[k] = v > 0.f ? v : v * slope;
+      }
+      *reinterpret_cast<uint4*>(y + (m + u * step) * y_ld + ch) = pack8b(f);
     }
   }
-  *reinterpret_cast<uint4*>(dx + m * dx_ld + ch) = pack8b(d);
+  for (; m < npix; m += step) {
+    float f[8];
+    unpack8b(__ldg(reinterpret_cast<const uint4*>(x + m * x_ld + ch)), f);
+#pragma unroll
+    for (int k = 0; k < 8; ++k) {
+      const float v = fmaf(f[k] - mu[k], gi[k], be[k]);
+      f[k] = v > 0.f ? v : v * slope;
+    }
+    *reinterpret_cast<uint4*>(y + m * y_ld + ch) = pack8b(f);
+  }
+}
+
+__global__ void __launch_bounds__(256)
+bn_bwd_apply_vec(const __nv_bfloat16* __restrict__ dy, int dy_ld, const __nv_bfloat16* __restrict__ y,
+                 int y_ld, const __nv_bfloat16* __restrict__ x, int x_ld, __nv_bfloat16* __restrict__ dx,
+                 int dx_ld, int64_t npix, int c, const float* __restrict__ gamma,
+                 const float* __restrict__ mean, const float* __restrict__ invstd,
+                 const float* __restrict__ tot, float slope, int training) {
+  const int oct = c >> 3;
+  const int rows_per_iter = 256 / oct;
+  const int oc = threadIdx.x % oct, rl = threadIdx.x / oct;
+  if (rl >= rows_per_iter) return;
+  const int ch = oc * 8;
+  const float inv_n = 1.f / (float)npix;
+  float mu[8], is[8], g[8], t0[8], t1[8];
+#pragma unroll
+  for (int k = 0; k < 8; ++k) {
+    is[k] = invstd[ch + k]; g[k] = gamma[ch + k] * is[k]; mu[k] = mean[ch + k];
+    t0[k] = training ? tot[ch + k] * inv_n : 0.f; t1[k] = training ? tot[c + ch + k] * inv_n : 0.f;
+  }
+  const int64_t step = (int64_t)gridDim.x * rows_per_iter;
+  int64_t m = (int64_t)blockIdx.x * rows_per_iter + rl;
+  for (; m < npix; m += 2 * step) {
+    const bool two = m + step < npix;
+    uint4 qd[2], qy[2], qx[2];
+#pragma unroll
+    for (int u = 0; u < 2; ++u) {
+      if (u == 0 || two) {
+        const int64_t mm = m + u * step;
+        qd[u] = __ldg(reinterpret_cast<const uint4*>(dy + mm * dy_ld + ch));
+        qy[u] = __ldg(reinterpret_cast<const uint4*>(y + mm * y_ld + ch));
+        qx[u] = __ldg(reinterpret_cast<const uint4*>(x + mm * x_ld + ch));
+      }
+    }
+#pragma unroll
+    for (int u = 0; u < 2; ++u) {
+      if (u == 0 || two) {
+        float d[8], yy[8], xx[8];
+        unpack8b(qd[u], d); unpack8b(qy[u], yy); unpack8b(qx[u], xx);
+#pragma unroll
+        for (int k = 0; k < 8; ++k) {
+          const float dz = yy[k] > 0.f ? d[k] : d[k] * slope;
+          if (training) {
+            const float xh = (xx[k] - mu[k]) * is[k];
+            d[k] = g[k] * (dz - t0[k] - xh * t1[k]);
+          } else {
+            d[k] = g[k] * dz;
+          }
+        }
+        *reinterpret_cast<uint4*>(dx + (m + u * step) * dx_ld + ch) = pack8b(d);
+      }
+    }
+  }
 }
 
 // bf16, 16-byte loads: thread = (row lane, channel octet); two sums per channel, block tree-reduce
@@ -165,7 +216,44 @@ bn_partial_vec(const __nv_bfloat16* __restrict__ x, int x_ld, const __nv_bfloat1
 #pragma unroll
       for (int i = 0; i < 8; ++i) { mu[i] = mean[oc * 8 + i]; is[i] = invstd[oc * 8 + i]; }
     }
-    for (int64_t m = (int64_t)blockIdx.x * rows_per_iter + rl; m < npix; m += (int64_t)gridDim.x * rows_per_iter) {
+    const int64_t step = (int64_t)gridDim.x * rows_per_iter;
+    int64_t m = (int64_t)blockIdx.x * rows_per_iter + rl;
+    if (!BWD) {                                   // four independent 16-byte loads in flight (HBM-bound pass)
+      for (; m + 3 * step < npix; m += 4 * step) {
+        uint4 qv[4];
+#pragma unroll
+        for (int u = 0; u < 4; ++u) qv[u] = __ldg(reinterpret_cast<const uint4*>(x + (m + u * step) * x_ld + oc * 8));
+#pragma unroll
+        for (int u = 0; u < 4; ++u) {
+          float xv[8];
+          unpack8b(qv[u], xv);
+#pragma unroll
+          for (int i = 0; i < 8; ++i) { s[i] += xv[i]; q[i] = fmaf(xv[i], xv[i], q[i]); }
+        }
+      }
+    }
+    if (BWD) {                                    // two pixels (six 16-byte loads) in flight
+      for (; m + step < npix; m += 2 * step) {
+        uint4 qx[2], qd[2], qy[2];
+#pragma unroll
+        for (int u = 0; u < 2; ++u) {
+          qx[u] = __ldg(reinterpret_cast<const uint4*>(x + (m + u * step) * x_ld + oc * 8));
+          qd[u] = __ldg(reinterpret_cast<const uint4*>(dy + (m + u * step) * dy_ld + oc * 8));
+          qy[u] = __ldg(reinterpret_cast<const uint4*>(y + (m + u * step) * y_ld + oc * 8));
+        }
+#pragma unroll
+        for (int u = 0; u < 2; ++u) {
+          float xv[8], dv[8], yv[8];
+          unpack8b(qx[u], xv); unpack8b(qd[u], dv); unpack8b(qy[u], yv);
+#pragma unroll
+          for (int i = 0; i < 8; ++i) {
+            const float dz = yv[i] > 0.f ? dv[i] : dv[i] * slope;
+            s[i] += dz; q[i] = fmaf(dz, (xv[i] - mu[i]) * is[i], q[i]);
+          }
+        }
+      }
+    }
+    for (; m < npix; m += step) {
       float xv[8];
       unpack8b(__ldg(reinterpret_cast<const uint4*>(x + m * x_ld + oc * 8)), xv);
       if (!BWD) {
@@ -261,6 +349,14 @@ __global__ void bn_bwd_apply(const T* __restrict__ dy, int dy_ld, const T* __res
   dx[m * dx_ld + ch] = from_f32<T>(v);
 }
 
+// grid of the streaming apply kernels: every block covers 256 / (c/8) pixels per iteration, four iterations per trip
+static unsigned bn_stream_blocks(int64_t npix, int c) {
+  const int rows_per_iter = 256 / (c >> 3);
+  int64_t nb = (npix + (int64_t)rows_per_iter * 4 - 1) / ((int64_t)rows_per_iter * 4);
+  if (nb > 16 * kNumSMs) nb = 16 * kNumSMs;
+  return (unsigned)(nb < 1 ? 1 : nb);
+}
+
 template <typename T>
 static int bn_forward_t(const T* x, int x_ld, T* y, int y_ld, int64_t npix, int c, const float* gamma,
                         const float* beta, float* rm, float* rv, float* save_mean, float* save_invstd, int training,
@@ -282,9 +378,9 @@ static int bn_forward_t(const T* x, int x_ld, T* y, int y_ld, int64_t npix, int 
     bn_eval_stats<<<ceil_div(c, 128), 128, 0, st>>>(rm, rv, c, eps, save_mean, save_invstd);
     count_launch();
   }
-  if (sizeof(T) == 2 && c % 8 == 0 && x_ld % 8 == 0 && y_ld % 8 == 0 && ((uintptr_t)x) % 16 == 0 &&
+  if (sizeof(T) == 2 && c % 8 == 0 && c <= 2048 && x_ld % 8 == 0 && y_ld % 8 == 0 && ((uintptr_t)x) % 16 == 0 &&
       ((uintptr_t)y) % 16 == 0)
-    bn_apply_vec<<<ceil_div(npix * (c / 8), 256), 256, 0, st>>>(
+    bn_apply_vec<<<bn_stream_blocks(npix, c), 256, 0, st>>>(
         reinterpret_cast<const __nv_bfloat16*>(x), x_ld, reinterpret_cast<__nv_bfloat16*>(y), y_ld, npix, c, gamma,
         beta, save_mean, save_invstd, slope);
   else
@@ -325,9 +421,9 @@ static int bn_backward_t(const T* dy, int dy_ld, const T* y, int y_ld, const T* 
   else
     bn_bwd_partial<T><<<grid, blk, 0, st>>>(dy, dy_ld, y, y_ld, x, x_ld, npix, c, mean, invstd, slope, p0, p1);
   bn_bwd_finalize<<<ceil_div(c, 128), 128, 0, st>>>(p0, p1, parts, c, tot, dgamma, dbeta, accumulate);
-  if (sizeof(T) == 2 && c % 8 == 0 && dy_ld % 8 == 0 && y_ld % 8 == 0 && x_ld % 8 == 0 && dx_ld % 8 == 0 &&
+  if (sizeof(T) == 2 && c % 8 == 0 && c <= 2048 && dy_ld % 8 == 0 && y_ld % 8 == 0 && x_ld % 8 == 0 && dx_ld % 8 == 0 &&
       ((uintptr_t)dy) % 16 == 0 && ((uintptr_t)y) % 16 == 0 && ((uintptr_t)x) % 16 == 0 && ((uintptr_t)dx) % 16 == 0)
-    bn_bwd_apply_vec<<<ceil_div(npix * (c / 8), 256), 256, 0, st>>>(
+    bn_bwd_apply_vec<<<bn_stream_blocks(npix, c), 256, 0, st>>>(
         reinterpret_cast<const __nv_bfloat16*>(dy), dy_ld, reinterpret_cast<const __nv_bfloat16*>(y), y_ld,
         reinterpret_cast<const __nv_bfloat16*>(x), x_ld, reinterpret_cast<__nv_bfloat16*>(dx), dx_ld, npix, c, gamma,
         mean, invstd, tot, slope, training);
