@@ -1199,9 +1199,9 @@ __device__ __forceinline__ void publish_unit(int* list, uint64_t* bars, int i, i
 }
 
 // warp 0 producer, warp 1 MMA issuer, then SW2_GROUPS epilogue groups of four warps.  A group has SW2_GROUPS column periods
-// to drain one column; with two groups the 64-channel epilogue (TMEM loads compete with N = 192 MMAs) took 2 600-2 900 clk
-// per column against 2 x 1 152 clk of MMAs and the issuer waited 500 clk per column for free accumulator blocks.
-constexpr int SW2_GROUPS = 3;
+// to drain one column.  Three groups (448 threads) were measured at +1 % and cap the kernel at 128 registers per thread,
+// which spills once the side operands are prefetched; two groups (320 threads, 170 registers) it is.
+constexpr int SW2_GROUPS = 2;
 constexpr int SW2_THREADS = 64 + 128 * SW2_GROUPS;
 template <int BN, int CG>
 __global__ void __launch_bounds__(SW2_THREADS, 1)
@@ -1516,6 +1516,19 @@ conv3x3_sweep2_tc(const __grid_constant__ CUtensorMap tmap_x, const Sw2Args a) {
         const bool real = j >= 1 && j <= n_in - 2;
         const int x = x_start + j - 1;
         if (prof) { tc0 = clock64(); ++ncol; }
+        // residual / mask operands of this pixel do not depend on the accumulator: request them before waiting for it
+        // (issued behind the wait they cost one DRAM round trip per column and group - the dgrad launches all have a mask)
+        const long long pix = (long long)img * a.img_stride + (long long)y * a.lane_stride + (long long)x * a.sweep_stride;
+        uint4 pr1[4], pr2[4], pmk[4];
+        auto fetch_side = [&](int cb) {
+#pragma unroll
+          for (int gq = 0; gq < 4; ++gq) {
+            if (a.r1) pr1[gq] = __ldg(reinterpret_cast<const uint4*>(a.r1 + pix * a.r1_ld + cb + gq * 8));
+            if (a.r2) pr2[gq] = __ldg(reinterpret_cast<const uint4*>(a.r2 + pix * a.r2_ld + cb + gq * 8));
+            if (a.mask) pmk[gq] = __ldg(reinterpret_cast<const uint4*>(a.mask + pix * a.mask_ld + cb + gq * 8));
+          }
+        };
+        if (real && row_ok) fetch_side(0);
         mbar_wait(&y_full[pb], ppar);
         if (sb >= 0) mbar_wait(&y_full[sb], spar);
         tc_fence_after();
@@ -1530,11 +1543,11 @@ conv3x3_sweep2_tc(const __grid_constant__ CUtensorMap tmap_x, const Sw2Args a) {
             if (sb >= 0) tmem_st32_zero(saddr + cb);
           }
         } else {
-          const long long pix = (long long)img * a.img_stride + (long long)y * a.lane_stride + (long long)x * a.sweep_stride;
 #pragma unroll 1
           for (int cb = 0; cb < BN; cb += 32) {
             uint32_t z[32];
             float f[32];
+
             if (sb >= 0) {
               uint32_t z2[32];
               tmem_ld32_nowait(taddr + cb, z);
@@ -1567,22 +1580,21 @@ conv3x3_sweep2_tc(const __grid_constant__ CUtensorMap tmap_x, const Sw2Args a) {
               uint4 ov[4];
 #pragma unroll
               for (int gq = 0; gq < 4; ++gq) {
-                const int cc = cb + gq * 8;
                 if (a.r1) {
                   float rr[8];
-                  unpack8(__ldg(reinterpret_cast<const uint4*>(a.r1 + pix * a.r1_ld + cc)), rr);
+                  unpack8(pr1[gq], rr);
 #pragma unroll
                   for (int i = 0; i < 8; ++i) f[gq * 8 + i] = fmaf(a.beta1, rr[i], f[gq * 8 + i]);
                 }
                 if (a.r2) {
                   float rr[8];
-                  unpack8(__ldg(reinterpret_cast<const uint4*>(a.r2 + pix * a.r2_ld + cc)), rr);
+                  unpack8(pr2[gq], rr);
 #pragma unroll
                   for (int i = 0; i < 8; ++i) f[gq * 8 + i] = fmaf(a.beta2, rr[i], f[gq * 8 + i]);
                 }
                 if (a.mask) {
                   float mm[8];
-                  unpack8(__ldg(reinterpret_cast<const uint4*>(a.mask + pix * a.mask_ld + cc)), mm);
+                  unpack8(pmk[gq], mm);
 #pragma unroll
                   for (int i = 0; i < 8; ++i) f[gq * 8 + i] *= (mm[i] > 0.f ? 1.f : a.mask_slope);
                 }
@@ -1598,6 +1610,7 @@ conv3x3_sweep2_tc(const __grid_constant__ CUtensorMap tmap_x, const Sw2Args a) {
 #pragma unroll
                 for (int gq = 0; gq < 4; ++gq) *reinterpret_cast<uint4*>(dst + gq * 8) = ov[gq];
               }
+              if (cb + 32 < BN) fetch_side(cb + 32);                   // in flight during the next chunk's TMEM load
             }
           }
         }
