@@ -241,7 +241,12 @@ def run_ours(args):
                 "launches_per_step": d["launches"] / args.steps, "avg_launch_ms": d["ms"] / d["launches"],
                 "share_of_step": d["ms"] / ms_instr, "conv_share_of_step": conv_ms / ms_instr,
                 "instrumented_ms_per_step": ms_instr / args.steps,
+                # the dense-block layers (intensity 192-432 FLOP/B) sit near the machine's ridge: the same launches against
+                # the measured copy bandwidth, from algorithmic bytes (input slice read once, output slice written once)
+                "hbm": {"achieved": d["bytes"] / (d["ms"] * 1e-3) / 1e9, "peak": peaks["hbm"], "unit": "GB/s",
+                        "frac": d["bytes"] / (d["ms"] * 1e-3) / 1e9 / peaks["hbm"]},
                 "families": {k: {"ms_per_step": v["ms"] / args.steps, "tflops": v["flops"] / (v["ms"] * 1e-3) / 1e12,
+                                 "gbs": v["bytes"] / (v["ms"] * 1e-3) / 1e9,
                                  "launches_per_step": v["launches"] / args.steps} for k, v in sorted(ksum.items())}}
     line = {
         "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps, "warmup": args.warmup,

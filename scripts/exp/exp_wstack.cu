@@ -87,6 +87,58 @@ __global__ void __launch_bounds__(128, 1) wstack_kernel(const __nv_bfloat16* x, 
   if (warp == 0) asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem), "r"(512u) : "memory");
 }
 
+// issue rate of the same instruction shape (MN-major A and B, N = 3*BN): rounds x 24 MMAs over 8 slab rows
+template <int BN>
+__global__ void __launch_bounds__(128, 1) wrate_kernel(long long* clocks, int rounds) {
+  extern __shared__ uint8_t raw[];
+  uint8_t* smem = (uint8_t*)(((uintptr_t)raw + 1023) & ~(uintptr_t)1023);
+  uint8_t* sa = smem;                       // two atoms of 10 rows x 16 px x 128 B, 20480 B apart
+  uint8_t* sb = smem + 40960;               // [8 rows][18 px][BN ch]
+  __shared__ uint64_t bar;
+  __shared__ uint32_t slot;
+  const int warp = threadIdx.x >> 5;
+  if (threadIdx.x == 0) { mbar_init(&bar, 1); asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory"); }
+  if (warp == 0) {
+    asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(&slot)), "r"(512u) : "memory");
+    asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
+  }
+  asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
+  __syncthreads();
+  asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+  const uint32_t tmem = slot;
+  constexpr int N = 3 * BN;
+  constexpr uint32_t idesc = (1u << 4) | (1u << 7) | (1u << 10) | (1u << 15) | (1u << 16) | ((uint32_t)(N >> 3) << 17) | ((128u >> 4) << 24);
+  if (threadIdx.x == 0) {
+    const long long t0 = clock64();
+    for (int it = 0; it < rounds; ++it)
+      for (int g = 0; g < 3; ++g)
+#pragma unroll
+        for (int r = 0; r < 8; ++r) {
+          const uint64_t ad = desc(smem_u32(sa) + (r + g) * 2048, 20480, 1024, 2);
+          const uint64_t bd = desc(smem_u32(sb) + r * 18 * BN * 2, BN * 2, 8 * BN * 2, BN == 64 ? 2 : 4);
+          asm volatile("{\n\t.reg .pred p;\n\tsetp.ne.b32 p, %4, 0;\n\ttcgen05.mma.cta_group::1.kind::f16 [%0], %1, %2, %3, p;\n\t}" ::"r"(tmem + g * N), "l"(ad), "l"(bd), "r"(idesc), "r"(1u) : "memory");
+        }
+    asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(smem_u32(&bar)) : "memory");
+    while (!mbar_try(&bar, 0)) {}
+    clocks[blockIdx.x] = clock64() - t0;
+  }
+  asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
+  __syncthreads();
+  if (warp == 0) asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem), "r"(512u) : "memory");
+}
+template <int BN>
+void rate() {
+  long long* d; cudaMalloc(&d, 148 * 8);
+  cudaFuncSetAttribute(wrate_kernel<BN>, cudaFuncAttributeMaxDynamicSharedMemorySize, 65536);
+  wrate_kernel<BN><<<148, 128, 65536>>>(d, 10);
+  wrate_kernel<BN><<<148, 128, 65536>>>(d, 1000);
+  cudaError_t err = cudaDeviceSynchronize();
+  long long h[148]; cudaMemcpy(h, d, sizeof(h), cudaMemcpyDeviceToHost);
+  const double c = (double)h[0] / (1000.0 * 24);
+  printf("rate MN-major A,B  N=%d: %s  %.1f clk/MMA  (%.0f%% of 8192 FLOP/clk)\n", 3 * BN, cudaGetErrorString(err), c, 100.0 * 2 * 128 * 3 * BN * 16 / c / 8192);
+  cudaFree(d);
+}
+
 template <int BN>
 void run(int kbase) {
   constexpr int N = 3 * BN;
@@ -120,5 +172,6 @@ void run(int kbase) {
 
 int main() {
   for (int kb : {0, 1, 3, 5}) { run<32>(kb); run<64>(kb); }
+  rate<32>(); rate<64>();
   return 0;
 }

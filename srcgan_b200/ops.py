@@ -120,7 +120,7 @@ class KernelTimer:
 
     def __init__(self):
         self.enabled = False
-        self.records = []      # (key, flops, start_event, end_event)
+        self.records = []      # (key, flops, start_event, end_event, algorithmic bytes)
 
     def reset(self):
         self.records = []
@@ -128,11 +128,12 @@ class KernelTimer:
     def summary(self):
         """-> {key: dict(launches, ms, flops)} ; call after torch.cuda.synchronize()"""
         out = {}
-        for key, flops, a, b in self.records:
-            d = out.setdefault(key, {"launches": 0, "ms": 0.0, "flops": 0.0})
+        for key, flops, a, b, nbytes in self.records:
+            d = out.setdefault(key, {"launches": 0, "ms": 0.0, "flops": 0.0, "bytes": 0.0})
             d["launches"] += 1
             d["ms"] += a.elapsed_time(b)
             d["flops"] += flops
+            d["bytes"] += nbytes
         return out
 
 
@@ -151,6 +152,10 @@ class _Timed:
                 stacked = p.cout in (32, 64) and p.cin >= 16 and p.cin % 8 == 0 and p.pad == 1     # wgrad_stack_ok
                 self.key = "conv3x3_wgrad_stack_tc" if stacked else "conv3x3_wgrad_halo_tc<%d>" % (64 if p.cout % 64 == 0 else 32)
             self.flops = 2.0 * p.n * p.ho * p.wo * p.cin * p.cout * p.kh * p.kw
+            # algorithmic bytes (single read of the input slice, single write / read of the output-side slice; stride and
+            # the epilogue's residual / mask operands ignored): what an HBM roofline is computed from
+            esz = 2 if p.dtype == DT_BF16 else 4
+            self.bytes = float(esz) * p.n * (p.h * p.w * p.cin + p.ho * p.wo * p.cout)
 
     def __enter__(self):
         if self.on:
@@ -166,7 +171,7 @@ class _Timed:
                 name = _lib.last_kernel()
                 if name.startswith("conv"):
                     self.key = name
-            timer.records.append((self.key, self.flops, self.a, self.b))
+            timer.records.append((self.key, self.flops, self.a, self.b, self.bytes))
         return False
 
 
