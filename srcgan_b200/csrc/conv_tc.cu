@@ -2634,11 +2634,22 @@ constexpr int WS_TH = 8, WS_TW = 16;                                  // pixel t
 constexpr int WS_X_ROWS = WS_TH + 2;
 constexpr int WS_X_ATOM = WS_X_ROWS * WS_TW * 128;                    // 20480: [10 rows][16 px][64 ch]
 constexpr int WS_G_W = WS_TW + 2;
-constexpr int WS_G_BYTES = WS_TH * WS_G_W * 64;                       // 9216:  [8 rows][18 px][32 ch]
-constexpr int WS_STAGE = 2 * WS_X_ATOM + WS_G_BYTES;                  // 50176
-constexpr int WS_STAGES = (SMEM_BUDGET - SMEM_AUX - 1024) / WS_STAGE; // 4
-constexpr int WS_SMEM = WS_STAGES * WS_STAGE + SMEM_AUX + 1024;
-static_assert(WS_STAGES >= 3, "wgrad pipeline too shallow");
+// BN = 32: N = 96, channel blocks of 128 (two X atoms) or <= 64 (one atom, two vertical taps per M).
+// BN = 64: N = 192; three accumulators would need 576 TMEM columns, so every channel block is <= 64 channels with two
+//          vertical taps per M (2 x 192 columns) - X is then read once for all 64 output channels.
+template <int BN>
+struct W4Cfg {
+  static constexpr int N = 3 * BN;
+  static constexpr int CBLK = BN == 64 ? 64 : 128;                    // input channels per CTA
+  static constexpr int NATOM = CBLK / 64;
+  static constexpr int PX = BN * 2;                                   // bytes of one dY pixel in the slab
+  static constexpr int G_BYTES = WS_TH * WS_G_W * PX;                 // [8 rows][18 px][BN ch]: 9216 / 18432
+  static constexpr int STAGE = NATOM * WS_X_ATOM + G_BYTES;           // 50176 / 38912
+  static constexpr int STAGES_RAW = (SMEM_BUDGET - SMEM_AUX - 1024) / STAGE;
+  static constexpr int STAGES = STAGES_RAW > 6 ? 6 : STAGES_RAW;      // 4 / 5
+  static constexpr int SMEM = STAGES * STAGE + SMEM_AUX + 1024;
+  static_assert(STAGES >= 3, "wgrad pipeline too shallow");
+};
 
 struct Wg4Args {
   int n, ho, wo, cin, cout;
@@ -2653,8 +2664,16 @@ __host__ __device__ constexpr uint32_t desc_hi_sw64(uint32_t sbo_bytes) {
   return (sbo_bytes >> 4) | (1u << 14) | (4u << 29);                  // SBO, descriptor version 1, SWIZZLE_64B
 }
 
+__host__ __device__ constexpr uint32_t desc_hi_sw(uint32_t sbo_bytes, int bn) {
+  return bn == 64 ? desc_hi(sbo_bytes) : desc_hi_sw64(sbo_bytes);     // 128-byte pixels: SWIZZLE_128B, 64-byte: SWIZZLE_64B
+}
+
+template <int BN>
 __global__ void __launch_bounds__(NUM_THREADS, 1)
 conv3x3_wgrad_stack_tc(const __grid_constant__ CUtensorMap tmap_x, const __grid_constant__ CUtensorMap tmap_g, const Wg4Args a) {
+  using C = W4Cfg<BN>;
+  constexpr int WS_STAGES = C::STAGES, WS_STAGE = C::STAGE, WS_G_BYTES = C::G_BYTES;
+  constexpr int G_OFF = C::NATOM * WS_X_ATOM;                          // dY slab offset inside a stage
   extern __shared__ uint8_t smem_raw[];
   uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~(uintptr_t)1023);
   uint8_t* aux = smem + WS_STAGES * WS_STAGE;
@@ -2686,9 +2705,9 @@ conv3x3_wgrad_stack_tc(const __grid_constant__ CUtensorMap tmap_x, const __grid_
   tc_fence_after();
   const uint32_t tmem_base = *tmem_slot;
 
-  const int c_rem = a.cin - cb * 128;
-  const bool paired = c_rem <= 64;                                   // one 64-channel atom: M = (tap kh | tap kh + 1)
-  const int ngroups = paired ? 2 : 3;                                // accumulators of 96 columns
+  const int c_rem = a.cin - cb * C::CBLK;
+  const bool paired = BN == 64 || c_rem <= 64;                       // one 64-channel atom: M = (tap kh | tap kh + 1)
+  const int ngroups = paired ? 2 : 3;                                // accumulators of N columns
   const long long t_beg = (long long)split * a.tiles_per_split;
   long long t_end = t_beg + a.tiles_per_split;
   if (t_end > a.num_tiles) t_end = a.num_tiles;
@@ -2709,17 +2728,17 @@ conv3x3_wgrad_stack_tc(const __grid_constant__ CUtensorMap tmap_x, const __grid_
       uint8_t* sx = smem + stage * WS_STAGE;
       if (elect_one()) {
         mbar_expect_tx(&full_bar[stage], stage_tx);
-        tma_load_4d(&tmap_x, &full_bar[stage], sx, cb * 128, x0, y0 - 1, img);
-        if (!paired) tma_load_4d(&tmap_x, &full_bar[stage], sx + WS_X_ATOM, cb * 128 + 64, x0, y0 - 1, img);
-        tma_load_4d(&tmap_g, &full_bar[stage], sx + 2 * WS_X_ATOM, nb * 32, x0 - 1, y0, img);
+        tma_load_4d(&tmap_x, &full_bar[stage], sx, cb * C::CBLK, x0, y0 - 1, img);
+        if (!paired) tma_load_4d(&tmap_x, &full_bar[stage], sx + WS_X_ATOM, cb * C::CBLK + 64, x0, y0 - 1, img);
+        tma_load_4d(&tmap_g, &full_bar[stage], sx + G_OFF, nb * BN, x0 - 1, y0, img);
       }
       __syncwarp();
       if (++stage == WS_STAGES) { stage = 0; phase ^= 1; }
     }
   } else if (warp == 1) {
-    constexpr uint32_t idesc = tcw::umma_idesc_mn(128, 96);
-    constexpr uint32_t a_hi = desc_hi(1024), g_hi = desc_hi_sw64(512);  // 8 pixels of a row: 8 x 128 B resp. 8 x 64 B
-    constexpr uint32_t ROW_A = WS_TW * 128, ROW_G = WS_G_W * 64;        // slab row pitches: 2048 B, 1152 B
+    constexpr uint32_t idesc = tcw::umma_idesc_mn(128, C::N);
+    constexpr uint32_t a_hi = desc_hi(1024), g_hi = desc_hi_sw(8 * C::PX, BN);   // 8 pixels of a row: 8 x 128 B resp. 8 dY pixels
+    constexpr uint32_t ROW_A = WS_TW * 128, ROW_G = WS_G_W * C::PX;     // slab row pitches: 2048 B, 1152 / 2304 B
     int stage = 0;
     uint32_t phase = 0;
     uint32_t accumulate = 0;
@@ -2727,14 +2746,14 @@ conv3x3_wgrad_stack_tc(const __grid_constant__ CUtensorMap tmap_x, const __grid_
       mbar_wait(&full_bar[stage], phase);
       tc_fence_after();
       const uint32_t sx = smem_u32(smem + stage * WS_STAGE);
-      const uint32_t sg = sx + 2 * WS_X_ATOM;
+      const uint32_t sg = sx + G_OFF;
       if (elect_one()) {
         // A: LBO = distance of the second 64-row half of M (the other channel atom, or the next vertical tap's row)
         const uint32_t a_lo = desc_lo(sx, paired ? ROW_A : (uint32_t)WS_X_ATOM);
-        const uint32_t g_lo = desc_lo(sg, 64);                          // N atoms one pixel (64 B) apart
+        const uint32_t g_lo = desc_lo(sg, C::PX);                       // N atoms one pixel apart
         for (int g = 0; g < ngroups; ++g) {
           const int kh0 = paired ? 2 * g : g;                           // vertical tap of the first half of M
-          const uint32_t tmem_d = tmem_base + (uint32_t)(g * 96);
+          const uint32_t tmem_d = tmem_base + (uint32_t)(g * C::N);
 #pragma unroll
           for (int r = 0; r < WS_TH; ++r)
             umma_bf16_w(tmem_d, a_lo + (uint32_t)(((r + kh0) * ROW_A) >> 4), a_hi, g_lo + (uint32_t)((r * ROW_G) >> 4), g_hi, idesc,
@@ -2753,22 +2772,24 @@ conv3x3_wgrad_stack_tc(const __grid_constant__ CUtensorMap tmap_x, const __grid_
     const int row = q * 32 + lane;
     const bool has_work = t_end > t_beg;
     if (do_db) {
-      // thread = (8-channel group c4, pixel lane): four 16-byte reads per tile from the SWIZZLE_64B slab
-      // [8 rows][18 px][32 ch] (interior pixels only; pixels outside the image were zero-filled by TMA)
-      const int t = (warp - 2) * 32 + lane, c4 = t & 3, pl = t >> 2;
+      // thread = (8-channel group cg, pixel lane): 16-byte reads from the swizzled slab [8 rows][18 px][BN ch]
+      // (interior pixels only; pixels outside the image were zero-filled by TMA)
+      constexpr int CG8 = BN / 8, PL = 128 / CG8;                       // channel groups, pixel lanes
+      const int t = (warp - 2) * 32 + lane, cg = t % CG8, pl = t / CG8;
       float acc[8] = {0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f};
       int stage = 0;
       uint32_t phase = 0;
       for (long long tt = t_beg; tt < t_end; ++tt) {
         mbar_wait(&full_bar[stage], phase);
-        const uint32_t sg = smem_u32(smem + stage * WS_STAGE) + 2 * WS_X_ATOM;
+        const uint32_t sg = smem_u32(smem + stage * WS_STAGE) + G_OFF;
 #pragma unroll
-        for (int i = 0; i < 4; ++i) {
-          const int px = pl + 32 * i;
+        for (int i = 0; i < 128 / PL; ++i) {
+          const int px = pl + PL * i;
           const int idx = (px >> 4) * WS_G_W + (px & 15) + 1;
+          const int sw = BN == 64 ? (cg ^ (idx & 7)) : (cg ^ ((idx >> 1) & 3));     // SWIZZLE_128B / SWIZZLE_64B
           uint4 qv;
           asm volatile("ld.shared.v4.b32 {%0, %1, %2, %3}, [%4];" : "=r"(qv.x), "=r"(qv.y), "=r"(qv.z), "=r"(qv.w)
-                       : "r"(sg + (uint32_t)(idx * 64 + ((c4 ^ ((idx >> 1) & 3)) << 4))));
+                       : "r"(sg + (uint32_t)(idx * C::PX + (sw << 4))));
           float f8[8];
           unpack8(qv, f8);
 #pragma unroll
@@ -2778,22 +2799,22 @@ conv3x3_wgrad_stack_tc(const __grid_constant__ CUtensorMap tmap_x, const __grid_
         if (lane == 0) mbar_arrive(&empty_bar[stage]);
         if (++stage == WS_STAGES) { stage = 0; phase ^= 1; }
       }
-      // lanes with equal (lane & 3) hold the same channel group: fold lane bits 2..4, then the four warps through smem
+      // lanes with equal (lane % CG8) hold the same channel group: fold the other lane bits, then the four warps through smem
 #pragma unroll
       for (int j = 0; j < 8; ++j) {
-        acc[j] += __shfl_xor_sync(0xffffffffu, acc[j], 4);
+        if (CG8 == 4) acc[j] += __shfl_xor_sync(0xffffffffu, acc[j], 4);
         acc[j] += __shfl_xor_sync(0xffffffffu, acc[j], 8);
         acc[j] += __shfl_xor_sync(0xffffffffu, acc[j], 16);
       }
-      float* red = reinterpret_cast<float*>(aux + 512);                 // [4 warps][32 channels]
-      if (lane < 4) {
+      float* red = reinterpret_cast<float*>(aux + 512);                 // [4 warps][BN channels]
+      if (lane < CG8) {
 #pragma unroll
-        for (int j = 0; j < 8; ++j) red[q * 32 + lane * 8 + j] = acc[j];
+        for (int j = 0; j < 8; ++j) red[q * BN + lane * 8 + j] = acc[j];
       }
       asm volatile("bar.sync 1, 128;" ::: "memory");
-      if (t < 32) {
-        const float sum = (red[t] + red[32 + t]) + (red[64 + t] + red[96 + t]);
-        a.dbpart[(long long)split * a.cout + nb * 32 + t] = has_work ? sum : 0.f;
+      if (t < BN) {
+        const float sum = (red[t] + red[BN + t]) + (red[2 * BN + t] + red[3 * BN + t]);
+        a.dbpart[(long long)split * a.cout + nb * BN + t] = has_work ? sum : 0.f;
       }
     }
     mbar_wait(done_bar, 0);
@@ -2801,24 +2822,27 @@ conv3x3_wgrad_stack_tc(const __grid_constant__ CUtensorMap tmap_x, const __grid_
 #pragma unroll 1
     for (int g = 0; g < ngroups; ++g) {
       int kh, ci;
-      if (paired) { kh = 2 * g + (row >> 6); ci = cb * 128 + (row & 63); }
-      else { kh = g; ci = cb * 128 + row; }
+      if (paired) { kh = 2 * g + (row >> 6); ci = cb * C::CBLK + (row & 63); }
+      else { kh = g; ci = cb * C::CBLK + row; }
       const bool row_ok = kh < 3 && ci < a.cin;
 #pragma unroll 1
       for (int j = 0; j < 3; ++j) {
-        uint32_t v[32];
-        tmem_ld32(tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)(g * 96 + j * 32), v);
-        if (row_ok) {
-          const int tap = kh * 3 + (2 - j);
-          float* dst = a.part + (((long long)split * 9 + tap) * a.cin + ci) * a.cout + nb * 32;
+#pragma unroll 1
+        for (int c32 = 0; c32 < BN; c32 += 32) {
+          uint32_t v[32];
+          tmem_ld32(tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)(g * C::N + j * BN + c32), v);
+          if (row_ok) {
+            const int tap = kh * 3 + (2 - j);
+            float* dst = a.part + (((long long)split * 9 + tap) * a.cin + ci) * a.cout + nb * BN + c32;
 #pragma unroll
-          for (int i = 0; i < 8; ++i) {
-            float4 o;
-            o.x = has_work ? __uint_as_float(v[4 * i + 0]) : 0.f;
-            o.y = has_work ? __uint_as_float(v[4 * i + 1]) : 0.f;
-            o.z = has_work ? __uint_as_float(v[4 * i + 2]) : 0.f;
-            o.w = has_work ? __uint_as_float(v[4 * i + 3]) : 0.f;
-            *reinterpret_cast<float4*>(dst + 4 * i) = o;
+            for (int i = 0; i < 8; ++i) {
+              float4 o;
+              o.x = has_work ? __uint_as_float(v[4 * i + 0]) : 0.f;
+              o.y = has_work ? __uint_as_float(v[4 * i + 1]) : 0.f;
+              o.z = has_work ? __uint_as_float(v[4 * i + 2]) : 0.f;
+              o.w = has_work ? __uint_as_float(v[4 * i + 3]) : 0.f;
+              *reinterpret_cast<float4*>(dst + 4 * i) = o;
+            }
           }
         }
       }
@@ -2831,14 +2855,17 @@ conv3x3_wgrad_stack_tc(const __grid_constant__ CUtensorMap tmap_x, const __grid_
   }
 }
 
+static int bn4(const srcgan_conv_params* p) { return p->cout == 64 && !getenv("SRCGAN_B200_WSTACK32") ? 64 : 32; }
+
 static void plan4(const srcgan_conv_params* p, Wg4Args& a) {
-  a.cblocks = (p->cin + 127) / 128;
-  a.nblocks = p->cout / 32;
+  const int bn = bn4(p);
+  a.cblocks = bn == 64 ? (p->cin + 63) / 64 : (p->cin + 127) / 128;
+  a.nblocks = p->cout / bn;
   a.tiles_x = (p->wo + WS_TW - 1) / WS_TW;
   a.tiles_y = (p->ho + WS_TH - 1) / WS_TH;
   a.num_tiles = (long long)a.tiles_x * a.tiles_y * p->n;
   const int groups = a.cblocks * a.nblocks;
-  long long s = (kNumSMs + groups - 1) / groups;          // one wave of CTAs: fewer fp32 partials to reduce
+  long long s = kNumSMs / groups;                          // one wave of CTAs, never a second one for a remainder
   if (s > a.num_tiles) s = a.num_tiles;
   if (s < 1) s = 1;
   a.tiles_per_split = (a.num_tiles + s - 1) / s;
@@ -2863,16 +2890,18 @@ static int make_tmap_box(CUtensorMap* tm, const void* ptr, int c, int w, int h, 
   return SRCGAN_OK;
 }
 
+template <int BN>
 static int launch4(const CUtensorMap& tx, const CUtensorMap& tg, const Wg4Args& a, cudaStream_t st) {
+  using C = W4Cfg<BN>;
   static bool attr_set = false;
   if (!attr_set) {
-    SRCGAN_CUDA(cudaFuncSetAttribute(conv3x3_wgrad_stack_tc, cudaFuncAttributeMaxDynamicSharedMemorySize, WS_SMEM));
+    SRCGAN_CUDA(cudaFuncSetAttribute(conv3x3_wgrad_stack_tc<BN>, cudaFuncAttributeMaxDynamicSharedMemorySize, C::SMEM));
     attr_set = true;
   }
   const unsigned grid = (unsigned)(a.cblocks * a.nblocks * a.splits);
-  conv3x3_wgrad_stack_tc<<<grid, NUM_THREADS, WS_SMEM, st>>>(tx, tg, a);
+  conv3x3_wgrad_stack_tc<BN><<<grid, NUM_THREADS, C::SMEM, st>>>(tx, tg, a);
   count_launch();
-  return check_launch("conv3x3_wgrad_stack_tc");
+  return check_launch(BN == 64 ? "conv3x3_wgrad_stack_tc<64>" : "conv3x3_wgrad_stack_tc<32>");
 }
 }  // namespace tcw4
 
@@ -2938,10 +2967,11 @@ int conv_wgrad_tc(const srcgan_conv_params* p, float* dw, float* db, int accumul
     int rc = tcw4::make_tmap_box(&tx, p->x, p->cin, p->w, p->h, p->n, p->x_ld, 64, tcw4::WS_TW, tcw4::WS_X_ROWS,
                                  CU_TENSOR_MAP_SWIZZLE_128B, "conv_wgrad_tc(stack x)");
     if (rc) return rc;
-    rc = tcw4::make_tmap_box(&tg, p->y, p->cout, p->wo, p->ho, p->n, p->y_ld, 32, tcw4::WS_G_W, tcw4::WS_TH,
-                             CU_TENSOR_MAP_SWIZZLE_64B, "conv_wgrad_tc(stack dy)");
+    const int bn = tcw4::bn4(p);
+    rc = tcw4::make_tmap_box(&tg, p->y, p->cout, p->wo, p->ho, p->n, p->y_ld, bn, tcw4::WS_G_W, tcw4::WS_TH,
+                             bn == 64 ? CU_TENSOR_MAP_SWIZZLE_128B : CU_TENSOR_MAP_SWIZZLE_64B, "conv_wgrad_tc(stack dy)");
     if (rc) return rc;
-    rc = tcw4::launch4(tx, tg, a4, st);
+    rc = bn == 64 ? tcw4::launch4<64>(tx, tg, a4, st) : tcw4::launch4<32>(tx, tg, a4, st);
     if (rc) return rc;
     rc = wgrad_reduce_launch(reinterpret_cast<const float*>(ws), a4.splits, 9, p->cin, p->cout, dw, accumulate,
                              p->alpha, st);
