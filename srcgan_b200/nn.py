@@ -25,7 +25,7 @@ import torch
 import torch.nn as nn
 
 from . import ops
-from .ops import ENGINE_SIMT, ENGINE_TC, Slice, WL_RSCK, WL_RSKC, WL_TC_DGRAD_S2
+from .ops import ENGINE_SIMT, ENGINE_TC, Slice, WL_RSCK, WL_RSKC, WL_TC, WL_TC_DGRAD_S2
 
 LRELU = 0.2
 
@@ -143,6 +143,24 @@ class _NetBase(nn.Module):
     def _fprop(self, conv: nn.Conv2d, x: Slice, y: Slice, *, upsample=False, **ep) -> None:
         k, s, p = conv.kernel_size[0], conv.stride[0], conv.padding[0]
         eng, layout = select_engine(x.c, y.c, k, s, upsample, x.dtype, y.h, y.w)
+        if (eng == ENGINE_SIMT and x.dtype == torch.bfloat16 and y.c <= 4 and k == 4 and s == 1 and not upsample
+                and x.c % 64 == 0 and not ep.get("r1") and not ep.get("r2") and not ep.get("mask")
+                and select_engine(x.c, 32, k, s, False, x.dtype, y.h, y.w)[0] == ENGINE_TC):
+            # patch-logit layer (256 -> 1, 4x4): the one-thread-per-pixel SIMT kernel takes 1.8 ms at batch 64; run it on
+            # the tcgen05 implicit GEMM with the output channels zero-padded to 32 and copy the real channels out
+            oc = conv.out_channels
+            wp = self._pk().get(("f32pad", id(conv)), (conv.weight,),
+                                lambda: torch.cat([conv.weight.detach(),
+                                                   conv.weight.new_zeros((32 - oc,) + tuple(conv.weight.shape[1:]))]),
+                                WL_TC, x.dtype)
+            bias = None
+            if conv.bias is not None:
+                bias = torch.zeros(32, dtype=torch.float32, device=conv.bias.device)
+                bias[:oc] = conv.bias.detach()
+            tmp = Slice(ops.new_buf(y.n, y.h, y.w, 32, x.dtype, x.buf.device))
+            ops.conv_fprop(x, wp, bias, tmp, k, s, p, engine=ENGINE_TC, **ep)
+            y.buf[..., y.c0:y.c0 + y.c].copy_(tmp.buf[..., :y.c])
+            return
         ops.conv_fprop(x, self._w_f(conv, x.dtype, layout), conv.bias, y, k, s, p, upsample=upsample, engine=eng, **ep)
 
     def _dgrad(self, conv: nn.Conv2d, dy: Slice, dx: Slice, **ep) -> None:
