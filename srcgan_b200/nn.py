@@ -188,6 +188,23 @@ class _NetBase(nn.Module):
             raise RuntimeError("inconsistent accumulate state")
         from . import engine as _engine
         eng = _engine.select_wgrad(x.c, dy.c, k, s, upsample, x.dtype, dy.h, dy.w)
+        if (eng == ENGINE_SIMT and dw is not None and x.dtype == torch.bfloat16 and dy.c <= 4 and k == 4 and s == 1
+                and not upsample and x.c % 64 == 0
+                and _engine.select_wgrad(x.c, 64, k, s, False, x.dtype, dy.h, dy.w) == ENGINE_TC):
+            # patch-logit layer: weight gradient on the tcgen05 wgrad kernel with dY zero-padded to 64 channels
+            oc = dy.c
+            dyp = ops.new_buf(dy.n, dy.h, dy.w, 64, x.dtype, x.buf.device)
+            dyp.zero_()
+            dyp[..., :oc].copy_(dy.buf[..., dy.c0:dy.c0 + oc])
+            dwp = torch.empty((64,) + tuple(dw.shape[1:]), dtype=torch.float32, device=dw.device)
+            ops.conv_wgrad(x, Slice(dyp), dwp, None, k, s, p, accumulate=False, alpha=alpha, engine=ENGINE_TC)
+            if acc_w:
+                dw.add_(dwp[:oc])
+            else:
+                dw.copy_(dwp[:oc])
+            if db is not None:
+                ops.colsum(dy, db, alpha=alpha, accumulate=acc_b)
+            return
         ops.conv_wgrad(x, dy, dw, db, k, s, p, upsample=upsample, accumulate=acc_w or acc_b, alpha=alpha, engine=eng)
 
 
