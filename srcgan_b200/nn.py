@@ -205,6 +205,25 @@ class _NetBase(nn.Module):
             if db is not None:
                 ops.colsum(dy, db, alpha=alpha, accumulate=acc_b)
             return
+        if (eng == ENGINE_SIMT and dw is not None and x.dtype == torch.bfloat16 and x.c <= 4 and k == 4 and s == 2
+                and not upsample and dy.c % 64 == 0
+                and _engine.select_wgrad(16, dy.c, k, s, False, x.dtype, dy.h, dy.w) == ENGINE_TC):
+            # first discriminator layer (3 -> 64, 4x4 stride 2): weight gradient on the tcgen05 wgrad kernel with the image
+            # zero-padded to 16 channels
+            ic = x.c
+            xp = ops.new_buf(x.n, x.h, x.w, 16, x.dtype, x.buf.device)
+            xp.zero_()
+            xp[..., :ic].copy_(x.buf[..., x.c0:x.c0 + ic])
+            dwp = torch.empty((dw.shape[0], 16) + tuple(dw.shape[2:]), dtype=torch.float32, device=dw.device)
+            ops.conv_wgrad(Slice(xp), dy, dwp, db, k, s, p, accumulate=False, alpha=alpha, engine=ENGINE_TC) if not acc_b else \
+                ops.conv_wgrad(Slice(xp), dy, dwp, None, k, s, p, accumulate=False, alpha=alpha, engine=ENGINE_TC)
+            if acc_b and db is not None:
+                ops.colsum(dy, db, alpha=alpha, accumulate=True)
+            if acc_w:
+                dw.add_(dwp[:, :ic])
+            else:
+                dw.copy_(dwp[:, :ic])
+            return
         ops.conv_wgrad(x, dy, dw, db, k, s, p, upsample=upsample, accumulate=acc_w or acc_b, alpha=alpha, engine=eng)
 
 
