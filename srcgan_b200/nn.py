@@ -174,6 +174,18 @@ class _NetBase(nn.Module):
             ops.conv_fprop(dy, self._w_t(conv, dy.dtype, layout), None, dx, k, 1, k - 1 - p, engine=eng, **ep)
         elif _engine_mod().tc_dgrad_s2_supported(dx.c, dy.c, k, s, p, dy.dtype):
             ops.conv_dgrad(dy, self._w_d2(conv, dy.dtype), dx, k, s, p, engine=ENGINE_TC, **ep)
+        elif (dx.c <= 4 and not ep and _engine_mod().tc_dgrad_s2_supported(32, dy.c, k, s, p, dy.dtype)):
+            # gradient w.r.t. a 3-channel image through a stride-2 layer (first discriminator layer): the four-phase
+            # tcgen05 dgrad with the input channels zero-padded to 32, real channels copied out
+            ic = dx.c
+            wp = self._pk().get(("d2pad", id(conv)), (conv.weight,),
+                                lambda: torch.cat([conv.weight.detach(),
+                                                   conv.weight.new_zeros((conv.weight.shape[0], 32 - ic) +
+                                                                         tuple(conv.weight.shape[2:]))], dim=1),
+                                WL_TC_DGRAD_S2, dy.dtype)
+            tmp = Slice(ops.new_buf(dx.n, dx.h, dx.w, 32, dy.dtype, dy.buf.device))
+            ops.conv_dgrad(dy, wp, tmp, k, s, p, engine=ENGINE_TC)
+            dx.buf[..., dx.c0:dx.c0 + ic].copy_(tmp.buf[..., :ic])
         else:
             ops.conv_dgrad(dy, self._w_d(conv, dy.dtype), dx, k, s, p, **ep)
 
