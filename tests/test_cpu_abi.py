@@ -53,6 +53,30 @@ def test_argument_validation_without_gpu():
     assert lib.srcgan_pack_weights(None, 1, 1, 3, 3, 0, 0, None, None) == 1
 
 
+def test_introspection_entry_points_without_gpu():
+    """launch counter and last-kernel name are callable before any launch (bench.py keys its roofline record on them)."""
+    from srcgan_b200 import _lib
+    assert _lib.launch_count() >= 0
+    assert isinstance(_lib.last_kernel(), str)
+
+
+def test_thin_layers_are_padded_onto_the_tensor_core_engine():
+    """engine.select() sends the 1- and 3-channel sides of the discriminator to SIMT; nn.py pads them to 16/32/64
+    channels for the tcgen05 kernels - the padded shapes must be ones the tensor-core engine accepts."""
+    import torch
+    from srcgan_b200 import engine
+    from srcgan_b200._lib import ENGINE_SIMT, ENGINE_TC
+    bf = torch.bfloat16
+    assert engine.select(256, 1, 4, 1, False, bf, 62, 62)[0] == ENGINE_SIMT
+    assert engine.select(256, 32, 4, 1, False, bf, 62, 62)[0] == ENGINE_TC           # patch logits, cout padded to 32
+    assert engine.select_wgrad(256, 1, 4, 1, False, bf, 62, 62) == ENGINE_SIMT
+    assert engine.select_wgrad(256, 64, 4, 1, False, bf, 62, 62) == ENGINE_TC        # its wgrad, dY padded to 64
+    assert engine.select_wgrad(3, 64, 4, 2, False, bf, 128, 128) == ENGINE_SIMT
+    assert engine.select_wgrad(16, 64, 4, 2, False, bf, 128, 128) == ENGINE_TC       # first layer wgrad, image padded to 16
+    assert not engine.tc_dgrad_s2_supported(3, 64, 4, 2, 1, bf)
+    assert engine.tc_dgrad_s2_supported(32, 64, 4, 2, 1, bf)                         # its dgrad, image padded to 32
+
+
 def test_missing_library_fails_loudly(tmp_path, monkeypatch):
     from srcgan_b200 import _lib
     monkeypatch.setattr(_lib, "_lib", None)

@@ -267,6 +267,35 @@ def test_conv_tc_matches_reference(case):
     assert float(ys.buf[..., :64].abs().max()) == 0.0
 
 
+@pytest.mark.parametrize("env", [{}, {"SRCGAN_B200_SWEEP_STATIC": "1"}, {"SRCGAN_B200_SWEEP_TR": "0"},
+                                 {"SRCGAN_B200_SWEEP2_CG": "1"}, {"SRCGAN_B200_NO_SWEEP2": "1"}])
+def test_conv_tc_sweep_variants(env, monkeypatch):
+    """The paired sweep's launch variants (dynamic / static unit queue, row / column orientation, CTA pair / single CTA) and
+    the kw-stacked fallback all compute the same convolution; the unit queue does not change a single bit."""
+    from srcgan_b200 import ops
+    n, h, w, cin, cout = 3, 256, 160, 96, 32
+    x = rand((n, cin, h, w), 31).bfloat16().float()
+    wt = rand((cout, cin, 3, 3), 32, 0.1).bfloat16().float()
+    b = rand((cout,), 33)
+    y_ref = F.conv2d(x, wt, b, stride=1, padding=1)
+    xs = to_nhwc(x, torch.bfloat16, ctot=192, c0=0)
+    wp = ops.pack_weights(wt.to(DEV), ops.WL_TC, torch.bfloat16)
+
+    def run():
+        ys = ops.Slice(torch.zeros((n, h, w, 192), dtype=torch.bfloat16, device=DEV), 96, cout)
+        ops.conv_fprop(xs, wp, b.to(DEV), ys, 3, 1, 1, act=0.2, engine=ops.ENGINE_TC)
+        torch.cuda.synchronize()
+        return ys
+
+    base = run()
+    for k, v in env.items():
+        monkeypatch.setenv(k, v)
+    got = run()
+    assert relerr(from_nhwc(got), F.leaky_relu(y_ref, 0.2)) < 1e-2
+    if env in ({}, {"SRCGAN_B200_SWEEP_STATIC": "1"}):
+        assert torch.equal(got.buf, base.buf)
+
+
 @pytest.mark.parametrize("shape", [(2, 32, 16, 128, 64), (1, 160, 24, 64, 64), (1, 128, 50, 128, 32)])
 def test_conv_tc_epilogue_matches_simt(shape):
     from srcgan_b200 import ops
