@@ -296,6 +296,49 @@ def test_conv_tc_sweep_variants(env, monkeypatch):
         assert torch.equal(got.buf, base.buf)
 
 
+@pytest.mark.parametrize("cin,cout", [(64, 32), (160, 32), (192, 64)])
+def test_conv_tc_full_size_identities(cin, cout):
+    """BASELINE's full size (batch 64, 256 x 256, the dense block's 192-channel concat buffer) is far beyond what the CPU
+    oracle can check element-wise; two size-independent properties tie the three tcgen05 kernels together there:
+      * linearity: conv(2x) == 2 conv(x) BIT FOR BIT (a power-of-two scale commutes with every bf16 / fp32 rounding), with
+        and without the LeakyReLU-mask epilogue of the dgrad steps;
+      * the trilinear form: <conv(x; W), g> == <W, wgrad(x, g)> (both equal sum x*W*g; bf16 output rounding of the left side
+        and fp32 accumulation order are the only differences)."""
+    from srcgan_b200 import ops
+    n, h, w = 64, 256, 256
+    g0 = torch.Generator(device=DEV).manual_seed(7)
+    xb = torch.randn((n, h, w, 192), dtype=torch.bfloat16, device=DEV, generator=g0)
+    x = ops.Slice(xb, 0, cin)
+    wt = (torch.randn((cout, cin, 3, 3), device=DEV, generator=g0) * 0.05).bfloat16().float()
+    wp = ops.pack_weights(wt, ops.WL_TC, torch.bfloat16)
+    y1 = ops.Slice(torch.empty((n, h, w, cout), dtype=torch.bfloat16, device=DEV))
+    ops.conv_fprop(x, wp, None, y1, 3, 1, 1, engine=ops.ENGINE_TC)
+    x2 = ops.Slice(xb * 2, 0, cin)
+    y2 = ops.Slice(torch.empty((n, h, w, cout), dtype=torch.bfloat16, device=DEV))
+    ops.conv_fprop(x2, wp, None, y2, 3, 1, 1, engine=ops.ENGINE_TC)
+    assert torch.equal(y2.buf, y1.buf * 2)
+    mk = ops.Slice(torch.randn((n, h, w, cout), dtype=torch.bfloat16, device=DEV, generator=g0))
+    m1 = ops.Slice(torch.empty((n, h, w, cout), dtype=torch.bfloat16, device=DEV))
+    m2 = ops.Slice(torch.empty((n, h, w, cout), dtype=torch.bfloat16, device=DEV))
+    ops.conv_fprop(x, wp, None, m1, 3, 1, 1, mask=mk, mask_slope=0.25, engine=ops.ENGINE_TC)
+    ops.conv_fprop(x2, wp, None, m2, 3, 1, 1, mask=mk, mask_slope=0.25, engine=ops.ENGINE_TC)
+    assert torch.equal(m2.buf, m1.buf * 2)
+    assert torch.equal(m1.buf, torch.where(mk.buf > 0, y1.buf, y1.buf * 0.25))      # x0.25 is exact in bf16
+    del x2, y2, m1, m2, mk
+    gy = ops.Slice(torch.randn((n, h, w, cout), dtype=torch.bfloat16, device=DEV, generator=g0))
+    dw = torch.empty((cout, cin, 3, 3), device=DEV)
+    db = torch.empty((cout,), device=DEV)
+    ops.conv_wgrad(x, gy, dw, db, 3, 1, 1, engine=ops.ENGINE_TC)
+    torch.cuda.synchronize()
+    lhs = float((y1.buf.double() * gy.buf.double()).sum())
+    rhs = float((dw.double() * wt.double()).sum())
+    scale = float((y1.buf.double() * gy.buf.double()).abs().sum()) ** 0.5 * 16      # ~ std of a sum of that many rounded terms
+    assert abs(lhs - rhs) <= max(2e-3 * abs(rhs), scale * 2 ** -8), (lhs, rhs, scale)
+    # bias gradient summed inside the wgrad kernel == column sums of dY
+    ref_db = gy.buf.double().sum((0, 1, 2))
+    assert float((db.double() - ref_db).abs().max()) <= 1e-3 * float(ref_db.abs().max()) + 1.0
+
+
 @pytest.mark.parametrize("shape", [(2, 32, 16, 128, 64), (1, 160, 24, 64, 64), (1, 128, 50, 128, 32)])
 def test_conv_tc_epilogue_matches_simt(shape):
     from srcgan_b200 import ops
