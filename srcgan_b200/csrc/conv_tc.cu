@@ -1166,8 +1166,9 @@ __device__ __forceinline__ void umma_commit_pair(uint64_t* bar) {           // a
                : "memory");
 }
 
-// Dynamic unit queue of a CTA pair.  The pairs of one launch take 127-216 us for equal shares of the work (the HBM-bound
-// layers see very different TMA latencies per SM), so units are claimed from a global counter instead of dealt round-robin.
+// Dynamic unit queue of a CTA pair (opt-in, SRCGAN_B200_SWEEP_DYNAMIC=1).  The pairs of one launch take 127-216 us for equal
+// shares of the work (the HBM-bound layers see very different TMA latencies per SM), so units can be claimed from a global
+// counter instead of dealt round-robin.
 // The leader's producer warp claims one unit ahead and publishes it to both CTAs' `unit_list` (one single-use mbarrier per
 // list slot); every role of both CTAs walks the list.  A pair stops claiming after SW_MAXU - 1 units (host guarantees that
 // ncl * (SW_MAXU - 1) >= num_units, else the launch is static).
@@ -1948,8 +1949,12 @@ static int launch_sweep2(const CUtensorMap& tx, Sw2Args& a, cudaStream_t st) {
     if (best < 0 || cost < best) { best = cost; a.wseg = ws; a.segs_x = (int)segs; a.num_units = (int)units; }
   }
   const int ncl = a.num_units < ncl_max ? a.num_units : ncl_max;
+  // The dynamic unit queue is opt-in: which output columns straddle a lap of the accumulator ring (two partial blocks added
+  // in the epilogue instead of one accumulation chain) depends on a pair's position in its unit sequence, so claiming units
+  // at run time changes the fp32 summation order of a few columns from run to run (last-bit differences after the bf16
+  // rounding).  Round-robin units keep the kernel bit-reproducible; the queue is worth +15 % on 64->32, +1 % on a dense block.
   a.sched = nullptr;
-  if (a.num_units > ncl && (long long)ncl * (SW_MAXU - 1) >= a.num_units && !getenv("SRCGAN_B200_SWEEP_STATIC"))
+  if (a.num_units > ncl && (long long)ncl * (SW_MAXU - 1) >= a.num_units && getenv("SRCGAN_B200_SWEEP_DYNAMIC"))
     a.sched = sweep2_sched_slot();
   cudaLaunchConfig_t cfg = {};
   cfg.gridDim = dim3((unsigned)(ncl * CG)); cfg.blockDim = dim3(SW2_THREADS); cfg.dynamicSmemBytes = smem; cfg.stream = st;

@@ -265,7 +265,7 @@ def test_full_step_gray_against_golden(golden_step_gray, net):
 
 def test_bf16_step_at_bench_patch_size_is_deterministic_and_finite():
     """The benchmark's patch size (64x64 -> 256x256, where every dense-block layer of G_B runs on the paired sweep / stacked
-    wgrad kernels with their dynamic unit queue and split reductions) cannot be checked element-wise on the CPU; what must
+    wgrad kernels with their split reductions) cannot be checked element-wise on the CPU; what must
     hold at any size: two runs from the same state give bit-identical losses and updated weights, and everything is finite."""
     from oracle import srcgan_oracle as O
     from srcgan_b200 import nn as snn
