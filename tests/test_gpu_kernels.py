@@ -396,6 +396,37 @@ def test_conv_wgrad_tc_matches_reference(case):
     assert relerr(dw.cpu(), 1.5 * wt.grad) < 5e-3
 
 
+@pytest.mark.parametrize("env", [{}, {"SRCGAN_B200_WSTACK32": "1"}, {"SRCGAN_B200_NO_WSTACK": "1"}])
+def test_conv_wgrad_tc_variants(env, monkeypatch):
+    """kw-stacked wgrad as N = 192 (default for 64 output channels), as two N = 96 halves, and the per-tap halo kernel all
+    give the same weight / bias gradients; the default launch is bit-reproducible."""
+    from srcgan_b200 import ops
+    n, h, w, cin, cout = 2, 72, 40, 192, 64
+    x = rand((n, cin, h, w), 41).bfloat16().float()
+    wt = torch.zeros(cout, cin, 3, 3, requires_grad=True)
+    y = F.conv2d(x, wt, None, stride=1, padding=1)
+    gy = rand(tuple(y.shape), 42).bfloat16().float()
+    y.backward(gy)
+    xs = to_nhwc(x, torch.bfloat16, ctot=cin, c0=0)
+    gys = to_nhwc(gy, torch.bfloat16, ctot=cout + 64, c0=64)
+
+    def run():
+        dw = torch.empty((cout, cin, 3, 3), device=DEV)
+        db = torch.empty((cout,), device=DEV)
+        ops.conv_wgrad(xs, gys, dw, db, 3, 1, 1, engine=ops.ENGINE_TC)
+        torch.cuda.synchronize()
+        return dw, db
+
+    base_dw, base_db = run()
+    for k, v in env.items():
+        monkeypatch.setenv(k, v)
+    dw, db = run()
+    assert relerr(dw.cpu(), wt.grad) < 5e-3
+    assert relerr(db.cpu(), gy.sum((0, 2, 3))) < 5e-3
+    if env == {}:
+        assert torch.equal(dw, base_dw) and torch.equal(db, base_db)
+
+
 S2_CASES = [
     # n, h, w, cin, cout, k
     (2, 32, 16, 128, 128, 3),      # Decoder conv3
