@@ -95,6 +95,12 @@ typedef struct srcgan_conv_params {
   const void* mask;
   int32_t mask_ld;
   float mask_slope;
+  /* Packed LeakyReLU masks (paired-sweep fprop kernel only; any other kernel returns SRCGAN_E_INVALID if one is set).
+     Layout [n][ho][wo][cout/32] uint32, bit i of word j = channel 32j+i.
+       signbits : OUT, bit = (value stored to y > 0) - what `mask` of the matching backward step would test
+       maskbits : IN,  replaces `mask`: value *= bit ? 1 : mask_slope  (4 bytes instead of 64 per pixel and 32 channels) */
+  void* signbits;
+  const void* maskbits;
 } srcgan_conv_params;
 
 const char* srcgan_version(void);

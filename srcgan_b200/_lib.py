@@ -34,6 +34,7 @@ class ConvParams(C.Structure):
         ("r1", C.c_void_p), ("r1_ld", C.c_int32), ("beta1", C.c_float),
         ("r2", C.c_void_p), ("r2_ld", C.c_int32), ("beta2", C.c_float),
         ("mask", C.c_void_p), ("mask_ld", C.c_int32), ("mask_slope", C.c_float),
+        ("signbits", C.c_void_p), ("maskbits", C.c_void_p),
     ]
 
 

@@ -1107,6 +1107,8 @@ struct Sw2Args {
   const __nv_bfloat16* r1; int r1_ld; float beta1;
   const __nv_bfloat16* r2; int r2_ld; float beta2;
   const __nv_bfloat16* mask; int mask_ld; float mask_slope;
+  uint32_t* signbits;                   // OUT [pixel][BN/32]: bit = stored value > 0 (the mask of the matching backward step)
+  const uint32_t* maskbits;             // IN  [pixel][BN/32]: replaces `mask` (4 bytes instead of 64 per pixel and 32 channels)
   int dbg;
 };
 
@@ -1521,7 +1523,9 @@ conv3x3_sweep2_tc(const __grid_constant__ CUtensorMap tmap_x, const Sw2Args a) {
         // (issued behind the wait they cost one DRAM round trip per column and group - the dgrad launches all have a mask)
         const long long pix = (long long)img * a.img_stride + (long long)y * a.lane_stride + (long long)x * a.sweep_stride;
         uint4 pr1[4], pr2[4], pmk[4];
+        uint32_t pbits = 0;
         auto fetch_side = [&](int cb) {
+          if (a.maskbits) pbits = __ldg(a.maskbits + pix * (BN / 32) + (cb >> 5));
 #pragma unroll
           for (int gq = 0; gq < 4; ++gq) {
             if (a.r1) pr1[gq] = __ldg(reinterpret_cast<const uint4*>(a.r1 + pix * a.r1_ld + cb + gq * 8));
@@ -1576,6 +1580,16 @@ conv3x3_sweep2_tc(const __grid_constant__ CUtensorMap tmap_x, const Sw2Args a) {
             if (a.alpha != 1.f) {
 #pragma unroll
               for (int i = 0; i < 32; ++i) f[i] *= a.alpha;
+            }
+            if (row_ok && a.maskbits) {
+#pragma unroll
+              for (int i = 0; i < 32; ++i) f[i] *= ((pbits >> i) & 1u) ? 1.f : a.mask_slope;
+            }
+            if (row_ok && a.signbits) {
+              uint32_t sb32 = 0;
+#pragma unroll
+              for (int i = 0; i < 32; ++i) sb32 |= (f[i] > 0.f ? 1u : 0u) << i;
+              a.signbits[pix * (BN / 32) + (cb >> 5)] = sb32;
             }
             if (row_ok) {
               uint4 ov[4];
@@ -2113,6 +2127,9 @@ static int conv_fprop_sweep2(const srcgan_conv_params* p, int cg, cudaStream_t s
   a.r1 = (const __nv_bfloat16*)p->r1; a.r1_ld = p->r1_ld; a.beta1 = p->beta1;
   a.r2 = (const __nv_bfloat16*)p->r2; a.r2_ld = p->r2_ld; a.beta2 = p->beta2;
   a.mask = (const __nv_bfloat16*)p->mask; a.mask_ld = p->mask_ld; a.mask_slope = p->mask_slope;
+  SRCGAN_REQUIRE(!((p->signbits || p->maskbits) && (p->r1 || p->r2 || p->mask)),
+                 "conv_fprop_tc: packed sign / mask bits cannot be combined with residual or bf16 mask operands");
+  a.signbits = (uint32_t*)p->signbits; a.maskbits = (const uint32_t*)p->maskbits;
   { const char* d = getenv("SRCGAN_B200_DBG"); a.dbg = d ? atoi(d) : 0; }
   { const char* d = getenv("SRCGAN_B200_PFD"); a.pfd = d ? atoi(d) : 0; }
   if (cg == 2) return p->cout == 64 ? tc::launch_sweep2<64, 2>(tx, a, st) : tc::launch_sweep2<32, 2>(tx, a, st);
@@ -2121,6 +2138,8 @@ static int conv_fprop_sweep2(const srcgan_conv_params* p, int cg, cudaStream_t s
 
 int conv_fprop_tc(const srcgan_conv_params* p, cudaStream_t st) {
   if (const int cg = sweep2_cg(p)) return conv_fprop_sweep2(p, cg, st);
+  SRCGAN_REQUIRE(!p->signbits && !p->maskbits,
+                 "conv_fprop_tc: packed sign / mask bits need the paired-sweep kernel (3x3 s1 p1, cout 32/64, map >= 96)");
   if (const int v = kws_variant(p)) return conv_fprop_kws(p, v, st);
   tc::HostPlan hp = tc::fprop_plan(p->kh, p->stride, p->pad);
   const bool halo = p->kh == 3 && p->stride == 1 && (p->cout <= 16 || p->cout == 32 || p->cout == 64);

@@ -43,6 +43,21 @@ def tc_wgrad_supported(cin: int, cout: int, k: int, stride: int, upsample: bool,
     return cin >= 16 and cin % 8 == 0 and cout >= 16 and cout % 8 == 0
 
 
+def sweep_bits_supported(cin: int, cout: int, k: int, stride: int, pad: int, dtype, h: int, w: int) -> bool:
+    """True if conv_fprop_tc() will run this layer on the paired-sweep kernel (mirror of sweep2_cg() in csrc/conv_tc.cu),
+    the only kernel that reads / writes the packed LeakyReLU masks; the C side refuses loudly if this mirror is wrong."""
+    if _force_simt or dtype != torch.bfloat16 or k != 3 or stride != 1 or pad != 1 or cout not in (32, 64):
+        return False
+    if h < 96 and w < 96:
+        return False
+    if any(os.environ.get(v) for v in ("SRCGAN_B200_NO_SWEEP2", "SRCGAN_B200_SWEEP2_CG", "SRCGAN_B200_NO_MASKBITS")):
+        return False
+    nchunks = (cin + 63) // 64
+    fixed = nchunks * (3 * (3 * cout * 128 // 2)) + 2048 + 1024          # the pair's half of the stacked weights + aux
+    ring = min(10, (227 * 1024 - fixed) // 17408)
+    return ring >= nchunks + 2
+
+
 def select(cin, cout, k, stride, upsample, dtype, h, w):
     """-> (engine, fprop weight layout); (h, w) are the OUTPUT spatial dims."""
     if not _force_simt and dtype == torch.bfloat16 and tc_fprop_supported(cin, cout, k, stride, upsample, dtype, h, w):

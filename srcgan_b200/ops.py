@@ -206,12 +206,20 @@ def _epilogue(p: ConvParams, bias, act, alpha, r1, beta1, r2, beta2, mask, mask_
 def conv_fprop(x: Slice, wgt: torch.Tensor, bias: Optional[torch.Tensor], y: Slice, k: int, stride: int = 1,
                pad: int = 1, *, upsample: bool = False, act: Optional[float] = None, alpha: float = 1.0,
                r1: Optional[Slice] = None, beta1: float = 0.0, r2: Optional[Slice] = None, beta2: float = 0.0,
-               mask: Optional[Slice] = None, mask_slope: float = 0.0, engine: int = ENGINE_SIMT) -> None:
-    """y = epilogue(conv(x, w)); see include/srcgan_b200.h for the epilogue definition."""
+               mask: Optional[Slice] = None, mask_slope: float = 0.0, engine: int = ENGINE_SIMT,
+               signbits: Optional[torch.Tensor] = None, maskbits: Optional[torch.Tensor] = None) -> None:
+    """y = epilogue(conv(x, w)); see include/srcgan_b200.h for the epilogue definition.
+    ``signbits`` (out) / ``maskbits`` (in): packed LeakyReLU masks, int32 (n, h, w, cout/32) - paired-sweep kernel only."""
     _require_cuda(x.buf, "conv input")
     p = _conv_params(x.n, x.h, x.w, x.c, y.c, k, stride, pad, upsample, y.h, y.w, x.dtype, engine)
     p.x, p.x_ld, p.wgt, p.y, p.y_ld = x.ptr, x.ld, wgt.data_ptr(), y.ptr, y.ld
     _epilogue(p, bias, act, alpha, r1, beta1, r2, beta2, mask, mask_slope)
+    for name, t in (("signbits", signbits), ("maskbits", maskbits)):
+        if t is not None:
+            assert t.dtype == torch.int32 and t.is_contiguous() and tuple(t.shape) == (y.n, y.h, y.w, y.c // 32), name
+            setattr(p, name, t.data_ptr())
+    if maskbits is not None:
+        p.mask_slope = float(mask_slope)
     with _Timed("fprop", p):
         _lib.check(_lib.load().srcgan_conv_fprop(C.byref(p), _stream()), "conv_fprop")
 
