@@ -532,21 +532,28 @@ class RDDBNetB(_RRDBGenerator):
         ops.nchw_to_nhwc(x, x_in)
         cur = self._trunk_forward(x_in, st)
         acts = [cur]
+        abits = [None]      # packed sign masks of the activations (paired-sweep layers): the dgrad steps read 8 B/px, not 128
         ups = {}            # stage index -> materialised nearest-x2 input (bf16 mode: keeps the conv on tcgen05)
         materialise = dt == torch.bfloat16
         for i, (conv, up) in enumerate(self._stages()):
             hh, ww = (cur.h * 2, cur.w * 2) if up else (cur.h, cur.w)
             nxt = Slice(ops.new_buf(n, hh, ww, self.nf, dt, dev))
+            sb = None
+            if (materialise or not up) and self.nf == 64 and \
+                    _engine_mod().sweep_bits_supported(self.nf, self.nf, 3, 1, 1, dt, hh, ww):
+                sb = torch.empty((n, hh, ww, 2), dtype=torch.int32, device=dev)
+            ep = {"signbits": sb} if sb is not None else {}
             if up and materialise:
                 big = Slice(ops.new_buf(n, hh, ww, self.nf, dt, dev))
                 ops.upsample2x(cur, big)
                 ups[i] = big
-                self._fprop(conv, big, nxt, act=LRELU)
+                self._fprop(conv, big, nxt, act=LRELU, **ep)
             else:
-                self._fprop(conv, cur, nxt, upsample=up, act=LRELU)
+                self._fprop(conv, cur, nxt, upsample=up, act=LRELU, **ep)
             acts.append(nxt)
+            abits.append(sb)
             cur = nxt
-        st["ups"] = ups
+        st["ups"], st["abits"] = ups, abits
         out = _io_buf(n, cur.h, cur.w, self.conv_last.out_channels, dt, dev)
         self._fprop(self.conv_last, cur, out)
         st["acts"] = acts
@@ -564,7 +571,21 @@ class RDDBNetB(_RRDBGenerator):
         self._wgrad(self.conv_last, last, d_o, sink, W(self.conv_last.weight), W(self.conv_last.bias))
         stages = self._stages()
         gz = Slice(ops.new_buf(n, last.h, last.w, self.nf, dt, dev))
-        self._dgrad(self.conv_last, d_o, gz, mask=(last if stages else None), mask_slope=LRELU)
+        abits = st.get("abits") or [None] * len(acts)
+
+        def mask_ep(i, cin_d, t):
+            """epilogue arguments of the dgrad that multiplies by LeakyReLU'(acts[i]); packed bits when both ends are sweep layers"""
+            if i <= 0 and t is None:
+                return {}
+            mb = abits[i] if 0 <= i < len(abits) else None
+            if mb is not None and _engine_mod().sweep_bits_supported(cin_d, self.nf, 3, 1, 1, dt, t.h, t.w):
+                return {"maskbits": mb, "mask_slope": LRELU}
+            return {"mask": t, "mask_slope": LRELU}
+
+        if stages:
+            self._dgrad(self.conv_last, d_o, gz, **mask_ep(len(acts) - 1, d_o.c, last))
+        else:
+            self._dgrad(self.conv_last, d_o, gz)
         for i in range(len(stages) - 1, -1, -1):
             conv, up = stages[i]
             src = acts[i]
@@ -580,7 +601,10 @@ class RDDBNetB(_RRDBGenerator):
                 ops.upsample2x_adjoint(full, nxt, mask, LRELU)
             else:
                 nxt = Slice(ops.new_buf(n, src.h, src.w, self.nf, dt, dev))
-                self._dgrad(conv, gz, nxt, mask=mask, mask_slope=LRELU)
+                if mask is None:
+                    self._dgrad(conv, gz, nxt)
+                else:
+                    self._dgrad(conv, gz, nxt, **mask_ep(i, gz.c, mask))
             gz = nxt
             if "_debug" in st:
                 st["_debug"]["gz%d" % i] = gz.view().float().permute(0, 3, 1, 2).clone()
