@@ -296,6 +296,39 @@ def test_conv_tc_sweep_variants(env, monkeypatch):
         assert torch.equal(got.buf, base.buf)
 
 
+@pytest.mark.parametrize("cin,cout", [(96, 32), (64, 64)])
+def test_conv_tc_packed_masks(cin, cout):
+    """signbits out == (stored activation > 0); a launch with maskbits == the same launch with the bf16 activation as mask,
+    bit for bit; kernels that do not implement the bits refuse them."""
+    from srcgan_b200 import ops
+    n, h, w = 2, 128, 100
+    g0 = torch.Generator(device=DEV).manual_seed(3)
+    xb = torch.randn((n, h, w, 192), dtype=torch.bfloat16, device=DEV, generator=g0)
+    x = ops.Slice(xb, 0, cin)
+    wp = ops.pack_weights(torch.randn((cout, cin, 3, 3), device=DEV, generator=g0) * 0.05, ops.WL_TC, torch.bfloat16)
+    b = torch.randn(cout, device=DEV, generator=g0)
+    act = ops.Slice(torch.empty((n, h, w, cout), dtype=torch.bfloat16, device=DEV))
+    bits = torch.zeros((n, h, w, cout // 32), dtype=torch.int32, device=DEV)
+    ops.conv_fprop(x, wp, b, act, 3, 1, 1, act=0.2, engine=ops.ENGINE_TC, signbits=bits)
+    torch.cuda.synchronize()
+    pos = (act.buf > 0).view(n, h, w, cout // 32, 32).long()
+    want = (pos << torch.arange(32, device=DEV)).sum(-1)
+    want = torch.where(want >= 2 ** 31, want - 2 ** 32, want).to(torch.int32)
+    assert torch.equal(bits, want)
+    # backward-style launch: same input, multiply by LeakyReLU'(act)
+    y_bf = ops.Slice(torch.empty((n, h, w, cout), dtype=torch.bfloat16, device=DEV))
+    y_bits = ops.Slice(torch.empty((n, h, w, cout), dtype=torch.bfloat16, device=DEV))
+    ops.conv_fprop(x, wp, None, y_bf, 3, 1, 1, mask=act, mask_slope=0.2, engine=ops.ENGINE_TC)
+    ops.conv_fprop(x, wp, None, y_bits, 3, 1, 1, maskbits=bits, mask_slope=0.2, engine=ops.ENGINE_TC)
+    torch.cuda.synchronize()
+    assert torch.equal(y_bf.buf, y_bits.buf)
+    small = ops.Slice(torch.randn((1, 32, 32, cin), dtype=torch.bfloat16, device=DEV))      # < 96 px: kw-stacked kernel
+    ys = ops.Slice(torch.empty((1, 32, 32, cout), dtype=torch.bfloat16, device=DEV))
+    with pytest.raises(RuntimeError, match="paired-sweep"):
+        ops.conv_fprop(small, wp, None, ys, 3, 1, 1, engine=ops.ENGINE_TC,
+                       signbits=torch.zeros((1, 32, 32, cout // 32), dtype=torch.int32, device=DEV))
+
+
 @pytest.mark.parametrize("cin,cout", [(64, 32), (160, 32), (192, 64)])
 def test_conv_tc_full_size_identities(cin, cout):
     """BASELINE's full size (batch 64, 256 x 256, the dense block's 192-channel concat buffer) is far beyond what the CPU
