@@ -2,7 +2,8 @@
 """Benchmark of the SRCGAN G+D training step (BASELINE.json metric).
 
     python bench.py --gpus N --steps K --warmup W            # this repo's CUDA path
-    python bench.py --impl reference --steps K --warmup W    # the reference's CPU path (oracle port)
+    python bench.py --impl reference --steps K --warmup W    # the reference's CPU path (baseline/_ref, else the oracle port)
+    python bench.py --impl torch-gpu --batch 16              # the incumbent: reference modules on stock PyTorch/cuDNN, same GPU
 
 One *step* = one ``SRCycleGAN.optimize_parameters`` (3 G_A + 3 G_B + 3 D_A + 3 D_B forwards, backward_G,
 two D backwards, both Adam steps) over a batch of synthetic Sat2Aer-shaped patches
@@ -38,7 +39,8 @@ def parse():
     ap.add_argument("--gpus", type=int, default=1)
     ap.add_argument("--steps", type=int, default=3)
     ap.add_argument("--warmup", type=int, default=3)
-    ap.add_argument("--impl", default="srcgan_b200", choices=["srcgan_b200", "reference"])
+    ap.add_argument("--impl", default="srcgan_b200", choices=["srcgan_b200", "reference", "torch-gpu"])
+    ap.add_argument("--variant", default="", help="torch-gpu arm: comma list of fp32,tf32,bf16-autocast-channels_last")
     ap.add_argument("--batch", type=int, default=64, help="patches per GPU")
     ap.add_argument("--lr-size", type=int, default=64, help="LR patch edge (HR = 4x)")
     ap.add_argument("--precision", default="bf16", choices=["bf16", "fp32"])
@@ -125,21 +127,83 @@ class ClockSampler(threading.Thread):
 # reference arm / cpu baseline: the oracle port of the reference's step on the host cores
 # --------------------------------------------------------------------------------------------
 
-def cpu_reference_steps(batch: int, lr: int, steps: int, warmup: int):
-    """-> (patches/s, cores, seconds per step).  fp32, all host threads."""
+REF_SRC = os.path.join(ROOT, "baseline", "_ref", "src")
+
+
+def reference_staged() -> bool:
+    return os.path.isfile(os.path.join(REF_SRC, "train.py"))
+
+
+def import_reference_train():
+    """The reference's UNMODIFIED ``train`` module from baseline/_ref/src (scripts/stage_reference.py), with its own
+    ``model`` / ``losses`` packages.  visdom / skimage (logging, image I/O) are stubbed; the class ``RDDBNetA`` that
+    train.py:11 imports but the reference never defines is the documented shim, built from reference classes only:
+    ``model.model.RDDBNet`` constructor + ``model.model.Decoder``, forward = the commented-out one at model.py:370-378."""
+    import importlib
+    import types
+    if REF_SRC not in sys.path:
+        sys.path.insert(0, REF_SRC)
+    sys.modules.setdefault("visdom", types.SimpleNamespace(Visdom=lambda *a, **k: None))
+    try:
+        import skimage  # noqa: F401
+    except Exception:
+        sk = types.ModuleType("skimage")
+        sk.io, sk.color = types.ModuleType("skimage.io"), types.ModuleType("skimage.color")
+        sk.color.lab2rgb = sk.color.rgb2lab = sk.color.rgb2gray = None
+        sk.io.imsave = sk.io.imread = None
+        sys.modules.update({"skimage": sk, "skimage.io": sk.io, "skimage.color": sk.color})
+    pkg = importlib.import_module("model")
+    mm = importlib.import_module("model.model")
+    if not hasattr(pkg, "RDDBNetA"):
+        class RDDBNetA(mm.RDDBNet):
+            def __init__(self, in_nc, out_nc, nf, nb, gc=32, mode="x2"):
+                super().__init__(in_nc, out_nc, nf, nb, gc=gc, mode=mode)
+                self.decode = mm.Decoder()
+
+            def forward(self, x):
+                fea = self.conv_first(x)
+                fea = fea + self.trunk_conv(self.RRDB_trunk(fea))
+                return self.conv_last(self.decode(fea))
+        pkg.RDDBNetA = RDDBNetA
+    for name in ("RDDBNetB", "NLayerDiscriminator", "SRDenseNetA", "SRDenseNetB"):
+        if not hasattr(pkg, name):
+            setattr(pkg, name, getattr(mm, name))
+    return importlib.import_module("train")
+
+
+def synthetic_patches(batch: int, lr: int, seed: int):
     import torch
-    from oracle import srcgan_oracle as O
+    import torch.nn.functional as F
+    g = torch.Generator().manual_seed(seed)
+    real_B = torch.rand(batch, 3, lr * 4, lr * 4, generator=g)
+    return F.interpolate(real_B, scale_factor=0.25, mode="nearest"), real_B
+
+
+def cpu_reference_steps(batch: int, lr: int, steps: int, warmup: int):
+    """-> (patches/s, cores, seconds per step, kind).  fp32, all host threads.  kind "reference": the reference's own
+    train.SRCycleGAN from baseline/_ref; "port": the oracle restatement when that tree is not staged."""
+    import random
+    import torch
     cores = os.cpu_count() or 1
     torch.set_num_threads(cores)
-    step = O.CycleGANStepOracle(O.default_states(0))
-    real_A, real_B = O.synthetic_batch(batch, lr=lr, scale=4, seed=1234)
+    real_A, real_B = synthetic_patches(batch, lr, 1234)
+    if reference_staged():
+        train = import_reference_train()
+        opt = train.params()
+        opt.device, opt.mode, opt.net = torch.device("cpu"), "x4", "1"
+        torch.manual_seed(0)
+        random.seed(0)
+        step, kind = train.SRCycleGAN(opt), "reference"
+    else:
+        from oracle import srcgan_oracle as O
+        step, kind = O.CycleGANStepOracle(O.default_states(0)), "port"
     for _ in range(warmup):
         step.optimize_parameters(real_A, real_B)
     t0 = time.perf_counter()
     for _ in range(steps):
         step.optimize_parameters(real_A, real_B)
     dt = (time.perf_counter() - t0) / max(steps, 1)
-    return batch / dt, cores, dt
+    return batch / dt, cores, dt, kind
 
 
 def run_reference(args):
@@ -148,19 +212,116 @@ def run_reference(args):
         return
     batch = 1                      # bounded sample: ~9 s of CPU work per step at the full patch size
     steps, warmup = min(args.steps, 3), min(args.warmup, 1)
-    v, cores, dt = cpu_reference_steps(batch, args.lr_size, steps, warmup)
+    v, cores, dt, kind = cpu_reference_steps(batch, args.lr_size, steps, warmup)
+    how = ("the reference's own unmodified train.SRCycleGAN (baseline/_ref/src, RDDBNetA = the documented shim)" if kind == "reference"
+           else "the oracle port (oracle/srcgan_oracle.py, pinned to the reference by tests/golden)")
     line = {
         "impl": "reference", "metric": METRIC, "value": v, "unit": UNIT, "n_gpus": args.gpus, "steps": steps,
         "warmup": warmup, "ms_per_step": dt * 1e3, "higher_is_better": True, "scaling": "weak",
         "vs_baseline": None, "dtype": "f32", "data": "synthetic",
         "config": {"workload": "RDDBNet x4 G+D training step (SRCycleGAN.optimize_parameters), 64x64->256x256 RGB",
-                   "patches_per_step": batch, "note": "reference is pure Python/PyTorch: timed as the oracle port "
-                   "(oracle/srcgan_oracle.py, pinned to the reference by tests/golden) on the host cores"},
-        "cpu_baseline": {"value": v, "unit": UNIT, "cores": cores, "kind": "port",
+                   "patches_per_step": batch, "note": "reference is pure Python/PyTorch: timed as %s on the host cores" % how},
+        "cpu_baseline": {"value": v, "unit": UNIT, "cores": cores, "kind": kind,
                          "sample": "batch %d x %d steps of the full-size step (fp32, torch CPU)" % (batch, steps)},
         "e2e": {"value": v, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
     }
     print(json.dumps(line), flush=True)
+
+
+# --------------------------------------------------------------------------------------------
+# the incumbent: the same unmodified reference modules through stock PyTorch / cuDNN on the same B200
+# ("the kernel to beat on the same box")
+# --------------------------------------------------------------------------------------------
+
+def run_torch_gpu(args):
+    """Prints one JSON line per variant: fp32 with TF32 off (the reference as shipped), fp32 with TF32 on, and
+    autocast(bf16) + channels_last + cudnn.benchmark (what a user gets from stock PyTorch with the usual switches)."""
+    import random
+    import torch
+    if int(os.environ.get("RANK", "0")) != 0:
+        return
+    if not torch.cuda.is_available():
+        print(json.dumps({"impl": "torch-gpu", "unavailable": "no CUDA device"}))
+        return
+    dev = torch.device("cuda", 0)
+    lr = args.lr_size
+    if reference_staged():
+        train, src = import_reference_train(), "reference modules (baseline/_ref/src) + RDDBNetA shim"
+    else:
+        train, src = None, "oracle port (baseline/_ref not staged)"
+    variants = [("fp32", dict(tf32=False, autocast=False, cl=False)),
+                ("tf32", dict(tf32=True, autocast=False, cl=False)),
+                ("bf16-autocast-channels_last", dict(tf32=True, autocast=True, cl=True))]
+    if args.variant:
+        variants = [v for v in variants if v[0] in args.variant.split(",")]
+    for name, cfg in variants:
+        torch.backends.cuda.matmul.allow_tf32 = cfg["tf32"]
+        torch.backends.cudnn.allow_tf32 = cfg["tf32"]
+        torch.backends.cudnn.benchmark = True
+        batch = args.batch
+        while True:
+            try:
+                torch.manual_seed(0)
+                random.seed(0)
+                if train is not None:
+                    opt = train.params()
+                    opt.device, opt.mode, opt.net = dev, "x4", "1"
+                    model = train.SRCycleGAN(opt)
+                    nets = [model.netG_A, model.netG_B, model.netD_A, model.netD_B]
+                    if cfg["cl"]:
+                        for n in nets:
+                            n.to(memory_format=torch.channels_last)
+                    step = model.optimize_parameters
+                else:
+                    from oracle import srcgan_oracle as O
+                    st = {k: {kk: vv.to(dev) for kk, vv in sd.items()} for k, sd in O.default_states(0).items()}
+                    model = O.CycleGANStepOracle(st)
+                    step = model.optimize_parameters
+                real_A, real_B = (t.to(dev) for t in synthetic_patches(batch, lr, 1234))
+                if cfg["cl"]:
+                    real_A, real_B = real_A.contiguous(memory_format=torch.channels_last), real_B.contiguous(memory_format=torch.channels_last)
+
+                def one():
+                    if cfg["autocast"]:
+                        with torch.autocast("cuda", dtype=torch.bfloat16):
+                            step(real_A, real_B)
+                    else:
+                        step(real_A, real_B)
+                for _ in range(max(args.warmup, 2)):
+                    one()
+                torch.cuda.synchronize()
+                a, b = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+                a.record()
+                for _ in range(args.steps):
+                    one()
+                b.record()
+                torch.cuda.synchronize()
+                ms = a.elapsed_time(b) / args.steps
+                peak_gb = torch.cuda.max_memory_allocated() / 2 ** 30
+                break
+            except torch.cuda.OutOfMemoryError:
+                model = step = real_A = real_B = None
+                import gc
+                gc.collect()
+                torch.cuda.empty_cache()
+                torch.cuda.reset_peak_memory_stats()
+                if batch == 1:
+                    raise
+                batch //= 2
+        line = {"impl": "torch-gpu", "variant": name, "metric": METRIC, "value": batch / (ms * 1e-3), "unit": UNIT, "n_gpus": 1,
+                "steps": args.steps, "warmup": max(args.warmup, 2), "ms_per_step": ms, "higher_is_better": True,
+                "dtype": name, "data": "synthetic",
+                "config": {"workload": "RDDBNet x4 G+D training step through stock PyTorch %s / cuDNN %s, batch %d (requested %d; "
+                                       "halved on out-of-memory), %dx%d->%dx%d RGB" % (torch.__version__, torch.backends.cudnn.version(),
+                                                                                     batch, args.batch, lr, lr, lr * 4, lr * 4),
+                           "source": src, "peak_memory_gb": peak_gb},
+                "step_tflops": batch / (ms * 1e-3) * GFLOP_PER_PATCH * (lr / 64.0) ** 2 / 1e3}
+        print(json.dumps(line), flush=True)
+        model = step = real_A = real_B = None
+        import gc
+        gc.collect()
+        torch.cuda.empty_cache()
+        torch.cuda.reset_peak_memory_stats()
 
 
 # --------------------------------------------------------------------------------------------
@@ -172,7 +333,6 @@ def run_ours(args):
     import torch.distributed as dist
     import torch.nn.functional as F
 
-    from oracle import srcgan_oracle as O          # only for the shared deterministic weight init + cpu_baseline
     from srcgan_b200 import _lib, dist as sdist, nn as snn, ops, trainer
 
     if not torch.cuda.is_available():
@@ -186,10 +346,8 @@ def run_ours(args):
 
     opt = trainer.params()
     opt.device, opt.mode, opt.net = dev, "x4", "1"
+    torch.manual_seed(0)                            # random-init weights of the reference's distributions (package ctor)
     model = trainer.SRCycleGAN(opt)
-    states = O.default_states(0)
-    for name in ("G_A", "G_B", "D_A", "D_B"):
-        getattr(model, "net" + name).load_state_dict(states[name], strict=True)
     sdist.make_data_parallel(model)
 
     import random
@@ -297,10 +455,11 @@ def run_ours(args):
         "e2e": e2e, "gpu_launches": int(launches), "clocks": sampler.summary(), "roofline": roof,
     }
     if world == 1 and not args.no_cpu_baseline:
-        v, cores, dt = cpu_reference_steps(1, lr, 1, 0)
-        line["cpu_baseline"] = {"value": v, "unit": UNIT, "cores": cores, "kind": "port",
-                                "sample": "1 step at batch 1 of the same full-size step, fp32, oracle port of the "
-                                          "reference (pure PyTorch) on the host cores, %.1f s" % dt}
+        v, cores, dt, kind = cpu_reference_steps(1, lr, 1, 0)
+        line["cpu_baseline"] = {"value": v, "unit": UNIT, "cores": cores, "kind": kind,
+                                "sample": "1 step at batch 1 of the same full-size step, fp32, %s on the host cores, %.1f s"
+                                          % ("the reference's own train.SRCycleGAN (baseline/_ref)" if kind == "reference"
+                                             else "oracle port of the reference (pure PyTorch)", dt)}
     print(json.dumps(line), flush=True)
     if world > 1:
         dist.barrier()
@@ -310,6 +469,8 @@ def main():
     args = parse()
     if args.impl == "reference":
         run_reference(args)
+    elif args.impl == "torch-gpu":
+        run_torch_gpu(args)
     else:
         run_ours(args)
         try:

@@ -210,6 +210,12 @@ int srcgan_minmax(const float* a, int64_t n, float* out_min_max, void* stream);
 /* colour: NCHW fp32; rgb in [0,1]; lab normalised as dataset.py:154-157 (L/100,(a,b+128)/255) when normalised!=0 */
 int srcgan_rgb2lab(const float* rgb, float* lab, int n, int h, int w, int normalised, void* stream);
 int srcgan_lab2rgb(const float* lab, float* rgb, int n, int h, int w, int normalised, void* stream);
+/* the dataset glue itself, exact (float64 arithmetic like scikit-image): uint8 [n][h][w][3] image -> normalised LAB
+   [n][3][h][w] float32 tensor (Basic._arr2lab, src/dataset.py:148-159) and back with the uint8 truncation of
+   Basic._lab2img / utils.tensor2img (src/dataset.py:94-104, src/utils.py:22-26).  Reproduces the reference's example
+   PNG tiles bit for bit (tests/test_color.py). */
+int srcgan_rgb2lab_u8(const uint8_t* rgb_nhwc, float* lab_nchw, int n, int h, int w, void* stream);
+int srcgan_lab2rgb_u8(const float* lab_nchw, uint8_t* rgb_nhwc, int n, int h, int w, void* stream);
 
 #ifdef __cplusplus
 }

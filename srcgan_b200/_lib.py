@@ -82,6 +82,8 @@ SIGNATURES = {
     "srcgan_minmax": (_I, [_P, _L, _P, _P]),
     "srcgan_rgb2lab": (_I, [_P, _P, _I, _I, _I, _I, _P]),
     "srcgan_lab2rgb": (_I, [_P, _P, _I, _I, _I, _I, _P]),
+    "srcgan_rgb2lab_u8": (_I, [_P, _P, _I, _I, _I, _P]),
+    "srcgan_lab2rgb_u8": (_I, [_P, _P, _I, _I, _I, _P]),
 }
 
 _lib = None

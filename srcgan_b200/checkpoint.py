@@ -48,6 +48,8 @@ def save_state(net: torch.nn.Module, path: str) -> None:
 
 def load_state(net: torch.nn.Module, path: str) -> None:
     net.load_state_dict(torch.load(path, map_location="cpu"), strict=True)
+    if hasattr(net, "invalidate_packs"):
+        net.invalidate_packs()
 
 
 def save_cascade(model, ckpt_dir: str, epoch: int) -> Tuple[str, str]:

@@ -90,6 +90,8 @@ int metrics_ae(const float* p, const float* t, int n, int c, int h, int w, float
 int minmax(const float* a, int64_t n, float* out, cudaStream_t st);
 int rgb2lab(const float* rgb, float* lab, int n, int h, int w, int normalised, cudaStream_t st);
 int lab2rgb(const float* lab, float* rgb, int n, int h, int w, int normalised, cudaStream_t st);
+int rgb2lab_u8(const uint8_t* rgb, float* lab, int n, int h, int w, cudaStream_t st);
+int lab2rgb_u8(const float* lab, uint8_t* rgb, int n, int h, int w, cudaStream_t st);
 
 }  // namespace srcgan
 
@@ -285,6 +287,12 @@ int srcgan_rgb2lab(const float* rgb, float* lab, int n, int h, int w, int normal
 }
 int srcgan_lab2rgb(const float* lab, float* rgb, int n, int h, int w, int normalised, void* stream) {
   return lab2rgb(lab, rgb, n, h, w, normalised, (cudaStream_t)stream);
+}
+int srcgan_rgb2lab_u8(const uint8_t* rgb_nhwc, float* lab_nchw, int n, int h, int w, void* stream) {
+  return rgb2lab_u8(rgb_nhwc, lab_nchw, n, h, w, (cudaStream_t)stream);
+}
+int srcgan_lab2rgb_u8(const float* lab_nchw, uint8_t* rgb_nhwc, int n, int h, int w, void* stream) {
+  return lab2rgb_u8(lab_nchw, rgb_nhwc, n, h, w, (cudaStream_t)stream);
 }
 
 }  // extern "C"

@@ -155,8 +155,9 @@ bn_apply_vec(const __nv_bfloat16* __restrict__ x, int x_ld, __nv_bfloat16* __res
 }
 
 __global__ void __launch_bounds__(256)
-bn_bwd_apply_vec(const __nv_bfloat16* __restrict__ dy, int dy_ld, const __nv_bfloat16* __restrict__ y,
-                 int y_ld, const __nv_bfloat16* __restrict__ x, int x_ld, __nv_bfloat16* __restrict__ dx,
+bn_bwd_apply_vec(const __nv_bfloat16* dy /* may alias dx (in-place): plain loads, no __restrict__ */, int dy_ld,
+                 const __nv_bfloat16* __restrict__ y,
+                 int y_ld, const __nv_bfloat16* __restrict__ x, int x_ld, __nv_bfloat16* dx,
                  int dx_ld, int64_t npix, int c, const float* __restrict__ gamma,
                  const float* __restrict__ mean, const float* __restrict__ invstd,
                  const float* __restrict__ tot, float slope, int training) {
@@ -181,7 +182,7 @@ bn_bwd_apply_vec(const __nv_bfloat16* __restrict__ dy, int dy_ld, const __nv_bfl
     for (int u = 0; u < 2; ++u) {
       if (u == 0 || two) {
         const int64_t mm = m + u * step;
-        qd[u] = __ldg(reinterpret_cast<const uint4*>(dy + mm * dy_ld + ch));
+        qd[u] = *reinterpret_cast<const uint4*>(dy + mm * dy_ld + ch);
         qy[u] = __ldg(reinterpret_cast<const uint4*>(y + mm * y_ld + ch));
         qx[u] = __ldg(reinterpret_cast<const uint4*>(x + mm * x_ld + ch));
       }
@@ -344,8 +345,8 @@ bn_bwd_finalize(const float* __restrict__ p0, const float* __restrict__ p1, int 
 }
 
 template <typename T>
-__global__ void bn_bwd_apply(const T* __restrict__ dy, int dy_ld, const T* __restrict__ y, int y_ld,
-                             const T* __restrict__ x, int x_ld, T* __restrict__ dx, int dx_ld, int64_t npix, int c,
+__global__ void bn_bwd_apply(const T* dy /* may alias dx */, int dy_ld, const T* __restrict__ y, int y_ld,
+                             const T* __restrict__ x, int x_ld, T* dx, int dx_ld, int64_t npix, int c,
                              const float* __restrict__ gamma, const float* __restrict__ mean,
                              const float* __restrict__ invstd, const float* __restrict__ tot, float slope,
                              int training) {

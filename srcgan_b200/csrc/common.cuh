@@ -53,6 +53,24 @@ __device__ __forceinline__ double warp_sum(double v) {
 
 constexpr int kNumSMs = 148;  // B200
 
+// Guard for per-DEVICE CUDA state (cudaFuncSetAttribute, __constant__ uploads): one bit per device ordinal, so a process
+// that touches a second GPU initialises it there too.  A race between the main and the autograd thread only repeats an
+// idempotent call.
+struct DeviceOnce {
+  unsigned long long done = 0ull;
+  // -> true if the calling thread's current device still needs the initialisation; call mark() after it succeeded
+  bool needed(int* dev_out) {
+    int dev = 0;
+    cudaGetDevice(&dev);
+    *dev_out = dev;
+    if (dev < 0 || dev >= 64) return true;
+    return !((__atomic_load_n(&done, __ATOMIC_ACQUIRE) >> dev) & 1ull);
+  }
+  void mark(int dev) {
+    if (dev >= 0 && dev < 64) __atomic_fetch_or(&done, 1ull << dev, __ATOMIC_RELEASE);
+  }
+};
+
 static inline int ceil_div(int64_t a, int64_t b) { return (int)((a + b - 1) / b); }
 
 }  // namespace srcgan

@@ -736,19 +736,21 @@ static int launch_igemm(const srcgan_conv_params* p, cudaStream_t st) {
   auto al = [&](const void* ptr, int ld) { return ptr == nullptr || (((uintptr_t)ptr) % (8 * es) == 0 && ld % 8 == 0); };
   if (nch <= 4 && kch % 4 == 0 && a.vec_a && (size_t)p->kh * p->kw * kch * 16 <= 160 * 1024) {
     const size_t smem = (size_t)p->kh * p->kw * kch * sizeof(float4);
-    static bool attr_done = false;
-    if (!attr_done) {
+    static DeviceOnce attr_done;
+    int attr_done_dev;
+    if (attr_done.needed(&attr_done_dev)) {
       cudaFuncSetAttribute(thin_out_conv<T, DGRAD>, cudaFuncAttributeMaxDynamicSharedMemorySize, 160 * 1024);
-      attr_done = true;
+      attr_done.mark(attr_done_dev);
     }
     thin_out_conv<T, DGRAD><<<ceil_div(M, 256), 256, smem, st>>>(a);
   } else if (kch <= 4 && nch % 8 == 0 && al(p->y, p->y_ld) && al(p->r1, p->r1_ld) && al(p->r2, p->r2_ld) &&
              al(p->mask, p->mask_ld) && (size_t)p->kh * p->kw * kch * nch * 4 <= 160 * 1024) {
     const size_t smem = (size_t)p->kh * p->kw * kch * nch * sizeof(float);
-    static bool attr_done2 = false;
-    if (!attr_done2) {
+    static DeviceOnce attr_done2;
+    int attr_done2_dev;
+    if (attr_done2.needed(&attr_done2_dev)) {
       cudaFuncSetAttribute(thin_in_conv<T, DGRAD>, cudaFuncAttributeMaxDynamicSharedMemorySize, 160 * 1024);
-      attr_done2 = true;
+      attr_done2.mark(attr_done2_dev);
     }
     thin_in_conv<T, DGRAD><<<ceil_div(M * (nch / 8), 256), 256, smem, st>>>(a);
   } else if (nch <= 4) {

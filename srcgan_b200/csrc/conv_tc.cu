@@ -1809,11 +1809,12 @@ static int pack_launch(const float* w, int n_total, int k_total, long long nstri
 template <int BN, int MAXT>
 static int launch(const CUtensorMap& tmap, const TcArgs& a, cudaStream_t st) {
   using C = Cfg<BN, MAXT>;
-  static bool attr_set = false;
-  if (!attr_set) {
+  static DeviceOnce attr_set;
+  int attr_set_dev;
+  if (attr_set.needed(&attr_set_dev)) {
     SRCGAN_CUDA(cudaFuncSetAttribute(conv_igemm_tc<BN, MAXT>, cudaFuncAttributeMaxDynamicSharedMemorySize,
                                      C::SMEM_BYTES));
-    attr_set = true;
+    attr_set.mark(attr_set_dev);
   }
   long long grid = a.num_tiles < kNumSMs ? a.num_tiles : kNumSMs;
   conv_igemm_tc<BN, MAXT><<<(unsigned)grid, NUM_THREADS, C::SMEM_BYTES, st>>>(tmap, a);
@@ -1824,10 +1825,11 @@ static int launch(const CUtensorMap& tmap, const TcArgs& a, cudaStream_t st) {
 template <int BN>
 static int launch_halo(const CUtensorMap& tmap, const TcArgs& a, cudaStream_t st) {
   using C = HCfg<BN>;
-  static bool attr_set = false;
-  if (!attr_set) {
+  static DeviceOnce attr_set;
+  int attr_set_dev;
+  if (attr_set.needed(&attr_set_dev)) {
     SRCGAN_CUDA(cudaFuncSetAttribute(conv3x3_halo_tc<BN>, cudaFuncAttributeMaxDynamicSharedMemorySize, C::SMEM_BYTES));
-    attr_set = true;
+    attr_set.mark(attr_set_dev);
   }
   long long grid = a.num_tiles < kNumSMs ? a.num_tiles : kNumSMs;
   conv3x3_halo_tc<BN><<<(unsigned)grid, NUM_THREADS, C::SMEM_BYTES, st>>>(tmap, a);
@@ -1876,10 +1878,11 @@ static int launch_kws(const CUtensorMap& tx, const CUtensorMap& ty, KwArgs& a, c
   a.tiles_x = (a.w + KW_VX - 1) / KW_VX;
   a.tiles_y = (a.h + KW_TH * R - 1) / (KW_TH * R);
   a.num_tiles = (long long)a.tiles_x * a.tiles_y * a.n;
-  static bool attr_set = false;
-  if (!attr_set) {
+  static DeviceOnce attr_set;
+  int attr_set_dev;
+  if (attr_set.needed(&attr_set_dev)) {
     SRCGAN_CUDA(cudaFuncSetAttribute(conv3x3_kws_tc<BN, R>, cudaFuncAttributeMaxDynamicSharedMemorySize, SMEM_BUDGET));
-    attr_set = true;
+    attr_set.mark(attr_set_dev);
   }
   long long grid = a.num_tiles < kNumSMs ? a.num_tiles : kNumSMs;
   conv3x3_kws_tc<BN, R><<<(unsigned)grid, KW_THREADS, C::smem_bytes(a.nchunks, a.na), st>>>(tx, ty, a);
@@ -1944,10 +1947,11 @@ static int launch_sweep2(const CUtensorMap& tx, Sw2Args& a, cudaStream_t st) {
   a.na = sweep2_ring_depth<BN, CG>(a.nchunks);
   a.strips_y = (a.h + SW_ROWS - 1) / SW_ROWS;
   a.strips = a.n * a.strips_y;
-  static bool attr_set = false;
-  if (!attr_set) {
+  static DeviceOnce attr_set;
+  int attr_set_dev;
+  if (attr_set.needed(&attr_set_dev)) {
     SRCGAN_CUDA(cudaFuncSetAttribute(conv3x3_sweep2_tc<BN, CG>, cudaFuncAttributeMaxDynamicSharedMemorySize, SMEM_BUDGET));
-    attr_set = true;
+    attr_set.mark(attr_set_dev);
   }
   const size_t smem = C::smem_bytes(a.nchunks, a.na);
   const int ncl_max = sweep2_max_clusters<BN, CG>(SMEM_BUDGET);
@@ -2410,11 +2414,12 @@ static void plan(const srcgan_conv_params* p, int& bn, int& cblocks, int& nblock
 template <int BN, int KH>
 static int launch(const CUtensorMap& tx, const CUtensorMap& tg, const WgArgs& a, cudaStream_t st) {
   using C = WCfg<BN, KH>;
-  static bool attr_set = false;
-  if (!attr_set) {
+  static DeviceOnce attr_set;
+  int attr_set_dev;
+  if (attr_set.needed(&attr_set_dev)) {
     SRCGAN_CUDA(cudaFuncSetAttribute(conv_wgrad_tc_kernel<BN, KH>, cudaFuncAttributeMaxDynamicSharedMemorySize,
                                      C::SMEM_BYTES));
-    attr_set = true;
+    attr_set.mark(attr_set_dev);
   }
   const unsigned grid = (unsigned)(a.plan.nloads * a.cblocks * a.nblocks * a.splits);
   conv_wgrad_tc_kernel<BN, KH><<<grid, NUM_THREADS, C::SMEM_BYTES, st>>>(tx, tg, a);
@@ -2624,11 +2629,12 @@ static void plan3(const srcgan_conv_params* p, Wg3Args& a) {
 template <int BN>
 static int launch3(const CUtensorMap& tx, const CUtensorMap& tg, const Wg3Args& a, cudaStream_t st) {
   using C = W3Cfg<BN>;
-  static bool attr_set = false;
-  if (!attr_set) {
+  static DeviceOnce attr_set;
+  int attr_set_dev;
+  if (attr_set.needed(&attr_set_dev)) {
     SRCGAN_CUDA(cudaFuncSetAttribute(conv3x3_wgrad_halo_tc<BN>, cudaFuncAttributeMaxDynamicSharedMemorySize,
                                      C::SMEM_BYTES));
-    attr_set = true;
+    attr_set.mark(attr_set_dev);
   }
   const unsigned grid = (unsigned)(a.ngroups * a.cblocks * a.nblocks * a.splits);
   conv3x3_wgrad_halo_tc<BN><<<grid, NUM_THREADS, C::SMEM_BYTES, st>>>(tx, tg, a);
@@ -2917,10 +2923,11 @@ static int make_tmap_box(CUtensorMap* tm, const void* ptr, int c, int w, int h, 
 template <int BN>
 static int launch4(const CUtensorMap& tx, const CUtensorMap& tg, const Wg4Args& a, cudaStream_t st) {
   using C = W4Cfg<BN>;
-  static bool attr_set = false;
-  if (!attr_set) {
+  static DeviceOnce attr_set;
+  int attr_set_dev;
+  if (attr_set.needed(&attr_set_dev)) {
     SRCGAN_CUDA(cudaFuncSetAttribute(conv3x3_wgrad_stack_tc<BN>, cudaFuncAttributeMaxDynamicSharedMemorySize, C::SMEM));
-    attr_set = true;
+    attr_set.mark(attr_set_dev);
   }
   const unsigned grid = (unsigned)(a.cblocks * a.nblocks * a.splits);
   conv3x3_wgrad_stack_tc<BN><<<grid, NUM_THREADS, C::SMEM, st>>>(tx, tg, a);

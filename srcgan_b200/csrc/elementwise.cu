@@ -194,7 +194,7 @@ int depth_to_space(const void* src, int src_ld, void* dst, int dst_ld, const voi
 }
 
 template <typename T>
-__global__ void add_k(const T* __restrict__ a, int a_ld, const T* __restrict__ b, int b_ld, T* __restrict__ d, int d_ld,
+__global__ void add_k(const T* a, int a_ld, const T* b, int b_ld, T* d /* may alias a or b */, int d_ld,
                       int64_t npix, int c) {
   int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
   if (i >= npix * c) return;
@@ -203,13 +203,13 @@ __global__ void add_k(const T* __restrict__ a, int a_ld, const T* __restrict__ b
   d[m * d_ld + ch] = from_f32<T>(to_f32(a[m * a_ld + ch]) + to_f32(b[m * b_ld + ch]));
 }
 
-__global__ void add_vec_bf16(const __nv_bfloat16* __restrict__ a, int a_ld, const __nv_bfloat16* __restrict__ b, int b_ld,
-                             __nv_bfloat16* __restrict__ d, int d_ld, int64_t npix, int oct) {
+__global__ void add_vec_bf16(const __nv_bfloat16* a, int a_ld, const __nv_bfloat16* b, int b_ld,
+                             __nv_bfloat16* d /* may alias a or b */, int d_ld, int64_t npix, int oct) {
   int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
   if (i >= npix * oct) return;
   const int ch = (int)(i % oct) * 8;
   const int64_t m = i / oct;
-  uint4 qa = __ldg(reinterpret_cast<const uint4*>(a + m * a_ld + ch)), qb = __ldg(reinterpret_cast<const uint4*>(b + m * b_ld + ch));
+  uint4 qa = *reinterpret_cast<const uint4*>(a + m * a_ld + ch), qb = *reinterpret_cast<const uint4*>(b + m * b_ld + ch);
   const __nv_bfloat162* ha = reinterpret_cast<const __nv_bfloat162*>(&qa);
   const __nv_bfloat162* hb = reinterpret_cast<const __nv_bfloat162*>(&qb);
   uint4 o;
@@ -241,7 +241,7 @@ int add_slices(const void* a, int a_ld, const void* b, int b_ld, void* d, int d_
 }
 
 template <typename T>
-__global__ void act_bwd_k(const T* __restrict__ dy, int dy_ld, const T* __restrict__ y, int y_ld, T* __restrict__ d, int d_ld,
+__global__ void act_bwd_k(const T* dy, int dy_ld, const T* y, int y_ld, T* d /* may alias dy or y */, int d_ld,
                           int64_t npix, int c, float slope) {
   int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
   if (i >= npix * c) return;
@@ -251,13 +251,13 @@ __global__ void act_bwd_k(const T* __restrict__ dy, int dy_ld, const T* __restri
   d[m * d_ld + ch] = from_f32<T>(to_f32(y[m * y_ld + ch]) > 0.f ? g : g * slope);
 }
 
-__global__ void act_bwd_vec_bf16(const __nv_bfloat16* __restrict__ dy, int dy_ld, const __nv_bfloat16* __restrict__ y,
-                                 int y_ld, __nv_bfloat16* __restrict__ d, int d_ld, int64_t npix, int oct, float slope) {
+__global__ void act_bwd_vec_bf16(const __nv_bfloat16* dy, int dy_ld, const __nv_bfloat16* y,
+                                 int y_ld, __nv_bfloat16* d /* may alias dy or y */, int d_ld, int64_t npix, int oct, float slope) {
   int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
   if (i >= npix * oct) return;
   const int ch = (int)(i % oct) * 8;
   const int64_t m = i / oct;
-  uint4 qa = __ldg(reinterpret_cast<const uint4*>(dy + m * dy_ld + ch)), qb = __ldg(reinterpret_cast<const uint4*>(y + m * y_ld + ch));
+  uint4 qa = *reinterpret_cast<const uint4*>(dy + m * dy_ld + ch), qb = *reinterpret_cast<const uint4*>(y + m * y_ld + ch);
   const __nv_bfloat162* ha = reinterpret_cast<const __nv_bfloat162*>(&qa);
   const __nv_bfloat162* hb = reinterpret_cast<const __nv_bfloat162*>(&qb);
   uint4 o;

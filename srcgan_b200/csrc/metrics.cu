@@ -108,8 +108,9 @@ int ssim(const float* p, const float* t, int n, int c, int h, int w, float L, fl
   SRCGAN_REQUIRE(p && t && out, "ssim: null pointer");
   SRCGAN_REQUIRE(h >= SS_W && w >= SS_W, "ssim: image smaller than the 11x11 window");
   SRCGAN_REQUIRE(ws && ws_bytes >= ssim_workspace_bytes(n, c, h, w), "ssim: workspace too small");
-  static bool init = false;
-  if (!init) {
+  static DeviceOnce init;     // __constant__ memory is per device
+  int init_dev;
+  if (init.needed(&init_dev)) {
     float g[SS_W];
     double s = 0.0;
     for (int i = 0; i < SS_W; ++i) { g[i] = (float)exp(-((i - SS_W / 2) * (i - SS_W / 2)) / (2.0 * 1.5 * 1.5)); s += g[i]; }
@@ -118,8 +119,8 @@ int ssim(const float* p, const float* t, int n, int c, int h, int w, float L, fl
     for (int i = 0; i < SS_W; ++i) fs += g[i];
     for (int i = 0; i < SS_W; ++i) g[i] = g[i] / fs;
     (void)s;
-    SRCGAN_CUDA(cudaMemcpyToSymbol(c_gauss, g, sizeof(g)));
-    init = true;
+    SRCGAN_CUDA(cudaMemcpyToSymbolAsync(c_gauss, g, sizeof(g), 0, cudaMemcpyHostToDevice, st));
+    init.mark(init_dev);
   }
   const int ho = h - SS_W + 1, wo = w - SS_W + 1;
   dim3 grid(ceil_div(wo, SS_T), ceil_div(ho, SS_T), n * c), blk(32, 8);

@@ -2,7 +2,9 @@
 gradient averaging with NCCL over NVLink.
 
 The batch shards by patch: every rank runs the whole step on its own patches, BatchNorm
-uses rank-local statistics (what torch DDP does by default; the reference has no SyncBN to mirror) and
+normalises with rank-local batch statistics (no SyncBN - the reference has none to mirror) and the running
+mean / variance buffers therefore drift apart per rank (torch DDP would re-broadcast rank 0's every forward;
+here ``sync_buffers`` averages them on demand, and ``checkpoint.save_state`` callers should call it first) and
 the only exchange is the all-reduce of the fp32 gradients right before each optimizer step.  The
 trainers construct their optimizers themselves (train.py:191-192), so the exchange is attached as an
 optimizer *step pre-hook*: nothing in the trainer has to change.  ~27 MB per step over NVSwitch is
@@ -44,7 +46,9 @@ def broadcast_module_state(modules: Iterable[torch.nn.Module], src: int = 0) -> 
     with torch.no_grad():
         for m in modules:
             for t in list(m.parameters()) + list(m.buffers()):
-                dist.broadcast(t.data, src)
+                dist.broadcast(t, src)          # through the tensor itself (not .data): bumps its version counter
+            if hasattr(m, "invalidate_packs"):
+                m.invalidate_packs()            # packed bf16 weight caches are derived from the parameters
 
 
 def allreduce_mean_(tensors: List[torch.Tensor]) -> None:
@@ -61,6 +65,19 @@ def allreduce_mean_(tensors: List[torch.Tensor]) -> None:
         views.append(flat[off:off + k].view_as(t))
         off += k
     torch._foreach_copy_(tensors, views)                         # one fused scatter back into the .grad tensors
+
+
+def sync_buffers(modules: Iterable[torch.nn.Module]) -> None:
+    """Average the floating-point buffers (BatchNorm running statistics) over ranks - call before checkpointing."""
+    n = world()
+    if n == 1:
+        return
+    with torch.no_grad():
+        for m in modules:
+            for b in m.buffers():
+                if b.is_floating_point():
+                    dist.all_reduce(b, op=dist.ReduceOp.SUM)
+                    b.mul_(1.0 / n)
 
 
 def _step_pre_hook(optimizer, args, kwargs):

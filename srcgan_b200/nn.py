@@ -71,8 +71,16 @@ def _engine_mod():
 # ------------------------------------------------------------------------------------------
 
 class _Packs:
+    """Packed (engine-layout) copies of the parameters, keyed on ``(param._version, data_ptr)``.  Every in-place update
+    torch knows about (optimizer steps, ``load_state_dict``, ``copy_`` under ``no_grad``) bumps the version; a write through
+    ``param.data`` does NOT - code that does that must call ``net.invalidate_packs()`` (``dist.broadcast_module_state`` and
+    ``checkpoint.load_state`` do)."""
+
     def __init__(self):
         self.d: Dict[tuple, tuple] = {}
+
+    def clear(self) -> None:
+        self.d.clear()
 
     def get(self, key, params, build, layout: int, dtype: torch.dtype) -> torch.Tensor:
         stamp = tuple((p._version, p.data_ptr()) for p in params)
@@ -127,6 +135,10 @@ class _NetBase(nn.Module):
     # nn.Module.__setattr__ would try to register the cache; keep it a plain attribute
     def _pk(self) -> _Packs:
         return self.__dict__["_packs"]
+
+    def invalidate_packs(self) -> None:
+        """Drop the packed-weight caches (needed after writes through ``param.data``, which torch does not version)."""
+        self._pk().clear()
 
     def _w_f(self, conv: nn.Conv2d, dtype, layout=WL_RSCK):
         return self._pk().get(("f", id(conv)), (conv.weight,), lambda: conv.weight.detach(), layout, dtype)
@@ -480,7 +492,8 @@ class _NetFn(torch.autograd.Function):
         if not x.is_cuda:
             raise RuntimeError("srcgan_b200: input must be a CUDA tensor - there is no CPU fallback")
         st: dict = {}
-        out = net._forward_impl(x, st)
+        with torch.cuda.device(x.device):      # kernels launch on the current device's stream
+            out = net._forward_impl(x, st)
         ctx.net, ctx.st, ctx.params = net, st, params
         return out
 
@@ -490,7 +503,8 @@ class _NetFn(torch.autograd.Function):
         flags = ctx.needs_input_grad
         want = _want_map(flags[2:], params)
         sink = _GradSink()
-        dx = net._backward_impl(st, grad_out, sink, want, flags[1])
+        with torch.cuda.device(grad_out.device):
+            dx = net._backward_impl(st, grad_out, sink, want, flags[1])
         ctx.st = None
         grads = [sink.get(p) if want[id(p)] else None for p in params]
         return (None, dx) + tuple(grads)

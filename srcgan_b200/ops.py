@@ -27,8 +27,13 @@ def _stream() -> int:
 
 
 def _require_cuda(t: torch.Tensor, what: str) -> None:
+    """Kernels launch on the CURRENT device's stream: a tensor that lives on another GPU would be dereferenced by the wrong
+    device (or silently through peer access), so that is refused; callers switch with ``torch.cuda.device(t.device)``."""
     if not t.is_cuda:
         raise RuntimeError("srcgan_b200: %s must be a CUDA tensor - this library has no CPU path" % what)
+    if t.device.index != torch.cuda.current_device():
+        raise RuntimeError("srcgan_b200: %s lives on %s but the current CUDA device is %d - wrap the call in "
+                           "torch.cuda.device(tensor.device)" % (what, t.device, torch.cuda.current_device()))
 
 
 class Slice:
@@ -477,4 +482,25 @@ def lab2rgb(lab: torch.Tensor, normalised: bool = True) -> torch.Tensor:
     assert c == 3
     out = torch.empty_like(lab)
     _lib.check(_lib.load().srcgan_lab2rgb(lab.data_ptr(), out.data_ptr(), n, h, w, int(normalised), _stream()), "lab2rgb")
+    return out
+
+
+def rgb2lab_u8(img: torch.Tensor) -> torch.Tensor:
+    """uint8 (N,H,W,3) image -> normalised LAB (N,3,H,W) float32, float64 arithmetic (dataset.py:148-159)."""
+    _require_cuda(img, "image")
+    assert img.dtype == torch.uint8 and img.dim() == 4 and img.shape[3] == 3
+    img = img.contiguous()
+    n, h, w, _ = img.shape
+    out = torch.empty((n, 3, h, w), dtype=torch.float32, device=img.device)
+    _lib.check(_lib.load().srcgan_rgb2lab_u8(img.data_ptr(), out.data_ptr(), n, h, w, _stream()), "rgb2lab_u8")
+    return out
+
+
+def lab2rgb_u8(lab: torch.Tensor) -> torch.Tensor:
+    """normalised LAB (N,3,H,W) float32 -> uint8 (N,H,W,3) image with the reference's truncation (dataset.py:94-104)."""
+    lab = _f32c(lab, "lab")
+    n, c, h, w = lab.shape
+    assert c == 3
+    out = torch.empty((n, h, w, 3), dtype=torch.uint8, device=lab.device)
+    _lib.check(_lib.load().srcgan_lab2rgb_u8(lab.data_ptr(), out.data_ptr(), n, h, w, _stream()), "lab2rgb_u8")
     return out

@@ -22,6 +22,27 @@ from .nn import NLayerDiscriminator, RDDBNetA, RDDBNetB
 from .zoo import SRDenseNetA, SRDenseNetB
 
 
+def update_lr(optimizers, opt) -> None:
+    """Per-epoch learning-rate update, behaviour of train.py:196-213 / trainCas.py:45-61: a FRESH scheduler is built for
+    every optimizer on every call and stepped once.  With the default ``lr_policy='cosine'`` that multiplies the learning
+    rate by (1 + cos(pi / num_epochs)) / 2 each epoch; 'step' (StepLR 50, 0.1) leaves it unchanged on a fresh
+    scheduler's first step, 'plateau' (factor 0.2, patience 5) never fires on a fresh scheduler.  'linear' raises: the
+    reference's branch reads an undefined name (train.py:199) and cannot run."""
+    from torch.optim import lr_scheduler
+    import warnings
+    for optimizer in optimizers:
+        with warnings.catch_warnings():
+            warnings.simplefilter("ignore")     # "lr_scheduler.step() before optimizer.step()" on the first epoch, as upstream
+            if opt.lr_policy == "step":
+                lr_scheduler.StepLR(optimizer, step_size=50, gamma=0.1).step()
+            elif opt.lr_policy == "plateau":
+                lr_scheduler.ReduceLROnPlateau(optimizer, mode="min", factor=0.2, threshold=0.01, patience=5).step(opt.matrix)
+            elif opt.lr_policy == "cosine":
+                lr_scheduler.CosineAnnealingLR(optimizer, T_max=opt.num_epochs, eta_min=0).step()
+            else:
+                raise NotImplementedError("learning rate policy [%s] is not implemented" % opt.lr_policy)
+
+
 class ImagePool:
     """Buffer of previously generated images (pool_size 0 disables it); 50% of the queries swap the
     incoming image with a stored one.  Uses python ``random`` exactly as the reference does."""
@@ -116,6 +137,10 @@ class SRCycleGAN(object):
         self.optimizer_D = torch.optim.Adam(
             itertools.chain(self.netD_A.parameters(), self.netD_B.parameters()), lr=1e-5, betas=(opt.beta1, 0.999))
         self.optimizers = [self.optimizer_G, self.optimizer_D]
+
+    def update_lr(self, opt) -> None:
+        """train.py:196-213; called once per epoch by the reference's loop (train.py:378)."""
+        update_lr(self.optimizers, opt)
 
     @staticmethod
     def set_requires_grad(nets, requires_grad: bool = False) -> None:

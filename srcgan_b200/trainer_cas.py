@@ -63,6 +63,11 @@ class CasSRC(object):
         self.optimizers = [self.optimizer_G, self.optimizer_D]
         self.init_log()
 
+    def update_lr(self, opt) -> None:
+        """trainCas.py:45-61; called once per epoch by the reference's loop (trainCas.py:189)."""
+        from .trainer import update_lr
+        update_lr(self.optimizers, opt)
+
     def init_log(self):
         self._log = {"loss_sr": [], "loss_c": [], "psnr_sr": [], "psnr_c": []}
 

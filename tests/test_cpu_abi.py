@@ -40,6 +40,19 @@ def test_conv_params_struct_matches_header():
     assert C.sizeof(ConvParams) % 8 == 0
 
 
+def test_integration_doc_struct_matches_binding():
+    """The stand-alone ConvParams mirror printed in INTEGRATION.md is field for field (name and ctype) the one
+    srcgan_b200/_lib.py binds - a reader who copies the document must not pass a short struct."""
+    import ctypes as C
+    from srcgan_b200._lib import ConvParams
+    doc = open(os.path.join(ROOT, "INTEGRATION.md")).read()
+    body = doc[doc.index("class ConvParams(C.Structure)"):]
+    body = body[:body.index("lib.srcgan_conv_fprop.argtypes")]
+    fields = re.findall(r'\("([a-z0-9_]+)",\s*C\.(c_[a-z0-9_]+)\)', body)
+    assert fields == [(n, t.__name__) for n, t in ConvParams._fields_]
+    assert C.sizeof(ConvParams) % 8 == 0
+
+
 def test_argument_validation_without_gpu():
     """Bad arguments are rejected with an error code + message before any CUDA call."""
     import ctypes as C

@@ -1,0 +1,84 @@
+"""The reference's OWN callers on the CUDA path: the unmodified ``train.py`` (``SRCycleGAN.optimize_parameters``,
+/root/reference/src/train.py:325-340) and ``trainCas*.py`` (``CasSRC.optimize_parameters``, trainCas.py:133-153) are
+imported from the staged copy ``baseline/_ref/src`` (scripts/stage_reference.py; git-ignored, ships with the snapshot) in a
+child process whose sys.path puts ``srcgan_b200/dropin`` first, run real steps on cuda:0 and must reproduce the losses /
+images that the same scripts produced with the reference's own modules on the CPU (tests/golden/step_tiny.pt,
+cas_step_tiny.pt, written by oracle/make_golden.py)."""
+import math
+import os
+import subprocess
+import sys
+
+import pytest
+import torch
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+REF_SRC = os.path.join(ROOT, "baseline", "_ref", "src")
+pytestmark = [pytest.mark.gpu,
+              pytest.mark.skipif(not os.path.isfile(os.path.join(REF_SRC, "train.py")),
+                                 reason="baseline/_ref/src not staged (run scripts/stage_reference.py in the build container)")]
+
+
+def rand(shape, seed):
+    return torch.rand(*shape, generator=torch.Generator().manual_seed(seed))
+
+
+def relerr(a, b):
+    return float((a.double() - b.double()).abs().max() / b.double().abs().max().clamp_min(1e-30))
+
+
+def run_child(which, job, tmp_path, precision):
+    inp, outp = str(tmp_path / "job.pt"), str(tmp_path / "out.pt")
+    torch.save(job, inp)
+    env = dict(os.environ, SRCGAN_B200_PRECISION=precision)
+    env.pop("PYTHONPATH", None)
+    r = subprocess.run([sys.executable, "-W", "ignore", os.path.join(ROOT, "tests", "_ref_caller.py"), which, inp, outp],
+                       capture_output=True, text=True, cwd=str(tmp_path), env=env, timeout=900)
+    assert r.returncode == 0, r.stderr[-4000:]
+    log_dir = os.path.join(ROOT, "gpurun_out")
+    if os.path.isdir(log_dir):
+        with open(os.path.join(log_dir, "reference_callers.log"), "a") as f:
+            f.write("[%s %s] %s" % (which, precision, r.stdout))
+    return torch.load(outp, weights_only=False)
+
+
+@pytest.mark.parametrize("precision,tol", [("fp32", 1e-3), ("bf16", 3e-2)])
+def test_reference_train_py_steps_on_the_cuda_path(golden_step, tmp_path, precision, tol):
+    from oracle import srcgan_oracle as O
+    job = {"states": O.default_states(0), "seed": 5,
+           "batches": [O.synthetic_batch(2, lr=16, scale=4, seed=1234 + it) for it in range(len(golden_step["steps"]))]}
+    out = run_child("train", job, tmp_path, precision)
+    assert out["module_file"].startswith(REF_SRC)
+    assert out["classes"]["netG_A"] == "srcgan_b200.nn.RDDBNetB" and out["classes"]["netG_B"] == "srcgan_b200.nn.RDDBNetA"
+    assert out["classes"]["netD_A"] == "srcgan_b200.nn.NLayerDiscriminator"
+    assert out["classes"]["criterionGAN"] == "train.GANLoss"                  # the reference's own GANLoss consumes D's output
+    assert out["classes"]["criterionCycle"].startswith("srcgan_b200.losses.")
+    assert out["launches"] > 500                                              # the C-ABI kernels really ran
+    for it, rec in enumerate(golden_step["steps"]):
+        for n, v in rec["losses"].items():
+            assert math.isclose(out["steps"][it]["losses"][n], v, rel_tol=tol, abs_tol=1e-5 if precision == "fp32" else 2e-3), \
+                (precision, it, n, out["steps"][it]["losses"][n], v)
+        if "fake_B" in rec:
+            assert relerr(out["steps"][it]["fake_B"], rec["fake_B"]) < (1e-3 if precision == "fp32" else 5e-2)
+            assert relerr(out["steps"][it]["fake_A"], rec["fake_A"]) < (1e-3 if precision == "fp32" else 5e-2)
+    # train.py:378 -> update_lr: fresh CosineAnnealingLR(T_max=25) stepped once
+    f = (1 + math.cos(math.pi / 25)) / 2
+    assert out["lr_after_update"] == pytest.approx([1e-4 * f, 1e-5 * f], rel=1e-6)
+
+
+@pytest.mark.parametrize("variant", ["", "ConstLAB"])
+def test_reference_traincas_py_steps_on_the_cuda_path(golden_cas_step, tmp_path, variant):
+    from oracle import srcgan_oracle as O
+    const, lab = "Const" in variant, "LAB" in variant
+    job = {"up": 2, "SRModel": "SRCNN" if const else "ESPCN", "CModel": "SRCNN",
+           "states": {"A2C": O.init_srcnn(51, 1, 1) if const else O.init_espcn(51, 1, 1, 2),
+                      "C2B": O.init_srcnn(52, 1, 2 if lab else 3)},
+           "batches": [(rand((2, 1, 32, 32), 700 + it), rand((2, 3, 32, 32), 600 + it)) for it in range(2)]}
+    out = run_child("trainCas" + variant, job, tmp_path, "fp32")
+    assert out["classes"]["netG_A2C"].startswith("srcgan_b200.") and out["classes"]["netG_C2B"].startswith("srcgan_b200.")
+    assert out["launches"] > 20
+    for it, rec in enumerate(golden_cas_step[variant or "plain"]):
+        got = out["steps"][it]
+        for k in ("loss_SR", "loss_C", "psnr_SR", "psnr_C"):
+            assert math.isclose(got[k], rec[k], rel_tol=1e-3, abs_tol=1e-5), (variant, it, k, got[k], rec[k])
+        assert relerr(got["fake_AB"], rec["fake_AB"]) < 1e-3
