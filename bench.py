@@ -41,7 +41,10 @@ def parse():
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="srcgan_b200", choices=["srcgan_b200", "reference", "torch-gpu"])
     ap.add_argument("--variant", default="", help="torch-gpu arm: comma list of fp32,tf32,bf16-autocast-channels_last")
-    ap.add_argument("--batch", type=int, default=64, help="patches per GPU")
+    ap.add_argument("--workload", default="gd", choices=["gd", "cascade", "cascade_lab", "eval"],
+                    help="gd = BASELINE configs[1] (default, the driver's line); cascade / cascade_lab / eval = configs[2..4]")
+    ap.add_argument("--batch", type=int, default=None, help="units per GPU per step (default: 64 patches; eval: 16 tiles)")
+    ap.add_argument("--no-overlap", action="store_true", help="N>1: flat all-reduce in the step pre-hook instead of the bucket reducer")
     ap.add_argument("--lr-size", type=int, default=64, help="LR patch edge (HR = 4x)")
     ap.add_argument("--precision", default="bf16", choices=["bf16", "fp32"])
     ap.add_argument("--no-cpu-baseline", action="store_true")
@@ -210,6 +213,18 @@ def run_reference(args):
     rank = int(os.environ.get("RANK", "0"))
     if rank != 0:
         return
+    if args.workload != "gd":
+        v, cores, dt, kind, sample = cpu_cascade(args.workload == "cascade_lab", 1) if args.workload != "eval" else cpu_eval()
+        unit = "tiles/s" if args.workload == "eval" else UNIT
+        print(json.dumps({"impl": "reference", "metric": {"cascade": "cascade train-step patches/sec (x4)",
+                                                            "cascade_lab": "cascade train-step patches/sec (ConstLAB)",
+                                                            "eval": "eval sweep tiles/sec (512x512, x4)"}[args.workload],
+                          "value": v, "unit": unit, "n_gpus": args.gpus, "steps": 1, "warmup": 0, "ms_per_step": dt * 1e3,
+                          "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
+                          "config": {"workload": args.workload, "units_per_step": 1},
+                          "cpu_baseline": {"value": v, "unit": unit, "cores": cores, "kind": kind, "sample": sample},
+                          "e2e": {"value": v, "unit": unit, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}}), flush=True)
+        return
     batch = 1                      # bounded sample: ~9 s of CPU work per step at the full patch size
     steps, warmup = min(args.steps, 3), min(args.warmup, 1)
     v, cores, dt, kind = cpu_reference_steps(batch, args.lr_size, steps, warmup)
@@ -258,7 +273,7 @@ def run_torch_gpu(args):
         torch.backends.cuda.matmul.allow_tf32 = cfg["tf32"]
         torch.backends.cudnn.allow_tf32 = cfg["tf32"]
         torch.backends.cudnn.benchmark = True
-        batch = args.batch
+        batch = args.batch or 16
         while True:
             try:
                 torch.manual_seed(0)
@@ -313,7 +328,7 @@ def run_torch_gpu(args):
                 "dtype": name, "data": "synthetic",
                 "config": {"workload": "RDDBNet x4 G+D training step through stock PyTorch %s / cuDNN %s, batch %d (requested %d; "
                                        "halved on out-of-memory), %dx%d->%dx%d RGB" % (torch.__version__, torch.backends.cudnn.version(),
-                                                                                     batch, args.batch, lr, lr, lr * 4, lr * 4),
+                                                                                     batch, args.batch or 16, lr, lr, lr * 4, lr * 4),
                            "source": src, "peak_memory_gb": peak_gb},
                 "step_tflops": batch / (ms * 1e-3) * GFLOP_PER_PATCH * (lr / 64.0) ** 2 / 1e3}
         print(json.dumps(line), flush=True)
@@ -328,12 +343,204 @@ def run_torch_gpu(args):
 # this repo's arm
 # --------------------------------------------------------------------------------------------
 
+def cpu_cascade(lab: bool, batch: int):
+    """-> (patches/s, cores, seconds, kind, sample): one CasSRC.optimize_parameters on the host cores (the reference's own
+    trainCas*.py from baseline/_ref when staged, else the oracle port)."""
+    import torch
+    variant, up, sr_name = ("ConstLAB", 2, "SRDN") if lab else ("", 4, "RDDBNet")
+    import time as _t
+    torch.set_num_threads(os.cpu_count() or 1)
+    ra = torch.rand(batch, 1, 256, 256)
+    rb = torch.rand(batch, 3, 256, 256)
+    kind = "port"
+    if reference_staged():
+        import importlib
+        import_reference_train()                                  # stubs + the reference's model package on sys.path
+        mod = importlib.import_module("trainCas" + variant)
+        ropt = mod.params()
+        ropt.device = torch.device("cpu")
+        ropt.up, ropt.SRModel, ropt.CModel = up, sr_name, "ResDeconv"
+        m = mod.CasSRC(ropt)
+        m.init_log()
+        step, kind = (lambda: m.optimize_parameters(ra, rb)), "reference"
+    else:
+        from oracle import srcgan_oracle as O
+        if lab:
+            o = O.CascadeStepOracle(O.init_srdn(1), O.init_resdeconv(2, 2), lambda s_, t_: O.srdn(s_, t_),
+                                    lambda s_, t_: O.resdeconv(s_, t_), 2, "ConstLAB")
+        else:
+            o = O.CascadeStepOracle(O.init_rddbnet_pkg(1, 1, 1, 4), O.init_resdeconv(2, 3),
+                                    lambda s_, t_: O.rddbnet_pkg(s_, t_, 4), lambda s_, t_: O.resdeconv(s_, t_), 4, "")
+        step = lambda: o.optimize_parameters(ra, rb)
+    t0 = _t.perf_counter()
+    step()
+    dt = _t.perf_counter() - t0
+    return batch / dt, os.cpu_count() or 1, dt, kind, "1 step at batch %d, fp32, %s on the host cores, %.1f s" % (
+        batch, "the reference's own trainCas%s.CasSRC (baseline/_ref)" % variant if kind == "reference" else "oracle port", dt)
+
+
+
+def cpu_eval():
+    """-> (tiles/s, cores, seconds, kind, sample): one 512x512 tile through the reference's RDDBNetB + metrics.py on the host."""
+    import torch
+    import torch.nn.functional as F
+    import time as _t
+    torch.set_num_threads(os.cpu_count() or 1)
+    h = torch.rand(1, 3, 512, 512)
+    l = F.interpolate(h, scale_factor=0.25, mode="nearest")
+    kind = "port"
+    if reference_staged():
+        import importlib
+        import_reference_train()
+        mm, met = importlib.import_module("model.model"), importlib.import_module("metrics")
+        rnet = mm.RDDBNetB(3, 3, 64, nb=3, mode="x4").eval()
+        evs = [met.MSE(), met.PSNR(), met.AE(), met.SSIM()]
+
+        def step():
+            out = rnet(l)                                          # the reference builds the graph here too (no no_grad)
+            return [float(torch.as_tensor(e(out.detach(), h)).mean()) for e in evs]
+        kind = "reference"
+    else:
+        from oracle import srcgan_oracle as O
+        sd = O.init_rddbnet_b(1)
+
+        def step():
+            out = O.rddbnet_b(sd, l, "x4")
+            return [float(O.mse_loss(out, h)), float(O.psnr(out, h)), float(O.angular_error(out, h).mean()), float(O.ssim(out, h))]
+    t0 = _t.perf_counter()
+    step()
+    dt = _t.perf_counter() - t0
+    return 1.0 / dt, os.cpu_count() or 1, dt, kind, "1 tile (128x128 -> 512x512), fp32, %s on the host cores, %.1f s" % (
+        "the reference's RDDBNetB + metrics.py (baseline/_ref)" if kind == "reference" else "oracle port", dt)
+
+
+
+# ---- workloads (BASELINE.json configs; the default "gd" = configs[1] is the line the driver records) --------------------
+# each builder returns a dict: name, unit, units_per_step (per rank), step_resident(), step_e2e() -> d2h bytes,
+# h2d_bytes, gflop_per_unit (algorithmic, or None), cpu(batch) -> (units/s, seconds, kind, sample text), dp_nets/dp_opts
+
+def wl_gd(args, dev, rank):
+    """configs[1]: RDDBNet x4 G+D training step, 64x64 -> 256x256 RGB patches (src/train.py:325-340)."""
+    import random
+    import torch
+    import torch.nn.functional as F
+    from srcgan_b200 import trainer
+    opt = trainer.params()
+    opt.device, opt.mode, opt.net = dev, "x4", "1"
+    torch.manual_seed(0)                            # random-init weights of the reference's distributions (package ctor)
+    model = trainer.SRCycleGAN(opt)
+    random.seed(rank)
+    B, lr = args.batch, args.lr_size
+    g = torch.Generator().manual_seed(1234 + rank)
+    host_B = torch.rand(B, 3, lr * 4, lr * 4, generator=g).pin_memory()
+    real_B = host_B.to(dev, non_blocking=True)
+    real_A = F.interpolate(real_B, scale_factor=0.25, mode="nearest")
+
+    def step_resident():
+        model.optimize_parameters(real_A, real_B)
+
+    def step_e2e():
+        rb = host_B.to(dev, non_blocking=True)                       # pinned host -> device, every step
+        ra = F.interpolate(rb, scale_factor=0.25, mode="nearest")     # as train.py:381-382
+        model.optimize_parameters(ra, rb)
+        return 4 * len(model.current_losses())                        # device -> host read of the 9 losses
+
+    def cpu(batch):
+        v, cores, dt, kind = cpu_reference_steps(batch, lr, 1, 0)
+        return v, cores, dt, kind, "1 step at batch %d of the same full-size step, fp32, %s on the host cores, %.1f s" % (
+            batch, "the reference's own train.SRCycleGAN (baseline/_ref)" if kind == "reference" else "oracle port", dt)
+
+    return dict(name="RDDBNet x4 G+D training step (SRCycleGAN.optimize_parameters), batch %d per GPU, %dx%d->%dx%d RGB patches"
+                     % (B, lr, lr, lr * 4, lr * 4), metric=METRIC, unit=UNIT, units=B, step_resident=step_resident,
+                step_e2e=step_e2e, h2d=host_B.numel() * 4, gflop=GFLOP_PER_PATCH * (lr / 64.0) ** 2, cpu=cpu,
+                nets=[model.netG_A, model.netG_B, model.netD_A, model.netD_B], opts=[model.optimizer_G, model.optimizer_D])
+
+
+def _cascade(args, dev, rank, lab: bool):
+    """configs[2] / configs[3]: the cascaded SR + colourisation trainers (src/trainCas.py:133-153; trainCasConstLAB.py)."""
+    import torch
+    from srcgan_b200 import color, trainer_cas
+    opt = trainer_cas.params()
+    opt.device = dev
+    if lab:     # runConstLAB.sh: SRDN at full resolution (x2 blur), ResDeconv(1, 2) on LAB tensors
+        opt.up, opt.SRModel, opt.CModel, opt.variant = 2, "SRDN", "ResDeconv", "ConstLAB"
+    else:       # run.sh: RDDBNet x4 + ResDeconv
+        opt.up, opt.SRModel, opt.CModel, opt.variant = 4, "RDDBNet", "ResDeconv", ""
+    torch.manual_seed(0)
+    model = trainer_cas.CasSRC(opt)
+    B = args.batch
+    g = torch.Generator().manual_seed(1234 + rank)
+    host_A = torch.rand(B, 1, 256, 256, generator=g).pin_memory()
+    if lab:     # the dataset hands out uint8 RGB tiles; Basic._arr2lab (dataset.py:148-159) runs on the device here
+        host_B = (torch.rand(B, 256, 256, 3, generator=g) * 255).to(torch.uint8).pin_memory()
+        to_dev_B = lambda: color.image_to_lab(host_B.to(dev, non_blocking=True))
+        h2d = host_A.numel() * 4 + host_B.numel()
+    else:
+        host_B = torch.rand(B, 3, 256, 256, generator=g).pin_memory()
+        to_dev_B = lambda: host_B.to(dev, non_blocking=True)
+        h2d = host_A.numel() * 4 + host_B.numel() * 4
+    real_A, real_B = host_A.to(dev), to_dev_B()
+
+    def step_resident():
+        model.optimize_parameters(real_A, real_B)
+
+    def step_e2e():
+        model.init_log()
+        model.optimize_parameters(host_A.to(dev, non_blocking=True), to_dev_B())
+        return 4 * len(model.log_values())                            # one batched read of the four logged scalars
+
+    cpu = lambda batch: cpu_cascade(lab, batch)
+
+    what = ("SRDN x2 (full-resolution input) + ResDeconv(1,2) on LAB tensors, trainCasConstLAB.py step, uint8 RGB -> LAB on the device"
+            if lab else "RDDBNet x4 + ResDeconv, trainCas.py step")
+    return dict(name="cascaded SR + colourisation: %s, batch %d per GPU, 256x256 targets" % (what, B),
+                metric="cascade train-step patches/sec (%s)" % ("ConstLAB" if lab else "x4"), unit=UNIT, units=B,
+                step_resident=step_resident, step_e2e=step_e2e, h2d=h2d, gflop=None, cpu=cpu,
+                nets=[model.netG_A2C, model.netG_C2B], opts=[model.optimizer_G, model.optimizer_D])
+
+
+def wl_eval(args, dev, rank):
+    """configs[4]: eval sweep (src/test.py / testCas.py:63-85): generator inference on 512x512 tiles + MSE / PSNR / AE / SSIM."""
+    import torch
+    import torch.nn.functional as F
+    from srcgan_b200 import evaluate, nn as snn
+    torch.manual_seed(0)
+    net = snn.RDDBNetB(3, 3, 64, nb=3, mode="x4").to(dev).eval()
+    B = args.batch
+    g = torch.Generator().manual_seed(1234 + rank)
+    host_hr = [torch.rand(1, 3, 512, 512, generator=g).pin_memory() for _ in range(B)]
+    hr = [t.to(dev) for t in host_hr]
+    lr = [F.interpolate(t, scale_factor=0.25, mode="nearest") for t in hr]
+
+    def step_resident():
+        with torch.no_grad():
+            for l, h in zip(lr, hr):
+                evaluate.metrics_on_device(net(l), h)
+
+    def step_e2e():
+        pairs = []
+        for t in host_hr:
+            h = t.to(dev, non_blocking=True)
+            pairs.append((F.interpolate(h, scale_factor=0.25, mode="nearest"), h))
+        rows, _mean = evaluate.evaluate(net, pairs)                    # ONE device -> host copy for the whole sweep
+        return 16 * len(rows)
+
+    cpu = lambda batch: cpu_eval()
+
+    return dict(name="eval sweep: RDDBNetB x4 inference on 128x128 -> 512x512 tiles + fused MSE/PSNR/AE/SSIM, %d tiles per step per GPU" % B,
+                metric="eval sweep tiles/sec (512x512, x4)", unit="tiles/s", units=B, step_resident=step_resident,
+                step_e2e=step_e2e, h2d=B * 3 * 512 * 512 * 4, gflop=62.904 * 4.0, cpu=cpu, nets=[], opts=[])
+
+
+WORKLOADS = {"gd": wl_gd, "cascade": lambda a, d, r: _cascade(a, d, r, False), "cascade_lab": lambda a, d, r: _cascade(a, d, r, True),
+             "eval": wl_eval}
+
+
 def run_ours(args):
     import torch
     import torch.distributed as dist
-    import torch.nn.functional as F
 
-    from srcgan_b200 import _lib, dist as sdist, nn as snn, ops, trainer
+    from srcgan_b200 import _lib, dist as sdist, nn as snn, ops
 
     if not torch.cuda.is_available():
         raise SystemExit("bench.py: no CUDA device - the srcgan_b200 arm has no CPU fallback")
@@ -343,20 +550,14 @@ def run_ours(args):
     dev = torch.device("cuda", local_rank)
     snn.set_precision(args.precision)
     peaks = load_peaks()
-
-    opt = trainer.params()
-    opt.device, opt.mode, opt.net = dev, "x4", "1"
-    torch.manual_seed(0)                            # random-init weights of the reference's distributions (package ctor)
-    model = trainer.SRCycleGAN(opt)
-    sdist.make_data_parallel(model)
-
-    import random
-    random.seed(rank)
-    B, lr = args.batch, args.lr_size
-    g = torch.Generator().manual_seed(1234 + rank)
-    host_B = torch.rand(B, 3, lr * 4, lr * 4, generator=g).pin_memory()
-    real_B = host_B.to(dev, non_blocking=True)
-    real_A = F.interpolate(real_B, scale_factor=0.25, mode="nearest")
+    if args.batch is None:
+        args.batch = {"gd": 64, "cascade": 64, "cascade_lab": 8, "eval": 16}[args.workload]
+    wl = WORKLOADS[args.workload](args, dev, rank)
+    reducer = None
+    if world > 1 and wl["nets"]:
+        sdist.broadcast_module_state(wl["nets"])
+        reducer = sdist.attach(wl["opts"], wl["nets"], overlap=not args.no_overlap)
+    B = wl["units"]
 
     def barrier():
         if world > 1:
@@ -376,18 +577,12 @@ def run_ours(args):
             dist.all_reduce(ms, op=dist.ReduceOp.MAX)
         return float(ms.item())
 
-    def step_resident():
-        model.optimize_parameters(real_A, real_B)
-
+    step_resident = wl["step_resident"]
     d2h_bytes = 0
 
     def step_e2e():
         nonlocal d2h_bytes
-        rb = host_B.to(dev, non_blocking=True)                       # pinned host -> device, every step
-        ra = F.interpolate(rb, scale_factor=0.25, mode="nearest")     # as train.py:381-382
-        model.optimize_parameters(ra, rb)
-        losses = model.current_losses()                               # device -> host read of the 9 losses
-        d2h_bytes = 4 * len(losses)
+        d2h_bytes = wl["step_e2e"]()
 
     sampler = ClockSampler(local_rank)
     if rank == 0:
@@ -410,8 +605,8 @@ def run_ours(args):
     if not args.no_e2e:
         step_e2e()
         ms_e2e = timed(step_e2e, args.steps)
-        e2e = {"value": B * world * args.steps / (ms_e2e * 1e-3), "unit": UNIT,
-               "h2d_bytes_per_step": host_B.numel() * 4, "d2h_bytes_per_step": d2h_bytes}
+        e2e = {"value": B * world * args.steps / (ms_e2e * 1e-3), "unit": wl["unit"],
+               "h2d_bytes_per_step": wl["h2d"], "d2h_bytes_per_step": d2h_bytes}
     sampler.stop_flag = True
 
     if rank != 0:
@@ -426,11 +621,9 @@ def run_ours(args):
         name, d = top
         achieved = d["flops"] / (d["ms"] * 1e-3) / 1e12
         conv_ms = sum(v["ms"] for v in ksum.values())
+        traffic, traffic_note = measured_traffic(name)
         roof = {"bound": "tensor", "kernel": name, "achieved": achieved, "peak": peaks["tflops"], "unit": "TFLOP/s",
-                "frac": achieved / peaks["tflops"], "traffic": None,
-                "traffic_note": "launches of this kernel family span several layer shapes; per-shape DRAM bytes from ncu --set "
-                                "full are in profiles/r1_ncu_sweep2.txt and profiles/r1_ncu_wgrad_stack.txt (64->32 @64x256x256: "
-                                "563+248 MB measured vs 805 MB algorithmic; 192->64 @32x256x256: 897+247 MB vs 1074 MB)",
+                "frac": achieved / peaks["tflops"], "traffic": traffic, "traffic_note": traffic_note,
                 "peak_source": peaks["source"],
                 "launches_per_step": d["launches"] / args.steps, "avg_launch_ms": d["ms"] / d["launches"],
                 "share_of_step": d["ms"] / ms_instr, "conv_share_of_step": conv_ms / ms_instr,
@@ -442,27 +635,52 @@ def run_ours(args):
                 "families": {k: {"ms_per_step": v["ms"] / args.steps, "tflops": v["flops"] / (v["ms"] * 1e-3) / 1e12,
                                  "gbs": v["bytes"] / (v["ms"] * 1e-3) / 1e9,
                                  "launches_per_step": v["launches"] / args.steps} for k, v in sorted(ksum.items())}}
+    cfg = {"workload": wl["name"], "global_batch": B * world, "parallelism": "dp%d" % world,
+           "l2": "not flushed: each step streams >10 GB of activations per GPU through the 126 MB L2"}
+    if wl["gflop"] is not None:
+        cfg["algorithmic_gflop_per_unit"] = wl["gflop"]
+        cfg["step_tflops"] = value * wl["gflop"] / 1e3 / world
+    if reducer is not None and hasattr(reducer, "launched"):
+        cfg["allreduce"] = {"overlapped_launches": reducer.launched, "fallbacks": reducer.fallbacks,
+                            "how": "one NCCL all_reduce per network over its flat gradient bucket, launched inside backward "
+                                   "when the network's last wgrad has been issued, joined in the optimizer step pre-hook"}
     line = {
-        "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps, "warmup": args.warmup,
+        "metric": wl["metric"], "value": value, "unit": wl["unit"], "n_gpus": world, "steps": args.steps, "warmup": args.warmup,
         "ms_per_step": ms / args.steps, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
-        "dtype": args.precision, "data": "synthetic",
-        "config": {"workload": "RDDBNet x4 G+D training step (SRCycleGAN.optimize_parameters), batch %d per GPU, "
-                               "%dx%d->%dx%d RGB patches" % (B, lr, lr, lr * 4, lr * 4),
-                   "global_batch": B * world, "parallelism": "dp%d" % world,
-                   "l2": "not flushed: each step streams >10 GB of activations per GPU through the 126 MB L2",
-                   "algorithmic_gflop_per_patch": GFLOP_PER_PATCH * (lr / 64.0) ** 2,
-                   "step_tflops": value * GFLOP_PER_PATCH * (lr / 64.0) ** 2 / 1e3 / world},
+        "dtype": args.precision, "data": "synthetic", "config": cfg,
         "e2e": e2e, "gpu_launches": int(launches), "clocks": sampler.summary(), "roofline": roof,
     }
     if world == 1 and not args.no_cpu_baseline:
-        v, cores, dt, kind = cpu_reference_steps(1, lr, 1, 0)
-        line["cpu_baseline"] = {"value": v, "unit": UNIT, "cores": cores, "kind": kind,
-                                "sample": "1 step at batch 1 of the same full-size step, fp32, %s on the host cores, %.1f s"
-                                          % ("the reference's own train.SRCycleGAN (baseline/_ref)" if kind == "reference"
-                                             else "oracle port of the reference (pure PyTorch)", dt)}
+        v, cores, dt, kind, sample = wl["cpu"](1)
+        line["cpu_baseline"] = {"value": v, "unit": wl["unit"], "cores": cores, "kind": kind, "sample": sample}
     print(json.dumps(line), flush=True)
     if world > 1:
         dist.barrier()
+
+
+# per-launch DRAM traffic of the dominant kernel family, from the committed `ncu --set full` captures (profiles/): the
+# family's launches span several layer shapes, so the record names the shape it was measured on
+TRAFFIC = {
+    "conv3x3_wgrad_stack_tc": (2.73e9 + 0.02e9, "160->32 @64x256x256 (profiles/r1_ncu_wgrad_stack.txt): dram read 2.73 GB + write 0.02 GB "
+                               "per launch vs 1.61 GB algorithmic"),
+    "conv3x3_sweep2_tc<32,2>": (0.563e9 + 0.248e9, "64->32 @64x256x256 (profiles/r1_ncu_sweep2.txt): dram read 563 MB + write 248 MB per "
+                                "launch vs 805 MB algorithmic"),
+    "conv3x3_sweep2_tc<64,2>": (0.897e9 + 0.247e9, "192->64 @32x256x256 (profiles/r1_ncu_sweep2.txt): dram read 897 MB + write 247 MB per "
+                                "launch vs 1074 MB algorithmic"),
+}
+
+
+def measured_traffic(kernel: str):
+    try:
+        with open(os.path.join(ROOT, "profiles", "traffic.json")) as f:
+            t = json.load(f)
+        if kernel in t:
+            return float(t[kernel]["bytes_per_launch"]), t[kernel]["note"]
+    except Exception:
+        pass
+    if kernel in TRAFFIC:
+        return TRAFFIC[kernel]
+    return None, "no ncu --set full capture of this kernel family is committed"
 
 
 def main():

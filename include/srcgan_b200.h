@@ -115,6 +115,26 @@ int srcgan_pack_weights(const float* w_oihw, int cout, int cin, int kh, int kw, 
                         void* out, void* stream);
 size_t srcgan_packed_weight_bytes(int cout, int cin, int kh, int kw, int layout, int dtype);
 
+/* Batched re-pack of tcgen05-layout (SRCGAN_WL_TC) weights: ONE launch for all packed tensors of a network.  A packed
+   tensor is a list of source blocks concatenated along the GEMM-K channel axis; the table lives in DEVICE memory.
+   srcgan_pack_slots() gives the slot table (tap offset kh*kw_size + kw per slot) and the N tile BN for a layer shape. */
+typedef struct srcgan_pack_block {
+  const float* src;       /* fp32 OIHW parameter                                                     */
+  void* out;              /* base of the packed tensor (bf16); its K / N padding must already be zero */
+  int64_t nstride, kstride;   /* element strides of the GEMM-N / GEMM-K channel index in src          */
+  int64_t src_off;        /* element offset of this block's (n = 0, k = 0, tap 0)                     */
+  int64_t elem0;          /* first global work index of this block (prefix sum of n_pad*slots*k_len)  */
+  int32_t n_count;        /* GEMM-N channels that exist in src (rows n_count .. n_pad are written 0)  */
+  int32_t k0, k_len;      /* the block fills packed K channels [k0, k0 + k_len)                       */
+  int32_t bn, nchunks, total_slots;
+  int32_t taps;           /* kh * kw                                                                  */
+  int32_t flip;           /* 1: rotate the taps by 180 degrees (dgrad)                                */
+  float scale;
+  int32_t slot_off[16];
+} srcgan_pack_block;
+int srcgan_pack_slots(int cout, int kh, int kw, int layout, int32_t* slot_off16, int32_t* nslots, int32_t* bn);
+int srcgan_pack_weights_batch(const srcgan_pack_block* blocks_dev, int nblocks, int64_t total_elems, void* stream);
+
 int srcgan_conv_fprop(const srcgan_conv_params* p, void* stream);
 int srcgan_conv_dgrad(const srcgan_conv_params* p, void* stream);
 size_t srcgan_conv_wgrad_workspace_bytes(const srcgan_conv_params* p);
@@ -206,6 +226,21 @@ size_t srcgan_ssim_workspace_bytes(int n, int c, int h, int w);
 int srcgan_ssim(const float* pred, const float* truth, int n, int c, int h, int w, float L, float* out_per_image,
                 void* workspace, size_t workspace_bytes, void* stream);
 int srcgan_minmax(const float* a, int64_t n, float* out_min_max, void* stream);
+
+/* The eval sweep's four metrics (src/testCas.py:63-85: metrics.MSE, PSNR, AE, SSIM of src/metrics.py:10-144) in ONE kernel
+   launch over pred / truth [n][c][h][w] fp32; SSIM's data range L is chosen on the device from pred's min / max exactly as
+   metrics.py:102-111 does on the host.  out (8 + 2n floats): [0] MSE [1] PSNR [2] AE mean (degrees) [3] SSIM mean [4] L
+   [5] min(pred) [6] max(pred) [7] 0, then n per-image SSIM means, then n per-image AE.  The first 256 bytes of the workspace
+   hold a ticket counter: pass a workspace that was zero-filled once (the kernel re-arms it). */
+size_t srcgan_eval_metrics_workspace_bytes(int n, int c, int h, int w);
+int srcgan_eval_metrics(const float* pred, const float* truth, int n, int c, int h, int w, float* out, void* workspace,
+                        size_t workspace_bytes, void* stream);
+/* d SSIM-sum / d pred (losses.SSIM / DSSIMLoss are differentiable, src/losses.py:40-93,170-180):
+   dpred = *scale_dev * coef * d(sum of the SSIM map)/d pred; L_dev = device scalar holding the data range (out[4] above) */
+size_t srcgan_ssim_backward_workspace_bytes(int n, int c, int h, int w);
+int srcgan_ssim_backward(const float* pred, const float* truth, int n, int c, int h, int w, const float* L_dev,
+                         const float* scale_dev, float coef, float* dpred, void* workspace, size_t workspace_bytes,
+                         void* stream);
 
 /* colour: NCHW fp32; rgb in [0,1]; lab normalised as dataset.py:154-157 (L/100,(a,b+128)/255) when normalised!=0 */
 int srcgan_rgb2lab(const float* rgb, float* lab, int n, int h, int w, int normalised, void* stream);

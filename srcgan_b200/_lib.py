@@ -38,6 +38,18 @@ class ConvParams(C.Structure):
     ]
 
 
+class PackBlock(C.Structure):
+    """Mirror of ``srcgan_pack_block`` (include/srcgan_b200.h): one source block of a batched weight re-pack."""
+    _fields_ = [
+        ("src", C.c_void_p), ("out", C.c_void_p),
+        ("nstride", C.c_int64), ("kstride", C.c_int64), ("src_off", C.c_int64), ("elem0", C.c_int64),
+        ("n_count", C.c_int32), ("k0", C.c_int32), ("k_len", C.c_int32),
+        ("bn", C.c_int32), ("nchunks", C.c_int32), ("total_slots", C.c_int32),
+        ("taps", C.c_int32), ("flip", C.c_int32), ("scale", C.c_float),
+        ("slot_off", C.c_int32 * 16),
+    ]
+
+
 _P = C.c_void_p
 _I = C.c_int
 _L = C.c_int64
@@ -52,6 +64,8 @@ SIGNATURES = {
     "srcgan_last_kernel": (C.c_char_p, []),
     "srcgan_pack_weights": (_I, [_P, _I, _I, _I, _I, _I, _I, _P, _P]),
     "srcgan_packed_weight_bytes": (_Z, [_I, _I, _I, _I, _I, _I]),
+    "srcgan_pack_slots": (_I, [_I, _I, _I, _I, C.POINTER(C.c_int32), C.POINTER(C.c_int32), C.POINTER(C.c_int32)]),
+    "srcgan_pack_weights_batch": (_I, [_P, _I, _L, _P]),
     "srcgan_conv_fprop": (_I, [C.POINTER(ConvParams), _P]),
     "srcgan_conv_dgrad": (_I, [C.POINTER(ConvParams), _P]),
     "srcgan_conv_wgrad_workspace_bytes": (_Z, [C.POINTER(ConvParams)]),
@@ -80,6 +94,10 @@ SIGNATURES = {
     "srcgan_ssim_workspace_bytes": (_Z, [_I, _I, _I, _I]),
     "srcgan_ssim": (_I, [_P, _P, _I, _I, _I, _I, _F, _P, _P, _Z, _P]),
     "srcgan_minmax": (_I, [_P, _L, _P, _P]),
+    "srcgan_eval_metrics_workspace_bytes": (_Z, [_I, _I, _I, _I]),
+    "srcgan_eval_metrics": (_I, [_P, _P, _I, _I, _I, _I, _P, _P, _Z, _P]),
+    "srcgan_ssim_backward_workspace_bytes": (_Z, [_I, _I, _I, _I]),
+    "srcgan_ssim_backward": (_I, [_P, _P, _I, _I, _I, _I, _P, _P, _F, _P, _P, _Z, _P]),
     "srcgan_rgb2lab": (_I, [_P, _P, _I, _I, _I, _I, _P]),
     "srcgan_lab2rgb": (_I, [_P, _P, _I, _I, _I, _I, _P]),
     "srcgan_rgb2lab_u8": (_I, [_P, _P, _I, _I, _I, _P]),

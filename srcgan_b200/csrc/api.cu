@@ -42,6 +42,8 @@ bool conv_tc_supported(const srcgan_conv_params* p);
 int conv_fprop_tc(const srcgan_conv_params* p, cudaStream_t st);
 int pack_weights_tc_host(const float* w, int cout, int cin, int kh, int kw, int layout, void* out, cudaStream_t st);
 size_t packed_weight_bytes_tc(int cout, int cin, int kh, int kw, int layout);
+int pack_slots_tc(int cout, int kh, int kw, int layout, int32_t* slot_off16, int32_t* nslots, int32_t* bn);
+int pack_weights_batch(const srcgan_pack_block* blocks_dev, int nblocks, long long total, cudaStream_t st);
 bool conv_dgrad_tc_supported(const srcgan_conv_params* p);
 int conv_dgrad_tc(const srcgan_conv_params* p, cudaStream_t st);
 bool conv_wgrad_tc_supported(const srcgan_conv_params* p);
@@ -88,6 +90,12 @@ int ssim(const float* p, const float* t, int n, int c, int h, int w, float L, fl
          cudaStream_t st);
 int metrics_ae(const float* p, const float* t, int n, int c, int h, int w, float* out, cudaStream_t st);
 int minmax(const float* a, int64_t n, float* out, cudaStream_t st);
+size_t eval_metrics_workspace_bytes(int n, int c, int h, int w);
+int eval_metrics(const float* p, const float* t, int n, int c, int h, int w, float* out, void* ws, size_t ws_bytes,
+                 cudaStream_t st);
+size_t ssim_backward_workspace_bytes(int n, int c, int h, int w);
+int ssim_backward(const float* p, const float* t, int n, int c, int h, int w, const float* L_dev, const float* scale_dev,
+                  float coef, float* dp, void* ws, size_t ws_bytes, cudaStream_t st);
 int rgb2lab(const float* rgb, float* lab, int n, int h, int w, int normalised, cudaStream_t st);
 int lab2rgb(const float* lab, float* rgb, int n, int h, int w, int normalised, cudaStream_t st);
 int rgb2lab_u8(const uint8_t* rgb, float* lab, int n, int h, int w, cudaStream_t st);
@@ -118,6 +126,14 @@ int srcgan_pack_weights(const float* w, int cout, int cin, int kh, int kw, int l
   }
   SRCGAN_REQUIRE(layout == SRCGAN_WL_RSCK || layout == SRCGAN_WL_RSKC, "pack_weights: unknown layout %d", layout);
   return pack_weights_simt_host(w, cout, cin, kh, kw, layout, dtype, out, (cudaStream_t)stream);
+}
+
+int srcgan_pack_slots(int cout, int kh, int kw, int layout, int32_t* slot_off16, int32_t* nslots, int32_t* bn) {
+  SRCGAN_REQUIRE(slot_off16 && nslots && bn && cout > 0 && kh > 0 && kw > 0, "pack_slots: bad arguments");
+  return pack_slots_tc(cout, kh, kw, layout, slot_off16, nslots, bn);
+}
+int srcgan_pack_weights_batch(const srcgan_pack_block* blocks_dev, int nblocks, int64_t total_elems, void* stream) {
+  return pack_weights_batch(blocks_dev, nblocks, (long long)total_elems, (cudaStream_t)stream);
 }
 
 int srcgan_conv_fprop(const srcgan_conv_params* p, void* stream) {
@@ -281,6 +297,18 @@ int srcgan_ssim(const float* pred, const float* truth, int n, int c, int h, int 
 }
 int srcgan_minmax(const float* a, int64_t n, float* out_min_max, void* stream) {
   return minmax(a, n, out_min_max, (cudaStream_t)stream);
+}
+size_t srcgan_eval_metrics_workspace_bytes(int n, int c, int h, int w) { return eval_metrics_workspace_bytes(n, c, h, w); }
+int srcgan_eval_metrics(const float* pred, const float* truth, int n, int c, int h, int w, float* out, void* workspace,
+                        size_t workspace_bytes, void* stream) {
+  return eval_metrics(pred, truth, n, c, h, w, out, workspace, workspace_bytes, (cudaStream_t)stream);
+}
+size_t srcgan_ssim_backward_workspace_bytes(int n, int c, int h, int w) { return ssim_backward_workspace_bytes(n, c, h, w); }
+int srcgan_ssim_backward(const float* pred, const float* truth, int n, int c, int h, int w, const float* L_dev,
+                         const float* scale_dev, float coef, float* dpred, void* workspace, size_t workspace_bytes,
+                         void* stream) {
+  return ssim_backward(pred, truth, n, c, h, w, L_dev, scale_dev, coef, dpred, workspace, workspace_bytes,
+                       (cudaStream_t)stream);
 }
 int srcgan_rgb2lab(const float* rgb, float* lab, int n, int h, int w, int normalised, void* stream) {
   return rgb2lab(rgb, lab, n, h, w, normalised, (cudaStream_t)stream);

@@ -2037,6 +2037,20 @@ size_t packed_weight_bytes_tc(int cout, int cin, int kh, int kw, int layout) {
   return tc::packed_elems(cin, cout, kh * kw) * sizeof(__nv_bfloat16);     // SRCGAN_WL_TC_DGRAD_S2: 4 phases
 }
 
+// slot table + N tile of a SRCGAN_WL_TC pack, exactly what pack_weights_tc_host() below uses (for the batched packer)
+int pack_slots_tc(int cout, int kh, int kw, int layout, int32_t* slot_off16, int32_t* nslots, int32_t* bn) {
+  SRCGAN_REQUIRE(layout == SRCGAN_WL_TC && kh == kw, "pack_slots: only the stride-1 tcgen05 layout is batched");
+  SRCGAN_REQUIRE(tc_nch_ok(cout) || cout <= 16, "pack_slots: cout %d unsupported", cout);
+  tc::HostPlan hp = tc::fprop_plan(kh, 1, 0);
+  if (kh == 3 && cout <= 64)
+    for (int t = 0; t < 9; ++t) { hp.slot_kh[t] = t / 3; hp.slot_kw[t] = 2 - t % 3; }
+  SRCGAN_REQUIRE(hp.plan.total_slots <= 16, "pack_slots: too many taps");
+  for (int s2 = 0; s2 < 16; ++s2) slot_off16[s2] = s2 < hp.plan.total_slots ? hp.slot_kh[s2] * kw + hp.slot_kw[s2] : 0;
+  *nslots = hp.plan.total_slots;
+  *bn = tc::bn_for(cout);
+  return SRCGAN_OK;
+}
+
 int pack_weights_tc_host(const float* w, int cout, int cin, int kh, int kw, int layout, void* out, cudaStream_t st) {
   SRCGAN_REQUIRE(kh == kw, "pack_weights(tc): square filters only");
   const long long taps = (long long)kh * kw;

@@ -52,7 +52,8 @@ def broadcast_module_state(modules: Iterable[torch.nn.Module], src: int = 0) -> 
 
 
 def allreduce_mean_(tensors: List[torch.Tensor]) -> None:
-    """In-place mean over ranks of a list of same-dtype tensors through one flat bucket."""
+    """In-place mean over ranks of a list of same-dtype tensors through one flat bucket (the fallback path for gradients
+    that are not views of a network's bucket)."""
     n = world()
     if n == 1 or not tensors:
         return
@@ -65,6 +66,78 @@ def allreduce_mean_(tensors: List[torch.Tensor]) -> None:
         views.append(flat[off:off + k].view_as(t))
         off += k
     torch._foreach_copy_(tensors, views)                         # one fused scatter back into the .grad tensors
+
+
+class BucketReducer:
+    """Overlapped gradient exchange.  Every network of ``srcgan_b200.nn`` writes its parameter gradients into
+    ONE flat fp32 bucket (``nn._GradBucket``; ``param.grad`` is a view of it).  When the last pending backward of a network
+    has been issued - inside ``loss.backward()``, on autograd's thread - its ``_grads_ready_hook`` fires and the bucket's
+    ``all_reduce`` is launched asynchronously: NCCL's stream waits for the compute stream at that point and the reduction
+    runs beside the rest of the backward pass (G_B's 12.8 MB while G_A's last backward runs; D_A's while D_B's runs).  The
+    optimizer *step pre-hook* joins (a stream-side wait, no host synchronisation).  No ``torch.cat``, no copy back.
+
+    Gradients that are not bucket views at step time (a foreign ``.grad``, a module without buckets, a network whose
+    backward never completed) go through the flat-copy fallback so the result is always the mean over ranks."""
+
+    def __init__(self, nets, optimizers):
+        self.nets = [n for n in nets if hasattr(n, "grad_bucket")]
+        self.pending = {}            # id(net) -> (work, writes at launch)
+        self.launched = 0
+        self.fallbacks = 0
+        self.avg = dist.get_backend() == "nccl"
+        for n in self.nets:
+            n.__dict__["_grads_ready_hook"] = self._ready
+        self.handles = [opt.register_step_pre_hook(self._pre_step) for opt in optimizers]
+        self._owner = {}
+        for n in self.nets:
+            for p in n.parameters():
+                self._owner[id(p)] = n
+
+    def _ready(self, net) -> None:
+        b = net.grad_bucket()
+        if b.flat is None:
+            return
+        if id(net) in self.pending:
+            raise RuntimeError("srcgan_b200.dist: a second backward pass wrote gradients after this network's all-reduce "
+                               "was launched and before optimizer.step() - gradient accumulation over several backward "
+                               "passes needs attach(..., overlap=False)")
+        work = dist.all_reduce(b.flat, op=dist.ReduceOp.AVG if self.avg else dist.ReduceOp.SUM, async_op=True)
+        self.pending[id(net)] = (work, b.writes)
+        self.launched += 1
+
+    def _pre_step(self, optimizer, args, kwargs) -> None:
+        n = world()
+        params = [p for g in optimizer.param_groups for p in g["params"] if p.grad is not None]
+        nets, loose = {}, []
+        for p in params:
+            net = self._owner.get(id(p))
+            if net is not None and net.grad_bucket().holds(p):
+                nets[id(net)] = net
+            else:
+                loose.append(p.grad)
+        for net in nets.values():
+            b = net.grad_bucket()
+            got = self.pending.pop(id(net), None)
+            if got is not None and got[1] != b.writes:
+                raise RuntimeError("srcgan_b200.dist: gradients were written after the all-reduce was launched")
+            if got is None:                                      # the ready hook never fired: reduce here, synchronously
+                work = dist.all_reduce(b.flat, op=dist.ReduceOp.AVG if self.avg else dist.ReduceOp.SUM, async_op=True)
+                self.fallbacks += 1
+            else:
+                work = got[0]
+            work.wait()                                          # the compute stream waits for NCCL's; the host does not
+            if not self.avg:
+                b.flat.mul_(1.0 / n)
+            net.__dict__["_pending_bw"] = 0
+        if loose:
+            self.fallbacks += 1
+            allreduce_mean_(loose)
+
+    def detach(self) -> None:
+        for h in self.handles:
+            h.remove()
+        for n in self.nets:
+            n.__dict__["_grads_ready_hook"] = None
 
 
 def sync_buffers(modules: Iterable[torch.nn.Module]) -> None:
@@ -85,14 +158,21 @@ def _step_pre_hook(optimizer, args, kwargs):
     allreduce_mean_(grads)
 
 
-def attach(optimizers: Iterable[torch.optim.Optimizer]):
-    """Average gradients over ranks before every ``optimizer.step()``.  Returns the hook handles."""
+def attach(optimizers: Iterable[torch.optim.Optimizer], nets: Iterable[torch.nn.Module] = (), overlap: bool = True):
+    """Average gradients over ranks before every ``optimizer.step()``.  With ``nets`` (the ``srcgan_b200.nn`` modules the
+    optimizers own) and ``overlap`` the exchange is the bucketed, overlapped ``BucketReducer``; otherwise one flat
+    all-reduce inside the step pre-hook.  Returns the reducer (or the hook handles)."""
     if world() == 1:
         return []
+    optimizers = list(optimizers)
+    nets = list(nets)
+    if overlap and nets:
+        return BucketReducer(nets, optimizers)
     return [opt.register_step_pre_hook(_step_pre_hook) for opt in optimizers]
 
 
-def make_data_parallel(model) -> list:
-    """``model``: a trainer.SRCycleGAN (or the reference's own).  Broadcast + hooks."""
-    broadcast_module_state([model.netG_A, model.netG_B, model.netD_A, model.netD_B])
-    return attach([model.optimizer_G, model.optimizer_D])
+def make_data_parallel(model, overlap: bool = True):
+    """``model``: a trainer.SRCycleGAN (or the reference's own, built on the drop-in modules).  Broadcast + hooks."""
+    nets = [model.netG_A, model.netG_B, model.netD_A, model.netD_B]
+    broadcast_module_state(nets)
+    return attach([model.optimizer_G, model.optimizer_D], nets, overlap)

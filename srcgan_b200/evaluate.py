@@ -16,13 +16,10 @@ _EVALUATORS = (M.MSE(), M.PSNR(), M.AE(), M.SSIM())
 
 
 def metrics_on_device(pred: torch.Tensor, truth: torch.Tensor) -> torch.Tensor:
-    """(4,) fp32 device tensor [MSE, PSNR, AE (mean over the batch), SSIM] - no host sync except the
-    data-range probe SSIM needs (same heuristic as metrics.py:102-111)."""
-    vals = []
-    for ev in _EVALUATORS:
-        v = ev(pred, truth)
-        vals.append(v.mean() if v.dim() else v)
-    return torch.stack([v.float() for v in vals])
+    """(4,) fp32 device tensor [MSE, PSNR, AE (mean over the batch), SSIM]: ONE kernel launch (csrc/metrics.cu
+    eval_metrics_k), no host synchronisation - SSIM's data-range heuristic (metrics.py:102-111) runs on the device."""
+    from . import ops
+    return ops.eval_metrics(pred, truth)[:4]
 
 
 @torch.no_grad()

@@ -62,8 +62,7 @@ class PSNRLoss(nn.Module):
 
 
 class DSSIMLoss(nn.Module):
-    """(1 - SSIM)/2.  Forward only: the trainers in scope never back-propagate through it
-    (GANLoss is built with gan_mode='lsgan', train.py:186)."""
+    """(1 - SSIM) / 2, differentiable through SSIM like the reference's (src/losses.py:170-180)."""
 
     def __init__(self):
         super().__init__()
@@ -73,6 +72,4 @@ class DSSIMLoss(nn.Module):
         return "DSSIM"
 
     def forward(self, output, target):
-        if output.requires_grad and torch.is_grad_enabled():
-            raise NotImplementedError("srcgan_b200.losses.DSSIMLoss: backward through SSIM is not implemented")
         return (1.0 - self.criterion(output, target)) / 2.0

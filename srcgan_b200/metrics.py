@@ -42,6 +42,30 @@ class PSNR(object):
         return 10 * torch.log10(1 / mse)
 
 
+class _SSIMFn(torch.autograd.Function):
+    """mean (or per-image mean) of the SSIM map, differentiable w.r.t. the prediction (losses.py:40-93 builds it from
+    conv2d calls, so autograd flows through it in the reference; here: csrc/metrics.cu ssim_bwd_*)."""
+
+    @staticmethod
+    def forward(ctx, y_pred, y_true, size_average):
+        res = ops.eval_metrics(y_pred, y_true)
+        n = y_pred.shape[0]
+        ctx.save_for_backward(y_pred.detach(), y_true.detach(), res[4:5])
+        ctx.size_average = size_average
+        return res[3] if size_average else res[8:8 + n]
+
+    @staticmethod
+    def backward(ctx, go):
+        y_pred, y_true, L = ctx.saved_tensors
+        n, c, h, w = y_pred.shape
+        count = c * (h - 10) * (w - 10)
+        if ctx.size_average:
+            d = ops.ssim_backward(y_pred, y_true, L, go, 1.0 / (n * count))
+        else:   # per-image upstream gradients: one launch per image (the reference's scripts never use this form)
+            d = torch.cat([ops.ssim_backward(y_pred[i:i + 1], y_true[i:i + 1], L, go[i], 1.0 / count) for i in range(n)])
+        return d, None, None
+
+
 class SSIM(object):
     def __init__(self, des="structural similarity index"):
         self.des = des
@@ -53,11 +77,6 @@ class SSIM(object):
         if w_size != 11 or full:
             raise NotImplementedError("srcgan_b200.metrics.SSIM: only w_size=11, full=False (what the reference's "
                                       "scripts use) is implemented")
-        lo, hi = ops.minmax(y_pred).tolist()              # data-range heuristics, metrics.py:102-111
-        L = (255 if hi > 128 else 1) - (-1 if lo < -0.5 else 0)
-        n, c, h, w = y_pred.shape
-        sums = ops.ssim_sums(y_pred, y_true, float(L))
-        count = c * (h - w_size + 1) * (w - w_size + 1)
-        if size_average:
-            return sums.sum() / (n * count)
-        return sums / count
+        # the data-range heuristic of metrics.py:102-111 (max > 128 -> 255, min < -0.5 -> +1) runs inside the kernel:
+        # no host synchronisation
+        return _SSIMFn.apply(y_pred, y_true, bool(size_average))

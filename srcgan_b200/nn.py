@@ -24,7 +24,7 @@ from typing import Dict, List, Optional, Tuple
 import torch
 import torch.nn as nn
 
-from . import ops
+from . import _lib, ops
 from .ops import ENGINE_SIMT, ENGINE_TC, Slice, WL_RSCK, WL_RSKC, WL_TC, WL_TC_DGRAD_S2
 
 LRELU = 0.2
@@ -70,17 +70,35 @@ def _engine_mod():
 # packed-weight cache
 # ------------------------------------------------------------------------------------------
 
+class _PackEntry:
+    __slots__ = ("dest", "blocks", "stamp", "params", "cout", "ksize", "k_total")
+
+
 class _Packs:
     """Packed (engine-layout) copies of the parameters, keyed on ``(param._version, data_ptr)``.  Every in-place update
     torch knows about (optimizer steps, ``load_state_dict``, ``copy_`` under ``no_grad``) bumps the version; a write through
     ``param.data`` does NOT - code that does that must call ``net.invalidate_packs()`` (``dist.broadcast_module_state`` and
-    ``checkpoint.load_state`` do)."""
+    ``checkpoint.load_state`` do).
+
+    Two paths:
+    * ``get``     - one tensor at a time: ``build()`` (a torch expression) + ``srcgan_pack_weights``; the SIMT layouts and
+                    the few stride-2 / padded tcgen05 layers.
+    * ``get_tc``  - stride-1 tcgen05 layout, declared as SOURCE BLOCKS of parameters (transposed / rotated / sliced / scaled,
+                    concatenated along K).  All such tensors of a network are re-packed by ONE launch
+                    (``srcgan_pack_weights_batch``) the first time one of them is requested after its parameters changed:
+                    no ATen flip / cat / mul, ~4 launches per training step instead of ~1100."""
 
     def __init__(self):
         self.d: Dict[tuple, tuple] = {}
+        self.tc: Dict[tuple, _PackEntry] = {}
+        self.table = None            # device copy of the block table of every entry in self.tc
+        self.table_key = None
+        self.repacks = 0             # batched launches so far (tests / bench read it)
 
     def clear(self) -> None:
         self.d.clear()
+        for e in self.tc.values():
+            e.stamp = None
 
     def get(self, key, params, build, layout: int, dtype: torch.dtype) -> torch.Tensor:
         stamp = tuple((p._version, p.data_ptr()) for p in params)
@@ -93,36 +111,192 @@ class _Packs:
         self.d[k] = (stamp, packed)
         return packed
 
+    # ---- batched tcgen05 packs ------------------------------------------------------------------------------------
+    @staticmethod
+    def _stamp(params):
+        return tuple((p._version, p.data_ptr()) for p in params)
+
+    def get_tc(self, key, cout: int, ksize: int, blocks) -> torch.Tensor:
+        """``blocks``: [(param OIHW, transposed, n_lo, k_lo, k_len, scale)] concatenated along the GEMM-K axis.
+        Not transposed: GEMM-N = the parameter's output channels [n_lo, n_lo + cout), GEMM-K = its input channels
+        [k_lo, k_lo + k_len).  Transposed (dgrad): N = input channels, K = output channels, taps rotated by 180 degrees."""
+        e = self.tc.get(key)
+        if e is None:
+            e = _PackEntry()
+            e.params = tuple(b[0] for b in blocks)
+            e.blocks, e.cout, e.ksize = list(blocks), cout, ksize
+            e.k_total = sum(b[4] for b in blocks)
+            dev = e.params[0].device
+            nbytes = _lib.load().srcgan_packed_weight_bytes(cout, e.k_total, ksize, ksize, WL_TC, _lib.DT_BF16)
+            e.dest = torch.zeros(nbytes // 2, dtype=torch.bfloat16, device=dev)       # K / N padding stays zero for good
+            e.stamp = None
+            self.tc[key] = e
+            self.table = None
+            self._launch([e])                                   # first use: this tensor alone
+            e.stamp = self._stamp(e.params)
+            return e.dest
+        if e.stamp != self._stamp(e.params):
+            if e.dest.device != e.params[0].device:             # the module was moved: start over on the new device
+                del self.tc[key]
+                self.table = None
+                return self.get_tc(key, cout, ksize, blocks)
+            self.repack_all()
+        return e.dest
+
+    def _table_for(self, entries):
+        import ctypes as C
+        lib = _lib.load()
+        rows, elem0 = [], 0
+        slot = (C.c_int32 * 16)()
+        ns, bn = C.c_int32(), C.c_int32()
+        for e in entries:
+            _lib.check(lib.srcgan_pack_slots(e.cout, e.ksize, e.ksize, WL_TC, slot, C.byref(ns), C.byref(bn)), "pack_slots")
+            taps = e.ksize * e.ksize
+            n_pad = (e.cout + bn.value - 1) // bn.value * bn.value
+            nchunks = (e.k_total + 63) // 64
+            k0 = 0
+            for (p, transposed, n_lo, k_lo, k_len, scale) in e.blocks:
+                o, i = p.shape[0], p.shape[1]
+                b = _lib.PackBlock()
+                b.src, b.out = p.data_ptr(), e.dest.data_ptr()
+                if transposed:
+                    b.nstride, b.kstride, b.src_off = taps, i * taps, n_lo * taps + k_lo * i * taps
+                else:
+                    b.nstride, b.kstride, b.src_off = i * taps, taps, n_lo * i * taps + k_lo * taps
+                b.elem0, b.n_count, b.k0, b.k_len = elem0, e.cout, k0, k_len
+                b.bn, b.nchunks, b.total_slots, b.taps = bn.value, nchunks, ns.value, taps
+                b.flip, b.scale = int(bool(transposed)), float(scale)
+                for t in range(16):
+                    b.slot_off[t] = slot[t]
+                rows.append(b)
+                elem0 += n_pad * ns.value * k_len
+                k0 += k_len
+        arr = (_lib.PackBlock * len(rows))(*rows)
+        host = torch.frombuffer(bytearray(bytes(arr)), dtype=torch.uint8)
+        return host.to(entries[0].dest.device), len(rows), elem0
+
+    def _launch(self, entries) -> None:
+        with torch.cuda.device(entries[0].dest.device):
+            tab, n, total = self._table_for(entries)
+            _lib.check(_lib.load().srcgan_pack_weights_batch(tab.data_ptr(), n, total, ops._stream()), "pack_weights_batch")
+        self.repacks += 1
+        self._keep = tab                                        # alive until the next launch (stream-ordered use)
+
+    def repack_all(self) -> None:
+        entries = list(self.tc.values())
+        key = tuple(p.data_ptr() for e in entries for p in e.params)
+        if self.table is None or self.table_key != key:
+            self.table, self.table_n, self.table_total = self._table_for(entries)
+            self.table_key = key
+        with torch.cuda.device(entries[0].dest.device):
+            _lib.check(_lib.load().srcgan_pack_weights_batch(self.table.data_ptr(), self.table_n, self.table_total,
+                                                             ops._stream()), "pack_weights_batch")
+        self.repacks += 1
+        for e in entries:
+            e.stamp = self._stamp(e.params)
+
+
+def _batched_ok(cout: int, ksize: int) -> bool:
+    """Shapes the batched packer (csrc/pack_batch.cu) takes: the stride-1 tcgen05 layout's channel counts, <= 16 taps."""
+    return (cout in (32, 64, 128, 256) or cout <= 16) and ksize * ksize <= 16 and not os.environ.get("SRCGAN_B200_NO_BATCH_PACK")
+
 
 def _wT(w: torch.Tensor) -> torch.Tensor:
     """OIHW weight of the stride-1 convolution that computes dgrad: swap in/out, rotate taps 180."""
     return w.detach().transpose(0, 1).flip(2, 3)
 
 
-class _GradSink:
-    """Collects parameter gradients produced by wgrad kernels (handles shared weights)."""
+class _GradBucket:
+    """Flat fp32 buffer that holds the gradients of ALL parameters of one network; the wgrad kernels write straight into
+    it and ``param.grad`` becomes a view of it (what DDP calls ``gradient_as_bucket_view``).  Consequences:
+
+    * the data-parallel exchange is ONE ``all_reduce`` over ``flat`` per network - no ``torch.cat``, no copy back;
+    * a network that runs several times in one backward pass (G_A / G_B: three times per ``loss_G.backward()``,
+      train.py:298-323) accumulates in place: the first node of a pass returns the view to autograd, the later ones add to
+      the same memory and return nothing - the ~470 per-parameter ATen adds per step of autograd's input buffer are gone.
+
+    ``seen`` remembers, per parameter, the autograd graph task that wrote it last (``torch._C._current_graph_task_id``)."""
+    ALIGN = 64          # floats: every parameter's gradient starts on a 256-byte boundary
 
     def __init__(self):
+        self.flat: Optional[torch.Tensor] = None
+        self.off: Dict[int, int] = {}
+        self.key = None
+        self.seen: Dict[int, int] = {}
+        self.writes = 0                 # backward passes that wrote into the bucket (the DP reducer checks it)
+
+    def ensure(self, params, device) -> None:
+        key = (tuple(id(p) for p in params), str(device))
+        if self.key == key and self.flat is not None:
+            return
+        off, total = {}, 0
+        for p in params:
+            if id(p) in off:
+                continue
+            off[id(p)] = total
+            total += (p.numel() + self.ALIGN - 1) // self.ALIGN * self.ALIGN
+        self.flat = torch.zeros(max(total, 1), dtype=torch.float32, device=device)
+        self.off, self.key, self.seen = off, key, {}
+
+    def view(self, p) -> Optional[torch.Tensor]:
+        o = self.off.get(id(p))
+        if o is None or p.dtype != torch.float32:
+            return None
+        return self.flat[o:o + p.numel()].view(p.shape)
+
+    def holds(self, p) -> bool:
+        """True if ``p.grad`` currently IS this bucket's view of ``p``."""
+        o = self.off.get(id(p))
+        g = p.grad
+        return (o is not None and g is not None and self.flat is not None and g.dtype == torch.float32
+                and g.data_ptr() == self.flat.data_ptr() + 4 * o and g.is_contiguous())
+
+
+class _GradSink:
+    """Collects the parameter gradients produced by the wgrad kernels of ONE backward call of one network (handles shared
+    weights: HRconv is applied eight times).  With a bucket the kernels write into the flat buffer; see _GradBucket."""
+
+    def __init__(self, bucket: Optional[_GradBucket] = None, graph_task: int = -1):
         self.g: Dict[int, torch.Tensor] = {}
+        self.ret: Dict[int, Optional[torch.Tensor]] = {}
+        self.bucket, self.gt = bucket, graph_task
 
     def slot(self, p: Optional[torch.Tensor], wanted: bool):
         """-> (tensor or None, accumulate)"""
         if p is None or not wanted:
             return None, False
         t = self.g.get(id(p))
-        if t is None:
+        if t is not None:
+            return t, True
+        v = self.bucket.view(p) if self.bucket is not None else None
+        if v is None:
             t = torch.empty_like(p, dtype=torch.float32, memory_format=torch.contiguous_format)
-            self.g[id(p)] = t
+            self.g[id(p)] = self.ret[id(p)] = t
             return t, False
-        return t, True
+        b = self.bucket
+        # accumulate in place when this graph task already wrote the parameter (an earlier node of the same backward
+        # pass), or when p.grad still is the bucket view (gradient accumulation over several backward passes)
+        inplace = (self.gt != -1 and b.seen.get(id(p)) == self.gt) or b.holds(p)
+        b.seen[id(p)] = self.gt
+        self.g[id(p)] = v
+        self.ret[id(p)] = None if inplace else v
+        return v, inplace
 
     def get(self, p):
-        return self.g.get(id(p))
+        """What the autograd Function returns for ``p``: the gradient tensor, or None if it was added in place."""
+        return self.ret.get(id(p))
 
     def put(self, p, t: torch.Tensor) -> None:
         """Adopt an externally computed gradient (adds if the parameter already has one)."""
         cur = self.g.get(id(p))
-        self.g[id(p)] = t if cur is None else cur.add_(t)
+        if cur is not None:
+            cur.add_(t)
+            return
+        v, acc = self.slot(p, True)
+        if acc:
+            v.add_(t)
+        else:
+            v.copy_(t)
 
 
 class _NetBase(nn.Module):
@@ -131,6 +305,12 @@ class _NetBase(nn.Module):
     def __init__(self):
         super().__init__()
         object.__setattr__(self, "_packs", _Packs())
+        object.__setattr__(self, "_bucket", _GradBucket())
+        object.__setattr__(self, "_pending_bw", 0)          # forward calls whose backward has not run yet
+        object.__setattr__(self, "_grads_ready_hook", None)  # callable(net): every pending backward of this net has run
+
+    def grad_bucket(self) -> "_GradBucket":
+        return self.__dict__["_bucket"]
 
     # nn.Module.__setattr__ would try to register the cache; keep it a plain attribute
     def _pk(self) -> _Packs:
@@ -141,9 +321,15 @@ class _NetBase(nn.Module):
         self._pk().clear()
 
     def _w_f(self, conv: nn.Conv2d, dtype, layout=WL_RSCK):
+        w = conv.weight
+        if layout == WL_TC and dtype == torch.bfloat16 and _batched_ok(w.shape[0], w.shape[2]):
+            return self._pk().get_tc(("f", id(conv)), w.shape[0], w.shape[2], [(w, False, 0, 0, w.shape[1], 1.0)])
         return self._pk().get(("f", id(conv)), (conv.weight,), lambda: conv.weight.detach(), layout, dtype)
 
     def _w_t(self, conv: nn.Conv2d, dtype, layout=WL_RSCK):
+        w = conv.weight
+        if layout == WL_TC and dtype == torch.bfloat16 and _batched_ok(w.shape[1], w.shape[2]):
+            return self._pk().get_tc(("t", id(conv)), w.shape[1], w.shape[2], [(w, True, 0, 0, w.shape[0], 1.0)])
         return self._pk().get(("t", id(conv)), (conv.weight,), lambda: _wT(conv.weight).contiguous(), layout, dtype)
 
     def _w_d(self, conv: nn.Conv2d, dtype):
@@ -353,6 +539,11 @@ class _RRDBGenerator(_NetBase):
                 blocks.append(_wT(convs[j - 1].weight[:, sl]))
             return torch.cat(blocks, dim=1).contiguous()
 
+        if layout == WL_TC and dtype == torch.bfloat16 and _batched_ok(sl.stop - sl.start, 3):
+            # [conv5 | conv4 | ... | conv(k+1)] slices, transposed + rotated, conv5's scaled: blocks of one batched re-pack
+            blocks = [(convs[4].weight, True, sl.start, 0, nf, s5)]
+            blocks += [(convs[j - 1].weight, True, sl.start, 0, gc, 1.0) for j in range(4, k, -1)]
+            return self._pk().get_tc(("dense", id(rdb), k, s5), sl.stop - sl.start, 3, blocks)
         params = tuple(c.weight for c in convs[k:])
         return self._pk().get(("dense", id(rdb), k, s5), params, build, layout, dtype)
 
@@ -484,17 +675,25 @@ def _want_map(ctx_flags, params) -> dict:
     return {id(p): bool(f) for p, f in zip(params, ctx_flags)}
 
 
+def _device_of(t: torch.Tensor):
+    import contextlib
+    return torch.cuda.device(t.device) if t.is_cuda else contextlib.nullcontext()
+
+
 class _NetFn(torch.autograd.Function):
     """forward(net, x, *params) -> NCHW fp32; the module implements _forward_impl/_backward_impl."""
 
     @staticmethod
     def forward(ctx, net, x, *params):
-        if not x.is_cuda:
-            raise RuntimeError("srcgan_b200: input must be a CUDA tensor - there is no CPU fallback")
+        if not x.is_cuda and not getattr(net, "_host_test_double", False):   # (tests/test_dist_cpu.py drives the bucket /
+            raise RuntimeError("srcgan_b200: input must be a CUDA tensor - there is no CPU fallback")   # reducer logic on gloo)
         st: dict = {}
-        with torch.cuda.device(x.device):      # kernels launch on the current device's stream
+        with _device_of(x):                    # kernels launch on the current device's stream
             out = net._forward_impl(x, st)
         ctx.net, ctx.st, ctx.params = net, st, params
+        ctx.counted = any(ctx.needs_input_grad[2:])      # False under no_grad / for frozen parameters: no backward will come
+        if ctx.counted:
+            net.__dict__["_pending_bw"] += 1
         return out
 
     @staticmethod
@@ -502,11 +701,25 @@ class _NetFn(torch.autograd.Function):
         net, st, params = ctx.net, ctx.st, ctx.params
         flags = ctx.needs_input_grad
         want = _want_map(flags[2:], params)
-        sink = _GradSink()
-        with torch.cuda.device(grad_out.device):
+        bucket = None
+        if any(flags[2:]) and not os.environ.get("SRCGAN_B200_NO_GRAD_BUCKET"):
+            bucket = net.grad_bucket()
+            plist = net.__dict__.get("_bucket_params")
+            if plist is None:
+                plist = net.__dict__["_bucket_params"] = list(net.parameters())
+            bucket.ensure(plist, grad_out.device)
+            bucket.writes += 1
+        sink = _GradSink(bucket, torch._C._current_graph_task_id())
+        with _device_of(grad_out):
             dx = net._backward_impl(st, grad_out, sink, want, flags[1])
         ctx.st = None
         grads = [sink.get(p) if want[id(p)] else None for p in params]
+        del sink                                   # no Python reference may outlive this call: autograd adopts the views
+        if ctx.counted:
+            d = net.__dict__
+            d["_pending_bw"] = max(0, d["_pending_bw"] - 1)
+            if d["_pending_bw"] == 0 and d["_grads_ready_hook"] is not None and any(flags[2:]):
+                d["_grads_ready_hook"](net)
         return (None, dx) + tuple(grads)
 
 

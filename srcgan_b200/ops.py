@@ -504,3 +504,39 @@ def lab2rgb_u8(lab: torch.Tensor) -> torch.Tensor:
     out = torch.empty((n, h, w, 3), dtype=torch.uint8, device=lab.device)
     _lib.check(_lib.load().srcgan_lab2rgb_u8(lab.data_ptr(), out.data_ptr(), n, h, w, _stream()), "lab2rgb_u8")
     return out
+
+
+_eval_ws = {}
+
+
+def eval_metrics(pred: torch.Tensor, truth: torch.Tensor) -> torch.Tensor:
+    """One kernel launch -> fp32 device tensor of 8 + 2n values: [MSE, PSNR, AE mean, SSIM mean, L, min, max, 0,
+    per-image SSIM (n), per-image AE (n)] (see include/srcgan_b200.h); no host synchronisation."""
+    p, t = _f32c(pred, "metric input"), _f32c(truth, "metric input")
+    assert p.shape == t.shape and p.dim() == 4
+    n, c, h, w = p.shape
+    lib = _lib.load()
+    nbytes = lib.srcgan_eval_metrics_workspace_bytes(n, c, h, w)
+    key = (p.device.index, torch.cuda.current_stream().cuda_stream)
+    ws = _eval_ws.get(key)
+    if ws is None or ws.numel() < nbytes:
+        ws = torch.zeros(max(int(nbytes), 1 << 16), dtype=torch.uint8, device=p.device)   # zeroed once: the ticket counter
+        _eval_ws[key] = ws
+    out = torch.empty(8 + 2 * n, dtype=torch.float32, device=p.device)
+    _lib.check(lib.srcgan_eval_metrics(p.data_ptr(), t.data_ptr(), n, c, h, w, out.data_ptr(), ws.data_ptr(), ws.numel(),
+                                       _stream()), "eval_metrics")
+    return out
+
+
+def ssim_backward(pred: torch.Tensor, truth: torch.Tensor, L_dev: torch.Tensor, scale_dev: torch.Tensor,
+                  coef: float) -> torch.Tensor:
+    """scale_dev * coef * d(sum of the SSIM map)/d pred; L_dev / scale_dev are 1-element fp32 device tensors."""
+    p, t = _f32c(pred, "ssim input"), _f32c(truth, "ssim input")
+    n, c, h, w = p.shape
+    lib = _lib.load()
+    ws = workspace(lib.srcgan_ssim_backward_workspace_bytes(n, c, h, w), p.device)
+    dp = torch.empty_like(p)
+    sc = scale_dev.detach().to(torch.float32).reshape(1).contiguous()
+    _lib.check(lib.srcgan_ssim_backward(p.data_ptr(), t.data_ptr(), n, c, h, w, L_dev.data_ptr(), sc.data_ptr(), float(coef),
+                                        dp.data_ptr(), ws.data_ptr(), ws.numel(), _stream()), "ssim_backward")
+    return dp

@@ -49,8 +49,12 @@ def test_integration_doc_struct_matches_binding():
     body = doc[doc.index("class ConvParams(C.Structure)"):]
     body = body[:body.index("lib.srcgan_conv_fprop.argtypes")]
     fields = re.findall(r'\("([a-z0-9_]+)",\s*C\.(c_[a-z0-9_]+)\)', body)
-    assert fields == [(n, t.__name__) for n, t in ConvParams._fields_]
-    assert C.sizeof(ConvParams) % 8 == 0
+    assert [n for n, _t in fields] == [n for n, _t in ConvParams._fields_]
+    assert all(getattr(C, t) is bt for (_n, t), (_m, bt) in zip(fields, ConvParams._fields_))   # c_int32 is an alias of c_int
+
+    class DocParams(C.Structure):
+        _fields_ = [(n, getattr(C, t)) for n, t in fields]
+    assert C.sizeof(DocParams) == C.sizeof(ConvParams) and C.sizeof(ConvParams) % 8 == 0
 
 
 def test_argument_validation_without_gpu():
@@ -288,3 +292,39 @@ def test_reference_traincas_script_constructs_on_the_dropin():
         "print('ok')" % os.path.join(ROOT, "srcgan_b200", "dropin"))
     out = subprocess.run([sys.executable, "-W", "ignore", "-c", code], capture_output=True, text=True, cwd="/tmp")
     assert out.returncode == 0 and "ok" in out.stdout, out.stderr[-3000:]
+
+
+def test_update_lr_mirrors_the_reference_epoch_schedule():
+    """train.py:196-213 / trainCas.py:45-61: a fresh scheduler per call, stepped once - with the default 'cosine' policy the
+    learning rate is multiplied by (1 + cos(pi / num_epochs)) / 2 per epoch.  Compared with the closed form and, where the
+    reference tree is present, with the reference's own ``update_lr`` on identical optimizers."""
+    import math
+    import torch
+    from srcgan_b200 import trainer
+    opt = trainer.params()
+    lin = torch.nn.Linear(2, 2)
+    opts = [torch.optim.Adam(lin.parameters(), lr=1e-4, betas=(0.5, 0.999)), torch.optim.Adam(lin.parameters(), lr=1e-5)]
+    for _ in range(3):
+        trainer.update_lr(opts, opt)
+    f = (1 + math.cos(math.pi / opt.num_epochs)) / 2
+    assert opts[0].param_groups[0]["lr"] == pytest.approx(1e-4 * f ** 3, rel=1e-9)
+    assert opts[1].param_groups[0]["lr"] == pytest.approx(1e-5 * f ** 3, rel=1e-9)
+    opt.lr_policy = "linear"
+    with pytest.raises(NotImplementedError):
+        trainer.update_lr(opts, opt)
+    assert hasattr(trainer.SRCycleGAN, "update_lr")
+    from srcgan_b200 import trainer_cas
+    assert hasattr(trainer_cas.CasSRC, "update_lr")
+    if os.path.isdir("/root/reference/src"):
+        from oracle import ref_harness
+        train = ref_harness.import_train()
+
+        class Holder:                                  # update_lr only touches self.optimizers
+            pass
+        h = Holder()
+        h.optimizers = [torch.optim.Adam(lin.parameters(), lr=1e-4, betas=(0.5, 0.999)), torch.optim.Adam(lin.parameters(), lr=1e-5)]
+        ropt = train.params()
+        for _ in range(3):
+            train.SRCycleGAN.update_lr(h, ropt)
+        assert h.optimizers[0].param_groups[0]["lr"] == pytest.approx(1e-4 * f ** 3, rel=1e-9)
+        assert h.optimizers[1].param_groups[0]["lr"] == pytest.approx(1e-5 * f ** 3, rel=1e-9)

@@ -26,7 +26,7 @@ def _worker(rank, world, port, out):
     sdist.broadcast_module_state([net])                        # ... start from rank 0's state
     w0 = net[0].weight.detach().clone()
     opt = torch.optim.Adam(net.parameters(), lr=1e-3)
-    handles = sdist.attach([opt])
+    handles = sdist.attach([opt])                              # no bucketed nets: the flat-copy path
     assert len(handles) == 1
     g = torch.Generator().manual_seed(100 + rank)              # rank-local shard of the batch
     x = torch.rand(2, 3, 8, 8, generator=g)
@@ -50,6 +50,142 @@ def _worker(rank, world, port, out):
     if rank == 0:
         out.put("ok")
     dist.destroy_process_group()
+
+
+class _HostNet:
+    """Built lazily (needs srcgan_b200.nn): a two-layer net on the REAL _NetBase / _NetFn / _GradBucket machinery whose
+    kernels are torch CPU ops, so the bucket-view and overlapped-reducer logic runs under gloo without a GPU."""
+
+    @staticmethod
+    def make():
+        from srcgan_b200 import nn as snn
+
+        class HostNet(snn._NetBase):
+            _host_test_double = True
+
+            def __init__(self):
+                super().__init__()
+                self.a = torch.nn.Linear(4, 5)
+                self.b = torch.nn.Linear(5, 3, bias=False)
+
+            def forward(self, x):
+                return snn._NetFn.apply(self, x, *self.parameters())
+
+            def _forward_impl(self, x, st):
+                h = x @ self.a.weight.detach().t() + self.a.bias.detach()
+                st["x"], st["h"] = x, h
+                return h @ self.b.weight.detach().t()
+
+            def _backward_impl(self, st, g, sink, want, need_dx):
+                W = lambda p: want.get(id(p), False)
+                for p, val in ((self.b.weight, g.t() @ st["h"]),):
+                    t, acc = sink.slot(p, W(p))
+                    if t is not None:
+                        t.add_(val) if acc else t.copy_(val)
+                gh = g @ self.b.weight.detach()
+                for p, val in ((self.a.weight, gh.t() @ st["x"]), (self.a.bias, gh.sum(0))):
+                    t, acc = sink.slot(p, W(p))
+                    if t is not None:
+                        t.add_(val) if acc else t.copy_(val)
+                return gh @ self.a.weight.detach() if need_dx else None
+
+        return HostNet()
+
+
+def _bucket_worker(rank, world, port, out):
+    os.environ.update(MASTER_ADDR="127.0.0.1", MASTER_PORT=str(port), RANK=str(rank), WORLD_SIZE=str(world),
+                      LOCAL_RANK=str(rank))
+    from srcgan_b200 import dist as sdist
+    sdist.init_from_env(backend="gloo")
+    torch.manual_seed(rank)
+    net = _HostNet.make()
+    extra = torch.nn.Linear(3, 1)                              # a plain torch module in the same optimizer: "loose" grads
+    sdist.broadcast_module_state([net, extra])
+    ref = _HostNet.make()                                      # autograd reference of the same maths, plain torch
+    ref.load_state_dict(net.state_dict())
+    opt = torch.optim.SGD(list(net.parameters()) + list(extra.parameters()), lr=0.1)
+    red = sdist.attach([opt], [net])
+    assert isinstance(red, sdist.BucketReducer)
+    for it in range(3):
+        g = torch.Generator().manual_seed(10 * it + rank)
+        x1, x2 = torch.rand(6, 4, generator=g), torch.rand(6, 4, generator=g)
+        opt.zero_grad()
+        # the network runs TWICE in one backward pass (like G_A / G_B in loss_G.backward()): second node adds in place
+        loss = extra(net(x1)).square().mean() + 2.0 * extra(net(x2)).square().mean()
+        loss.backward()
+        b = net.grad_bucket()
+        assert all(b.holds(p) for p in net.parameters())       # param.grad IS the bucket view
+        # plain-torch reference of the local gradient
+        ws = {k: v.detach().clone().requires_grad_(True) for k, v in net.state_dict().items()}
+        f = lambda x: (x @ ws["a.weight"].t() + ws["a.bias"]) @ ws["b.weight"].t()
+        e = lambda h: h @ extra.weight.detach().t() + extra.bias.detach()
+        (e(f(x1)).square().mean() + 2.0 * e(f(x2)).square().mean()).backward()
+        local = {k: v.grad.clone() for k, v in ws.items()}
+        launched = red.launched
+        opt.step()                                             # pre-hook joins the all-reduce launched inside backward
+        assert launched == it + 1 and red.launched == it + 1   # ... it was launched by the ready hook, not by the pre-hook
+        for k, p in net.named_parameters():
+            parts = [torch.zeros_like(local[k]) for _ in range(world)]
+            dist.all_gather(parts, local[k])
+            assert torch.allclose(p.grad, sum(parts) / world, atol=1e-6), (it, k)
+        eg = [torch.zeros_like(extra.weight.grad) for _ in range(world)]
+        dist.all_gather(eg, extra.weight.grad)
+        assert torch.equal(eg[0], eg[1])                       # loose gradients were averaged by the fallback path
+    ws_ = [torch.zeros_like(net.a.weight) for _ in range(world)]
+    dist.all_gather(ws_, net.a.weight.detach())
+    assert torch.equal(ws_[0], ws_[1])                         # replicas in lock-step after three steps
+    # frozen parameters (backward_G phase of the discriminators): no gradient, no bucket traffic, hook does not fire
+    for p in net.parameters():
+        p.requires_grad = False
+    x = torch.rand(2, 4, requires_grad=True)
+    net(x).sum().backward()
+    assert x.grad is not None and red.launched == 3
+    if rank == 0:
+        out.put("ok")
+    dist.destroy_process_group()
+
+
+def test_bucket_views_and_overlapped_reducer_world2_gloo():
+    ctx = mp.get_context("spawn")
+    out = ctx.Queue()
+    port = _free_port()
+    procs = [ctx.Process(target=_bucket_worker, args=(r, 2, port, out)) for r in range(2)]
+    for p in procs:
+        p.start()
+    for p in procs:
+        p.join(timeout=180)
+        assert p.exitcode == 0
+    assert out.get(timeout=5) == "ok"
+
+
+def test_gradient_accumulation_over_backward_passes_uses_the_bucket_in_place():
+    """Two backward passes without zero_grad: the second adds into the bucket that p.grad already views."""
+    net = _HostNet.make()
+    x1, x2 = torch.rand(3, 4), torch.rand(3, 4)
+    net(x1).sum().backward()
+    g1 = {k: p.grad.clone() for k, p in net.named_parameters()}
+    net(x2).sum().backward()
+    ref = _HostNet.make()
+    ref.load_state_dict(net.state_dict())
+    for p in ref.parameters():
+        p.grad = None
+    import os as _os
+    _os.environ["SRCGAN_B200_NO_GRAD_BUCKET"] = "1"
+    try:
+        ref(x1).sum().backward()
+        ref(x2).sum().backward()
+    finally:
+        del _os.environ["SRCGAN_B200_NO_GRAD_BUCKET"]
+    for (k, p), q in zip(net.named_parameters(), ref.parameters()):
+        assert net.grad_bucket().holds(p) and not ref.grad_bucket().holds(q)
+        assert torch.allclose(p.grad, q.grad, atol=1e-6), k
+        assert not torch.allclose(p.grad, g1[k])
+    # zero_grad(set_to_none) then a new pass: written fresh, not added
+    for p in net.parameters():
+        p.grad = None
+    net(x1).sum().backward()
+    for k, p in net.named_parameters():
+        assert torch.allclose(p.grad, g1[k], atol=1e-6), k
 
 
 def test_gradient_averaging_world2_gloo():

@@ -201,6 +201,60 @@ def test_metrics_against_oracle_and_golden(golden_modules):
     assert repr(metrics.SSIM()) == "SSIM" and repr(metrics.AE()) == "AE"
 
 
+@pytest.mark.parametrize("shape,scale,shift", [((2, 3, 40, 36), 1.0, 0.0), ((1, 3, 150, 97), 255.0, 0.0),
+                                               ((3, 1, 11, 11), 2.0, -1.0), ((1, 3, 43, 75), 256.0, -1.0),
+                                               ((1, 3, 512, 512), 1.0, 0.0)])
+def test_fused_eval_metrics_kernel(shape, scale, shift):
+    """MSE, PSNR, AE, SSIM (+ the data range L picked on the device: 1 / 255 / 2 / 256) from ONE launch, against the oracle's
+    separate functions; ragged sizes (not multiples of the 32-pixel tile, the 11x11 minimum), 1 and 3 channels."""
+    from oracle import srcgan_oracle as O
+    from srcgan_b200 import _lib, ops
+    a = torch.rand(*shape, generator=torch.Generator().manual_seed(41)) * scale + shift
+    b = (a + 0.05 * scale * torch.randn(shape, generator=torch.Generator().manual_seed(42)))
+    before = _lib.launch_count()
+    res = ops.eval_metrics(a.to(DEV), b.to(DEV))
+    assert _lib.launch_count() - before == 1 and _lib.last_kernel() == "eval_metrics"
+    res = res.cpu()
+    n = shape[0]
+    want_L = (255 if float(a.max()) > 128 else 1) - (-1 if float(a.min()) < -0.5 else 0)
+    assert float(res[4]) == want_L and float(res[5]) == float(a.min()) and float(res[6]) == float(a.max())
+    close = lambda x, y, t=5e-5: math.isclose(float(x), float(y), rel_tol=t, abs_tol=1e-6)
+    assert close(res[0], O.mse_loss(a, b)) and close(res[1], O.psnr(a, b))
+    assert close(res[3], O.ssim(a, b))
+    assert torch.allclose(res[8:8 + n], O.ssim(a, b, size_average=False), rtol=5e-5, atol=1e-6)
+    if shape[1] == 3:
+        assert torch.allclose(res[8 + n:8 + 2 * n], O.angular_error(a, b), rtol=2e-4)
+        assert close(res[2], O.angular_error(a, b).mean(), 2e-4)
+    # bit-reproducible (fixed-order reduction behind the atomic ticket)
+    assert torch.equal(ops.eval_metrics(a.to(DEV), b.to(DEV)).cpu(), res)
+
+
+@pytest.mark.parametrize("shape,scale", [((2, 3, 40, 36), 1.0), ((1, 1, 75, 43), 255.0)])
+def test_dssim_loss_backward(shape, scale):
+    """losses.DSSIMLoss is differentiable through SSIM (src/losses.py:170-180): gradient against autograd on the oracle."""
+    from oracle import srcgan_oracle as O
+    from srcgan_b200 import losses
+    a = (torch.rand(*shape, generator=torch.Generator().manual_seed(51)) * scale).requires_grad_(True)
+    b = (a.detach() + 0.1 * scale * torch.randn(shape, generator=torch.Generator().manual_seed(52)))
+    ref = O.dssim_loss(a.double(), b.double())
+    ref.backward()
+    ad = a.detach().to(DEV).requires_grad_(True)
+    out = losses.DSSIMLoss()(ad, b.to(DEV))
+    (out * 3.0).backward()
+    assert math.isclose(float(out), float(ref), rel_tol=5e-5, abs_tol=1e-6)
+    err = (ad.grad.cpu().double() / 3.0 - a.grad.double()).abs().max() / a.grad.double().abs().max()
+    assert float(err) < 1e-3, float(err)
+    # per-image form
+    from srcgan_b200 import metrics
+    ad2 = a.detach().to(DEV).requires_grad_(True)
+    v = metrics.SSIM()(ad2, b.to(DEV), size_average=False)
+    (v * torch.arange(1, shape[0] + 1, device=DEV, dtype=torch.float32)).sum().backward()
+    a2 = a.detach().double().requires_grad_(True)
+    (O.ssim(a2, b.double(), size_average=False) * torch.arange(1, shape[0] + 1, dtype=torch.float64)).sum().backward()
+    err = (ad2.grad.cpu().double() - a2.grad).abs().max() / a2.grad.abs().max()
+    assert float(err) < 1e-3, float(err)
+
+
 def test_color_against_oracle():
     import numpy as np
     from oracle import srcgan_oracle as O

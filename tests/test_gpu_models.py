@@ -461,3 +461,74 @@ def test_cascade_step_against_golden(golden_cas_step, variant):
         assert relerr(m.fake_AB, rec["fake_AB"]) < TOL
     with pytest.raises(NotImplementedError):
         trainer_cas.build_model("NoSuchNet", 1, 3)
+
+
+def test_batched_repack_matches_single_packs():
+    """csrc/pack_batch.cu (one launch per network) writes bit for bit what srcgan_pack_weights writes from the torch-side
+    flip / cat / scale expressions: forward, transposed and mirrored-dense-block tensors of G_B and the discriminator; after an
+    in-place parameter update ONE launch refreshes everything; invalidate_packs() covers writes through ``.data``."""
+    from oracle import srcgan_oracle as O
+    from srcgan_b200 import nn as snn, ops
+    snn.set_precision("bf16")
+
+    def legacy(e):
+        parts = []
+        for (p, transposed, n_lo, k_lo, k_len, scale) in e.blocks:
+            w = p.detach()
+            blk = snn._wT(w[k_lo:k_lo + k_len, n_lo:n_lo + e.cout]) if transposed else w[n_lo:n_lo + e.cout, k_lo:k_lo + k_len]
+            parts.append(blk * scale)
+        return ops.pack_weights(torch.cat(parts, dim=1).contiguous(), ops.WL_TC, torch.bfloat16)
+
+    for net, sd, shape in ((snn.RDDBNetA(3, 3, 64, nb=3, mode="x4"), O.init_rddbnet_a(12), (1, 3, 128, 128)),
+                           (snn.NLayerDiscriminator(3, 64, 2), O.init_discriminator(13), (2, 3, 64, 64))):
+        net.load_state_dict(sd)
+        net.to(DEV)
+        x = rand(shape, 5).to(DEV).requires_grad_(True)
+        net(x).sum().backward()
+        pk = net._pk()
+        assert len(pk.tc) >= (90 if isinstance(net, snn.RDDBNetA) else 1)
+        for key, e in pk.tc.items():
+            assert torch.equal(e.dest, legacy(e)), key
+        before = pk.repacks
+        with torch.no_grad():
+            for p in net.parameters():
+                p.add_(0.01 * torch.randn_like(p))               # what an optimizer step does (bumps the version)
+        net(x).sum().backward()
+        assert pk.repacks == before + 1                          # ONE launch refreshed every tensor
+        for key, e in pk.tc.items():
+            assert torch.equal(e.dest, legacy(e)), key
+        # a write through .data is invisible to the version counter (ADVICE r1): stale until invalidate_packs()
+        first = next(iter(pk.tc.values()))
+        first.params[0].data.mul_(2.0)
+        net(x)
+        assert not torch.equal(first.dest, legacy(first))
+        net.invalidate_packs()
+        net(x)
+        assert torch.equal(first.dest, legacy(first))
+
+
+def test_gradients_are_bucket_views_and_accumulate_in_place():
+    """Every parameter gradient of a network is a view of ONE flat buffer (what the data-parallel all-reduce sends); a
+    network used twice in one backward pass adds in place and still matches two separate passes."""
+    from oracle import srcgan_oracle as O
+    from srcgan_b200 import nn as snn
+    net = snn.NLayerDiscriminator(3, 64, 2)
+    net.load_state_dict(O.init_discriminator(13))
+    net.to(DEV)
+    a, b = rand((2, 3, 64, 64), 1).to(DEV), rand((2, 3, 64, 64), 2).to(DEV)
+    (net(a).square().mean() + net(b).square().mean()).backward()          # backward_D_basic's shape: real + fake
+    bucket = net.grad_bucket()
+    assert all(bucket.holds(p) for p in net.parameters())
+    flat = bucket.flat
+    assert flat.numel() >= sum(p.numel() for p in net.parameters())
+    got = {k: p.grad.detach().clone() for k, p in net.named_parameters()}
+    net.load_state_dict(O.init_discriminator(13))                          # reset the BN buffers
+    for p in net.parameters():
+        p.grad = None
+    net(a).square().mean().backward()
+    ga = {k: p.grad.detach().clone() for k, p in net.named_parameters()}
+    for p in net.parameters():
+        p.grad = None
+    net(b).square().mean().backward()
+    for k, p in net.named_parameters():
+        assert l2err(got[k], ga[k] + p.grad) < 1e-5, k
