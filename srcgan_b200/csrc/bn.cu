@@ -43,24 +43,46 @@ __global__ void bn_stats_partial(const T* __restrict__ x, int ld, int64_t npix, 
   }
 }
 
-// block = 32 channels x 8 row lanes: each lane sums every 8th partial row in double, lanes are added in a fixed order
-__global__ void __launch_bounds__(256)
+// Fixed-order sum of `parts` partial rows for 32 channels by one block of 32 channels x 32 row lanes: lane rl adds rows
+// rl, rl + 32, ... in double (the loads of a lane are independent and issued four at a time - the old 8-lane version was a
+// serial chain of 74 dependent load+add steps and took 43 us, as long as the statistics pass itself at batch 16), then the
+// 32 lane sums are added in lane order.  Result in s / q of the threads with rl == 0.
+__device__ __forceinline__ void bn_reduce_parts(const float* __restrict__ a, const float* __restrict__ b, int parts, int c,
+                                                int ch, int rl, int cl, double (&rs)[32][33], double (&rq)[32][33],
+                                                double& s, double& q) {
+  s = 0.0; q = 0.0;
+  if (ch < c) {
+    int k = rl;
+    for (; k + 96 < parts; k += 128) {
+      const float a0 = __ldg(a + (int64_t)k * c + ch), a1 = __ldg(a + (int64_t)(k + 32) * c + ch),
+                  a2 = __ldg(a + (int64_t)(k + 64) * c + ch), a3 = __ldg(a + (int64_t)(k + 96) * c + ch);
+      const float b0 = __ldg(b + (int64_t)k * c + ch), b1 = __ldg(b + (int64_t)(k + 32) * c + ch),
+                  b2 = __ldg(b + (int64_t)(k + 64) * c + ch), b3 = __ldg(b + (int64_t)(k + 96) * c + ch);
+      s += (double)a0; s += (double)a1; s += (double)a2; s += (double)a3;
+      q += (double)b0; q += (double)b1; q += (double)b2; q += (double)b3;
+    }
+    for (; k < parts; k += 32) { s += (double)__ldg(a + (int64_t)k * c + ch); q += (double)__ldg(b + (int64_t)k * c + ch); }
+  }
+  rs[rl][cl] = s; rq[rl][cl] = q;
+  __syncthreads();
+  if (rl == 0) {
+    s = 0.0; q = 0.0;
+#pragma unroll 8
+    for (int r = 0; r < 32; ++r) { s += rs[r][cl]; q += rq[r][cl]; }
+  }
+}
+
+__global__ void __launch_bounds__(1024)
 bn_finalize(const float* __restrict__ psum, const float* __restrict__ psq, int parts, int c,
             int64_t npix, float eps, float momentum, float* __restrict__ running_mean,
             float* __restrict__ running_var, float* __restrict__ save_mean,
             float* __restrict__ save_invstd) {
-  __shared__ double rs[8][33], rq[8][33];
+  __shared__ double rs[32][33], rq[32][33];
   const int cl = threadIdx.x & 31, rl = threadIdx.x >> 5;
   const int ch = blockIdx.x * 32 + cl;
-  double s = 0.0, q = 0.0;
-  if (ch < c)
-    for (int k = rl; k < parts; k += 8) { s += (double)psum[(int64_t)k * c + ch]; q += (double)psq[(int64_t)k * c + ch]; }
-  rs[rl][cl] = s; rq[rl][cl] = q;
-  __syncthreads();
+  double s, q;
+  bn_reduce_parts(psum, psq, parts, c, ch, rl, cl, rs, rq, s, q);
   if (rl != 0 || ch >= c) return;
-  s = 0.0; q = 0.0;
-#pragma unroll
-  for (int r = 0; r < 8; ++r) { s += rs[r][cl]; q += rq[r][cl]; }
   double mean = s / (double)npix;
   double var = q / (double)npix - mean * mean;
   if (var < 0.0) var = 0.0;
@@ -323,22 +345,16 @@ __global__ void bn_bwd_partial(const T* __restrict__ dy, int dy_ld, const T* __r
   }
 }
 
-__global__ void __launch_bounds__(256)
+__global__ void __launch_bounds__(1024)
 bn_bwd_finalize(const float* __restrict__ p0, const float* __restrict__ p1, int parts, int c,
                 float* __restrict__ tot, float* __restrict__ dgamma, float* __restrict__ dbeta,
                 int accumulate) {
-  __shared__ double rs[8][33], rq[8][33];
+  __shared__ double rs[32][33], rq[32][33];
   const int cl = threadIdx.x & 31, rl = threadIdx.x >> 5;
   const int ch = blockIdx.x * 32 + cl;
-  double s = 0.0, q = 0.0;
-  if (ch < c)
-    for (int k = rl; k < parts; k += 8) { s += (double)p0[(int64_t)k * c + ch]; q += (double)p1[(int64_t)k * c + ch]; }
-  rs[rl][cl] = s; rq[rl][cl] = q;
-  __syncthreads();
+  double s, q;
+  bn_reduce_parts(p0, p1, parts, c, ch, rl, cl, rs, rq, s, q);
   if (rl != 0 || ch >= c) return;
-  s = 0.0; q = 0.0;
-#pragma unroll
-  for (int r = 0; r < 8; ++r) { s += rs[r][cl]; q += rq[r][cl]; }
   tot[ch] = (float)s; tot[c + ch] = (float)q;
   if (dbeta) dbeta[ch] = accumulate ? dbeta[ch] + (float)s : (float)s;
   if (dgamma) dgamma[ch] = accumulate ? dgamma[ch] + (float)q : (float)q;
@@ -391,7 +407,7 @@ static int bn_forward_t(const T* x, int x_ld, T* y, int y_ld, int64_t npix, int 
                                                    npix, c, nullptr, nullptr, 0.f, psum, psq);
     else
       bn_stats_partial<T><<<grid, blk, 0, st>>>(x, x_ld, npix, c, psum, psq);
-    bn_finalize<<<ceil_div(c, 32), 256, 0, st>>>(psum, psq, parts, c, npix, eps, momentum, rm, rv, save_mean,
+    bn_finalize<<<ceil_div(c, 32), 1024, 0, st>>>(psum, psq, parts, c, npix, eps, momentum, rm, rv, save_mean,
                                                   save_invstd);
     count_launch(2);
   } else {
@@ -440,7 +456,7 @@ static int bn_backward_t(const T* dy, int dy_ld, const T* y, int y_ld, const T* 
                                                 slope, p0, p1);
   else
     bn_bwd_partial<T><<<grid, blk, 0, st>>>(dy, dy_ld, y, y_ld, x, x_ld, npix, c, mean, invstd, slope, p0, p1);
-  bn_bwd_finalize<<<ceil_div(c, 32), 256, 0, st>>>(p0, p1, parts, c, tot, dgamma, dbeta, accumulate);
+  bn_bwd_finalize<<<ceil_div(c, 32), 1024, 0, st>>>(p0, p1, parts, c, tot, dgamma, dbeta, accumulate);
   if (sizeof(T) == 2 && c % 8 == 0 && c <= 2048 && dy_ld % 8 == 0 && y_ld % 8 == 0 && x_ld % 8 == 0 && dx_ld % 8 == 0 &&
       ((uintptr_t)dy) % 16 == 0 && ((uintptr_t)y) % 16 == 0 && ((uintptr_t)x) % 16 == 0 && ((uintptr_t)dx) % 16 == 0)
     bn_bwd_apply_vec<<<bn_stream_blocks(npix, c), 256, 0, st>>>(

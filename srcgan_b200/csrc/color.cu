@@ -92,7 +92,11 @@ __global__ void lab2rgb_u8_k(const float* __restrict__ lab, uint8_t* __restrict_
   int64_t n = i / hw, q = i - n * hw;
   const float* s = lab + n * 3 * hw + q;
   // float32 denormalisation, as the reference's in-place numpy arithmetic on the float32 array
-  double L = (double)(__ldg(s) * 100.f), A = (double)(__ldg(s + hw) * 255.f - 128.f), B = (double)(__ldg(s + 2 * hw) * 255.f - 128.f);
+  // (two roundings each, like numpy: an FMA contraction of x * 255 - 128 changes the last bit and, through the truncation
+  //  below, one uint8 value in five)
+  const double L = (double)__fmul_rn(__ldg(s), 100.f);
+  const double A = (double)__fsub_rn(__fmul_rn(__ldg(s + hw), 255.f), 128.f);
+  const double B = (double)__fsub_rn(__fmul_rn(__ldg(s + 2 * hw), 255.f), 128.f);
   double fy = (L + 16.0) / 116.0, fx = A / 500.0 + fy, fz = fmax(fy - B / 200.0, 0.0);
   double X = lab_finv64(fx) * 0.95047, Y = lab_finv64(fy), Z = lab_finv64(fz) * 1.08883;
   uint8_t* d = rgb + i * 3;

@@ -54,28 +54,25 @@ def test_full_size_step_matches_the_oracle(oracle_step, precision):
     finally:
         snn.set_precision(old)
     bf = precision == "bf16"
-    report = {"precision": precision, "losses": {}, "psnr": {}, "grads": {}}
-    # 1. the nine losses
+    report = {"precision": precision, "losses": {}, "images": {}, "grads": {}}
+    snr = lambda a, b: float(20 * torch.log10(b.double().norm() / (a.double().cpu() - b.double()).norm().clamp_min(1e-300)))
+    # ---- measure everything first (the report is written even when an assertion below fails)
     for n, v in ref_losses.items():
-        report["losses"][n] = {"cuda": got[n], "oracle": v}
-        assert math.isclose(got[n], v, rel_tol=2e-2 if bf else 1e-3, abs_tol=2e-3 if bf else 1e-5), (n, got[n], v)
-    # 2. generated images: PSNR against the data within 0.05 dB of the oracle's (north_star's bf16 criterion), and the
-    #    image itself against the oracle's image
+        report["losses"][n] = {"cuda": got[n], "oracle": v, "rel": abs(got[n] - v) / max(abs(v), 1e-30)}
     for name, tgt in (("fake_B", real_B), ("fake_A", real_A), ("recl_B", real_B), ("recl_A", real_A)):
         a, b = getattr(m, name).detach(), getattr(ref, name).detach()
-        pa, pb, direct = psnr(a, tgt), psnr(b, tgt), psnr(a, b)
-        report["psnr"][name] = {"cuda_vs_data": pa, "oracle_vs_data": pb, "cuda_vs_oracle": direct}
-        assert abs(pa - pb) < 0.05, (name, pa, pb)
-        assert direct > (35.0 if bf else 90.0), (name, direct)
-    # 3. every parameter gradient
+        report["images"][name] = {"psnr_cuda_vs_data": psnr(a, tgt), "psnr_oracle_vs_data": psnr(b, tgt),
+                                  "snr_cuda_vs_oracle_db": snr(a, b)}
     worst_cos, worst_l2, frac_all, total = 1.0, 0.0, 0.0, 0
+    missing = []
     for net in ("G_A", "G_B", "D_A", "D_B"):
         named = dict(getattr(m, "net" + net).named_parameters())
         for k, p in getattr(ref, net).items():
             if O.is_buffer_key(k):
                 continue
-            if p.grad is None:
-                assert named[k].grad is None, (net, k)
+            if p.grad is None or named[k].grad is None:
+                if (p.grad is None) != (named[k].grad is None):
+                    missing.append("%s.%s" % (net, k))
                 continue
             g, r = named[k].grad.detach().double().cpu().flatten(), p.grad.detach().double().flatten()
             cos = float(torch.dot(g, r) / (g.norm() * r.norm()).clamp_min(1e-300))
@@ -85,18 +82,30 @@ def test_full_size_step_matches_the_oracle(oracle_step, precision):
             worst_cos, worst_l2 = min(worst_cos, cos), max(worst_l2, l2)
             frac_all += within * g.numel()
             total += g.numel()
-            if bf:
-                assert cos >= 0.999 and l2 <= 3e-2, (net, k, cos, l2)
-            else:
-                assert cos >= 0.99999, (net, k, cos, l2)
-    frac_all /= total
-    report["summary"] = {"worst_cos": worst_cos, "worst_l2": worst_l2, "frac_elements_within_1e-3_of_tensor_max": frac_all,
-                         "parameters": total}
+    frac_all /= max(total, 1)
+    l2s = sorted(v["l2"] for v in report["grads"].values())
+    report["summary"] = {"worst_cos": worst_cos, "worst_l2": worst_l2, "median_l2": l2s[len(l2s) // 2],
+                         "frac_elements_within_1e-3_of_tensor_max": frac_all, "parameters": total, "tensors": len(l2s),
+                         "worst_loss_rel": max(v["rel"] for v in report["losses"].values()),
+                         "min_image_snr_db": min(v["snr_cuda_vs_oracle_db"] for v in report["images"].values())}
     out_dir = os.path.join(ROOT, "gpurun_out")
     if os.path.isdir(out_dir):
         with open(os.path.join(out_dir, "fullsize_parity_%s.json" % precision), "w") as f:
             json.dump(report, f, indent=1)
     print(json.dumps(report["summary"]))
+    # ---- the bar
+    assert not missing, missing
+    for n, v in report["losses"].items():       # 1. the nine losses
+        assert math.isclose(v["cuda"], v["oracle"], rel_tol=2e-2 if bf else 1e-3, abs_tol=2e-3 if bf else 1e-5), (n, v)
+    for name, v in report["images"].items():    # 2. generated images: north_star's bf16 criterion (PSNR within 0.05 dB of the
+        #    fp32 result) and the image itself against the oracle's (random-init networks leave [0, 1]: relative, in dB)
+        assert abs(v["psnr_cuda_vs_data"] - v["psnr_oracle_vs_data"]) < 0.05, (name, v)
+        assert v["snr_cuda_vs_oracle_db"] > (30.0 if bf else 80.0), (name, v)
+    for k, v in report["grads"].items():        # 3. every parameter gradient
+        if bf:
+            assert v["cos"] >= 0.999 and v["l2"] <= 3e-2, (k, v)
+        else:
+            assert v["cos"] >= 0.99999, (k, v)
     if not bf:
         # north_star: fp32 gradients within 1e-3 relative error - counted element by element (a LeakyReLU / L1-sign kink
         # flipped by the summation order moves single elements, see tests/test_gpu_models.py)
