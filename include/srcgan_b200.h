@@ -101,6 +101,12 @@ typedef struct srcgan_conv_params {
        maskbits : IN,  replaces `mask`: value *= bit ? 1 : mask_slope  (4 bytes instead of 64 per pixel and 32 channels) */
   void* signbits;
   const void* maskbits;
+  /* "Tall image" batching of small maps (paired-sweep fprop kernel only): the caller stacks the images of a batch vertically
+     in ONE image of n*(h+1)+1 rows with an all-zero separator row above, between and below them (the shared zero padding),
+     so that 64x64 maps fill the 128-lane strips of the sweep kernel.  zero_row_period = h+1 makes the epilogue store zeros
+     in the separator rows (row % period == 0) so that they stay zero from layer to layer.  0 = off. */
+  int32_t zero_row_period;
+  int32_t reserved0;
 } srcgan_conv_params;
 
 const char* srcgan_version(void);

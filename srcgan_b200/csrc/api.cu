@@ -145,8 +145,8 @@ int srcgan_conv_fprop(const srcgan_conv_params* p, void* stream) {
     SRCGAN_REQUIRE(conv_tc_supported(p), "conv_fprop: shape not supported by the tcgen05 engine");
     return conv_fprop_tc(p, (cudaStream_t)stream);
   }
-  if (p->signbits || p->maskbits) {
-    set_error("conv_fprop: packed sign / mask bits are only implemented by the paired-sweep tcgen05 kernel");
+  if (p->signbits || p->maskbits || p->zero_row_period) {
+    set_error("conv_fprop: packed sign / mask bits and zero_row_period are only implemented by the paired-sweep tcgen05 kernel");
     return SRCGAN_E_INVALID;
   }
   return conv_fprop_simt(p, (cudaStream_t)stream);
@@ -155,8 +155,8 @@ int srcgan_conv_fprop(const srcgan_conv_params* p, void* stream) {
 int srcgan_conv_dgrad(const srcgan_conv_params* p, void* stream) {
   int rc = validate_conv(p, true);
   if (rc) return rc;
-  if (p->signbits || p->maskbits) {
-    set_error("conv_dgrad: packed sign / mask bits are only implemented by the paired-sweep fprop kernel");
+  if (p->signbits || p->maskbits || p->zero_row_period) {
+    set_error("conv_dgrad: packed sign / mask bits and zero_row_period are only implemented by the paired-sweep fprop kernel");
     return SRCGAN_E_INVALID;
   }
   if (p->engine == SRCGAN_ENGINE_TC) {

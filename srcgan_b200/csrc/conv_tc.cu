@@ -1109,6 +1109,7 @@ struct Sw2Args {
   const __nv_bfloat16* mask; int mask_ld; float mask_slope;
   uint32_t* signbits;                   // OUT [pixel][BN/32]: bit = stored value > 0 (the mask of the matching backward step)
   const uint32_t* maskbits;             // IN  [pixel][BN/32]: replaces `mask` (4 bytes instead of 64 per pixel and 32 channels)
+  int zero_period;                      // > 0: image rows with row % zero_period == 0 are stored as zeros ("tall image" separators)
   int dbg;
 };
 
@@ -1518,6 +1519,8 @@ conv3x3_sweep2_tc(const __grid_constant__ CUtensorMap tmap_x, const Sw2Args a) {
         const uint32_t spar = ppar ^ 1u;                               // lap r + 1 or r - 1
         const bool real = j >= 1 && j <= n_in - 2;
         const int x = x_start + j - 1;
+        // separator row of a tall image (the zero padding shared by two stacked images): stored as zeros
+        const bool zrow = a.zero_period > 0 && ((a.tr ? x : y) % a.zero_period) == 0;
         if (prof) { tc0 = clock64(); ++ncol; }
         // residual / mask operands of this pixel do not depend on the accumulator: request them before waiting for it
         // (issued behind the wait they cost one DRAM round trip per column and group - the dgrad launches all have a mask)
@@ -1589,7 +1592,7 @@ conv3x3_sweep2_tc(const __grid_constant__ CUtensorMap tmap_x, const Sw2Args a) {
               uint32_t sb32 = 0;
 #pragma unroll
               for (int i = 0; i < 32; ++i) sb32 |= (f[i] > 0.f ? 1u : 0u) << i;
-              a.signbits[pix * (BN / 32) + (cb >> 5)] = sb32;
+              a.signbits[pix * (BN / 32) + (cb >> 5)] = zrow ? 0u : sb32;
             }
             if (row_ok) {
               uint4 ov[4];
@@ -1616,6 +1619,7 @@ conv3x3_sweep2_tc(const __grid_constant__ CUtensorMap tmap_x, const Sw2Args a) {
                 __nv_bfloat162* oh = reinterpret_cast<__nv_bfloat162*>(&ov[gq]);
 #pragma unroll
                 for (int i = 0; i < 4; ++i) oh[i] = __floats2bfloat162_rn(f[gq * 8 + 2 * i], f[gq * 8 + 2 * i + 1]);
+                if (zrow) ov[gq] = make_uint4(0u, 0u, 0u, 0u);
               }
               __nv_bfloat16* dst = a.y + pix * a.y_ld + cb;            // this pixel's 32 channels: 64 contiguous bytes
               if (wide_st) {
@@ -2148,6 +2152,7 @@ static int conv_fprop_sweep2(const srcgan_conv_params* p, int cg, cudaStream_t s
   SRCGAN_REQUIRE(!((p->signbits || p->maskbits) && (p->r1 || p->r2 || p->mask)),
                  "conv_fprop_tc: packed sign / mask bits cannot be combined with residual or bf16 mask operands");
   a.signbits = (uint32_t*)p->signbits; a.maskbits = (const uint32_t*)p->maskbits;
+  a.zero_period = p->zero_row_period;
   { const char* d = getenv("SRCGAN_B200_DBG"); a.dbg = d ? atoi(d) : 0; }
   { const char* d = getenv("SRCGAN_B200_PFD"); a.pfd = d ? atoi(d) : 0; }
   if (cg == 2) return p->cout == 64 ? tc::launch_sweep2<64, 2>(tx, a, st) : tc::launch_sweep2<32, 2>(tx, a, st);
@@ -2158,6 +2163,8 @@ int conv_fprop_tc(const srcgan_conv_params* p, cudaStream_t st) {
   if (const int cg = sweep2_cg(p)) return conv_fprop_sweep2(p, cg, st);
   SRCGAN_REQUIRE(!p->signbits && !p->maskbits,
                  "conv_fprop_tc: packed sign / mask bits need the paired-sweep kernel (3x3 s1 p1, cout 32/64, map >= 96)");
+  SRCGAN_REQUIRE(p->zero_row_period == 0,
+                 "conv_fprop_tc: zero_row_period (tall-image separators) needs the paired-sweep kernel (3x3 s1 p1, cout 32/64)");
   if (const int v = kws_variant(p)) return conv_fprop_kws(p, v, st);
   tc::HostPlan hp = tc::fprop_plan(p->kh, p->stride, p->pad);
   const bool halo = p->kh == 3 && p->stride == 1 && (p->cout <= 16 || p->cout == 32 || p->cout == 64);

@@ -88,6 +88,43 @@ __global__ void upsample2x_adjoint_k(const T* __restrict__ src, int src_ld, T* _
   dst[p * dst_ld + ch] = from_f32<T>(v);
 }
 
+// bf16, 16-byte vectors (8 channels per thread): the four source pixels are summed in fp32 in the scalar kernel's order
+__global__ void __launch_bounds__(256)
+upsample2x_adjoint_vec_bf16(const uint4* __restrict__ src, int src_ld16, uint4* __restrict__ dst, int dst_ld16,
+                            const uint4* __restrict__ mask, int mask_ld16, float mslope, int n, int h, int w, int c16) {
+  const int64_t total = (int64_t)n * h * w * c16;
+  const int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= total) return;
+  const int v = (int)(i % c16);
+  const int64_t p = i / c16;
+  const int x = (int)(p % w);
+  const int64_t t = p / w;
+  const int y = (int)(t % h);
+  const int64_t b = t / h;
+  const int W2 = 2 * w;
+  const int64_t s00 = ((b * 2 * h + 2 * y) * W2 + 2 * x) * src_ld16 + v;
+  const uint4 q0 = __ldg(src + s00), q1 = __ldg(src + s00 + src_ld16), q2 = __ldg(src + s00 + (int64_t)W2 * src_ld16),
+              q3 = __ldg(src + s00 + (int64_t)(W2 + 1) * src_ld16);
+  uint4 qm = make_uint4(0, 0, 0, 0);
+  if (mask) qm = __ldg(mask + p * mask_ld16 + v);
+  const __nv_bfloat162 *a0 = reinterpret_cast<const __nv_bfloat162*>(&q0), *a1 = reinterpret_cast<const __nv_bfloat162*>(&q1),
+                       *a2 = reinterpret_cast<const __nv_bfloat162*>(&q2), *a3 = reinterpret_cast<const __nv_bfloat162*>(&q3),
+                       *am = reinterpret_cast<const __nv_bfloat162*>(&qm);
+  uint4 o;
+  __nv_bfloat162* oh = reinterpret_cast<__nv_bfloat162*>(&o);
+#pragma unroll
+  for (int k = 0; k < 4; ++k) {
+    float lo = __low2float(a0[k]) + __low2float(a1[k]) + __low2float(a2[k]) + __low2float(a3[k]);
+    float hi = __high2float(a0[k]) + __high2float(a1[k]) + __high2float(a2[k]) + __high2float(a3[k]);
+    if (mask) {
+      lo *= __low2float(am[k]) > 0.f ? 1.f : mslope;
+      hi *= __high2float(am[k]) > 0.f ? 1.f : mslope;
+    }
+    oh[k] = __floats2bfloat162_rn(lo, hi);
+  }
+  dst[p * dst_ld16 + v] = o;
+}
+
 // nearest x2 upsampling, 16-byte vectors: dst[n,2y+a,2x+b,:] = src[n,y,x,:]
 __global__ void upsample2x_vec(const uint4* __restrict__ src, int src_ld16, uint4* __restrict__ dst, int dst_ld16, int n,
                                int h, int w, int c16) {
@@ -325,6 +362,13 @@ int nhwc_to_nchw(const void* src, int ld, int dtype, float* dst, int n, int c, i
 int upsample2x_adjoint(const void* src, int src_ld, void* dst, int dst_ld, const void* mask, int mask_ld,
                        float mslope, int n, int h, int w, int c, int dtype, cudaStream_t st) {
   int64_t total = (int64_t)n * h * w * c;
+  auto al16 = [](const void* ptr, int ld) { return ptr == nullptr || (((uintptr_t)ptr) % 16 == 0 && ld % 8 == 0); };
+  if (dtype == SRCGAN_DT_BF16 && c % 8 == 0 && al16(src, src_ld) && al16(dst, dst_ld) && al16(mask, mask_ld)) {
+    upsample2x_adjoint_vec_bf16<<<ceil_div(total / 8, 256), 256, 0, st>>>((const uint4*)src, src_ld / 8, (uint4*)dst, dst_ld / 8,
+                                                                          (const uint4*)mask, mask_ld / 8, mslope, n, h, w, c / 8);
+    count_launch();
+    return check_launch("upsample2x_adjoint");
+  }
   if (dtype == SRCGAN_DT_F32)
     upsample2x_adjoint_k<float><<<ceil_div(total, 256), 256, 0, st>>>((const float*)src, src_ld, (float*)dst, dst_ld,
                                                                      (const float*)mask, mask_ld, mslope, n, h, w, c);

@@ -549,13 +549,14 @@ class _RRDBGenerator(_NetBase):
 
     # ---- a chain of dense blocks (groups of three form an RRDB) over concat buffers --------------------
     def _chain_forward(self, rdbs: List[ResidualDenseBlock_5], bufs: List[torch.Tensor], out: Slice,
-                       bits: Optional[list] = None) -> None:
+                       bits: Optional[list] = None, zr: int = 0) -> None:
         """bufs[0][..., :nf] already holds the chain input; the chain output is written to ``out``.
         ``bits`` (a list, filled here): per dense block the packed sign masks of x1..x4 (int32 (n,h,w,1), 4 bytes per pixel)
         when the layer runs on the paired-sweep kernel - the backward steps then read those instead of the 64-byte
         activation slices (dgrad of the gc = 32 layers is HBM-bound: 13-23 % fewer bytes)."""
         nf, gc = self.nf, self.gc
         n, h, w, dt, dev = bufs[0].shape[0], bufs[0].shape[1], bufs[0].shape[2], bufs[0].dtype, bufs[0].device
+        zkw = {"zero_rows": zr} if zr else {}          # tall-image mode: separator rows are stored as zeros (see _tall_plan)
         for j, rdb in enumerate(rdbs):
             C = bufs[j]
             convs = rdb.convs()
@@ -566,23 +567,24 @@ class _RRDBGenerator(_NetBase):
                     sb = torch.empty((n, h, w, 1), dtype=torch.int32, device=dev)
                 row.append(sb)
                 self._fprop(convs[k - 1], Slice(C, 0, nf + gc * (k - 1)), Slice(C, nf + gc * (k - 1), gc), act=LRELU,
-                            **({"signbits": sb} if sb is not None else {}))
+                            **({"signbits": sb} if sb is not None else {}), **zkw)
             if bits is not None:
                 bits.append(row)
             dest = Slice(bufs[j + 1], 0, nf) if j + 1 < len(rdbs) else out
             if j % 3 != 2:      # x5*0.2 + x                                    (model.py:211)
-                self._fprop(convs[4], Slice(C), dest, alpha=0.2, r1=Slice(C, 0, nf), beta1=1.0)
+                self._fprop(convs[4], Slice(C), dest, alpha=0.2, r1=Slice(C, 0, nf), beta1=1.0, **zkw)
             else:               # RDB3: (x5*0.2 + x)*0.2 + rrdb_in              (model.py:211,233)
                 self._fprop(convs[4], Slice(C), dest, alpha=0.04, r1=Slice(C, 0, nf), beta1=0.2,
-                            r2=Slice(bufs[j - 2], 0, nf), beta2=1.0)
+                            r2=Slice(bufs[j - 2], 0, nf), beta2=1.0, **zkw)
 
     def _chain_backward(self, rdbs, bufs, Dbuf: List[torch.Tensor], dest: Slice, sink: "_GradSink", W,
-                        bits: Optional[list] = None) -> None:
+                        bits: Optional[list] = None, zr: int = 0) -> None:
         """Dbuf[(len-1) % 4][..., :nf] already holds the gradient w.r.t. the chain output; the gradient
         w.r.t. the chain input (through the chain) is written to ``dest``.  Mirrored dense blocks."""
         nf, gc = self.nf, self.gc
         ctot = nf + 4 * gc
         h, w, dt, dev = bufs[0].shape[1], bufs[0].shape[2], bufs[0].dtype, bufs[0].device
+        zkw = {"zero_rows": zr} if zr else {}
         for j in range(len(rdbs) - 1, -1, -1):
             rdb, C, D = rdbs[j], bufs[j], Dbuf[j % 4]
             convs = rdb.convs()
@@ -596,16 +598,16 @@ class _RRDBGenerator(_NetBase):
                     mb = None
                 if mb is not None:
                     ops.conv_fprop(Slice(D, 0, cin_v), self._dense_wT(rdb, k, s5, dt, layout), None,
-                                   Slice(D, nf + gc * (4 - k), gc), 3, 1, 1, maskbits=mb, mask_slope=LRELU, engine=eng)
+                                   Slice(D, nf + gc * (4 - k), gc), 3, 1, 1, maskbits=mb, mask_slope=LRELU, engine=eng, **zkw)
                 else:
                     ops.conv_fprop(Slice(D, 0, cin_v), self._dense_wT(rdb, k, s5, dt, layout), None,
                                    Slice(D, nf + gc * (4 - k), gc), 3, 1, 1,
-                                   mask=Slice(C, nf + gc * (k - 1), gc), mask_slope=LRELU, engine=eng)
+                                   mask=Slice(C, nf + gc * (k - 1), gc), mask_slope=LRELU, engine=eng, **zkw)
             dst = Slice(Dbuf[(j - 1) % 4], 0, nf) if j > 0 else dest
             eng, layout = select_engine(ctot, nf, 3, 1, False, dt, h, w)
             ops.conv_fprop(Slice(D), self._dense_wT(rdb, 0, s5, dt, layout), None, dst, 3, 1, 1,
                            r1=Slice(D, 0, nf), beta1=(0.2 if is_rdb3 else 1.0),
-                           r2=(Slice(Dbuf[(j + 2) % 4], 0, nf) if is_rdb1 else None), beta2=1.0, engine=eng)
+                           r2=(Slice(Dbuf[(j + 2) % 4], 0, nf) if is_rdb1 else None), beta2=1.0, engine=eng, **zkw)
             # bias gradients: the kw-stacked tcgen05 wgrad kernel sums dY out of the slabs it has in shared memory anyway
             # (csrc/conv_tc.cu, tcw4); other engines take one fused column-sum pass over the gradient concat buffer
             from . import engine as _engine
@@ -626,20 +628,63 @@ class _RRDBGenerator(_NetBase):
                     if W(convs[k - 1].bias):
                         sink.put(convs[k - 1].bias, flat[nf + gc * (4 - k): nf + gc * (5 - k)])
 
+    # ---- "tall image" batching of small maps ---------------------------------------------------------------------------
+    # The paired-sweep kernel needs 128 lanes along one image dimension; the G_A trunk runs at 64x64 (BASELINE configs[1]) where
+    # only the 4x32-pixel-tile kernels apply (0.23 of the tensor peak).  A batch of n small maps is therefore stacked
+    # vertically into ONE image of n*(h+1)+1 rows with an all-zero separator row above, between and below the images: the
+    # separator IS the zero padding both neighbours need, so a 3x3 convolution over the tall image equals the per-image
+    # convolution as long as every layer writes zeros into the separator rows (conv epilogue option zero_rows = h+1).
+    # Weight gradients need nothing: the separators are zero in X and in dY.
+    def _tall_plan(self, n: int, h: int, w: int, cin_first: int, dt) -> int:
+        """-> separator period (h + 1) if the trunk of this call runs in tall-image mode, else 0"""
+        if dt != torch.bfloat16 or max(h, w) >= 96 or os.environ.get("SRCGAN_B200_NO_TALL"):
+            return 0
+        rows = n * (h + 1) + 1
+        if rows < 128:
+            return 0
+        nf, gc = self.nf, self.gc
+        shapes = [(cin_first, nf), (nf, nf), (nf + 4 * gc, nf)] + [(nf + gc * k, gc) for k in range(4)]
+        eng = _engine_mod()
+        ok = all(eng.sweep_bits_supported(ci, co, 3, 1, 1, dt, rows, w) for ci, co in shapes)
+        ok = ok and all(eng.sweep_bits_supported(ci, co, 3, 1, 1, dt, rows, w) for ci, co in
+                        [(nf + gc * k, gc) for k in range(4)] + [(nf + 4 * gc, nf)])           # the mirrored backward steps
+        return h + 1 if ok else 0
+
+    @staticmethod
+    def _to_tall(src: torch.Tensor, period: int) -> torch.Tensor:
+        """(n, h, w, c) -> (1, n*(h+1)+1, w, c) with zero separator rows"""
+        n, h, w, c = src.shape
+        tall = torch.zeros((1, n * period + 1, w, c), dtype=src.dtype, device=src.device)
+        tall[0, 1:].view(n, period, w, c)[:, :h].copy_(src)
+        return tall
+
+    @staticmethod
+    def _from_tall(tall: torch.Tensor, n: int, h: int) -> torch.Tensor:
+        _one, rows, w, c = tall.shape
+        return tall[0, 1:].view(n, h + 1, w, c)[:, :h].contiguous()
+
     def _trunk_forward(self, x_in: Slice, st: dict) -> Slice:
         """conv_first -> nb x RRDB -> trunk_conv (+fea).  Returns fea2; saves buffers in ``st``."""
         nf, gc = self.nf, self.gc
         ctot = nf + 4 * gc
-        n, h, w, dev, dt = x_in.n, x_in.h, x_in.w, x_in.buf.device, x_in.dtype
+        n0, h0, w0 = x_in.n, x_in.h, x_in.w
+        dev, dt = x_in.buf.device, x_in.dtype
+        zr = self._tall_plan(n0, h0, w0, x_in.c, dt)
+        if zr:
+            x_in = Slice(self._to_tall(x_in.buf, zr), x_in.c0, x_in.c)
+        zkw = {"zero_rows": zr} if zr else {}
+        n, h, w = x_in.n, x_in.h, x_in.w
         rdbs = self._rdbs()
         bufs = [ops.new_buf(n, h, w, ctot, dt, dev) for _ in rdbs]
         trunk_out = ops.new_buf(n, h, w, nf, dt, dev)
         fea2 = ops.new_buf(n, h, w, nf, dt, dev)
-        self._fprop(self.conv_first, x_in, Slice(bufs[0], 0, nf))
+        self._fprop(self.conv_first, x_in, Slice(bufs[0], 0, nf), **zkw)
         st["bits"] = []
-        self._chain_forward(rdbs, bufs, Slice(trunk_out), st["bits"])
-        self._fprop(self.trunk_conv, Slice(trunk_out), Slice(fea2), r1=Slice(bufs[0], 0, nf), beta1=1.0)
-        st["x_in"], st["bufs"], st["trunk_out"], st["fea2"] = x_in, bufs, trunk_out, fea2
+        self._chain_forward(rdbs, bufs, Slice(trunk_out), st["bits"], zr)
+        self._fprop(self.trunk_conv, Slice(trunk_out), Slice(fea2), r1=Slice(bufs[0], 0, nf), beta1=1.0, **zkw)
+        st["x_in"], st["bufs"], st["trunk_out"], st["fea2"], st["tall"] = x_in, bufs, trunk_out, fea2, (zr, n0, h0)
+        if zr:
+            return Slice(self._from_tall(fea2, n0, h0))
         return Slice(fea2)
 
     def _trunk_backward(self, st: dict, g_fea2: Slice, sink: _GradSink, want: dict, need_dx: bool) -> Optional[Slice]:
@@ -647,15 +692,19 @@ class _RRDBGenerator(_NetBase):
         nf, gc = self.nf, self.gc
         ctot = nf + 4 * gc
         bufs, trunk_out, x_in = st["bufs"], st["trunk_out"], st["x_in"]
+        zr, n0, h0 = st.get("tall", (0, 0, 0))
+        zkw = {"zero_rows": zr} if zr else {}
+        if zr:
+            g_fea2 = Slice(self._to_tall(g_fea2.view().contiguous() if g_fea2.c != g_fea2.ld else g_fea2.buf, zr))
         n, h, w, dev, dt = x_in.n, x_in.h, x_in.w, x_in.buf.device, x_in.dtype
         rdbs = self._rdbs()
         W = lambda p: p is not None and want.get(id(p), False)
         Dbuf = [ops.new_buf(n, h, w, ctot, dt, dev) for _ in range(4)]
         last = len(rdbs) - 1
         self._wgrad(self.trunk_conv, Slice(trunk_out), g_fea2, sink, W(self.trunk_conv.weight), W(self.trunk_conv.bias))
-        self._dgrad(self.trunk_conv, g_fea2, Slice(Dbuf[last % 4], 0, nf))
+        self._dgrad(self.trunk_conv, g_fea2, Slice(Dbuf[last % 4], 0, nf), **zkw)
         dfea_trunk = ops.new_buf(n, h, w, nf, dt, dev)
-        self._chain_backward(rdbs, bufs, Dbuf, Slice(dfea_trunk), sink, W, st.get("bits"))
+        self._chain_backward(rdbs, bufs, Dbuf, Slice(dfea_trunk), sink, W, st.get("bits"), zr)
         # fea feeds both the trunk and the skip (model.py:421)
         d_fea = ops.new_buf(n, h, w, nf, dt, dev)
         ops.add(Slice(dfea_trunk), g_fea2, Slice(d_fea))
@@ -663,7 +712,9 @@ class _RRDBGenerator(_NetBase):
         if not need_dx:
             return None
         dx = _io_buf(n, h, w, x_in.c, dt, dev)
-        self._dgrad(self.conv_first, Slice(d_fea), dx)
+        self._dgrad(self.conv_first, Slice(d_fea), dx)          # (the separator rows of dx are never read)
+        if zr:
+            return Slice(self._from_tall(dx.buf, n0, h0), dx.c0, dx.c)
         return dx
 
 

@@ -212,9 +212,10 @@ def conv_fprop(x: Slice, wgt: torch.Tensor, bias: Optional[torch.Tensor], y: Sli
                pad: int = 1, *, upsample: bool = False, act: Optional[float] = None, alpha: float = 1.0,
                r1: Optional[Slice] = None, beta1: float = 0.0, r2: Optional[Slice] = None, beta2: float = 0.0,
                mask: Optional[Slice] = None, mask_slope: float = 0.0, engine: int = ENGINE_SIMT,
-               signbits: Optional[torch.Tensor] = None, maskbits: Optional[torch.Tensor] = None) -> None:
+               signbits: Optional[torch.Tensor] = None, maskbits: Optional[torch.Tensor] = None, zero_rows: int = 0) -> None:
     """y = epilogue(conv(x, w)); see include/srcgan_b200.h for the epilogue definition.
-    ``signbits`` (out) / ``maskbits`` (in): packed LeakyReLU masks, int32 (n, h, w, cout/32) - paired-sweep kernel only."""
+    ``signbits`` (out) / ``maskbits`` (in): packed LeakyReLU masks, int32 (n, h, w, cout/32) - paired-sweep kernel only.
+    ``zero_rows``: separator period of a tall image (rows % zero_rows == 0 are stored as zeros) - paired-sweep kernel only."""
     _require_cuda(x.buf, "conv input")
     p = _conv_params(x.n, x.h, x.w, x.c, y.c, k, stride, pad, upsample, y.h, y.w, x.dtype, engine)
     p.x, p.x_ld, p.wgt, p.y, p.y_ld = x.ptr, x.ld, wgt.data_ptr(), y.ptr, y.ld
@@ -225,6 +226,7 @@ def conv_fprop(x: Slice, wgt: torch.Tensor, bias: Optional[torch.Tensor], y: Sli
             setattr(p, name, t.data_ptr())
     if maskbits is not None:
         p.mask_slope = float(mask_slope)
+    p.zero_row_period = int(zero_rows)
     with _Timed("fprop", p):
         _lib.check(_lib.load().srcgan_conv_fprop(C.byref(p), _stream()), "conv_fprop")
 

@@ -123,6 +123,21 @@ def test_layout_roundtrip_and_adjoint(c):
     d = ops.Slice(torch.zeros((2, 10, 12, c), device=DEV))
     ops.upsample2x_adjoint(to_nhwc(g, torch.float32), d)
     assert relerr(from_nhwc(d), ref) < 1e-6
+    if c % 8 == 0:      # the vectorised bf16 kernel (with and without the LeakyReLU mask), channel slices of wider buffers
+        gb = g.to(torch.bfloat16).float()
+        mk = rand((2, c, 10, 12), 3) - 0.5
+        src = ops.Slice(torch.zeros((2, 20, 24, c + 8), dtype=torch.bfloat16, device=DEV), 8, c)
+        src.view().copy_(gb.permute(0, 2, 3, 1).to(DEV))
+        msk = ops.Slice(mk.permute(0, 2, 3, 1).contiguous().to(DEV).to(torch.bfloat16))
+        for m in (None, msk):
+            db = ops.Slice(torch.zeros((2, 10, 12, 2 * c), dtype=torch.bfloat16, device=DEV), c, c)
+            ops.upsample2x_adjoint(src, db, m, 0.2)
+            want = F.avg_pool2d(gb, 2) * 4
+            if m is not None:
+                want = want * torch.where(mk.to(torch.bfloat16).float() > 0, torch.ones_like(mk), torch.full_like(mk, 0.2))
+            got = db.view().float().permute(0, 3, 1, 2).cpu()
+            assert relerr(got, want) < 1e-2 and torch.equal(got, want.to(torch.bfloat16).float())
+            assert float(db.buf[..., :c].abs().max()) == 0.0           # the neighbouring slice is untouched
 
 
 @pytest.mark.parametrize("training", [True, False])
