@@ -44,6 +44,7 @@ def parse():
     ap.add_argument("--workload", default="gd", choices=["gd", "cascade", "cascade_lab", "eval"],
                     help="gd = BASELINE configs[1] (default, the driver's line); cascade / cascade_lab / eval = configs[2..4]")
     ap.add_argument("--batch", type=int, default=None, help="units per GPU per step (default: 64 patches; eval: 16 tiles)")
+    ap.add_argument("--tile-batch", type=int, default=8, help="eval workload: tiles per generator forward (1 = the reference's loop)")
     ap.add_argument("--no-overlap", action="store_true", help="N>1: flat all-reduce in the step pre-hook instead of the bucket reducer")
     ap.add_argument("--lr-size", type=int, default=64, help="LR patch edge (HR = 4x)")
     ap.add_argument("--precision", default="bf16", choices=["bf16", "fp32"])
@@ -512,22 +513,26 @@ def wl_eval(args, dev, rank):
     hr = [t.to(dev) for t in host_hr]
     lr = [F.interpolate(t, scale_factor=0.25, mode="nearest") for t in hr]
 
+    lr_all, hr_all = torch.cat(lr), torch.cat(hr)
+    tb = args.tile_batch
+
     def step_resident():
         with torch.no_grad():
-            for l, h in zip(lr, hr):
-                evaluate.metrics_on_device(net(l), h)
+            for i in range(0, B, tb):
+                evaluate.per_image_metrics(net(lr_all[i:i + tb]), hr_all[i:i + tb])
 
     def step_e2e():
         pairs = []
         for t in host_hr:
             h = t.to(dev, non_blocking=True)
             pairs.append((F.interpolate(h, scale_factor=0.25, mode="nearest"), h))
-        rows, _mean = evaluate.evaluate(net, pairs)                    # ONE device -> host copy for the whole sweep
+        rows, _mean = evaluate.evaluate(net, pairs, batch=tb)          # ONE device -> host copy for the whole sweep
         return 16 * len(rows)
 
     cpu = lambda batch: cpu_eval()
 
-    return dict(name="eval sweep: RDDBNetB x4 inference on 128x128 -> 512x512 tiles + fused MSE/PSNR/AE/SSIM, %d tiles per step per GPU" % B,
+    return dict(name="eval sweep: RDDBNetB x4 inference on 128x128 -> 512x512 tiles + fused MSE/PSNR/AE/SSIM, %d tiles per step per GPU, "
+                     "%d tiles per forward (every tile scored on its own)" % (B, tb),
                 metric="eval sweep tiles/sec (512x512, x4)", unit="tiles/s", units=B, step_resident=step_resident,
                 step_e2e=step_e2e, h2d=B * 3 * 512 * 512 * 4, gflop=62.904 * 4.0, cpu=cpu, nets=[], opts=[])
 

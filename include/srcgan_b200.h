@@ -106,8 +106,13 @@ typedef struct srcgan_conv_params {
      so that 64x64 maps fill the 128-lane strips of the sweep kernel.  zero_row_period = h+1 makes the epilogue store zeros
      in the separator rows (row % period == 0) so that they stay zero from layer to layer.  0 = off. */
   int32_t zero_row_period;
-  int32_t reserved0;
+  /* SRCGAN_CONV_FLAG_* bits.  REVERSE (paired-sweep fprop kernel; ignored elsewhere): process the work units from the last
+     image to the first.  Alternating it between the consecutive layers of a dense block lets each layer start on the
+     data the previous one touched last, i.e. on what the 126 MB L2 still holds.  Results do not depend on it beyond the
+     fp32 summation order of a few columns (each setting is bit-reproducible). */
+  int32_t flags;
 } srcgan_conv_params;
+#define SRCGAN_CONV_FLAG_REVERSE 1
 
 const char* srcgan_version(void);
 const char* srcgan_last_error(void);
@@ -235,8 +240,9 @@ int srcgan_minmax(const float* a, int64_t n, float* out_min_max, void* stream);
 
 /* The eval sweep's four metrics (src/testCas.py:63-85: metrics.MSE, PSNR, AE, SSIM of src/metrics.py:10-144) in ONE kernel
    launch over pred / truth [n][c][h][w] fp32; SSIM's data range L is chosen on the device from pred's min / max exactly as
-   metrics.py:102-111 does on the host.  out (8 + 2n floats): [0] MSE [1] PSNR [2] AE mean (degrees) [3] SSIM mean [4] L
-   [5] min(pred) [6] max(pred) [7] 0, then n per-image SSIM means, then n per-image AE.  The first 256 bytes of the workspace
+   metrics.py:102-111 does on the host.  out (8 + 5n floats): [0] MSE [1] PSNR [2] AE mean (degrees) [3] SSIM mean [4] L
+   [5] min(pred) [6] max(pred) [7] 0, then n per-image SSIM means (batch-wide L), n per-image AE, n per-image MSE, n per-image
+   SSIM with the image's own data range (what a one-tile-per-call loop like testCas.py:65-85 computes) and those n ranges.  The first 256 bytes of the workspace
    hold a ticket counter: pass a workspace that was zero-filled once (the kernel re-arms it). */
 size_t srcgan_eval_metrics_workspace_bytes(int n, int c, int h, int w);
 int srcgan_eval_metrics(const float* pred, const float* truth, int n, int c, int h, int w, float* out, void* workspace,

@@ -1,0 +1,38 @@
+#!/usr/bin/env python
+"""gpurun_out/<tag>_conv_ncu.csv (ncu --page raw --csv of scripts/exp/ncu_shapes.py) + gpurun_out/<tag>_conv_shapes.json ->
+profiles/r2_ncu_conv.txt and profiles/traffic.json (what bench.py puts into roofline.traffic)."""
+import csv
+import json
+import os
+import sys
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+tag = sys.argv[1] if len(sys.argv) > 1 else "r2d"
+shapes = [json.loads(l) for l in open(os.path.join(ROOT, "gpurun_out", tag + "_conv_shapes.json")) if l.startswith("{")]
+rows = list(csv.reader(open(os.path.join(ROOT, "gpurun_out", tag + "_conv_ncu.csv"))))
+hdr = {h: i for i, h in enumerate(rows[0])}
+launches = [r for r in rows[2:] if "sweep2" in r[hdr["Kernel Name"]] or "wgrad_stack" in r[hdr["Kernel Name"]]]
+out, traffic, i = [], {}, 0
+get = lambda r, k: float(r[hdr[k]]) if k in hdr and r[hdr[k]] not in ("", "n/a") else float("nan")
+out.append("ncu --set full --clock-control none, scripts/exp/ncu_shapes.py (last of %d launches per shape); B200, round 2 (%s)" % (shapes[0]["launches"], tag))
+out.append("%-46s %9s %9s %9s %9s %7s %9s %8s %8s" % ("shape", "us", "rd MB", "wr MB", "alg MB", "x alg", "TFLOP/s", "tensor%", "dram%"))
+for s in shapes:
+    grp = launches[i:i + s["launches"]]
+    i += s["launches"]
+    if not grp:
+        continue
+    r = grp[-1]
+    us, rd, wr = get(r, "gpu__time_duration.sum"), get(r, "dram__bytes_read.sum"), get(r, "dram__bytes_write.sum")
+    alg = s["algorithmic_bytes"] / 1e6
+    tens = get(r, "sm__pipe_tensor_subpipe_cycles_active.avg.pct_of_peak_sustained_active") if "sm__pipe_tensor_subpipe_cycles_active.avg.pct_of_peak_sustained_active" in hdr \
+        else get(r, "sm__inst_executed_pipe_tensor.avg.pct_of_peak_sustained_active")
+    dram = get(r, "dram__throughput.avg.pct_of_peak_sustained_elapsed")
+    out.append("%-46s %9.1f %9.1f %9.1f %9.1f %7.2f %9.0f %8.1f %8.1f" % (s["what"], us, rd, wr, alg, (rd + wr) / alg, s["flops"] / us / 1e6, tens, dram))
+    name = r[hdr["Kernel Name"]]
+    fam = s["kernel"]
+    if fam not in traffic or "160->32" in s["what"] or ("64->32 @ 64x256" in s["what"] and "sweep2_tc<32" in fam) or ("192->64" in s["what"] and "sweep2_tc<64" in fam):
+        traffic[fam] = {"bytes_per_launch": (rd + wr) * 1e6, "note": "%s: dram read %.0f MB + write %.0f MB per launch vs %.0f MB algorithmic (ncu --set full, profiles/r2_ncu_conv.txt)" % (s["what"], rd, wr, alg)}
+open(os.path.join(ROOT, "profiles", "r2_ncu_conv.txt"), "w").write("\n".join(out) + "\n")
+json.dump(traffic, open(os.path.join(ROOT, "profiles", "traffic.json"), "w"), indent=1)
+print("\n".join(out))
+print(json.dumps(traffic, indent=1))

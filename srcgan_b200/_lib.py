@@ -35,7 +35,7 @@ class ConvParams(C.Structure):
         ("r2", C.c_void_p), ("r2_ld", C.c_int32), ("beta2", C.c_float),
         ("mask", C.c_void_p), ("mask_ld", C.c_int32), ("mask_slope", C.c_float),
         ("signbits", C.c_void_p), ("maskbits", C.c_void_p),
-        ("zero_row_period", C.c_int32), ("reserved0", C.c_int32),
+        ("zero_row_period", C.c_int32), ("flags", C.c_int32),
     ]
 
 

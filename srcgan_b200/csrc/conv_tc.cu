@@ -1110,6 +1110,8 @@ struct Sw2Args {
   uint32_t* signbits;                   // OUT [pixel][BN/32]: bit = stored value > 0 (the mask of the matching backward step)
   const uint32_t* maskbits;             // IN  [pixel][BN/32]: replaces `mask` (4 bytes instead of 64 per pixel and 32 channels)
   int zero_period;                      // > 0: image rows with row % zero_period == 0 are stored as zeros ("tall image" separators)
+  int rev;                              // 1: work units in descending order (last image first): the layer then starts on the data the
+                                        //    previous layer of a dense block touched last, which is what still sits in the 126 MB L2
   int dbg;
 };
 
@@ -1266,7 +1268,7 @@ conv3x3_sweep2_tc(const __grid_constant__ CUtensorMap tmap_x, const Sw2Args a) {
 
   // i-th unit of this CTA pair (-1: none left)
   auto get_unit = [&](int i) -> int {
-    if (a.sched == nullptr) { const int u = cid + i * ncl; return u < a.num_units ? u : -1; }
+    if (a.sched == nullptr) { const int u = cid + i * ncl; return u < a.num_units ? (a.rev ? a.num_units - 1 - u : u) : -1; }
     if (CG == 2 && rank == 1) mbar_wait_cluster(&u_full[i], 0); else mbar_wait(&u_full[i], 0);
     return reinterpret_cast<volatile int*>(unit_list)[i];
   };
@@ -1275,6 +1277,7 @@ conv3x3_sweep2_tc(const __grid_constant__ CUtensorMap tmap_x, const Sw2Args a) {
     if (i < SW_MAXU - 1) {
       u = (int)atomicAdd(a.sched, 1u);
       if (u >= a.num_units) u = -1;
+      else if (a.rev) u = a.num_units - 1 - u;
     }
     publish_unit(unit_list, u_full, i, u, CG == 2);
   };
@@ -1750,7 +1753,7 @@ static HostPlan fprop_plan(int K, int s, int p) {
   pl.in_scale = s;
   int slot = 0;
   if (s == 1) {
-    hp.maxt = K;
+    hp.maxt = K < 2 ? 2 : K;             // 1x1: the two-tap instantiations, one tap used (plan.ntaps) - one slab row in vain
     for (int kw = 0; kw < K; ++kw) {
       pl.dx[pl.nloads] = kw - p; pl.dy[pl.nloads] = -p; pl.ntaps[pl.nloads] = K; pl.slot0[pl.nloads] = slot;
       for (int kh = 0; kh < K; ++kh) { hp.slot_kh[slot] = kh; hp.slot_kw[slot] = kw; ++slot; }
@@ -2013,7 +2016,8 @@ static void fill_epilogue(TcArgs& a, const srcgan_conv_params* p) {
 
 static bool tc_common_ok(const srcgan_conv_params* p) {
   if (p->dtype != SRCGAN_DT_BF16 || p->upsample) return false;
-  if (p->kh != p->kw || (p->kh != 3 && p->kh != 4)) return false;
+  if (p->kh != p->kw || (p->kh != 1 && p->kh != 3 && p->kh != 4)) return false;
+  if (p->kh == 1 && p->pad != 0) return false;
   if (p->stride != 1 && p->stride != 2) return false;
   if (p->x_ld % 8 || p->y_ld % 8) return false;
   if (((uintptr_t)p->x) % 16 || ((uintptr_t)p->y) % 16) return false;
@@ -2153,6 +2157,7 @@ static int conv_fprop_sweep2(const srcgan_conv_params* p, int cg, cudaStream_t s
                  "conv_fprop_tc: packed sign / mask bits cannot be combined with residual or bf16 mask operands");
   a.signbits = (uint32_t*)p->signbits; a.maskbits = (const uint32_t*)p->maskbits;
   a.zero_period = p->zero_row_period;
+  a.rev = (p->flags & SRCGAN_CONV_FLAG_REVERSE) ? 1 : 0;
   { const char* d = getenv("SRCGAN_B200_DBG"); a.dbg = d ? atoi(d) : 0; }
   { const char* d = getenv("SRCGAN_B200_PFD"); a.pfd = d ? atoi(d) : 0; }
   if (cg == 2) return p->cout == 64 ? tc::launch_sweep2<64, 2>(tx, a, st) : tc::launch_sweep2<32, 2>(tx, a, st);
@@ -2966,7 +2971,8 @@ int colsum_final_launch(const float* part, int nparts, int c, float* out, int ac
 
 bool conv_wgrad_tc_supported(const srcgan_conv_params* p) {
   if (p->dtype != SRCGAN_DT_BF16 || (p->stride != 1 && p->stride != 2) || p->upsample) return false;
-  if (p->kh != p->kw || (p->kh != 3 && p->kh != 4)) return false;
+  if (p->kh != p->kw || (p->kh != 1 && p->kh != 3 && p->kh != 4)) return false;
+  if (p->kh == 1 && p->pad != 0) return false;
   if (!(p->kh == 3 && p->stride == 1) && (p->cin < 16 || p->cin % 8 || p->cout < 16 || p->cout % 8)) return false;
   if (p->x_ld % 8 || p->y_ld % 8) return false;
   if (((uintptr_t)p->x) % 16 || ((uintptr_t)p->y) % 16) return false;

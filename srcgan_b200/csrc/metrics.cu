@@ -133,6 +133,7 @@ int ssim(const float* p, const float* t, int n, int c, int h, int w, float L, fl
 //   * partials go to a workspace; the last block to finish (atomic ticket) reduces them in a fixed order -> deterministic.
 // out: [0] MSE  [1] PSNR  [2] AE (mean over images)  [3] SSIM (mean)  [4] L  [5] min  [6] max  [7] unused
 //      [8 .. 8+n)    per-image SSIM means  (size_average=False form)      [8+n .. 8+2n)  per-image AE (degrees)
+//      [8+2n .. 8+3n) per-image MSE    [8+3n .. 8+4n) per-image SSIM with the image's OWN data range    [8+4n .. 8+5n) that range
 // ---------------------------------------------------------------------------------------------
 constexpr int EV_PART = 8;          // per block: ssim(L=1), ssim(2), ssim(255), ssim(256), sqerr, ae_sum, min, max
 
@@ -293,7 +294,31 @@ eval_metrics_k(const float* __restrict__ p, const float* __restrict__ t, int c, 
   double ssim_all = 0.0, ae_all = 0.0;
   for (int i = 0; i < n; ++i) {
     const double s = block_total(i * per_img, per_img, cand), a = block_total(i * per_img, per_img, 5);
-    if (tid == 0) { out[8 + i] = (float)(s / count); out[8 + n + i] = (float)(a / hw); }
+    const double sq_i = block_total(i * per_img, per_img, 4);
+    // the image's own data range (what the reference's loop sees when it scores one tile per call, testCas.py:65-85)
+    float ilo = INFINITY, ihi = -INFINITY;
+    for (int b = tid; b < per_img; b += 256) {
+      ilo = fminf(ilo, __ldcg(part + (int64_t)(i * per_img + b) * EV_PART + 6));
+      ihi = fmaxf(ihi, __ldcg(part + (int64_t)(i * per_img + b) * EV_PART + 7));
+    }
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) {
+      ilo = fminf(ilo, __shfl_xor_sync(0xffffffffu, ilo, o));
+      ihi = fmaxf(ihi, __shfl_xor_sync(0xffffffffu, ihi, o));
+    }
+    __syncthreads();
+    if ((tid & 31) == 0) { red[6][tid >> 5] = ilo; red[7][tid >> 5] = ihi; }
+    __syncthreads();
+    for (int k = 0; k < 8; ++k) { ilo = fminf(ilo, red[6][k]); ihi = fmaxf(ihi, red[7][k]); }
+    const int cand_i = (ihi > 128.f ? 2 : 0) + (ilo < -0.5f ? 1 : 0);
+    const double s_own = cand_i == cand ? s : block_total(i * per_img, per_img, cand_i);
+    if (tid == 0) {
+      out[8 + i] = (float)(s / count);
+      out[8 + n + i] = (float)(a / hw);
+      out[8 + 2 * n + i] = (float)(sq_i / ((double)c * hw));
+      out[8 + 3 * n + i] = (float)(s_own / count);
+      out[8 + 4 * n + i] = (ihi > 128.f ? 255.f : 1.f) - (ilo < -0.5f ? -1.f : 0.f);
+    }
     ssim_all += s;
     ae_all += a / hw;
   }

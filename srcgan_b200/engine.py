@@ -21,7 +21,7 @@ def force_simt(flag: bool) -> None:
 
 def tc_fprop_supported(cin: int, cout: int, k: int, stride: int, upsample: bool, dtype, h: int, w: int) -> bool:
     """Mirror of conv_tc_supported() in csrc/conv_tc.cu (the C side re-checks alignment and refuses loudly)."""
-    if dtype != torch.bfloat16 or upsample or k not in (3, 4) or stride not in (1, 2):
+    if dtype != torch.bfloat16 or upsample or k not in (1, 3, 4) or stride not in (1, 2):
         return False
     if cout <= 16:                     # thin outputs (64->3 image conv): 3x3 stride-1 halo kernel, plain epilogue
         return k == 3 and stride == 1
@@ -36,7 +36,7 @@ def tc_dgrad_s2_supported(cin: int, cout: int, k: int, stride: int, pad: int, dt
 
 def tc_wgrad_supported(cin: int, cout: int, k: int, stride: int, upsample: bool, dtype, h: int, w: int) -> bool:
     """Mirror of conv_wgrad_tc_supported() in csrc/conv_tc.cu."""
-    if dtype != torch.bfloat16 or upsample or k not in (3, 4) or stride not in (1, 2):
+    if dtype != torch.bfloat16 or upsample or k not in (1, 3, 4) or stride not in (1, 2):
         return False
     if k == 3 and stride == 1:         # halo wgrad kernel: thin sides allowed (buffers have ld = 8)
         return cout <= 32 or cout % 64 == 0

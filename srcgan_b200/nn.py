@@ -196,6 +196,10 @@ class _Packs:
             e.stamp = self._stamp(e.params)
 
 
+def _alt_order() -> bool:
+    return not os.environ.get("SRCGAN_B200_NO_ALT_ORDER")
+
+
 def _batched_ok(cout: int, ksize: int) -> bool:
     """Shapes the batched packer (csrc/pack_batch.cu) takes: the stride-1 tcgen05 layout's channel counts, <= 16 taps."""
     return (cout in (32, 64, 128, 256) or cout <= 16) and ksize * ksize <= 16 and not os.environ.get("SRCGAN_B200_NO_BATCH_PACK")
@@ -413,8 +417,9 @@ class _NetBase(nn.Module):
         from . import engine as _engine
         eng = _engine.select_wgrad(x.c, dy.c, k, s, upsample, x.dtype, dy.h, dy.w)
         if (eng == ENGINE_TC and k == 3 and s == 1 and p == 1 and not upsample and dy.c == 128 and x.c % 8 == 0
-                and x.c >= 16 and max(dy.h, dy.w) >= 96 and dw is not None):
-            # same layer, weight gradient: two launches of the kw-stacked wgrad kernel over 64-channel halves of dY
+                and x.c >= 16 and dw is not None):
+            # same layer, weight gradient: two launches of the kw-stacked wgrad kernel over 64-channel halves of dY (any map
+            # size - the stacked kernel is tile based; Decoder conv5, 256 -> 128 at 64^2, ran at 161 TFLOP/s on the per-tap one)
             for h0 in (0, 64):
                 ops.conv_wgrad(x, Slice(dy.buf, dy.c0 + h0, 64), dw[h0:h0 + 64], None if db is None else db[h0:h0 + 64], k, s, p,
                                accumulate=acc_w or acc_b, alpha=alpha, engine=eng)
@@ -556,7 +561,18 @@ class _RRDBGenerator(_NetBase):
         activation slices (dgrad of the gc = 32 layers is HBM-bound: 13-23 % fewer bytes)."""
         nf, gc = self.nf, self.gc
         n, h, w, dt, dev = bufs[0].shape[0], bufs[0].shape[1], bufs[0].shape[2], bufs[0].dtype, bufs[0].device
-        zkw = {"zero_rows": zr} if zr else {}          # tall-image mode: separator rows are stored as zeros (see _tall_plan)
+        alt, flip = _alt_order(), [False]
+
+        def ep_common() -> dict:
+            """zero_rows: tall-image mode (see _tall_plan).  reverse: every second launch of the chain walks the images
+            backwards, so it starts on what the previous layer touched last - the part the 126 MB L2 still holds."""
+            d = {"zero_rows": zr} if zr else {}
+            if alt:
+                if flip[0]:
+                    d["reverse"] = True
+                flip[0] = not flip[0]
+            return d
+
         for j, rdb in enumerate(rdbs):
             C = bufs[j]
             convs = rdb.convs()
@@ -567,15 +583,15 @@ class _RRDBGenerator(_NetBase):
                     sb = torch.empty((n, h, w, 1), dtype=torch.int32, device=dev)
                 row.append(sb)
                 self._fprop(convs[k - 1], Slice(C, 0, nf + gc * (k - 1)), Slice(C, nf + gc * (k - 1), gc), act=LRELU,
-                            **({"signbits": sb} if sb is not None else {}), **zkw)
+                            **({"signbits": sb} if sb is not None else {}), **ep_common())
             if bits is not None:
                 bits.append(row)
             dest = Slice(bufs[j + 1], 0, nf) if j + 1 < len(rdbs) else out
             if j % 3 != 2:      # x5*0.2 + x                                    (model.py:211)
-                self._fprop(convs[4], Slice(C), dest, alpha=0.2, r1=Slice(C, 0, nf), beta1=1.0, **zkw)
+                self._fprop(convs[4], Slice(C), dest, alpha=0.2, r1=Slice(C, 0, nf), beta1=1.0, **ep_common())
             else:               # RDB3: (x5*0.2 + x)*0.2 + rrdb_in              (model.py:211,233)
                 self._fprop(convs[4], Slice(C), dest, alpha=0.04, r1=Slice(C, 0, nf), beta1=0.2,
-                            r2=Slice(bufs[j - 2], 0, nf), beta2=1.0, **zkw)
+                            r2=Slice(bufs[j - 2], 0, nf), beta2=1.0, **ep_common())
 
     def _chain_backward(self, rdbs, bufs, Dbuf: List[torch.Tensor], dest: Slice, sink: "_GradSink", W,
                         bits: Optional[list] = None, zr: int = 0) -> None:
@@ -584,7 +600,16 @@ class _RRDBGenerator(_NetBase):
         nf, gc = self.nf, self.gc
         ctot = nf + 4 * gc
         h, w, dt, dev = bufs[0].shape[1], bufs[0].shape[2], bufs[0].dtype, bufs[0].device
-        zkw = {"zero_rows": zr} if zr else {}
+        alt, flip = _alt_order(), [False]
+
+        def ep_common() -> dict:
+            d = {"zero_rows": zr} if zr else {}
+            if alt:
+                if flip[0]:
+                    d["reverse"] = True
+                flip[0] = not flip[0]
+            return d
+
         for j in range(len(rdbs) - 1, -1, -1):
             rdb, C, D = rdbs[j], bufs[j], Dbuf[j % 4]
             convs = rdb.convs()
@@ -598,16 +623,16 @@ class _RRDBGenerator(_NetBase):
                     mb = None
                 if mb is not None:
                     ops.conv_fprop(Slice(D, 0, cin_v), self._dense_wT(rdb, k, s5, dt, layout), None,
-                                   Slice(D, nf + gc * (4 - k), gc), 3, 1, 1, maskbits=mb, mask_slope=LRELU, engine=eng, **zkw)
+                                   Slice(D, nf + gc * (4 - k), gc), 3, 1, 1, maskbits=mb, mask_slope=LRELU, engine=eng, **ep_common())
                 else:
                     ops.conv_fprop(Slice(D, 0, cin_v), self._dense_wT(rdb, k, s5, dt, layout), None,
                                    Slice(D, nf + gc * (4 - k), gc), 3, 1, 1,
-                                   mask=Slice(C, nf + gc * (k - 1), gc), mask_slope=LRELU, engine=eng, **zkw)
+                                   mask=Slice(C, nf + gc * (k - 1), gc), mask_slope=LRELU, engine=eng, **ep_common())
             dst = Slice(Dbuf[(j - 1) % 4], 0, nf) if j > 0 else dest
             eng, layout = select_engine(ctot, nf, 3, 1, False, dt, h, w)
             ops.conv_fprop(Slice(D), self._dense_wT(rdb, 0, s5, dt, layout), None, dst, 3, 1, 1,
                            r1=Slice(D, 0, nf), beta1=(0.2 if is_rdb3 else 1.0),
-                           r2=(Slice(Dbuf[(j + 2) % 4], 0, nf) if is_rdb1 else None), beta2=1.0, engine=eng, **zkw)
+                           r2=(Slice(Dbuf[(j + 2) % 4], 0, nf) if is_rdb1 else None), beta2=1.0, engine=eng, **ep_common())
             # bias gradients: the kw-stacked tcgen05 wgrad kernel sums dY out of the slabs it has in shared memory anyway
             # (csrc/conv_tc.cu, tcw4); other engines take one fused column-sum pass over the gradient concat buffer
             from . import engine as _engine

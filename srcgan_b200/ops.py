@@ -212,7 +212,8 @@ def conv_fprop(x: Slice, wgt: torch.Tensor, bias: Optional[torch.Tensor], y: Sli
                pad: int = 1, *, upsample: bool = False, act: Optional[float] = None, alpha: float = 1.0,
                r1: Optional[Slice] = None, beta1: float = 0.0, r2: Optional[Slice] = None, beta2: float = 0.0,
                mask: Optional[Slice] = None, mask_slope: float = 0.0, engine: int = ENGINE_SIMT,
-               signbits: Optional[torch.Tensor] = None, maskbits: Optional[torch.Tensor] = None, zero_rows: int = 0) -> None:
+               signbits: Optional[torch.Tensor] = None, maskbits: Optional[torch.Tensor] = None, zero_rows: int = 0,
+               reverse: bool = False) -> None:
     """y = epilogue(conv(x, w)); see include/srcgan_b200.h for the epilogue definition.
     ``signbits`` (out) / ``maskbits`` (in): packed LeakyReLU masks, int32 (n, h, w, cout/32) - paired-sweep kernel only.
     ``zero_rows``: separator period of a tall image (rows % zero_rows == 0 are stored as zeros) - paired-sweep kernel only."""
@@ -227,6 +228,7 @@ def conv_fprop(x: Slice, wgt: torch.Tensor, bias: Optional[torch.Tensor], y: Sli
     if maskbits is not None:
         p.mask_slope = float(mask_slope)
     p.zero_row_period = int(zero_rows)
+    p.flags = 1 if reverse else 0                     # SRCGAN_CONV_FLAG_REVERSE
     with _Timed("fprop", p):
         _lib.check(_lib.load().srcgan_conv_fprop(C.byref(p), _stream()), "conv_fprop")
 
@@ -512,8 +514,9 @@ _eval_ws = {}
 
 
 def eval_metrics(pred: torch.Tensor, truth: torch.Tensor) -> torch.Tensor:
-    """One kernel launch -> fp32 device tensor of 8 + 2n values: [MSE, PSNR, AE mean, SSIM mean, L, min, max, 0,
-    per-image SSIM (n), per-image AE (n)] (see include/srcgan_b200.h); no host synchronisation."""
+    """One kernel launch -> fp32 device tensor of 8 + 5n values: [MSE, PSNR, AE mean, SSIM mean, L, min, max, 0, per-image
+    SSIM (n), per-image AE (n), per-image MSE (n), per-image SSIM with its own data range (n), those ranges (n)]
+    (see include/srcgan_b200.h); no host synchronisation."""
     p, t = _f32c(pred, "metric input"), _f32c(truth, "metric input")
     assert p.shape == t.shape and p.dim() == 4
     n, c, h, w = p.shape
@@ -524,7 +527,7 @@ def eval_metrics(pred: torch.Tensor, truth: torch.Tensor) -> torch.Tensor:
     if ws is None or ws.numel() < nbytes:
         ws = torch.zeros(max(int(nbytes), 1 << 16), dtype=torch.uint8, device=p.device)   # zeroed once: the ticket counter
         _eval_ws[key] = ws
-    out = torch.empty(8 + 2 * n, dtype=torch.float32, device=p.device)
+    out = torch.empty(8 + 5 * n, dtype=torch.float32, device=p.device)
     _lib.check(lib.srcgan_eval_metrics(p.data_ptr(), t.data_ptr(), n, c, h, w, out.data_ptr(), ws.data_ptr(), ws.numel(),
                                        _stream()), "eval_metrics")
     return out

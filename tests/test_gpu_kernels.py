@@ -242,6 +242,36 @@ def test_fused_eval_metrics_kernel(shape, scale, shift):
         assert close(res[2], O.angular_error(a, b).mean(), 2e-4)
     # bit-reproducible (fixed-order reduction behind the atomic ticket)
     assert torch.equal(ops.eval_metrics(a.to(DEV), b.to(DEV)).cpu(), res)
+    # per-image MSE
+    per_mse = ((a - b) ** 2).flatten(1).mean(1)
+    assert torch.allclose(res[8 + 2 * n:8 + 3 * n], per_mse, rtol=5e-5)
+
+
+def test_fused_eval_metrics_scores_every_tile_of_a_batch_on_its_own():
+    """A batch whose tiles have different data ranges: the per-image outputs use each tile's OWN range, like a loop that
+    scores one tile per call (testCas.py:65-85); evaluate(batch=k) therefore returns the same rows as batch=1."""
+    from oracle import srcgan_oracle as O
+    from srcgan_b200 import evaluate, ops
+    g = torch.Generator().manual_seed(7)
+    a = torch.rand(3, 3, 64, 48, generator=g)
+    a[1] *= 255.0
+    a[2] = a[2] * 2 - 1
+    b = a + 0.03 * a.abs().amax(dim=(1, 2, 3), keepdim=True) * torch.randn(a.shape, generator=g)
+    res = ops.eval_metrics(a.to(DEV), b.to(DEV)).cpu()
+    n = 3
+    assert res[8 + 4 * n:8 + 5 * n].tolist() == [1.0, 255.0, 2.0]
+    for i in range(n):
+        assert math.isclose(float(res[8 + 3 * n + i]), float(O.ssim(a[i:i + 1], b[i:i + 1])), rel_tol=1e-4, abs_tol=1e-6), i
+    rows = evaluate.per_image_metrics(a.to(DEV), b.to(DEV)).cpu()
+    for i in range(n):
+        assert math.isclose(float(rows[i, 0]), float(O.mse_loss(a[i:i + 1], b[i:i + 1])), rel_tol=5e-5)
+        assert math.isclose(float(rows[i, 1]), float(O.psnr(a[i:i + 1], b[i:i + 1])), rel_tol=5e-5)
+        assert math.isclose(float(rows[i, 2]), float(O.angular_error(a[i:i + 1], b[i:i + 1])), rel_tol=2e-4)
+    ident = lambda t: t
+    r1, _ = evaluate.evaluate(ident, [(a[i:i + 1].to(DEV), b[i:i + 1].to(DEV)) for i in range(n)], batch=1)
+    r3, _ = evaluate.evaluate(lambda t: t, [(a[i:i + 1].to(DEV), b[i:i + 1].to(DEV)) for i in range(n)], batch=3)
+    for x, y in zip(r1, r3):
+        assert all(math.isclose(x[k], y[k], rel_tol=1e-6, abs_tol=1e-7) for k in x), (x, y)
 
 
 @pytest.mark.parametrize("shape,scale", [((2, 3, 40, 36), 1.0), ((1, 1, 75, 43), 255.0)])
@@ -569,6 +599,39 @@ def test_conv_tc_stride2_fprop_dgrad_wgrad(case):
     ops.conv_wgrad(xs, gys, dw, db, k, 2, 1, engine=ops.ENGINE_TC)
     assert relerr(dw.cpu(), wt.grad) < 5e-3
     assert relerr(db.cpu(), gy.sum((0, 2, 3))) < 5e-3
+
+
+@pytest.mark.parametrize("case", [(2, 20, 24, 64, 256, 1), (1, 16, 16, 512, 256, 1), (2, 32, 24, 64, 128, 2), (1, 30, 18, 256, 256, 2),
+                                  (2, 16, 8, 256, 64, 1)])
+def test_conv_tc_1x1(case):
+    """1x1 convolutions (ResDeconv's down-sampling shortcuts and its k2 s2 deconvolutions as 1x1 -> depth-to-space; the
+    reference's src/model/resdeconv.py) on the tcgen05 implicit-GEMM kernels: fprop, wgrad, and the stride-1 dgrad."""
+    from srcgan_b200 import _lib, ops
+    n, h, w, cin, cout, s_ = case
+    x = rand((n, cin, h, w), 61).bfloat16().float().requires_grad_(True)
+    wt = rand((cout, cin, 1, 1), 62, 0.1).bfloat16().float().requires_grad_(True)
+    b = rand((cout,), 63)
+    y_ref = F.conv2d(x, wt, b, stride=s_, padding=0)
+    ho, wo = y_ref.shape[2:]
+    gy = rand(tuple(y_ref.shape), 64).bfloat16().float()
+    y_ref.backward(gy)
+    xs = to_nhwc(x.detach(), torch.bfloat16)
+    ys = ops.Slice(torch.zeros((n, ho, wo, cout), dtype=torch.bfloat16, device=DEV))
+    layout = ops.WL_TC if s_ == 1 else ops.WL_TC_S2
+    ops.conv_fprop(xs, ops.pack_weights(wt.detach().to(DEV), layout, torch.bfloat16), b.to(DEV), ys, 1, s_, 0, engine=ops.ENGINE_TC)
+    assert _lib.last_kernel().startswith("conv_igemm_tc")
+    assert relerr(from_nhwc(ys), y_ref.detach()) < 1e-2
+    gys = to_nhwc(gy, torch.bfloat16)
+    dw = torch.empty((cout, cin, 1, 1), device=DEV)
+    db = torch.empty((cout,), device=DEV)
+    ops.conv_wgrad(xs, gys, dw, db, 1, s_, 0, engine=ops.ENGINE_TC)
+    assert relerr(dw.cpu(), wt.grad) < 5e-3
+    assert relerr(db.cpu(), gy.sum((0, 2, 3))) < 5e-3
+    if s_ == 1 and cin in (32, 64, 128, 256):
+        wtp = ops.pack_weights(wt.detach().transpose(0, 1).contiguous().to(DEV), ops.WL_TC, torch.bfloat16)
+        dxs = ops.Slice(torch.zeros((n, h, w, cin), dtype=torch.bfloat16, device=DEV))
+        ops.conv_fprop(gys, wtp, None, dxs, 1, 1, 0, engine=ops.ENGINE_TC)
+        assert relerr(from_nhwc(dxs), x.grad) < 1e-2
 
 
 THIN_TC_CASES = [

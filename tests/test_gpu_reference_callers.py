@@ -55,8 +55,12 @@ def test_reference_train_py_steps_on_the_cuda_path(golden_step, tmp_path, precis
     assert out["classes"]["criterionCycle"].startswith("srcgan_b200.losses.")
     assert out["launches"] > 500                                              # the C-ABI kernels really ran
     for it, rec in enumerate(golden_step["steps"]):
+        # bf16, second iteration: Adam's first update moves every weight by ~lr whatever the size of its gradient, so the
+        # weights whose bf16 gradient has the other sign than the fp32 one end up 2 lr apart - the losses of the next
+        # iteration carry that (measured up to 4 % on the 1.3-sized adversarial terms); the first iteration is held to 3e-2
+        rt = tol if (precision == "fp32" or it == 0) else 8e-2
         for n, v in rec["losses"].items():
-            assert math.isclose(out["steps"][it]["losses"][n], v, rel_tol=tol, abs_tol=1e-5 if precision == "fp32" else 2e-3), \
+            assert math.isclose(out["steps"][it]["losses"][n], v, rel_tol=rt, abs_tol=1e-5 if precision == "fp32" else 2e-3), \
                 (precision, it, n, out["steps"][it]["losses"][n], v)
         if "fake_B" in rec:
             assert relerr(out["steps"][it]["fake_B"], rec["fake_B"]) < (1e-3 if precision == "fp32" else 5e-2)
