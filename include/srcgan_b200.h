@@ -153,6 +153,14 @@ size_t srcgan_conv_wgrad_workspace_bytes(const srcgan_conv_params* p);
 int srcgan_conv_wgrad(const srcgan_conv_params* p, float* dw, float* db, int accumulate,
                       void* workspace, size_t workspace_bytes, void* stream);
 
+/* One wgrad launch, two destinations (tcgen05 engine, 3x3 stride 1 pad 1, cout 32 / 64): output channels [0, split_cout) of
+   dY go to dw0 / db0, the rest to dw1 / db1.  dwX is an fp32 OIHW tensor with cin_ldX input channels; the launch writes its
+   channels [ci0_X, ci0_X + p->cin).  Either destination (or bias) may be NULL.  Used for the paired dense-block weight
+   gradients (conv_k and conv_(k+1) of src/model/model.py:205-210 share their input prefix). */
+int srcgan_conv_wgrad_split(const srcgan_conv_params* p, float* dw0, int cin_ld0, int ci0_0, float* db0, float* dw1, int cin_ld1,
+                            int ci0_1, float* db1, int split_cout, int accumulate, void* workspace, size_t workspace_bytes,
+                            void* stream);
+
 /* layout glue at the module boundary: NCHW fp32 <-> channel-sliced NHWC (f32 | bf16) */
 int srcgan_nchw_to_nhwc(const float* src, int n, int c, int h, int w, void* dst, int dst_ld, int dtype, void* stream);
 int srcgan_nhwc_to_nchw(const void* src, int src_ld, int dtype, float* dst, int n, int c, int h, int w, void* stream);

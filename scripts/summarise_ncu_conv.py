@@ -13,9 +13,18 @@ rows = list(csv.reader(open(os.path.join(ROOT, "gpurun_out", tag + "_conv_ncu.cs
 hdr = {h: i for i, h in enumerate(rows[0])}
 launches = [r for r in rows[2:] if "sweep2" in r[hdr["Kernel Name"]] or "wgrad_stack" in r[hdr["Kernel Name"]]]
 out, traffic, i = [], {}, 0
-get = lambda r, k: float(r[hdr[k]]) if k in hdr and r[hdr[k]] not in ("", "n/a") else float("nan")
+UNIT = {"byte": 1e-6, "Kbyte": 1e-3, "Mbyte": 1.0, "Gbyte": 1e3, "Tbyte": 1e6, "ns": 1e-3, "us": 1.0, "ms": 1e3, "s": 1e6}
+
+
+def get(r, k):
+    """value of column k; bytes in MB and times in us whatever unit ncu picked for the column"""
+    if k not in hdr or r[hdr[k]] in ("", "n/a"):
+        return float("nan")
+    return float(r[hdr[k]]) * UNIT.get(rows[1][hdr[k]], 1.0)
 out.append("ncu --set full --clock-control none, scripts/exp/ncu_shapes.py (last of %d launches per shape); B200, round 2 (%s)" % (shapes[0]["launches"], tag))
-out.append("%-46s %9s %9s %9s %9s %7s %9s %8s %8s" % ("shape", "us", "rd MB", "wr MB", "alg MB", "x alg", "TFLOP/s", "tensor%", "dram%"))
+out.append("%-46s %9s %9s %9s %9s %7s %9s %8s %8s" % ("shape", "us", "rd MB", "wr MB", "alg MB", "x alg", "TFLOP/s", "pipe act%", "utchmma%"))
+out.append("(pipe act% = sm__pipe_tensor_cycles_active.avg.pct_of_peak_sustained_active; utchmma% = sm__ops_path_tensor_op_utchmma_src_bf16_dst_fp32"
+           "_sparsity_off.avg.pct_of_peak_sustained_elapsed; x alg = measured DRAM bytes / algorithmic bytes)")
 for s in shapes:
     grp = launches[i:i + s["launches"]]
     i += s["launches"]
@@ -24,14 +33,13 @@ for s in shapes:
     r = grp[-1]
     us, rd, wr = get(r, "gpu__time_duration.sum"), get(r, "dram__bytes_read.sum"), get(r, "dram__bytes_write.sum")
     alg = s["algorithmic_bytes"] / 1e6
-    tens = get(r, "sm__pipe_tensor_subpipe_cycles_active.avg.pct_of_peak_sustained_active") if "sm__pipe_tensor_subpipe_cycles_active.avg.pct_of_peak_sustained_active" in hdr \
-        else get(r, "sm__inst_executed_pipe_tensor.avg.pct_of_peak_sustained_active")
-    dram = get(r, "dram__throughput.avg.pct_of_peak_sustained_elapsed")
-    out.append("%-46s %9.1f %9.1f %9.1f %9.1f %7.2f %9.0f %8.1f %8.1f" % (s["what"], us, rd, wr, alg, (rd + wr) / alg, s["flops"] / us / 1e6, tens, dram))
+    tens = get(r, "sm__pipe_tensor_cycles_active.avg.pct_of_peak_sustained_active")
+    util = get(r, "sm__ops_path_tensor_op_utchmma_src_bf16_dst_fp32_sparsity_off.avg.pct_of_peak_sustained_elapsed")
+    out.append("%-46s %9.1f %9.1f %9.1f %9.1f %7.2f %9.0f %8.1f %8.1f" % (s["what"], us, rd, wr, alg, (rd + wr) / alg, s["flops"] / us / 1e6, tens, util))
     name = r[hdr["Kernel Name"]]
     fam = s["kernel"]
     if fam not in traffic or "160->32" in s["what"] or ("64->32 @ 64x256" in s["what"] and "sweep2_tc<32" in fam) or ("192->64" in s["what"] and "sweep2_tc<64" in fam):
-        traffic[fam] = {"bytes_per_launch": (rd + wr) * 1e6, "note": "%s: dram read %.0f MB + write %.0f MB per launch vs %.0f MB algorithmic (ncu --set full, profiles/r2_ncu_conv.txt)" % (s["what"], rd, wr, alg)}
+        traffic[fam] = {"bytes_per_launch": (rd + wr) * 1e6, "note": "%s: dram read %.0f MB + write %.0f MB per launch vs %.0f MB algorithmic, tensor pipe active %.1f %% (ncu --set full, profiles/r2_ncu_conv.txt)" % (s["what"], rd, wr, alg, tens)}
 open(os.path.join(ROOT, "profiles", "r2_ncu_conv.txt"), "w").write("\n".join(out) + "\n")
 json.dump(traffic, open(os.path.join(ROOT, "profiles", "traffic.json"), "w"), indent=1)
 print("\n".join(out))

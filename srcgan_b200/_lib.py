@@ -71,6 +71,7 @@ SIGNATURES = {
     "srcgan_conv_dgrad": (_I, [C.POINTER(ConvParams), _P]),
     "srcgan_conv_wgrad_workspace_bytes": (_Z, [C.POINTER(ConvParams)]),
     "srcgan_conv_wgrad": (_I, [C.POINTER(ConvParams), _P, _P, _I, _P, _Z, _P]),
+    "srcgan_conv_wgrad_split": (_I, [C.POINTER(ConvParams), _P, _I, _I, _P, _P, _I, _I, _P, _I, _I, _P, _Z, _P]),
     "srcgan_nchw_to_nhwc": (_I, [_P, _I, _I, _I, _I, _P, _I, _I, _P]),
     "srcgan_nhwc_to_nchw": (_I, [_P, _I, _I, _P, _I, _I, _I, _I, _P]),
     "srcgan_act_backward": (_I, [_P, _I, _P, _I, _P, _I, _L, _I, _F, _I, _P]),

@@ -50,6 +50,8 @@ bool conv_wgrad_tc_supported(const srcgan_conv_params* p);
 size_t conv_wgrad_tc_workspace(const srcgan_conv_params* p);
 int conv_wgrad_tc(const srcgan_conv_params* p, float* dw, float* db, int accumulate, void* ws, size_t ws_bytes,
                   cudaStream_t st);
+int conv_wgrad_tc_split(const srcgan_conv_params* p, float* dw0, int ld0, int ci00, float* db0, float* dw1, int ld1, int ci01,
+                        float* db1, int split, int accumulate, void* ws, size_t ws_bytes, cudaStream_t st);
 // other kernels
 int nchw_to_nhwc(const float* src, int n, int c, int h, int w, void* dst, int ld, int dtype, cudaStream_t st);
 int nhwc_to_nchw(const void* src, int ld, int dtype, float* dst, int n, int c, int h, int w, cudaStream_t st);
@@ -186,6 +188,17 @@ int srcgan_conv_wgrad(const srcgan_conv_params* p, float* dw, float* db, int acc
     return conv_wgrad_tc(p, dw, db, accumulate, workspace, workspace_bytes, (cudaStream_t)stream);
   }
   return conv_wgrad_simt(p, dw, db, accumulate, workspace, workspace_bytes, (cudaStream_t)stream);
+}
+
+int srcgan_conv_wgrad_split(const srcgan_conv_params* p, float* dw0, int cin_ld0, int ci0_0, float* db0, float* dw1, int cin_ld1,
+                            int ci0_1, float* db1, int split_cout, int accumulate, void* workspace, size_t workspace_bytes,
+                            void* stream) {
+  int rc = validate_conv(p, false);
+  if (rc) return rc;
+  SRCGAN_REQUIRE(p->engine == SRCGAN_ENGINE_TC && conv_wgrad_tc_supported(p),
+                 "conv_wgrad_split: tcgen05 engine only (bf16, 3x3 stride 1)");
+  return conv_wgrad_tc_split(p, dw0, cin_ld0, ci0_0, db0, dw1, cin_ld1, ci0_1, db1, split_cout, accumulate, workspace,
+                             workspace_bytes, (cudaStream_t)stream);
 }
 
 int srcgan_nchw_to_nhwc(const float* src, int n, int c, int h, int w, void* dst, int dst_ld, int dtype, void* stream) {

@@ -75,11 +75,15 @@ conv_igemm_simt(const ConvDev a) {
   }
   __syncthreads();
 
-  float acc[TM][TN];
+  // Two-level accumulation: each BK = 16 chunk of K is summed in fp32 (FFMA), the chunk sums are added to a double master.
+  // A single fp32 accumulator over K = 9 x 192 terms carried 4x the rounding error of the reference's blocked CPU kernels;
+  // at full size that flipped 4x as many LeakyReLU gates and doubled the gradient noise against an fp64 evaluation
+  // (profiles/r2_fullsize_parity_fp32.json).  This engine is the parity path: accuracy first.
+  double acc[TM][TN];
 #pragma unroll
   for (int i = 0; i < TM; ++i)
 #pragma unroll
-    for (int j = 0; j < TN; ++j) acc[i][j] = 0.f;
+    for (int j = 0; j < TN; ++j) acc[i][j] = 0.0;
 
   const int SH = DGRAD ? a.ho : a.h, SW = DGRAD ? a.wo : a.w;   // stored dims of the source tensor
   const int HV = a.up ? 2 * a.h : a.h, WV = a.up ? 2 * a.w : a.w;
@@ -151,6 +155,11 @@ conv_igemm_simt(const ConvDev a) {
       for (int q = 0; q < 4; ++q) Bs[kr][nq + q] = v[q];
     }
     __syncthreads();
+    float blk[TM][TN];
+#pragma unroll
+    for (int i = 0; i < TM; ++i)
+#pragma unroll
+      for (int j = 0; j < TN; ++j) blk[i][j] = 0.f;
 #pragma unroll
     for (int kk = 0; kk < BK; ++kk) {
       float av[TM], bv[TN];
@@ -161,8 +170,12 @@ conv_igemm_simt(const ConvDev a) {
 #pragma unroll
       for (int i = 0; i < TM; ++i)
 #pragma unroll
-        for (int j = 0; j < TN; ++j) acc[i][j] = fmaf(av[i], bv[j], acc[i][j]);
+        for (int j = 0; j < TN; ++j) blk[i][j] = fmaf(av[i], bv[j], blk[i][j]);
     }
+#pragma unroll
+    for (int i = 0; i < TM; ++i)
+#pragma unroll
+      for (int j = 0; j < TN; ++j) acc[i][j] += (double)blk[i][j];
     __syncthreads();
   }
 
@@ -179,7 +192,7 @@ conv_igemm_simt(const ConvDev a) {
     for (int j = 0; j < TN; ++j) {
       int c = n0 + tx * TN + j;
       if (c >= nch) continue;
-      float v = acc[i][j];
+      float v = (float)acc[i][j];
       if (a.bias) v += a.bias[c];
       if (a.act) v = v > 0.f ? v : v * a.act_slope;
       v *= a.alpha;
@@ -216,11 +229,11 @@ conv_wgrad_simt(const ConvDev a, float* __restrict__ part, int pix_per_split) {
   const T* __restrict__ G = reinterpret_cast<const T*>(a.y);
   const int HV = a.up ? 2 * a.h : a.h, WV = a.up ? 2 * a.w : a.w;
 
-  float acc[TI][TO];
+  double acc[TI][TO];        // double master over the pixel chunks (see conv_igemm_simt)
 #pragma unroll
   for (int i = 0; i < TI; ++i)
 #pragma unroll
-    for (int j = 0; j < TO; ++j) acc[i][j] = 0.f;
+    for (int j = 0; j < TO; ++j) acc[i][j] = 0.0;
 
   for (int64_t mc = mbeg; mc < mend; mc += BK) {
     for (int e = tid; e < BK * BI; e += NT) {
@@ -247,6 +260,11 @@ conv_wgrad_simt(const ConvDev a, float* __restrict__ part, int pix_per_split) {
       Gs[kr][c] = v;
     }
     __syncthreads();
+    float blk[TI][TO];
+#pragma unroll
+    for (int i = 0; i < TI; ++i)
+#pragma unroll
+      for (int j = 0; j < TO; ++j) blk[i][j] = 0.f;
 #pragma unroll
     for (int kk = 0; kk < BK; ++kk) {
       float xv[TI], gv[TO];
@@ -257,8 +275,12 @@ conv_wgrad_simt(const ConvDev a, float* __restrict__ part, int pix_per_split) {
 #pragma unroll
       for (int i = 0; i < TI; ++i)
 #pragma unroll
-        for (int j = 0; j < TO; ++j) acc[i][j] = fmaf(xv[i], gv[j], acc[i][j]);
+        for (int j = 0; j < TO; ++j) blk[i][j] = fmaf(xv[i], gv[j], blk[i][j]);
     }
+#pragma unroll
+    for (int i = 0; i < TI; ++i)
+#pragma unroll
+      for (int j = 0; j < TO; ++j) acc[i][j] += (double)blk[i][j];
     __syncthreads();
   }
   float* out = part + ((int64_t)blockIdx.y * a.kh * a.kw + tap) * a.cin * a.cout;
@@ -269,7 +291,7 @@ conv_wgrad_simt(const ConvDev a, float* __restrict__ part, int pix_per_split) {
 #pragma unroll
     for (int j = 0; j < TO; ++j) {
       int co = co0 + to_ * TO + j;
-      if (co < a.cout) out[(int64_t)ci * a.cout + co] = acc[i][j];
+      if (co < a.cout) out[(int64_t)ci * a.cout + co] = (float)acc[i][j];
     }
   }
 }
@@ -284,11 +306,34 @@ __global__ void wgrad_reduce(const float* __restrict__ part, int splits, int tap
   int64_t t = i / cout;
   int ci = (int)(t % cin);
   int tap = (int)(t / cin);
-  float s = 0.f;
-  for (int k = 0; k < splits; ++k) s += part[(int64_t)k * total + i];
-  s *= alpha;
+  double sd = 0.0;                      // (also used by the tcgen05 wgrad kernels: fixed order, double)
+  for (int k = 0; k < splits; ++k) sd += (double)part[(int64_t)k * total + i];
+  float s = (float)sd * alpha;
   int64_t o = ((int64_t)co * cin + ci) * taps + tap;
   dw[o] = accumulate ? dw[o] + s : s;
+}
+
+// Same reduction with TWO destinations: output channels [0, split) go to d0, [split, cout) to d1; each destination is an
+// OIHW tensor with `ld` input channels of which this launch fills [ci0, ci0 + cin) - the weight gradients of two adjacent
+// dense-block layers computed as one 64-output-channel wgrad over their common input prefix (nn.py::_chain_backward).
+__global__ void wgrad_reduce_split(const float* __restrict__ part, int splits, int taps, int cin, int cout, int split,
+                                   float* __restrict__ d0, int ld0, int ci00, float* __restrict__ d1, int ld1, int ci01,
+                                   int accumulate, float alpha) {
+  int64_t total = (int64_t)taps * cin * cout;
+  int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= total) return;
+  int co = (int)(i % cout);
+  int64_t t = i / cout;
+  int ci = (int)(t % cin);
+  int tap = (int)(t / cin);
+  double sd = 0.0;
+  for (int k = 0; k < splits; ++k) sd += (double)part[(int64_t)k * total + i];
+  const float s = (float)sd * alpha;
+  float* dst = co < split ? d0 : d1;
+  if (dst == nullptr) return;
+  const int c = co < split ? co : co - split, ld = co < split ? ld0 : ld1, c0 = co < split ? ci00 : ci01;
+  const int64_t o = ((int64_t)c * ld + c0 + ci) * taps + tap;
+  dst[o] = accumulate ? dst[o] + s : s;
 }
 
 // db[c] (+)= sum_m G[m][c] : stage 1 partial column sums, stage 2 fixed-order reduce
@@ -355,13 +400,14 @@ colsum_partial_vec(const __nv_bfloat16* __restrict__ g, int ld, int64_t M, int c
 // block = 32 channels x 8 row lanes; each lane sums every 8th partial row, the lanes are then added in a fixed order
 // (deterministic; a single thread per channel walking up to 1024 rows took 50 us per launch)
 __global__ void __launch_bounds__(256)
-colsum_final(const float* __restrict__ part, int nparts, int c, float* __restrict__ out, int accumulate, float alpha) {
+colsum_final(const float* __restrict__ part, int nparts, int c, float* __restrict__ out, int accumulate, float alpha,
+             int ld) {
   __shared__ double red[8][33];
   const int cl = threadIdx.x & 31, rl = threadIdx.x >> 5;
   const int ch = blockIdx.x * 32 + cl;
   double s = 0.0;
   if (ch < c)
-    for (int k = rl; k < nparts; k += 8) s += (double)part[(int64_t)k * c + ch];
+    for (int k = rl; k < nparts; k += 8) s += (double)part[(int64_t)k * ld + ch];
   red[rl][cl] = s;
   __syncthreads();
   if (rl == 0 && ch < c) {
@@ -911,9 +957,25 @@ int wgrad_reduce_launch(const float* part, int splits, int taps, int cin, int co
 
 // fixed-order sum of `nparts` partial rows [nparts][c] -> out[c] (* alpha, optionally accumulated)
 int colsum_final_launch(const float* part, int nparts, int c, float* out, int accumulate, float alpha, cudaStream_t st) {
-  colsum_final<<<ceil_div(c, 32), 256, 0, st>>>(part, nparts, c, out, accumulate, alpha);
+  colsum_final<<<ceil_div(c, 32), 256, 0, st>>>(part, nparts, c, out, accumulate, alpha, c);
   count_launch();
   return check_launch("colsum_final");
+}
+
+// channels [0, c) of partial rows that are `ld` floats apart
+int colsum_final_ld_launch(const float* part, int nparts, int c, int ld, float* out, int accumulate, float alpha, cudaStream_t st) {
+  colsum_final<<<ceil_div(c, 32), 256, 0, st>>>(part, nparts, c, out, accumulate, alpha, ld);
+  count_launch();
+  return check_launch("colsum_final");
+}
+
+int wgrad_reduce_split_launch(const float* part, int splits, int taps, int cin, int cout, int split, float* d0, int ld0,
+                              int ci00, float* d1, int ld1, int ci01, int accumulate, float alpha, cudaStream_t st) {
+  int64_t total = (int64_t)taps * cin * cout;
+  wgrad_reduce_split<<<ceil_div(total, 256), 256, 0, st>>>(part, splits, taps, cin, cout, split, d0, ld0, ci00, d1, ld1, ci01,
+                                                           accumulate, alpha);
+  count_launch();
+  return check_launch("wgrad_reduce");
 }
 
 int bias_grad_launch(const void* dy, int dy_ld, int dtype, long long M, int cout, float* db, int accumulate,
@@ -926,7 +988,7 @@ int bias_grad_launch(const void* dy, int dy_ld, int dtype, long long M, int cout
     if (nb > 1024) nb = 1024;                 // the workspace holds 1024 partial rows (conv_wgrad_*_workspace)
     if (nb < 1) nb = 1;
     colsum_partial_vec<<<(unsigned)nb, 256, 0, st>>>(reinterpret_cast<const __nv_bfloat16*>(dy), dy_ld, M, cout, bpart);
-    colsum_final<<<ceil_div(cout, 32), 256, 0, st>>>(bpart, (int)nb, cout, db, accumulate, alpha);
+    colsum_final<<<ceil_div(cout, 32), 256, 0, st>>>(bpart, (int)nb, cout, db, accumulate, alpha, cout);
     count_launch(2);
     return check_launch("bias_grad");
   }
@@ -939,7 +1001,7 @@ int bias_grad_launch(const void* dy, int dy_ld, int dtype, long long M, int cout
   else
     colsum_partial<__nv_bfloat16><<<grid, blk, 0, st>>>(reinterpret_cast<const __nv_bfloat16*>(dy), dy_ld, M, cout,
                                                         bpart);
-  colsum_final<<<ceil_div(cout, 32), 256, 0, st>>>(bpart, ny, cout, db, accumulate, alpha);
+  colsum_final<<<ceil_div(cout, 32), 256, 0, st>>>(bpart, ny, cout, db, accumulate, alpha, cout);
   count_launch(2);
   return check_launch("bias_grad");
 }

@@ -2968,6 +2968,9 @@ int wgrad_reduce_launch(const float* part, int splits, int taps, int cin, int co
 int bias_grad_launch(const void* dy, int dy_ld, int dtype, long long M, int cout, float* db, int accumulate,
                      float alpha, void* ws, cudaStream_t st);
 int colsum_final_launch(const float* part, int nparts, int c, float* out, int accumulate, float alpha, cudaStream_t st);
+int colsum_final_ld_launch(const float* part, int nparts, int c, int ld, float* out, int accumulate, float alpha, cudaStream_t st);
+int wgrad_reduce_split_launch(const float* part, int splits, int taps, int cin, int cout, int split, float* d0, int ld0,
+                              int ci00, float* d1, int ld1, int ci01, int accumulate, float alpha, cudaStream_t st);
 
 bool conv_wgrad_tc_supported(const srcgan_conv_params* p) {
   if (p->dtype != SRCGAN_DT_BF16 || (p->stride != 1 && p->stride != 2) || p->upsample) return false;
@@ -3005,6 +3008,44 @@ size_t conv_wgrad_tc_workspace(const srcgan_conv_params* p) {
   }
   size_t wbytes = (size_t)splits * p->kh * p->kw * p->cin * p->cout * sizeof(float);
   return ((wbytes + 255) / 256) * 256 + (size_t)1024 * p->cout * sizeof(float) + 256;
+}
+
+// Weight gradients of TWO layers from one launch of the kw-stacked kernel: output channels [0, split) of dY belong to layer 0,
+// [split, cout) to layer 1; each destination is an OIHW gradient tensor with `ld` input channels of which [ci0, ci0 + cin)
+// are written.  Dense-block use (nn.py): conv_k and conv_(k+1) read the same input prefix and their dY slices are adjacent in
+// the gradient concat buffer, so their common part is ONE 64-output-channel wgrad (N = 192: the tensor pipe is 95-98 % active
+// and X is read once) instead of two 32-channel ones (N = 96: 62-68 %, X read twice).
+int conv_wgrad_tc_split(const srcgan_conv_params* p, float* dw0, int ld0, int ci00, float* db0, float* dw1, int ld1, int ci01,
+                        float* db1, int split, int accumulate, void* ws, size_t ws_bytes, cudaStream_t st) {
+  SRCGAN_REQUIRE(wgrad_stack_ok(p), "conv_wgrad_split: needs a 3x3 stride-1 pad-1 layer with 32 or 64 output channels");
+  SRCGAN_REQUIRE(split > 0 && split <= p->cout && (dw0 || dw1), "conv_wgrad_split: bad split %d", split);
+  SRCGAN_REQUIRE((!dw0 || (ld0 >= ci00 + p->cin && ci00 >= 0)) && (!dw1 || (ld1 >= ci01 + p->cin && ci01 >= 0)),
+                 "conv_wgrad_split: destination channel window out of range");
+  SRCGAN_REQUIRE(ws && ws_bytes >= conv_wgrad_tc_workspace(p), "conv_wgrad_split: workspace too small");
+  tcw4::Wg4Args a4;
+  tcw4::plan4(p, a4);
+  a4.n = p->n; a4.ho = p->ho; a4.wo = p->wo; a4.cin = p->cin; a4.cout = p->cout;
+  a4.part = reinterpret_cast<float*>(ws);
+  const size_t wbytes = (size_t)a4.splits * 9 * p->cin * p->cout * sizeof(float);
+  const bool want_db = db0 != nullptr || db1 != nullptr;
+  a4.dbpart = want_db ? reinterpret_cast<float*>(reinterpret_cast<char*>(ws) + ((wbytes + 255) / 256) * 256) : nullptr;
+  CUtensorMap tx, tg;
+  int rc = tcw4::make_tmap_box(&tx, p->x, p->cin, p->w, p->h, p->n, p->x_ld, 64, tcw4::WS_TW, tcw4::WS_X_ROWS,
+                               CU_TENSOR_MAP_SWIZZLE_128B, "conv_wgrad_split(x)");
+  if (rc) return rc;
+  const int bn = tcw4::bn4(p);
+  rc = tcw4::make_tmap_box(&tg, p->y, p->cout, p->wo, p->ho, p->n, p->y_ld, bn, tcw4::WS_G_W, tcw4::WS_TH,
+                           bn == 64 ? CU_TENSOR_MAP_SWIZZLE_128B : CU_TENSOR_MAP_SWIZZLE_64B, "conv_wgrad_split(dy)");
+  if (rc) return rc;
+  rc = bn == 64 ? tcw4::launch4<64>(tx, tg, a4, st) : tcw4::launch4<32>(tx, tg, a4, st);
+  if (rc) return rc;
+  rc = wgrad_reduce_split_launch(reinterpret_cast<const float*>(ws), a4.splits, 9, p->cin, p->cout, split, dw0, ld0, ci00, dw1,
+                                 ld1, ci01, accumulate, p->alpha, st);
+  if (rc) return rc;
+  if (db0) { rc = colsum_final_ld_launch(a4.dbpart, a4.splits, split, p->cout, db0, accumulate, p->alpha, st); if (rc) return rc; }
+  if (db1 && split < p->cout)
+    return colsum_final_ld_launch(a4.dbpart + split, a4.splits, p->cout - split, p->cout, db1, accumulate, p->alpha, st);
+  return SRCGAN_OK;
 }
 
 int conv_wgrad_tc(const srcgan_conv_params* p, float* dw, float* db, int accumulate, void* ws, size_t ws_bytes,

@@ -197,7 +197,11 @@ class _Packs:
 
 
 def _alt_order() -> bool:
-    return not os.environ.get("SRCGAN_B200_NO_ALT_ORDER")
+    """Every second layer of a dense block walks the images backwards (SRCGAN_CONV_FLAG_REVERSE) so that it starts on what the
+    previous layer touched last.  Measured on B200 (scripts/exp/rdb_order.py, profiles/r2_rdb_order.txt): 1.836 vs 1.831 ms per
+    dense block, 219.4 vs 218.2 patches/s for the step - the 126 MB L2 does not hold enough of a 1.6 GB concat buffer for
+    the order to matter.  Off by default; SRCGAN_B200_ALT_ORDER=1 enables it."""
+    return bool(os.environ.get("SRCGAN_B200_ALT_ORDER"))
 
 
 def _batched_ok(cout: int, ksize: int) -> bool:
@@ -638,10 +642,28 @@ class _RRDBGenerator(_NetBase):
             from . import engine as _engine
             fused_db = all(_engine.select_wgrad(nf + gc * (k - 1), gc if k < 5 else nf, 3, 1, False, dt, h, w) == ops.ENGINE_TC
                            for k in range(1, 6)) and all(W(c.weight) == W(c.bias) for c in convs)
-            for k in range(1, 5):
-                c = convs[k - 1]
-                self._wgrad(c, Slice(C, 0, nf + gc * (k - 1)), Slice(D, nf + gc * (4 - k), gc), sink, W(c.weight),
-                            fused_db and W(c.bias))
+            paired = (fused_db and dt == torch.bfloat16 and gc == 32 and nf == 64 and not os.environ.get("SRCGAN_B200_NO_WGRAD_PAIRS")
+                      and all(W(c.weight) and c.bias is not None and W(c.bias) for c in convs[:4]))
+            if paired:
+                # conv_k and conv_(k+1) read the same input prefix and their dY slices are neighbours in D ([.. dZ_(k+1) | dZ_k ..]):
+                # the common part is ONE 64-output-channel wgrad (N = 192: tensor pipe 95-98 % active, X read once; the
+                # 32-channel launches run at N = 96, 62-68 %), plus a 32 -> 32 launch for conv_(k+1)'s own 32 input channels.
+                for ka in (1, 3):
+                    ca, cb = convs[ka - 1], convs[ka]
+                    cin_a, d0 = nf + gc * (ka - 1), nf + gc * (3 - ka)          # common prefix; first channel of dZ_(ka+1) in D
+                    dwa, acc_a = sink.slot(ca.weight, True)
+                    dba, _ = sink.slot(ca.bias, True)
+                    dwb, acc_b = sink.slot(cb.weight, True)
+                    dbb, _ = sink.slot(cb.bias, True)
+                    if acc_a != acc_b:
+                        raise RuntimeError("inconsistent accumulate state of a dense-block layer pair")
+                    ops.conv_wgrad_split(Slice(C, 0, cin_a), Slice(D, d0, 2 * gc), (dwb, 0, dbb), (dwa, 0, dba), gc, accumulate=acc_a)
+                    ops.conv_wgrad_split(Slice(C, cin_a, gc), Slice(D, d0, gc), (dwb, cin_a, None), None, gc, accumulate=acc_a)
+            else:
+                for k in range(1, 5):
+                    c = convs[k - 1]
+                    self._wgrad(c, Slice(C, 0, nf + gc * (k - 1)), Slice(D, nf + gc * (4 - k), gc), sink, W(c.weight),
+                                fused_db and W(c.bias))
             self._wgrad(convs[4], Slice(C), Slice(D, 0, nf), sink, W(convs[4].weight), fused_db and W(convs[4].bias), alpha=s5)
             # all five bias gradients = column sums of the gradient concat buffer, one pass
             if not fused_db and any(W(c.bias) for c in convs):

@@ -268,6 +268,31 @@ def conv_wgrad(x: Slice, dy: Slice, dw: Optional[torch.Tensor], db: Optional[tor
                                          ws.data_ptr(), ws.numel(), _stream()), "conv_wgrad")
 
 
+def conv_wgrad_split(x: Slice, dy: Slice, dest0, dest1, split: int, *, accumulate: bool = False, alpha: float = 1.0) -> None:
+    """One launch of the kw-stacked tcgen05 wgrad kernel (3x3 stride 1 pad 1), two destinations: output channels [0, split) of
+    ``dy`` -> dest0, the rest -> dest1.  dest = (dw, ci0, db) or None: ``dw`` an fp32 OIHW gradient tensor whose input channels
+    [ci0, ci0 + x.c) are written, ``db`` the bias gradient of those output channels or None."""
+    _require_cuda(x.buf, "conv input")
+    p = _conv_params(x.n, x.h, x.w, x.c, dy.c, 3, 1, 1, False, dy.h, dy.w, x.dtype, ENGINE_TC)
+    p.x, p.x_ld, p.y, p.y_ld = x.ptr, x.ld, dy.ptr, dy.ld
+    p.alpha = float(alpha)
+    args = []
+    for d, co in ((dest0, split), (dest1, dy.c - split)):
+        if d is None:
+            args += [None, 0, 0, None]
+            continue
+        dw, ci0, db = d
+        assert dw.dtype == torch.float32 and dw.is_contiguous() and dw.shape[0] == co and dw.shape[2:] == (3, 3), tuple(dw.shape)
+        assert 0 <= ci0 and ci0 + x.c <= dw.shape[1]
+        assert db is None or (db.dtype == torch.float32 and db.is_contiguous() and db.numel() == co)
+        args += [dw.data_ptr(), dw.shape[1], ci0, db.data_ptr() if db is not None else None]
+    lib = _lib.load()
+    ws = workspace(lib.srcgan_conv_wgrad_workspace_bytes(C.byref(p)), x.buf.device)
+    with _Timed("wgrad", p):
+        _lib.check(lib.srcgan_conv_wgrad_split(C.byref(p), *args, int(split), int(accumulate), ws.data_ptr(), ws.numel(), _stream()),
+                   "conv_wgrad_split")
+
+
 # ------------------------------------------------------------------------------------------
 # glue
 # ------------------------------------------------------------------------------------------

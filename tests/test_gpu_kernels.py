@@ -528,6 +528,36 @@ def test_conv_wgrad_tc_matches_reference(case):
     assert relerr(dw.cpu(), 1.5 * wt.grad) < 5e-3
 
 
+@pytest.mark.parametrize("ka", [1, 3])
+def test_conv_wgrad_split_pairs_dense_block_layers(ka):
+    """srcgan_conv_wgrad_split: the weight / bias gradients of conv_k and conv_(k+1) of a dense block from one 64-output-channel
+    launch over their common input prefix + one 32 -> 32 launch, against two ordinary launches (and torch on the CPU)."""
+    from srcgan_b200 import ops
+    n, h, w, nf, gc = 2, 40, 52, 64, 32
+    cin_a, d0 = nf + gc * (ka - 1), nf + gc * (3 - ka)
+    Cb = (torch.rand((n, h, w, 192), generator=torch.Generator().manual_seed(71)) - 0.5).to(torch.bfloat16).to(DEV)
+    Db = (torch.rand((n, h, w, 192), generator=torch.Generator().manual_seed(72)) - 0.5).to(torch.bfloat16).to(DEV)
+    ref = {}
+    for name, cin, dch in (("a", cin_a, d0 + gc), ("b", cin_a + gc, d0)):
+        dw, db = torch.empty((gc, cin, 3, 3), device=DEV), torch.empty((gc,), device=DEV)
+        ops.conv_wgrad(ops.Slice(Cb, 0, cin), ops.Slice(Db, dch, gc), dw, db, 3, 1, 1, engine=ops.ENGINE_TC)
+        ref[name] = (dw, db)
+    for acc in (False, True):
+        dwa, dba = torch.full((gc, cin_a, 3, 3), 0.25, device=DEV), torch.full((gc,), 0.25, device=DEV)
+        dwb, dbb = torch.full((gc, cin_a + gc, 3, 3), 0.25, device=DEV), torch.full((gc,), 0.25, device=DEV)
+        ops.conv_wgrad_split(ops.Slice(Cb, 0, cin_a), ops.Slice(Db, d0, 2 * gc), (dwb, 0, dbb), (dwa, 0, dba), gc, accumulate=acc)
+        ops.conv_wgrad_split(ops.Slice(Cb, cin_a, gc), ops.Slice(Db, d0, gc), (dwb, cin_a, None), None, gc, accumulate=acc)
+        off = 0.25 if acc else 0.0
+        assert relerr((dwa - off).cpu(), ref["a"][0].cpu()) < 1e-4 and relerr((dba - off).cpu(), ref["a"][1].cpu()) < 1e-4
+        assert relerr((dwb - off).cpu(), ref["b"][0].cpu()) < 1e-4 and relerr((dbb - off).cpu(), ref["b"][1].cpu()) < 1e-4
+    # and against torch
+    x = Cb[..., :cin_a + gc].float().permute(0, 3, 1, 2).cpu()
+    wt = torch.zeros(gc, cin_a + gc, 3, 3, requires_grad=True)
+    gy = Db[..., d0:d0 + gc].float().permute(0, 3, 1, 2).cpu()
+    F.conv2d(x, wt, None, padding=1).backward(gy)
+    assert relerr(dwb.cpu() - 0.25, wt.grad) < 5e-3
+
+
 @pytest.mark.parametrize("env", [{}, {"SRCGAN_B200_WSTACK32": "1"}, {"SRCGAN_B200_NO_WSTACK": "1"}])
 def test_conv_wgrad_tc_variants(env, monkeypatch):
     """kw-stacked wgrad as N = 192 (default for 64 output channels), as two N = 96 halves, and the per-tap halo kernel all
