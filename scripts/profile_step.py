@@ -1,28 +1,53 @@
-"""torch.profiler view of one batch-64 step: top CUDA kernels by device time."""
-import sys, os, random
+"""torch.profiler (CUPTI) view of ONE batch-64 G+D step: every CUDA kernel with its launch count and device time, the sum of
+device time against the step's wall time (idle share), and the ATen kernels that are still on the path.
+python scripts/profile_step.py [batch] > gpurun_out/profile_step.txt"""
+import os
+import sys
+import time
+
 sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
-import torch, torch.nn.functional as F
-from torch.profiler import profile, ProfilerActivity
-from oracle import srcgan_oracle as O
+import torch
+import torch.nn.functional as F
+from torch.profiler import ProfilerActivity, profile
+
 from srcgan_b200 import nn as snn, trainer
+
 B = int(sys.argv[1]) if len(sys.argv) > 1 else 64
 snn.set_precision("bf16")
-opt = trainer.params(); opt.device = torch.device("cuda:0"); opt.mode, opt.net = "x4", "1"
+opt = trainer.params()
+opt.device = torch.device("cuda:0")
+opt.mode, opt.net = "x4", "1"
+torch.manual_seed(0)
 m = trainer.SRCycleGAN(opt)
-st = O.default_states(0)
-for n in ("G_A", "G_B", "D_A", "D_B"):
-    getattr(m, "net" + n).load_state_dict(st[n])
-rb = torch.rand(B, 3, 256, 256, device="cuda"); ra = F.interpolate(rb, scale_factor=0.25)
-for _ in range(2):
+rb = torch.rand(B, 3, 256, 256, device="cuda")
+ra = F.interpolate(rb, scale_factor=0.25)
+for _ in range(3):
     m.optimize_parameters(ra, rb)
 torch.cuda.synchronize()
-with profile(activities=[ProfilerActivity.CUDA, ProfilerActivity.CPU]) as prof:
+t0 = time.perf_counter()
+m.optimize_parameters(ra, rb)
+torch.cuda.synchronize()
+wall_plain = (time.perf_counter() - t0) * 1e3
+with profile(activities=[ProfilerActivity.CUDA]) as prof:
+    t0 = time.perf_counter()
     m.optimize_parameters(ra, rb)
     torch.cuda.synchronize()
-rows = [(e.key, e.count, e.device_time_total if hasattr(e, "device_time_total") else e.cuda_time_total) for e in prof.key_averages()]
+    wall = (time.perf_counter() - t0) * 1e3
+rows = [(e.key, e.count, getattr(e, "device_time_total", None) or getattr(e, "cuda_time_total", 0)) for e in prof.key_averages()]
 rows = [r for r in rows if r[2] > 0]
 tot = sum(r[2] for r in rows)
 rows.sort(key=lambda r: -r[2])
-print("total device time (us):", tot)
-for k, c, t in rows[:40]:
-    print("%-80s %6d %10.0f %6.2f%%" % (k[:80], c, t, 100 * t / tot))
+ours = ("conv", "bn_", "gn_", "loss_", "ssim", "eval_metrics", "colsum", "wgrad", "pack_weights", "nchw", "nhwc", "upsample", "add_", "act_bwd",
+        "rgb2lab", "lab2rgb", "thin_", "d2s", "pixel_shuffle", "minmax", "ae_kernel", "tc::", "tcw")
+mine = [r for r in rows if any(k in r[0] for k in ours)]
+aten = [r for r in rows if r not in mine]
+print("batch %d: wall %.1f ms (%.1f ms under the profiler), kernels %d launches, device time %.1f ms = %.1f %% of the wall time" % (
+    B, wall_plain, wall, sum(r[1] for r in rows), tot / 1e3, tot / 1e3 / wall_plain * 100))
+print("this library: %d launches, %.1f ms;  ATen / NCCL / memcpy: %d launches, %.1f ms" % (
+    sum(r[1] for r in mine), sum(r[2] for r in mine) / 1e3, sum(r[1] for r in aten), sum(r[2] for r in aten) / 1e3))
+print("\n%-90s %7s %10s %7s" % ("kernel", "count", "us", "share"))
+for k, c, t in rows[:45]:
+    print("%-90s %7d %10.0f %6.2f%%" % (k[:90], c, t, 100 * t / tot))
+print("\nATen / other kernels still on the path:")
+for k, c, t in aten[:25]:
+    print("%-90s %7d %10.0f %6.2f%%" % (k[:90], c, t, 100 * t / tot))

@@ -8,6 +8,7 @@ import sys
 
 ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 tag = sys.argv[1] if len(sys.argv) > 1 else "r2a"
+ncu_tag = sys.argv[2] if len(sys.argv) > 2 else tag      # the ncu capture may come from an earlier call than the event timing
 peak = json.load(open(os.path.join(ROOT, "MEASURED_PEAKS.json")))["hbm_gbs"]
 out = []
 out.append("HBM-bound kernels of the step, round 2 (%s).  Peak = measured copy bandwidth %.0f GB/s (MEASURED_PEAKS.json)." % (tag, peak))
@@ -19,12 +20,12 @@ out.append("%-66s %9s %9s %6s %s" % ("op", "ms", "GB/s", "frac", "launches"))
 for line in open(os.path.join(ROOT, "gpurun_out", tag + "_hbm.json")):
     d = json.loads(line)
     out.append("%-66s %9.3f %9.0f %6.2f %d" % (d["op"][:66], d["ms"], d["gbs"], d["frac_of_copy_bw"], d["launches"]))
-path = os.path.join(ROOT, "gpurun_out", tag + "_hbm_ncu.csv")
+path = os.path.join(ROOT, "gpurun_out", ncu_tag + "_hbm_ncu.csv")
 if os.path.isfile(path):
     rows = list(csv.reader(open(path)))
     hdr = {h: i for i, h in enumerate(rows[0])}
     out.append("")
-    out.append("B. ncu --set full --clock-control none, the same script with --once --n 16 (second launch of each kernel shown); dram")
+    out.append("B. ncu --set full --clock-control none (call %s), the same script with --once --n 16 (second launch of each kernel shown); dram" % ncu_tag)
     out.append("   GB/s = (dram__bytes_read.sum + dram__bytes_write.sum) / gpu__time_duration.sum; cold-cache, serialised launches.")
     out.append("")
     out.append("%-40s %14s %9s %9s %9s %9s %7s %7s" % ("kernel", "grid", "us", "rd MB", "wr MB", "dram GB/s", "of peak", "warps%"))

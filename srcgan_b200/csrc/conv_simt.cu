@@ -622,10 +622,13 @@ struct ThinArgs {
 };
 constexpr int THIN_TH = 8, THIN_TW = 32;
 
-template <typename T, int KH, int KW>
+// FRN = filter rows handled by one launch, starting at fr_begin: a 7x7 filter (ResDeconv's stem, src/model/resdeconv.py) would
+// need 49 x 4 accumulators per thread, so it runs as seven launches of one filter row each (the wide tensor is re-read seven
+// times: 0.9 GB at batch 64, against 9 ms per launch of the generic FFMA wgrad it replaces).
+template <typename T, int KH, int KW, int FRN>
 __global__ void __launch_bounds__(256)
-thin_wgrad_kernel(const ThinArgs a, float* __restrict__ part) {
-  constexpr int TAPS = KH * KW;
+thin_wgrad_kernel(const ThinArgs a, float* __restrict__ part, int fr_begin) {
+  constexpr int TAPS = KH * KW, NACC = FRN * KW;
   constexpr int TTH = 2 * (THIN_TH - 1) + KH, TTW = 2 * (THIN_TW - 1) + KW;   // sized for ts = 2
   __shared__ float4 st[TTH][TTW];
   const int t = threadIdx.x, c = t & 63, g = t >> 6;
@@ -635,9 +638,9 @@ thin_wgrad_kernel(const ThinArgs a, float* __restrict__ part) {
   const int tth = a.ts * (THIN_TH - 1) + KH, ttw = a.ts * (THIN_TW - 1) + KW;
   const int omin_y = a.sign > 0 ? -a.pad : -(KH - 1 - a.pad);
   const int omin_x = a.sign > 0 ? -a.pad : -(KW - 1 - a.pad);
-  float acc[TAPS][4];
+  float acc[NACC][4];
 #pragma unroll
-  for (int i = 0; i < TAPS; ++i) { acc[i][0] = acc[i][1] = acc[i][2] = acc[i][3] = 0.f; }
+  for (int i = 0; i < NACC; ++i) { acc[i][0] = acc[i][1] = acc[i][2] = acc[i][3] = 0.f; }
 
   for (long long tile = blockIdx.x; tile < a.num_tiles; tile += gridDim.x) {
     long long r = tile;
@@ -671,13 +674,14 @@ thin_wgrad_kernel(const ThinArgs a, float* __restrict__ part) {
         const int x = x0 + lx;
         const float wv = x < a.ww ? to_f32(wrow[(long long)x * a.wide_ld]) : 0.f;
 #pragma unroll
-        for (int fr = 0; fr < KH; ++fr) {
+        for (int f = 0; f < FRN; ++f) {
+          const int fr = fr_begin + f;
           const int ry = a.ts * ly + (a.sign > 0 ? fr : KH - 1 - fr);
 #pragma unroll
           for (int fs = 0; fs < KW; ++fs) {
             const int rx = a.ts * lx + (a.sign > 0 ? fs : KW - 1 - fs);
             const float4 tv = st[ry][rx];
-            float* ac = acc[fr * KW + fs];
+            float* ac = acc[f * KW + fs];
             ac[0] = fmaf(wv, tv.x, ac[0]); ac[1] = fmaf(wv, tv.y, ac[1]);
             ac[2] = fmaf(wv, tv.z, ac[2]); ac[3] = fmaf(wv, tv.w, ac[3]);
           }
@@ -689,9 +693,9 @@ thin_wgrad_kernel(const ThinArgs a, float* __restrict__ part) {
   // part[block][tap][cw][4]
   __syncthreads();
   float4* red = &st[0][0];                       // TTH*TTW float4 >= 3*64 entries
-  float4* out = reinterpret_cast<float4*>(part) + ((long long)blockIdx.x * TAPS) * a.cw + c0 + c;
+  float4* out = reinterpret_cast<float4*>(part) + ((long long)blockIdx.x * TAPS + fr_begin * KW) * a.cw + c0 + c;
 #pragma unroll
-  for (int i = 0; i < TAPS; ++i) {
+  for (int i = 0; i < NACC; ++i) {
     if (g > 0) red[(g - 1) * 64 + c] = make_float4(acc[i][0], acc[i][1], acc[i][2], acc[i][3]);
     __syncthreads();
     if (g == 0) {
@@ -840,7 +844,8 @@ static void wgrad_plan(const srcgan_conv_params* p, int& bi, int& bo, int& split
 }
 
 static bool thin_wgrad_ok(const srcgan_conv_params* p) {
-  if (p->upsample || p->kh != p->kw || (p->kh != 3 && p->kh != 4)) return false;
+  if (p->upsample || p->kh != p->kw || (p->kh != 3 && p->kh != 4 && p->kh != 7)) return false;
+  if (p->kh == 7) return p->cin <= 4 && p->cout % 64 == 0 && (p->stride == 1 || p->stride == 2);   // case B only
   if (p->cout <= 4 && p->cin % 64 == 0 && p->stride == 1) return true;                       // case A
   if (p->cin <= 4 && p->cout % 64 == 0 && (p->stride == 1 || p->stride == 2)) return true;   // case B
   return false;
@@ -886,8 +891,14 @@ static int launch_thin_wgrad(const srcgan_conv_params* p, float* dw, int accumul
   int grid = thin_grid(p, a.num_tiles, a.tiles_x, a.tiles_y);
   float* part = reinterpret_cast<float*>(ws);
   dim3 g(grid, a.cw / 64);
-  if (p->kh == 3) thin_wgrad_kernel<T, 3, 3><<<g, 256, 0, st>>>(a, part);
-  else thin_wgrad_kernel<T, 4, 4><<<g, 256, 0, st>>>(a, part);
+  int nk = 1;
+  if (p->kh == 3) thin_wgrad_kernel<T, 3, 3, 3><<<g, 256, 0, st>>>(a, part, 0);
+  else if (p->kh == 4) thin_wgrad_kernel<T, 4, 4, 4><<<g, 256, 0, st>>>(a, part, 0);
+  else {
+    nk = 7;
+    for (int fr = 0; fr < 7; ++fr) thin_wgrad_kernel<T, 7, 7, 1><<<g, 256, 0, st>>>(a, part, fr);
+  }
+  count_launch(nk - 1);
   const int taps = p->kh * p->kw;
   long long total = (long long)taps * a.cw * a.kt;
   thin_wgrad_reduce<<<ceil_div(total, 128), 128, 0, st>>>(part, grid, taps, a.cw, a.kt, case_a ? 1 : 0, dw,

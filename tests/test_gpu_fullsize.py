@@ -78,7 +78,8 @@ def test_full_size_step_matches_the_oracle(oracle_step, precision):
     pre-activation lies within rounding of zero flip under any change of summation order or precision, and a flipped gate
     changes that pixel's contribution by 80 % - so every floating-point evaluation, the reference's own included, carries a
     noise floor that is measured here and used as the yardstick:
-      fp32: error against an fp64 evaluation of the oracle; must stay within 2x the REFERENCE's own fp32 error per tensor;
+      fp32: error against an fp64 evaluation of the oracle; >= 99.5 % of all gradient elements within 1e-3 of their tensor's
+            maximum, median tensor error <= 1.2e-3, every tensor within 3x the REFERENCE's own fp32 error;
       bf16: error against the fp32 oracle; must stay within 1.5x what STOCK PyTorch bf16 autocast (cuDNN) shows on the same
             step, same weights, same inputs."""
     from oracle import srcgan_oracle as O
@@ -145,14 +146,20 @@ def test_full_size_step_matches_the_oracle(oracle_step, precision):
             assert v["snr_cuda_vs_oracle_db"] > 80.0, (name, v)                                  # 1e-4 of the image norm
     # 3. every parameter gradient against the measured noise floor.  Measured on B200 (profiles/r2_fullsize_parity_*.json):
     #    bf16: median L2 error 0.149 against the fp32 oracle - stock bf16 autocast 0.146 (cosines 0.9896 / 0.9900);
-    #    fp32: median 2.7e-3 against the fp64 oracle - the reference's own fp32 arithmetic 1.3e-3 (worst 1.3e-2 / 5.2e-3).
+    #    fp32: median 9.1e-4 / worst 3.4e-3 against the fp64 oracle, 99.8 % of the elements within 1e-3 - the reference's own
+    #          fp32 arithmetic: 1.3e-3 / 5.2e-3, 99.0 % (before the two-level accumulation of csrc/conv_simt.cu the CUDA fp32
+    #          engine stood at 2.7e-3 / 1.3e-2, 93.6 %).
     for k, v in ours.items():
         y = yard[k]
-        assert v["l2"] <= max(5e-2 if bf else 3e-3, (2.5 if bf else 3.0) * y["l2"]), (k, v, y)
+        assert v["l2"] <= max(5e-2 if bf else 4e-3, (2.5 if bf else 3.0) * y["l2"]), (k, v, y)
     so, sy = _summary(ours), _summary(yard)
-    assert so["median_l2"] <= (1.15 if bf else 2.5) * sy["median_l2"] + 1e-4, (so, sy)
+    assert so["median_l2"] <= (1.15 if bf else 1.1) * sy["median_l2"] + 1e-4, (so, sy)
     assert so["median_cos"] >= sy["median_cos"] - (5e-3 if bf else 1e-5), (so, sy)
-    assert so["frac_elements_within_1e-3_of_tensor_max"] >= sy["frac_elements_within_1e-3_of_tensor_max"] - 0.08, (so, sy)
+    if bf:
+        assert so["frac_elements_within_1e-3_of_tensor_max"] >= sy["frac_elements_within_1e-3_of_tensor_max"] - 0.03, (so, sy)
+    else:   # north_star: fp32 gradients within 1e-3 - element by element against the fp64 truth
+        assert so["frac_elements_within_1e-3_of_tensor_max"] >= 0.995, so
+        assert so["median_l2"] <= 1.2e-3, so
     if not bf:      # discriminator gradients are well conditioned: north_star's 1e-3 holds outright
         for k, v in ours.items():
             if k.startswith("D_"):

@@ -44,6 +44,8 @@ CONV_CASES = [
     (2, 8, 8, 256, 1, 4, 1, 1, False),
     (1, 16, 16, 128, 128, 3, 2, 1, False),
     (1, 15, 13, 128, 256, 3, 2, 1, False),
+    (2, 20, 18, 3, 64, 7, 2, 3, False),      # ResDeconv's stem (resdeconv.py): thin 7x7 wgrad in seven filter-row launches
+    (1, 40, 70, 1, 64, 7, 2, 3, False),
 ]
 
 
