@@ -111,6 +111,12 @@ typedef struct srcgan_conv_params {
      data the previous one touched last, i.e. on what the 126 MB L2 still holds.  Results do not depend on it beyond the
      fp32 summation order of a few columns (each setting is bit-reproducible). */
   int32_t flags;
+  /* Planar concat buffers (paired-sweep fprop kernel only): x points at group 0 of a buffer laid out [group][n][h][w][64
+     channels] (x_ld = 64); channel c of the slice lives in group c / 64, x_group_stride ELEMENTS further per group.  0 =
+     ordinary interleaved NHWC.  A dense block's 192-channel concat buffer as three such groups turns the 64-byte slice writes
+     at a 384-byte pitch (28 % slower on 64->32) into writes at a 128-byte pitch.  Outputs and side operands
+     never span groups, so they stay (pointer, ld). */
+  int64_t x_group_stride;
 } srcgan_conv_params;
 #define SRCGAN_CONV_FLAG_REVERSE 1
 

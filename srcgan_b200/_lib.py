@@ -36,6 +36,7 @@ class ConvParams(C.Structure):
         ("mask", C.c_void_p), ("mask_ld", C.c_int32), ("mask_slope", C.c_float),
         ("signbits", C.c_void_p), ("maskbits", C.c_void_p),
         ("zero_row_period", C.c_int32), ("flags", C.c_int32),
+        ("x_group_stride", C.c_int64),
     ]
 
 

@@ -147,8 +147,9 @@ int srcgan_conv_fprop(const srcgan_conv_params* p, void* stream) {
     SRCGAN_REQUIRE(conv_tc_supported(p), "conv_fprop: shape not supported by the tcgen05 engine");
     return conv_fprop_tc(p, (cudaStream_t)stream);
   }
-  if (p->signbits || p->maskbits || p->zero_row_period) {
-    set_error("conv_fprop: packed sign / mask bits and zero_row_period are only implemented by the paired-sweep tcgen05 kernel");
+  if (p->signbits || p->maskbits || p->zero_row_period || p->x_group_stride) {
+    set_error("conv_fprop: packed sign / mask bits, zero_row_period and planar inputs are only implemented by the paired-sweep "
+              "tcgen05 kernel");
     return SRCGAN_E_INVALID;
   }
   return conv_fprop_simt(p, (cudaStream_t)stream);
@@ -157,8 +158,9 @@ int srcgan_conv_fprop(const srcgan_conv_params* p, void* stream) {
 int srcgan_conv_dgrad(const srcgan_conv_params* p, void* stream) {
   int rc = validate_conv(p, true);
   if (rc) return rc;
-  if (p->signbits || p->maskbits || p->zero_row_period) {
-    set_error("conv_dgrad: packed sign / mask bits and zero_row_period are only implemented by the paired-sweep fprop kernel");
+  if (p->signbits || p->maskbits || p->zero_row_period || p->x_group_stride) {
+    set_error("conv_dgrad: packed sign / mask bits, zero_row_period and planar inputs are only implemented by the paired-sweep "
+              "fprop kernel");
     return SRCGAN_E_INVALID;
   }
   if (p->engine == SRCGAN_ENGINE_TC) {
@@ -181,6 +183,7 @@ int srcgan_conv_wgrad(const srcgan_conv_params* p, float* dw, float* db, int acc
   int rc = validate_conv(p, false);
   if (rc) return rc;
   SRCGAN_REQUIRE(dw || db, "conv_wgrad: nothing to compute");
+  SRCGAN_REQUIRE(p->x_group_stride == 0, "conv_wgrad: planar inputs are passed one 64-channel group at a time");
   int engine = p->engine;
   if (engine == SRCGAN_ENGINE_AUTO) engine = conv_wgrad_tc_supported(p) ? SRCGAN_ENGINE_TC : SRCGAN_ENGINE_SIMT;
   if (engine == SRCGAN_ENGINE_TC) {
@@ -197,6 +200,7 @@ int srcgan_conv_wgrad_split(const srcgan_conv_params* p, float* dw0, int cin_ld0
   if (rc) return rc;
   SRCGAN_REQUIRE(p->engine == SRCGAN_ENGINE_TC && conv_wgrad_tc_supported(p),
                  "conv_wgrad_split: tcgen05 engine only (bf16, 3x3 stride 1)");
+  SRCGAN_REQUIRE(p->x_group_stride == 0, "conv_wgrad_split: planar inputs are passed one 64-channel group at a time");
   return conv_wgrad_tc_split(p, dw0, cin_ld0, ci0_0, db0, dw1, cin_ld1, ci0_1, db1, split_cout, accumulate, workspace,
                              workspace_bytes, (cudaStream_t)stream);
 }

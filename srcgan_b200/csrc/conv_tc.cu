@@ -1110,6 +1110,7 @@ struct Sw2Args {
   uint32_t* signbits;                   // OUT [pixel][BN/32]: bit = stored value > 0 (the mask of the matching backward step)
   const uint32_t* maskbits;             // IN  [pixel][BN/32]: replaces `mask` (4 bytes instead of 64 per pixel and 32 channels)
   int zero_period;                      // > 0: image rows with row % zero_period == 0 are stored as zeros ("tall image" separators)
+  int planar;                           // 1: x is a planar concat buffer [group][n][h][w][64]: tmap_x is 5-D, K chunk k = group k
   int rev;                              // 1: work units in descending order (last image first): the layer then starts on the data the
                                         //    previous layer of a dense block touched last, which is what still sits in the 126 MB L2
   int dbg;
@@ -1143,6 +1144,19 @@ __device__ __forceinline__ void tma_load_4d_pair(const CUtensorMap* map, uint64_
   asm volatile(
       "cp.async.bulk.tensor.4d.cta_group::2.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4, %5, %6}], [%2];"
       ::"r"(smem_u32(dst)), "l"(map), "r"(smem_u32(bar) & PEER_MASK), "r"(c0), "r"(c1), "r"(c2), "r"(c3)
+      : "memory");
+}
+// 5-D forms for planar concat buffers ([group][n][h][w][64 ch]: coordinate 4 = the 64-channel group = the K chunk)
+__device__ __forceinline__ void tma_load_5d(const CUtensorMap* map, uint64_t* bar, void* dst, int c0, int c1, int c2, int c3, int c4) {
+  asm volatile(
+      "cp.async.bulk.tensor.5d.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4, %5, %6, %7}], [%2];"
+      ::"r"(smem_u32(dst)), "l"(map), "r"(smem_u32(bar)), "r"(c0), "r"(c1), "r"(c2), "r"(c3), "r"(c4)
+      : "memory");
+}
+__device__ __forceinline__ void tma_load_5d_pair(const CUtensorMap* map, uint64_t* bar, void* dst, int c0, int c1, int c2, int c3, int c4) {
+  asm volatile(
+      "cp.async.bulk.tensor.5d.cta_group::2.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4, %5, %6, %7}], [%2];"
+      ::"r"(smem_u32(dst)), "l"(map), "r"(smem_u32(bar) & PEER_MASK), "r"(c0), "r"(c1), "r"(c2), "r"(c3), "r"(c4)
       : "memory");
 }
 __device__ __forceinline__ void tma_prefetch_4d(const CUtensorMap* map, int c0, int c1, int c2, int c3) {
@@ -1346,10 +1360,12 @@ conv3x3_sweep2_tc(const __grid_constant__ CUtensorMap tmap_x, const Sw2Args a) {
               if (rank == 0) mbar_arrive(&a_full[as]);
             } else if (CG == 1) {
               mbar_expect_tx(&a_full[as], SW_SLAB_BYTES);
-              tma_load_4d(&tmap_x, &a_full[as], dst, k * KCH, c, y0 - 1, img);
+              if (a.planar) tma_load_5d(&tmap_x, &a_full[as], dst, 0, c, y0 - 1, img, k);
+              else tma_load_4d(&tmap_x, &a_full[as], dst, k * KCH, c, y0 - 1, img);
             } else {
               if (rank == 0) mbar_expect_tx(&a_full[as], 2 * SW_SLAB_BYTES);
-              tma_load_4d_pair(&tmap_x, &a_full[as], dst, k * KCH, c, y0 - 1, img);
+              if (a.planar) tma_load_5d_pair(&tmap_x, &a_full[as], dst, 0, c, y0 - 1, img, k);
+              else tma_load_4d_pair(&tmap_x, &a_full[as], dst, k * KCH, c, y0 - 1, img);
             }
           }
           __syncwarp();
@@ -1728,6 +1744,35 @@ static int make_tmap(CUtensorMap* tm, const void* ptr, int c, int w, int h, int 
                        CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
   if (cr != CUDA_SUCCESS) {
     set_error("%s: cuTensorMapEncodeTiled failed with CUresult %d", what, (int)cr);
+    return SRCGAN_E_CUDA;
+  }
+  return SRCGAN_OK;
+}
+
+// Planar concat buffer [groups][n][h][w][64 ch] (group g at ptr + g * group_stride elements, pixel pitch ld = 64) -> 5-D tensor
+// map whose box is one sweep slab [rows lanes][64 ch] of one group; coordinate order (ch, lane-or-sweep, sweep-or-lane, image,
+// group) like make_tmap, `transposed` swaps the two image coordinates.  `c` = channels of the slice: the last group may be
+// half used - its unused channels are loaded but never multiplied (k-steps stop at cin).
+static int make_tmap_planar(CUtensorMap* tm, const void* ptr, int c, int w, int h, int n, int ld, long long group_stride, int rows,
+                            const char* what, bool transposed) {
+  EncodeTiledFn encode = get_encode_fn();
+  SRCGAN_REQUIRE(encode != nullptr, "%s: cuTensorMapEncodeTiled is not available from the driver", what);
+  SRCGAN_REQUIRE(ld == KCH && group_stride >= (long long)n * h * w * ld && group_stride % 8 == 0,
+                 "%s: a planar buffer has 64-channel groups (ld 64) at a 16-byte aligned stride", what);
+  const cuuint64_t groups = (cuuint64_t)((c + KCH - 1) / KCH);
+  cuuint64_t gdim[5] = {(cuuint64_t)KCH, (cuuint64_t)w, (cuuint64_t)h, (cuuint64_t)n, groups};
+  cuuint64_t gstr[4] = {(cuuint64_t)ld * 2, (cuuint64_t)ld * 2 * w, (cuuint64_t)ld * 2 * w * h, (cuuint64_t)group_stride * 2};
+  if (transposed) {
+    gdim[1] = (cuuint64_t)h; gdim[2] = (cuuint64_t)w;
+    gstr[0] = (cuuint64_t)ld * 2 * w; gstr[1] = (cuuint64_t)ld * 2;
+  }
+  cuuint32_t box[5] = {(cuuint32_t)KCH, 1, (cuuint32_t)rows, 1, 1};
+  cuuint32_t estr[5] = {1, 1, 1, 1, 1};
+  CUresult cr = encode(tm, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 5, const_cast<void*>(ptr), gdim, gstr, box, estr,
+                       CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
+                       CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+  if (cr != CUDA_SUCCESS) {
+    set_error("%s: cuTensorMapEncodeTiled (5-D) failed with CUresult %d", what, (int)cr);
     return SRCGAN_E_CUDA;
   }
   return SRCGAN_OK;
@@ -2137,10 +2182,14 @@ static int conv_fprop_sweep2(const srcgan_conv_params* p, int cg, cudaStream_t s
   // neighbouring pixels and a warp's stores land on neighbouring pixels - else lanes along a column (sweep over x)
   bool tr = p->wo >= 96;
   { const char* e = getenv("SRCGAN_B200_SWEEP_TR"); if (e) tr = (atoi(e) != 0 && p->wo >= 96) || p->ho < 96; }
-  int rc = tc::make_tmap(&tx, p->x, p->cin, p->w, p->h, p->n, p->x_ld, tc::SW_SLAB_ROWS, 1, "conv_fprop_tc(sweep2 x)", 1, tr,
-                         /*promote256=*/p->cin % 128 == 0 && p->x_ld == p->cin);
+  int rc = p->x_group_stride
+               ? tc::make_tmap_planar(&tx, p->x, p->cin, p->w, p->h, p->n, p->x_ld, p->x_group_stride, tc::SW_SLAB_ROWS,
+                                      "conv_fprop_tc(sweep2 planar x)", tr)
+               : tc::make_tmap(&tx, p->x, p->cin, p->w, p->h, p->n, p->x_ld, tc::SW_SLAB_ROWS, 1, "conv_fprop_tc(sweep2 x)", 1, tr,
+                               /*promote256=*/p->cin % 128 == 0 && p->x_ld == p->cin);
   if (rc) return rc;
   tc::Sw2Args a;
+  a.planar = p->x_group_stride ? 1 : 0;
   a.n = p->n; a.cin = p->cin; a.cout = p->cout;
   a.h = tr ? p->wo : p->ho; a.w = tr ? p->ho : p->wo;              // a.h = lane extent, a.w = sweep extent
   a.tr = tr ? 1 : 0;
@@ -2170,6 +2219,8 @@ int conv_fprop_tc(const srcgan_conv_params* p, cudaStream_t st) {
                  "conv_fprop_tc: packed sign / mask bits need the paired-sweep kernel (3x3 s1 p1, cout 32/64, map >= 96)");
   SRCGAN_REQUIRE(p->zero_row_period == 0,
                  "conv_fprop_tc: zero_row_period (tall-image separators) needs the paired-sweep kernel (3x3 s1 p1, cout 32/64)");
+  SRCGAN_REQUIRE(p->x_group_stride == 0,
+                 "conv_fprop_tc: a planar input (x_group_stride) needs the paired-sweep kernel (3x3 s1 p1, cout 32/64, map >= 96)");
   if (const int v = kws_variant(p)) return conv_fprop_kws(p, v, st);
   tc::HostPlan hp = tc::fprop_plan(p->kh, p->stride, p->pad);
   const bool halo = p->kh == 3 && p->stride == 1 && (p->cout <= 16 || p->cout == 32 || p->cout == 64);

@@ -697,6 +697,16 @@ class _RRDBGenerator(_NetBase):
                         [(nf + gc * k, gc) for k in range(4)] + [(nf + 4 * gc, nf)])           # the mirrored backward steps
         return h + 1 if ok else 0
 
+    def _planar_plan(self, h: int, w: int, dt) -> bool:
+        """True if the concat buffers of this call are laid out as planar 64-channel groups (ops.PlanarBuf): every layer of the
+        dense blocks then writes its 32-channel slice at a 128-byte pitch instead of 384.  Needs every
+        dense-block shape on the paired-sweep kernel (the only one that reads across groups)."""
+        if dt != torch.bfloat16 or self.nf != 64 or self.gc != 32 or os.environ.get("SRCGAN_B200_NO_PLANAR"):
+            return False
+        eng = _engine_mod()
+        return all(eng.sweep_bits_supported(ci, co, 3, 1, 1, dt, h, w) for ci, co in
+                   [(64, 32), (96, 32), (128, 32), (160, 32), (192, 64)])
+
     @staticmethod
     def _to_tall(src: torch.Tensor, period: int) -> torch.Tensor:
         """(n, h, w, c) -> (1, n*(h+1)+1, w, c) with zero separator rows"""
@@ -722,7 +732,8 @@ class _RRDBGenerator(_NetBase):
         zkw = {"zero_rows": zr} if zr else {}
         n, h, w = x_in.n, x_in.h, x_in.w
         rdbs = self._rdbs()
-        bufs = [ops.new_buf(n, h, w, ctot, dt, dev) for _ in rdbs]
+        planar = self._planar_plan(h, w, dt)
+        bufs = [ops.new_concat(n, h, w, ctot, dt, dev, planar) for _ in rdbs]
         trunk_out = ops.new_buf(n, h, w, nf, dt, dev)
         fea2 = ops.new_buf(n, h, w, nf, dt, dev)
         self._fprop(self.conv_first, x_in, Slice(bufs[0], 0, nf), **zkw)
@@ -730,6 +741,7 @@ class _RRDBGenerator(_NetBase):
         self._chain_forward(rdbs, bufs, Slice(trunk_out), st["bits"], zr)
         self._fprop(self.trunk_conv, Slice(trunk_out), Slice(fea2), r1=Slice(bufs[0], 0, nf), beta1=1.0, **zkw)
         st["x_in"], st["bufs"], st["trunk_out"], st["fea2"], st["tall"] = x_in, bufs, trunk_out, fea2, (zr, n0, h0)
+        st["planar"] = planar
         if zr:
             return Slice(self._from_tall(fea2, n0, h0))
         return Slice(fea2)
@@ -746,7 +758,7 @@ class _RRDBGenerator(_NetBase):
         n, h, w, dev, dt = x_in.n, x_in.h, x_in.w, x_in.buf.device, x_in.dtype
         rdbs = self._rdbs()
         W = lambda p: p is not None and want.get(id(p), False)
-        Dbuf = [ops.new_buf(n, h, w, ctot, dt, dev) for _ in range(4)]
+        Dbuf = [ops.new_concat(n, h, w, ctot, dt, dev, st.get("planar", False)) for _ in range(4)]
         last = len(rdbs) - 1
         self._wgrad(self.trunk_conv, Slice(trunk_out), g_fea2, sink, W(self.trunk_conv.weight), W(self.trunk_conv.bias))
         self._dgrad(self.trunk_conv, g_fea2, Slice(Dbuf[last % 4], 0, nf), **zkw)

@@ -36,23 +36,70 @@ def _require_cuda(t: torch.Tensor, what: str) -> None:
                            "torch.cuda.device(tensor.device)" % (what, t.device, torch.cuda.current_device()))
 
 
+class PlanarBuf:
+    """A concat buffer stored as 64-channel GROUPS: physically (groups, N, H, W, 64), logically (N, H, W, groups * 64).
+    A slice that stays inside one group is an ordinary (pointer, ld = 64) slice; one that spans groups is described to the
+    paired-sweep kernel by ``x_group_stride`` (include/srcgan_b200.h).  Why: a dense block's layers write 32-channel slices;
+    in an interleaved 192-channel buffer that is 64 bytes at a 384-byte pitch, which costs 28 % on the 64->32 layer against
+    a 128-byte pitch (scripts/exp/layout_probe.py)."""
+    GROUP = 64
+
+    def __init__(self, n: int, h: int, w: int, c: int, dtype: torch.dtype, device):
+        assert c % self.GROUP == 0
+        self.groups = torch.empty((c // self.GROUP, n, h, w, self.GROUP), dtype=dtype, device=device)
+        self.shape = (n, h, w, c)
+        self.dtype, self.device = dtype, self.groups.device
+
+    def dim(self) -> int:
+        return 4
+
+    @property
+    def is_cuda(self) -> bool:
+        return self.groups.is_cuda
+
+    def element_size(self) -> int:
+        return self.groups.element_size()
+
+    @property
+    def group_stride(self) -> int:
+        return self.groups.stride(0)
+
+
 class Slice:
-    """Channels [c0, c0+c) of an NHWC buffer tensor of shape (N, H, W, Ctot)."""
+    """Channels [c0, c0+c) of an NHWC buffer tensor of shape (N, H, W, Ctot) - or of a ``PlanarBuf``."""
     __slots__ = ("buf", "c0", "c")
 
-    def __init__(self, buf: torch.Tensor, c0: int = 0, c: Optional[int] = None):
-        assert buf.dim() == 4 and buf.is_contiguous()
+    def __init__(self, buf, c0: int = 0, c: Optional[int] = None):
+        assert buf.dim() == 4 and (isinstance(buf, PlanarBuf) or buf.is_contiguous())
         self.buf, self.c0 = buf, c0
         self.c = buf.shape[3] - c0 if c is None else c
         assert 0 <= c0 and c0 + self.c <= buf.shape[3]
 
     @property
+    def planar(self) -> bool:
+        return isinstance(self.buf, PlanarBuf)
+
+    @property
+    def gs(self) -> int:
+        """group stride in elements if the slice spans more than one 64-channel group of a planar buffer, else 0"""
+        if not self.planar:
+            return 0
+        g = PlanarBuf.GROUP
+        if self.c0 % g:
+            assert self.c0 // g == (self.c0 + self.c - 1) // g, "a planar slice that spans groups starts at a group boundary"
+            return 0
+        return self.buf.group_stride if self.c > g else 0
+
+    @property
     def ptr(self) -> int:
+        if self.planar:
+            g = PlanarBuf.GROUP
+            return self.buf.groups.data_ptr() + ((self.c0 // g) * self.buf.group_stride + self.c0 % g) * self.buf.element_size()
         return self.buf.data_ptr() + self.c0 * self.buf.element_size()
 
     @property
     def ld(self) -> int:
-        return self.buf.shape[3]
+        return PlanarBuf.GROUP if self.planar else self.buf.shape[3]
 
     @property
     def n(self) -> int:
@@ -74,12 +121,36 @@ class Slice:
     def dtype(self) -> torch.dtype:
         return self.buf.dtype
 
+    @property
+    def device(self):
+        return self.buf.device
+
     def view(self) -> torch.Tensor:
+        if self.planar:
+            g = PlanarBuf.GROUP
+            assert self.c0 // g == (self.c0 + self.c - 1) // g, "view() of a planar slice: one group only"
+            return self.buf.groups[self.c0 // g][..., self.c0 % g:self.c0 % g + self.c]
         return self.buf[..., self.c0:self.c0 + self.c]
+
+    def group_slices(self):
+        """the slice cut at the 64-channel group boundaries (a non-planar slice is returned whole)"""
+        if not self.planar:
+            return [self]
+        g, out, c = PlanarBuf.GROUP, [], self.c0
+        while c < self.c0 + self.c:
+            e = min(self.c0 + self.c, (c // g + 1) * g)
+            out.append(Slice(self.buf, c, e - c))
+            c = e
+        return out
 
 
 def new_buf(n: int, h: int, w: int, c: int, dtype: torch.dtype, device) -> torch.Tensor:
     return torch.empty((n, h, w, c), dtype=dtype, device=device)
+
+
+def new_concat(n: int, h: int, w: int, c: int, dtype: torch.dtype, device, planar: bool):
+    """A dense block's concat buffer: planar 64-channel groups (PlanarBuf) or ordinary interleaved NHWC."""
+    return PlanarBuf(n, h, w, c, dtype, device) if planar else new_buf(n, h, w, c, dtype, device)
 
 
 # ------------------------------------------------------------------------------------------
@@ -229,6 +300,8 @@ def conv_fprop(x: Slice, wgt: torch.Tensor, bias: Optional[torch.Tensor], y: Sli
         p.mask_slope = float(mask_slope)
     p.zero_row_period = int(zero_rows)
     p.flags = 1 if reverse else 0                     # SRCGAN_CONV_FLAG_REVERSE
+    p.x_group_stride = x.gs
+    assert y.gs == 0 and all(t is None or t.gs == 0 for t in (r1, r2, mask)), "outputs / side operands stay inside one group"
     with _Timed("fprop", p):
         _lib.check(_lib.load().srcgan_conv_fprop(C.byref(p), _stream()), "conv_fprop")
 
@@ -251,6 +324,13 @@ def conv_wgrad(x: Slice, dy: Slice, dw: Optional[torch.Tensor], db: Optional[tor
                engine: int = ENGINE_SIMT) -> None:
     """dw (fp32 OIHW) (+)= alpha * sum_pixels x (x) dy ; db (+)= alpha * sum_pixels dy."""
     _require_cuda(x.buf, "conv input")
+    assert dy.gs == 0, "dY slices stay inside one group of a planar buffer"
+    if x.gs:
+        # planar input that spans 64-channel groups: one launch of the kw-stacked kernel per group, each writing its window of
+        # input channels of dw (the bias gradient comes out of the first one)
+        assert dw is not None and engine == ENGINE_TC and k == 3 and stride == 1 and pad == 1 and not upsample
+        conv_wgrad_split(x, dy, (dw, 0, db), None, dy.c, accumulate=accumulate, alpha=alpha)
+        return
     if dw is not None:
         assert dw.dtype == torch.float32 and dw.is_contiguous() and tuple(dw.shape) == (dy.c, x.c, k, k), \
             (tuple(dw.shape), (dy.c, x.c, k, k))
@@ -273,6 +353,14 @@ def conv_wgrad_split(x: Slice, dy: Slice, dest0, dest1, split: int, *, accumulat
     ``dy`` -> dest0, the rest -> dest1.  dest = (dw, ci0, db) or None: ``dw`` an fp32 OIHW gradient tensor whose input channels
     [ci0, ci0 + x.c) are written, ``db`` the bias gradient of those output channels or None."""
     _require_cuda(x.buf, "conv input")
+    assert dy.gs == 0, "dY slices stay inside one group of a planar buffer"
+    if x.gs:
+        for i, xs in enumerate(x.group_slices()):
+            off = xs.c0 - x.c0
+            d0 = None if dest0 is None else (dest0[0], dest0[1] + off, dest0[2] if i == 0 else None)
+            d1 = None if dest1 is None else (dest1[0], dest1[1] + off, dest1[2] if i == 0 else None)
+            conv_wgrad_split(xs, dy, d0, d1, split, accumulate=accumulate, alpha=alpha)
+        return
     p = _conv_params(x.n, x.h, x.w, x.c, dy.c, 3, 1, 1, False, dy.h, dy.w, x.dtype, ENGINE_TC)
     p.x, p.x_ld, p.y, p.y_ld = x.ptr, x.ld, dy.ptr, dy.ld
     p.alpha = float(alpha)
@@ -283,7 +371,7 @@ def conv_wgrad_split(x: Slice, dy: Slice, dest0, dest1, split: int, *, accumulat
             continue
         dw, ci0, db = d
         assert dw.dtype == torch.float32 and dw.is_contiguous() and dw.shape[0] == co and dw.shape[2:] == (3, 3), tuple(dw.shape)
-        assert 0 <= ci0 and ci0 + x.c <= dw.shape[1]
+        assert 0 <= ci0 and ci0 + x.c <= dw.shape[1], (ci0, x.c, tuple(dw.shape))
         assert db is None or (db.dtype == torch.float32 and db.is_contiguous() and db.numel() == co)
         args += [dw.data_ptr(), dw.shape[1], ci0, db.data_ptr() if db is not None else None]
     lib = _lib.load()
@@ -328,6 +416,10 @@ def act_backward(dy: Slice, y: Slice, dz: Slice, slope: float) -> None:
 def colsum(x: Slice, out: torch.Tensor, alpha: float = 1.0, accumulate: bool = False) -> None:
     """out[c] (+)= alpha * sum over all pixels of x[..., c]   (fp32 out, one entry per channel of the slice)"""
     assert out.dtype == torch.float32 and out.is_contiguous() and out.numel() == x.c
+    if x.gs:
+        for xs in x.group_slices():
+            colsum(xs, out[xs.c0 - x.c0:xs.c0 - x.c0 + xs.c], alpha, accumulate)
+        return
     lib = _lib.load()
     ws = workspace(lib.srcgan_colsum_workspace_bytes(x.npix, x.c), x.buf.device)
     _lib.check(lib.srcgan_colsum(x.ptr, x.ld, dt_code(x.dtype), x.npix, x.c, out.data_ptr(), float(alpha),

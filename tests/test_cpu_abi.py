@@ -34,7 +34,7 @@ def test_conv_params_struct_matches_header():
     from srcgan_b200._lib import ConvParams
     src = open(os.path.join(ROOT, "include", "srcgan_b200.h")).read()
     body = src[src.index("typedef struct srcgan_conv_params {"):src.index("} srcgan_conv_params;")]
-    fields = re.findall(r"(?:int32_t|float|const void\*|const float\*|void\*)\s+([a-z0-9_, ]+);", body)
+    fields = re.findall(r"(?:int32_t|int64_t|float|const void\*|const float\*|void\*)\s+([a-z0-9_, ]+);", body)
     names = [n.strip() for grp in fields for n in grp.split(",")]
     assert names == [f[0] for f in ConvParams._fields_]
     assert C.sizeof(ConvParams) % 8 == 0

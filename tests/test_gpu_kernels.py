@@ -737,3 +737,36 @@ def test_groupnorm_fwd_bwd(shape, dtype, tol):
     ops.gn_backward(gz, xs, dx, g_dev, mean, rstd, 32, dgamma, dbeta)
     assert relerr(from_nhwc(dx), xr.grad) < 2 * tol
     assert relerr(dgamma.cpu(), gamma.grad) < tol and relerr(dbeta.cpu(), beta.grad) < tol
+
+
+@pytest.mark.parametrize("cin,cout", [(64, 32), (96, 32), (128, 32), (160, 32), (192, 64)])
+def test_planar_concat_buffer_matches_interleaved(cin, cout):
+    """ops.PlanarBuf (a dense block's concat buffer as three 64-channel groups, read across groups by the paired sweep through
+    a 5-D tensor map): same numbers as the interleaved 192-channel buffer, bit for bit for the forward convolution (same
+    arithmetic order), to fp32 rounding for the weight gradient (one launch per group)."""
+    from srcgan_b200 import _lib, ops
+    n, h, w = 2, 128, 40
+    g = torch.Generator().manual_seed(91)
+    inter = (torch.rand((n, h, w, 192), generator=g) - 0.5).to(torch.bfloat16).to(DEV)
+    planar = ops.PlanarBuf(n, h, w, 192, torch.bfloat16, DEV)
+    for k in range(3):
+        planar.groups[k].copy_(inter[..., 64 * k:64 * k + 64])
+    wt = ((torch.rand((cout, cin, 3, 3), generator=g) - 0.5) * 0.2).to(DEV)
+    b = torch.rand((cout,), generator=g).to(DEV)
+    wp = ops.pack_weights(wt, ops.WL_TC, torch.bfloat16)
+    oc0 = cin if cout == 32 else 0                       # a dense-block layer writes the slice right after its input prefix
+    out_i = torch.zeros((n, h, w, 192), dtype=torch.bfloat16, device=DEV)
+    out_p = ops.PlanarBuf(n, h, w, 192, torch.bfloat16, DEV)
+    out_p.groups.zero_()
+    ops.conv_fprop(ops.Slice(inter, 0, cin), wp, b, ops.Slice(out_i, oc0, cout), 3, 1, 1, act=0.2, engine=ops.ENGINE_TC)
+    ops.conv_fprop(ops.Slice(planar, 0, cin), wp, b, ops.Slice(out_p, oc0, cout), 3, 1, 1, act=0.2, engine=ops.ENGINE_TC)
+    assert _lib.last_kernel().startswith("conv3x3_sweep2_tc")
+    got = torch.cat([out_p.groups[k] for k in range(3)], dim=-1)
+    assert torch.equal(got, out_i)
+    assert float(out_i[..., oc0:oc0 + cout].abs().max()) > 0
+    # weight gradient: dY = the slice just written
+    dw_i, db_i = torch.empty((cout, cin, 3, 3), device=DEV), torch.empty((cout,), device=DEV)
+    dw_p, db_p = torch.empty((cout, cin, 3, 3), device=DEV), torch.empty((cout,), device=DEV)
+    ops.conv_wgrad(ops.Slice(inter, 0, cin), ops.Slice(out_i, oc0, cout), dw_i, db_i, 3, 1, 1, engine=ops.ENGINE_TC)
+    ops.conv_wgrad(ops.Slice(planar, 0, cin), ops.Slice(out_p, oc0, cout), dw_p, db_p, 3, 1, 1, engine=ops.ENGINE_TC)
+    assert relerr(dw_p.cpu(), dw_i.cpu()) < 1e-4 and relerr(db_p.cpu(), db_i.cpu()) < 1e-4
