@@ -177,6 +177,9 @@ int srcgan_act_backward(const void* dy, int dy_ld, const void* y, int y_ld, void
                         float slope, int dtype, void* stream);
 int srcgan_add(const void* a, int a_ld, const void* b, int b_ld, void* dst, int dst_ld, int64_t npix, int c, int dtype,
                void* stream);
+/* in place: y = leaky(y + bias[ch]) (bias may be NULL, has_act = 0 skips the activation) - nn.ConvTranspose2d's bias and the
+   LeakyReLU / ReLU that follows it in the reference's generators (src/model/resdeconv.py, src/model/edsr.py) */
+int srcgan_bias_act(void* y, int y_ld, int64_t npix, int c, const float* bias, int has_act, float slope, int dtype, void* stream);
 
 /* out[ch] (+)= alpha * sum over the npix rows of x[row, ch]  (bias gradients of a whole dense block in one pass:
  * the gradient concat buffer [dOut | dZ4 | dZ3 | dZ2 | dZ1] holds the output gradients of all five convs) */

@@ -76,6 +76,7 @@ SIGNATURES = {
     "srcgan_nchw_to_nhwc": (_I, [_P, _I, _I, _I, _I, _P, _I, _I, _P]),
     "srcgan_nhwc_to_nchw": (_I, [_P, _I, _I, _P, _I, _I, _I, _I, _P]),
     "srcgan_act_backward": (_I, [_P, _I, _P, _I, _P, _I, _L, _I, _F, _I, _P]),
+    "srcgan_bias_act": (_I, [_P, _I, _L, _I, _P, _I, _F, _I, _P]),
     "srcgan_add": (_I, [_P, _I, _P, _I, _P, _I, _L, _I, _I, _P]),
     "srcgan_colsum_workspace_bytes": (_Z, [_L, _I]),
     "srcgan_colsum": (_I, [_P, _I, _I, _L, _I, _P, _F, _I, _P, _Z, _P]),

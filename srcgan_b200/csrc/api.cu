@@ -63,6 +63,7 @@ int upsample2x(const void* src, int src_ld, void* dst, int dst_ld, int n, int h,
                cudaStream_t st);
 int upsample2x_adjoint(const void* src, int src_ld, void* dst, int dst_ld, const void* mask, int mask_ld,
                        float mslope, int n, int h, int w, int c, int dtype, cudaStream_t st);
+int bias_act(void* y, int ld, int64_t npix, int c, const float* bias, int has_act, float slope, int dtype, cudaStream_t st);
 int add_slices(const void* a, int a_ld, const void* b, int b_ld, void* d, int d_ld, int64_t npix, int c, int dtype,
                cudaStream_t st);
 int bias_grad_launch(const void* dy, int dy_ld, int dtype, long long M, int cout, float* db, int accumulate,
@@ -244,6 +245,11 @@ int srcgan_add(const void* a, int a_ld, const void* b, int b_ld, void* dst, int 
                void* stream) {
   SRCGAN_REQUIRE(a && b && dst && npix > 0 && c > 0, "add: bad arguments");
   return add_slices(a, a_ld, b, b_ld, dst, dst_ld, npix, c, dtype, (cudaStream_t)stream);
+}
+
+int srcgan_bias_act(void* y, int y_ld, int64_t npix, int c, const float* bias, int has_act, float slope, int dtype, void* stream) {
+  SRCGAN_REQUIRE(y && npix > 0 && c > 0 && (bias || has_act), "bias_act: bad arguments");
+  return bias_act(y, y_ld, npix, c, bias, has_act, slope, dtype, (cudaStream_t)stream);
 }
 
 int srcgan_act_backward(const void* dy, int dy_ld, const void* y, int y_ld, void* dz, int dz_ld, int64_t npix, int c,

@@ -5,6 +5,8 @@
 //
 // Reference semantics: nn.Conv2d fwd/bwd as used at src/model/model.py:193-211 (dense block),
 // :236-289 (Decoder), :396-440 (RDDBNetB), :612-635 (NLayerDiscriminator).
+#include <type_traits>
+
 #include "common.cuh"
 
 namespace srcgan {
@@ -296,44 +298,57 @@ conv_wgrad_simt(const ConvDev a, float* __restrict__ part, int pix_per_split) {
   }
 }
 
-// dw[co][ci][tap] (+)= sum_s part[s][tap][ci][co]    (deterministic, fixed order)
-__global__ void wgrad_reduce(const float* __restrict__ part, int splits, int taps, int cin, int cout,
-                             float* __restrict__ dw, int accumulate, float alpha) {
-  int64_t total = (int64_t)taps * cin * cout;
-  int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
-  if (i >= total) return;
-  int co = (int)(i % cout);
-  int64_t t = i / cout;
-  int ci = (int)(t % cin);
-  int tap = (int)(t / cin);
-  double sd = 0.0;                      // (also used by the tcgen05 wgrad kernels: fixed order, double)
-  for (int k = 0; k < splits; ++k) sd += (double)part[(int64_t)k * total + i];
-  float s = (float)sd * alpha;
-  int64_t o = ((int64_t)co * cin + ci) * taps + tap;
-  dw[o] = accumulate ? dw[o] + s : s;
-}
-
-// Same reduction with TWO destinations: output channels [0, split) go to d0, [split, cout) to d1; each destination is an
-// OIHW tensor with `ld` input channels of which this launch fills [ci0, ci0 + cin) - the weight gradients of two adjacent
-// dense-block layers computed as one 64-output-channel wgrad over their common input prefix (nn.py::_chain_backward).
-__global__ void wgrad_reduce_split(const float* __restrict__ part, int splits, int taps, int cin, int cout, int split,
-                                   float* __restrict__ d0, int ld0, int ci00, float* __restrict__ d1, int ld1, int ci01,
-                                   int accumulate, float alpha) {
-  int64_t total = (int64_t)taps * cin * cout;
-  int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
-  if (i >= total) return;
-  int co = (int)(i % cout);
-  int64_t t = i / cout;
-  int ci = (int)(t % cin);
-  int tap = (int)(t / cin);
-  double sd = 0.0;
-  for (int k = 0; k < splits; ++k) sd += (double)part[(int64_t)k * total + i];
-  const float s = (float)sd * alpha;
+// dw[co][ci][tap] (+)= alpha * sum_s part[s][tap][ci][co]   - the split-K reduction behind every wgrad kernel.
+// Deterministic (fixed partition, fixed order) and built for latency: a block is 32 outputs x 8 split lanes; lane y adds
+// splits y, y+8, ... with four independent accumulators (4 loads in flight per thread, ~1 150 blocks for a 64x64x9 gradient),
+// the eight lane sums are added in lane order.  The one-thread-per-output loop it replaces was a chain of up to 148
+// dependent load+add steps: 41-46 us per launch, 22 ms of a 299 ms step (profiles/r2_profile_step.txt).
+// DBL: double accumulation for the fp32 parity engine.  Two destinations (see srcgan_conv_wgrad_split): output channels
+// [0, split) go to d0, the rest to d1; each is an OIHW tensor with `ld` input channels, filled from channel ci0.
+template <bool DBL>
+__global__ void __launch_bounds__(256)
+wgrad_reduce_k(const float* __restrict__ part, int splits, int taps, int cin, int cout, int split, float* __restrict__ d0,
+               int ld0, int ci00, float* __restrict__ d1, int ld1, int ci01, int accumulate, float alpha) {
+  using Acc = typename std::conditional<DBL, double, float>::type;
+  __shared__ Acc red[8][33];
+  const int64_t total = (int64_t)taps * cin * cout;
+  const int64_t i = (int64_t)blockIdx.x * 32 + threadIdx.x;
+  const int y = threadIdx.y;
+  Acc a0 = 0, a1 = 0, a2 = 0, a3 = 0;
+  if (i < total) {
+    const float* p = part + i;
+    int k = y;
+    for (; k + 24 < splits; k += 32) {
+      const float v0 = __ldg(p + (int64_t)k * total), v1 = __ldg(p + (int64_t)(k + 8) * total),
+                  v2 = __ldg(p + (int64_t)(k + 16) * total), v3 = __ldg(p + (int64_t)(k + 24) * total);
+      a0 += (Acc)v0; a1 += (Acc)v1; a2 += (Acc)v2; a3 += (Acc)v3;
+    }
+    for (; k < splits; k += 8) a0 += (Acc)__ldg(p + (int64_t)k * total);
+  }
+  red[y][threadIdx.x] = (a0 + a1) + (a2 + a3);
+  __syncthreads();
+  if (y != 0 || i >= total) return;
+  Acc t = 0;
+#pragma unroll
+  for (int r = 0; r < 8; ++r) t += red[r][threadIdx.x];
+  const float sv = (float)t * alpha;
+  const int co = (int)(i % cout);
+  const int64_t q = i / cout;
+  const int ci = (int)(q % cin);
+  const int tap = (int)(q / cin);
   float* dst = co < split ? d0 : d1;
   if (dst == nullptr) return;
   const int c = co < split ? co : co - split, ld = co < split ? ld0 : ld1, c0 = co < split ? ci00 : ci01;
   const int64_t o = ((int64_t)c * ld + c0 + ci) * taps + tap;
-  dst[o] = accumulate ? dst[o] + s : s;
+  dst[o] = accumulate ? dst[o] + sv : sv;
+}
+
+template <bool DBL>
+static void wgrad_reduce_go(const float* part, int splits, int taps, int cin, int cout, int split, float* d0, int ld0, int ci00,
+                            float* d1, int ld1, int ci01, int accumulate, float alpha, cudaStream_t st) {
+  const int64_t total = (int64_t)taps * cin * cout;
+  wgrad_reduce_k<DBL><<<ceil_div(total, 32), dim3(32, 8), 0, st>>>(part, splits, taps, cin, cout, split, d0, ld0, ci00, d1, ld1,
+                                                                   ci01, accumulate, alpha);
 }
 
 // db[c] (+)= sum_m G[m][c] : stage 1 partial column sums, stage 2 fixed-order reduce
@@ -940,8 +955,7 @@ static int launch_wgrad(const srcgan_conv_params* p, float* dw, float* db, int a
     else conv_wgrad_simt<T, 4, 4, 1, 1><<<grid, 16, 0, st>>>(a, part, pps);
     count_launch();
     int64_t total = (int64_t)taps * p->cin * p->cout;
-    wgrad_reduce<<<ceil_div(total, 256), 256, 0, st>>>(part, splits, taps, p->cin, p->cout, dw, accumulate,
-                                                           p->alpha);
+    wgrad_reduce_go<true>(part, splits, taps, p->cin, p->cout, p->cout, dw, p->cin, 0, nullptr, 0, 0, accumulate, p->alpha, st);
     count_launch();
   }
   if (db) {
@@ -961,7 +975,7 @@ int conv_wgrad_simt(const srcgan_conv_params* p, float* dw, float* db, int accum
 int wgrad_reduce_launch(const float* part, int splits, int taps, int cin, int cout, float* dw, int accumulate,
                         float alpha, cudaStream_t st) {
   int64_t total = (int64_t)taps * cin * cout;
-  wgrad_reduce<<<ceil_div(total, 256), 256, 0, st>>>(part, splits, taps, cin, cout, dw, accumulate, alpha);
+  wgrad_reduce_go<false>(part, splits, taps, cin, cout, cout, dw, cin, 0, nullptr, 0, 0, accumulate, alpha, st);   // tcgen05 partials: float
   count_launch();
   return check_launch("wgrad_reduce");
 }
@@ -983,8 +997,7 @@ int colsum_final_ld_launch(const float* part, int nparts, int c, int ld, float* 
 int wgrad_reduce_split_launch(const float* part, int splits, int taps, int cin, int cout, int split, float* d0, int ld0,
                               int ci00, float* d1, int ld1, int ci01, int accumulate, float alpha, cudaStream_t st) {
   int64_t total = (int64_t)taps * cin * cout;
-  wgrad_reduce_split<<<ceil_div(total, 256), 256, 0, st>>>(part, splits, taps, cin, cout, split, d0, ld0, ci00, d1, ld1, ci01,
-                                                           accumulate, alpha);
+  wgrad_reduce_go<false>(part, splits, taps, cin, cout, split, d0, ld0, ci00, d1, ld1, ci01, accumulate, alpha, st);
   count_launch();
   return check_launch("wgrad_reduce");
 }

@@ -277,6 +277,27 @@ int add_slices(const void* a, int a_ld, const void* b, int b_ld, void* d, int d_
   return check_launch("add");
 }
 
+// y[px][ch] = leaky(y[px][ch] + bias[ch]) in place: bias / activation after a gather-form transposed convolution
+// (functional._ConvTranspose2d), instead of materialising a broadcast bias tensor for the add kernel
+template <typename T>
+__global__ void bias_act_k(T* y, int ld, int64_t npix, int c, const float* __restrict__ bias, int has_act, float slope) {
+  int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= npix * c) return;
+  const int ch = (int)(i % c);
+  const int64_t m = i / c;
+  float v = to_f32(y[m * ld + ch]);
+  if (bias) v += __ldg(bias + ch);
+  if (has_act) v = v > 0.f ? v : v * slope;
+  y[m * ld + ch] = from_f32<T>(v);
+}
+
+int bias_act(void* y, int ld, int64_t npix, int c, const float* bias, int has_act, float slope, int dtype, cudaStream_t st) {
+  if (dtype == SRCGAN_DT_F32) bias_act_k<float><<<ceil_div(npix * c, 256), 256, 0, st>>>((float*)y, ld, npix, c, bias, has_act, slope);
+  else bias_act_k<__nv_bfloat16><<<ceil_div(npix * c, 256), 256, 0, st>>>((__nv_bfloat16*)y, ld, npix, c, bias, has_act, slope);
+  count_launch();
+  return check_launch("bias_act");
+}
+
 template <typename T>
 __global__ void act_bwd_k(const T* dy, int dy_ld, const T* y, int y_ld, T* d /* may alias dy or y */, int d_ld,
                           int64_t npix, int c, float slope) {

@@ -278,14 +278,9 @@ class _ConvTranspose2d(torch.autograd.Function):
 
 
 def _bias_act_(y: torch.Tensor, b: Optional[torch.Tensor], act: Optional[float]) -> torch.Tensor:
-    """Per-channel bias and (Leaky)ReLU after a gather-form transposed convolution: a 1x1 identity-free pass
-    through the conv epilogue would cost a GEMM, so this is the one place that uses the elementwise add kernel."""
-    if b is not None:
-        row = b.detach().to(y.dtype).view(1, 1, 1, -1).expand_as(y).contiguous()
-        ops.add(Slice(y), Slice(row), Slice(y))
-    if act is not None:
-        # y = y > 0 ? y : act * y  ==  act_backward(dy = y, mask = y)
-        ops.act_backward(Slice(y), Slice(y), Slice(y), act)
+    """Per-channel bias and (Leaky)ReLU after a gather-form transposed convolution, in place, one small kernel."""
+    if b is not None or act is not None:
+        ops.bias_act_(Slice(y), b, act)
     return y
 
 

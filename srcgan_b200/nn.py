@@ -701,7 +701,9 @@ class _RRDBGenerator(_NetBase):
         """True if the concat buffers of this call are laid out as planar 64-channel groups (ops.PlanarBuf): every layer of the
         dense blocks then writes its 32-channel slice at a 128-byte pitch instead of 384.  Needs every
         dense-block shape on the paired-sweep kernel (the only one that reads across groups)."""
-        if dt != torch.bfloat16 or self.nf != 64 or self.gc != 32 or os.environ.get("SRCGAN_B200_NO_PLANAR"):
+        # OFF by default: measured in the step (profiles/r2_bench_planar_ab.txt) the isolated 28 % on 64->32 shrinks to
+        # -1.5 ms for the sweep family while the per-group weight-gradient launches cost +10 ms: 210.4 vs 216.5 patches/s.
+        if dt != torch.bfloat16 or self.nf != 64 or self.gc != 32 or not os.environ.get("SRCGAN_B200_PLANAR"):
             return False
         eng = _engine_mod()
         return all(eng.sweep_bits_supported(ci, co, 3, 1, 1, dt, h, w) for ci, co in

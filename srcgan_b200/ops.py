@@ -408,6 +408,18 @@ def add(a: Slice, b: Slice, dst: Slice) -> None:
                                       _stream()), "add")
 
 
+def bias_act_(y: Slice, bias: Optional[torch.Tensor], act: Optional[float]) -> None:
+    """in place: y = leaky(y + bias[channel], act)"""
+    b = None
+    if bias is not None:
+        b = bias.detach()
+        if b.dtype != torch.float32 or not b.is_contiguous():
+            b = b.float().contiguous()
+        assert b.numel() == y.c
+    _lib.check(_lib.load().srcgan_bias_act(y.ptr, y.ld, y.npix, y.c, b.data_ptr() if b is not None else None,
+                                           int(act is not None), float(act or 0.0), dt_code(y.dtype), _stream()), "bias_act")
+
+
 def act_backward(dy: Slice, y: Slice, dz: Slice, slope: float) -> None:
     _lib.check(_lib.load().srcgan_act_backward(dy.ptr, dy.ld, y.ptr, y.ld, dz.ptr, dz.ld, dz.npix, dz.c, float(slope),
                                                dt_code(dz.dtype), _stream()), "act_backward")
