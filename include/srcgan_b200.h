@@ -216,9 +216,11 @@ int srcgan_bn_forward(const void* x, int x_ld, void* y, int y_ld, int64_t npix, 
                       float* save_mean, float* save_invstd, int training, float momentum, float eps,
                       float slope, void* workspace, size_t workspace_bytes, void* stream);
 /* dy_post: gradient w.r.t. y (after LeakyReLU); y: saved forward output (sign = LeakyReLU mask);
- * x: saved conv output.  Writes dx (may alias dy_post), dgamma/dbeta (+= if accumulate). */
+ * x: saved conv output.  Writes dx (may alias dy_post), dgamma/dbeta (+= if accumulate).
+ * beta (optional): with it the bf16 kernels RECOMPUTE the LeakyReLU mask from x with the forward's own expression
+ * (fmaf(x - mean, gamma * invstd, beta) > 0) and do not read y at all: 5 tensor sweeps instead of 7. */
 int srcgan_bn_backward(const void* dy_post, int dy_ld, const void* y, int y_ld, const void* x, int x_ld,
-                       void* dx, int dx_ld, int64_t npix, int c, int dtype, const float* gamma,
+                       void* dx, int dx_ld, int64_t npix, int c, int dtype, const float* gamma, const float* beta,
                        const float* save_mean, const float* save_invstd, float slope, int training,
                        float* dgamma, float* dbeta, int accumulate,
                        void* workspace, size_t workspace_bytes, void* stream);

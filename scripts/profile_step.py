@@ -26,8 +26,19 @@ for _ in range(3):
 torch.cuda.synchronize()
 t0 = time.perf_counter()
 m.optimize_parameters(ra, rb)
+t_enq = (time.perf_counter() - t0) * 1e3          # host time to ENQUEUE the step (returns before the GPU is done)
 torch.cuda.synchronize()
 wall_plain = (time.perf_counter() - t0) * 1e3
+print("host enqueue time of one step: %.1f ms of %.1f ms wall (the GPU is starved whenever the host is the later one)" % (t_enq, wall_plain))
+if os.environ.get("PROFILE_STEP_HOST"):
+    import cProfile
+    import pstats
+    pr = cProfile.Profile()
+    pr.enable()
+    m.optimize_parameters(ra, rb)
+    pr.disable()
+    torch.cuda.synchronize()
+    pstats.Stats(pr).sort_stats("tottime").print_stats(30)
 with profile(activities=[ProfilerActivity.CUDA]) as prof:
     t0 = time.perf_counter()
     m.optimize_parameters(ra, rb)

@@ -87,7 +87,7 @@ SIGNATURES = {
     "srcgan_upsample2x_adjoint": (_I, [_P, _I, _P, _I, _P, _I, _F, _I, _I, _I, _I, _I, _P]),
     "srcgan_bn_workspace_bytes": (_Z, [_L, _I]),
     "srcgan_bn_forward": (_I, [_P, _I, _P, _I, _L, _I, _I, _P, _P, _P, _P, _P, _P, _I, _F, _F, _F, _P, _Z, _P]),
-    "srcgan_bn_backward": (_I, [_P, _I, _P, _I, _P, _I, _P, _I, _L, _I, _I, _P, _P, _P, _F, _I, _P, _P, _I, _P, _Z, _P]),
+    "srcgan_bn_backward": (_I, [_P, _I, _P, _I, _P, _I, _P, _I, _L, _I, _I, _P, _P, _P, _P, _F, _I, _P, _P, _I, _P, _Z, _P]),
     "srcgan_gn_workspace_bytes": (_Z, [_I, _I]),
     "srcgan_gn_forward": (_I, [_P, _I, _P, _I, _I, _L, _I, _I, _I, _P, _P, _P, _P, _F, _P, _I, _I, _F, _P, _Z, _P]),
     "srcgan_gn_backward": (_I, [_P, _I, _P, _I, _P, _I, _I, _L, _I, _I, _I, _P, _P, _P, _P, _P, _I, _P, _Z, _P]),

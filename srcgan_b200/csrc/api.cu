@@ -75,7 +75,7 @@ int bn_forward(const void* x, int x_ld, void* y, int y_ld, int64_t npix, int c, 
 int bn_backward(const void* dy, int dy_ld, const void* y, int y_ld, const void* x, int x_ld, void* dx, int dx_ld,
                 int64_t npix, int c, int dtype, const float* gamma, const float* mean, const float* invstd,
                 float slope, int training, float* dgamma, float* dbeta, int accumulate, void* ws, size_t ws_bytes,
-                cudaStream_t st);
+                cudaStream_t st, const float* beta);
 size_t gn_workspace_bytes(int n, int c);
 int gn_forward(const void* x, int x_ld, void* y, int y_ld, int n, int64_t hw, int c, int groups, int dtype,
                const float* gamma, const float* beta, float* mean, float* rstd, float eps, const void* res, int res_ld,
@@ -275,11 +275,11 @@ int srcgan_bn_forward(const void* x, int x_ld, void* y, int y_ld, int64_t npix, 
                     training, momentum, eps, slope, workspace, workspace_bytes, (cudaStream_t)stream);
 }
 int srcgan_bn_backward(const void* dy_post, int dy_ld, const void* y, int y_ld, const void* x, int x_ld, void* dx,
-                       int dx_ld, int64_t npix, int c, int dtype, const float* gamma, const float* save_mean,
-                       const float* save_invstd, float slope, int training, float* dgamma, float* dbeta,
-                       int accumulate, void* workspace, size_t workspace_bytes, void* stream) {
+                       int dx_ld, int64_t npix, int c, int dtype, const float* gamma, const float* beta,
+                       const float* save_mean, const float* save_invstd, float slope, int training, float* dgamma,
+                       float* dbeta, int accumulate, void* workspace, size_t workspace_bytes, void* stream) {
   return bn_backward(dy_post, dy_ld, y, y_ld, x, x_ld, dx, dx_ld, npix, c, dtype, gamma, save_mean, save_invstd,
-                     slope, training, dgamma, dbeta, accumulate, workspace, workspace_bytes, (cudaStream_t)stream);
+                     slope, training, dgamma, dbeta, accumulate, workspace, workspace_bytes, (cudaStream_t)stream, beta);
 }
 
 size_t srcgan_gn_workspace_bytes(int n, int c) { return gn_workspace_bytes(n, c); }

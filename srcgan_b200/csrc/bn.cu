@@ -182,18 +182,22 @@ bn_bwd_apply_vec(const __nv_bfloat16* dy /* may alias dx (in-place): plain loads
                  int y_ld, const __nv_bfloat16* __restrict__ x, int x_ld, __nv_bfloat16* dx,
                  int dx_ld, int64_t npix, int c, const float* __restrict__ gamma,
                  const float* __restrict__ mean, const float* __restrict__ invstd,
-                 const float* __restrict__ tot, float slope, int training) {
+                 const float* __restrict__ tot, float slope, int training, const float* __restrict__ beta) {
+  // beta != nullptr: the LeakyReLU mask is RECOMPUTED from x with the forward's own expression (bn_apply_vec:
+  // fmaf(x - mean, gamma * invstd, beta) > 0) instead of read from the saved activation y - 5 tensor sweeps instead of 7
+  const bool recompute = beta != nullptr;
   const int oct = c >> 3;
   const int rows_per_iter = 256 / oct;
   const int oc = threadIdx.x % oct, rl = threadIdx.x / oct;
   if (rl >= rows_per_iter) return;
   const int ch = oc * 8;
   const float inv_n = 1.f / (float)npix;
-  float mu[8], is[8], g[8], t0[8], t1[8];
+  float mu[8], is[8], g[8], t0[8], t1[8], be[8];
 #pragma unroll
   for (int k = 0; k < 8; ++k) {
     is[k] = invstd[ch + k]; g[k] = gamma[ch + k] * is[k]; mu[k] = mean[ch + k];
     t0[k] = training ? tot[ch + k] * inv_n : 0.f; t1[k] = training ? tot[c + ch + k] * inv_n : 0.f;
+    be[k] = recompute ? beta[ch + k] : 0.f;
   }
   const int64_t step = (int64_t)gridDim.x * rows_per_iter;
   int64_t m = (int64_t)blockIdx.x * rows_per_iter + rl;
@@ -205,7 +209,7 @@ bn_bwd_apply_vec(const __nv_bfloat16* dy /* may alias dx (in-place): plain loads
       if (u == 0 || two) {
         const int64_t mm = m + u * step;
         qd[u] = *reinterpret_cast<const uint4*>(dy + mm * dy_ld + ch);
-        qy[u] = __ldg(reinterpret_cast<const uint4*>(y + mm * y_ld + ch));
+        if (!recompute) qy[u] = __ldg(reinterpret_cast<const uint4*>(y + mm * y_ld + ch));
         qx[u] = __ldg(reinterpret_cast<const uint4*>(x + mm * x_ld + ch));
       }
     }
@@ -213,10 +217,12 @@ bn_bwd_apply_vec(const __nv_bfloat16* dy /* may alias dx (in-place): plain loads
     for (int u = 0; u < 2; ++u) {
       if (u == 0 || two) {
         float d[8], yy[8], xx[8];
-        unpack8b(qd[u], d); unpack8b(qy[u], yy); unpack8b(qx[u], xx);
+        unpack8b(qd[u], d); unpack8b(qx[u], xx);
+        if (!recompute) unpack8b(qy[u], yy);
 #pragma unroll
         for (int k = 0; k < 8; ++k) {
-          const float dz = yy[k] > 0.f ? d[k] : d[k] * slope;
+          const float z = recompute ? fmaf(xx[k] - mu[k], g[k], be[k]) : yy[k];
+          const float dz = z > 0.f ? d[k] : d[k] * slope;
           if (training) {
             const float xh = (xx[k] - mu[k]) * is[k];
             d[k] = g[k] * (dz - t0[k] - xh * t1[k]);
@@ -235,8 +241,10 @@ template <bool BWD>
 __global__ void __launch_bounds__(256)
 bn_partial_vec(const __nv_bfloat16* __restrict__ x, int x_ld, const __nv_bfloat16* __restrict__ dy, int dy_ld,
                const __nv_bfloat16* __restrict__ y, int y_ld, int64_t npix, int c, const float* __restrict__ mean,
-               const float* __restrict__ invstd, float slope, float* __restrict__ p0, float* __restrict__ p1) {
+               const float* __restrict__ invstd, float slope, float* __restrict__ p0, float* __restrict__ p1,
+               const float* __restrict__ gamma, const float* __restrict__ beta) {
   __shared__ float r0[256][9], r1[256][9];
+  const bool recompute = BWD && beta != nullptr;     // LeakyReLU mask from x (see bn_bwd_apply_vec), y is not read
   const int octets = c >> 3;
   const int rows_per_iter = 256 / octets;
   const int oc = threadIdx.x % octets, rl = threadIdx.x / octets;
@@ -244,10 +252,13 @@ bn_partial_vec(const __nv_bfloat16* __restrict__ x, int x_ld, const __nv_bfloat1
 #pragma unroll
   for (int i = 0; i < 8; ++i) { s[i] = 0.f; q[i] = 0.f; }
   if (rl < rows_per_iter) {
-    float mu[8], is[8];
+    float mu[8], is[8], gi[8], be[8];
     if (BWD) {
 #pragma unroll
-      for (int i = 0; i < 8; ++i) { mu[i] = mean[oc * 8 + i]; is[i] = invstd[oc * 8 + i]; }
+      for (int i = 0; i < 8; ++i) {
+        mu[i] = mean[oc * 8 + i]; is[i] = invstd[oc * 8 + i];
+        gi[i] = recompute ? gamma[oc * 8 + i] * is[i] : 0.f; be[i] = recompute ? beta[oc * 8 + i] : 0.f;
+      }
     }
     const int64_t step = (int64_t)gridDim.x * rows_per_iter;
     int64_t m = (int64_t)blockIdx.x * rows_per_iter + rl;
@@ -272,15 +283,17 @@ bn_partial_vec(const __nv_bfloat16* __restrict__ x, int x_ld, const __nv_bfloat1
         for (int u = 0; u < 2; ++u) {
           qx[u] = __ldg(reinterpret_cast<const uint4*>(x + (m + u * step) * x_ld + oc * 8));
           qd[u] = __ldg(reinterpret_cast<const uint4*>(dy + (m + u * step) * dy_ld + oc * 8));
-          qy[u] = __ldg(reinterpret_cast<const uint4*>(y + (m + u * step) * y_ld + oc * 8));
+          if (!recompute) qy[u] = __ldg(reinterpret_cast<const uint4*>(y + (m + u * step) * y_ld + oc * 8));
         }
 #pragma unroll
         for (int u = 0; u < 2; ++u) {
           float xv[8], dv[8], yv[8];
-          unpack8b(qx[u], xv); unpack8b(qd[u], dv); unpack8b(qy[u], yv);
+          unpack8b(qx[u], xv); unpack8b(qd[u], dv);
+          if (!recompute) unpack8b(qy[u], yv);
 #pragma unroll
           for (int i = 0; i < 8; ++i) {
-            const float dz = yv[i] > 0.f ? dv[i] : dv[i] * slope;
+            const float z = recompute ? fmaf(xv[i] - mu[i], gi[i], be[i]) : yv[i];
+            const float dz = z > 0.f ? dv[i] : dv[i] * slope;
             s[i] += dz; q[i] = fmaf(dz, (xv[i] - mu[i]) * is[i], q[i]);
           }
         }
@@ -295,10 +308,11 @@ bn_partial_vec(const __nv_bfloat16* __restrict__ x, int x_ld, const __nv_bfloat1
       } else {
         float dv[8], yv[8];
         unpack8b(__ldg(reinterpret_cast<const uint4*>(dy + m * dy_ld + oc * 8)), dv);
-        unpack8b(__ldg(reinterpret_cast<const uint4*>(y + m * y_ld + oc * 8)), yv);
+        if (!recompute) unpack8b(__ldg(reinterpret_cast<const uint4*>(y + m * y_ld + oc * 8)), yv);
 #pragma unroll
         for (int i = 0; i < 8; ++i) {
-          const float dz = yv[i] > 0.f ? dv[i] : dv[i] * slope;
+          const float z = recompute ? fmaf(xv[i] - mu[i], gi[i], be[i]) : yv[i];
+          const float dz = z > 0.f ? dv[i] : dv[i] * slope;
           s[i] += dz; q[i] = fmaf(dz, (xv[i] - mu[i]) * is[i], q[i]);
         }
       }
@@ -404,7 +418,7 @@ static int bn_forward_t(const T* x, int x_ld, T* y, int y_ld, int64_t npix, int 
     dim3 grid(ceil_div(c, 32), parts), blk(32, 8);
     if (sizeof(T) == 2 && c % 8 == 0 && c <= 256 && x_ld % 8 == 0 && ((uintptr_t)x) % 16 == 0)
       bn_partial_vec<false><<<parts, 256, 0, st>>>(reinterpret_cast<const __nv_bfloat16*>(x), x_ld, nullptr, 0, nullptr, 0,
-                                                   npix, c, nullptr, nullptr, 0.f, psum, psq);
+                                                   npix, c, nullptr, nullptr, 0.f, psum, psq, nullptr, nullptr);
     else
       bn_stats_partial<T><<<grid, blk, 0, st>>>(x, x_ld, npix, c, psum, psq);
     bn_finalize<<<ceil_div(c, 32), 1024, 0, st>>>(psum, psq, parts, c, npix, eps, momentum, rm, rv, save_mean,
@@ -442,7 +456,8 @@ int bn_forward(const void* x, int x_ld, void* y, int y_ld, int64_t npix, int c, 
 template <typename T>
 static int bn_backward_t(const T* dy, int dy_ld, const T* y, int y_ld, const T* x, int x_ld, T* dx, int dx_ld,
                          int64_t npix, int c, const float* gamma, const float* mean, const float* invstd, float slope,
-                         int training, float* dgamma, float* dbeta, int accumulate, float* ws, cudaStream_t st) {
+                         int training, float* dgamma, float* dbeta, int accumulate, float* ws, cudaStream_t st,
+                         const float* beta) {
   int parts = bn_parts(npix);
   float* p0 = ws;
   float* p1 = ws + (size_t)parts * c;
@@ -453,7 +468,7 @@ static int bn_backward_t(const T* dy, int dy_ld, const T* y, int y_ld, const T* 
     bn_partial_vec<true><<<parts, 256, 0, st>>>(reinterpret_cast<const __nv_bfloat16*>(x), x_ld,
                                                 reinterpret_cast<const __nv_bfloat16*>(dy), dy_ld,
                                                 reinterpret_cast<const __nv_bfloat16*>(y), y_ld, npix, c, mean, invstd,
-                                                slope, p0, p1);
+                                                slope, p0, p1, gamma, beta);
   else
     bn_bwd_partial<T><<<grid, blk, 0, st>>>(dy, dy_ld, y, y_ld, x, x_ld, npix, c, mean, invstd, slope, p0, p1);
   bn_bwd_finalize<<<ceil_div(c, 32), 1024, 0, st>>>(p0, p1, parts, c, tot, dgamma, dbeta, accumulate);
@@ -462,7 +477,7 @@ static int bn_backward_t(const T* dy, int dy_ld, const T* y, int y_ld, const T* 
     bn_bwd_apply_vec<<<bn_stream_blocks(npix, c), 256, 0, st>>>(
         reinterpret_cast<const __nv_bfloat16*>(dy), dy_ld, reinterpret_cast<const __nv_bfloat16*>(y), y_ld,
         reinterpret_cast<const __nv_bfloat16*>(x), x_ld, reinterpret_cast<__nv_bfloat16*>(dx), dx_ld, npix, c, gamma,
-        mean, invstd, tot, slope, training);
+        mean, invstd, tot, slope, training, beta);
   else
     bn_bwd_apply<T><<<ceil_div(npix * c, 256), 256, 0, st>>>(dy, dy_ld, y, y_ld, x, x_ld, dx, dx_ld, npix, c, gamma,
                                                              mean, invstd, tot, slope, training);
@@ -473,16 +488,16 @@ static int bn_backward_t(const T* dy, int dy_ld, const T* y, int y_ld, const T* 
 int bn_backward(const void* dy, int dy_ld, const void* y, int y_ld, const void* x, int x_ld, void* dx, int dx_ld,
                 int64_t npix, int c, int dtype, const float* gamma, const float* mean, const float* invstd,
                 float slope, int training, float* dgamma, float* dbeta, int accumulate, void* ws, size_t ws_bytes,
-                cudaStream_t st) {
+                cudaStream_t st, const float* beta) {
   SRCGAN_REQUIRE(dy && y && x && dx && gamma && mean && invstd, "bn_backward: null pointer");
   SRCGAN_REQUIRE(ws && ws_bytes >= bn_workspace_bytes(npix, c), "bn_backward: workspace too small");
   if (dtype == SRCGAN_DT_F32)
     return bn_backward_t<float>((const float*)dy, dy_ld, (const float*)y, y_ld, (const float*)x, x_ld, (float*)dx,
                                 dx_ld, npix, c, gamma, mean, invstd, slope, training, dgamma, dbeta, accumulate,
-                                (float*)ws, st);
+                                (float*)ws, st, nullptr);
   return bn_backward_t<__nv_bfloat16>((const __nv_bfloat16*)dy, dy_ld, (const __nv_bfloat16*)y, y_ld,
                                       (const __nv_bfloat16*)x, x_ld, (__nv_bfloat16*)dx, dx_ld, npix, c, gamma, mean,
-                                      invstd, slope, training, dgamma, dbeta, accumulate, (float*)ws, st);
+                                      invstd, slope, training, dgamma, dbeta, accumulate, (float*)ws, st, beta);
 }
 
 }  // namespace srcgan

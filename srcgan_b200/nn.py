@@ -1019,7 +1019,7 @@ class RDDBNetA(_RRDBGenerator):
             y, z, (sm, si, use_batch) = ys[i], zs[i + 1], stats[i]
             dg, acc_g = sink.slot(bn.weight, W(bn.weight))
             db, acc_b = sink.slot(bn.bias, W(bn.bias))
-            ops.bn_backward(g, z, y, g, bn.weight, sm, si, Decoder.SLOPE, use_batch, dg, db, acc_g or acc_b)
+            ops.bn_backward(g, z, y, g, bn.weight, sm, si, Decoder.SLOPE, use_batch, dg, db, acc_g or acc_b, beta=bn.bias)
             src = zs[i]
             self._wgrad(conv, src, g, sink, W(conv.weight), False)
             nxt = Slice(ops.new_buf(n, src.h, src.w, src.c, dt, dev))
@@ -1381,7 +1381,7 @@ class NLayerDiscriminator(_NetBase):
                 dg, acc_g = sink.slot(bn.weight, W(bn.weight))
                 db, acc_b = sink.slot(bn.bias, W(bn.bias))
                 ops.bn_backward(g, outs[i], ys[i], g, bn.weight, sm, si, LRELU if act else 1.0, use_batch, dg, db,
-                                acc_g or acc_b)
+                                acc_g or acc_b, beta=bn.bias)
             self._wgrad(conv, ins[i], g, sink, W(conv.weight), W(conv.bias))
             if i == 0 and not need_dx:
                 return None

@@ -493,13 +493,15 @@ def bn_forward(x: Slice, y: Slice, gamma, beta, running_mean, running_var, train
 
 
 def bn_backward(dy_post: Slice, y: Slice, x: Slice, dx: Slice, gamma, save_mean, save_invstd, slope: float,
-                training: bool, dgamma, dbeta, accumulate: bool = False) -> None:
+                training: bool, dgamma, dbeta, accumulate: bool = False, beta=None) -> None:
+    """``beta`` (the BatchNorm bias): lets the bf16 kernels recompute the LeakyReLU mask from x instead of reading y."""
     lib = _lib.load()
     c = x.c
     ws = workspace(lib.srcgan_bn_workspace_bytes(x.npix, c), x.buf.device)
     _lib.check(lib.srcgan_bn_backward(
         dy_post.ptr, dy_post.ld, y.ptr, y.ld, x.ptr, x.ld, dx.ptr, dx.ld, x.npix, c, dt_code(x.dtype),
-        gamma.data_ptr(), save_mean.data_ptr(), save_invstd.data_ptr(), float(slope), int(training),
+        gamma.data_ptr(), beta.data_ptr() if beta is not None else None, save_mean.data_ptr(), save_invstd.data_ptr(),
+        float(slope), int(training),
         dgamma.data_ptr() if dgamma is not None else None, dbeta.data_ptr() if dbeta is not None else None,
         int(accumulate), ws.data_ptr(), ws.numel(), _stream()), "bn_backward")
 

@@ -168,6 +168,20 @@ def test_batchnorm_lrelu(training):
     ops.bn_backward(dys, ys, xs, dys, g_d, sm, si, 0.2, training, dg, dbt)
     assert relerr(from_nhwc(dys), xr.grad) < 1e-4
     assert relerr(dg.cpu(), gr.grad) < 1e-4 and relerr(dbt.cpu(), br.grad) < 1e-4
+    # bf16 kernels: with beta the LeakyReLU mask is recomputed from x instead of read from the saved activation -
+    # bit-identical gradients (the saved activation is then not touched: it is poisoned with NaNs here)
+    xb = to_nhwc(x, torch.bfloat16)
+    yb = ops.Slice(torch.zeros((n, h, w, c), dtype=torch.bfloat16, device=DEV))
+    smb, sib = ops.bn_forward(xb, yb, g_d, b_d, rm.to(DEV), rv.to(DEV), training, 0.2)
+    res = []
+    for use_beta in (False, True):
+        d = to_nhwc(gy, torch.bfloat16)
+        dgb, dbb = torch.empty(c, device=DEV), torch.empty(c, device=DEV)
+        ysave = yb if not use_beta else ops.Slice(torch.full((n, h, w, c), float("nan"), dtype=torch.bfloat16, device=DEV))
+        ops.bn_backward(d, ysave, xb, d, g_d, smb, sib, 0.2, training, dgb, dbb, beta=b_d if use_beta else None)
+        res.append((d.buf.clone(), dgb, dbb))
+    assert torch.equal(res[0][0], res[1][0]) and torch.equal(res[0][1], res[1][1]) and torch.equal(res[0][2], res[1][2])
+    assert relerr(res[1][0].float().permute(0, 3, 1, 2).cpu(), xr.grad) < 3e-2
 
 
 @pytest.mark.parametrize("shape", [(2, 3, 64, 64), (1, 1, 14, 14), (3, 3, 7, 5)])
