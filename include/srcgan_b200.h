@@ -154,6 +154,16 @@ int srcgan_pack_weights_batch(const srcgan_pack_block* blocks_dev, int nblocks, 
 
 int srcgan_conv_fprop(const srcgan_conv_params* p, void* stream);
 int srcgan_conv_dgrad(const srcgan_conv_params* p, void* stream);
+/* Two consecutive layers of a dense block in ONE launch (tcgen05 engine; replaces two srcgan_conv_fprop calls for
+   x_k = lrelu(conv_k(cat(x, x1..x_(k-1)))), x_(k+1) = lrelu(conv_(k+1)(cat(x, x1..x_k))) of src/model/model.py:205-210, and for
+   the same two pairs of the mirrored dense block of the backward pass).  pa reads the prefix x[:, :cin] (cin = 64 | 128) and
+   writes the 32-channel slice right behind it; pb reads [prefix | that slice] (same x, x_ld; cin + 32) and writes another
+   32-channel slice.  3x3 stride 1 pad 1, bf16, lane extent (the image width if >= 96, else the height) <= 256.  Epilogue fields
+   honoured: bias, act / act_slope, signbits, maskbits / mask_slope.  The prefix is read from HBM once and x_k goes from layer A's
+   epilogue to layer B's MMAs through shared memory.  Results equal the two separate calls up to fp32 summation order.
+   srcgan_conv_fprop_pair_supported() -> 1 if the pair can run fused (else call srcgan_conv_fprop twice). */
+int srcgan_conv_fprop_pair_supported(const srcgan_conv_params* pa, const srcgan_conv_params* pb);
+int srcgan_conv_fprop_pair(const srcgan_conv_params* pa, const srcgan_conv_params* pb, void* stream);
 size_t srcgan_conv_wgrad_workspace_bytes(const srcgan_conv_params* p);
 /* dw: fp32 [cout][cin][kh][kw]; db: fp32 [cout] or NULL; accumulate != 0 adds into dw/db */
 int srcgan_conv_wgrad(const srcgan_conv_params* p, float* dw, float* db, int accumulate,

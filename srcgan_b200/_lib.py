@@ -69,6 +69,8 @@ SIGNATURES = {
     "srcgan_pack_slots": (_I, [_I, _I, _I, _I, C.POINTER(C.c_int32), C.POINTER(C.c_int32), C.POINTER(C.c_int32)]),
     "srcgan_pack_weights_batch": (_I, [_P, _I, _L, _P]),
     "srcgan_conv_fprop": (_I, [C.POINTER(ConvParams), _P]),
+    "srcgan_conv_fprop_pair": (_I, [C.POINTER(ConvParams), C.POINTER(ConvParams), _P]),
+    "srcgan_conv_fprop_pair_supported": (_I, [C.POINTER(ConvParams), C.POINTER(ConvParams)]),
     "srcgan_conv_dgrad": (_I, [C.POINTER(ConvParams), _P]),
     "srcgan_conv_wgrad_workspace_bytes": (_Z, [C.POINTER(ConvParams)]),
     "srcgan_conv_wgrad": (_I, [C.POINTER(ConvParams), _P, _P, _I, _P, _Z, _P]),

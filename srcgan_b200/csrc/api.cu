@@ -40,6 +40,8 @@ int pack_weights_simt_host(const float* w, int cout, int cin, int kh, int kw, in
                            cudaStream_t st);
 bool conv_tc_supported(const srcgan_conv_params* p);
 int conv_fprop_tc(const srcgan_conv_params* p, cudaStream_t st);
+bool conv_fprop_pair_supported(const srcgan_conv_params* pa, const srcgan_conv_params* pb);
+int conv_fprop_pair_tc(const srcgan_conv_params* pa, const srcgan_conv_params* pb, cudaStream_t st);
 int pack_weights_tc_host(const float* w, int cout, int cin, int kh, int kw, int layout, void* out, cudaStream_t st);
 size_t packed_weight_bytes_tc(int cout, int cin, int kh, int kw, int layout);
 int pack_slots_tc(int cout, int kh, int kw, int layout, int32_t* slot_off16, int32_t* nslots, int32_t* bn);
@@ -154,6 +156,19 @@ int srcgan_conv_fprop(const srcgan_conv_params* p, void* stream) {
     return SRCGAN_E_INVALID;
   }
   return conv_fprop_simt(p, (cudaStream_t)stream);
+}
+
+int srcgan_conv_fprop_pair_supported(const srcgan_conv_params* pa, const srcgan_conv_params* pb) {
+  if (!pa || !pb || validate_conv(pa, true) || validate_conv(pb, true)) return 0;
+  return conv_fprop_pair_supported(pa, pb) ? 1 : 0;
+}
+int srcgan_conv_fprop_pair(const srcgan_conv_params* pa, const srcgan_conv_params* pb, void* stream) {
+  SRCGAN_REQUIRE(pa && pb, "conv_fprop_pair: null parameters");
+  int rc = validate_conv(pa, true);
+  if (rc) return rc;
+  rc = validate_conv(pb, true);
+  if (rc) return rc;
+  return conv_fprop_pair_tc(pa, pb, (cudaStream_t)stream);
 }
 
 int srcgan_conv_dgrad(const srcgan_conv_params* p, void* stream) {

@@ -1681,6 +1681,8 @@ conv3x3_sweep2_tc(const __grid_constant__ CUtensorMap tmap_x, const Sw2Args a) {
   }
 }
 
+#include "conv_pair.cuh"
+
 // fp32 OIHW -> bf16 [n_block][chunk][slot][BN][64]: each [BN][64] tile is stored as its SWIZZLE_128B
 // shared-memory image (16-byte chunk j of row r lives at chunk j ^ (r & 7)), zero padded in K.
 // Rows are the GEMM-N channels, columns the GEMM-K channels: (co, ci) for fprop, (ci, co) for dgrad.
@@ -2038,6 +2040,55 @@ static int launch_sweep2(const CUtensorMap& tx, Sw2Args& a, cudaStream_t st) {
                                : (CG == 2 ? "conv3x3_sweep2_tc<32,2>" : "conv3x3_sweep2_tc<32,1>"));
 }
 
+// fused pair of dense-block layers (conv_pair.cuh): depth of the P slab ring that fits beside both layers' weights + the XK ring
+static int swf_ring_depth(int nchunks) {
+  const long long fixed = (long long)(2 * nchunks + 1) * SWF_W_CHUNK_BYTES + SWF_XK_BYTES + SMEM_AUX + 1024;
+  long long na = (SMEM_BUDGET - fixed) / SW_SLAB_STRIDE;
+  return na > SW_MAX_NA ? SW_MAX_NA : (int)(na < 0 ? 0 : na);
+}
+static int swf_max_clusters() {
+  static int cached = 0;
+  if (cached) return cached;
+  int ncl = kNumSMs / 2;
+  cudaLaunchConfig_t cfg = {};
+  cfg.gridDim = dim3((unsigned)kNumSMs); cfg.blockDim = dim3(SWF_THREADS); cfg.dynamicSmemBytes = SMEM_BUDGET;
+  cudaLaunchAttribute at[1];
+  at[0].id = cudaLaunchAttributeClusterDimension;
+  at[0].val.clusterDim.x = 2; at[0].val.clusterDim.y = 1; at[0].val.clusterDim.z = 1;
+  cfg.attrs = at; cfg.numAttrs = 1;
+  int q = 0;
+  const cudaError_t qe = cudaOccupancyMaxActiveClusters(&q, conv3x3_pair_sweep_tc, &cfg);
+  if (getenv("SRCGAN_B200_DBG")) fprintf(stderr, "pair_sweep: cudaOccupancyMaxActiveClusters -> %s, %d clusters\n", cudaGetErrorString(qe), q);
+  if (qe == cudaSuccess && q > 0 && q < ncl) ncl = q;
+  (void)cudaGetLastError();
+  cached = ncl;
+  return ncl;
+}
+static int launch_pair_sweep(const CUtensorMap& tx, SwfArgs& a, cudaStream_t st) {
+  a.na = swf_ring_depth(a.nchunks);
+  static DeviceOnce attr_set;
+  int attr_set_dev;
+  if (attr_set.needed(&attr_set_dev)) {
+    SRCGAN_CUDA(cudaFuncSetAttribute(conv3x3_pair_sweep_tc, cudaFuncAttributeMaxDynamicSharedMemorySize, SMEM_BUDGET));
+    attr_set.mark(attr_set_dev);
+  }
+  const int ncl_max = swf_max_clusters();
+  a.total = a.n * a.w;
+  a.per = (a.total + ncl_max - 1) / ncl_max;
+  if (a.per < 8) a.per = 8;                                            // a unit sweeps 4 halo columns: keep ranges worth it
+  const int ncl = (a.total + a.per - 1) / a.per;
+  cudaLaunchConfig_t cfg = {};
+  cfg.gridDim = dim3((unsigned)(ncl * 2)); cfg.blockDim = dim3(SWF_THREADS); cfg.dynamicSmemBytes = swf_smem_bytes(a.nchunks, a.na);
+  cfg.stream = st;
+  cudaLaunchAttribute at[1];
+  at[0].id = cudaLaunchAttributeClusterDimension;
+  at[0].val.clusterDim.x = 2; at[0].val.clusterDim.y = 1; at[0].val.clusterDim.z = 1;
+  cfg.attrs = at; cfg.numAttrs = 1;
+  SRCGAN_CUDA(cudaLaunchKernelEx(&cfg, conv3x3_pair_sweep_tc, tx, a));
+  count_launch();
+  return check_launch("conv3x3_pair_sweep_tc");
+}
+
 static int dispatch(int bn, int maxt, const CUtensorMap& tmap, const TcArgs& a, cudaStream_t st) {
 #define SRCGAN_TC_CASE(B, T) if (bn == B && maxt == T) return launch<B, T>(tmap, a, st)
   SRCGAN_TC_CASE(32, 2); SRCGAN_TC_CASE(64, 2); SRCGAN_TC_CASE(128, 2);
@@ -2211,6 +2262,64 @@ static int conv_fprop_sweep2(const srcgan_conv_params* p, int cg, cudaStream_t s
   { const char* d = getenv("SRCGAN_B200_PFD"); a.pfd = d ? atoi(d) : 0; }
   if (cg == 2) return p->cout == 64 ? tc::launch_sweep2<64, 2>(tx, a, st) : tc::launch_sweep2<32, 2>(tx, a, st);
   return p->cout == 64 ? tc::launch_sweep2<64, 1>(tx, a, st) : tc::launch_sweep2<32, 1>(tx, a, st);
+}
+
+// Two consecutive dense-block layers in one launch (conv_pair.cuh).  pa: P = x[:, :cin] -> the 32-channel slice right behind it;
+// pb: [P | that slice] -> another 32-channel slice.  Epilogues: bias, LeakyReLU, packed masks in / out.
+static const char* pair_why_not(const srcgan_conv_params* pa, const srcgan_conv_params* pb) {
+  const srcgan_conv_params* ps[2] = {pa, pb};
+  for (int i = 0; i < 2; ++i) {
+    const srcgan_conv_params* p = ps[i];
+    if (!tc_common_ok(p)) return "not a bf16 tcgen05 layer";
+    if (p->kh != 3 || p->stride != 1 || p->pad != 1 || p->cout != 32) return "layers must be 3x3 stride 1 pad 1 with 32 output channels";
+    if (p->r1 || p->r2 || p->mask) return "residual / bf16 mask operands are not supported (packed maskbits are)";
+    if (p->alpha != 1.f) return "alpha must be 1";
+    if (p->zero_row_period || p->x_group_stride) return "tall-image / planar buffers are not supported";
+    if (p->y_ld % 8 || ((uintptr_t)p->y) % 16) return "output slice alignment";
+  }
+  if (pa->n != pb->n || pa->h != pb->h || pa->w != pb->w || pa->ho != pb->ho || pa->wo != pb->wo) return "geometry differs";
+  if (pa->cin != 64 && pa->cin != 128) return "the shared prefix must have 64 or 128 channels";
+  if (pb->cin != pa->cin + 32 || pb->x != pa->x || pb->x_ld != pa->x_ld) return "layer B must read [prefix | layer A's output]";
+  if ((const char*)pa->y != (const char*)pa->x + (size_t)pa->cin * 2 || pa->y_ld != pa->x_ld)
+    return "layer A must write the 32-channel slice right behind the prefix";
+  const bool tr = pa->wo >= 96;
+  const int lanes = tr ? pa->wo : pa->ho;
+  if (lanes > 2 * tc::SW_ROWS) return "lane extent above 256";
+  if (lanes < 96) return "map too small";
+  if (tc::swf_ring_depth(pa->cin / tc::KCH) < pa->cin / tc::KCH + 1) return "shared memory";
+  return nullptr;
+}
+bool conv_fprop_pair_supported(const srcgan_conv_params* pa, const srcgan_conv_params* pb) { return pair_why_not(pa, pb) == nullptr; }
+
+int conv_fprop_pair_tc(const srcgan_conv_params* pa, const srcgan_conv_params* pb, cudaStream_t st) {
+  const char* why = pair_why_not(pa, pb);
+  SRCGAN_REQUIRE(why == nullptr, "conv_fprop_pair: %s", why ? why : "");
+  const bool tr = pa->wo >= 96;
+  CUtensorMap tx;
+  int rc = tc::make_tmap(&tx, pa->x, pa->cin, pa->w, pa->h, pa->n, pa->x_ld, tc::SW_SLAB_ROWS, 1, "conv_fprop_pair(x)", 1, tr,
+                         /*promote256=*/pa->cin % 128 == 0 && pa->x_ld == pa->cin);
+  if (rc) return rc;
+  tc::SwfArgs a;
+  a.n = pa->n; a.cin = pa->cin;
+  a.h = tr ? pa->wo : pa->ho; a.w = tr ? pa->ho : pa->wo;
+  a.tr = tr ? 1 : 0;
+  a.img_stride = (long long)pa->ho * pa->wo;
+  a.lane_stride = tr ? 1 : pa->wo; a.sweep_stride = tr ? pa->wo : 1;
+  a.nchunks = pa->cin / tc::KCH;
+  a.wgt_a = (const __nv_bfloat16*)pa->wgt; a.wgt_b = (const __nv_bfloat16*)pb->wgt;
+  const srcgan_conv_params* ps[2] = {pa, pb};
+  for (int i = 0; i < 2; ++i) {
+    tc::SwfLayer& L = a.L[i];
+    L.bias = ps[i]->bias;
+    L.y = (__nv_bfloat16*)ps[i]->y; L.y_ld = ps[i]->y_ld;
+    L.act = ps[i]->act; L.act_slope = ps[i]->act_slope;
+    L.signbits = (uint32_t*)ps[i]->signbits; L.maskbits = (const uint32_t*)ps[i]->maskbits;
+    L.mask_slope = ps[i]->mask_slope;
+  }
+  { const char* d = getenv("SRCGAN_B200_DBG"); a.dbg = d ? atoi(d) : 0; }
+  { const char* d = getenv("SRCGAN_B200_PAIR_PFD"); a.pfd = d ? atoi(d) : 0; }
+  { const char* d = getenv("SRCGAN_B200_PAIR_ISSUERS"); a.issuers = d ? atoi(d) : 1; }
+  return tc::launch_pair_sweep(tx, a, st);
 }
 
 int conv_fprop_tc(const srcgan_conv_params* p, cudaStream_t st) {

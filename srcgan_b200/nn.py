@@ -577,16 +577,32 @@ class _RRDBGenerator(_NetBase):
                 flip[0] = not flip[0]
             return d
 
+        # fused layer pairs (csrc/conv_pair.cuh): bf16, gc = 32, ordinary interleaved buffers, whole lane extent in one CTA pair
+        fuse = (dt == torch.bfloat16 and gc == 32 and nf % 64 == 0 and not zr and not alt and not isinstance(bufs[0], ops.PlanarBuf)
+                and select_engine(nf, gc, 3, 1, False, dt, h, w)[0] == ENGINE_TC)
         for j, rdb in enumerate(rdbs):
             C = bufs[j]
             convs = rdb.convs()
             row = []
+            fused_upto = 0
             for k in range(1, 5):
                 sb = None
                 if bits is not None and gc == 32 and _engine_mod().sweep_bits_supported(nf + gc * (k - 1), gc, 3, 1, 1, dt, h, w):
                     sb = torch.empty((n, h, w, 1), dtype=torch.int32, device=dev)
                 row.append(sb)
-                self._fprop(convs[k - 1], Slice(C, 0, nf + gc * (k - 1)), Slice(C, nf + gc * (k - 1), gc), act=LRELU,
+            for k in range(1, 5):
+                cin_k = nf + gc * (k - 1)
+                if k in (1, 3) and fuse:
+                    # conv_k and conv_(k+1) in one launch: the prefix is read once, x_k reaches conv_(k+1) through shared memory
+                    ca, cb = convs[k - 1], convs[k]
+                    if ops.conv_fprop_pair(Slice(C, 0, cin_k), self._w_f(ca, dt, WL_TC), ca.bias, Slice(C, cin_k, gc),
+                                           Slice(C, 0, cin_k + gc), self._w_f(cb, dt, WL_TC), cb.bias, Slice(C, cin_k + gc, gc),
+                                           act=LRELU, signbits=(row[k - 1], row[k])):
+                        fused_upto = k + 1
+                if k <= fused_upto:
+                    continue
+                sb = row[k - 1]
+                self._fprop(convs[k - 1], Slice(C, 0, cin_k), Slice(C, cin_k, gc), act=LRELU,
                             **({"signbits": sb} if sb is not None else {}), **ep_common())
             if bits is not None:
                 bits.append(row)
@@ -605,6 +621,8 @@ class _RRDBGenerator(_NetBase):
         ctot = nf + 4 * gc
         h, w, dt, dev = bufs[0].shape[1], bufs[0].shape[2], bufs[0].dtype, bufs[0].device
         alt, flip = _alt_order(), [False]
+        fuse = (dt == torch.bfloat16 and gc == 32 and nf % 64 == 0 and not zr and not alt and not isinstance(bufs[0], ops.PlanarBuf)
+                and not isinstance(Dbuf[0], ops.PlanarBuf))
 
         def ep_common() -> dict:
             d = {"zero_rows": zr} if zr else {}
@@ -619,12 +637,22 @@ class _RRDBGenerator(_NetBase):
             convs = rdb.convs()
             is_rdb3, is_rdb1 = (j % 3 == 2), (j % 3 == 0)
             s5 = 0.04 if is_rdb3 else 0.2
+            fused_downto = 5
             for k in (4, 3, 2, 1):
                 cin_v = nf + gc * (4 - k)
                 eng, layout = select_engine(cin_v, gc, 3, 1, False, dt, h, w)
                 mb = bits[j][k - 1] if bits else None
                 if mb is not None and not _engine_mod().sweep_bits_supported(cin_v, gc, 3, 1, 1, dt, h, w):
                     mb = None
+                if (k in (4, 2) and fuse and eng == ENGINE_TC and layout == WL_TC and mb is not None and bits[j][k - 2] is not None
+                        and _engine_mod().sweep_bits_supported(cin_v + gc, gc, 3, 1, 1, dt, h, w)):
+                    # mirrored steps k and k-1 (dZ_k, dZ_(k-1)) in one launch
+                    if ops.conv_fprop_pair(Slice(D, 0, cin_v), self._dense_wT(rdb, k, s5, dt, layout), None, Slice(D, cin_v, gc),
+                                           Slice(D, 0, cin_v + gc), self._dense_wT(rdb, k - 1, s5, dt, layout), None,
+                                           Slice(D, cin_v + gc, gc), maskbits=(mb, bits[j][k - 2]), mask_slope=LRELU):
+                        fused_downto = k - 1
+                if k >= fused_downto:
+                    continue
                 if mb is not None:
                     ops.conv_fprop(Slice(D, 0, cin_v), self._dense_wT(rdb, k, s5, dt, layout), None,
                                    Slice(D, nf + gc * (4 - k), gc), 3, 1, 1, maskbits=mb, mask_slope=LRELU, engine=eng, **ep_common())

@@ -5,6 +5,7 @@ Activations inside the networks are channel-sliced NHWC buffers (``Slice``)."""
 from __future__ import annotations
 
 import ctypes as C
+import os
 from typing import Optional
 
 import torch
@@ -217,7 +218,7 @@ timer = KernelTimer()
 
 
 class _Timed:
-    def __init__(self, kind: str, p: ConvParams):
+    def __init__(self, kind: str, p: ConvParams, extra: Optional[ConvParams] = None):
         self.on = timer.enabled
         if self.on:
             eng = {ENGINE_SIMT: "simt", ENGINE_TC: "tc", ENGINE_AUTO: "auto"}[p.engine]
@@ -232,6 +233,9 @@ class _Timed:
             # the epilogue's residual / mask operands ignored): what an HBM roofline is computed from
             esz = 2 if p.dtype == DT_BF16 else 4
             self.bytes = float(esz) * p.n * (p.h * p.w * p.cin + p.ho * p.wo * p.cout)
+            if extra is not None:          # a fused pair of layers: the second one's FLOPs; its input is already counted
+                self.flops += 2.0 * extra.n * extra.ho * extra.wo * extra.cin * extra.cout * extra.kh * extra.kw
+                self.bytes += float(esz) * extra.n * extra.ho * extra.wo * extra.cout
 
     def __enter__(self):
         if self.on:
@@ -304,6 +308,35 @@ def conv_fprop(x: Slice, wgt: torch.Tensor, bias: Optional[torch.Tensor], y: Sli
     assert y.gs == 0 and all(t is None or t.gs == 0 for t in (r1, r2, mask)), "outputs / side operands stay inside one group"
     with _Timed("fprop", p):
         _lib.check(_lib.load().srcgan_conv_fprop(C.byref(p), _stream()), "conv_fprop")
+
+
+def conv_fprop_pair(xa: Slice, wa: torch.Tensor, ba: Optional[torch.Tensor], ya: Slice,
+                    xb: Slice, wb: torch.Tensor, bb: Optional[torch.Tensor], yb: Slice, *, act: Optional[float] = None,
+                    signbits=(None, None), maskbits=(None, None), mask_slope: float = 0.0) -> bool:
+    """Two consecutive 3x3 layers of a dense block in ONE launch (csrc/conv_pair.cuh): ya = epi(conv(xa, wa)),
+    yb = epi(conv(xb, wb)) with xb = [xa | ya] in the same concat buffer.  Returns False WITHOUT launching anything if the
+    library cannot fuse this pair (the caller then issues two conv_fprop calls); see srcgan_conv_fprop_pair in the header."""
+    _require_cuda(xa.buf, "conv input")
+    if os.environ.get("SRCGAN_B200_NO_PAIR_FPROP") or xa.gs or xb.gs or ya.gs or yb.gs:
+        return False
+    ps = []
+    for x, w, b, y, sb, mb in ((xa, wa, ba, ya, signbits[0], maskbits[0]), (xb, wb, bb, yb, signbits[1], maskbits[1])):
+        p = _conv_params(x.n, x.h, x.w, x.c, y.c, 3, 1, 1, False, y.h, y.w, x.dtype, ENGINE_TC)
+        p.x, p.x_ld, p.wgt, p.y, p.y_ld = x.ptr, x.ld, w.data_ptr(), y.ptr, y.ld
+        _epilogue(p, b, act, 1.0, None, 0.0, None, 0.0, None, 0.0)
+        for name, t in (("signbits", sb), ("maskbits", mb)):
+            if t is not None:
+                assert t.dtype == torch.int32 and t.is_contiguous() and tuple(t.shape) == (y.n, y.h, y.w, y.c // 32), name
+                setattr(p, name, t.data_ptr())
+        if mb is not None:
+            p.mask_slope = float(mask_slope)
+        ps.append(p)
+    lib = _lib.load()
+    if not lib.srcgan_conv_fprop_pair_supported(C.byref(ps[0]), C.byref(ps[1])):
+        return False
+    with _Timed("fprop", ps[0], extra=ps[1]):
+        _lib.check(lib.srcgan_conv_fprop_pair(C.byref(ps[0]), C.byref(ps[1]), _stream()), "conv_fprop_pair")
+    return True
 
 
 def conv_dgrad(dy: Slice, wgt_rskc: torch.Tensor, dx: Slice, k: int, stride: int, pad: int, *, alpha: float = 1.0,

@@ -18,6 +18,16 @@ def relerr(a, b):
     return float((a.double() - b.double()).abs().max() / b.double().abs().max().clamp_min(1e-30))
 
 
+def _lib_last_kernel():
+    from srcgan_b200 import _lib
+    return _lib.last_kernel()
+
+
+def _lib_launch_count():
+    from srcgan_b200 import _lib
+    return _lib.launch_count()
+
+
 def to_nhwc(x, dtype, ctot=None, c0=0):
     from srcgan_b200 import ops
     n, c, h, w = x.shape
@@ -181,7 +191,14 @@ def test_batchnorm_lrelu(training):
         ops.bn_backward(d, ysave, xb, d, g_d, smb, sib, 0.2, training, dgb, dbb, beta=b_d if use_beta else None)
         res.append((d.buf.clone(), dgb, dbb))
     assert torch.equal(res[0][0], res[1][0]) and torch.equal(res[0][1], res[1][1]) and torch.equal(res[0][2], res[1][2])
-    assert relerr(res[1][0].float().permute(0, 3, 1, 2).cpu(), xr.grad) < 3e-2
+    # against fp32 autograd on the SAME bf16-rounded x and dy (so the LeakyReLU mask is the same one; a mask flipped by
+    # rounding x would change single elements by 0.8*dy and says nothing about the kernel)
+    xq = x.bfloat16().float().requires_grad_(True)
+    yq = F.leaky_relu(F.batch_norm(xq, rm.clone(), rv.clone(), gamma, beta, training, 0.1, 1e-5), 0.2)
+    yq.backward(gy.bfloat16().float())
+    got = res[1][0].float().permute(0, 3, 1, 2).cpu()
+    assert float((got - xq.grad).norm() / xq.grad.norm()) < 1e-2
+    assert float(((got - xq.grad).abs() > 3e-2 * xq.grad.abs().max()).float().mean()) < 1e-3
 
 
 @pytest.mark.parametrize("shape", [(2, 3, 64, 64), (1, 1, 14, 14), (3, 3, 7, 5)])
@@ -442,6 +459,113 @@ def test_conv_tc_packed_masks(cin, cout):
     with pytest.raises(RuntimeError, match="paired-sweep"):
         ops.conv_fprop(small, wp, None, ys, 3, 1, 1, engine=ops.ENGINE_TC,
                        signbits=torch.zeros((1, 32, 32, cout // 32), dtype=torch.int32, device=DEV))
+
+
+PAIR_CASES = [
+    # n, h, w, cin of the shared prefix
+    (2, 40, 256, 64),        # lanes = the 256 pixels of a row (both CTAs full), cluster ranges cut at image boundaries
+    (1, 64, 200, 128),       # ragged second strip (72 valid lanes), two K chunks
+    (2, 33, 100, 64),        # one strip only: the second CTA of the pair sweeps nothing but zeros
+    (1, 160, 48, 64),        # narrow image: lanes = image rows (160), sweep over the 48 columns
+    (3, 256, 256, 128),      # conv3 + conv4 at the benchmark's map size
+    (4, 256, 256, 64),       # conv1 + conv2
+]
+
+
+@pytest.mark.parametrize("case", PAIR_CASES)
+def test_conv_tc_fused_pair(case):
+    """srcgan_conv_fprop_pair (two dense-block layers, one launch; csrc/conv_pair.cuh) against torch fp32 convolutions on the
+    same bf16 operands, against the two separate launches it replaces, with packed masks out (forward) and in (mirrored
+    backward step); the launch is bit-reproducible."""
+    from srcgan_b200 import ops
+    n, h, w, cin = case
+    g0 = torch.Generator().manual_seed(71)
+    x = (torch.randn((n, cin, h, w), generator=g0)).bfloat16().float()
+    wa = (torch.randn((32, cin, 3, 3), generator=g0) * 0.05).bfloat16().float()
+    wb = (torch.randn((32, cin + 32, 3, 3), generator=g0) * 0.05).bfloat16().float()
+    ba, bb = torch.randn(32, generator=g0) * 0.1, torch.randn(32, generator=g0) * 0.1
+    wpa = ops.pack_weights(wa.to(DEV), ops.WL_TC, torch.bfloat16)
+    wpb = ops.pack_weights(wb.to(DEV), ops.WL_TC, torch.bfloat16)
+
+    def fresh():
+        buf = torch.zeros((n, h, w, 192), dtype=torch.bfloat16, device=DEV)
+        buf[..., :cin] = x.permute(0, 2, 3, 1).to(DEV)
+        return buf
+
+    def slices(buf):
+        return (ops.Slice(buf, 0, cin), ops.Slice(buf, cin, 32), ops.Slice(buf, 0, cin + 32), ops.Slice(buf, cin + 32, 32))
+
+    # ---- forward form: bias + LeakyReLU, sign bits out
+    buf = fresh()
+    xa, ya, xb, yb = slices(buf)
+    bits = [torch.zeros((n, h, w, 1), dtype=torch.int32, device=DEV) for _ in range(2)]
+    assert ops.conv_fprop_pair(xa, wpa, ba.to(DEV), ya, xb, wpb, bb.to(DEV), yb, act=0.2, signbits=bits), "pair not fused"
+    torch.cuda.synchronize()
+    assert _lib_last_kernel() == "conv3x3_pair_sweep_tc"
+    got_a, got_b = from_nhwc(ya), from_nhwc(yb)
+    ref_a = F.leaky_relu(F.conv2d(x, wa, ba, padding=1), 0.2)
+    assert relerr(got_a, ref_a) < 1e-2, relerr(got_a, ref_a)
+    # layer B against a reference that reads the kernel's own (bf16) x_k: isolates layer B from layer A's rounding
+    ref_b = F.leaky_relu(F.conv2d(torch.cat([x, got_a], 1), wb, bb, padding=1), 0.2)
+    assert relerr(got_b, ref_b) < 1e-2, relerr(got_b, ref_b)
+    if cin + 64 < 192:
+        assert float(buf[..., cin + 64:].abs().max()) == 0.0             # nothing written past the two slices
+    for sl, bt in ((ya, bits[0]), (yb, bits[1])):
+        pos = (sl.view() > 0).view(n, h, w, 1, 32).long()
+        want = (pos << torch.arange(32, device=DEV)).sum(-1)
+        want = torch.where(want >= 2 ** 31, want - 2 ** 32, want).to(torch.int32)
+        assert torch.equal(bt, want)
+    # the two launches it replaces (fp32 summation order differs: agreement to bf16 rounding, not bit for bit)
+    buf2 = fresh()
+    xa2, ya2, xb2, yb2 = slices(buf2)
+    ops.conv_fprop(xa2, wpa, ba.to(DEV), ya2, 3, 1, 1, act=0.2, engine=ops.ENGINE_TC)
+    ops.conv_fprop(xb2, wpb, bb.to(DEV), yb2, 3, 1, 1, act=0.2, engine=ops.ENGINE_TC)
+    torch.cuda.synchronize()
+    assert relerr(got_a, from_nhwc(ya2)) < 4e-3 and relerr(got_b, from_nhwc(yb2)) < 8e-3
+    # bit-reproducible
+    buf3 = fresh()
+    xa3, ya3, xb3, yb3 = slices(buf3)
+    assert ops.conv_fprop_pair(xa3, wpa, ba.to(DEV), ya3, xb3, wpb, bb.to(DEV), yb3, act=0.2)
+    torch.cuda.synchronize()
+    assert torch.equal(buf3, buf)
+    # ---- mirrored-backward form: no bias, no activation, packed masks in
+    mb = [torch.randint(-2 ** 31, 2 ** 31 - 1, (n, h, w, 1), dtype=torch.int64, generator=g0).to(torch.int32).to(DEV)
+          for _ in range(2)]
+    buf4, buf5 = fresh(), fresh()
+    xa4, ya4, xb4, yb4 = slices(buf4)
+    assert ops.conv_fprop_pair(xa4, wpa, None, ya4, xb4, wpb, None, yb4, maskbits=mb, mask_slope=0.2)
+    torch.cuda.synchronize()
+    if h >= 96:                                                           # the unfused kernel reads packed masks on maps >= 96 rows
+        xa5, ya5, xb5, yb5 = slices(buf5)
+        ops.conv_fprop(xa5, wpa, None, ya5, 3, 1, 1, maskbits=mb[0], mask_slope=0.2, engine=ops.ENGINE_TC)
+        ops.conv_fprop(xb5, wpb, None, yb5, 3, 1, 1, maskbits=mb[1], mask_slope=0.2, engine=ops.ENGINE_TC)
+        torch.cuda.synchronize()
+        assert relerr(from_nhwc(ya4), from_nhwc(ya5)) < 4e-3 and relerr(from_nhwc(yb4), from_nhwc(yb5)) < 8e-3
+    bit = lambda t: ((t.view(n, h, w, 1, 1).long() >> torch.arange(32, device=DEV)) & 1).view(n, h, w, 32).bool().cpu()
+    ref_m = F.conv2d(x, wa, None, padding=1).permute(0, 2, 3, 1)
+    ref_m = torch.where(bit(mb[0]), ref_m, 0.2 * ref_m)
+    got_m = ya4.view().float().cpu()
+    assert relerr(got_m, ref_m) < 1e-2
+    ref_n = F.conv2d(torch.cat([x, got_m.permute(0, 3, 1, 2)], 1), wb, None, padding=1).permute(0, 2, 3, 1)
+    ref_n = torch.where(bit(mb[1]), ref_n, 0.2 * ref_n)
+    assert relerr(yb4.view().float().cpu(), ref_n) < 1e-2
+
+
+def test_conv_tc_fused_pair_declines():
+    """Shapes the fused kernel does not cover return False without launching (the caller falls back to two launches)."""
+    from srcgan_b200 import ops
+    n, h, w = 1, 64, 320                                                  # lane extent 320 > 256
+    buf = torch.zeros((n, h, w, 192), dtype=torch.bfloat16, device=DEV)
+    wpa = ops.pack_weights(torch.zeros((32, 64, 3, 3), device=DEV), ops.WL_TC, torch.bfloat16)
+    wpb = ops.pack_weights(torch.zeros((32, 96, 3, 3), device=DEV), ops.WL_TC, torch.bfloat16)
+    before = _lib_launch_count()
+    assert not ops.conv_fprop_pair(ops.Slice(buf, 0, 64), wpa, None, ops.Slice(buf, 64, 32),
+                                   ops.Slice(buf, 0, 96), wpb, None, ops.Slice(buf, 96, 32))
+    # layer B must read [prefix | layer A's output]
+    buf = torch.zeros((1, 128, 128, 192), dtype=torch.bfloat16, device=DEV)
+    assert not ops.conv_fprop_pair(ops.Slice(buf, 0, 64), wpa, None, ops.Slice(buf, 96, 32),
+                                   ops.Slice(buf, 0, 96), wpb, None, ops.Slice(buf, 128, 32))
+    assert _lib_launch_count() == before
 
 
 @pytest.mark.parametrize("cin,cout", [(64, 32), (160, 32), (192, 64)])
