@@ -62,3 +62,37 @@ for k, c, t in rows[:45]:
 print("\nATen / other kernels still on the path:")
 for k, c, t in aten[:25]:
     print("%-90s %7d %10.0f %6.2f%%" % (k[:90], c, t, 100 * t / tot))
+
+# ---- where the device idles: gaps between consecutive kernels on the timeline (same profiler run)
+evs = []
+for e in prof.events():
+    dt = getattr(e, "device_type", None)
+    if dt is not None and "CUDA" in str(dt) and e.time_range.end > e.time_range.start:
+        evs.append((e.time_range.start, e.time_range.end, e.name))
+evs.sort()
+if evs:
+    gaps = []
+    end = evs[0][1]
+    prev = evs[0][2]
+    for s, t, name in evs[1:]:
+        if s > end:
+            gaps.append((s - end, prev, name))
+        if t > end:
+            end, prev = t, name
+    total_gap = sum(g[0] for g in gaps)
+    print("\ntimeline: first kernel start -> last kernel end %.1f ms; %d gaps, %.2f ms idle in total" % (
+        (evs[-1][1] - evs[0][0]) / 1e3, len(gaps), total_gap / 1e3))
+    for lo, hi in ((0, 2), (2, 5), (5, 20), (20, 100), (100, 1e9)):
+        sel = [g[0] for g in gaps if lo <= g[0] < hi]
+        print("  gaps of %5g - %5g us: %5d, %.2f ms" % (lo, hi, len(sel), sum(sel) / 1e3))
+    print("largest gaps (us, after kernel -> before kernel):")
+    for g in sorted(gaps, key=lambda g: -g[0])[:25]:
+        print("  %8.1f  %-60s -> %s" % (g[0], g[1][:60], g[2][:60]))
+    by_prev = {}
+    for g in gaps:
+        d = by_prev.setdefault(g[1][:70], [0, 0.0])
+        d[0] += 1
+        d[1] += g[0]
+    print("idle time by the kernel that ran before the gap:")
+    for k, (c, t) in sorted(by_prev.items(), key=lambda kv: -kv[1][1])[:15]:
+        print("  %8.1f us in %4d gaps after %s" % (t, c, k))

@@ -1221,12 +1221,13 @@ __device__ __forceinline__ void publish_unit(int* list, uint64_t* bars, int i, i
 // warp 0 producer, warp 1 MMA issuer, then SW2_GROUPS epilogue groups of four warps.  A group has SW2_GROUPS column periods
 // to drain one column.  Three groups (448 threads) were measured at +1 % and cap the kernel at 128 registers per thread,
 // which spills once the side operands are prefetched; two groups (320 threads, 170 registers) it is.
-constexpr int SW2_GROUPS = 2;
-constexpr int SW2_THREADS = 64 + 128 * SW2_GROUPS;
-template <int BN, int CG>
-__global__ void __launch_bounds__(SW2_THREADS, 1)
+constexpr int sw2_threads(int groups) { return 64 + 128 * groups; }
+// SIDE = false: no residual / bf16-mask operands (compiled out: the lean epilogue fits four groups into 96 registers)
+template <int BN, int CG, int SW2_GROUPS = 2, bool SIDE = true>
+__global__ void __launch_bounds__(sw2_threads(SW2_GROUPS), 1)
 conv3x3_sweep2_tc(const __grid_constant__ CUtensorMap tmap_x, const Sw2Args a) {
   using C = Sw2Cfg<BN, CG>;
+  constexpr int SW2_THREADS = sw2_threads(SW2_GROUPS);
   constexpr int NBLK = C::NBLK, RUN = C::RUN;
   extern __shared__ uint8_t smem_raw[];
   uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~(uintptr_t)1023);
@@ -1544,15 +1545,17 @@ conv3x3_sweep2_tc(const __grid_constant__ CUtensorMap tmap_x, const Sw2Args a) {
         // residual / mask operands of this pixel do not depend on the accumulator: request them before waiting for it
         // (issued behind the wait they cost one DRAM round trip per column and group - the dgrad launches all have a mask)
         const long long pix = (long long)img * a.img_stride + (long long)y * a.lane_stride + (long long)x * a.sweep_stride;
-        uint4 pr1[4], pr2[4], pmk[4];
+        uint4 pr1[SIDE ? 4 : 1], pr2[SIDE ? 4 : 1], pmk[SIDE ? 4 : 1];
         uint32_t pbits = 0;
         auto fetch_side = [&](int cb) {
           if (a.maskbits) pbits = __ldg(a.maskbits + pix * (BN / 32) + (cb >> 5));
+          if constexpr (SIDE) {
 #pragma unroll
-          for (int gq = 0; gq < 4; ++gq) {
-            if (a.r1) pr1[gq] = __ldg(reinterpret_cast<const uint4*>(a.r1 + pix * a.r1_ld + cb + gq * 8));
-            if (a.r2) pr2[gq] = __ldg(reinterpret_cast<const uint4*>(a.r2 + pix * a.r2_ld + cb + gq * 8));
-            if (a.mask) pmk[gq] = __ldg(reinterpret_cast<const uint4*>(a.mask + pix * a.mask_ld + cb + gq * 8));
+            for (int gq = 0; gq < 4; ++gq) {
+              if (a.r1) pr1[gq] = __ldg(reinterpret_cast<const uint4*>(a.r1 + pix * a.r1_ld + cb + gq * 8));
+              if (a.r2) pr2[gq] = __ldg(reinterpret_cast<const uint4*>(a.r2 + pix * a.r2_ld + cb + gq * 8));
+              if (a.mask) pmk[gq] = __ldg(reinterpret_cast<const uint4*>(a.mask + pix * a.mask_ld + cb + gq * 8));
+            }
           }
         };
         if (real && row_ok) fetch_side(0);
@@ -1617,23 +1620,25 @@ conv3x3_sweep2_tc(const __grid_constant__ CUtensorMap tmap_x, const Sw2Args a) {
               uint4 ov[4];
 #pragma unroll
               for (int gq = 0; gq < 4; ++gq) {
-                if (a.r1) {
-                  float rr[8];
-                  unpack8(pr1[gq], rr);
+                if constexpr (SIDE) {
+                  if (a.r1) {
+                    float rr[8];
+                    unpack8(pr1[gq], rr);
 #pragma unroll
-                  for (int i = 0; i < 8; ++i) f[gq * 8 + i] = fmaf(a.beta1, rr[i], f[gq * 8 + i]);
-                }
-                if (a.r2) {
-                  float rr[8];
-                  unpack8(pr2[gq], rr);
+                    for (int i = 0; i < 8; ++i) f[gq * 8 + i] = fmaf(a.beta1, rr[i], f[gq * 8 + i]);
+                  }
+                  if (a.r2) {
+                    float rr[8];
+                    unpack8(pr2[gq], rr);
 #pragma unroll
-                  for (int i = 0; i < 8; ++i) f[gq * 8 + i] = fmaf(a.beta2, rr[i], f[gq * 8 + i]);
-                }
-                if (a.mask) {
-                  float mm[8];
-                  unpack8(pmk[gq], mm);
+                    for (int i = 0; i < 8; ++i) f[gq * 8 + i] = fmaf(a.beta2, rr[i], f[gq * 8 + i]);
+                  }
+                  if (a.mask) {
+                    float mm[8];
+                    unpack8(pmk[gq], mm);
 #pragma unroll
-                  for (int i = 0; i < 8; ++i) f[gq * 8 + i] *= (mm[i] > 0.f ? 1.f : a.mask_slope);
+                    for (int i = 0; i < 8; ++i) f[gq * 8 + i] *= (mm[i] > 0.f ? 1.f : a.mask_slope);
+                  }
                 }
                 __nv_bfloat162* oh = reinterpret_cast<__nv_bfloat162*>(&ov[gq]);
 #pragma unroll
@@ -1954,20 +1959,20 @@ static int sweep2_ring_depth(int nchunks) {
 }
 
 // co-resident CTA pairs (clusters of CG) for the kernel's shared-memory footprint; queried once per instantiation
-template <int BN, int CG>
+template <int BN, int CG, int G, bool SIDE>
 static int sweep2_max_clusters(size_t smem) {
   static int cached = 0;
   if (cached) return cached;
   int ncl = kNumSMs / CG;
   if (CG > 1) {
     cudaLaunchConfig_t cfg = {};
-    cfg.gridDim = dim3((unsigned)kNumSMs); cfg.blockDim = dim3(SW2_THREADS); cfg.dynamicSmemBytes = smem;
+    cfg.gridDim = dim3((unsigned)kNumSMs); cfg.blockDim = dim3(sw2_threads(G)); cfg.dynamicSmemBytes = smem;
     cudaLaunchAttribute at[1];
     at[0].id = cudaLaunchAttributeClusterDimension;
     at[0].val.clusterDim.x = CG; at[0].val.clusterDim.y = 1; at[0].val.clusterDim.z = 1;
     cfg.attrs = at; cfg.numAttrs = 1;
     int q = 0;
-    const cudaError_t qe = cudaOccupancyMaxActiveClusters(&q, conv3x3_sweep2_tc<BN, CG>, &cfg);
+    const cudaError_t qe = cudaOccupancyMaxActiveClusters(&q, conv3x3_sweep2_tc<BN, CG, G, SIDE>, &cfg);
     if (getenv("SRCGAN_B200_DBG")) fprintf(stderr, "sweep2<%d,%d>: cudaOccupancyMaxActiveClusters -> %s, %d clusters\n", BN, CG, cudaGetErrorString(qe), q);
     if (qe == cudaSuccess && q > 0 && q < ncl) ncl = q;
     (void)cudaGetLastError();
@@ -1995,8 +2000,8 @@ static unsigned int* sweep2_sched_slot() {
   return base[dev] + 2 * (next[dev]++ % SLOTS);
 }
 
-template <int BN, int CG>
-static int launch_sweep2(const CUtensorMap& tx, Sw2Args& a, cudaStream_t st) {
+template <int BN, int CG, int G, bool SIDE>
+static int launch_sweep2_g(const CUtensorMap& tx, Sw2Args& a, cudaStream_t st) {
   using C = Sw2Cfg<BN, CG>;
   a.na = sweep2_ring_depth<BN, CG>(a.nchunks);
   a.strips_y = (a.h + SW_ROWS - 1) / SW_ROWS;
@@ -2004,11 +2009,11 @@ static int launch_sweep2(const CUtensorMap& tx, Sw2Args& a, cudaStream_t st) {
   static DeviceOnce attr_set;
   int attr_set_dev;
   if (attr_set.needed(&attr_set_dev)) {
-    SRCGAN_CUDA(cudaFuncSetAttribute(conv3x3_sweep2_tc<BN, CG>, cudaFuncAttributeMaxDynamicSharedMemorySize, SMEM_BUDGET));
+    SRCGAN_CUDA((cudaFuncSetAttribute(conv3x3_sweep2_tc<BN, CG, G, SIDE>, cudaFuncAttributeMaxDynamicSharedMemorySize, SMEM_BUDGET)));
     attr_set.mark(attr_set_dev);
   }
   const size_t smem = C::smem_bytes(a.nchunks, a.na);
-  const int ncl_max = sweep2_max_clusters<BN, CG>(SMEM_BUDGET);
+  const int ncl_max = sweep2_max_clusters<BN, CG, G, SIDE>(SMEM_BUDGET);
   // segment width: fewest waves x (segment + 2 halo columns) over the co-resident clusters
   const long long groups = (a.strips + CG - 1) / CG;
   long long best = -1;
@@ -2029,15 +2034,29 @@ static int launch_sweep2(const CUtensorMap& tx, Sw2Args& a, cudaStream_t st) {
   if (a.num_units > ncl && (long long)ncl * (SW_MAXU - 1) >= a.num_units && getenv("SRCGAN_B200_SWEEP_DYNAMIC"))
     a.sched = sweep2_sched_slot();
   cudaLaunchConfig_t cfg = {};
-  cfg.gridDim = dim3((unsigned)(ncl * CG)); cfg.blockDim = dim3(SW2_THREADS); cfg.dynamicSmemBytes = smem; cfg.stream = st;
+  cfg.gridDim = dim3((unsigned)(ncl * CG)); cfg.blockDim = dim3(sw2_threads(G)); cfg.dynamicSmemBytes = smem; cfg.stream = st;
   cudaLaunchAttribute at[1];
   at[0].id = cudaLaunchAttributeClusterDimension;
   at[0].val.clusterDim.x = CG; at[0].val.clusterDim.y = 1; at[0].val.clusterDim.z = 1;
   cfg.attrs = at; cfg.numAttrs = 1;
-  SRCGAN_CUDA(cudaLaunchKernelEx(&cfg, conv3x3_sweep2_tc<BN, CG>, tx, a));
+  SRCGAN_CUDA((cudaLaunchKernelEx(&cfg, conv3x3_sweep2_tc<BN, CG, G, SIDE>, tx, a)));
   count_launch();
   return check_launch(BN == 64 ? (CG == 2 ? "conv3x3_sweep2_tc<64,2>" : "conv3x3_sweep2_tc<64,1>")
                                : (CG == 2 ? "conv3x3_sweep2_tc<32,2>" : "conv3x3_sweep2_tc<32,1>"));
+}
+// epilogue groups (SRCGAN_B200_SWEEP_GROUPS=2 turns the third group off for A/B tests)
+template <int BN, int CG>
+static int launch_sweep2(const CUtensorMap& tx, Sw2Args& a, cudaStream_t st) {
+  if constexpr (CG == 2 && BN == 64) {
+    // 64 -> 64 layers (HRconv, upconv) are bound by the epilogue (1 152 clocks of MMAs per column against ~2 600 per group and
+    // column): launches without residual / bf16-mask operands run the lean epilogue (122 registers) with THREE groups - 0.308 ->
+    // 0.258 ms at 64 x 256^2.  With the side operands three groups spill (0.30 -> 0.48 ms), and the 32-channel layers lose with
+    // three groups (0.236 -> 0.257 ms), so both stay at two.
+    const char* e = getenv("SRCGAN_B200_SWEEP_GROUPS");
+    const int groups = e ? atoi(e) : 3;
+    if (!a.r1 && !a.r2 && !a.mask && groups == 3) return launch_sweep2_g<BN, CG, 3, false>(tx, a, st);
+  }
+  return launch_sweep2_g<BN, CG, 2, true>(tx, a, st);
 }
 
 // fused pair of dense-block layers (conv_pair.cuh): depth of the P slab ring that fits beside both layers' weights + the XK ring
