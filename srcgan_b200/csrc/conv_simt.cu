@@ -308,9 +308,33 @@ conv_wgrad_simt(const ConvDev a, float* __restrict__ part, int pix_per_split) {
 template <bool DBL>
 __global__ void __launch_bounds__(256)
 wgrad_reduce_k(const float* __restrict__ part, int splits, int taps, int cin, int cout, int split, float* __restrict__ d0,
-               int ld0, int ci00, float* __restrict__ d1, int ld1, int ci01, int accumulate, float alpha) {
+               int ld0, int ci00, float* __restrict__ d1, int ld1, int ci01, int accumulate, float alpha,
+               const float* __restrict__ dbpart, float* __restrict__ db0, float* __restrict__ db1, int nred) {
   using Acc = typename std::conditional<DBL, double, float>::type;
   __shared__ Acc red[8][33];
+  if ((int)blockIdx.x >= nred) {
+    // blocks behind the weight-gradient ones: the bias gradients of the same launch, db[c] (+)= alpha * sum_s dbpart[s][c]
+    // (what colsum_final does - same partition, same order, double accumulation - without its own launch)
+    __shared__ double redd[8][33];
+    const int ch = ((int)blockIdx.x - nred) * 32 + (int)threadIdx.x, rl = threadIdx.y;
+    double s = 0.0;
+    if (ch < cout)
+      for (int k = rl; k < splits; k += 8) s += (double)dbpart[(int64_t)k * cout + ch];
+    redd[rl][threadIdx.x] = s;
+    __syncthreads();
+    if (rl == 0 && ch < cout) {
+      float* out = ch < split ? db0 : db1;
+      if (out != nullptr) {
+        double t = 0.0;
+#pragma unroll
+        for (int r = 0; r < 8; ++r) t += redd[r][threadIdx.x];
+        t *= (double)alpha;
+        const int c = ch < split ? ch : ch - split;
+        out[c] = accumulate ? out[c] + (float)t : (float)t;
+      }
+    }
+    return;
+  }
   const int64_t total = (int64_t)taps * cin * cout;
   const int64_t i = (int64_t)blockIdx.x * 32 + threadIdx.x;
   const int y = threadIdx.y;
@@ -345,10 +369,13 @@ wgrad_reduce_k(const float* __restrict__ part, int splits, int taps, int cin, in
 
 template <bool DBL>
 static void wgrad_reduce_go(const float* part, int splits, int taps, int cin, int cout, int split, float* d0, int ld0, int ci00,
-                            float* d1, int ld1, int ci01, int accumulate, float alpha, cudaStream_t st) {
+                            float* d1, int ld1, int ci01, int accumulate, float alpha, cudaStream_t st,
+                            const float* dbpart = nullptr, float* db0 = nullptr, float* db1 = nullptr) {
   const int64_t total = (int64_t)taps * cin * cout;
-  wgrad_reduce_k<DBL><<<ceil_div(total, 32), dim3(32, 8), 0, st>>>(part, splits, taps, cin, cout, split, d0, ld0, ci00, d1, ld1,
-                                                                   ci01, accumulate, alpha);
+  const int nred = ceil_div(total, 32);
+  const int ndb = (dbpart && (db0 || db1)) ? ceil_div(cout, 32) : 0;
+  wgrad_reduce_k<DBL><<<nred + ndb, dim3(32, 8), 0, st>>>(part, splits, taps, cin, cout, split, d0, ld0, ci00, d1, ld1, ci01,
+                                                          accumulate, alpha, dbpart, db0, db1, nred);
 }
 
 // db[c] (+)= sum_m G[m][c] : stage 1 partial column sums, stage 2 fixed-order reduce
@@ -974,7 +1001,6 @@ int conv_wgrad_simt(const srcgan_conv_params* p, float* dw, float* db, int accum
 
 int wgrad_reduce_launch(const float* part, int splits, int taps, int cin, int cout, float* dw, int accumulate,
                         float alpha, cudaStream_t st) {
-  int64_t total = (int64_t)taps * cin * cout;
   wgrad_reduce_go<false>(part, splits, taps, cin, cout, cout, dw, cin, 0, nullptr, 0, 0, accumulate, alpha, st);   // tcgen05 partials: float
   count_launch();
   return check_launch("wgrad_reduce");
@@ -996,8 +1022,18 @@ int colsum_final_ld_launch(const float* part, int nparts, int c, int ld, float* 
 
 int wgrad_reduce_split_launch(const float* part, int splits, int taps, int cin, int cout, int split, float* d0, int ld0,
                               int ci00, float* d1, int ld1, int ci01, int accumulate, float alpha, cudaStream_t st) {
-  int64_t total = (int64_t)taps * cin * cout;
   wgrad_reduce_go<false>(part, splits, taps, cin, cout, split, d0, ld0, ci00, d1, ld1, ci01, accumulate, alpha, st);
+  count_launch();
+  return check_launch("wgrad_reduce");
+}
+
+// the same launch also finishes the bias gradients the kw-stacked wgrad kernel summed per split: dbpart [splits][cout] ->
+// db0 (channels [0, split)) / db1 (the rest); either may be null
+int wgrad_reduce_db_launch(const float* part, int splits, int taps, int cin, int cout, int split, float* d0, int ld0, int ci00,
+                           float* d1, int ld1, int ci01, int accumulate, float alpha, const float* dbpart, float* db0, float* db1,
+                           cudaStream_t st) {
+  wgrad_reduce_go<false>(part, splits, taps, cin, cout, split, d0, ld0, ci00, d1, ld1, ci01, accumulate, alpha, st, dbpart, db0,
+                         db1);
   count_launch();
   return check_launch("wgrad_reduce");
 }

@@ -3150,6 +3150,9 @@ int colsum_final_launch(const float* part, int nparts, int c, float* out, int ac
 int colsum_final_ld_launch(const float* part, int nparts, int c, int ld, float* out, int accumulate, float alpha, cudaStream_t st);
 int wgrad_reduce_split_launch(const float* part, int splits, int taps, int cin, int cout, int split, float* d0, int ld0,
                               int ci00, float* d1, int ld1, int ci01, int accumulate, float alpha, cudaStream_t st);
+int wgrad_reduce_db_launch(const float* part, int splits, int taps, int cin, int cout, int split, float* d0, int ld0, int ci00,
+                           float* d1, int ld1, int ci01, int accumulate, float alpha, const float* dbpart, float* db0, float* db1,
+                           cudaStream_t st);
 
 bool conv_wgrad_tc_supported(const srcgan_conv_params* p) {
   if (p->dtype != SRCGAN_DT_BF16 || (p->stride != 1 && p->stride != 2) || p->upsample) return false;
@@ -3218,13 +3221,9 @@ int conv_wgrad_tc_split(const srcgan_conv_params* p, float* dw0, int ld0, int ci
   if (rc) return rc;
   rc = bn == 64 ? tcw4::launch4<64>(tx, tg, a4, st) : tcw4::launch4<32>(tx, tg, a4, st);
   if (rc) return rc;
-  rc = wgrad_reduce_split_launch(reinterpret_cast<const float*>(ws), a4.splits, 9, p->cin, p->cout, split, dw0, ld0, ci00, dw1,
-                                 ld1, ci01, accumulate, p->alpha, st);
-  if (rc) return rc;
-  if (db0) { rc = colsum_final_ld_launch(a4.dbpart, a4.splits, split, p->cout, db0, accumulate, p->alpha, st); if (rc) return rc; }
-  if (db1 && split < p->cout)
-    return colsum_final_ld_launch(a4.dbpart + split, a4.splits, p->cout - split, p->cout, db1, accumulate, p->alpha, st);
-  return SRCGAN_OK;
+  // split-K reduce of the weight gradients and, in the same launch, of the bias gradients the kernel summed per split
+  return wgrad_reduce_db_launch(reinterpret_cast<const float*>(ws), a4.splits, 9, p->cin, p->cout, split, dw0, ld0, ci00, dw1, ld1,
+                                ci01, accumulate, p->alpha, a4.dbpart, db0, split < p->cout ? db1 : nullptr, st);
 }
 
 int conv_wgrad_tc(const srcgan_conv_params* p, float* dw, float* db, int accumulate, void* ws, size_t ws_bytes,
@@ -3251,11 +3250,8 @@ int conv_wgrad_tc(const srcgan_conv_params* p, float* dw, float* db, int accumul
     if (rc) return rc;
     rc = bn == 64 ? tcw4::launch4<64>(tx, tg, a4, st) : tcw4::launch4<32>(tx, tg, a4, st);
     if (rc) return rc;
-    rc = wgrad_reduce_launch(reinterpret_cast<const float*>(ws), a4.splits, 9, p->cin, p->cout, dw, accumulate,
-                             p->alpha, st);
-    if (rc) return rc;
-    if (db) return colsum_final_launch(a4.dbpart, a4.splits, p->cout, db, accumulate, p->alpha, st);   // summed in-kernel
-    return SRCGAN_OK;
+    return wgrad_reduce_db_launch(reinterpret_cast<const float*>(ws), a4.splits, 9, p->cin, p->cout, p->cout, dw, p->cin, 0, nullptr,
+                                  0, 0, accumulate, p->alpha, a4.dbpart, db, nullptr, st);   // bias gradient: summed in-kernel
   } else if (dw && wgrad_halo_ok(p)) {
     tcw3::Wg3Args a3;
     tcw3::plan3(p, a3);
