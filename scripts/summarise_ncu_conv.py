@@ -11,7 +11,8 @@ tag = sys.argv[1] if len(sys.argv) > 1 else "r2d"
 shapes = [json.loads(l) for l in open(os.path.join(ROOT, "gpurun_out", tag + "_conv_shapes.json")) if l.startswith("{")]
 rows = list(csv.reader(open(os.path.join(ROOT, "gpurun_out", tag + "_conv_ncu.csv"))))
 hdr = {h: i for i, h in enumerate(rows[0])}
-launches = [r for r in rows[2:] if "sweep2" in r[hdr["Kernel Name"]] or "wgrad_stack" in r[hdr["Kernel Name"]]]
+launches = [r for r in rows[2:] if "sweep" in r[hdr["Kernel Name"]] or "wgrad_stack" in r[hdr["Kernel Name"]]]
+out_name = sys.argv[2] if len(sys.argv) > 2 else "r2_ncu_conv.txt"
 out, traffic, i = [], {}, 0
 UNIT = {"byte": 1e-6, "Kbyte": 1e-3, "Mbyte": 1.0, "Gbyte": 1e3, "Tbyte": 1e6, "ns": 1e-3, "us": 1.0, "ms": 1e3, "s": 1e6}
 
@@ -38,9 +39,12 @@ for s in shapes:
     out.append("%-46s %9.1f %9.1f %9.1f %9.1f %7.2f %9.0f %8.1f %8.1f" % (s["what"], us, rd, wr, alg, (rd + wr) / alg, s["flops"] / us / 1e6, tens, util))
     name = r[hdr["Kernel Name"]]
     fam = s["kernel"]
-    if fam not in traffic or "160->32" in s["what"] or ("64->32 @ 64x256" in s["what"] and "sweep2_tc<32" in fam) or ("192->64" in s["what"] and "sweep2_tc<64" in fam):
-        traffic[fam] = {"bytes_per_launch": (rd + wr) * 1e6, "note": "%s: dram read %.0f MB + write %.0f MB per launch vs %.0f MB algorithmic, tensor pipe active %.1f %% (ncu --set full, profiles/r2_ncu_conv.txt)" % (s["what"], rd, wr, alg, tens)}
-open(os.path.join(ROOT, "profiles", "r2_ncu_conv.txt"), "w").write("\n".join(out) + "\n")
+    # the shape bench.py names for a family: the one that carries most of the family's time in the step
+    prefer = {"conv3x3_wgrad_stack_tc": "wgrad 192->64", "conv3x3_pair_sweep_tc": "128->32 + 160->32", "conv3x3_sweep2_tc<64,2>": "192->64",
+              "conv3x3_sweep2_tc<32,2>": "64->32 @ 64x256"}
+    if fam not in traffic or prefer.get(fam, "\0") in s["what"]:
+        traffic[fam] = {"bytes_per_launch": (rd + wr) * 1e6, "note": "%s: dram read %.0f MB + write %.0f MB per launch vs %.0f MB algorithmic, tensor pipe active %.1f %% (ncu --set full, profiles/%s)" % (s["what"], rd, wr, alg, tens, out_name)}
+open(os.path.join(ROOT, "profiles", out_name), "w").write("\n".join(out) + "\n")
 json.dump(traffic, open(os.path.join(ROOT, "profiles", "traffic.json"), "w"), indent=1)
 print("\n".join(out))
 print(json.dumps(traffic, indent=1))
