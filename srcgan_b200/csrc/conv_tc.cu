@@ -2337,7 +2337,7 @@ int conv_fprop_pair_tc(const srcgan_conv_params* pa, const srcgan_conv_params* p
   }
   { const char* d = getenv("SRCGAN_B200_DBG"); a.dbg = d ? atoi(d) : 0; }
   { const char* d = getenv("SRCGAN_B200_PAIR_PFD"); a.pfd = d ? atoi(d) : 0; }
-  { const char* d = getenv("SRCGAN_B200_PAIR_ISSUERS"); a.issuers = d ? atoi(d) : 1; }
+  { const char* d = getenv("SRCGAN_B200_PAIR_ISSUERS"); a.issuers = (d && atoi(d) == 1) ? 1 : 2; }
   return tc::launch_pair_sweep(tx, a, st);
 }
 
