@@ -1113,6 +1113,9 @@ struct Sw2Args {
   int planar;                           // 1: x is a planar concat buffer [group][n][h][w][64]: tmap_x is 5-D, K chunk k = group k
   int rev;                              // 1: work units in descending order (last image first): the layer then starts on the data the
                                         //    previous layer of a dense block touched last, which is what still sits in the 126 MB L2
+  int per, total;                       // per > 0: "range mode" - the total = (strip groups) x w input columns of the launch are dealt to
+                                        //    the clusters as equal contiguous ranges of `per` columns, cut into units at group boundaries
+                                        //    (64 images x 256 columns on 74 CTA pairs: 222 columns each instead of 64 units of 256)
   int dbg;
 };
 
@@ -1283,6 +1286,10 @@ conv3x3_sweep2_tc(const __grid_constant__ CUtensorMap tmap_x, const Sw2Args a) {
 
   // i-th unit of this CTA pair (-1: none left)
   auto get_unit = [&](int i) -> int {
+    if (a.per > 0) {                                                   // range mode: the i-th strip group this cluster's range touches
+      const int g0 = cid * a.per, g1 = (g0 + a.per) < a.total ? (g0 + a.per) : a.total;
+      return (g0 < g1 && (g0 / a.w + i) * a.w < g1) ? i : -1;
+    }
     if (a.sched == nullptr) { const int u = cid + i * ncl; return u < a.num_units ? (a.rev ? a.num_units - 1 - u : u) : -1; }
     if (CG == 2 && rank == 1) mbar_wait_cluster(&u_full[i], 0); else mbar_wait(&u_full[i], 0);
     return reinterpret_cast<volatile int*>(unit_list)[i];
@@ -1299,15 +1306,27 @@ conv3x3_sweep2_tc(const __grid_constant__ CUtensorMap tmap_x, const Sw2Args a) {
 
   // unit u -> column segment [x_start, x_end) of strip (u / segs_x) * CG + rank; an absent strip (odd total) sweeps
   // rows below the image: its loads are zero-filled, its stores suppressed
+#define SRCGAN_DECODE_SW2_RANGE(u)                                                 \
+  uint32_t sg_;                                                                    \
+  int x_start, x_end;                                                              \
+  if (a.per > 0) {                                                                 \
+    const int g0_ = cid * a.per, g1_ = (g0_ + a.per) < a.total ? (g0_ + a.per) : a.total; \
+    sg_ = (uint32_t)(g0_ / a.w + (u));                                             \
+    const int base_ = (int)sg_ * a.w;                                              \
+    x_start = (u) == 0 ? g0_ - base_ : 0;                                          \
+    x_end = (g1_ - base_) < a.w ? (g1_ - base_) : a.w;                             \
+  } else {                                                                         \
+    sg_ = (uint32_t)(u) / (uint32_t)a.segs_x;                                      \
+    const int seg_ = (int)((uint32_t)(u) - sg_ * (uint32_t)a.segs_x);              \
+    x_start = seg_ * a.wseg;                                                       \
+    x_end = (x_start + a.wseg) < a.w ? (x_start + a.wseg) : a.w;                   \
+  }
 #define SRCGAN_DECODE_SW2_UNIT(u)                                                  \
-  const uint32_t sg_ = (uint32_t)(u) / (uint32_t)a.segs_x;                         \
-  const int seg = (int)((uint32_t)(u) - sg_ * (uint32_t)a.segs_x);                 \
+  SRCGAN_DECODE_SW2_RANGE(u)                                                       \
   const int sidx = (int)sg_ * CG + (int)rank;                                      \
   const bool strip_ok = sidx < a.strips;                                           \
   const int img = strip_ok ? sidx / a.strips_y : 0;                                \
-  const int y0 = strip_ok ? (sidx - img * a.strips_y) * SW_ROWS : a.h + 1;         \
-  const int x_start = seg * a.wseg;                                                \
-  const int x_end = (x_start + a.wseg) < a.w ? (x_start + a.wseg) : a.w;
+  const int y0 = strip_ok ? (sidx - img * a.strips_y) * SW_ROWS : a.h + 1;
 
   if (warp == 0) {
     // ---- producer: this CTA's weight rows once, then one column slab per (input column, K chunk)
@@ -1404,9 +1423,8 @@ conv3x3_sweep2_tc(const __grid_constant__ CUtensorMap tmap_x, const Sw2Args a) {
       for (int ui = 0;; ++ui) {
         const int u = get_unit(ui);
         if (u < 0) break;
-        const int seg = u % a.segs_x;
-        const int x_start = seg * a.wseg;
-        const int x_end = (x_start + a.wseg) < a.w ? (x_start + a.wseg) : a.w;
+        SRCGAN_DECODE_SW2_RANGE(u)
+        (void)sg_;
         for (int c = x_start - 1; c <= x_end; ++c) {
           if (prof) { tc0 = clock64(); ++ncol; }
           // blocks touched for the first time in this lap must have been drained (and zeroed) by the epilogues
@@ -1677,6 +1695,7 @@ conv3x3_sweep2_tc(const __grid_constant__ CUtensorMap tmap_x, const Sw2Args a) {
 #undef SRCGAN_TICK
   }
 #undef SRCGAN_DECODE_SW2_UNIT
+#undef SRCGAN_DECODE_SW2_RANGE
   tc_fence_before();
   __syncthreads();
   if (CG == 2) cluster_sync_all();                                     // the peer may still signal this CTA's barriers
@@ -2025,13 +2044,23 @@ static int launch_sweep2_g(const CUtensorMap& tx, Sw2Args& a, cudaStream_t st) {
     const long long cost = waves * (ws + 2);
     if (best < 0 || cost < best) { best = cost; a.wseg = ws; a.segs_x = (int)segs; a.num_units = (int)units; }
   }
-  const int ncl = a.num_units < ncl_max ? a.num_units : ncl_max;
+  int ncl = a.num_units < ncl_max ? a.num_units : ncl_max;
+  // range mode: equal contiguous column ranges instead of whole units when that shortens the longest cluster's sweep
+  // (every unit a range is cut into sweeps 2 halo columns)
+  a.per = 0;
+  a.total = (int)(groups * a.w);
+  if (!getenv("SRCGAN_B200_NO_SWEEP_RANGES") && !getenv("SRCGAN_B200_SWEEP_DYNAMIC") && !a.rev) {
+    int per = (a.total + ncl_max - 1) / ncl_max;
+    if (per < 8) per = 8;
+    const long long range_cost = per + 2 * ((per + a.w - 1) / a.w + 1);
+    if (range_cost < best) { a.per = per; ncl = (a.total + per - 1) / per; }
+  }
   // The dynamic unit queue is opt-in: which output columns straddle a lap of the accumulator ring (two partial blocks added
   // in the epilogue instead of one accumulation chain) depends on a pair's position in its unit sequence, so claiming units
   // at run time changes the fp32 summation order of a few columns from run to run (last-bit differences after the bf16
   // rounding).  Round-robin units keep the kernel bit-reproducible; the queue is worth +15 % on 64->32, +1 % on a dense block.
   a.sched = nullptr;
-  if (a.num_units > ncl && (long long)ncl * (SW_MAXU - 1) >= a.num_units && getenv("SRCGAN_B200_SWEEP_DYNAMIC"))
+  if (a.per == 0 && a.num_units > ncl && (long long)ncl * (SW_MAXU - 1) >= a.num_units && getenv("SRCGAN_B200_SWEEP_DYNAMIC"))
     a.sched = sweep2_sched_slot();
   cudaLaunchConfig_t cfg = {};
   cfg.gridDim = dim3((unsigned)(ncl * CG)); cfg.blockDim = dim3(sw2_threads(G)); cfg.dynamicSmemBytes = smem; cfg.stream = st;
