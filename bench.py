@@ -440,8 +440,14 @@ def wl_gd(args, dev, rank):
     def step_resident():
         model.optimize_parameters(real_A, real_B)
 
+    feed = [None]
+
     def step_e2e():
-        rb = host_B.to(dev, non_blocking=True)                       # pinned host -> device, every step
+        if feed[0] is None:       # the training loop's host -> device feed: every step's batch is copied from pinned host memory,
+            import itertools      # one step ahead on a side stream (srcgan_b200/data.py), so the copy overlaps the previous step
+            from srcgan_b200 import data
+            feed[0] = data.DevicePrefetcher(itertools.repeat(host_B), dev)
+        rb = next(feed[0])                                            # pinned host -> device, every step
         ra = F.interpolate(rb, scale_factor=0.25, mode="nearest")     # as train.py:381-382
         model.optimize_parameters(ra, rb)
         return 4 * len(model.current_losses())                        # device -> host read of the 9 losses

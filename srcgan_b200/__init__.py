@@ -6,6 +6,7 @@ Public surface:
   srcgan_b200.metrics   MSE, PSNR, AE, SSIM                          (drop-in for src/metrics.py)
   srcgan_b200.color     rgb2lab / lab2rgb on the device
   srcgan_b200.trainer   SRCycleGAN step driver mirroring src/train.py:145-340
+  srcgan_b200.data      DevicePrefetcher: the host -> device feed of the training loop, one batch ahead on a side stream
   srcgan_b200.dropin/   directory to put on PYTHONPATH so the reference's unmodified scripts
                         (`import model`, `import losses`, `import metrics`) resolve to this package
 """

@@ -328,3 +328,9 @@ def test_update_lr_mirrors_the_reference_epoch_schedule():
             train.SRCycleGAN.update_lr(h, ropt)
         assert h.optimizers[0].param_groups[0]["lr"] == pytest.approx(1e-4 * f ** 3, rel=1e-9)
         assert h.optimizers[1].param_groups[0]["lr"] == pytest.approx(1e-5 * f ** 3, rel=1e-9)
+
+
+def test_device_prefetcher_refuses_cpu():
+    from srcgan_b200 import data
+    with pytest.raises(RuntimeError, match="CUDA device"):
+        data.DevicePrefetcher([torch.zeros(2)], "cpu")

@@ -603,3 +603,18 @@ def test_tall_image_conv_kernel_separators():
     packed = (wantbits << torch.arange(32, dtype=torch.int64)).sum(-1)
     agree = ((sb.to(torch.int64) & 0xFFFFFFFF) == packed).float().mean()
     assert float(agree) > 0.999          # (a value that rounds to +-0 in bf16 may differ)
+
+
+@pytest.mark.gpu
+def test_device_prefetcher_yields_every_batch_once_in_order():
+    """srcgan_b200.data.DevicePrefetcher: the copies run one batch ahead on a side stream; values, order and count are those of
+    the host iterable (tensors and tuples)."""
+    from srcgan_b200 import data
+    host = [(torch.full((3, 5), float(i)).pin_memory(), torch.arange(4) + i) for i in range(5)]
+    got = list(data.DevicePrefetcher(host, "cuda:0"))
+    assert len(got) == 5
+    for i, (a, b) in enumerate(got):
+        assert a.is_cuda and b.is_cuda
+        assert torch.equal(a.cpu(), host[i][0]) and torch.equal(b.cpu(), host[i][1])
+    single = list(data.DevicePrefetcher([torch.ones(2).pin_memory()], "cuda:0"))
+    assert len(single) == 1 and torch.equal(single[0].cpu(), torch.ones(2))
