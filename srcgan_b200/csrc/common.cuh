@@ -4,6 +4,7 @@
 #include <cuda_runtime.h>
 #include <stdint.h>
 #include <stdio.h>
+#include <stdlib.h>
 
 #include "../../include/srcgan_b200.h"
 
@@ -72,5 +73,22 @@ struct DeviceOnce {
 };
 
 static inline int ceil_div(int64_t a, int64_t b) { return (int)((a + b - 1) / b); }
+
+// Programmatic dependent launch (sm_90+).  A kernel launched with pdl_attr() may start while its predecessor in the stream is
+// still draining: its CTAs are scheduled as soon as every CTA of the predecessor has executed pdl_launch_dependents() (or
+// exited) and an SM has room, run their prologue (barrier init, TMEM allocation, weight / bias loads - data no triggering
+// kernel writes) and block in pdl_wait() until the predecessor grid has completed and its writes are visible.  EVERY global
+// access to data another kernel of the step produces or still reads - activations in, outputs, workspaces - must come after
+// pdl_wait().  Kernels that write parameters or packed weights never call pdl_launch_dependents(), so nothing can start (and
+// pre-load weights) before they are done.  Both instructions are no-ops in a launch without the attribute.
+__device__ __forceinline__ void pdl_launch_dependents() { asm volatile("griddepcontrol.launch_dependents;" ::: "memory"); }
+__device__ __forceinline__ void pdl_wait() { asm volatile("griddepcontrol.wait;" ::: "memory"); }
+// fills one launch attribute; returns the number of attributes written (0 when SRCGAN_B200_NO_PDL is set)
+static inline int pdl_attr(cudaLaunchAttribute* at) {
+  if (getenv("SRCGAN_B200_NO_PDL")) return 0;
+  at->id = cudaLaunchAttributeProgrammaticStreamSerialization;
+  at->val.programmaticStreamSerializationAllowed = 1;
+  return 1;
+}
 
 }  // namespace srcgan

@@ -116,6 +116,7 @@ conv3x3_pair_sweep_tc(const __grid_constant__ CUtensorMap tmap_x, const SwfArgs 
   const uint32_t rank = cluster_ctarank();
   const int cid = (int)(blockIdx.x / CG);
   const bool no_halo = (a.dbg & 128) != 0;
+  pdl_launch_dependents();                                             // the next kernel's prologue may overlap this kernel's tail
   if (threadIdx.x == 0) {
     for (int s = 0; s < a.na; ++s) { mbar_init(&a_full[s], 1); mbar_init(&a_empty[s], a.issuers == 2 ? 2 : 1); }
     for (int s = 0; s < 16; ++s) { mbar_init(&y_full[s], 1); mbar_init(&y_empty[s], 4 * CG); }
@@ -193,6 +194,7 @@ conv3x3_pair_sweep_tc(const __grid_constant__ CUtensorMap tmap_x, const SwfArgs 
     }
     int as = 0;
     uint32_t aph = 0;
+    pdl_wait();                                                        // the prefix is the previous kernels' output
     for (int ui = 0;; ++ui) {
       int img, xs, xe;
       if (!unit(ui, img, xs, xe)) break;
@@ -369,6 +371,7 @@ conv3x3_pair_sweep_tc(const __grid_constant__ CUtensorMap tmap_x, const SwfArgs 
     const uint32_t lane_base = tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)(gb ? SWF_TB0 : 0);
     const bool wide_st = (Ly_ld % 16 == 0) && ((reinterpret_cast<uintptr_t>(Ly) & 31) == 0);
     auto arrive_empty = [&](int blk) { mbar_arrive_leader(&y_empty[ring + blk]); };
+    pdl_wait();                                                        // packed masks in, outputs the previous kernels may still read
     int T = 0;                                                         // input columns of this cluster's stream
     for (int ui = 0;; ++ui) {
       int img, xs, xe;

@@ -312,6 +312,8 @@ wgrad_reduce_k(const float* __restrict__ part, int splits, int taps, int cin, in
                const float* __restrict__ dbpart, float* __restrict__ db0, float* __restrict__ db1, int nred) {
   using Acc = typename std::conditional<DBL, double, float>::type;
   __shared__ Acc red[8][33];
+  pdl_launch_dependents();
+  pdl_wait();                                                          // the partials are the wgrad kernel's output
   if ((int)blockIdx.x >= nred) {
     // blocks behind the weight-gradient ones: the bias gradients of the same launch, db[c] (+)= alpha * sum_s dbpart[s][c]
     // (what colsum_final does - same partition, same order, double accumulation - without its own launch)
@@ -374,8 +376,12 @@ static void wgrad_reduce_go(const float* part, int splits, int taps, int cin, in
   const int64_t total = (int64_t)taps * cin * cout;
   const int nred = ceil_div(total, 32);
   const int ndb = (dbpart && (db0 || db1)) ? ceil_div(cout, 32) : 0;
-  wgrad_reduce_k<DBL><<<nred + ndb, dim3(32, 8), 0, st>>>(part, splits, taps, cin, cout, split, d0, ld0, ci00, d1, ld1, ci01,
-                                                          accumulate, alpha, dbpart, db0, db1, nred);
+  cudaLaunchConfig_t cfg = {};
+  cfg.gridDim = dim3((unsigned)(nred + ndb)); cfg.blockDim = dim3(32, 8); cfg.dynamicSmemBytes = 0; cfg.stream = st;
+  cudaLaunchAttribute at[1];
+  cfg.attrs = at; cfg.numAttrs = pdl_attr(&at[0]);
+  (void)cudaLaunchKernelEx(&cfg, wgrad_reduce_k<DBL>, part, splits, taps, cin, cout, split, d0, ld0, ci00, d1, ld1, ci01, accumulate,
+                           alpha, dbpart, db0, db1, nred);
 }
 
 // db[c] (+)= sum_m G[m][c] : stage 1 partial column sums, stage 2 fixed-order reduce

@@ -1251,6 +1251,7 @@ conv3x3_sweep2_tc(const __grid_constant__ CUtensorMap tmap_x, const Sw2Args a) {
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const uint32_t rank = CG == 2 ? cluster_ctarank() : 0u;
   const int cid = (int)(blockIdx.x / CG), ncl = (int)(gridDim.x / CG);
+  pdl_launch_dependents();                                             // the next kernel's prologue may overlap this kernel's tail
   if (threadIdx.x == 0) {
     for (int s = 0; s < a.na; ++s) { mbar_init(&a_full[s], 1); mbar_init(&a_empty[s], 1); }
     for (int s = 0; s < NBLK; ++s) { mbar_init(&y_full[s], 1); mbar_init(&y_empty[s], 4 * CG); }
@@ -1355,6 +1356,7 @@ conv3x3_sweep2_tc(const __grid_constant__ CUtensorMap tmap_x, const Sw2Args a) {
     }
     int as = 0;
     uint32_t aph = 0;
+    pdl_wait();                                                        // the activations are the previous kernels' outputs
     const bool fetcher = a.sched != nullptr && rank == 0;
     if (fetcher && elect_one()) claim_unit(0);
     __syncwarp();
@@ -1510,6 +1512,7 @@ conv3x3_sweep2_tc(const __grid_constant__ CUtensorMap tmap_x, const Sw2Args a) {
     const int row = q * 32 + lane;
     const uint32_t lane_base = tmem_base + ((uint32_t)(q * 32) << 16);
     const bool wide_st = (a.y_ld % 16 == 0) && ((reinterpret_cast<uintptr_t>(a.y) & 31) == 0);
+    pdl_wait();                                                        // side operands in, outputs the previous kernels may still read
     auto arrive_empty = [&](int blk) {
       if (CG == 1) mbar_arrive(&y_empty[blk]); else mbar_arrive_leader(&y_empty[blk]);
     };
@@ -2064,10 +2067,10 @@ static int launch_sweep2_g(const CUtensorMap& tx, Sw2Args& a, cudaStream_t st) {
     a.sched = sweep2_sched_slot();
   cudaLaunchConfig_t cfg = {};
   cfg.gridDim = dim3((unsigned)(ncl * CG)); cfg.blockDim = dim3(sw2_threads(G)); cfg.dynamicSmemBytes = smem; cfg.stream = st;
-  cudaLaunchAttribute at[1];
+  cudaLaunchAttribute at[2];
   at[0].id = cudaLaunchAttributeClusterDimension;
   at[0].val.clusterDim.x = CG; at[0].val.clusterDim.y = 1; at[0].val.clusterDim.z = 1;
-  cfg.attrs = at; cfg.numAttrs = 1;
+  cfg.attrs = at; cfg.numAttrs = 1 + pdl_attr(&at[1]);
   SRCGAN_CUDA((cudaLaunchKernelEx(&cfg, conv3x3_sweep2_tc<BN, CG, G, SIDE>, tx, a)));
   count_launch();
   return check_launch(BN == 64 ? (CG == 2 ? "conv3x3_sweep2_tc<64,2>" : "conv3x3_sweep2_tc<64,1>")
@@ -2128,10 +2131,10 @@ static int launch_pair_sweep(const CUtensorMap& tx, SwfArgs& a, cudaStream_t st)
   cudaLaunchConfig_t cfg = {};
   cfg.gridDim = dim3((unsigned)(ncl * 2)); cfg.blockDim = dim3(SWF_THREADS); cfg.dynamicSmemBytes = swf_smem_bytes(a.nchunks, a.na);
   cfg.stream = st;
-  cudaLaunchAttribute at[1];
+  cudaLaunchAttribute at[2];
   at[0].id = cudaLaunchAttributeClusterDimension;
   at[0].val.clusterDim.x = 2; at[0].val.clusterDim.y = 1; at[0].val.clusterDim.z = 1;
-  cfg.attrs = at; cfg.numAttrs = 1;
+  cfg.attrs = at; cfg.numAttrs = 1 + pdl_attr(&at[1]);
   SRCGAN_CUDA(cudaLaunchKernelEx(&cfg, conv3x3_pair_sweep_tc, tx, a));
   count_launch();
   return check_launch("conv3x3_pair_sweep_tc");
@@ -2946,6 +2949,7 @@ conv3x3_wgrad_stack_tc(const __grid_constant__ CUtensorMap tmap_x, const __grid_
   uint64_t* done_bar = empty_bar + WS_STAGES;
   uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(done_bar + 1);
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  pdl_launch_dependents();
 
   int b = blockIdx.x;
   const int split = b % a.splits; b /= a.splits;
@@ -2980,6 +2984,7 @@ conv3x3_wgrad_stack_tc(const __grid_constant__ CUtensorMap tmap_x, const __grid_
   if (warp == 0) {
     int stage = 0;
     uint32_t phase = 0;
+    pdl_wait();                                                        // X and dY are the previous kernels' outputs
     for (long long t = t_beg; t < t_end; ++t) {
       // tiles run down a 16-pixel-wide strip first: the two halo rows a tile shares with the tile above were read one
       // tile ago and still sit in L2 (x-first order re-read them 16 tiles later: 2.9 GB of DRAM reads for 1.6 GB of data)
@@ -3035,6 +3040,7 @@ conv3x3_wgrad_stack_tc(const __grid_constant__ CUtensorMap tmap_x, const __grid_
     const int q = warp & 3;
     const int row = q * 32 + lane;
     const bool has_work = t_end > t_beg;
+    pdl_wait();                                                        // the partials' workspace is still being reduced by the previous launch
     if (do_db) {
       // thread = (8-channel group cg, pixel lane): 16-byte reads from the swizzled slab [8 rows][18 px][BN ch]
       // (interior pixels only; pixels outside the image were zero-filled by TMA)
@@ -3164,7 +3170,11 @@ static int launch4(const CUtensorMap& tx, const CUtensorMap& tg, const Wg4Args& 
     attr_set.mark(attr_set_dev);
   }
   const unsigned grid = (unsigned)(a.cblocks * a.nblocks * a.splits);
-  conv3x3_wgrad_stack_tc<BN><<<grid, NUM_THREADS, C::SMEM, st>>>(tx, tg, a);
+  cudaLaunchConfig_t cfg = {};
+  cfg.gridDim = dim3(grid); cfg.blockDim = dim3(NUM_THREADS); cfg.dynamicSmemBytes = C::SMEM; cfg.stream = st;
+  cudaLaunchAttribute at[1];
+  cfg.attrs = at; cfg.numAttrs = pdl_attr(&at[0]);
+  SRCGAN_CUDA(cudaLaunchKernelEx(&cfg, conv3x3_wgrad_stack_tc<BN>, tx, tg, a));
   count_launch();
   return check_launch(BN == 64 ? "conv3x3_wgrad_stack_tc<64>" : "conv3x3_wgrad_stack_tc<32>");
 }
