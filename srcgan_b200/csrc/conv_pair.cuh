@@ -54,6 +54,7 @@ struct SwfArgs {
 
 constexpr int SWF_BN = 32, SWF_N = 3 * SWF_BN;
 constexpr int SWF_RUN_A = 4, SWF_RUN_B = 8;                            // laps; blocks = RUN + 2: 6 + 10 = 16 x 32 TMEM columns
+                                                                       // (5 / 7 measures the same, 6 / 6 is 6-8 % slower)
 constexpr int SWF_TB0 = (SWF_RUN_A + 2) * SWF_BN, SWF_YB0 = SWF_RUN_A + 2;   // ring B: first TMEM column, first barrier index
 constexpr int SWF_W_KH_BYTES = SWF_N * 128 / 2, SWF_W_CHUNK_BYTES = 3 * SWF_W_KH_BYTES;     // per CTA of the pair
 constexpr int SWF_NXK = 4;                                                                  // XK column slots (two per slab)
