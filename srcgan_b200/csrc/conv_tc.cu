@@ -2912,9 +2912,10 @@ struct W4Cfg {
   static constexpr int PX = BN * 2;                                   // bytes of one dY pixel in the slab
   static constexpr int G_BYTES = WS_TH * WS_G_W * PX;                 // [8 rows][18 px][BN ch]: 9216 / 18432
   static constexpr int STAGE = NATOM * WS_X_ATOM + G_BYTES;           // 50176 / 38912
-  static constexpr int STAGES_RAW = (SMEM_BUDGET - SMEM_AUX - 1024) / STAGE;
+  static constexpr int STAGES_RAW = (SMEM_BUDGET - SMEM_AUX - 2048 - 1024) / STAGE;
   static constexpr int STAGES = STAGES_RAW > 6 ? 6 : STAGES_RAW;      // 4 / 5
-  static constexpr int SMEM = STAGES * STAGE + SMEM_AUX + 1024;
+  static constexpr int ZROW = WS_TW * 128;                            // one all-zero slab row [16 px][64 ch] (the phantom tap's operand)
+  static constexpr int SMEM = STAGES * STAGE + SMEM_AUX + ZROW + 1024;
   static_assert(STAGES >= 3, "wgrad pipeline too shallow");
 };
 
@@ -2925,6 +2926,7 @@ struct Wg4Args {
   long long num_tiles, tiles_per_split;
   float* part;
   float* dbpart;                        // [splits][cout] column sums of dY (bias gradient partials), or nullptr
+  int zero_phantom;                     // 1: the phantom fourth tap multiplies a row of zeros (SRCGAN_B200_WGRAD_PHANTOM=data: the slab)
 };
 
 __host__ __device__ constexpr uint32_t desc_hi_sw64(uint32_t sbo_bytes) {
@@ -2948,8 +2950,11 @@ conv3x3_wgrad_stack_tc(const __grid_constant__ CUtensorMap tmap_x, const __grid_
   uint64_t* empty_bar = full_bar + WS_STAGES;
   uint64_t* done_bar = empty_bar + WS_STAGES;
   uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(done_bar + 1);
+  uint8_t* zrow = aux + SMEM_AUX;                                      // zeros: see the MMA warp
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   pdl_launch_dependents();
+  for (int i = threadIdx.x; i < C::ZROW / 16; i += NUM_THREADS) sts_u4(smem_u32(zrow) + (uint32_t)i * 16u, make_uint4(0u, 0u, 0u, 0u));
+  asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
 
   int b = blockIdx.x;
   const int split = b % a.splits; b /= a.splits;
@@ -3011,6 +3016,8 @@ conv3x3_wgrad_stack_tc(const __grid_constant__ CUtensorMap tmap_x, const __grid_
     int stage = 0;
     uint32_t phase = 0;
     uint32_t accumulate = 0;
+    const uint32_t z_addr = smem_u32(zrow);
+    const bool zero_phantom = a.zero_phantom != 0;
     for (long long t = t_beg; t < t_end; ++t) {
       mbar_wait(&full_bar[stage], phase);
       tc_fence_after();
@@ -3023,6 +3030,19 @@ conv3x3_wgrad_stack_tc(const __grid_constant__ CUtensorMap tmap_x, const __grid_
         for (int g = 0; g < ngroups; ++g) {
           const int kh0 = paired ? 2 * g : g;                           // vertical tap of the first half of M
           const uint32_t tmem_d = tmem_base + (uint32_t)(g * C::N);
+          if (paired && g == 1 && zero_phantom) {
+            // taps (2, phantom 3): the second 64-row half of M has no tap to compute - it would multiply the slab row below
+            // the tile's last one.  Point it at a row of zeros instead (LBO = distance from this k-step's row to `zrow`): the
+            // result rows are discarded either way, but multipliers fed with zeros do not toggle, and the kernel runs at the
+            // board's power limit.
+#pragma unroll
+            for (int r = 0; r < WS_TH; ++r) {
+              const uint32_t row_addr = sx + (uint32_t)((r + 2) * ROW_A);
+              umma_bf16_w(tmem_d, desc_lo(row_addr, z_addr - row_addr), a_hi, g_lo + (uint32_t)((r * ROW_G) >> 4), g_hi, idesc,
+                          accumulate | (uint32_t)(r > 0));
+            }
+            continue;
+          }
 #pragma unroll
           for (int r = 0; r < WS_TH; ++r)
             umma_bf16_w(tmem_d, a_lo + (uint32_t)(((r + kh0) * ROW_A) >> 4), a_hi, g_lo + (uint32_t)((r * ROW_G) >> 4), g_hi, idesc,
@@ -3140,6 +3160,7 @@ static void plan4(const srcgan_conv_params* p, Wg4Args& a) {
   if (s < 1) s = 1;
   a.tiles_per_split = (a.num_tiles + s - 1) / s;
   a.splits = (int)((a.num_tiles + a.tiles_per_split - 1) / a.tiles_per_split);
+  a.zero_phantom = getenv("SRCGAN_B200_WGRAD_PHANTOM") ? 0 : 1;
 }
 
 // NHWC bf16 tensor -> tensor map with an explicit box [boxc ch][boxw px][rows] and swizzle
