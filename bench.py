@@ -45,7 +45,10 @@ def parse():
                     help="gd = BASELINE configs[1] (default, the driver's line); cascade / cascade_lab / eval = configs[2..4]")
     ap.add_argument("--batch", type=int, default=None, help="units per GPU per step (default: 64 patches; eval: 16 tiles)")
     ap.add_argument("--tile-batch", type=int, default=8, help="eval workload: tiles per generator forward (1 = the reference's loop)")
-    ap.add_argument("--no-overlap", action="store_true", help="N>1: flat all-reduce in the step pre-hook instead of the bucket reducer")
+    ap.add_argument("--overlap", action="store_true", help="N>1: launch each network's bucket all-reduce from inside backward "
+                    "(default: in the optimizer step pre-hook; the overlap loses time, see srcgan_b200/dist.py)")
+    ap.add_argument("--no-overlap", action="store_true", help="N>1: flat cat / all-reduce / copy-back in the step pre-hook "
+                    "instead of the bucket reducer")
     ap.add_argument("--lr-size", type=int, default=64, help="LR patch edge (HR = 4x)")
     ap.add_argument("--precision", default="bf16", choices=["bf16", "fp32"])
     ap.add_argument("--no-cpu-baseline", action="store_true")
@@ -567,7 +570,7 @@ def run_ours(args):
     reducer = None
     if world > 1 and wl["nets"]:
         sdist.broadcast_module_state(wl["nets"])
-        reducer = sdist.attach(wl["opts"], wl["nets"], overlap=not args.no_overlap)
+        reducer = sdist.attach(wl["opts"], wl["nets"], overlap=args.overlap, bucketed=not args.no_overlap)
     B = wl["units"]
 
     def barrier():
@@ -652,9 +655,12 @@ def run_ours(args):
         cfg["algorithmic_gflop_per_unit"] = wl["gflop"]
         cfg["step_tflops"] = value * wl["gflop"] / 1e3 / world
     if reducer is not None and hasattr(reducer, "launched"):
-        cfg["allreduce"] = {"overlapped_launches": reducer.launched, "fallbacks": reducer.fallbacks,
-                            "how": "one NCCL all_reduce per network over its flat gradient bucket, launched inside backward "
-                                   "when the network's last wgrad has been issued, joined in the optimizer step pre-hook"}
+        cfg["allreduce"] = {"overlapped_launches": reducer.launched, "pre_hook_launches": reducer.deferred,
+                            "fallbacks": reducer.fallbacks,
+                            "how": "one in-place NCCL all_reduce per network over its flat gradient bucket, " +
+                                   ("launched inside backward when the network's last wgrad has been issued, joined in the "
+                                    "optimizer step pre-hook" if reducer.overlap else
+                                    "launched and joined (stream-side) in the optimizer step pre-hook")}
     line = {
         "metric": wl["metric"], "value": value, "unit": wl["unit"], "n_gpus": world, "steps": args.steps, "warmup": args.warmup,
         "ms_per_step": ms / args.steps, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,

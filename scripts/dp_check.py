@@ -31,7 +31,7 @@ def main():
     A = trainer.SRCycleGAN(opt)
     torch.manual_seed(0)
     B = trainer.SRCycleGAN(opt)
-    reducer = sdist.make_data_parallel(A)
+    reducer = sdist.make_data_parallel(A, overlap=bool(int(os.environ.get('DP_CHECK_OVERLAP', '0'))))
     for n in ("G_A", "G_B", "D_A", "D_B"):
         getattr(B, "net" + n).load_state_dict(getattr(A, "net" + n).state_dict())
     g = torch.Generator().manual_seed(100 + rank)                  # rank-local shard
@@ -65,8 +65,10 @@ def main():
         dist.all_reduce(lo, op=dist.ReduceOp.MIN)
         dist.all_reduce(hi, op=dist.ReduceOp.MAX)
         assert torch.equal(lo, hi), n
-    report.update(worst_rel_err_vs_manual_mean=worst, overlapped_launches=reducer.launched, fallbacks=reducer.fallbacks)
-    assert reducer.launched == 8 and reducer.fallbacks == 0, (reducer.launched, reducer.fallbacks)   # 4 buckets x 2 steps
+    report.update(worst_rel_err_vs_manual_mean=worst, overlapped_launches=reducer.launched, pre_hook_launches=reducer.deferred,
+                  fallbacks=reducer.fallbacks)
+    assert reducer.launched + reducer.deferred == 8 and reducer.fallbacks == 0, (reducer.launched, reducer.deferred,
+                                                                                 reducer.fallbacks)   # 4 buckets x 2 steps
     if rank == 0:
         print(json.dumps(report), flush=True)
     dist.barrier()

@@ -8,7 +8,7 @@ here ``sync_buffers`` averages them on demand, and ``checkpoint.save_state`` cal
 the only exchange is the all-reduce of the fp32 gradients right before each optimizer step.  The
 trainers construct their optimizers themselves (train.py:191-192), so the exchange is attached as an
 optimizer *step pre-hook*: nothing in the trainer has to change.  ~27 MB per step over NVSwitch is
-<0.1% of a step; it is issued on the compute stream right after the last wgrad.
+<0.1% of a step (see BucketReducer for why it is NOT overlapped with the backward pass by default).
 """
 from __future__ import annotations
 
@@ -69,21 +69,30 @@ def allreduce_mean_(tensors: List[torch.Tensor]) -> None:
 
 
 class BucketReducer:
-    """Overlapped gradient exchange.  Every network of ``srcgan_b200.nn`` writes its parameter gradients into
-    ONE flat fp32 bucket (``nn._GradBucket``; ``param.grad`` is a view of it).  When the last pending backward of a network
-    has been issued - inside ``loss.backward()``, on autograd's thread - its ``_grads_ready_hook`` fires and the bucket's
-    ``all_reduce`` is launched asynchronously: NCCL's stream waits for the compute stream at that point and the reduction
-    runs beside the rest of the backward pass (G_B's 12.8 MB while G_A's last backward runs; D_A's while D_B's runs).  The
-    optimizer *step pre-hook* joins (a stream-side wait, no host synchronisation).  No ``torch.cat``, no copy back.
+    """Bucketed gradient exchange.  Every network of ``srcgan_b200.nn`` writes its parameter gradients into
+    ONE flat fp32 bucket (``nn._GradBucket``; ``param.grad`` is a view of it), so the exchange is one in-place NCCL
+    ``all_reduce`` (AVG) per network - no ``torch.cat``, no copy back - joined by a stream-side wait (no host
+    synchronisation) in the optimizer *step pre-hook*.
+
+    ``overlap=False`` (default): the all-reduces are launched in the pre-hook itself, when the compute stream has nothing
+    else to run.  ``overlap=True``: when the last pending backward of a network has been issued - inside
+    ``loss.backward()``, on autograd's thread - its ``_grads_ready_hook`` fires and the bucket's all-reduce is launched
+    right there: NCCL's stream waits for the compute stream at that point and the reduction runs beside the rest of the
+    backward pass (G_B's 12.8 MB while G_A's last backward runs; D_A's while D_B's runs).  Measured on two B200s the
+    overlap LOSES 13 ms of a 256 ms step (profiles/r2_bench_2gpu_*.json): 27 MB over NVLink take ~0.1 ms, there is nothing
+    to hide, while the convolution kernels are persistent grids over all 74 CTA pairs with a static split of the work -
+    every SM NCCL's kernels hold for a while turns one pair's share into a straggler.
 
     Gradients that are not bucket views at step time (a foreign ``.grad``, a module without buckets, a network whose
     backward never completed) go through the flat-copy fallback so the result is always the mean over ranks."""
 
-    def __init__(self, nets, optimizers):
+    def __init__(self, nets, optimizers, overlap: bool = False):
         self.nets = [n for n in nets if hasattr(n, "grad_bucket")]
         self.pending = {}            # id(net) -> (work, writes at launch)
-        self.launched = 0
+        self.launched = 0            # all-reduces launched from inside backward (overlap mode)
+        self.deferred = 0            # all-reduces launched in the step pre-hook
         self.fallbacks = 0
+        self.overlap = bool(overlap)
         self.avg = dist.get_backend() == "nccl"
         for n in self.nets:
             n.__dict__["_grads_ready_hook"] = self._ready
@@ -95,7 +104,7 @@ class BucketReducer:
 
     def _ready(self, net) -> None:
         b = net.grad_bucket()
-        if b.flat is None:
+        if b.flat is None or not self.overlap:
             return
         if id(net) in self.pending:
             raise RuntimeError("srcgan_b200.dist: a second backward pass wrote gradients after this network's all-reduce "
@@ -120,9 +129,12 @@ class BucketReducer:
             got = self.pending.pop(id(net), None)
             if got is not None and got[1] != b.writes:
                 raise RuntimeError("srcgan_b200.dist: gradients were written after the all-reduce was launched")
-            if got is None:                                      # the ready hook never fired: reduce here, synchronously
+            if got is None:                                      # not launched from inside backward: reduce here
                 work = dist.all_reduce(b.flat, op=dist.ReduceOp.AVG if self.avg else dist.ReduceOp.SUM, async_op=True)
-                self.fallbacks += 1
+                if self.overlap:
+                    self.fallbacks += 1                          # the ready hook should have fired
+                else:
+                    self.deferred += 1
             else:
                 work = got[0]
             work.wait()                                          # the compute stream waits for NCCL's; the host does not
@@ -158,20 +170,22 @@ def _step_pre_hook(optimizer, args, kwargs):
     allreduce_mean_(grads)
 
 
-def attach(optimizers: Iterable[torch.optim.Optimizer], nets: Iterable[torch.nn.Module] = (), overlap: bool = True):
+def attach(optimizers: Iterable[torch.optim.Optimizer], nets: Iterable[torch.nn.Module] = (), overlap: bool = False,
+           bucketed: bool = True):
     """Average gradients over ranks before every ``optimizer.step()``.  With ``nets`` (the ``srcgan_b200.nn`` modules the
-    optimizers own) and ``overlap`` the exchange is the bucketed, overlapped ``BucketReducer``; otherwise one flat
-    all-reduce inside the step pre-hook.  Returns the reducer (or the hook handles)."""
+    optimizers own) the exchange is the ``BucketReducer`` (one in-place all-reduce per network's gradient bucket; launched
+    in the step pre-hook, or from inside backward with ``overlap``); without them, or with ``bucketed=False``, one flat
+    cat / all-reduce / copy-back inside the step pre-hook.  Returns the reducer (or the hook handles)."""
     if world() == 1:
         return []
     optimizers = list(optimizers)
     nets = list(nets)
-    if overlap and nets:
-        return BucketReducer(nets, optimizers)
+    if bucketed and nets:
+        return BucketReducer(nets, optimizers, overlap)
     return [opt.register_step_pre_hook(_step_pre_hook) for opt in optimizers]
 
 
-def make_data_parallel(model, overlap: bool = True):
+def make_data_parallel(model, overlap: bool = False):
     """``model``: a trainer.SRCycleGAN (or the reference's own, built on the drop-in modules).  Broadcast + hooks."""
     nets = [model.netG_A, model.netG_B, model.netD_A, model.netD_B]
     broadcast_module_state(nets)

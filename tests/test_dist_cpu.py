@@ -2,6 +2,7 @@
 import os
 import socket
 
+import pytest
 import torch
 import torch.distributed as dist
 import torch.multiprocessing as mp
@@ -92,7 +93,7 @@ class _HostNet:
         return HostNet()
 
 
-def _bucket_worker(rank, world, port, out):
+def _bucket_worker(rank, world, port, out, overlap):
     os.environ.update(MASTER_ADDR="127.0.0.1", MASTER_PORT=str(port), RANK=str(rank), WORLD_SIZE=str(world),
                       LOCAL_RANK=str(rank))
     from srcgan_b200 import dist as sdist
@@ -104,7 +105,7 @@ def _bucket_worker(rank, world, port, out):
     ref = _HostNet.make()                                      # autograd reference of the same maths, plain torch
     ref.load_state_dict(net.state_dict())
     opt = torch.optim.SGD(list(net.parameters()) + list(extra.parameters()), lr=0.1)
-    red = sdist.attach([opt], [net])
+    red = sdist.attach([opt], [net], overlap=overlap)
     assert isinstance(red, sdist.BucketReducer)
     for it in range(3):
         g = torch.Generator().manual_seed(10 * it + rank)
@@ -122,8 +123,11 @@ def _bucket_worker(rank, world, port, out):
         (e(f(x1)).square().mean() + 2.0 * e(f(x2)).square().mean()).backward()
         local = {k: v.grad.clone() for k, v in ws.items()}
         launched = red.launched
-        opt.step()                                             # pre-hook joins the all-reduce launched inside backward
-        assert launched == it + 1 and red.launched == it + 1   # ... it was launched by the ready hook, not by the pre-hook
+        opt.step()                                             # pre-hook joins (overlap) or launches + joins the all-reduce
+        if overlap:
+            assert launched == it + 1 and red.launched == it + 1 and red.deferred == 0   # launched by the ready hook
+        else:
+            assert red.launched == 0 and red.deferred == it + 1 and red.fallbacks == it + 1   # (fallbacks: the loose grads)
         for k, p in net.named_parameters():
             parts = [torch.zeros_like(local[k]) for _ in range(world)]
             dist.all_gather(parts, local[k])
@@ -139,17 +143,19 @@ def _bucket_worker(rank, world, port, out):
         p.requires_grad = False
     x = torch.rand(2, 4, requires_grad=True)
     net(x).sum().backward()
-    assert x.grad is not None and red.launched == 3
+    assert x.grad is not None and red.launched == (3 if overlap else 0)
     if rank == 0:
         out.put("ok")
     dist.destroy_process_group()
 
 
-def test_bucket_views_and_overlapped_reducer_world2_gloo():
+@pytest.mark.parametrize("overlap", [False, True])
+def test_bucket_views_and_reducer_world2_gloo(overlap):
+    """The bucket reducer in both modes: all-reduce launched in the optimizer step pre-hook (default) or from inside backward."""
     ctx = mp.get_context("spawn")
     out = ctx.Queue()
     port = _free_port()
-    procs = [ctx.Process(target=_bucket_worker, args=(r, 2, port, out)) for r in range(2)]
+    procs = [ctx.Process(target=_bucket_worker, args=(r, 2, port, out, overlap)) for r in range(2)]
     for p in procs:
         p.start()
     for p in procs:
