@@ -3172,8 +3172,12 @@ static int make_tmap_box(CUtensorMap* tm, const void* ptr, int c, int w, int h, 
   cuuint64_t gstr[3] = {(cuuint64_t)ld * 2, (cuuint64_t)ld * 2 * w, (cuuint64_t)ld * 2 * w * h};
   cuuint32_t box[4] = {(cuuint32_t)boxc, (cuuint32_t)boxw, (cuuint32_t)rows, 1};
   cuuint32_t estr[4] = {1, 1, 1, 1};
+  // a 32-channel slice of a wider buffer is 64 useful bytes per pixel: with 128-byte L2 promotion every pixel pulls the whole
+  // line from DRAM (ncu: 2.12x the algorithmic bytes on the 32 -> 32 remainders of the paired wgrads, which are HBM-bound)
+  const bool narrow = (c < boxc ? c : boxc) * 2 <= 64 && ld > c && !getenv("SRCGAN_B200_NO_L2_64B");
   CUresult cr = encode(tm, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 4, const_cast<void*>(ptr), gdim, gstr, box, estr,
-                       CU_TENSOR_MAP_INTERLEAVE_NONE, sw, CU_TENSOR_MAP_L2_PROMOTION_L2_128B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+                       CU_TENSOR_MAP_INTERLEAVE_NONE, sw, narrow ? CU_TENSOR_MAP_L2_PROMOTION_L2_64B : CU_TENSOR_MAP_L2_PROMOTION_L2_128B,
+                       CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
   if (cr != CUDA_SUCCESS) {
     set_error("%s: cuTensorMapEncodeTiled failed with CUresult %d", what, (int)cr);
     return SRCGAN_E_CUDA;
