@@ -229,6 +229,7 @@ conv3x3_pair_sweep_tc(const __grid_constant__ CUtensorMap tmap_x, const SwfArgs 
       constexpr uint32_t idesc = umma_idesc(TILE_M * CG, SWF_N);
       constexpr uint32_t hi = desc_hi(1024);
       constexpr int LAG = 3;                                           // the x_k part trails the P stream by three columns
+                                                                       // (2 and 4, and an XK ring of 8, measure the same)
       mbar_wait(w_full, 0);
       mbar_wait(w_pair, 0);
       const uint32_t wa_lo = desc_lo(smem_u32(smem_wa)), wb_lo = desc_lo(smem_u32(smem_wb));
