@@ -428,6 +428,68 @@ def test_conv_tc_sweep_variants(env, monkeypatch):
         assert torch.equal(got.buf, base.buf)
 
 
+@pytest.mark.parametrize("env,exact", [({"SRCGAN_B200_SWEEP_GROUPS": "2"}, True), ({"SRCGAN_B200_NO_PDL": "1"}, True),
+                                       ({"SRCGAN_B200_NO_SWEEP_RANGES": "1"}, False)])
+def test_conv_tc_lean_epilogue_and_launch_variants(env, exact, monkeypatch):
+    """64 -> 64 without residual / mask operands runs the lean epilogue with three groups, range-mode scheduling and
+    programmatic dependent launch by default.  Two groups and ordinary stream-ordered launches give the SAME bits (the order of
+    the MMAs does not change); whole-image units instead of column ranges move the lap boundaries of the accumulator ring, so
+    they agree to fp32 rounding."""
+    from srcgan_b200 import ops
+    n, h, w, cin, cout = 5, 256, 256, 64, 64
+    g0 = torch.Generator(device=DEV).manual_seed(5)
+    xb = torch.randn((n, h, w, 192), dtype=torch.bfloat16, device=DEV, generator=g0)
+    wt = torch.randn((cout, cin, 3, 3), device=DEV, generator=g0) * 0.05
+    wp = ops.pack_weights(wt, ops.WL_TC, torch.bfloat16)
+    b = torch.randn(cout, device=DEV, generator=g0)
+
+    def run():
+        y = ops.Slice(torch.zeros((n, h, w, cout), dtype=torch.bfloat16, device=DEV))
+        # back to back, so that the second launch starts under the first one's tail when dependent launch is on
+        ops.conv_fprop(ops.Slice(xb, 0, cin), wp, b, y, 3, 1, 1, act=0.2, engine=ops.ENGINE_TC)
+        y2 = ops.Slice(torch.zeros((n, h, w, cout), dtype=torch.bfloat16, device=DEV))
+        ops.conv_fprop(y, wp, b, y2, 3, 1, 1, act=0.2, engine=ops.ENGINE_TC)
+        torch.cuda.synchronize()
+        return y.buf, y2.buf
+
+    base = run()
+    ref = F.leaky_relu(F.conv2d(xb[..., :cin].float().permute(0, 3, 1, 2), wt.bfloat16().float(), b, padding=1), 0.2)
+    assert relerr(base[0].float().permute(0, 3, 1, 2).cpu(), ref.cpu()) < 1e-2
+    for k, v in env.items():
+        monkeypatch.setenv(k, v)
+    got = run()
+    if exact:
+        assert torch.equal(got[0], base[0]) and torch.equal(got[1], base[1])
+    else:
+        assert relerr(got[0].float().cpu(), base[0].float().cpu()) < 4e-3 and relerr(got[1].float().cpu(), base[1].float().cpu()) < 8e-3
+
+
+@pytest.mark.parametrize("env", [{"SRCGAN_B200_WGRAD_PHANTOM": "1"}, {"SRCGAN_B200_NO_L2_64B": "1"}, {"SRCGAN_B200_NO_PDL": "1"}])
+def test_wgrad_stack_variants_bit_identical(env, monkeypatch):
+    """The stacked wgrad kernel's phantom tap (zeros vs slab data), the L2 promotion of its 32-channel tensor maps and the
+    dependent launch change nothing in the result."""
+    from srcgan_b200 import ops
+    n, h, w = 3, 128, 96
+    g0 = torch.Generator(device=DEV).manual_seed(9)
+    X = torch.randn((n, h, w, 192), dtype=torch.bfloat16, device=DEV, generator=g0)
+    D = torch.randn((n, h, w, 192), dtype=torch.bfloat16, device=DEV, generator=g0)
+
+    def run():
+        out = []
+        for cin, c0, cout, d0 in ((64, 0, 64, 0), (32, 64, 32, 96), (160, 0, 32, 64)):
+            dw, db = torch.empty(cout, cin, 3, 3, device=DEV), torch.empty(cout, device=DEV)
+            ops.conv_wgrad(ops.Slice(X, c0, cin), ops.Slice(D, d0, cout), dw, db, 3, 1, 1, engine=ops.ENGINE_TC)
+            out += [dw, db]
+        torch.cuda.synchronize()
+        return out
+
+    base = run()
+    for k, v in env.items():
+        monkeypatch.setenv(k, v)
+    got = run()
+    assert all(torch.equal(a, b) for a, b in zip(base, got))
+
+
 @pytest.mark.parametrize("cin,cout", [(96, 32), (64, 64)])
 def test_conv_tc_packed_masks(cin, cout):
     """signbits out == (stored activation > 0); a launch with maskbits == the same launch with the bf16 activation as mask,
