@@ -1222,10 +1222,12 @@ __device__ __forceinline__ void publish_unit(int* list, uint64_t* bars, int i, i
 }
 
 // warp 0 producer, warp 1 MMA issuer, then SW2_GROUPS epilogue groups of four warps.  A group has SW2_GROUPS column periods
-// to drain one column.  Three groups (448 threads) were measured at +1 % and cap the kernel at 128 registers per thread,
-// which spills once the side operands are prefetched; two groups (320 threads, 170 registers) it is.
+// to drain one column (one warp needs ~2 000 clocks per [32 lanes][32 channels] block: the thin layers are bound by this
+// epilogue, not by their MMAs).  With the residual / bf16-mask operands compiled in (SIDE = true, 165 registers) a third
+// group caps the kernel at 128 registers and spills (64 -> 64: 0.30 -> 0.48 ms), so that variant runs two groups.
+// SIDE = false compiles those operands out (122 registers): three groups without spills, used for 64 output channels
+// (0.308 -> 0.258 ms); for 32 output channels a third group loses (0.236 -> 0.257 ms).
 constexpr int sw2_threads(int groups) { return 64 + 128 * groups; }
-// SIDE = false: no residual / bf16-mask operands (compiled out: the lean epilogue fits four groups into 96 registers)
 template <int BN, int CG, int SW2_GROUPS = 2, bool SIDE = true>
 __global__ void __launch_bounds__(sw2_threads(SW2_GROUPS), 1)
 conv3x3_sweep2_tc(const __grid_constant__ CUtensorMap tmap_x, const Sw2Args a) {
