@@ -246,8 +246,13 @@ struct Cfg {
   static_assert(NA >= 3, "not enough shared memory for the activation ring");
 };
 
+// two epilogue groups of four warps (warps 2..5, 6..9) share every accumulator: group g takes the 32-column chunks with
+// (chunk index % 2) == g.  One group needed ~1 200 clocks per (tile, chunk) = ~10 000 per super-tile of BN = 128, more than the
+// 9 216 clocks of MMAs of a 3x3 128 -> 128 layer: the low-K layers of the Decoder / discriminators were bound by it.
+constexpr int IG_GROUPS = 2;
+constexpr int IG_THREADS = 64 + 128 * IG_GROUPS;
 template <int BN, int MAXT>
-__global__ void __launch_bounds__(NUM_THREADS, 1)
+__global__ void __launch_bounds__(IG_THREADS, 1)
 conv_igemm_tc(const __grid_constant__ CUtensorMap tmap_x, const TcArgs a) {
   using C = Cfg<BN, MAXT>;
   constexpr int MT = C::MT;
@@ -270,10 +275,10 @@ conv_igemm_tc(const __grid_constant__ CUtensorMap tmap_x, const TcArgs a) {
   if (threadIdx.x == 0) {
     for (int s = 0; s < C::NA; ++s) { mbar_init(&a_full[s], 1); mbar_init(&a_empty[s], 1); }
     for (int s = 0; s < C::NB; ++s) { mbar_init(&b_full[s], 1); mbar_init(&b_empty[s], 1); }
-    for (int s = 0; s < 2; ++s) { mbar_init(&tfull_bar[s], 1); mbar_init(&tempty_bar[s], 128); }
+    for (int s = 0; s < 2; ++s) { mbar_init(&tfull_bar[s], 1); mbar_init(&tempty_bar[s], 128 * IG_GROUPS); }
     asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
   }
-  for (int i = threadIdx.x; i < 256; i += NUM_THREADS) sbias[i] = (a.bias && i < a.cout) ? a.bias[i] : 0.f;
+  for (int i = threadIdx.x; i < 256; i += IG_THREADS) sbias[i] = (a.bias && i < a.cout) ? a.bias[i] : 0.f;
   if (warp == 1) {
     asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(tmem_slot)),
                  "r"((uint32_t)C::TMEM_COLS)
@@ -393,8 +398,9 @@ conv_igemm_tc(const __grid_constant__ CUtensorMap tmap_x, const TcArgs a) {
       }
     }
   } else {
-    // ------------------------------------------------------------------ epilogue (warps 2..5)
+    // ------------------------------------------------------------------ epilogue (warps 2..5 and 6..9)
     const int q = warp & 3;                        // TMEM lane quadrant this warp may access
+    const int eg = (warp - 2) >> 2;                // epilogue group: its share of the 32-column chunks
     const int row = q * 32 + lane;                 // GEMM row = tile pixel
     const int ty = row >> 3, tx = row & 7;
     int set = 0;
@@ -411,7 +417,7 @@ conv_igemm_tc(const __grid_constant__ CUtensorMap tmap_x, const TcArgs a) {
         const long long pix = ((long long)img * a.oh + (y * a.os + a.oa)) * a.ow + (x * a.os + a.ob);
         const uint32_t taddr = tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)((set * MT + m) * BN);
 #pragma unroll 1
-        for (int cb = 0; cb < BN; cb += 32) {
+        for (int cb = eg * 32; cb < BN; cb += 32 * IG_GROUPS) {
           uint32_t v[32];
           tmem_ld32(taddr + cb, v);
           if (valid) {
@@ -1900,7 +1906,7 @@ static int launch(const CUtensorMap& tmap, const TcArgs& a, cudaStream_t st) {
     attr_set.mark(attr_set_dev);
   }
   long long grid = a.num_tiles < kNumSMs ? a.num_tiles : kNumSMs;
-  conv_igemm_tc<BN, MAXT><<<(unsigned)grid, NUM_THREADS, C::SMEM_BYTES, st>>>(tmap, a);
+  conv_igemm_tc<BN, MAXT><<<(unsigned)grid, IG_THREADS, C::SMEM_BYTES, st>>>(tmap, a);
   count_launch();
   return check_launch(BN == 128 ? "conv_igemm_tc<128>" : (BN == 64 ? "conv_igemm_tc<64>" : "conv_igemm_tc<32>"));
 }
