@@ -53,6 +53,8 @@ def parse():
     ap.add_argument("--precision", default="bf16", choices=["bf16", "fp32"])
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-e2e", action="store_true")
+    ap.add_argument("--by-shape", action="store_true",
+                    help="key the roofline record's families by kernel | call shape instead of by kernel family")
     return ap.parse_args()
 
 
@@ -610,6 +612,7 @@ def run_ours(args):
     # per-kernel timing for the roofline record: the same steps again with CUDA events around every convolution launch
     # (the event records cost ~8 % of a step, so this pass is separate and its wall time is only the share denominator)
     ops.timer.enabled = True
+    ops.timer.by_shape = args.by_shape
     ops.timer.reset()
     ms_instr = timed(step_resident, args.steps)
     ops.timer.enabled = False

@@ -206,6 +206,7 @@ class KernelTimer:
 
     def __init__(self):
         self.enabled = False
+        self.by_shape = False  # key every record by "kernel | kind n x h x w cin->cout k s" (scripts/profile_shapes.py)
         self.records = []      # (key, flops, start_event, end_event, algorithmic bytes)
 
     def reset(self):
@@ -238,6 +239,9 @@ class _Timed:
                 stacked = p.cout in (32, 64) and p.cin >= 16 and p.cin % 8 == 0 and p.pad == 1     # wgrad_stack_ok
                 self.key = "conv3x3_wgrad_stack_tc" if stacked else "conv3x3_wgrad_halo_tc<%d>" % (64 if p.cout % 64 == 0 else 32)
             self.flops = 2.0 * p.n * p.ho * p.wo * p.cin * p.cout * p.kh * p.kw
+            self.shape = "%s %dx%dx%d %d->%d k%d s%d" % (kind, p.n, p.h, p.w, p.cin, p.cout, p.kh, p.stride)
+            if extra is not None:
+                self.shape += " + %d->%d" % (extra.cin, extra.cout)
             # algorithmic bytes (single read of the input slice, single write / read of the output-side slice; stride and
             # the epilogue's residual / mask operands ignored): what an HBM roofline is computed from
             esz = 2 if p.dtype == DT_BF16 else 4
@@ -260,6 +264,8 @@ class _Timed:
                 name = _lib.last_kernel()
                 if name.startswith("conv"):
                     self.key = name
+            if timer.by_shape:
+                self.key += " | " + self.shape
             timer.records.append((self.key, self.flops, self.a, self.b, self.bytes))
         return False
 
