@@ -653,6 +653,125 @@ thin_in_conv(const ConvDev a) {
 }
 
 // ---------------------------------------------------------------------------------------------
+// thin_in_tiled : <= 4 GEMM-K channels and a multiple of 64 output channels (first discriminator layer 3 -> 64 4x4 stride 2,
+// ResDeconv's 7x7 stride-2 stem, gradient of the 256 -> 1 patch-logit layer), FFMA-bound instead of load-bound.
+// thin_in_conv above issues one scalar global load and two shared-memory loads per 8 FMAs and recomputes the source
+// pixel per tap (7x7 stem at batch 64: 2.3 ms for 9.9 GFMA).  Here a block owns a tile of 8 x 32 output pixels x 64 channels:
+//   * the haloed input patch of the tile sits in shared memory as fp32 planes [k channel][row][col] (zero outside the image),
+//     the layer's weights as [tap * kch][64] fp32, loaded once per block (persistent over tiles);
+//   * a warp = 32 columns x one 16-channel group x 4 rows: per (tap, k channel) a thread reads 4 patch values (consecutive
+//     lanes -> consecutive or every-second bank) and 4 x LDS.128 of weights (warp-uniform broadcast) for 64 FMAs.
+// Accumulation order per output = (filter row, filter column, k channel), exactly thin_in_conv's; taps outside the image
+// contribute fma(0, w, acc) = acc.  DGRAD (gather form) is supported for stride 1: tap (fr, fs) reads the patch mirrored.
+// ---------------------------------------------------------------------------------------------
+constexpr int TI_TH = 8, TI_TW = 32;
+
+template <typename T, bool DGRAD>
+__global__ void __launch_bounds__(256, 2)
+thin_in_tiled(const ConvDev a, int tiles_x, int tiles_y, long long num_tiles, int ph, int pw) {
+  extern __shared__ float ti_smem[];
+  const int kch = DGRAD ? a.cout : a.cin, nch = DGRAD ? a.cin : a.cout;
+  const int OH = DGRAD ? a.h : a.ho, OW = DGRAD ? a.w : a.wo;          // output of this launch
+  const int SH = DGRAD ? a.ho : a.h, SW = DGRAD ? a.wo : a.w;          // its source
+  const int taps = a.kh * a.kw, K = taps * kch;
+  const int s = DGRAD ? 1 : a.stride;
+  float* wsm = ti_smem;                                                // [K][64]
+  float* xs = ti_smem + K * 64;                                        // [kch][ph][pw]
+  const int n0 = blockIdx.y * 64;
+  const T* __restrict__ Wt = reinterpret_cast<const T*>(a.wgt);
+  for (int i = threadIdx.x; i < K * 64; i += 256) wsm[i] = to_f32(Wt[(long long)(i >> 6) * nch + n0 + (i & 63)]);
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const int cg = (warp & 3) * 16, r0 = (warp >> 2) * 4;
+  const T* __restrict__ X = reinterpret_cast<const T*>(a.x);
+  // patch origin in source coordinates for output tile origin (oy0, ox0): fprop oy0*s - pad; dgrad oy0 + pad - (kh - 1)
+  const int org_y = DGRAD ? a.pad - (a.kh - 1) : -a.pad, org_x = DGRAD ? a.pad - (a.kw - 1) : -a.pad;
+  for (long long tile = blockIdx.x; tile < num_tiles; tile += gridDim.x) {
+    long long r = tile;
+    const int bx = (int)(r % tiles_x); r /= tiles_x;
+    const int by = (int)(r % tiles_y);
+    const int img = (int)(r / tiles_y);
+    const int oy0 = by * TI_TH, ox0 = bx * TI_TW;
+    const int sy0 = oy0 * s + org_y, sx0 = ox0 * s + org_x;
+    __syncthreads();                                                   // previous tile's readers are done (and wsm is written)
+    for (int e = threadIdx.x; e < ph * pw; e += 256) {
+      const int ry = e / pw, rx = e - ry * pw;
+      const int gy = sy0 + ry, gx = sx0 + rx;
+      const bool in = gy >= 0 && gy < SH && gx >= 0 && gx < SW;
+      const T* src = X + (((long long)img * SH + (in ? gy : 0)) * SW + (in ? gx : 0)) * a.x_ld;
+      for (int k = 0; k < kch; ++k) xs[(k * ph + ry) * pw + rx] = in ? to_f32(src[k]) : 0.f;
+    }
+    __syncthreads();
+    float acc[4][16];
+#pragma unroll
+    for (int p = 0; p < 4; ++p)
+#pragma unroll
+      for (int c = 0; c < 16; ++c) acc[p][c] = 0.f;
+    for (int fr = 0; fr < a.kh; ++fr) {
+      const int pr = DGRAD ? a.kh - 1 - fr : fr;
+      for (int fs = 0; fs < a.kw; ++fs) {
+        const int pc = (DGRAD ? a.kw - 1 - fs : fs) + lane * s;
+        const float* wrow = wsm + ((fr * a.kw + fs) * kch) * 64 + cg;
+        for (int k = 0; k < kch; ++k) {
+          const float* xp = xs + (k * ph + r0 * s + pr) * pw + pc;
+          float xv[4];
+#pragma unroll
+          for (int p = 0; p < 4; ++p) xv[p] = xp[p * s * pw];
+          const float4 w0 = *reinterpret_cast<const float4*>(wrow + k * 64);
+          const float4 w1 = *reinterpret_cast<const float4*>(wrow + k * 64 + 4);
+          const float4 w2 = *reinterpret_cast<const float4*>(wrow + k * 64 + 8);
+          const float4 w3 = *reinterpret_cast<const float4*>(wrow + k * 64 + 12);
+          const float wv[16] = {w0.x, w0.y, w0.z, w0.w, w1.x, w1.y, w1.z, w1.w, w2.x, w2.y, w2.z, w2.w, w3.x, w3.y, w3.z, w3.w};
+#pragma unroll
+          for (int p = 0; p < 4; ++p)
+#pragma unroll
+            for (int c = 0; c < 16; ++c) acc[p][c] = fmaf(xv[p], wv[c], acc[p][c]);
+        }
+      }
+    }
+    const int ox = ox0 + lane;
+    if (ox < OW) {
+#pragma unroll
+      for (int p = 0; p < 4; ++p) {
+        const int oy = oy0 + r0 + p;
+        if (oy >= OH) continue;
+        const long long m = ((long long)img * OH + oy) * OW + ox;
+#pragma unroll
+        for (int h8 = 0; h8 < 2; ++h8) {
+          const int c0 = n0 + cg + h8 * 8;
+          float v[8];
+#pragma unroll
+          for (int i = 0; i < 8; ++i) {
+            float t = acc[p][h8 * 8 + i];
+            if (a.bias) t += a.bias[c0 + i];
+            if (a.act) t = t > 0.f ? t : t * a.act_slope;
+            v[i] = t * a.alpha;
+          }
+          if (a.r1) {
+            float rr[8];
+            load8<T>(reinterpret_cast<const T*>(a.r1) + m * a.r1_ld + c0, rr);
+#pragma unroll
+            for (int i = 0; i < 8; ++i) v[i] = fmaf(a.beta1, rr[i], v[i]);
+          }
+          if (a.r2) {
+            float rr[8];
+            load8<T>(reinterpret_cast<const T*>(a.r2) + m * a.r2_ld + c0, rr);
+#pragma unroll
+            for (int i = 0; i < 8; ++i) v[i] = fmaf(a.beta2, rr[i], v[i]);
+          }
+          if (a.mask) {
+            float rr[8];
+            load8<T>(reinterpret_cast<const T*>(a.mask) + m * a.mask_ld + c0, rr);
+#pragma unroll
+            for (int i = 0; i < 8; ++i) v[i] *= (rr[i] > 0.f ? 1.f : a.mask_slope);
+          }
+          store8<T>(reinterpret_cast<T*>(a.y) + m * a.y_ld + c0, v);
+        }
+      }
+    }
+  }
+}
+
+// ---------------------------------------------------------------------------------------------
 // thin wgrad: one side of the convolution has <= 4 channels (image convs 3->64 / 64->3, patch logits
 // 256->1).  Bandwidth-bound: every element of the wide tensor is read exactly once, by the thread that
 // owns its channel; the thin tensor's haloed tile sits in shared memory as float4 per pixel and is
@@ -759,6 +878,84 @@ thin_wgrad_kernel(const ThinArgs a, float* __restrict__ part, int fr_begin) {
   }
 }
 
+// 7x7 filters (ResDeconv's stem, case B) in ONE launch: the filter row is a thread dimension - a block is 64 wide channels x 7
+// filter rows x 2 groups of four tile rows, a thread keeps the 7 x 4 accumulators of its filter row.  Same tile and partial
+// layout as seven thin_wgrad_kernel<T, 7, 7, 1> launches (3.7 ms at batch 64 for 13 GFMA: each re-read the wide tensor with
+// 16 warps per SM; SRCGAN_B200_THIN_WGRAD7_ROWS=1 brings them back); a thread sums four tile rows instead of two, so the fp32
+// results differ in the last bits.
+template <typename T>
+__global__ void __launch_bounds__(896)
+thin_wgrad7_kernel(const ThinArgs a, float* __restrict__ part) {
+  constexpr int K7 = 7, TAPS = 49;
+  constexpr int TTH = 2 * (THIN_TH - 1) + K7, TTW = 2 * (THIN_TW - 1) + K7;   // sized for ts = 2
+  __shared__ float4 st[TTH][TTW];
+  const int t = threadIdx.x, c = t & 63, fr = (t >> 6) % K7, g = t / (64 * K7);
+  const int c0 = blockIdx.y * 64;
+  const T* __restrict__ W = reinterpret_cast<const T*>(a.wide);
+  const T* __restrict__ Th = reinterpret_cast<const T*>(a.thin);
+  const int tth = a.ts * (THIN_TH - 1) + K7, ttw = a.ts * (THIN_TW - 1) + K7;
+  const int omin_y = -a.pad, omin_x = -a.pad;                           // case B: sign = +1
+  float acc[K7][4];
+#pragma unroll
+  for (int i = 0; i < K7; ++i) { acc[i][0] = acc[i][1] = acc[i][2] = acc[i][3] = 0.f; }
+
+  for (long long tile = blockIdx.x; tile < a.num_tiles; tile += gridDim.x) {
+    long long r = tile;
+    const int bx = (int)(r % a.tiles_x); r /= a.tiles_x;
+    const int by = (int)(r % a.tiles_y);
+    const int img = (int)(r / a.tiles_y);
+    const int y0 = by * THIN_TH, x0 = bx * THIN_TW;
+    const int gy0 = a.ts * y0 + omin_y, gx0 = a.ts * x0 + omin_x;
+    __syncthreads();
+    for (int e = t; e < tth * ttw; e += 896) {
+      int ry = e / ttw, rx = e - ry * ttw;
+      int gy = gy0 + ry, gx = gx0 + rx;
+      float4 v = make_float4(0.f, 0.f, 0.f, 0.f);
+      if (gy >= 0 && gy < a.ht && gx >= 0 && gx < a.wt) {
+        const T* src = Th + (((long long)img * a.ht + gy) * a.wt + gx) * a.thin_ld;
+        v.x = to_f32(src[0]);
+        if (a.kt > 1) v.y = to_f32(src[1]);
+        if (a.kt > 2) v.z = to_f32(src[2]);
+        if (a.kt > 3) v.w = to_f32(src[3]);
+      }
+      st[ry][rx] = v;
+    }
+    __syncthreads();
+#pragma unroll 1
+    for (int rr = 0; rr < 4; ++rr) {
+      const int ly = 4 * g + rr, y = y0 + ly;
+      if (y >= a.hw) continue;
+      const T* wrow = W + (((long long)img * a.hw + y) * a.ww) * a.wide_ld + c0 + c;
+      const float4* trow = &st[a.ts * ly + fr][0];
+#pragma unroll 4
+      for (int lx = 0; lx < THIN_TW; ++lx) {
+        const int x = x0 + lx;
+        const float wv = x < a.ww ? to_f32(wrow[(long long)x * a.wide_ld]) : 0.f;
+#pragma unroll
+        for (int fs = 0; fs < K7; ++fs) {
+          const float4 tv = trow[a.ts * lx + fs];
+          acc[fs][0] = fmaf(wv, tv.x, acc[fs][0]); acc[fs][1] = fmaf(wv, tv.y, acc[fs][1]);
+          acc[fs][2] = fmaf(wv, tv.z, acc[fs][2]); acc[fs][3] = fmaf(wv, tv.w, acc[fs][3]);
+        }
+      }
+    }
+  }
+  // fold the two row groups through shared memory (reusing the thin tile), one partial per block: part[block][tap][cw][4]
+  __syncthreads();
+  float4* red = &st[0][0];                       // TTH*TTW float4 >= 7*64 entries
+  float4* out = reinterpret_cast<float4*>(part) + ((long long)blockIdx.x * TAPS + fr * K7) * a.cw + c0 + c;
+#pragma unroll
+  for (int i = 0; i < K7; ++i) {
+    if (g > 0) red[fr * 64 + c] = make_float4(acc[i][0], acc[i][1], acc[i][2], acc[i][3]);
+    __syncthreads();
+    if (g == 0) {
+      const float4 v = red[fr * 64 + c];
+      out[(long long)i * a.cw] = make_float4(acc[i][0] + v.x, acc[i][1] + v.y, acc[i][2] + v.z, acc[i][3] + v.w);
+    }
+    __syncthreads();
+  }
+}
+
 // dw (OIHW) (+)= alpha * sum_parts part[p][tap][c][k];  thin_is_out: k indexes cout (case A) else cin (case B)
 __global__ void thin_wgrad_reduce(const float* __restrict__ part, int nparts, int taps, int cw, int kt, int thin_is_out,
                                   float* __restrict__ dw, int accumulate, float alpha) {
@@ -841,6 +1038,26 @@ static int launch_igemm(const srcgan_conv_params* p, cudaStream_t st) {
       attr_done.mark(attr_done_dev);
     }
     thin_out_conv<T, DGRAD><<<ceil_div(M, 256), 256, smem, st>>>(a);
+  } else if (kch <= 4 && nch % 64 == 0 && !p->upsample && (!DGRAD || p->stride == 1) && al(p->y, p->y_ld) &&
+             al(p->r1, p->r1_ld) && al(p->r2, p->r2_ld) && al(p->mask, p->mask_ld) && p->kh * p->kw * kch <= 256 &&
+             !getenv("SRCGAN_B200_NO_THIN_TILED")) {
+    const int s = DGRAD ? 1 : p->stride;
+    const int ph = (TI_TH - 1) * s + p->kh, pw = ((TI_TW - 1) * s + p->kw) | 1;     // odd row pitch: rows land on different banks
+    const size_t smem = ((size_t)p->kh * p->kw * kch * 64 + (size_t)kch * ph * pw) * sizeof(float);
+    static DeviceOnce attr_done3;
+    int attr_done3_dev;
+    if (attr_done3.needed(&attr_done3_dev)) {
+      cudaFuncSetAttribute(thin_in_tiled<T, DGRAD>, cudaFuncAttributeMaxDynamicSharedMemorySize, 100 * 1024);
+      attr_done3.mark(attr_done3_dev);
+    }
+    SRCGAN_REQUIRE(smem <= 100 * 1024, "thin_in_tiled: %zu bytes of shared memory", smem);
+    const int OH = DGRAD ? p->h : p->ho, OW = DGRAD ? p->w : p->wo;
+    const int tx = (OW + TI_TW - 1) / TI_TW, ty = (OH + TI_TH - 1) / TI_TH;
+    const long long tiles = (long long)tx * ty * p->n;
+    const int ngroups = nch / 64;
+    long long gx = (2LL * kNumSMs + ngroups - 1) / ngroups;
+    if (gx > tiles) gx = tiles;
+    thin_in_tiled<T, DGRAD><<<dim3((unsigned)gx, (unsigned)ngroups), 256, smem, st>>>(a, tx, ty, tiles, ph, pw);
   } else if (kch <= 4 && nch % 8 == 0 && al(p->y, p->y_ld) && al(p->r1, p->r1_ld) && al(p->r2, p->r2_ld) &&
              al(p->mask, p->mask_ld) && (size_t)p->kh * p->kw * kch * nch * 4 <= 160 * 1024) {
     const size_t smem = (size_t)p->kh * p->kw * kch * nch * sizeof(float);
@@ -942,7 +1159,9 @@ static int launch_thin_wgrad(const srcgan_conv_params* p, float* dw, int accumul
   int nk = 1;
   if (p->kh == 3) thin_wgrad_kernel<T, 3, 3, 3><<<g, 256, 0, st>>>(a, part, 0);
   else if (p->kh == 4) thin_wgrad_kernel<T, 4, 4, 4><<<g, 256, 0, st>>>(a, part, 0);
-  else {
+  else if (!getenv("SRCGAN_B200_THIN_WGRAD7_ROWS")) {
+    thin_wgrad7_kernel<T><<<g, 896, 0, st>>>(a, part);
+  } else {
     nk = 7;
     for (int fr = 0; fr < 7; ++fr) thin_wgrad_kernel<T, 7, 7, 1><<<g, 256, 0, st>>>(a, part, fr);
   }

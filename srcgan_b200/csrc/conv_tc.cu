@@ -3211,6 +3211,217 @@ static int launch4(const CUtensorMap& tx, const CUtensorMap& tg, const Wg4Args& 
   count_launch();
   return check_launch(BN == 64 ? "conv3x3_wgrad_stack_tc<64>" : "conv3x3_wgrad_stack_tc<32>");
 }
+
+// ---------------------------------------------------------------------------------------------
+// kw-stacked wgrad for a 32-channel input slice and 32 output channels (the 32 -> 32 remainder launches of the paired dense-block
+// weight gradients: x_k slice x dZ_(k+1) slice of two 192-channel concat buffers, 64 useful bytes per pixel and operand).
+// Experiment (opt-in, see r32_ok): the hypothesis was that conv3x3_wgrad_stack_tc<32> spends those launches on the TMA engine -
+// a TMA unit retires one box row per ~3.3 clk whatever its length, a 128-pixel tile is 160 rows of X + 144 rows of dY (1 000 clk) -
+// and on 2 x 8 MMAs of N = 96 per tile (900 clk; one 64-channel atom holds only two vertical taps).  Here
+//   * X is a SWIZZLE_64B slab of 32-channel atoms: M = 128 = FOUR atoms one slab row apart = the three vertical taps + a
+//     phantom, ONE MMA of N = 96 per 16-pixel row (8 per tile, 450 clk);
+//   * dY does not go through TMA: the four epilogue warps, idle until the last tile, copy it with 16-byte cp.async into the
+//     same swizzled [8 rows][18 px][32 ch] slab (zero fill outside the image), several tiles in flight; the TMA unit
+//     moves the 160 rows of X only (530 clk).
+// Same tile order, k-step order and fp32 partial layout as conv3x3_wgrad_stack_tc, so the reduce launch is shared.
+// ---------------------------------------------------------------------------------------------
+constexpr int R32_X_BYTES = WS_X_ROWS * WS_TW * 64;                   // 10240: [10 rows][16 px][32 ch]
+constexpr int R32_G_BYTES = WS_TH * WS_G_W * 64;                      //  9216: [ 8 rows][18 px][32 ch]
+constexpr int R32_STAGE = R32_X_BYTES + R32_G_BYTES;                  // 19456 (both slabs 1024-byte aligned)
+constexpr int R32_STAGES = 8;
+constexpr int R32_LAG = 3;                                            // cp.async groups (tiles) in flight per thread
+constexpr int R32_SMEM = R32_STAGES * R32_STAGE + SMEM_AUX + 1024;
+constexpr int R32_CHUNKS = WS_TH * WS_G_W * 4;                        // 576 16-byte chunks of a dY slab
+constexpr int R32_PER_THREAD = (R32_CHUNKS + 127) / 128;              // 5
+static_assert(R32_LAG < R32_STAGES, "the cp.async producers would wait for a stage their own pending arrival frees");
+
+__global__ void __launch_bounds__(NUM_THREADS, 1)
+conv3x3_wgrad_r32_tc(const __grid_constant__ CUtensorMap tmap_x, const __nv_bfloat16* __restrict__ g, int g_ld, const Wg4Args a) {
+  extern __shared__ uint8_t smem_raw[];
+  uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~(uintptr_t)1023);
+  uint8_t* aux = smem + R32_STAGES * R32_STAGE;
+  uint64_t* full_bar = reinterpret_cast<uint64_t*>(aux);
+  uint64_t* empty_bar = full_bar + R32_STAGES;
+  uint64_t* done_bar = empty_bar + R32_STAGES;
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(done_bar + 1);
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  pdl_launch_dependents();
+  const int split = blockIdx.x;
+  if (threadIdx.x == 0) {
+    // a stage is full when the TMA bytes of X have landed (one arrive.expect_tx) and all 128 copy threads have arrived
+    for (int s = 0; s < R32_STAGES; ++s) { mbar_init(&full_bar[s], 1 + 128); mbar_init(&empty_bar[s], 1); }
+    mbar_init(done_bar, 1);
+    asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+  }
+  if (warp == 1) {
+    asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(tmem_slot)), "r"(128u)
+                 : "memory");
+    asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
+  }
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  const uint32_t tmem_base = *tmem_slot;
+
+  const long long t_beg = (long long)split * a.tiles_per_split;
+  long long t_end = t_beg + a.tiles_per_split;
+  if (t_end > a.num_tiles) t_end = a.num_tiles;
+
+  if (warp == 0) {
+    int stage = 0;
+    uint32_t phase = 0;
+    pdl_wait();
+    for (long long t = t_beg; t < t_end; ++t) {
+      long long r = t;
+      const int by = (int)(r % a.tiles_y); r /= a.tiles_y;
+      const int bx = (int)(r % a.tiles_x);
+      const int img = (int)(r / a.tiles_x);
+      mbar_wait(&empty_bar[stage], phase ^ 1);
+      if (elect_one()) {
+        mbar_expect_tx(&full_bar[stage], (uint32_t)R32_X_BYTES);
+        tma_load_4d(&tmap_x, &full_bar[stage], smem + stage * R32_STAGE, 0, bx * WS_TW, by * WS_TH - 1, img);
+      }
+      __syncwarp();
+      if (++stage == R32_STAGES) { stage = 0; phase ^= 1; }
+    }
+  } else if (warp == 1) {
+    constexpr uint32_t idesc = tcw::umma_idesc_mn(128, 96);
+    constexpr uint32_t ROW_A = WS_TW * 64, ROW_G = WS_G_W * 64;         // slab row pitches: 1024 B, 1152 B
+    constexpr uint32_t a_hi = desc_hi_sw64(8 * 64), g_hi = desc_hi_sw64(8 * 64);   // K groups: 8 pixels of a row
+    int stage = 0;
+    uint32_t phase = 0;
+    uint32_t accumulate = 0;
+    for (long long t = t_beg; t < t_end; ++t) {
+      mbar_wait(&full_bar[stage], phase);
+      tc_fence_after();
+      const uint32_t sx = smem_u32(smem + stage * R32_STAGE);
+      const uint32_t sg = sx + R32_X_BYTES;
+      if (elect_one()) {
+        const uint32_t a_lo = desc_lo(sx, ROW_A);                       // M atoms (32 channels) one slab row apart: taps kh = 0..3
+        const uint32_t g_lo = desc_lo(sg, 64);                          // N atoms (32 channels) one pixel apart: taps kw = 2..0
+#pragma unroll
+        for (int r = 0; r < WS_TH; ++r)                                 // (row 7's phantom atom reads the first row of the dY slab)
+          umma_bf16_w(tmem_base, a_lo + (uint32_t)((r * ROW_A) >> 4), a_hi, g_lo + (uint32_t)((r * ROW_G) >> 4), g_hi, idesc,
+                      accumulate | (uint32_t)(r > 0));
+        umma_commit(&empty_bar[stage]);
+      }
+      __syncwarp();
+      accumulate = 1;
+      if (++stage == R32_STAGES) { stage = 0; phase ^= 1; }
+    }
+    if (elect_one()) umma_commit(done_bar);
+    __syncwarp();
+  } else {
+    // ---- dY producer: thread -> up to five fixed (slab pixel, 16-byte chunk) slots of every tile
+    const int tid = threadIdx.x - 64;
+    uint32_t dst_off[R32_PER_THREAD], src_off[R32_PER_THREAD];
+    int pr[R32_PER_THREAD], pj[R32_PER_THREAD];
+#pragma unroll
+    for (int i = 0; i < R32_PER_THREAD; ++i) {
+      const int id = tid + 128 * i;
+      const int idx = id >> 2, ch = id & 3;                             // slab pixel, chunk of its 64 bytes
+      pr[i] = idx / WS_G_W;
+      pj[i] = idx - pr[i] * WS_G_W;
+      dst_off[i] = (uint32_t)(idx * 64 + ((ch ^ ((idx >> 1) & 3)) << 4));            // SWIZZLE_64B (slab 1024-byte aligned)
+      src_off[i] = (uint32_t)(((pr[i] * a.wo + pj[i]) * g_ld + ch * 8) * 2);
+      if (id >= R32_CHUNKS) pr[i] = 1 << 20;                            // never inside the image
+    }
+    const char* gbase = reinterpret_cast<const char*>(g);
+    int stage = 0, sig = 0, pend = 0;
+    uint32_t phase = 0;
+    pdl_wait();                                                         // dY is the previous kernels' output
+    for (long long t = t_beg; t < t_end; ++t) {
+      long long r = t;
+      const int by = (int)(r % a.tiles_y); r /= a.tiles_y;
+      const int bx = (int)(r % a.tiles_x);
+      const int img = (int)(r / a.tiles_x);
+      const int x0 = bx * WS_TW - 1, y0 = by * WS_TH;
+      const char* tile = gbase + (((long long)img * a.ho + y0) * a.wo + x0) * (long long)g_ld * 2;
+      mbar_wait(&empty_bar[stage], phase ^ 1);
+      const uint32_t sg = smem_u32(smem + stage * R32_STAGE) + R32_X_BYTES;
+#pragma unroll
+      for (int i = 0; i < R32_PER_THREAD; ++i) {
+        if (i < R32_PER_THREAD - 1 || tid + 128 * i < R32_CHUNKS) {
+          const int x = x0 + pj[i];
+          const bool ok = y0 + pr[i] < a.ho && x >= 0 && x < a.wo;
+          const char* src = ok ? tile + src_off[i] : gbase;
+          asm volatile("cp.async.cg.shared.global [%0], [%1], 16, %2;" ::"r"(sg + dst_off[i]), "l"(src), "r"(ok ? 16 : 0) : "memory");
+        }
+      }
+      asm volatile("cp.async.commit_group;" ::: "memory");
+      if (++pend > R32_LAG) {
+        asm volatile("cp.async.wait_group %0;" ::"n"(R32_LAG) : "memory");
+        asm volatile("fence.proxy.async.shared::cta;" ::: "memory");    // generic-proxy writes -> the MMA's async-proxy reads
+        mbar_arrive(&full_bar[sig]);
+        if (++sig == R32_STAGES) sig = 0;
+        --pend;
+      }
+      if (++stage == R32_STAGES) { stage = 0; phase ^= 1; }
+    }
+    asm volatile("cp.async.wait_group 0;" ::: "memory");
+    asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
+    for (; pend > 0; --pend) {
+      mbar_arrive(&full_bar[sig]);
+      if (++sig == R32_STAGES) sig = 0;
+    }
+    // ---- epilogue: TMEM lane = (kh, ci) = (lane quadrant, lane); columns = (j, co), kw = 2 - j
+    const int q = warp & 3;
+    const bool has_work = t_end > t_beg;
+    mbar_wait(done_bar, 0);
+    tc_fence_after();
+    const bool row_ok = q < 3 && lane < a.cin;
+#pragma unroll 1
+    for (int j = 0; j < 3; ++j) {
+      uint32_t v[32];
+      tmem_ld32(tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)(j * 32), v);
+      if (row_ok) {
+        const int tap = q * 3 + (2 - j);
+        float* dst = a.part + (((long long)split * 9 + tap) * a.cin + lane) * a.cout;
+#pragma unroll
+        for (int i = 0; i < 8; ++i) {
+          float4 o;
+          o.x = has_work ? __uint_as_float(v[4 * i + 0]) : 0.f;
+          o.y = has_work ? __uint_as_float(v[4 * i + 1]) : 0.f;
+          o.z = has_work ? __uint_as_float(v[4 * i + 2]) : 0.f;
+          o.w = has_work ? __uint_as_float(v[4 * i + 3]) : 0.f;
+          *reinterpret_cast<float4*>(dst + 4 * i) = o;
+        }
+      }
+    }
+  }
+  tc_fence_before();
+  __syncthreads();
+  if (warp == 1) {
+    asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "r"(128u) : "memory");
+  }
+}
+
+// 32-channel (or thinner) input slice, 32 output channels, no in-kernel bias gradient.  OPT-IN (SRCGAN_B200_WGRAD_R32=1): measured
+// at 64 x 256 x 256 it takes 0.1754 ms against 0.1712 ms of conv3x3_wgrad_stack_tc<32> - neither the TMA row rate nor the MMA count
+// bounds these launches ("What bounds them" 19).
+static bool r32_ok(const srcgan_conv_params* p, const float* dbpart) {
+  return p->cout == 32 && p->cin <= 32 && dbpart == nullptr && getenv("SRCGAN_B200_WGRAD_R32");
+}
+
+static int launch_r32(const srcgan_conv_params* p, const Wg4Args& a, cudaStream_t st) {
+  CUtensorMap tx;
+  int rc = make_tmap_box(&tx, p->x, p->cin, p->w, p->h, p->n, p->x_ld, 32, WS_TW, WS_X_ROWS, CU_TENSOR_MAP_SWIZZLE_64B,
+                         "conv_wgrad_r32(x)");
+  if (rc) return rc;
+  static DeviceOnce attr_set;
+  int attr_set_dev;
+  if (attr_set.needed(&attr_set_dev)) {
+    SRCGAN_CUDA(cudaFuncSetAttribute(conv3x3_wgrad_r32_tc, cudaFuncAttributeMaxDynamicSharedMemorySize, R32_SMEM));
+    attr_set.mark(attr_set_dev);
+  }
+  cudaLaunchConfig_t cfg = {};
+  cfg.gridDim = dim3((unsigned)a.splits); cfg.blockDim = dim3(NUM_THREADS); cfg.dynamicSmemBytes = R32_SMEM; cfg.stream = st;
+  cudaLaunchAttribute at[1];
+  cfg.attrs = at; cfg.numAttrs = pdl_attr(&at[0]);
+  SRCGAN_CUDA(cudaLaunchKernelEx(&cfg, conv3x3_wgrad_r32_tc, tx, reinterpret_cast<const __nv_bfloat16*>(p->y), (int)p->y_ld, a));
+  count_launch();
+  return check_launch("conv3x3_wgrad_r32_tc");
+}
 }  // namespace tcw4
 
 // shared with the SIMT engine (conv_simt.cu)
@@ -3291,7 +3502,8 @@ int conv_wgrad_tc_split(const srcgan_conv_params* p, float* dw0, int ld0, int ci
   rc = tcw4::make_tmap_box(&tg, p->y, p->cout, p->wo, p->ho, p->n, p->y_ld, bn, tcw4::WS_G_W, tcw4::WS_TH,
                            bn == 64 ? CU_TENSOR_MAP_SWIZZLE_128B : CU_TENSOR_MAP_SWIZZLE_64B, "conv_wgrad_split(dy)");
   if (rc) return rc;
-  rc = bn == 64 ? tcw4::launch4<64>(tx, tg, a4, st) : tcw4::launch4<32>(tx, tg, a4, st);
+  if (tcw4::r32_ok(p, a4.dbpart)) rc = tcw4::launch_r32(p, a4, st);
+  else rc = bn == 64 ? tcw4::launch4<64>(tx, tg, a4, st) : tcw4::launch4<32>(tx, tg, a4, st);
   if (rc) return rc;
   // split-K reduce of the weight gradients and, in the same launch, of the bias gradients the kernel summed per split
   return wgrad_reduce_db_launch(reinterpret_cast<const float*>(ws), a4.splits, 9, p->cin, p->cout, split, dw0, ld0, ci00, dw1, ld1,
@@ -3320,7 +3532,8 @@ int conv_wgrad_tc(const srcgan_conv_params* p, float* dw, float* db, int accumul
     rc = tcw4::make_tmap_box(&tg, p->y, p->cout, p->wo, p->ho, p->n, p->y_ld, bn, tcw4::WS_G_W, tcw4::WS_TH,
                              bn == 64 ? CU_TENSOR_MAP_SWIZZLE_128B : CU_TENSOR_MAP_SWIZZLE_64B, "conv_wgrad_tc(stack dy)");
     if (rc) return rc;
-    rc = bn == 64 ? tcw4::launch4<64>(tx, tg, a4, st) : tcw4::launch4<32>(tx, tg, a4, st);
+    if (tcw4::r32_ok(p, a4.dbpart)) rc = tcw4::launch_r32(p, a4, st);
+    else rc = bn == 64 ? tcw4::launch4<64>(tx, tg, a4, st) : tcw4::launch4<32>(tx, tg, a4, st);
     if (rc) return rc;
     return wgrad_reduce_db_launch(reinterpret_cast<const float*>(ws), a4.splits, 9, p->cin, p->cout, p->cout, dw, p->cin, 0, nullptr,
                                   0, 0, accumulate, p->alpha, a4.dbpart, db, nullptr, st);   // bias gradient: summed in-kernel

@@ -61,6 +61,10 @@ def sweep_bits_supported(cin: int, cout: int, k: int, stride: int, pad: int, dty
 def select(cin, cout, k, stride, upsample, dtype, h, w):
     """-> (engine, fprop weight layout); (h, w) are the OUTPUT spatial dims."""
     if not _force_simt and dtype == torch.bfloat16 and tc_fprop_supported(cin, cout, k, stride, upsample, dtype, h, w):
+        if cin <= 4 and cout % 64 == 0 and not (k == 3 and stride == 1) and not os.environ.get("SRCGAN_B200_NO_THIN_TILED"):
+            # image -> features through a 4x4 (stride-2) filter, gradient of a 256 -> 1 patch-logit layer: the FFMA kernel
+            # thin_in_tiled (csrc/conv_simt.cu) beats the tcgen05 GEMM with K zero-padded from <= 4 to 64 channels per tap
+            return ENGINE_SIMT, WL_RSCK
         return ENGINE_TC, (WL_TC if stride == 1 else WL_TC_S2)
     return ENGINE_SIMT, WL_RSCK
 

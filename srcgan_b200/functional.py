@@ -1,13 +1,15 @@
 """Per-operator autograd layer over NHWC activations, for the cascaded trainers' model zoo
 (ResDeconv, EDSR, SRDenseNetA/B: SURVEY.md section 8 row a14).
 
-Tensors are contiguous ``(N, H, W, C)`` in the activation dtype (``nn.act_dtype()``: fp32 parity mode or bf16).
+Tensors are contiguous ``(N, H, W, C)`` in the activation dtype (``nn.act_dtype()``: fp32 parity mode or bf16); in bf16 mode
+thin ones (fewer than 8 channels) are views of pitch-8 buffers (see ``_new_thin``).
 Every operator is one ``torch.autograd.Function`` whose forward and backward call the C-ABI kernels
 (``ops.*``); nothing here falls back to torch convolutions.  The networks on the CycleGAN hot path
 (``nn.RDDBNetB`` etc.) do NOT use this layer - they run whole-network fused schedules.
 """
 from __future__ import annotations
 
+import os
 import weakref
 from typing import Dict, List, Optional, Tuple
 
@@ -48,15 +50,50 @@ def _aligned(*cs: int) -> bool:
     return all(c % 8 == 0 for c in cs)
 
 
-def _select(cin, cout, k, stride, dtype, ho, wo):
+# Thin tensors (images, logits: fewer than 8 channels) live in bf16 mode in NHWC buffers whose pixel pitch is padded to 8 channels
+# (16 bytes), as in nn._io_buf: TMA tensor maps can then address them and the thin layers (64 -> 3 prediction conv, its data and
+# weight gradients) run on the tcgen05 kernels instead of the FFMA ones (cascade step: 5.3 + 1.7 + 2.1 ms -> 0.7 + 0.3 + 0.5 ms).
+# Between the functions of this module such a tensor travels as the channel-sliced VIEW buf[..., :c] of its buffer; only the
+# first c channels are ever read or written.  Anything that calls .contiguous() on it gets an ordinary dense copy.
+_THIN_PITCH = 8
+
+
+def _new_thin(n, h, w, c, like: torch.Tensor) -> torch.Tensor:
+    if like.dtype == torch.bfloat16 and c < _THIN_PITCH and not os.environ.get("SRCGAN_B200_NO_THIN_PITCH"):
+        return ops.new_buf(n, h, w, _THIN_PITCH, like.dtype, like.device)[..., :c]
+    return ops.new_buf(n, h, w, c, like.dtype, like.device)
+
+
+def _is_padded_view(t: torch.Tensor) -> bool:
+    if t.dim() != 4 or t.shape[3] >= _THIN_PITCH or t.is_contiguous():
+        return False
+    n, h, w, c = t.shape
+    return t.stride() == (h * w * _THIN_PITCH, w * _THIN_PITCH, _THIN_PITCH, 1) and t.storage_offset() % _THIN_PITCH == 0
+
+
+def _canon(t: torch.Tensor) -> torch.Tensor:
+    """dense NHWC tensor or a padded thin view, whichever ``t`` already is; anything else is copied to dense"""
+    return t if (t.is_contiguous() or _is_padded_view(t)) else t.contiguous()
+
+
+def _sl(t: torch.Tensor, c0: int = 0, c: Optional[int] = None) -> Slice:
+    """Slice over a tensor accepted by _canon()"""
+    if _is_padded_view(t):
+        n, h, w, cc = t.shape
+        base = t.as_strided((n, h, w, _THIN_PITCH), t.stride(), t.storage_offset())
+        return Slice(base, c0, cc - c0 if c is None else c)
+    return Slice(t, c0, c)
+
+
+def _select(cin, cout, k, stride, dtype, ho, wo, x_ld=None, y_ld=None):
     """(engine, layout) for a full-tensor conv: the tcgen05 engine needs 16-byte pixel pitches on both sides."""
-    if dtype == torch.bfloat16 and _aligned(cin, cout):
+    if dtype == torch.bfloat16 and _aligned(cin if x_ld is None else x_ld, cout if y_ld is None else y_ld):
         return _engine.select(cin, cout, k, stride, False, dtype, ho, wo)
     return ENGINE_SIMT, WL_RSCK
 
 
-def _select_wgrad(cin, cout, k, stride, dtype, ho, wo):
-    if dtype == torch.bfloat16 and _aligned(cin, cout):
+def _select_wgrad(cin, cout, k, stride, dtype, ho, wo, x_ld=None, y_ld=None):
+    if dtype == torch.bfloat16 and _aligned(cin if x_ld is None else x_ld, cout if y_ld is None else y_ld):
         return _engine.select_wgrad(cin, cout, k, stride, False, dtype, ho, wo)
     return ENGINE_SIMT
 
@@ -73,12 +110,13 @@ def _conv_into(x: torch.Tensor, w: torch.Tensor, kind: str, build, bias, y: torc
                act=None) -> None:
     """y = act(conv(x, build()) + bias) where build() is an OIHW weight derived from parameter ``w``."""
     cin, cout = x.shape[3], y.shape[3]
+    xs, ys = _sl(x), _sl(y)
     for c0, cc in _chunks(cout, cin, k, stride, x.dtype, y.shape[1], y.shape[2]):
-        eng, layout = _select(cin, cc, k, stride, x.dtype, y.shape[1], y.shape[2])
+        eng, layout = _select(cin, cc, k, stride, x.dtype, y.shape[1], y.shape[2], xs.ld, ys.ld)
         sub = (lambda c0=c0, cc=cc: build()[c0:c0 + cc]) if (c0, cc) != (0, cout) else build
         pk = _packs.get(w, (kind, c0, cc), sub, layout, x.dtype)
         b = None if bias is None else (bias if (c0, cc) == (0, cout) else bias.detach()[c0:c0 + cc].contiguous())
-        ops.conv_fprop(Slice(x), pk, b, Slice(y, c0, cc), k, stride, pad, act=act, engine=eng)
+        ops.conv_fprop(xs, pk, b, Slice(ys.buf, c0, cc), k, stride, pad, act=act, engine=eng)
 
 
 def _new(n, h, w, c, like: torch.Tensor) -> torch.Tensor:
@@ -86,11 +124,11 @@ def _new(n, h, w, c, like: torch.Tensor) -> torch.Tensor:
 
 
 def _masked(gy: torch.Tensor, y: Optional[torch.Tensor], act: Optional[float]) -> torch.Tensor:
-    gy = gy.contiguous()
+    gy = _canon(gy)
     if act is None:
         return gy
-    gz = torch.empty_like(gy)
-    ops.act_backward(Slice(gy), Slice(y), Slice(gz), act)
+    gz = _new_thin(*gy.shape, gy) if _is_padded_view(gy) else torch.empty_like(gy)
+    ops.act_backward(_sl(gy), _sl(y), _sl(gz), act)
     return gz
 
 
@@ -102,26 +140,26 @@ class _ToNHWC(torch.autograd.Function):
     @staticmethod
     def forward(ctx, x, dtype):
         n, c, h, w = x.shape
-        y = ops.new_buf(n, h, w, c, dtype, x.device)
-        ops.nchw_to_nhwc(x, Slice(y))
+        y = _new_thin(n, h, w, c, torch.empty((), dtype=dtype, device=x.device))
+        ops.nchw_to_nhwc(x, _sl(y))
         return y
 
     @staticmethod
     def backward(ctx, gy):
-        return ops.nhwc_to_nchw(Slice(gy.contiguous())), None
+        return ops.nhwc_to_nchw(_sl(_canon(gy))), None
 
 
 class _ToNCHW(torch.autograd.Function):
     @staticmethod
     def forward(ctx, x):
         ctx.dt = x.dtype
-        return ops.nhwc_to_nchw(Slice(x.contiguous()))
+        return ops.nhwc_to_nchw(_sl(_canon(x)))
 
     @staticmethod
     def backward(ctx, gy):
         n, c, h, w = gy.shape
-        g = ops.new_buf(n, h, w, c, ctx.dt, gy.device)
-        ops.nchw_to_nhwc(gy, Slice(g))
+        g = _new_thin(n, h, w, c, torch.empty((), dtype=ctx.dt, device=gy.device))
+        ops.nchw_to_nhwc(gy, _sl(g))
         return g
 
 
@@ -140,11 +178,11 @@ def to_nchw(x: torch.Tensor) -> torch.Tensor:
 class _Conv2d(torch.autograd.Function):
     @staticmethod
     def forward(ctx, x, w, b, stride, pad, act):
-        x = x.contiguous()
+        x = _canon(x)
         n, h, wd, cin = x.shape
         cout, _, k, _ = w.shape
         ho, wo = (h + 2 * pad - k) // stride + 1, (wd + 2 * pad - k) // stride + 1
-        y = _new(n, ho, wo, cout, x)
+        y = _new_thin(n, ho, wo, cout, x)
         _conv_into(x, w, "f", lambda: w.detach(), b, y, k, stride, pad, act)
         ctx.save_for_backward(x, w, y if act is not None else None)
         ctx.cfg = (stride, pad, act, b is not None)
@@ -159,21 +197,31 @@ class _Conv2d(torch.autograd.Function):
         cout, _, k, _ = w.shape
         dx = dw = db = None
         if ctx.needs_input_grad[0]:
-            dx = _new(n, h, wd, cin, x)
+            dx = _new_thin(n, h, wd, cin, x)
             if stride == 1 and k - 1 - pad >= 0:
                 _conv_into(gz, w, "t", lambda: w.detach().transpose(0, 1).flip(2, 3), None, dx, k, 1, k - 1 - pad)
             elif _aligned(cin, cout) and _engine.tc_dgrad_s2_supported(cin, cout, k, stride, pad, x.dtype):
                 pk = _packs.get(w, ("d2",), lambda: w.detach(), WL_TC_DGRAD_S2, x.dtype)
-                ops.conv_dgrad(Slice(gz), pk, Slice(dx), k, stride, pad, engine=ENGINE_TC)
+                ops.conv_dgrad(_sl(gz), pk, _sl(dx), k, stride, pad, engine=ENGINE_TC)
+            elif (k == 1 and stride == 2 and pad == 0 and _aligned(cin, cout)
+                  and _select(cout, cin, 1, 1, x.dtype, gz.shape[1], gz.shape[2])[0] == ENGINE_TC):
+                # 1x1 stride-2 projection (ResDeconv's downsample branches): its data gradient is W^T dY at the even positions and
+                # zero elsewhere - a 1x1 stride-1 convolution on the tcgen05 engine into a compact buffer + one strided copy,
+                # instead of the gather-form FFMA kernel (0.8-0.9 ms per layer at batch 64)
+                tmp = _new(n, gz.shape[1], gz.shape[2], cin, x)
+                _conv_into(gz, w, "t1", lambda: w.detach().transpose(0, 1).contiguous(), None, tmp, 1, 1, 0)
+                dx.zero_()
+                dx[:, ::2, ::2, :].copy_(tmp)
             else:
                 pk = _packs.get(w, ("d",), lambda: w.detach(), WL_RSKC, x.dtype)
-                ops.conv_dgrad(Slice(gz), pk, Slice(dx), k, stride, pad)
+                ops.conv_dgrad(_sl(gz), pk, _sl(dx), k, stride, pad)
         want_w, want_b = ctx.needs_input_grad[1], has_b and ctx.needs_input_grad[2]
         if want_w or want_b:
             dw = torch.empty(w.shape, dtype=torch.float32, device=x.device) if want_w else None
             db = torch.empty(cout, dtype=torch.float32, device=x.device) if want_b else None
-            eng = _select_wgrad(cin, cout, k, stride, x.dtype, gz.shape[1], gz.shape[2])
-            ops.conv_wgrad(Slice(x), Slice(gz), dw, db, k, stride, pad, engine=eng)
+            xs, gs = _sl(x), _sl(gz)
+            eng = _select_wgrad(cin, cout, k, stride, x.dtype, gz.shape[1], gz.shape[2], xs.ld, gs.ld)
+            ops.conv_wgrad(xs, gs, dw, db, k, stride, pad, engine=eng)
         return dx, dw, db, None, None, None
 
 
@@ -259,7 +307,7 @@ class _ConvTranspose2d(torch.autograd.Function):
     def backward(ctx, gy):
         x, w, y = ctx.saved_tensors
         stride, pad, act, has_b = ctx.cfg
-        gz = _masked(gy, y, act)
+        gz = _masked(gy.contiguous(), y, act)
         n, h, wd, cin = x.shape
         _, cout, k, _ = w.shape
         dx = dw = db = None
@@ -312,7 +360,7 @@ class _GroupNorm(torch.autograd.Function):
     def backward(ctx, gy):
         x, gamma, mean, rstd, y = ctx.saved_tensors
         groups, act, has_res = ctx.cfg
-        gz = _masked(gy, y, act)
+        gz = _masked(gy.contiguous(), y, act)
         dx = torch.empty_like(x)
         dgamma = torch.empty(x.shape[3], dtype=torch.float32, device=x.device)
         dbeta = torch.empty_like(dgamma)

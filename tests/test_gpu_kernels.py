@@ -107,6 +107,85 @@ def test_conv_fprop_dgrad_wgrad(case, dtype, tol):
             assert relerr(from_nhwc(dxs2), xin.grad) < tol
 
 
+THIN_IN_CASES = [
+    # n, h, w, cin, cout, k, stride, pad
+    (2, 40, 70, 3, 64, 7, 2, 3),       # ResDeconv's stem, ragged tile grid
+    (3, 64, 64, 3, 64, 4, 2, 1),       # first discriminator layer
+    (1, 33, 17, 1, 128, 4, 1, 1),      # two 64-channel groups
+    (2, 19, 45, 3, 64, 3, 1, 1),
+    (1, 30, 30, 1, 64, 9, 1, 4),       # SRCNN's first layer
+]
+
+
+@pytest.mark.parametrize("dtype,tol", [(torch.float32, 2e-5), (torch.bfloat16, 2e-2)])
+@pytest.mark.parametrize("case", THIN_IN_CASES)
+def test_thin_in_tiled_kernel(case, dtype, tol, monkeypatch):
+    """thin_in_tiled (<= 4 input channels, tile of 8 x 32 pixels x 64 channels per block, patch and weights in shared memory):
+    against torch, bit for bit against thin_in_conv (same accumulation order), with the whole epilogue; and the gather-form
+    gradient of a thin-output layer (256 -> 1 patch logits) through the same kernel."""
+    from srcgan_b200 import ops
+    n, h, w, cin, cout, k, s, p = case
+    x = rand((n, cin, h, w), 11)
+    wt = rand((cout, cin, k, k), 12, 0.1)
+    b = rand((cout,), 13)
+    if dtype == torch.bfloat16:
+        x, wt = x.bfloat16().float(), wt.bfloat16().float()
+    y_ref = F.conv2d(x, wt, b, stride=s, padding=p)
+    ho, wo = y_ref.shape[2:]
+    r1 = rand(tuple(y_ref.shape), 14)
+    mk = rand(tuple(y_ref.shape), 15)
+    if dtype == torch.bfloat16:
+        r1, mk = r1.bfloat16().float(), mk.bfloat16().float()
+    lre = lambda t: torch.where(t > 0, t, 0.2 * t)
+    full_ref = (lre(y_ref) * 0.5 + 0.25 * r1) * torch.where(mk > 0, torch.ones_like(mk), torch.full_like(mk, 0.1))
+    xs = to_nhwc(x, dtype, ctot=8)                         # thin buffers have a pitch of 8 channels
+    wp = ops.pack_weights(wt.to(DEV), ops.WL_RSCK, dtype)
+    r1s, mks = to_nhwc(r1, dtype), to_nhwc(mk, dtype)
+
+    def run():
+        y0 = ops.Slice(torch.zeros((n, ho, wo, cout), dtype=dtype, device=DEV))
+        ops.conv_fprop(xs, wp, b.to(DEV), y0, k, s, p)
+        y1 = ops.Slice(torch.zeros((n, ho, wo, cout), dtype=dtype, device=DEV))
+        ops.conv_fprop(xs, wp, b.to(DEV), y1, k, s, p, act=0.2, alpha=0.5, r1=r1s, beta1=0.25, mask=mks, mask_slope=0.1)
+        torch.cuda.synchronize()
+        return y0, y1
+
+    y0, y1 = run()
+    assert relerr(from_nhwc(y0), y_ref) < tol
+    assert relerr(from_nhwc(y1), full_ref) < tol
+    monkeypatch.setenv("SRCGAN_B200_NO_THIN_TILED", "1")
+    o0, o1 = run()
+    assert torch.equal(y0.buf, o0.buf) and torch.equal(y1.buf, o1.buf)
+
+
+@pytest.mark.parametrize("dtype,tol", [(torch.float32, 2e-5), (torch.bfloat16, 2e-2)])
+def test_thin_in_tiled_dgrad(dtype, tol, monkeypatch):
+    from srcgan_b200 import ops
+    n, h, w, cin, cout, k, p = 2, 21, 37, 256, 1, 4, 1
+    x = rand((n, cin, h, w), 21).requires_grad_(True)
+    wt = rand((cout, cin, k, k), 22, 0.1)
+    if dtype == torch.bfloat16:
+        wt = wt.bfloat16().float()
+    y = F.conv2d(x, wt, None, stride=1, padding=p)
+    gy = rand(tuple(y.shape), 23)
+    if dtype == torch.bfloat16:
+        gy = gy.bfloat16().float()
+    y.backward(gy)
+    gys = to_nhwc(gy, dtype, ctot=8)
+    wd = ops.pack_weights(wt.to(DEV), ops.WL_RSKC, dtype)
+
+    def run():
+        dxs = ops.Slice(torch.zeros((n, h, w, cin), dtype=dtype, device=DEV))
+        ops.conv_dgrad(gys, wd, dxs, k, 1, p)
+        torch.cuda.synchronize()
+        return dxs
+
+    new = run()
+    assert relerr(from_nhwc(new), x.grad) < tol
+    monkeypatch.setenv("SRCGAN_B200_NO_THIN_TILED", "1")
+    assert torch.equal(new.buf, run().buf)
+
+
 def test_conv_epilogue():
     from srcgan_b200 import ops
     n, h, w, cin, cout = 1, 6, 7, 64, 32
@@ -758,6 +837,35 @@ def test_conv_wgrad_split_pairs_dense_block_layers(ka):
     gy = Db[..., d0:d0 + gc].float().permute(0, 3, 1, 2).cpu()
     F.conv2d(x, wt, None, padding=1).backward(gy)
     assert relerr(dwb.cpu() - 0.25, wt.grad) < 5e-3
+
+
+@pytest.mark.parametrize("shape", [(2, 40, 52, 32), (1, 131, 64, 32), (3, 16, 16, 16), (1, 9, 70, 24)])
+def test_conv_wgrad_r32_kernel(shape, monkeypatch):
+    """The opt-in conv3x3_wgrad_r32_tc (32-channel slice x 32-channel slice, dY copied by cp.async, four vertical taps in M) against
+    torch and against conv3x3_wgrad_stack_tc<32> on the same slices (ragged tile grids, thin slices, accumulate / alpha)."""
+    from srcgan_b200 import ops
+    n, h, w, cin = shape
+    g0 = torch.Generator().manual_seed(123)
+    X = (torch.rand((n, h, w, 192), generator=g0) - 0.5).to(torch.bfloat16).to(DEV)
+    D = (torch.rand((n, h, w, 192), generator=g0) - 0.5).to(torch.bfloat16).to(DEV)
+    xs, ds = ops.Slice(X, 128, cin), ops.Slice(D, 160, 32)
+
+    def run(acc):
+        dw = torch.full((32, cin, 3, 3), 0.5, device=DEV)
+        ops.conv_wgrad(xs, ds, dw, None, 3, 1, 1, engine=ops.ENGINE_TC, accumulate=acc, alpha=0.5 if acc else 1.0)
+        torch.cuda.synchronize()
+        return dw
+
+    old = run(False)
+    monkeypatch.setenv("SRCGAN_B200_WGRAD_R32", "1")
+    new = run(False)
+    new_acc = run(True)
+    x = X[..., 128:128 + cin].float().permute(0, 3, 1, 2).cpu()
+    wt = torch.zeros(32, cin, 3, 3, requires_grad=True)
+    F.conv2d(x, wt, None, padding=1).backward(D[..., 160:192].float().permute(0, 3, 1, 2).cpu())
+    assert relerr(new.cpu(), wt.grad) < 5e-3
+    assert relerr(new_acc.cpu() - 0.5, 0.5 * wt.grad) < 5e-3
+    assert relerr(new.cpu(), old.cpu()) < 1e-5, "r32 kernel vs the stacked <32> kernel"
 
 
 @pytest.mark.parametrize("env", [{}, {"SRCGAN_B200_WSTACK32": "1"}, {"SRCGAN_B200_NO_WSTACK": "1"}])
