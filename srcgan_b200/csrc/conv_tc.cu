@@ -3215,14 +3215,15 @@ static int launch4(const CUtensorMap& tx, const CUtensorMap& tg, const Wg4Args& 
 // ---------------------------------------------------------------------------------------------
 // kw-stacked wgrad for a 32-channel input slice and 32 output channels (the 32 -> 32 remainder launches of the paired dense-block
 // weight gradients: x_k slice x dZ_(k+1) slice of two 192-channel concat buffers, 64 useful bytes per pixel and operand).
-// Experiment (opt-in, see r32_ok): the hypothesis was that conv3x3_wgrad_stack_tc<32> spends those launches on the TMA engine -
-// a TMA unit retires one box row per ~3.3 clk whatever its length, a 128-pixel tile is 160 rows of X + 144 rows of dY (1 000 clk) -
-// and on 2 x 8 MMAs of N = 96 per tile (900 clk; one 64-channel atom holds only two vertical taps).  Here
-//   * X is a SWIZZLE_64B slab of 32-channel atoms: M = 128 = FOUR atoms one slab row apart = the three vertical taps + a
-//     phantom, ONE MMA of N = 96 per 16-pixel row (8 per tile, 450 clk);
-//   * dY does not go through TMA: the four epilogue warps, idle until the last tile, copy it with 16-byte cp.async into the
-//     same swizzled [8 rows][18 px][32 ch] slab (zero fill outside the image), several tiles in flight; the TMA unit
-//     moves the 160 rows of X only (530 clk).
+// In conv3x3_wgrad_stack_tc<32> one 64-channel X atom holds only two vertical taps, so a 128-pixel tile costs 2 x 8 MMAs of N = 96
+// (900 clk) beside 304 TMA box rows (160 of X + 144 of dY at ~3.3 clk per row: 1 000 clk); ncu: 71 % SM throughput, 40 % DRAM.
+//   * Here X is a SWIZZLE_64B slab of 32-channel atoms: M = 128 = FOUR atoms one slab row apart = the three vertical taps + a
+//     phantom, ONE MMA of N = 96 per 16-pixel row (8 per tile, 450 clk).
+//   * LSU = false (default): dY through TMA like X (tensor maps with 64-byte L2 promotion: DRAM traffic = the useful bytes).
+//   * LSU = true (SRCGAN_B200_WGRAD_R32=lsu, the first version): dY does not go through TMA - the four epilogue warps, idle
+//     until the last tile, copy it with 16-byte cp.async into the same swizzled [8 rows][18 px][32 ch] slab (zero fill outside
+//     the image), several tiles in flight.  Measured no faster than the stacked kernel: LSU loads of a 64-byte slice pull
+//     whole 128-byte lines from DRAM (867 instead of 568 MB per launch, 80 % of the copy bandwidth).
 // Same tile order, k-step order and fp32 partial layout as conv3x3_wgrad_stack_tc, so the reduce launch is shared.
 // ---------------------------------------------------------------------------------------------
 constexpr int R32_X_BYTES = WS_X_ROWS * WS_TW * 64;                   // 10240: [10 rows][16 px][32 ch]
@@ -3235,8 +3236,10 @@ constexpr int R32_CHUNKS = WS_TH * WS_G_W * 4;                        // 576 16-
 constexpr int R32_PER_THREAD = (R32_CHUNKS + 127) / 128;              // 5
 static_assert(R32_LAG < R32_STAGES, "the cp.async producers would wait for a stage their own pending arrival frees");
 
+template <bool LSU>      // dY through cp.async by the epilogue warps (true) or through TMA like X (false)
 __global__ void __launch_bounds__(NUM_THREADS, 1)
-conv3x3_wgrad_r32_tc(const __grid_constant__ CUtensorMap tmap_x, const __nv_bfloat16* __restrict__ g, int g_ld, const Wg4Args a) {
+conv3x3_wgrad_r32_tc(const __grid_constant__ CUtensorMap tmap_x, const __grid_constant__ CUtensorMap tmap_g,
+                     const __nv_bfloat16* __restrict__ g, int g_ld, const Wg4Args a) {
   extern __shared__ uint8_t smem_raw[];
   uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~(uintptr_t)1023);
   uint8_t* aux = smem + R32_STAGES * R32_STAGE;
@@ -3249,7 +3252,7 @@ conv3x3_wgrad_r32_tc(const __grid_constant__ CUtensorMap tmap_x, const __nv_bflo
   const int split = blockIdx.x;
   if (threadIdx.x == 0) {
     // a stage is full when the TMA bytes of X have landed (one arrive.expect_tx) and all 128 copy threads have arrived
-    for (int s = 0; s < R32_STAGES; ++s) { mbar_init(&full_bar[s], 1 + 128); mbar_init(&empty_bar[s], 1); }
+    for (int s = 0; s < R32_STAGES; ++s) { mbar_init(&full_bar[s], LSU ? 1 + 128 : 1); mbar_init(&empty_bar[s], 1); }
     mbar_init(done_bar, 1);
     asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
   }
@@ -3278,8 +3281,9 @@ conv3x3_wgrad_r32_tc(const __grid_constant__ CUtensorMap tmap_x, const __nv_bflo
       const int img = (int)(r / a.tiles_x);
       mbar_wait(&empty_bar[stage], phase ^ 1);
       if (elect_one()) {
-        mbar_expect_tx(&full_bar[stage], (uint32_t)R32_X_BYTES);
+        mbar_expect_tx(&full_bar[stage], (uint32_t)(LSU ? R32_X_BYTES : R32_STAGE));
         tma_load_4d(&tmap_x, &full_bar[stage], smem + stage * R32_STAGE, 0, bx * WS_TW, by * WS_TH - 1, img);
+        if (!LSU) tma_load_4d(&tmap_g, &full_bar[stage], smem + stage * R32_STAGE + R32_X_BYTES, 0, bx * WS_TW - 1, by * WS_TH, img);
       }
       __syncwarp();
       if (++stage == R32_STAGES) { stage = 0; phase ^= 1; }
@@ -3330,7 +3334,7 @@ conv3x3_wgrad_r32_tc(const __grid_constant__ CUtensorMap tmap_x, const __nv_bflo
     int stage = 0, sig = 0, pend = 0;
     uint32_t phase = 0;
     pdl_wait();                                                         // dY is the previous kernels' output
-    for (long long t = t_beg; t < t_end; ++t) {
+    for (long long t = t_beg; LSU && t < t_end; ++t) {
       long long r = t;
       const int by = (int)(r % a.tiles_y); r /= a.tiles_y;
       const int bx = (int)(r % a.tiles_x);
@@ -3358,8 +3362,10 @@ conv3x3_wgrad_r32_tc(const __grid_constant__ CUtensorMap tmap_x, const __nv_bflo
       }
       if (++stage == R32_STAGES) { stage = 0; phase ^= 1; }
     }
-    asm volatile("cp.async.wait_group 0;" ::: "memory");
-    asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
+    if (LSU) {
+      asm volatile("cp.async.wait_group 0;" ::: "memory");
+      asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
+    }
     for (; pend > 0; --pend) {
       mbar_arrive(&full_bar[sig]);
       if (++sig == R32_STAGES) sig = 0;
@@ -3396,14 +3402,18 @@ conv3x3_wgrad_r32_tc(const __grid_constant__ CUtensorMap tmap_x, const __nv_bflo
   }
 }
 
-// 32-channel (or thinner) input slice, 32 output channels, no in-kernel bias gradient.  OPT-IN (SRCGAN_B200_WGRAD_R32=1): measured
-// at 64 x 256 x 256 it takes 0.1754 ms against 0.1712 ms of conv3x3_wgrad_stack_tc<32> - neither the TMA row rate nor the MMA count
-// bounds these launches ("What bounds them" 19).
-static bool r32_ok(const srcgan_conv_params* p, const float* dbpart) {
-  return p->cout == 32 && p->cin <= 32 && dbpart == nullptr && getenv("SRCGAN_B200_WGRAD_R32");
+// 32-channel (or thinner) input slice, 32 output channels, no in-kernel bias gradient.  SRCGAN_B200_WGRAD_R32 = "0": off (the
+// stacked <32> kernel), "lsu": the cp.async variant - measured at 64 x 256 x 256: 0.1754 ms against 0.1712 ms of
+// conv3x3_wgrad_stack_tc<32>, because the LSU path reads whole 128-byte lines from DRAM ("What bounds them" 19).
+static int r32_mode(const srcgan_conv_params* p, const float* dbpart) {       // 0 off, 1 TMA, 2 cp.async
+  if (!(p->cout == 32 && p->cin <= 32 && dbpart == nullptr)) return 0;
+  const char* e = getenv("SRCGAN_B200_WGRAD_R32");
+  if (!e) return 1;
+  return e[0] == '0' ? 0 : (e[0] == 'l' ? 2 : 1);
 }
 
-static int launch_r32(const srcgan_conv_params* p, const Wg4Args& a, cudaStream_t st) {
+template <bool LSU>
+static int launch_r32(const srcgan_conv_params* p, const CUtensorMap& tg, const Wg4Args& a, cudaStream_t st) {
   CUtensorMap tx;
   int rc = make_tmap_box(&tx, p->x, p->cin, p->w, p->h, p->n, p->x_ld, 32, WS_TW, WS_X_ROWS, CU_TENSOR_MAP_SWIZZLE_64B,
                          "conv_wgrad_r32(x)");
@@ -3411,16 +3421,16 @@ static int launch_r32(const srcgan_conv_params* p, const Wg4Args& a, cudaStream_
   static DeviceOnce attr_set;
   int attr_set_dev;
   if (attr_set.needed(&attr_set_dev)) {
-    SRCGAN_CUDA(cudaFuncSetAttribute(conv3x3_wgrad_r32_tc, cudaFuncAttributeMaxDynamicSharedMemorySize, R32_SMEM));
+    SRCGAN_CUDA(cudaFuncSetAttribute(conv3x3_wgrad_r32_tc<LSU>, cudaFuncAttributeMaxDynamicSharedMemorySize, R32_SMEM));
     attr_set.mark(attr_set_dev);
   }
   cudaLaunchConfig_t cfg = {};
   cfg.gridDim = dim3((unsigned)a.splits); cfg.blockDim = dim3(NUM_THREADS); cfg.dynamicSmemBytes = R32_SMEM; cfg.stream = st;
   cudaLaunchAttribute at[1];
   cfg.attrs = at; cfg.numAttrs = pdl_attr(&at[0]);
-  SRCGAN_CUDA(cudaLaunchKernelEx(&cfg, conv3x3_wgrad_r32_tc, tx, reinterpret_cast<const __nv_bfloat16*>(p->y), (int)p->y_ld, a));
+  SRCGAN_CUDA(cudaLaunchKernelEx(&cfg, conv3x3_wgrad_r32_tc<LSU>, tx, tg, reinterpret_cast<const __nv_bfloat16*>(p->y), (int)p->y_ld, a));
   count_launch();
-  return check_launch("conv3x3_wgrad_r32_tc");
+  return check_launch(LSU ? "conv3x3_wgrad_r32_tc<lsu>" : "conv3x3_wgrad_r32_tc<tma>");
 }
 }  // namespace tcw4
 
@@ -3502,7 +3512,7 @@ int conv_wgrad_tc_split(const srcgan_conv_params* p, float* dw0, int ld0, int ci
   rc = tcw4::make_tmap_box(&tg, p->y, p->cout, p->wo, p->ho, p->n, p->y_ld, bn, tcw4::WS_G_W, tcw4::WS_TH,
                            bn == 64 ? CU_TENSOR_MAP_SWIZZLE_128B : CU_TENSOR_MAP_SWIZZLE_64B, "conv_wgrad_split(dy)");
   if (rc) return rc;
-  if (tcw4::r32_ok(p, a4.dbpart)) rc = tcw4::launch_r32(p, a4, st);
+  if (const int m = tcw4::r32_mode(p, a4.dbpart)) rc = m == 2 ? tcw4::launch_r32<true>(p, tg, a4, st) : tcw4::launch_r32<false>(p, tg, a4, st);
   else rc = bn == 64 ? tcw4::launch4<64>(tx, tg, a4, st) : tcw4::launch4<32>(tx, tg, a4, st);
   if (rc) return rc;
   // split-K reduce of the weight gradients and, in the same launch, of the bias gradients the kernel summed per split
@@ -3532,7 +3542,7 @@ int conv_wgrad_tc(const srcgan_conv_params* p, float* dw, float* db, int accumul
     rc = tcw4::make_tmap_box(&tg, p->y, p->cout, p->wo, p->ho, p->n, p->y_ld, bn, tcw4::WS_G_W, tcw4::WS_TH,
                              bn == 64 ? CU_TENSOR_MAP_SWIZZLE_128B : CU_TENSOR_MAP_SWIZZLE_64B, "conv_wgrad_tc(stack dy)");
     if (rc) return rc;
-    if (tcw4::r32_ok(p, a4.dbpart)) rc = tcw4::launch_r32(p, a4, st);
+    if (const int m = tcw4::r32_mode(p, a4.dbpart)) rc = m == 2 ? tcw4::launch_r32<true>(p, tg, a4, st) : tcw4::launch_r32<false>(p, tg, a4, st);
     else rc = bn == 64 ? tcw4::launch4<64>(tx, tg, a4, st) : tcw4::launch4<32>(tx, tg, a4, st);
     if (rc) return rc;
     return wgrad_reduce_db_launch(reinterpret_cast<const float*>(ws), a4.splits, 9, p->cin, p->cout, p->cout, dw, p->cin, 0, nullptr,

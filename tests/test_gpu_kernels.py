@@ -841,8 +841,9 @@ def test_conv_wgrad_split_pairs_dense_block_layers(ka):
 
 @pytest.mark.parametrize("shape", [(2, 40, 52, 32), (1, 131, 64, 32), (3, 16, 16, 16), (1, 9, 70, 24)])
 def test_conv_wgrad_r32_kernel(shape, monkeypatch):
-    """The opt-in conv3x3_wgrad_r32_tc (32-channel slice x 32-channel slice, dY copied by cp.async, four vertical taps in M) against
-    torch and against conv3x3_wgrad_stack_tc<32> on the same slices (ragged tile grids, thin slices, accumulate / alpha)."""
+    """conv3x3_wgrad_r32_tc (32-channel slice x 32-channel slice: four vertical taps stacked into M, one MMA per 16-pixel row;
+    dY through TMA - the default - or copied by cp.async) against torch and against conv3x3_wgrad_stack_tc<32> on the same
+    slices (ragged tile grids, thin slices, accumulate / alpha)."""
     from srcgan_b200 import ops
     n, h, w, cin = shape
     g0 = torch.Generator().manual_seed(123)
@@ -856,16 +857,18 @@ def test_conv_wgrad_r32_kernel(shape, monkeypatch):
         torch.cuda.synchronize()
         return dw
 
-    old = run(False)
-    monkeypatch.setenv("SRCGAN_B200_WGRAD_R32", "1")
-    new = run(False)
-    new_acc = run(True)
     x = X[..., 128:128 + cin].float().permute(0, 3, 1, 2).cpu()
     wt = torch.zeros(32, cin, 3, 3, requires_grad=True)
     F.conv2d(x, wt, None, padding=1).backward(D[..., 160:192].float().permute(0, 3, 1, 2).cpu())
-    assert relerr(new.cpu(), wt.grad) < 5e-3
-    assert relerr(new_acc.cpu() - 0.5, 0.5 * wt.grad) < 5e-3
-    assert relerr(new.cpu(), old.cpu()) < 1e-5, "r32 kernel vs the stacked <32> kernel"
+    monkeypatch.setenv("SRCGAN_B200_WGRAD_R32", "0")
+    old = run(False)
+    for mode in ("tma", "lsu"):
+        monkeypatch.setenv("SRCGAN_B200_WGRAD_R32", mode)
+        new = run(False)
+        new_acc = run(True)
+        assert relerr(new.cpu(), wt.grad) < 5e-3, mode
+        assert relerr(new_acc.cpu() - 0.5, 0.5 * wt.grad) < 5e-3, mode
+        assert relerr(new.cpu(), old.cpu()) < 1e-5, "r32 kernel (%s) vs the stacked <32> kernel" % mode
 
 
 @pytest.mark.parametrize("env", [{}, {"SRCGAN_B200_WSTACK32": "1"}, {"SRCGAN_B200_NO_WSTACK": "1"}])
