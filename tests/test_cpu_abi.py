@@ -94,6 +94,44 @@ def test_thin_layers_are_padded_onto_the_tensor_core_engine():
     assert engine.tc_dgrad_s2_supported(32, 64, 4, 2, 1, bf)                         # its dgrad, image padded to 32
 
 
+def test_thin_input_layers_take_the_tiled_ffma_kernel(monkeypatch):
+    """<= 4 input channels through a 4x4 filter (first discriminator layer, gradient of the patch-logit layer) go to the FFMA
+    kernel thin_in_tiled; 3x3 stride-1 image convolutions stay on the tcgen05 sweep (K zero-filled by TMA)."""
+    import torch
+    from srcgan_b200 import engine
+    from srcgan_b200._lib import ENGINE_SIMT, ENGINE_TC, WL_RSCK
+    bf = torch.bfloat16
+    assert engine.select(3, 64, 4, 2, False, bf, 128, 128) == (ENGINE_SIMT, WL_RSCK)
+    assert engine.select(1, 256, 4, 1, False, bf, 62, 62) == (ENGINE_SIMT, WL_RSCK)
+    assert engine.select(3, 64, 3, 1, False, bf, 256, 256)[0] == ENGINE_TC
+    assert engine.select(3, 32, 4, 2, False, bf, 128, 128)[0] == ENGINE_TC           # not a multiple of 64 output channels
+    monkeypatch.setenv("SRCGAN_B200_NO_THIN_TILED", "1")
+    assert engine.select(3, 64, 4, 2, False, bf, 128, 128)[0] == ENGINE_TC
+
+
+def test_operator_layer_thin_tensors_are_pitch_8_views(monkeypatch):
+    """functional.py: a bf16 tensor with fewer than 8 channels is the view buf[..., :c] of a pitch-8 buffer (TMA-addressable),
+    recognised by _sl() / _canon(); fp32 tensors and wide tensors stay dense; .contiguous() gives an ordinary dense copy."""
+    import torch
+    from srcgan_b200 import functional as Fn
+    like = torch.empty((), dtype=torch.bfloat16)
+    t = Fn._new_thin(2, 5, 7, 3, like)
+    assert tuple(t.shape) == (2, 5, 7, 3) and t.stride() == (280, 56, 8, 1) and not t.is_contiguous()
+    assert Fn._is_padded_view(t) and Fn._canon(t) is t
+    s = Fn._sl(t)
+    assert (s.ld, s.c0, s.c, s.ptr) == (8, 0, 3, t.data_ptr()) and tuple(s.buf.shape) == (2, 5, 7, 8)
+    t.copy_(torch.arange(2 * 5 * 7 * 3, dtype=torch.float32).reshape(2, 5, 7, 3) % 17)
+    assert torch.equal(s.buf[..., :3], t) and t.contiguous().is_contiguous()
+    assert Fn._new_thin(2, 5, 7, 3, torch.empty((), dtype=torch.float32)).is_contiguous()      # fp32 parity mode: dense
+    assert Fn._new_thin(2, 5, 7, 8, like).is_contiguous()                                      # 8 channels: dense
+    odd = torch.empty(2, 5, 7, 6, dtype=torch.bfloat16)[..., :3]                               # some other strided view
+    assert not Fn._is_padded_view(odd) and Fn._canon(odd).is_contiguous()
+    wide = torch.empty(2, 5, 7, 64, dtype=torch.bfloat16)
+    assert Fn._sl(wide).ld == 64 and Fn._canon(wide) is wide
+    monkeypatch.setenv("SRCGAN_B200_NO_THIN_PITCH", "1")
+    assert Fn._new_thin(2, 5, 7, 3, like).is_contiguous()
+
+
 def test_missing_library_fails_loudly(tmp_path, monkeypatch):
     from srcgan_b200 import _lib
     monkeypatch.setattr(_lib, "_lib", None)
