@@ -2912,14 +2912,23 @@ constexpr int WS_G_W = WS_TW + 2;
 // BN = 32: N = 96, channel blocks of 128 (two X atoms) or <= 64 (one atom, two vertical taps per M).
 // BN = 64: N = 192; three accumulators would need 576 TMEM columns, so every channel block is <= 64 channels with two
 //          vertical taps per M (2 x 192 columns) - X is then read once for all 64 output channels.
-template <int BN>
+// T22 (BN = 64 only): the third vertical tap without a phantom.  Its accumulator is M = (X | X one pixel to the right) x
+// N = 128 = (dY | dY one pixel to the right): the four (X shift, dY shift) pairs are the horizontal taps kw = 1, 0, 2 and a
+// duplicate of kw = 1 that is discarded - 96 + 64 clk per k-step for nine taps (90 % useful) instead of 96 + 96 (75 %).  The X
+// slab is one pixel wider for it ([10 rows][17 px]); a tile's kw = 2 products then cover X pixels x0+1 .. x0+16, which still
+// partitions the image row (X pixel 0 only ever meets dY pixel -1 = padding).
+template <int BN, bool T22 = false>
 struct W4Cfg {
+  static_assert(!T22 || BN == 64, "T22 is the 64-output-channel scheme");
   static constexpr int N = 3 * BN;
   static constexpr int CBLK = BN == 64 ? 64 : 128;                    // input channels per CTA
   static constexpr int NATOM = CBLK / 64;
   static constexpr int PX = BN * 2;                                   // bytes of one dY pixel in the slab
   static constexpr int G_BYTES = WS_TH * WS_G_W * PX;                 // [8 rows][18 px][BN ch]: 9216 / 18432
-  static constexpr int STAGE = NATOM * WS_X_ATOM + G_BYTES;           // 50176 / 38912
+  static constexpr int XW = T22 ? WS_TW + 1 : WS_TW;                  // X slab width in pixels
+  static constexpr int X_BOX = WS_X_ROWS * XW * 128;                  // bytes of one X atom as TMA delivers it: 20480 / 21760
+  static constexpr int X_ATOM = (X_BOX + 1023) / 1024 * 1024;         // its slot in the stage (the dY slab stays 1024-byte aligned)
+  static constexpr int STAGE = NATOM * X_ATOM + G_BYTES;              // 50176 / 38912 / 40960
   static constexpr int STAGES_RAW = (SMEM_BUDGET - SMEM_AUX - 2048 - 1024) / STAGE;
   static constexpr int STAGES = STAGES_RAW > 6 ? 6 : STAGES_RAW;      // 4 / 5
   static constexpr int ZROW = WS_TW * 128;                            // one all-zero slab row [16 px][64 ch] (the phantom tap's operand)
@@ -2945,11 +2954,12 @@ __host__ __device__ constexpr uint32_t desc_hi_sw(uint32_t sbo_bytes, int bn) {
   return bn == 64 ? desc_hi(sbo_bytes) : desc_hi_sw64(sbo_bytes);     // 128-byte pixels: SWIZZLE_128B, 64-byte: SWIZZLE_64B
 }
 
-template <int BN>
+template <int BN, bool T22 = false>
 __global__ void __launch_bounds__(NUM_THREADS, 1)
 conv3x3_wgrad_stack_tc(const __grid_constant__ CUtensorMap tmap_x, const __grid_constant__ CUtensorMap tmap_g, const Wg4Args a) {
-  using C = W4Cfg<BN>;
+  using C = W4Cfg<BN, T22>;
   constexpr int WS_STAGES = C::STAGES, WS_STAGE = C::STAGE, WS_G_BYTES = C::G_BYTES;
+  constexpr int WS_X_ATOM = C::X_ATOM;
   constexpr int G_OFF = C::NATOM * WS_X_ATOM;                          // dY slab offset inside a stage
   extern __shared__ uint8_t smem_raw[];
   uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~(uintptr_t)1023);
@@ -2992,7 +3002,7 @@ conv3x3_wgrad_stack_tc(const __grid_constant__ CUtensorMap tmap_x, const __grid_
   const long long t_beg = (long long)split * a.tiles_per_split;
   long long t_end = t_beg + a.tiles_per_split;
   if (t_end > a.num_tiles) t_end = a.num_tiles;
-  const uint32_t stage_tx = (uint32_t)((paired ? 1 : 2) * WS_X_ATOM + WS_G_BYTES);
+  const uint32_t stage_tx = (uint32_t)((paired ? 1 : 2) * C::X_BOX + WS_G_BYTES);
 
   if (warp == 0) {
     int stage = 0;
@@ -3020,7 +3030,7 @@ conv3x3_wgrad_stack_tc(const __grid_constant__ CUtensorMap tmap_x, const __grid_
   } else if (warp == 1) {
     constexpr uint32_t idesc = tcw::umma_idesc_mn(128, C::N);
     constexpr uint32_t a_hi = desc_hi(1024), g_hi = desc_hi_sw(8 * C::PX, BN);   // 8 pixels of a row: 8 x 128 B resp. 8 dY pixels
-    constexpr uint32_t ROW_A = WS_TW * 128, ROW_G = WS_G_W * C::PX;     // slab row pitches: 2048 B, 1152 / 2304 B
+    constexpr uint32_t ROW_A = C::XW * 128, ROW_G = WS_G_W * C::PX;     // slab row pitches: 2048 (T22: 2176) B, 1152 / 2304 B
     int stage = 0;
     uint32_t phase = 0;
     uint32_t accumulate = 0;
@@ -3035,6 +3045,20 @@ conv3x3_wgrad_stack_tc(const __grid_constant__ CUtensorMap tmap_x, const __grid_
         // A: LBO = distance of the second 64-row half of M (the other channel atom, or the next vertical tap's row)
         const uint32_t a_lo = desc_lo(sx, paired ? ROW_A : (uint32_t)WS_X_ATOM);
         const uint32_t g_lo = desc_lo(sg, C::PX);                       // N atoms one pixel apart
+        if constexpr (T22) {
+          // accumulator 0: taps (kh 0 | kh 1) x kw 2..0 as below; accumulator 1 (columns 192..319): kh = 2, M atoms one PIXEL apart,
+          // N atoms = dY one and two slab pixels in (slab pixel 0 is image pixel x0 - 1): X - dY = 0, -1 | +1, 0
+          constexpr uint32_t idesc2 = tcw::umma_idesc_mn(128, 128);
+          const uint32_t a2_lo = desc_lo(sx, 128), g2_lo = desc_lo(sg + (uint32_t)C::PX, C::PX);
+#pragma unroll
+          for (int r = 0; r < WS_TH; ++r)
+            umma_bf16_w(tmem_base, a_lo + (uint32_t)((r * ROW_A) >> 4), a_hi, g_lo + (uint32_t)((r * ROW_G) >> 4), g_hi, idesc,
+                        accumulate | (uint32_t)(r > 0));
+#pragma unroll
+          for (int r = 0; r < WS_TH; ++r)
+            umma_bf16_w(tmem_base + (uint32_t)C::N, a2_lo + (uint32_t)(((r + 2) * ROW_A) >> 4), a_hi,
+                        g2_lo + (uint32_t)((r * ROW_G) >> 4), g_hi, idesc2, accumulate | (uint32_t)(r > 0));
+        } else
         for (int g = 0; g < ngroups; ++g) {
           const int kh0 = paired ? 2 * g : g;                           // vertical tap of the first half of M
           const uint32_t tmem_d = tmem_base + (uint32_t)(g * C::N);
@@ -3122,15 +3146,18 @@ conv3x3_wgrad_stack_tc(const __grid_constant__ CUtensorMap tmap_x, const __grid_
       int kh, ci;
       if (paired) { kh = 2 * g + (row >> 6); ci = cb * C::CBLK + (row & 63); }
       else { kh = g; ci = cb * C::CBLK + row; }
+      const bool t22 = T22 && g == 1;                                  // rows = (X, X + 1 px) of tap kh = 2, columns = 2 dY shifts
+      if (t22) kh = 2;
       const bool row_ok = kh < 3 && ci < a.cin;
 #pragma unroll 1
-      for (int j = 0; j < 3; ++j) {
+      for (int j = 0; j < (t22 ? 2 : 3); ++j) {
 #pragma unroll 1
         for (int c32 = 0; c32 < BN; c32 += 32) {
           uint32_t v[32];
           tmem_ld32(tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)(g * C::N + j * BN + c32), v);
-          if (row_ok) {
-            const int tap = kh * 3 + (2 - j);
+          const int kw = !t22 ? 2 - j : ((row >> 6) ? 2 : 1 - j);
+          if (row_ok && !(t22 && (row >> 6) && j == 1)) {                // (X + 1, dY + 1) repeats kw = 1 on a shifted window
+            const int tap = kh * 3 + kw;
             float* dst = a.part + (((long long)split * 9 + tap) * a.cin + ci) * a.cout + nb * BN + c32;
 #pragma unroll
             for (int i = 0; i < 8; ++i) {
@@ -3154,6 +3181,12 @@ conv3x3_wgrad_stack_tc(const __grid_constant__ CUtensorMap tmap_x, const __grid_
 }
 
 static int bn4(const srcgan_conv_params* p) { return p->cout == 64 && !getenv("SRCGAN_B200_WSTACK32") ? 64 : 32; }
+// 64 output channels: the phantom-free third tap (W4Cfg); SRCGAN_B200_WGRAD_T22=0 brings back (kh 2 | zero row) x N = 192
+static bool t22_on(const srcgan_conv_params* p) {
+  const char* e = getenv("SRCGAN_B200_WGRAD_T22");
+  return bn4(p) == 64 && !(e && e[0] == '0');
+}
+static int x_box_w(const srcgan_conv_params* p) { return t22_on(p) ? WS_TW + 1 : WS_TW; }
 
 static void plan4(const srcgan_conv_params* p, Wg4Args& a) {
   const int bn = bn4(p);
@@ -3193,13 +3226,13 @@ static int make_tmap_box(CUtensorMap* tm, const void* ptr, int c, int w, int h, 
   return SRCGAN_OK;
 }
 
-template <int BN>
+template <int BN, bool T22 = false>
 static int launch4(const CUtensorMap& tx, const CUtensorMap& tg, const Wg4Args& a, cudaStream_t st) {
-  using C = W4Cfg<BN>;
+  using C = W4Cfg<BN, T22>;
   static DeviceOnce attr_set;
   int attr_set_dev;
   if (attr_set.needed(&attr_set_dev)) {
-    SRCGAN_CUDA(cudaFuncSetAttribute(conv3x3_wgrad_stack_tc<BN>, cudaFuncAttributeMaxDynamicSharedMemorySize, C::SMEM));
+    SRCGAN_CUDA(cudaFuncSetAttribute(conv3x3_wgrad_stack_tc<BN, T22>, cudaFuncAttributeMaxDynamicSharedMemorySize, C::SMEM));
     attr_set.mark(attr_set_dev);
   }
   const unsigned grid = (unsigned)(a.cblocks * a.nblocks * a.splits);
@@ -3207,9 +3240,12 @@ static int launch4(const CUtensorMap& tx, const CUtensorMap& tg, const Wg4Args& 
   cfg.gridDim = dim3(grid); cfg.blockDim = dim3(NUM_THREADS); cfg.dynamicSmemBytes = C::SMEM; cfg.stream = st;
   cudaLaunchAttribute at[1];
   cfg.attrs = at; cfg.numAttrs = pdl_attr(&at[0]);
-  SRCGAN_CUDA(cudaLaunchKernelEx(&cfg, conv3x3_wgrad_stack_tc<BN>, tx, tg, a));
+  SRCGAN_CUDA(cudaLaunchKernelEx(&cfg, conv3x3_wgrad_stack_tc<BN, T22>, tx, tg, a));
   count_launch();
   return check_launch(BN == 64 ? "conv3x3_wgrad_stack_tc<64>" : "conv3x3_wgrad_stack_tc<32>");
+}
+static int launch4_64(const srcgan_conv_params* p, const CUtensorMap& tx, const CUtensorMap& tg, const Wg4Args& a, cudaStream_t st) {
+  return t22_on(p) ? launch4<64, true>(tx, tg, a, st) : launch4<64, false>(tx, tg, a, st);
 }
 
 // ---------------------------------------------------------------------------------------------
@@ -3458,8 +3494,11 @@ bool conv_wgrad_tc_supported(const srcgan_conv_params* p) {
 }
 
 static bool wgrad_stack_ok(const srcgan_conv_params* p) {
-  return p->kh == 3 && p->kw == 3 && p->stride == 1 && p->pad == 1 && (p->cout == 32 || p->cout == 64) && p->cin >= 16 &&
-         p->cin % 8 == 0 && !getenv("SRCGAN_B200_NO_WSTACK");
+  // any number of input channels: the X box is 64 channels wide and TMA zero-fills what the slice does not have (an image
+  // convolution, 3 -> 64, costs what 64 -> 64 costs: 0.29 ms at 64 x 256^2 against 0.56 ms on the per-tap halo kernel)
+  const bool thin_ok = p->cin < 16 && p->cout == 64 && !getenv("SRCGAN_B200_NO_WSTACK_THIN");
+  return p->kh == 3 && p->kw == 3 && p->stride == 1 && p->pad == 1 && (p->cout == 32 || p->cout == 64) &&
+         ((p->cin >= 16 && p->cin % 8 == 0) || thin_ok) && !getenv("SRCGAN_B200_NO_WSTACK");
 }
 
 static bool wgrad_halo_ok(const srcgan_conv_params* p) {
@@ -3505,7 +3544,7 @@ int conv_wgrad_tc_split(const srcgan_conv_params* p, float* dw0, int ld0, int ci
   const bool want_db = db0 != nullptr || db1 != nullptr;
   a4.dbpart = want_db ? reinterpret_cast<float*>(reinterpret_cast<char*>(ws) + ((wbytes + 255) / 256) * 256) : nullptr;
   CUtensorMap tx, tg;
-  int rc = tcw4::make_tmap_box(&tx, p->x, p->cin, p->w, p->h, p->n, p->x_ld, 64, tcw4::WS_TW, tcw4::WS_X_ROWS,
+  int rc = tcw4::make_tmap_box(&tx, p->x, p->cin, p->w, p->h, p->n, p->x_ld, 64, tcw4::x_box_w(p), tcw4::WS_X_ROWS,
                                CU_TENSOR_MAP_SWIZZLE_128B, "conv_wgrad_split(x)");
   if (rc) return rc;
   const int bn = tcw4::bn4(p);
@@ -3513,7 +3552,7 @@ int conv_wgrad_tc_split(const srcgan_conv_params* p, float* dw0, int ld0, int ci
                            bn == 64 ? CU_TENSOR_MAP_SWIZZLE_128B : CU_TENSOR_MAP_SWIZZLE_64B, "conv_wgrad_split(dy)");
   if (rc) return rc;
   if (const int m = tcw4::r32_mode(p, a4.dbpart)) rc = m == 2 ? tcw4::launch_r32<true>(p, tg, a4, st) : tcw4::launch_r32<false>(p, tg, a4, st);
-  else rc = bn == 64 ? tcw4::launch4<64>(tx, tg, a4, st) : tcw4::launch4<32>(tx, tg, a4, st);
+  else rc = bn == 64 ? tcw4::launch4_64(p, tx, tg, a4, st) : tcw4::launch4<32>(tx, tg, a4, st);
   if (rc) return rc;
   // split-K reduce of the weight gradients and, in the same launch, of the bias gradients the kernel summed per split
   return wgrad_reduce_db_launch(reinterpret_cast<const float*>(ws), a4.splits, 9, p->cin, p->cout, split, dw0, ld0, ci00, dw1, ld1,
@@ -3535,7 +3574,7 @@ int conv_wgrad_tc(const srcgan_conv_params* p, float* dw, float* db, int accumul
     wbytes = (size_t)a4.splits * 9 * p->cin * p->cout * sizeof(float);
     a4.dbpart = db ? reinterpret_cast<float*>(reinterpret_cast<char*>(ws) + ((wbytes + 255) / 256) * 256) : nullptr;
     CUtensorMap tx, tg;
-    int rc = tcw4::make_tmap_box(&tx, p->x, p->cin, p->w, p->h, p->n, p->x_ld, 64, tcw4::WS_TW, tcw4::WS_X_ROWS,
+    int rc = tcw4::make_tmap_box(&tx, p->x, p->cin, p->w, p->h, p->n, p->x_ld, 64, tcw4::x_box_w(p), tcw4::WS_X_ROWS,
                                  CU_TENSOR_MAP_SWIZZLE_128B, "conv_wgrad_tc(stack x)");
     if (rc) return rc;
     const int bn = tcw4::bn4(p);
@@ -3543,7 +3582,7 @@ int conv_wgrad_tc(const srcgan_conv_params* p, float* dw, float* db, int accumul
                              bn == 64 ? CU_TENSOR_MAP_SWIZZLE_128B : CU_TENSOR_MAP_SWIZZLE_64B, "conv_wgrad_tc(stack dy)");
     if (rc) return rc;
     if (const int m = tcw4::r32_mode(p, a4.dbpart)) rc = m == 2 ? tcw4::launch_r32<true>(p, tg, a4, st) : tcw4::launch_r32<false>(p, tg, a4, st);
-    else rc = bn == 64 ? tcw4::launch4<64>(tx, tg, a4, st) : tcw4::launch4<32>(tx, tg, a4, st);
+    else rc = bn == 64 ? tcw4::launch4_64(p, tx, tg, a4, st) : tcw4::launch4<32>(tx, tg, a4, st);
     if (rc) return rc;
     return wgrad_reduce_db_launch(reinterpret_cast<const float*>(ws), a4.splits, 9, p->cin, p->cout, p->cout, dw, p->cin, 0, nullptr,
                                   0, 0, accumulate, p->alpha, a4.dbpart, db, nullptr, st);   // bias gradient: summed in-kernel

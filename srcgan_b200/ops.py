@@ -236,7 +236,8 @@ class _Timed:
             self.tc = p.engine == ENGINE_TC and kind != "wgrad"
             if p.engine == ENGINE_TC and kind == "wgrad" and p.kh == 3 and p.stride == 1 and (p.cout == 32 or p.cout % 64 == 0):
                 # wgrad = the tcgen05 kernel + a split reduce; name the former (csrc/conv_tc.cu: wgrad_halo_ok)
-                stacked = p.cout in (32, 64) and p.cin >= 16 and p.cin % 8 == 0 and p.pad == 1     # wgrad_stack_ok
+                stacked = p.pad == 1 and ((p.cout in (32, 64) and p.cin >= 16 and p.cin % 8 == 0) or
+                                          (p.cout == 64 and p.cin < 16))                          # wgrad_stack_ok
                 self.key = "conv3x3_wgrad_stack_tc" if stacked else "conv3x3_wgrad_halo_tc<%d>" % (64 if p.cout % 64 == 0 else 32)
             self.flops = 2.0 * p.n * p.ho * p.wo * p.cin * p.cout * p.kh * p.kw
             self.shape = "%s %dx%dx%d %d->%d k%d s%d" % (kind, p.n, p.h, p.w, p.cin, p.cout, p.kh, p.stride)

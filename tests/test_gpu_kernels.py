@@ -871,12 +871,15 @@ def test_conv_wgrad_r32_kernel(shape, monkeypatch):
         assert relerr(new.cpu(), old.cpu()) < 1e-5, "r32 kernel (%s) vs the stacked <32> kernel" % mode
 
 
-@pytest.mark.parametrize("env", [{}, {"SRCGAN_B200_WSTACK32": "1"}, {"SRCGAN_B200_NO_WSTACK": "1"}])
-def test_conv_wgrad_tc_variants(env, monkeypatch):
-    """kw-stacked wgrad as N = 192 (default for 64 output channels), as two N = 96 halves, and the per-tap halo kernel all
-    give the same weight / bias gradients; the default launch is bit-reproducible."""
+@pytest.mark.parametrize("shape", [(2, 72, 40), (1, 33, 64), (2, 16, 17), (1, 9, 130)])
+@pytest.mark.parametrize("env", [{}, {"SRCGAN_B200_WGRAD_T22": "0"}, {"SRCGAN_B200_WSTACK32": "1"}, {"SRCGAN_B200_NO_WSTACK": "1"}])
+def test_conv_wgrad_tc_variants(env, shape, monkeypatch):
+    """kw-stacked wgrad for 64 output channels - with the phantom-free third tap (default: M = two X pixel shifts x N = two dY
+    shifts), with (tap | zero row) x N = 192, as two N = 96 halves - and the per-tap halo kernel all give the same weight / bias
+    gradients (image widths around the 16-pixel tile: the shifted X window at both borders); the default launch is
+    bit-reproducible."""
     from srcgan_b200 import ops
-    n, h, w, cin, cout = 2, 72, 40, 192, 64
+    (n, h, w), cin, cout = shape, 192, 64
     x = rand((n, cin, h, w), 41).bfloat16().float()
     wt = torch.zeros(cout, cin, 3, 3, requires_grad=True)
     y = F.conv2d(x, wt, None, stride=1, padding=1)
