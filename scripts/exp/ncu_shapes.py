@@ -1,5 +1,5 @@
 """The dominant convolution kernels on the benchmark's layer shapes (64 x 256 x 256 unless noted), two warm-up launches and
-one measured launch each - meant to run under `ncu --set full -k regex:'sweep|wgrad_stack'`; the launch order printed
+one measured launch each - meant to run under `ncu --set full -k regex:'sweep|wgrad_stack|wgrad_r32'`; the launch order printed
 here is the order of the rows in the exported CSV (scripts/summarise_ncu_conv.py turns it into profiles/traffic.json)."""
 import json
 import os
@@ -31,6 +31,8 @@ def wgrad(cin, cout, n, hw):
     X = ops.Slice(torch.randn((n, hw, hw, 192), dtype=torch.bfloat16, device=DEV), 0, cin)
     DY = ops.Slice(torch.randn((n, hw, hw, 192), dtype=torch.bfloat16, device=DEV), 192 - cout, cout)
     dw, db = torch.empty(cout, cin, 3, 3, device=DEV), torch.empty(cout, device=DEV)
+    if cin == 32:        # the 32 -> 32 remainder launches of the paired dense-block wgrads carry no bias gradient (conv3x3_wgrad_r32_tc)
+        db = None
     for _ in range(REPS):
         ops.conv_wgrad(X, DY, dw, db, 3, 1, 1, engine=ops.ENGINE_TC)
     torch.cuda.synchronize()

@@ -28,7 +28,7 @@ ours = sum(v[1] for k, v in agg.items() if k.startswith("srcgan"))
 print("%s: %d launches, %.1f ms of serialised device time; this library's kernels: %.1f %%" % (path, n, tot / 1e3, ours / tot * 100))
 fam = defaultdict(float)
 for k, v in agg.items():
-    for f_ in ("conv3x3_wgrad_stack_tc", "conv3x3_pair_sweep_tc", "conv3x3_sweep2_tc", "conv_igemm_tc", "conv_wgrad_tc_kernel", "bn_", "wgrad_reduce"):
+    for f_ in ("conv3x3_wgrad_stack_tc", "conv3x3_wgrad_r32_tc", "conv3x3_pair_sweep_tc", "conv3x3_sweep2_tc", "conv_igemm_tc", "conv_wgrad_tc_kernel", "bn_", "wgrad_reduce"):
         if f_ in k:
             fam[f_] += v[1]
 print("family shares of the run: " + ", ".join("%s %.1f %%" % (k, v / tot * 100) for k, v in sorted(fam.items(), key=lambda kv: -kv[1])))

@@ -11,7 +11,7 @@ tag = sys.argv[1] if len(sys.argv) > 1 else "r2d"
 shapes = [json.loads(l) for l in open(os.path.join(ROOT, "gpurun_out", tag + "_conv_shapes.json")) if l.startswith("{")]
 rows = list(csv.reader(open(os.path.join(ROOT, "gpurun_out", tag + "_conv_ncu.csv"))))
 hdr = {h: i for i, h in enumerate(rows[0])}
-launches = [r for r in rows[2:] if "sweep" in r[hdr["Kernel Name"]] or "wgrad_stack" in r[hdr["Kernel Name"]]]
+launches = [r for r in rows[2:] if any(k in r[hdr["Kernel Name"]] for k in ("sweep", "wgrad_stack", "wgrad_r32"))]
 out_name = sys.argv[2] if len(sys.argv) > 2 else "r2_ncu_conv.txt"
 out, traffic, i = [], {}, 0
 UNIT = {"byte": 1e-6, "Kbyte": 1e-3, "Mbyte": 1.0, "Gbyte": 1e3, "Tbyte": 1e6, "ns": 1e-3, "us": 1.0, "ms": 1e3, "s": 1e6}

@@ -441,6 +441,39 @@ def test_zoo_generators_parity(golden_zoo, which):
     assert all(p.grad is not None and torch.isfinite(p.grad).all() for p in net.parameters())
 
 
+@pytest.mark.parametrize("which,shape", [("ResDeconv", (2, 1, 64, 96)), ("EDSR_x4_rgb", (1, 3, 24, 20))])
+def test_operator_layer_thin_tensors_bf16(which, shape, monkeypatch):
+    """bf16 mode of the operator layer (functional.py): thin tensors in pitch-8 buffers put the image convolutions on the tcgen05
+    kernels and the <= 4-input-channel stem on thin_in_tiled; outputs, input gradient and every parameter gradient agree with the
+    dense-pitch / old-kernel path (same bf16 operands, fp32 accumulation on both sides)."""
+    from srcgan_b200 import nn as snn
+    snn.set_precision("bf16")
+    torch.manual_seed(5)
+    net = zoo_net(which).to(DEV)
+    x = rand(shape, 77).to(DEV)
+    gy = None
+
+    def run():
+        nonlocal gy
+        net.zero_grad()
+        xin = x.clone().requires_grad_(True)
+        y = net(xin)
+        if gy is None:
+            gy = rand(tuple(y.shape), 78).to(DEV)
+        y.backward(gy)
+        torch.cuda.synchronize()
+        return y.detach().clone(), xin.grad.clone(), {k: p.grad.clone() for k, p in net.named_parameters()}
+
+    y1, dx1, g1 = run()
+    monkeypatch.setenv("SRCGAN_B200_NO_THIN_PITCH", "1")
+    monkeypatch.setenv("SRCGAN_B200_NO_THIN_TILED", "1")
+    monkeypatch.setenv("SRCGAN_B200_THIN_WGRAD7_ROWS", "1")
+    y0, dx0, g0 = run()
+    assert relerr(y1, y0) < 2e-2 and l2err(dx1, dx0) < 2e-2
+    for k in g0:
+        assert l2err(g1[k], g0[k]) < 2e-2, k
+
+
 @pytest.mark.parametrize("variant", ["", "ConstLAB"])
 def test_cascade_step_against_golden(golden_cas_step, variant):
     """trainer_cas.CasSRC (mirror of trainCas*.py) on the CUDA path vs the real reference's iterations."""
