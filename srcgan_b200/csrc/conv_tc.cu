@@ -3506,7 +3506,23 @@ static bool wgrad_halo_ok(const srcgan_conv_params* p) {
          !getenv("SRCGAN_B200_NO_HALO");
 }
 
+// 3x3 weight gradient of a thin-output layer (64 -> 3 image convolution, 64 -> 1): the stacked kernel with dY's box 32 channels
+// wide - TMA zero-fills what the slice does not have - and partials / reduce over 32 output channels of which the first cout are
+// kept (the reduce's split destination); 0.45 ms on the per-tap halo kernel at 64 x 256^2
+static bool wgrad_stack_thin_out_ok(const srcgan_conv_params* p) {
+  return p->kh == 3 && p->kw == 3 && p->stride == 1 && p->pad == 1 && p->cout < 16 && p->cin >= 16 && p->cin % 8 == 0 &&
+         !getenv("SRCGAN_B200_NO_WSTACK") && !getenv("SRCGAN_B200_NO_WSTACK_THIN");
+}
+
 size_t conv_wgrad_tc_workspace(const srcgan_conv_params* p) {
+  if (wgrad_stack_thin_out_ok(p)) {
+    srcgan_conv_params q = *p;
+    q.cout = 32;
+    tcw4::Wg4Args a4;
+    tcw4::plan4(&q, a4);
+    const size_t wb = (size_t)a4.splits * 9 * q.cin * q.cout * sizeof(float);
+    return ((wb + 255) / 256) * 256 + (size_t)1024 * q.cout * sizeof(float) + 256;
+  }
   int bn, cblocks, nblocks, splits;
   long long tiles, tps;
   tcw::plan(p, bn, cblocks, nblocks, splits, tiles, tps);
@@ -3566,6 +3582,27 @@ int conv_wgrad_tc(const srcgan_conv_params* p, float* dw, float* db, int accumul
   long long tiles, tps;
   tcw::plan(p, bn, cblocks, nblocks, splits, tiles, tps);
   size_t wbytes = (size_t)splits * p->kh * p->kw * p->cin * p->cout * sizeof(float);
+  if (dw && wgrad_stack_thin_out_ok(p)) {
+    srcgan_conv_params q = *p;
+    q.cout = 32;
+    tcw4::Wg4Args a4;
+    tcw4::plan4(&q, a4);
+    a4.n = p->n; a4.ho = p->ho; a4.wo = p->wo; a4.cin = p->cin; a4.cout = 32;
+    a4.part = reinterpret_cast<float*>(ws);
+    wbytes = (size_t)a4.splits * 9 * p->cin * 32 * sizeof(float);
+    a4.dbpart = db ? reinterpret_cast<float*>(reinterpret_cast<char*>(ws) + ((wbytes + 255) / 256) * 256) : nullptr;
+    CUtensorMap tx, tg;
+    int rc = tcw4::make_tmap_box(&tx, p->x, p->cin, p->w, p->h, p->n, p->x_ld, 64, tcw4::WS_TW, tcw4::WS_X_ROWS,
+                                 CU_TENSOR_MAP_SWIZZLE_128B, "conv_wgrad_tc(stack x, thin dy)");
+    if (rc) return rc;
+    rc = tcw4::make_tmap_box(&tg, p->y, p->cout, p->wo, p->ho, p->n, p->y_ld, 32, tcw4::WS_G_W, tcw4::WS_TH,
+                             CU_TENSOR_MAP_SWIZZLE_64B, "conv_wgrad_tc(stack thin dy)");
+    if (rc) return rc;
+    rc = tcw4::launch4<32>(tx, tg, a4, st);
+    if (rc) return rc;
+    return wgrad_reduce_db_launch(reinterpret_cast<const float*>(ws), a4.splits, 9, p->cin, 32, p->cout, dw, p->cin, 0, nullptr, 0, 0,
+                                  accumulate, p->alpha, a4.dbpart, db, nullptr, st);
+  }
   if (dw && wgrad_stack_ok(p)) {
     tcw4::Wg4Args a4;
     tcw4::plan4(p, a4);
