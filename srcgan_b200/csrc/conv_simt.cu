@@ -309,7 +309,7 @@ template <bool DBL>
 __global__ void __launch_bounds__(256)
 wgrad_reduce_k(const float* __restrict__ part, int splits, int taps, int cin, int cout, int split, float* __restrict__ d0,
                int ld0, int ci00, float* __restrict__ d1, int ld1, int ci01, int accumulate, float alpha,
-               const float* __restrict__ dbpart, float* __restrict__ db0, float* __restrict__ db1, int nred) {
+               const float* __restrict__ dbpart, float* __restrict__ db0, float* __restrict__ db1, int nred, int ilp8) {
   using Acc = typename std::conditional<DBL, double, float>::type;
   __shared__ Acc red[8][33];
   pdl_launch_dependents();
@@ -344,6 +344,16 @@ wgrad_reduce_k(const float* __restrict__ part, int splits, int taps, int cin, in
   if (i < total) {
     const float* p = part + i;
     int k = y;
+    // eight loads in flight per thread while there are that many splits left (148 splits: 3 dependent rounds instead of 5 - the
+    // kernel is a chain of L2 latencies, three waves of blocks deep), then four, then one
+    for (; ilp8 && k + 56 < splits; k += 64) {
+      const float v0 = __ldg(p + (int64_t)k * total), v1 = __ldg(p + (int64_t)(k + 8) * total),
+                  v2 = __ldg(p + (int64_t)(k + 16) * total), v3 = __ldg(p + (int64_t)(k + 24) * total),
+                  v4 = __ldg(p + (int64_t)(k + 32) * total), v5 = __ldg(p + (int64_t)(k + 40) * total),
+                  v6 = __ldg(p + (int64_t)(k + 48) * total), v7 = __ldg(p + (int64_t)(k + 56) * total);
+      a0 += (Acc)v0; a1 += (Acc)v1; a2 += (Acc)v2; a3 += (Acc)v3;
+      a0 += (Acc)v4; a1 += (Acc)v5; a2 += (Acc)v6; a3 += (Acc)v7;
+    }
     for (; k + 24 < splits; k += 32) {
       const float v0 = __ldg(p + (int64_t)k * total), v1 = __ldg(p + (int64_t)(k + 8) * total),
                   v2 = __ldg(p + (int64_t)(k + 16) * total), v3 = __ldg(p + (int64_t)(k + 24) * total);
@@ -380,8 +390,9 @@ static void wgrad_reduce_go(const float* part, int splits, int taps, int cin, in
   cfg.gridDim = dim3((unsigned)(nred + ndb)); cfg.blockDim = dim3(32, 8); cfg.dynamicSmemBytes = 0; cfg.stream = st;
   cudaLaunchAttribute at[1];
   cfg.attrs = at; cfg.numAttrs = pdl_attr(&at[0]);
+  const int ilp8 = getenv("SRCGAN_B200_REDUCE_ILP4") ? 0 : 1;          // A/B switch: four loads in flight per thread as before
   (void)cudaLaunchKernelEx(&cfg, wgrad_reduce_k<DBL>, part, splits, taps, cin, cout, split, d0, ld0, ci00, d1, ld1, ci01, accumulate,
-                           alpha, dbpart, db0, db1, nred);
+                           alpha, dbpart, db0, db1, nred, ilp8);
 }
 
 // db[c] (+)= sum_m G[m][c] : stage 1 partial column sums, stage 2 fixed-order reduce
