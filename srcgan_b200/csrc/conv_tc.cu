@@ -3352,7 +3352,8 @@ conv3x3_wgrad_r32_tc(const __grid_constant__ CUtensorMap tmap_x, const __grid_co
     if (elect_one()) umma_commit(done_bar);
     __syncwarp();
   } else {
-    // ---- dY producer: thread -> up to five fixed (slab pixel, 16-byte chunk) slots of every tile
+    // ---- LSU variant only: dY producer, thread -> up to five fixed (slab pixel, 16-byte chunk) slots of every tile
+    // (with dY on TMA these warps go straight to the epilogue wait)
     const int tid = threadIdx.x - 64;
     uint32_t dst_off[R32_PER_THREAD], src_off[R32_PER_THREAD];
     int pr[R32_PER_THREAD], pj[R32_PER_THREAD];
@@ -3364,7 +3365,6 @@ conv3x3_wgrad_r32_tc(const __grid_constant__ CUtensorMap tmap_x, const __grid_co
       pj[i] = idx - pr[i] * WS_G_W;
       dst_off[i] = (uint32_t)(idx * 64 + ((ch ^ ((idx >> 1) & 3)) << 4));            // SWIZZLE_64B (slab 1024-byte aligned)
       src_off[i] = (uint32_t)(((pr[i] * a.wo + pj[i]) * g_ld + ch * 8) * 2);
-      if (id >= R32_CHUNKS) pr[i] = 1 << 20;                            // never inside the image
     }
     const char* gbase = reinterpret_cast<const char*>(g);
     int stage = 0, sig = 0, pend = 0;
